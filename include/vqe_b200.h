@@ -1,0 +1,132 @@
+/*
+ * vqe_b200.h -- C ABI of the B200-native VQE energy-and-gradient engine.
+ *
+ * Drop-in boundary for the hot path of OpenVQE (`openvqe.ucc_family`, `openvqe.adapt`).
+ * The reference has no FFI layer of its own: its hot path is Python calling myQLM's
+ * state-vector simulator and scipy.sparse.  Each entry point below names the reference
+ * code whose arithmetic it replaces (paths relative to the reference root).  The Python
+ * mirror of the reference interface (`openvqe_b200/ucc_family`, `openvqe_b200/adapt`)
+ * binds these symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - State: complex128, interleaved (re, im), 16 bytes per amplitude, 2^n amplitudes,
+ *     resident in HBM and owned by the library.  Caller owns every host array.
+ *   - Basis index: reference qubit q is index bit (n-1-q)  (myQLM: qubit 0 = MSB).
+ *   - A Pauli string is (xmask, zmask, ny) IN INDEX-BIT SPACE: bit b of xmask is set when
+ *     the letter on qubit n-1-b is X or Y, bit b of zmask when it is Y or Z, ny = number
+ *     of Y letters.   P|i> = i^ny (-1)^popcount(i & zmask) |i ^ xmask>.
+ *   - Every function returns VQE_OK (0) or a negative error code; vqe_last_error() returns
+ *     a thread-local message.  One host thread per context; one CUDA stream per context.
+ *   - There is no CPU fallback: without a CUDA device vqe_create fails.
+ */
+#ifndef VQE_B200_H
+#define VQE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQE_OK 0
+#define VQE_ERR_INVALID (-1)
+#define VQE_ERR_CUDA (-2)
+#define VQE_ERR_NOMEM (-3)
+
+typedef struct vqe_ctx vqe_ctx;
+typedef struct vqe_paulisum vqe_paulisum; /* device-resident, X-mask-grouped Pauli sum */
+
+/* gate kinds for vqe_apply_gates (myQLM conventions: RX(t)=exp(-itX/2), RY(t)=exp(-itY/2),
+ * RZ(t)=diag(e^{-it/2}, e^{it/2}), CNOT(control=q0, target=q1)) */
+enum { VQE_GATE_X = 0, VQE_GATE_H = 1, VQE_GATE_RX = 2, VQE_GATE_RY = 3, VQE_GATE_RZ = 4, VQE_GATE_CNOT = 5 };
+
+/* state buffers inside a context */
+enum { VQE_BUF_PSI = 0, VQE_BUF_SIGMA = 1, VQE_BUF_WORK = 2 };
+
+const char* vqe_last_error(void);
+int vqe_version(void);
+int vqe_device_count(void);
+
+/* Context = one state vector of n_qubits on one device.
+ * Replaces: the myQLM `Program`/`qalloc`/`get_default_qpu()` set-up at
+ * openvqe/ucc_family/get_energy_ucc.py:38-40. */
+int vqe_create(vqe_ctx** out, int n_qubits, int device);
+void vqe_destroy(vqe_ctx* ctx);
+int vqe_n_qubits(const vqe_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py `gpu_launches`) */
+uint64_t vqe_launch_count(const vqe_ctx* ctx);
+/* cumulative device time (ms) of the named kernel class since the last reset, measured with CUDA
+ * events on the context's stream when profiling is enabled (bench.py roofline leg).
+ * which: 0 = state-preparation tile kernel, 1 = expectation kernel, 2 = pauli-sum apply, 3 = pool sweep */
+int vqe_profile_enable(vqe_ctx* ctx, int on);
+int vqe_profile_read(vqe_ctx* ctx, int which, double* ms_total, uint64_t* launches, int reset);
+
+/* |psi> = |index>.  Replaces the X-gate Hartree-Fock preparation
+ * (openvqe/adapt/fermionic_adapt_vqe.py:183-213, get_energy_qucc.py:40-45). */
+int vqe_set_basis_state(vqe_ctx* ctx, uint64_t index);
+/* host <-> device copies of a whole buffer (interleaved re,im; 2*2^n doubles).
+ * get replaces get_statevector (fermionic_adapt_vqe.py:309-328). */
+int vqe_set_state(vqe_ctx* ctx, int buf, const double* re_im);
+int vqe_get_state(vqe_ctx* ctx, int buf, double* re_im);
+int vqe_copy_buffer(vqe_ctx* ctx, int dst_buf, int src_buf);
+
+/* Ordered product  psi <- prod_k exp(-i angle_k P_k) psi  (k = 0 applied first).
+ * Replaces build_ucc_ansatz + CLinalg gate-by-gate simulation
+ * (get_energy_ucc.py:42-48; fermionic_adapt_vqe.py:126-162; qubit_adapt_vqe.py:271-307) and,
+ * for single-string generators, the sparse expm at qubit_adapt_vqe.py:44-55. */
+int vqe_apply_pauli_rotations(vqe_ctx* ctx, int n_rot, const uint64_t* xmask, const uint64_t* zmask,
+                              const int32_t* ny, const double* angle);
+
+/* Gate-level circuit (reference qubit numbering, qubit 0 = MSB).  q1 is used by CNOT only.
+ * Replaces the QUCCSD excitation circuits of openvqe/common_files/circuit.py:13-106 as
+ * executed at get_energy_qucc.py:50-55. */
+int vqe_apply_gates(vqe_ctx* ctx, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
+                    const double* angle);
+
+/* Device-resident Pauli sum  O = sum_k (cre_k + i cim_k) P_k, grouped by X-mask at creation.
+ * Replaces the `observable=hamiltonian_sp` argument of the OBS job (get_energy_ucc.py:47) and the
+ * 2^n x 2^n scipy matrices hamiltonian_sparse / cluster_ops_sparse (fermionic_adapt_vqe.py:77-122). */
+int vqe_paulisum_create(vqe_ctx* ctx, vqe_paulisum** out, int n_terms, const uint64_t* xmask,
+                        const uint64_t* zmask, const int32_t* ny, const double* cre, const double* cim);
+void vqe_paulisum_destroy(vqe_paulisum* ps);
+int vqe_paulisum_groups(const vqe_paulisum* ps); /* number of distinct X-masks */
+int vqe_paulisum_passes(const vqe_paulisum* ps); /* number of state sweeps one evaluation makes */
+
+/* out[0] + i out[1] = <buf| O |buf>.  Replaces qpu.submit(OBS job).value (get_energy_ucc.py:48). */
+int vqe_expectation(vqe_ctx* ctx, int buf, const vqe_paulisum* ps, double* out_re_im);
+
+/* dst <- O src   (dst != src).  Replaces sig = hamiltonian_sparse.dot(curr_state)
+ * (fermionic_adapt_vqe.py:114). */
+int vqe_apply_paulisum(vqe_ctx* ctx, int dst_buf, int src_buf, const vqe_paulisum* ps);
+
+/* Pool sweep: for every operator k of the pool (terms op_offsets[k] .. op_offsets[k+1]-1)
+ *   out[2k] + i out[2k+1] = <bra_buf| A_k |ket_buf>.
+ * The caller forms 2*Re (fermionic ADAPT, fermionic_adapt_vqe.py:67-73) or 2*|.| (qubit ADAPT,
+ * qubit_adapt_vqe.py:145-149).  The whole pool is evaluated in one batched sweep. */
+int vqe_pool_overlaps(vqe_ctx* ctx, int bra_buf, int ket_buf, int n_ops, const int32_t* op_offsets,
+                      const uint64_t* xmask, const uint64_t* zmask, const int32_t* ny, const double* cre,
+                      const double* cim, double* out);
+
+/* psi <- exp(theta * A) psi for A = sum_k c_k P_k anti-Hermitian (exact exponential of the whole
+ * generator).  Replaces scipy.sparse.linalg.expm_multiply (fermionic_adapt_vqe.py:35-38).
+ * Commuting strings collapse to rotations; otherwise a scaled Taylor series on the device. */
+int vqe_apply_exp_paulisum(vqe_ctx* ctx, int n_terms, const uint64_t* xmask, const uint64_t* zmask,
+                           const int32_t* ny, const double* cre, const double* cim, double theta);
+
+/* out[0] + i out[1] = <vec|buf> with vec a host vector (fun_fidelity, fermionic_adapt_vqe.py:331-361) */
+int vqe_overlap_host(vqe_ctx* ctx, int buf, const double* vec_re_im, double* out_re_im);
+/* out = <buf|buf> */
+int vqe_norm2(vqe_ctx* ctx, int buf, double* out);
+/* out[0] + i out[1] = <a|b> for two device buffers */
+int vqe_inner(vqe_ctx* ctx, int a_buf, int b_buf, double* out_re_im);
+
+/* Raw device pointer / stream of a buffer (for the multi-GPU exchange layer, which wraps the
+ * shard in a torch tensor for torch.distributed). */
+int vqe_buffer_ptr(vqe_ctx* ctx, int buf, void** dev_ptr, uint64_t* n_amplitudes);
+int vqe_synchronize(vqe_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQE_B200_H */

@@ -1,0 +1,163 @@
+"""Shared GPU implementations behind the reference-shaped entry points.
+
+Every function here replaces the *body* of a reference hot-path function with
+calls into the CUDA engine; the reference-shaped wrappers live in
+``openvqe_b200/ucc_family`` and ``openvqe_b200/adapt``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .common_files.circuit import quccsd_circuit
+from .engine import BUF_PSI, BUF_SIGMA, GATE_KINDS, get_engine
+from .lowering import PackedTerms, pack_operator, pack_pool
+
+_PACK_CACHE = {}
+_PACK_CACHE_MAX = 16384
+
+
+def packed(op) -> PackedTerms:
+    """Lowered form of one operator, cached per object (the same generator objects
+    are passed on every one of the thousands of objective evaluations)."""
+    key = id(op)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] is op:
+        return hit[1]
+    p = pack_operator(op)
+    if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (op, p)  # strong ref: the id cannot be recycled while cached
+    return p
+
+
+class RotationProgram:
+    """Concatenated Pauli strings of an ordered generator list: rotation k has
+    angle theta[owner[k]] * creal[k]."""
+
+    __slots__ = ("x", "z", "ny", "creal", "owner", "n_ops")
+
+    def __init__(self, ops):
+        xs, zs, nys, cr, own = [], [], [], [], []
+        for j, op in enumerate(ops):
+            p = packed(op)
+            keep = (p.cre != 0) | (p.cim != 0)  # zero strings are exact identities
+            xs.append(p.x[keep])
+            zs.append(p.z[keep])
+            nys.append(p.ny[keep])
+            cr.append(p.cre[keep])
+            own.append(np.full(int(keep.sum()), j, dtype=np.int64))
+        cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dt)
+        self.x, self.z = cat(xs, np.uint64), cat(zs, np.uint64)
+        self.ny, self.creal = cat(nys, np.int32), cat(cr, np.float64)
+        self.owner = cat(own, np.int64)
+        self.n_ops = len(ops)
+
+
+_PROG_CACHE = {}
+
+
+def rotation_program(ops) -> RotationProgram:
+    key = tuple(id(o) for o in ops)
+    hit = _PROG_CACHE.get(key)
+    if hit is not None and all(a is b for a, b in zip(hit[0], ops)):
+        return hit[1]
+    prog = RotationProgram(ops)
+    if len(_PROG_CACHE) >= 256:
+        _PROG_CACHE.clear()
+    _PROG_CACHE[key] = (list(ops), prog)
+    return prog
+
+
+def prepare_ucc_state(engine, cluster_ops_sp, hf_init_sp, theta):
+    """|psi> = prod_j prod_k exp(-i theta_j Re(c_jk) P_jk) |HF> on the device.
+    Replaces reference get_energy_ucc.py:42-46.  ``zip`` truncation: only the first
+    min(len(ops), len(theta)) generators are applied; with no generator at all the
+    reference never applies the HF X gates (``init`` is only passed for n_term == 0)."""
+    m = min(len(cluster_ops_sp), len(theta))
+    if m == 0:
+        engine.set_basis_state(0)
+        return
+    ops = list(cluster_ops_sp[:m])
+    prog = rotation_program(ops)
+    th = np.asarray(theta, dtype=np.float64)[:m]
+    angles = th[prog.owner] * prog.creal
+    engine.set_basis_state(int(hf_init_sp))
+    engine.apply_rotations(prog.x, prog.z, prog.ny, angles)
+
+
+def ucc_energy(theta, hamiltonian_sp, cluster_ops_sp, hf_init_sp, device=0):
+    """E(theta) of the Trotterised UCC ansatz (reference get_energy_ucc.py:8-50)."""
+    engine = get_engine(hamiltonian_sp.nbqbits, device)
+    prepare_ucc_state(engine, cluster_ops_sp, hf_init_sp, theta)
+    return float(engine.expectation(engine.paulisum(hamiltonian_sp)).real)
+
+
+def apply_gate_list(engine, gates):
+    kinds = [GATE_KINDS[g[0]] for g in gates]
+    q0 = [g[1][0] for g in gates]
+    q1 = [g[1][1] if len(g[1]) > 1 else 0 for g in gates]
+    ang = [0.0 if g[2] is None else g[2] for g in gates]
+    engine.apply_gates(kinds, q0, q1, ang)
+
+
+def quccsd_energy(theta, hamiltonian_sp, cluster_ops, hf_init_sp, device=0):
+    """E(theta) of the gate-defined QUCCSD ansatz (reference get_energy_qucc.py:11-56)."""
+    n = hamiltonian_sp.nbqbits
+    engine = get_engine(n, device)
+    circ = quccsd_circuit(n, hf_init_sp, cluster_ops, theta)
+    engine.set_basis_state(0)
+    apply_gate_list(engine, circ.gates)
+    return float(engine.expectation(engine.paulisum(hamiltonian_sp)).real)
+
+
+def basis_energy(hamiltonian_sp, hf_init_sp, device=0):
+    """<HF|H|HF> (reference hf_energy, fermionic_adapt_vqe.py:216-238)."""
+    engine = get_engine(hamiltonian_sp.nbqbits, device)
+    engine.set_basis_state(int(hf_init_sp))
+    return float(engine.expectation(engine.paulisum(hamiltonian_sp)).real)
+
+
+def load_reference_ket(engine, reference_ket):
+    """Accept the reference's 2^n x 1 scipy-sparse / dense column or a flat vector."""
+    if hasattr(reference_ket, "toarray"):
+        reference_ket = reference_ket.toarray()
+    engine.set_state(np.asarray(reference_ket, dtype=np.complex128).reshape(-1))
+
+
+def pool_overlaps(engine, hamiltonian_sp, pool_ops):
+    """sigma = H psi once, then <sigma|A_k|psi> for the whole pool in one sweep
+    (reference fermionic_adapt_vqe.py:114-121 / qubit_adapt_vqe.py:462-472)."""
+    engine.apply_paulisum(engine.paulisum(hamiltonian_sp), dst=BUF_SIGMA, src=BUF_PSI)
+    key = ("pool",) + tuple(id(o) for o in pool_ops)
+    hit = _PROG_CACHE.get(key)
+    if hit is not None and all(a is b for a, b in zip(hit[0], pool_ops)):
+        pool = hit[1]
+    else:
+        pool = pack_pool(pool_ops)
+        if len(_PROG_CACHE) >= 256:
+            _PROG_CACHE.clear()
+        _PROG_CACHE[key] = (list(pool_ops), pool)
+    return engine.pool_overlaps(pool, bra=BUF_SIGMA, ket=BUF_PSI)
+
+
+def snap_ties(values, rel=1e-12):
+    """Gradients that are equal in exact arithmetic (spin-complement partners carry
+    +-g) may differ in the last bits after a parallel
+    reduction.  The reference's selection uses float equality with ties resolved to
+    the lowest pool index, so magnitudes within ``rel`` of each other are snapped to
+    the value of their lowest-index member before selection.  Signs are kept."""
+    vals = list(values)
+    order = sorted(range(len(vals)), key=lambda k: -abs(vals[k]))
+    i = 0
+    while i < len(order):
+        j = i + 1
+        top = abs(vals[order[i]])
+        while j < len(order) and top - abs(vals[order[j]]) <= rel * top and top > 0:
+            j += 1
+        if j - i > 1:
+            members = sorted(order[i:j])
+            mag = abs(vals[members[0]])
+            for k in members:
+                vals[k] = mag if vals[k] >= 0 else -mag
+        i = j
+    return vals

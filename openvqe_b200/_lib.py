@@ -1,0 +1,86 @@
+"""ctypes binding of the C ABI declared in include/vqe_b200.h.
+
+The shared library is built in-tree (``openvqe_b200/csrc/build.sh`` or
+``__graft_entry__.build()``).  If it is missing, or no CUDA device is present,
+every numeric call raises: there is deliberately no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libvqe_b200.so")
+
+# every symbol include/vqe_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "vqe_last_error", "vqe_version", "vqe_device_count", "vqe_create", "vqe_destroy", "vqe_n_qubits",
+    "vqe_launch_count", "vqe_profile_enable", "vqe_profile_read", "vqe_set_basis_state", "vqe_set_state",
+    "vqe_get_state", "vqe_copy_buffer", "vqe_apply_pauli_rotations", "vqe_apply_gates",
+    "vqe_paulisum_create", "vqe_paulisum_destroy", "vqe_paulisum_groups", "vqe_paulisum_passes",
+    "vqe_expectation", "vqe_apply_paulisum", "vqe_pool_overlaps", "vqe_apply_exp_paulisum",
+    "vqe_overlap_host", "vqe_norm2", "vqe_inner", "vqe_buffer_ptr", "vqe_synchronize",
+]
+
+
+class VQEError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises VQEError if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VQEError(
+            "CUDA extension %s not found: build it with openvqe_b200/csrc/build.sh "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, i32, dbl = C.c_void_p, C.c_uint64, C.c_int32, C.c_double
+    P = C.POINTER
+    sig = {
+        "vqe_last_error": (C.c_char_p, []),
+        "vqe_version": (C.c_int, []),
+        "vqe_device_count": (C.c_int, []),
+        "vqe_create": (C.c_int, [P(vp), C.c_int, C.c_int]),
+        "vqe_destroy": (None, [vp]),
+        "vqe_n_qubits": (C.c_int, [vp]),
+        "vqe_launch_count": (u64, [vp]),
+        "vqe_profile_enable": (C.c_int, [vp, C.c_int]),
+        "vqe_profile_read": (C.c_int, [vp, C.c_int, P(dbl), P(u64), C.c_int]),
+        "vqe_set_basis_state": (C.c_int, [vp, u64]),
+        "vqe_set_state": (C.c_int, [vp, C.c_int, vp]),
+        "vqe_get_state": (C.c_int, [vp, C.c_int, vp]),
+        "vqe_copy_buffer": (C.c_int, [vp, C.c_int, C.c_int]),
+        "vqe_apply_pauli_rotations": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
+        "vqe_apply_gates": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
+        "vqe_paulisum_create": (C.c_int, [vp, P(vp), C.c_int, vp, vp, vp, vp, vp]),
+        "vqe_paulisum_destroy": (None, [vp]),
+        "vqe_paulisum_groups": (C.c_int, [vp]),
+        "vqe_paulisum_passes": (C.c_int, [vp]),
+        "vqe_expectation": (C.c_int, [vp, C.c_int, vp, P(dbl)]),
+        "vqe_apply_paulisum": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "vqe_pool_overlaps": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+        "vqe_apply_exp_paulisum": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, dbl]),
+        "vqe_overlap_host": (C.c_int, [vp, C.c_int, vp, P(dbl)]),
+        "vqe_norm2": (C.c_int, [vp, C.c_int, P(dbl)]),
+        "vqe_inner": (C.c_int, [vp, C.c_int, C.c_int, P(dbl)]),
+        "vqe_buffer_ptr": (C.c_int, [vp, C.c_int, P(vp), P(u64)]),
+        "vqe_synchronize": (C.c_int, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().vqe_last_error()
+        raise VQEError("vqe_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))

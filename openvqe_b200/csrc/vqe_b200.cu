@@ -1,0 +1,1635 @@
+// vqe_b200.cu -- B200-native (sm_100a) state-vector engine for the OpenVQE hot path.
+//
+// Everything here is HBM-bound complex128 streaming work (0.2 flop/byte): no tensor cores.
+// Design:
+//   * The state lives in HBM as interleaved complex128.  Every kernel works on TILES: a tile is
+//     the set of 2^T amplitudes obtained by fixing all index bits outside a chosen set of T
+//     "tile bits".  The low L tile bits are always index bits 0..L-1, so a tile is a gather of
+//     2^(T-L) contiguous 16*2^L-byte segments (coalesced 16-byte loads, 512 B per warp request).
+//   * A CTA stages one tile in shared memory, applies EVERY consecutive operation whose X-mask
+//     lies inside the tile bits (Z-masks may touch any bit: bits outside the tile only contribute
+//     a per-tile sign), and writes the tile back: r rotations per HBM pass instead of one.
+//     Consecutive rotations with the same X-mask act on the same amplitude pairs and are applied
+//     in registers without touching shared memory again (8 Pauli strings of a JW double
+//     excitation -> one sweep).
+//   * <psi|H|psi>, H|psi> and the ADAPT pool sweep use the same tiles: H is grouped by X-mask,
+//     the groups are packed into passes by covering their X-masks with tile-bit sets, and all
+//     Z-variants of a group are accumulated in registers with popcount signs.  Reductions are
+//     fp64 warp-shuffle + block + fixed-order final pass (bit-reproducible run to run).
+//   * Persistent grids sized from the SM count; one stream per context.
+//
+// No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "vqe_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(VQE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),      \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+extern "C" const char* vqe_last_error(void) { return g_err.c_str(); }
+extern "C" int vqe_version(void) { return 100; }
+extern "C" int vqe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// device structures
+// ------------------------------------------------------------------------------------------
+enum { OP_ROT = 0, OP_GATE1 = 1, OP_CNOT = 2 };
+
+struct DevOp {       // 64 bytes
+    uint32_t lx;     // ROT: local X mask | GATE1: local bit mask | CNOT: local target mask
+    uint32_t lz;     // ROT: local Z mask | CNOT: local control mask (0 if control is outside the tile)
+    uint64_t zout;   // ROT: Z mask outside the tile | CNOT: control mask outside the tile
+    double c, s;     // ROT: cos, sin
+    uint32_t k4;     // ROT: (ny + 3) & 3, the unit phase (-i) * i^ny = i^k4
+    uint32_t pad2;
+    uint32_t kind;   // OP_*
+    uint32_t hb;     // highest set bit of lx
+    uint32_t run;    // ROT: number of consecutive ROT ops (starting here) sharing lx
+    uint32_t mat;    // GATE1: index into the matrix array (8 doubles each)
+    uint32_t nyodd;  // ROT: ny & 1
+    uint32_t pad;
+};
+
+struct TileGeom {
+    uint64_t comp_mask;  // index bits NOT in the tile
+    uint64_t n_tiles;    // 2^(n - T)
+    const uint64_t* scat;  // 2^(T-L) entries: deposit of the high local bits into index space
+    uint32_t tbits, lbits;
+};
+
+struct DevGroup {     // one X-mask group of a Pauli sum inside a pass
+    uint32_t lx, hb;
+    uint32_t t_begin;  // first term (index into the pass-local term list)
+    uint32_t n_even;   // terms with even ny come first, then n_odd terms with odd ny
+    uint32_t n_odd;
+    uint32_t pad;
+};
+struct DevTerm {      // 32 bytes
+    uint64_t zout;
+    uint32_t lz;
+    uint32_t pad;
+    double ar, ai;    // expectation: pair weight; apply: c_k * i^ny
+};
+
+__device__ __forceinline__ uint64_t pdep64(uint64_t v, uint64_t mask) {
+    uint64_t out = 0;
+    while (mask) {
+        uint64_t low = mask & (0 - mask);
+        if (v & 1) out |= low;
+        v >>= 1;
+        mask ^= low;
+    }
+    return out;
+}
+
+__device__ __forceinline__ uint32_t insert0(uint32_t p, uint32_t bit) {
+    return ((p >> bit) << (bit + 1)) | (p & ((1u << bit) - 1u));
+}
+
+__device__ __forceinline__ double2 ld_amp(const double2* p) { return *p; }
+
+__device__ __forceinline__ double flipsign(double v, uint32_t par) {
+    return __longlong_as_double(__double_as_longlong(v) ^ ((long long)(par & 1u) << 63));
+}
+
+// ------------------------------------------------------------------------------------------
+// simple kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_zero_set(double2* psi, uint64_t n_amp, uint64_t index) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n_amp; i += stride) psi[i] = make_double2(i == index ? 1.0 : 0.0, 0.0);
+}
+
+// dst = alpha * x + beta * dst   (complex alpha, beta given as re/im)
+__global__ void k_axpby(double2* dst, const double2* x, uint64_t n_amp, double are, double aim, double bre,
+                        double bim) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n_amp; i += stride) {
+        double2 d = dst[i], v = x[i];
+        double2 o;
+        o.x = are * v.x - aim * v.y + bre * d.x - bim * d.y;
+        o.y = are * v.y + aim * v.x + bre * d.y + bim * d.x;
+        dst[i] = o;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of (re, im); result valid in thread 0.  red must hold 2*32 doubles.
+__device__ __forceinline__ double2 block_sum2(double re, double im, double* red) {
+    re = warp_sum(re);
+    im = warp_sum(im);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) {
+        red[2 * w] = re;
+        red[2 * w + 1] = im;
+    }
+    __syncthreads();
+    double2 out = make_double2(0.0, 0.0);
+    if (threadIdx.x == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        for (int i = 0; i < nw; ++i) {  // fixed order
+            out.x += red[2 * i];
+            out.y += red[2 * i + 1];
+        }
+    }
+    return out;
+}
+
+// partial[b] = sum_i conj(a[i]) * b[i] over this block's grid-stride share
+__global__ void k_inner(const double2* a, const double2* b, uint64_t n_amp, double2* partial) {
+    __shared__ double red[64];
+    double re = 0.0, im = 0.0;
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n_amp; i += stride) {
+        double2 u = a[i], v = b[i];
+        re += u.x * v.x + u.y * v.y;
+        im += u.x * v.y - u.y * v.x;
+    }
+    double2 s = block_sum2(re, im, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// out[j] = sum_b partial[b * stride + j], fixed order (one thread per j)
+__global__ void k_reduce_partials(const double2* partial, int n_blocks, int stride, int n_out, double2* out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    double re = 0.0, im = 0.0;
+    for (int b = 0; b < n_blocks; ++b) {
+        double2 p = partial[(size_t)b * stride + j];
+        re += p.x;
+        im += p.y;
+    }
+    out[j] = make_double2(re, im);
+}
+
+// ------------------------------------------------------------------------------------------
+// tile load / store
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_load(double2* tile, const double2* __restrict__ src, const TileGeom& g,
+                                          uint64_t base) {
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t lmask = (1u << g.lbits) - 1u;
+#pragma unroll 4
+    for (uint32_t k = threadIdx.x; k < ts; k += blockDim.x) {
+        uint64_t gi = base | __ldg(g.scat + (k >> g.lbits)) | (uint64_t)(k & lmask);
+        tile[k] = ld_amp(src + gi);
+    }
+}
+__device__ __forceinline__ void tile_store(const double2* tile, double2* __restrict__ dst, const TileGeom& g,
+                                           uint64_t base) {
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t lmask = (1u << g.lbits) - 1u;
+#pragma unroll 4
+    for (uint32_t k = threadIdx.x; k < ts; k += blockDim.x) {
+        uint64_t gi = base | __ldg(g.scat + (k >> g.lbits)) | (uint64_t)(k & lmask);
+        dst[gi] = tile[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// state preparation: fused rotations / gates on a shared-memory tile
+// ------------------------------------------------------------------------------------------
+#define ROT_PAIRS 4
+
+__device__ __forceinline__ void rot_update(double2& a, double2& b, const DevOp& op, uint32_t pa) {
+    // P psi at l  = i^ny (-1)^pb b ;  at l2 = i^ny (-1)^pa a ;  new = c*old - i s (P psi)
+    //             = c*old + s (-1)^p i^k4 other,  k4 = (ny + 3) & 3
+    const uint32_t neg = op.k4 >> 1;
+    const double sb = flipsign(op.s, pa ^ op.nyodd ^ neg), sa = flipsign(op.s, pa ^ neg);
+    double tbr, tbi, tar, tai;
+    if (op.k4 & 1u) {  // multiply by i
+        tbr = -b.y; tbi = b.x; tar = -a.y; tai = a.x;
+    } else {
+        tbr = b.x; tbi = b.y; tar = a.x; tai = a.y;
+    }
+    double2 na, nb;
+    na.x = op.c * a.x + sb * tbr;
+    na.y = op.c * a.y + sb * tbi;
+    nb.x = op.c * b.x + sa * tar;
+    nb.y = op.c * b.y + sa * tai;
+    a = na;
+    b = nb;
+}
+
+__global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, TileGeom g,
+                                                  const DevOp* __restrict__ ops, int n_ops,
+                                                  const double* __restrict__ mats) {
+    extern __shared__ double2 tile[];
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t half = ts >> 1;
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = pdep64(t, g.comp_mask);
+        tile_load(tile, psi, g, base);
+        int i = 0;
+        while (i < n_ops) {
+            __syncthreads();
+            const DevOp op = ops[i];
+            if (op.kind == OP_ROT) {
+                const int run = (int)op.run;
+                if (op.lx == 0) {
+                    // diagonal run: psi[l] *= prod_r (c_r - i s_r (-1)^par_r)
+                    for (uint32_t l0 = threadIdx.x; l0 < ts; l0 += blockDim.x * ROT_PAIRS) {
+                        double2 a[ROT_PAIRS];
+#pragma unroll
+                        for (int j = 0; j < ROT_PAIRS; ++j) {
+                            const uint32_t l = l0 + j * blockDim.x;
+                            if (l < ts) a[j] = tile[l];
+                        }
+                        for (int r = 0; r < run; ++r) {
+                            const DevOp o2 = ops[i + r];
+                            const uint32_t opar = __popcll(base & o2.zout);
+#pragma unroll
+                            for (int j = 0; j < ROT_PAIRS; ++j) {
+                                const uint32_t l = l0 + j * blockDim.x;
+                                const double ss = flipsign(o2.s, __popc(l & o2.lz) + opar);
+                                double2 na;
+                                na.x = o2.c * a[j].x + ss * a[j].y;
+                                na.y = o2.c * a[j].y - ss * a[j].x;
+                                a[j] = na;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < ROT_PAIRS; ++j) {
+                            const uint32_t l = l0 + j * blockDim.x;
+                            if (l < ts) tile[l] = a[j];
+                        }
+                    }
+                } else {
+                    // the pairs (l, l^lx) are invariant under every rotation of the run: keep them
+                    // in registers and apply the whole run without touching shared memory again
+                    for (uint32_t p0 = threadIdx.x; p0 < half; p0 += blockDim.x * ROT_PAIRS) {
+                        double2 a[ROT_PAIRS], b[ROT_PAIRS];
+                        uint32_t li[ROT_PAIRS];
+#pragma unroll
+                        for (int j = 0; j < ROT_PAIRS; ++j) {
+                            const uint32_t p = p0 + j * blockDim.x;
+                            li[j] = insert0(p, op.hb);
+                            if (p < half) {
+                                a[j] = tile[li[j]];
+                                b[j] = tile[li[j] ^ op.lx];
+                            }
+                        }
+                        for (int r = 0; r < run; ++r) {
+                            const DevOp o2 = ops[i + r];
+                            const uint32_t opar = __popcll(base & o2.zout);
+#pragma unroll
+                            for (int j = 0; j < ROT_PAIRS; ++j)
+                                rot_update(a[j], b[j], o2, (__popc(li[j] & o2.lz) + opar) & 1u);
+                        }
+#pragma unroll
+                        for (int j = 0; j < ROT_PAIRS; ++j) {
+                            const uint32_t p = p0 + j * blockDim.x;
+                            if (p < half) {
+                                tile[li[j]] = a[j];
+                                tile[li[j] ^ op.lx] = b[j];
+                            }
+                        }
+                    }
+                }
+                i += run;
+            } else if (op.kind == OP_GATE1) {
+                const double* m = mats + (size_t)op.mat * 8;
+                const double m00r = m[0], m00i = m[1], m01r = m[2], m01i = m[3];
+                const double m10r = m[4], m10i = m[5], m11r = m[6], m11i = m[7];
+                for (uint32_t p = threadIdx.x; p < half; p += blockDim.x) {
+                    const uint32_t l = insert0(p, op.hb), l2 = l | op.lx;
+                    double2 a = tile[l], b = tile[l2], na, nb;
+                    na.x = m00r * a.x - m00i * a.y + m01r * b.x - m01i * b.y;
+                    na.y = m00r * a.y + m00i * a.x + m01r * b.y + m01i * b.x;
+                    nb.x = m10r * a.x - m10i * a.y + m11r * b.x - m11i * b.y;
+                    nb.y = m10r * a.y + m10i * a.x + m11r * b.y + m11i * b.x;
+                    tile[l] = na;
+                    tile[l2] = nb;
+                }
+                i += 1;
+            } else {  // OP_CNOT
+                const bool on = (op.zout == 0) || ((base & op.zout) != 0);
+                if (on) {
+                    for (uint32_t p = threadIdx.x; p < half; p += blockDim.x) {
+                        const uint32_t l = insert0(p, op.hb), l2 = l | op.lx;
+                        if (op.lz == 0 || (l & op.lz)) {
+                            double2 a = tile[l];
+                            tile[l] = tile[l2];
+                            tile[l2] = a;
+                        }
+                    }
+                }
+                i += 1;
+            }
+        }
+        __syncthreads();
+        tile_store(tile, psi, g, base);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// <psi| O |psi> for the X-mask groups of one pass.  grid = (tile workers, group chunks)
+// ------------------------------------------------------------------------------------------
+#define TERM_CAP 1024
+
+__global__ void __launch_bounds__(256, 3) k_tile_expect(const double2* __restrict__ psi, TileGeom g,
+                                                     const DevGroup* __restrict__ groups, int n_groups,
+                                                     const DevTerm* __restrict__ terms,
+                                                     double2* __restrict__ partial) {
+    extern __shared__ double2 tile[];
+    __shared__ double red[64];
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t half = ts >> 1;
+    // shared term cache lives after the tile
+    double2* s_coef = tile + ts;                         // TERM_CAP entries
+    uint32_t* s_lz = (uint32_t*)(s_coef + TERM_CAP);     // TERM_CAP entries
+    // group chunk of this CTA
+    const int per = (n_groups + gridDim.y - 1) / gridDim.y;
+    const int g0 = blockIdx.y * per, g1 = min(n_groups, g0 + per);
+    double er = 0.0, ei = 0.0;
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = pdep64(t, g.comp_mask);
+        __syncthreads();
+        tile_load(tile, psi, g, base);
+        int gi = g0;
+        while (gi < g1) {
+            // take as many whole groups as fit in the term cache
+            int ge = gi;
+            uint32_t nt = 0;
+            const uint32_t tb0 = groups[gi].t_begin;
+            while (ge < g1) {
+                uint32_t k = groups[ge].n_even + groups[ge].n_odd;
+                if (nt + k > TERM_CAP && ge > gi) break;
+                nt += k;
+                ++ge;
+            }
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < nt && k < TERM_CAP; k += blockDim.x) {
+                const DevTerm tm = terms[tb0 + k];
+                uint32_t par = __popcll(base & tm.zout) & 1u;
+                s_coef[k] = make_double2(flipsign(tm.ar, par), flipsign(tm.ai, par));
+                s_lz[k] = tm.lz;
+            }
+            __syncthreads();
+            for (int q = gi; q < ge; ++q) {
+                const DevGroup gr = groups[q];
+                const uint32_t off = gr.t_begin - tb0;
+                if (off + gr.n_even + gr.n_odd > TERM_CAP) continue;  // oversize single group: handled by host split
+                if (gr.lx == 0) {
+                    for (uint32_t l = threadIdx.x; l < ts; l += blockDim.x) {
+                        const double2 a = tile[l];
+                        const double w = a.x * a.x + a.y * a.y;
+                        double sr = 0.0, si = 0.0;
+                        for (uint32_t k = 0; k < gr.n_even; ++k) {
+                            uint32_t par = __popc(l & s_lz[off + k]);
+                            const double2 c = s_coef[off + k];
+                            sr += flipsign(c.x, par);
+                            si += flipsign(c.y, par);
+                        }
+                        er += w * sr;
+                        ei += w * si;
+                    }
+                } else {
+                    for (uint32_t p = threadIdx.x; p < half; p += blockDim.x) {
+                        const uint32_t l = insert0(p, gr.hb), l2 = l ^ gr.lx;
+                        const double2 a = tile[l], b = tile[l2];
+                        const double wr = 2.0 * (b.x * a.x + b.y * a.y);  // 2 Re(conj(b) a)
+                        const double wi = 2.0 * (b.x * a.y - b.y * a.x);  // 2 Im(conj(b) a)
+                        double sr = 0.0, si = 0.0, orr = 0.0, oi = 0.0;
+                        uint32_t k = off;
+                        for (uint32_t e = 0; e < gr.n_even; ++e, ++k) {
+                            uint32_t par = __popc(l & s_lz[k]);
+                            const double2 c = s_coef[k];
+                            sr += flipsign(c.x, par);
+                            si += flipsign(c.y, par);
+                        }
+                        for (uint32_t e = 0; e < gr.n_odd; ++e, ++k) {
+                            uint32_t par = __popc(l & s_lz[k]);
+                            const double2 c = s_coef[k];
+                            orr += flipsign(c.x, par);
+                            oi += flipsign(c.y, par);
+                        }
+                        er += wr * sr + wi * orr;
+                        ei += wr * si + wi * oi;
+                    }
+                }
+            }
+            gi = ge;
+        }
+    }
+    double2 s = block_sum2(er, ei, red);
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// dst (+)= O src for the groups of one pass.  One CTA per tile (persistent over tiles).
+// ------------------------------------------------------------------------------------------
+#define APPLY_PER_THREAD 16
+__global__ void __launch_bounds__(512) k_tile_apply(const double2* __restrict__ src, double2* __restrict__ dst,
+                                                    TileGeom g, const DevGroup* __restrict__ groups, int n_groups,
+                                                    const DevTerm* __restrict__ terms, int accumulate) {
+    extern __shared__ double2 tile[];
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t lmask = (1u << g.lbits) - 1u;
+    double2* s_coef = tile + ts;
+    uint32_t* s_lz = (uint32_t*)(s_coef + TERM_CAP);
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = pdep64(t, g.comp_mask);
+        __syncthreads();
+        tile_load(tile, src, g, base);
+        double2 acc[APPLY_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < APPLY_PER_THREAD; ++j) acc[j] = make_double2(0.0, 0.0);
+        int gi = 0;
+        while (gi < n_groups) {
+            int ge = gi;
+            uint32_t nt = 0;
+            const uint32_t tb0 = groups[gi].t_begin;
+            while (ge < n_groups) {
+                uint32_t k = groups[ge].n_even + groups[ge].n_odd;
+                if (nt + k > TERM_CAP && ge > gi) break;
+                nt += k;
+                ++ge;
+            }
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < nt && k < TERM_CAP; k += blockDim.x) {
+                const DevTerm tm = terms[tb0 + k];
+                uint32_t par = __popcll(base & tm.zout) & 1u;
+                s_coef[k] = make_double2(flipsign(tm.ar, par), flipsign(tm.ai, par));
+                s_lz[k] = tm.lz;
+            }
+            __syncthreads();
+            for (int q = gi; q < ge; ++q) {
+                const DevGroup gr = groups[q];
+                const uint32_t off = gr.t_begin - tb0;
+                const uint32_t nk = gr.n_even + gr.n_odd;
+                if (off + nk > TERM_CAP) continue;
+#pragma unroll
+                for (int j = 0; j < APPLY_PER_THREAD; ++j) {
+                    const uint32_t l = threadIdx.x + j * blockDim.x;
+                    if (l < ts) {
+                        const uint32_t sidx = l ^ gr.lx;
+                        double sr = 0.0, si = 0.0;
+                        for (uint32_t k = 0; k < nk; ++k) {
+                            uint32_t par = __popc(sidx & s_lz[off + k]);
+                            const double2 c = s_coef[off + k];
+                            sr += flipsign(c.x, par);
+                            si += flipsign(c.y, par);
+                        }
+                        const double2 v = tile[sidx];
+                        acc[j].x += sr * v.x - si * v.y;
+                        acc[j].y += sr * v.y + si * v.x;
+                    }
+                }
+            }
+            gi = ge;
+        }
+#pragma unroll
+        for (int j = 0; j < APPLY_PER_THREAD; ++j) {
+            const uint32_t l = threadIdx.x + j * blockDim.x;
+            if (l < ts) {
+                uint64_t gidx = base | __ldg(g.scat + (l >> g.lbits)) | (uint64_t)(l & lmask);
+                double2 o = acc[j];
+                if (accumulate) {
+                    double2 d = dst[gidx];
+                    o.x += d.x;
+                    o.y += d.y;
+                }
+                dst[gidx] = o;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ADAPT pool sweep: out_k = <bra| A_k |ket>, one warp per pool operator, whole pool per launch.
+// grid = (tile workers, operator chunks).  Both tiles are staged in shared memory.
+// ------------------------------------------------------------------------------------------
+struct DevPoolOp {
+    uint32_t t_begin, n_terms;  // terms of this operator (pass-local list)
+    uint32_t out_index;         // pool index
+    uint32_t pad;
+};
+struct DevPoolTerm {  // 32 bytes
+    uint64_t zout;
+    uint32_t lx, lz;
+    double ar, ai;    // c_k * i^ny
+};
+
+__global__ void __launch_bounds__(512) k_tile_pool(const double2* __restrict__ bra, const double2* __restrict__ ket,
+                                                   TileGeom g, const DevPoolOp* __restrict__ pops, int n_pops,
+                                                   const DevPoolTerm* __restrict__ terms,
+                                                   double2* __restrict__ partial /* [gridDim.x][n_pops] */) {
+    extern __shared__ double2 tile[];
+    const uint32_t ts = 1u << g.tbits;
+    double2* tbra = tile;
+    double2* tket = tile + ts;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int per = (n_pops + gridDim.y - 1) / gridDim.y;
+    const int o0 = blockIdx.y * per, o1 = min(n_pops, o0 + per);
+    const bool same = (bra == ket);
+    // zero this CTA's partial slots (accumulated over its tiles below)
+    for (int o = o0 + threadIdx.x; o < o1; o += blockDim.x)
+        partial[(size_t)blockIdx.x * n_pops + o] = make_double2(0.0, 0.0);
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = pdep64(t, g.comp_mask);
+        __syncthreads();
+        tile_load(tket, ket, g, base);
+        if (!same) tile_load(tbra, bra, g, base);
+        __syncthreads();
+        const double2* tb = same ? tket : tbra;
+        for (int o = o0 + warp; o < o1; o += nwarps) {
+            const DevPoolOp po = pops[o];
+            double re = 0.0, im = 0.0;
+            for (uint32_t k = 0; k < po.n_terms; ++k) {
+                const DevPoolTerm tm = terms[po.t_begin + k];
+                const uint32_t opar = __popcll(base & tm.zout) & 1u;
+                const double cr = flipsign(tm.ar, opar), ci = flipsign(tm.ai, opar);
+                double tr = 0.0, ti = 0.0;
+                for (uint32_t l = lane; l < ts; l += 32) {
+                    const uint32_t sidx = l ^ tm.lx;
+                    const uint32_t par = __popc(sidx & tm.lz);
+                    const double2 v = tket[sidx];
+                    const double2 b = tb[l];
+                    // conj(b) * v, signed
+                    tr += flipsign(b.x * v.x + b.y * v.y, par);
+                    ti += flipsign(b.x * v.y - b.y * v.x, par);
+                }
+                re += cr * tr - ci * ti;
+                im += cr * ti + ci * tr;
+            }
+            re = warp_sum(re);
+            im = warp_sum(im);
+            if (lane == 0) {
+                double2* slot = partial + (size_t)blockIdx.x * n_pops + o;
+                double2 cur = *slot;
+                cur.x += re;
+                cur.y += im;
+                *slot = cur;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct TilePlan {
+    uint64_t tile_mask = 0, comp_mask = 0, n_tiles = 1;
+    int tbits = 0, lbits = 0;
+    std::vector<int> bits;  // ascending
+    std::vector<uint64_t> scat;
+};
+
+static inline int popc64(uint64_t v) { return __builtin_popcountll(v); }
+
+static uint32_t pext_mask(uint64_t v, const TilePlan& tp) {
+    uint32_t out = 0;
+    for (int j = 0; j < tp.tbits; ++j)
+        if ((v >> tp.bits[j]) & 1ull) out |= 1u << j;
+    return out;
+}
+
+// finalize a plan from a set of required bits: add low bits first, then fill up to tbits
+static TilePlan make_plan(int n, uint64_t need_mask, int tbits_max, int low_bits) {
+    TilePlan tp;
+    int tb = std::min(tbits_max, n);
+    uint64_t m = need_mask;
+    int lb = std::min(low_bits, tb);
+    for (int b = 0; b < lb; ++b) m |= 1ull << b;
+    // fill with the lowest unused bits
+    for (int b = 0; b < n && popc64(m) < tb; ++b) m |= 1ull << b;
+    tp.tile_mask = m;
+    tp.tbits = popc64(m);
+    for (int b = 0; b < n; ++b)
+        if ((m >> b) & 1ull) tp.bits.push_back(b);
+    int l = 0;
+    while (l < tp.tbits && tp.bits[l] == l) ++l;
+    tp.lbits = l;
+    uint64_t full = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    tp.comp_mask = full & ~m;
+    tp.n_tiles = 1ull << (n - tp.tbits);
+    int hi = tp.tbits - tp.lbits;
+    tp.scat.resize(1ull << hi);
+    for (uint64_t v = 0; v < (1ull << hi); ++v) {
+        uint64_t o = 0;
+        for (int j = 0; j < hi; ++j)
+            if ((v >> j) & 1ull) o |= 1ull << tp.bits[tp.lbits + j];
+        tp.scat[v] = o;
+    }
+    return tp;
+}
+
+struct KernelProf {
+    double ms = 0.0;
+    uint64_t launches = 0;
+};
+
+struct vqe_ctx {
+    int n = 0, device = 0, sm_count = 148;
+    uint64_t n_amp = 0;
+    cudaStream_t stream = nullptr;
+    double2* buf[3] = {nullptr, nullptr, nullptr};
+    // staging
+    char* h_stage = nullptr;
+    char* d_stage = nullptr;
+    size_t stage_cap = 0;
+    double2* d_partial = nullptr;
+    size_t partial_cap = 0;  // in double2
+    double2* d_result = nullptr;
+    double2* h_result = nullptr;  // pinned
+    size_t result_cap = 0;        // in double2
+    int tile_bits = 12, low_bits = 5, threads = 256, ctas_per_sm = 3;
+    uint64_t launches = 0;
+    bool profiling = false;
+    KernelProf prof[4];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct ProfScope {
+    vqe_ctx* c;
+    int which;
+    ProfScope(vqe_ctx* c_, int w) : c(c_), which(w) {
+        if (c->profiling) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~ProfScope() {
+        c->prof[which].launches++;
+        if (c->profiling) {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            c->prof[which].ms += ms;
+        }
+    }
+};
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+static int ensure_stage(vqe_ctx* c, size_t bytes) {
+    if (bytes <= c->stage_cap) return VQE_OK;
+    size_t cap = std::max(bytes, c->stage_cap * 2 + 4096);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_stage) cudaFree(c->d_stage);
+    c->h_stage = nullptr;
+    c->d_stage = nullptr;
+    c->stage_cap = 0;
+    CK(cudaMallocHost((void**)&c->h_stage, cap));
+    CK(cudaMalloc((void**)&c->d_stage, cap));
+    c->stage_cap = cap;
+    return VQE_OK;
+}
+static int ensure_partial(vqe_ctx* c, size_t n) {
+    if (n <= c->partial_cap) return VQE_OK;
+    if (c->d_partial) cudaFree(c->d_partial);
+    c->d_partial = nullptr;
+    c->partial_cap = 0;
+    CK(cudaMalloc((void**)&c->d_partial, n * sizeof(double2)));
+    c->partial_cap = n;
+    return VQE_OK;
+}
+static int ensure_result(vqe_ctx* c, size_t n) {
+    if (n <= c->result_cap) return VQE_OK;
+    if (c->d_result) cudaFree(c->d_result);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    c->d_result = nullptr;
+    c->h_result = nullptr;
+    c->result_cap = 0;
+    CK(cudaMalloc((void**)&c->d_result, n * sizeof(double2)));
+    CK(cudaMallocHost((void**)&c->h_result, n * sizeof(double2)));
+    c->result_cap = n;
+    return VQE_OK;
+}
+static int ensure_buf(vqe_ctx* c, int b) {
+    if (b < 0 || b > 2) return fail(VQE_ERR_INVALID, "bad buffer id %d", b);
+    if (c->buf[b]) return VQE_OK;
+    cudaError_t e = cudaMalloc((void**)&c->buf[b], c->n_amp * sizeof(double2));
+    if (e != cudaSuccess) {
+        c->buf[b] = nullptr;
+        return fail(VQE_ERR_NOMEM, "cudaMalloc of state buffer %d (%.1f GB) failed: %s", b,
+                    c->n_amp * 16.0 / 1e9, cudaGetErrorString(e));
+    }
+    CK(cudaMemsetAsync(c->buf[b], 0, c->n_amp * sizeof(double2), c->stream));
+    return VQE_OK;
+}
+
+static size_t tile_smem(int tbits, int n_tiles_in_smem, bool term_cache) {
+    size_t s = (size_t)n_tiles_in_smem * (16ull << tbits);
+    if (term_cache) s += TERM_CAP * (sizeof(double2) + sizeof(uint32_t));
+    return s;
+}
+
+static bool g_attr_done = false;
+static int set_kernel_attrs() {
+    if (g_attr_done) return VQE_OK;
+    const int maxs = 227 * 1024;
+#define SET_SMEM(k)                                                                              \
+    do {                                                                                         \
+        cudaFuncAttributes fa_;                                                                  \
+        CK(cudaFuncGetAttributes(&fa_, k));                                                      \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
+                                maxs - (int)fa_.sharedSizeBytes));                               \
+    } while (0)
+    SET_SMEM(k_tile_ops);
+    SET_SMEM(k_tile_expect);
+    SET_SMEM(k_tile_apply);
+    SET_SMEM(k_tile_pool);
+#undef SET_SMEM
+    g_attr_done = true;
+    return VQE_OK;
+}
+
+extern "C" int vqe_create(vqe_ctx** out, int n_qubits, int device) {
+    if (!out) return fail(VQE_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > 40) return fail(VQE_ERR_INVALID, "n_qubits=%d out of range [1,40]", n_qubits);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(VQE_ERR_CUDA, "no CUDA device available (%s): this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(VQE_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
+    CK(cudaSetDevice(device));
+    vqe_ctx* c = new vqe_ctx();
+    c->n = n_qubits;
+    c->device = device;
+    c->n_amp = 1ull << n_qubits;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->tile_bits = env_int("VQE_TILE_BITS", 12);
+    c->low_bits = env_int("VQE_LOW_BITS", 5);
+    c->threads = env_int("VQE_THREADS", 256);
+    c->ctas_per_sm = env_int("VQE_CTAS_PER_SM", 3);
+    if (c->tile_bits < 6 || c->tile_bits > 13) c->tile_bits = 12;
+    if (c->threads < 64 || c->threads > 256 || (c->threads & 31)) c->threads = 256;
+    if (c->low_bits < 0 || c->low_bits > c->tile_bits) c->low_bits = 5;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    int rc = set_kernel_attrs();
+    if (rc) { delete c; return rc; }
+    rc = ensure_buf(c, VQE_BUF_PSI);
+    if (rc) { cudaStreamDestroy(c->stream); delete c; return rc; }
+    rc = ensure_result(c, 64);
+    if (rc) return rc;
+    *out = c;
+    return VQE_OK;
+}
+
+extern "C" void vqe_destroy(vqe_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int b = 0; b < 3; ++b)
+        if (c->buf[b]) cudaFree(c->buf[b]);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_stage) cudaFree(c->d_stage);
+    if (c->d_partial) cudaFree(c->d_partial);
+    if (c->d_result) cudaFree(c->d_result);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int vqe_n_qubits(const vqe_ctx* c) { return c ? c->n : 0; }
+extern "C" uint64_t vqe_launch_count(const vqe_ctx* c) { return c ? c->launches : 0; }
+extern "C" int vqe_profile_enable(vqe_ctx* c, int on) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    c->profiling = on != 0;
+    return VQE_OK;
+}
+extern "C" int vqe_profile_read(vqe_ctx* c, int which, double* ms_total, uint64_t* launches, int reset) {
+    if (!c || which < 0 || which > 3) return fail(VQE_ERR_INVALID, "bad profile slot");
+    if (ms_total) *ms_total = c->prof[which].ms;
+    if (launches) *launches = c->prof[which].launches;
+    if (reset) c->prof[which] = KernelProf();
+    return VQE_OK;
+}
+
+static int grid_1d(const vqe_ctx* c, uint64_t n_amp, int threads) {
+    uint64_t want = (n_amp + threads - 1) / threads;
+    uint64_t cap = (uint64_t)c->sm_count * 8;
+    return (int)std::max<uint64_t>(1, std::min(want, cap));
+}
+
+extern "C" int vqe_set_basis_state(vqe_ctx* c, uint64_t index) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    if (index >= c->n_amp) return fail(VQE_ERR_INVALID, "basis index %llu >= 2^%d", (unsigned long long)index, c->n);
+    CK(cudaSetDevice(c->device));
+    k_zero_set<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[0], c->n_amp, index);
+    c->launches++;
+    CK(cudaGetLastError());
+    return VQE_OK;
+}
+
+extern "C" int vqe_set_state(vqe_ctx* c, int b, const double* re_im) {
+    if (!c || !re_im) return fail(VQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, b);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->buf[b], re_im, c->n_amp * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return VQE_OK;
+}
+extern "C" int vqe_get_state(vqe_ctx* c, int b, double* re_im) {
+    if (!c || !re_im) return fail(VQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, b);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(re_im, c->buf[b], c->n_amp * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return VQE_OK;
+}
+extern "C" int vqe_copy_buffer(vqe_ctx* c, int dst, int src) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, dst);
+    if (rc) return rc;
+    rc = ensure_buf(c, src);
+    if (rc) return rc;
+    if (dst == src) return VQE_OK;
+    CK(cudaMemcpyAsync(c->buf[dst], c->buf[src], c->n_amp * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+    return VQE_OK;
+}
+extern "C" int vqe_buffer_ptr(vqe_ctx* c, int b, void** p, uint64_t* n_amp) {
+    if (!c || !p) return fail(VQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, b);
+    if (rc) return rc;
+    *p = c->buf[b];
+    if (n_amp) *n_amp = c->n_amp;
+    return VQE_OK;
+}
+extern "C" int vqe_synchronize(vqe_ctx* c) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return VQE_OK;
+}
+
+// ---- generic op program ---------------------------------------------------------------------
+struct HostOp {
+    int kind;
+    uint64_t x, z;       // ROT: masks | GATE1: x = bit | CNOT: x = target bit, z = control bit
+    double c, s;
+    int ny;
+    double m[8];
+};
+
+static int tile_grid(const vqe_ctx* c, const TilePlan& tp) {
+    uint64_t cap = (uint64_t)c->sm_count * c->ctas_per_sm;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(tp.n_tiles, cap));
+}
+
+// plan + upload + launch an ordered op list on buffer 0
+static int run_ops(vqe_ctx* c, const std::vector<HostOp>& ops) {
+    if (ops.empty()) return VQE_OK;
+    CK(cudaSetDevice(c->device));
+    const int n = c->n;
+    struct Pass {
+        TilePlan tp;
+        size_t op_begin, op_end;  // in dev op array
+    };
+    std::vector<Pass> passes;
+    std::vector<DevOp> dops;
+    std::vector<double> mats;
+    dops.reserve(ops.size());
+    size_t i = 0;
+    const int tb = std::min(c->tile_bits, n);
+    const int lb = std::min(c->low_bits, tb);
+    uint64_t lowmask = (lb >= 64) ? ~0ull : ((1ull << lb) - 1ull);
+    while (i < ops.size()) {
+        uint64_t need = 0;
+        size_t j = i;
+        while (j < ops.size()) {
+            uint64_t nb = ops[j].x;  // bits that must be inside the tile
+            uint64_t u = need | nb;
+            if (popc64(u | lowmask) > tb) break;
+            need = u;
+            ++j;
+        }
+        if (j == i)
+            return fail(VQE_ERR_INVALID, "operation %zu touches %d X-bits, more than a %d-bit tile can hold", i,
+                        popc64(ops[i].x), tb);
+        Pass p;
+        p.tp = make_plan(n, need, tb, lb);
+        p.op_begin = dops.size();
+        for (size_t k = i; k < j; ++k) {
+            const HostOp& h = ops[k];
+            DevOp d;
+            memset(&d, 0, sizeof d);
+            d.kind = h.kind;
+            if (h.kind == OP_ROT) {
+                d.lx = pext_mask(h.x, p.tp);
+                d.lz = pext_mask(h.z, p.tp);
+                d.zout = h.z & p.tp.comp_mask;
+                d.c = h.c;
+                d.s = h.s;
+                d.k4 = (uint32_t)((h.ny + 3) & 3);
+                d.nyodd = h.ny & 1;
+                d.hb = d.lx ? 31 - __builtin_clz(d.lx) : 0;
+                d.run = 1;
+            } else if (h.kind == OP_GATE1) {
+                d.lx = pext_mask(h.x, p.tp);
+                d.hb = 31 - __builtin_clz(d.lx);
+                d.mat = (uint32_t)(mats.size() / 8);
+                mats.insert(mats.end(), h.m, h.m + 8);
+            } else {
+                d.lx = pext_mask(h.x, p.tp);
+                d.hb = 31 - __builtin_clz(d.lx);
+                if (h.z & p.tp.tile_mask) d.lz = pext_mask(h.z, p.tp);
+                else d.zout = h.z;
+            }
+            dops.push_back(d);
+        }
+        p.op_end = dops.size();
+        // run lengths of consecutive same-lx rotations
+        for (size_t k = p.op_begin; k < p.op_end;) {
+            if (dops[k].kind != OP_ROT) { ++k; continue; }
+            size_t e = k + 1;
+            while (e < p.op_end && dops[e].kind == OP_ROT && dops[e].lx == dops[k].lx) ++e;
+            dops[k].run = (uint32_t)(e - k);
+            k = e;
+        }
+        passes.push_back(std::move(p));
+        i = j;
+    }
+    // upload: [ops][mats][scat tables]
+    size_t off_ops = 0, off_mats = dops.size() * sizeof(DevOp);
+    size_t off_scat = off_mats + mats.size() * sizeof(double);
+    off_scat = (off_scat + 15) & ~size_t(15);
+    size_t total = off_scat;
+    std::vector<size_t> scat_off(passes.size());
+    for (size_t p = 0; p < passes.size(); ++p) {
+        scat_off[p] = total;
+        total += passes[p].tp.scat.size() * sizeof(uint64_t);
+    }
+    int rc = ensure_stage(c, total);
+    if (rc) return rc;
+    // the staging buffer may still be read by an earlier async copy
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(c->h_stage + off_ops, dops.data(), dops.size() * sizeof(DevOp));
+    if (!mats.empty()) memcpy(c->h_stage + off_mats, mats.data(), mats.size() * sizeof(double));
+    for (size_t p = 0; p < passes.size(); ++p)
+        memcpy(c->h_stage + scat_off[p], passes[p].tp.scat.data(), passes[p].tp.scat.size() * sizeof(uint64_t));
+    CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
+    for (size_t p = 0; p < passes.size(); ++p) {
+        const Pass& ps = passes[p];
+        TileGeom g;
+        g.comp_mask = ps.tp.comp_mask;
+        g.n_tiles = ps.tp.n_tiles;
+        g.scat = (const uint64_t*)(c->d_stage + scat_off[p]);
+        g.tbits = ps.tp.tbits;
+        g.lbits = ps.tp.lbits;
+        size_t smem = tile_smem(ps.tp.tbits, 1, false);
+        int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
+        ProfScope prof(c, 0);
+        k_tile_ops<<<tile_grid(c, ps.tp), threads, smem, c->stream>>>(
+            c->buf[0], g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
+            (const double*)(c->d_stage + off_mats));
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return VQE_OK;
+}
+
+extern "C" int vqe_apply_pauli_rotations(vqe_ctx* c, int n_rot, const uint64_t* xmask, const uint64_t* zmask,
+                                         const int32_t* ny, const double* angle) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    if (n_rot < 0 || (n_rot > 0 && (!xmask || !zmask || !ny || !angle))) return fail(VQE_ERR_INVALID, "null array");
+    const uint64_t full = c->n_amp - 1;
+    std::vector<HostOp> ops;
+    ops.reserve(n_rot);
+    for (int k = 0; k < n_rot; ++k) {
+        if ((xmask[k] | zmask[k]) & ~full) return fail(VQE_ERR_INVALID, "rotation %d: mask has bits >= n_qubits", k);
+        if (popc64(xmask[k] & zmask[k]) != ny[k]) return fail(VQE_ERR_INVALID, "rotation %d: ny != popcount(x&z)", k);
+        if (angle[k] == 0.0) continue;  // exact identity
+        HostOp h;
+        memset(&h, 0, sizeof h);
+        h.kind = OP_ROT;
+        h.x = xmask[k];
+        h.z = zmask[k];
+        h.ny = ny[k];
+        h.c = cos(angle[k]);
+        h.s = sin(angle[k]);
+        ops.push_back(h);
+    }
+    return run_ops(c, ops);
+}
+
+extern "C" int vqe_apply_gates(vqe_ctx* c, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
+                               const double* angle) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    if (n_gates < 0 || (n_gates > 0 && (!kind || !q0))) return fail(VQE_ERR_INVALID, "null array");
+    std::vector<HostOp> ops;
+    ops.reserve(n_gates);
+    const double r2 = 0.70710678118654752440;
+    for (int k = 0; k < n_gates; ++k) {
+        if (q0[k] < 0 || q0[k] >= c->n) return fail(VQE_ERR_INVALID, "gate %d: qubit %d out of range", k, q0[k]);
+        HostOp h;
+        memset(&h, 0, sizeof h);
+        h.x = 1ull << (c->n - 1 - q0[k]);
+        double th = angle ? angle[k] : 0.0;
+        double cs = cos(0.5 * th), sn = sin(0.5 * th);
+        switch (kind[k]) {
+            case VQE_GATE_X: h.kind = OP_GATE1; h.m[2] = 1; h.m[4] = 1; break;
+            case VQE_GATE_H: h.kind = OP_GATE1; h.m[0] = r2; h.m[2] = r2; h.m[4] = r2; h.m[6] = -r2; break;
+            case VQE_GATE_RX: h.kind = OP_GATE1; h.m[0] = cs; h.m[3] = -sn; h.m[5] = -sn; h.m[6] = cs; break;
+            case VQE_GATE_RY: h.kind = OP_GATE1; h.m[0] = cs; h.m[2] = -sn; h.m[4] = sn; h.m[6] = cs; break;
+            case VQE_GATE_RZ: h.kind = OP_GATE1; h.m[0] = cs; h.m[1] = -sn; h.m[6] = cs; h.m[7] = sn; break;
+            case VQE_GATE_CNOT:
+                if (!q1 || q1[k] < 0 || q1[k] >= c->n || q1[k] == q0[k])
+                    return fail(VQE_ERR_INVALID, "gate %d: bad CNOT target", k);
+                h.kind = OP_CNOT;
+                h.z = 1ull << (c->n - 1 - q0[k]);  // control
+                h.x = 1ull << (c->n - 1 - q1[k]);  // target
+                break;
+            default: return fail(VQE_ERR_INVALID, "gate %d: unknown kind %d", k, kind[k]);
+        }
+        ops.push_back(h);
+    }
+    return run_ops(c, ops);
+}
+
+// ---- Pauli sums -----------------------------------------------------------------------------
+struct PSPass {
+    TilePlan tp;
+    std::vector<DevGroup> groups;
+    std::vector<DevTerm> terms_expect;  // pair weights (expectation)
+    std::vector<DevTerm> terms_apply;   // c_k i^ny   (apply)
+    // device copies
+    DevGroup* d_groups = nullptr;
+    DevTerm* d_terms_expect = nullptr;
+    DevTerm* d_terms_apply = nullptr;
+    uint64_t* d_scat = nullptr;
+};
+struct vqe_paulisum {
+    int n = 0, device = 0, n_groups = 0, tbits = 0;
+    std::vector<PSPass> passes;
+};
+
+struct HTerm {
+    uint64_t x, z;
+    int ny;
+    double cr, ci;
+};
+
+static void mul_i_pow(double& r, double& i, int k) {
+    k &= 3;
+    double a = r, b = i;
+    if (k == 1) { r = -b; i = a; }
+    else if (k == 2) { r = -a; i = -b; }
+    else if (k == 3) { r = b; i = -a; }
+}
+
+static int build_paulisum(vqe_paulisum* ps, int n, int tbits_max, int low_bits, std::vector<HTerm> terms) {
+    // group by x (stable: keep first-appearance order of groups, term order inside)
+    std::vector<uint64_t> xs;
+    std::vector<std::vector<HTerm>> grp;
+    {
+        std::vector<std::pair<uint64_t, size_t>> keyed;
+        for (size_t k = 0; k < terms.size(); ++k) keyed.push_back({terms[k].x, k});
+        std::stable_sort(keyed.begin(), keyed.end(),
+                         [](const std::pair<uint64_t, size_t>& a, const std::pair<uint64_t, size_t>& b) {
+                             return a.first < b.first;
+                         });
+        for (size_t k = 0; k < keyed.size(); ++k) {
+            if (k == 0 || keyed[k].first != keyed[k - 1].first) {
+                xs.push_back(keyed[k].first);
+                grp.emplace_back();
+            }
+            grp.back().push_back(terms[keyed[k].second]);
+        }
+    }
+    ps->n = n;
+    ps->n_groups = (int)xs.size();
+    const int tb = std::min(tbits_max, n);
+    const int lb = std::min(low_bits, tb);
+    ps->tbits = tb;
+    uint64_t lowmask = (1ull << lb) - 1ull;
+    // split oversize groups so that each fits in the term cache
+    {
+        std::vector<uint64_t> xs2;
+        std::vector<std::vector<HTerm>> grp2;
+        for (size_t g = 0; g < xs.size(); ++g) {
+            for (size_t o = 0; o < grp[g].size(); o += TERM_CAP) {
+                xs2.push_back(xs[g]);
+                grp2.emplace_back(grp[g].begin() + o, grp[g].begin() + std::min(grp[g].size(), o + TERM_CAP));
+            }
+        }
+        xs.swap(xs2);
+        grp.swap(grp2);
+    }
+    std::vector<char> done(xs.size(), 0);
+    size_t remaining = xs.size();
+    while (remaining) {
+        // seed
+        uint64_t need = 0;
+        std::vector<size_t> members;
+        for (size_t g = 0; g < xs.size(); ++g) {
+            if (done[g]) continue;
+            uint64_t u = need | xs[g];
+            if (popc64(u | lowmask) > tb) {
+                if (members.empty())
+                    return fail(VQE_ERR_INVALID, "Pauli term with %d X/Y letters exceeds the %d-bit tile", popc64(xs[g]), tb);
+                continue;
+            }
+            need = u;
+            members.push_back(g);
+            done[g] = 1;
+        }
+        PSPass p;
+        p.tp = make_plan(n, need, tb, lb);
+        // second sweep: anything already inside the final tile mask
+        for (size_t g = 0; g < xs.size(); ++g) {
+            if (done[g]) continue;
+            if ((xs[g] & ~p.tp.tile_mask) == 0) {
+                members.push_back(g);
+                done[g] = 1;
+            }
+        }
+        remaining -= members.size();
+        for (size_t g : members) {
+            DevGroup dg;
+            memset(&dg, 0, sizeof dg);
+            dg.lx = pext_mask(xs[g], p.tp);
+            dg.hb = dg.lx ? 31 - __builtin_clz(dg.lx) : 0;
+            dg.t_begin = (uint32_t)p.terms_expect.size();
+            for (int parity = 0; parity < 2; ++parity) {
+                for (const HTerm& t : grp[g]) {
+                    if ((t.ny & 1) != parity) continue;
+                    DevTerm e, a;
+                    memset(&e, 0, sizeof e);
+                    e.lz = pext_mask(t.z, p.tp);
+                    e.zout = t.z & p.tp.comp_mask;
+                    a = e;
+                    // apply weight: c * i^ny
+                    a.ar = t.cr;
+                    a.ai = t.ci;
+                    mul_i_pow(a.ar, a.ai, t.ny);
+                    // expectation pair weight: even ny: c * i^ny (multiplies 2Re w)
+                    //                          odd  ny: c * i^ny * i = c * i^(ny+1)  (multiplies 2Im w)
+                    e.ar = t.cr;
+                    e.ai = t.ci;
+                    mul_i_pow(e.ar, e.ai, parity ? t.ny + 1 : t.ny);
+                    if (xs[g] == 0) { e.ar = t.cr; e.ai = t.ci; }
+                    p.terms_expect.push_back(e);
+                    p.terms_apply.push_back(a);
+                    if (parity) dg.n_odd++; else dg.n_even++;
+                }
+            }
+            p.groups.push_back(dg);
+        }
+        ps->passes.push_back(std::move(p));
+    }
+    return VQE_OK;
+}
+
+static void free_paulisum_device(vqe_paulisum* ps) {
+    for (PSPass& p : ps->passes) {
+        if (p.d_groups) cudaFree(p.d_groups);
+        if (p.d_terms_expect) cudaFree(p.d_terms_expect);
+        if (p.d_terms_apply) cudaFree(p.d_terms_apply);
+        if (p.d_scat) cudaFree(p.d_scat);
+        p.d_groups = nullptr;
+        p.d_terms_expect = p.d_terms_apply = nullptr;
+        p.d_scat = nullptr;
+    }
+}
+
+static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
+    for (PSPass& p : ps->passes) {
+        CK(cudaMalloc((void**)&p.d_groups, p.groups.size() * sizeof(DevGroup)));
+        CK(cudaMalloc((void**)&p.d_terms_expect, std::max<size_t>(1, p.terms_expect.size()) * sizeof(DevTerm)));
+        CK(cudaMalloc((void**)&p.d_terms_apply, std::max<size_t>(1, p.terms_apply.size()) * sizeof(DevTerm)));
+        CK(cudaMalloc((void**)&p.d_scat, p.tp.scat.size() * sizeof(uint64_t)));
+        CK(cudaMemcpy(p.d_groups, p.groups.data(), p.groups.size() * sizeof(DevGroup), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p.d_terms_expect, p.terms_expect.data(), p.terms_expect.size() * sizeof(DevTerm), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p.d_terms_apply, p.terms_apply.data(), p.terms_apply.size() * sizeof(DevTerm), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p.d_scat, p.tp.scat.data(), p.tp.scat.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    return VQE_OK;
+}
+
+static int collect_terms(const vqe_ctx* c, int n_terms, const uint64_t* x, const uint64_t* z, const int32_t* ny,
+                         const double* cre, const double* cim, std::vector<HTerm>& out) {
+    if (n_terms < 0 || (n_terms > 0 && (!x || !z || !ny || !cre))) return fail(VQE_ERR_INVALID, "null array");
+    const uint64_t full = c->n_amp - 1;
+    out.reserve(n_terms);
+    for (int k = 0; k < n_terms; ++k) {
+        if ((x[k] | z[k]) & ~full) return fail(VQE_ERR_INVALID, "term %d: mask has bits >= n_qubits", k);
+        if (popc64(x[k] & z[k]) != ny[k]) return fail(VQE_ERR_INVALID, "term %d: ny != popcount(x&z)", k);
+        HTerm t;
+        t.x = x[k];
+        t.z = z[k];
+        t.ny = ny[k];
+        t.cr = cre[k];
+        t.ci = cim ? cim[k] : 0.0;
+        if (t.cr == 0.0 && t.ci == 0.0) continue;
+        out.push_back(t);
+    }
+    return VQE_OK;
+}
+
+extern "C" int vqe_paulisum_create(vqe_ctx* c, vqe_paulisum** out, int n_terms, const uint64_t* x,
+                                   const uint64_t* z, const int32_t* ny, const double* cre, const double* cim) {
+    if (!c || !out) return fail(VQE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    CK(cudaSetDevice(c->device));
+    std::vector<HTerm> terms;
+    int rc = collect_terms(c, n_terms, x, z, ny, cre, cim, terms);
+    if (rc) return rc;
+    vqe_paulisum* ps = new vqe_paulisum();
+    ps->device = c->device;
+    rc = build_paulisum(ps, c->n, c->tile_bits, c->low_bits, std::move(terms));
+    if (rc == VQE_OK) rc = upload_paulisum(c, ps);
+    if (rc) {
+        free_paulisum_device(ps);
+        delete ps;
+        return rc;
+    }
+    *out = ps;
+    return VQE_OK;
+}
+extern "C" void vqe_paulisum_destroy(vqe_paulisum* ps) {
+    if (!ps) return;
+    cudaSetDevice(ps->device);
+    free_paulisum_device(ps);
+    delete ps;
+}
+extern "C" int vqe_paulisum_groups(const vqe_paulisum* ps) { return ps ? ps->n_groups : 0; }
+extern "C" int vqe_paulisum_passes(const vqe_paulisum* ps) { return ps ? (int)ps->passes.size() : 0; }
+
+static TileGeom geom_of(const PSPass& p) {
+    TileGeom g;
+    g.comp_mask = p.tp.comp_mask;
+    g.n_tiles = p.tp.n_tiles;
+    g.scat = p.d_scat;
+    g.tbits = p.tp.tbits;
+    g.lbits = p.tp.lbits;
+    return g;
+}
+
+extern "C" int vqe_expectation(vqe_ctx* c, int b, const vqe_paulisum* ps, double* out) {
+    if (!c || !ps || !out) return fail(VQE_ERR_INVALID, "null argument");
+    if (ps->n != c->n) return fail(VQE_ERR_INVALID, "Pauli sum built for %d qubits, context has %d", ps->n, c->n);
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, b);
+    if (rc) return rc;
+    // partial layout: consecutive blocks of every pass
+    size_t total_blocks = 0;
+    std::vector<dim3> grids(ps->passes.size());
+    for (size_t p = 0; p < ps->passes.size(); ++p) {
+        const PSPass& pp = ps->passes[p];
+        int gx = tile_grid(c, pp.tp);
+        int want = std::max(1, (c->sm_count * c->ctas_per_sm) / gx);
+        int gy = std::max(1, std::min<int>((int)pp.groups.size(), want));
+        grids[p] = dim3(gx, gy, 1);
+        total_blocks += (size_t)gx * gy;
+    }
+    rc = ensure_partial(c, std::max<size_t>(1, total_blocks));
+    if (rc) return rc;
+    size_t off = 0;
+    for (size_t p = 0; p < ps->passes.size(); ++p) {
+        const PSPass& pp = ps->passes[p];
+        size_t smem = tile_smem(pp.tp.tbits, 1, true);
+        int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << pp.tp.tbits) / 2));
+        ProfScope prof(c, 1);
+        k_tile_expect<<<grids[p], threads, smem, c->stream>>>(c->buf[b], geom_of(pp), pp.d_groups,
+                                                             (int)pp.groups.size(), pp.d_terms_expect,
+                                                             c->d_partial + off);
+        c->launches++;
+        off += (size_t)grids[p].x * grids[p].y;
+    }
+    if (total_blocks == 0) {
+        out[0] = out[1] = 0.0;
+        return VQE_OK;
+    }
+    k_reduce_partials<<<1, 32, 0, c->stream>>>(c->d_partial, (int)total_blocks, 1, 1, c->d_result);
+    c->launches++;
+    CK(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    out[0] = c->h_result[0].x;
+    out[1] = c->h_result[0].y;
+    return VQE_OK;
+}
+
+static int apply_paulisum_bufs(vqe_ctx* c, double2* dst, const double2* src, const vqe_paulisum* ps) {
+    if (ps->passes.empty()) {
+        CK(cudaMemsetAsync(dst, 0, c->n_amp * sizeof(double2), c->stream));
+        return VQE_OK;
+    }
+    for (size_t p = 0; p < ps->passes.size(); ++p) {
+        const PSPass& pp = ps->passes[p];
+        size_t smem = tile_smem(pp.tp.tbits, 1, true);
+        uint64_t ts = 1ull << pp.tp.tbits;
+        int threads = (int)std::min<uint64_t>(512, std::max<uint64_t>(32, ts));
+        while ((uint64_t)threads * APPLY_PER_THREAD < ts) threads *= 2;  // ts <= 8192 = 512*16
+        ProfScope prof(c, 2);
+        k_tile_apply<<<tile_grid(c, pp.tp), threads, smem, c->stream>>>(src, dst, geom_of(pp), pp.d_groups,
+                                                                       (int)pp.groups.size(), pp.d_terms_apply,
+                                                                       p == 0 ? 0 : 1);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return VQE_OK;
+}
+
+extern "C" int vqe_apply_paulisum(vqe_ctx* c, int dst, int src, const vqe_paulisum* ps) {
+    if (!c || !ps) return fail(VQE_ERR_INVALID, "null argument");
+    if (dst == src) return fail(VQE_ERR_INVALID, "dst and src buffers must differ");
+    if (ps->n != c->n) return fail(VQE_ERR_INVALID, "Pauli sum built for %d qubits, context has %d", ps->n, c->n);
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, dst);
+    if (rc) return rc;
+    rc = ensure_buf(c, src);
+    if (rc) return rc;
+    return apply_paulisum_bufs(c, c->buf[dst], c->buf[src], ps);
+}
+
+// ---- pool sweep -------------------------------------------------------------------------------
+extern "C" int vqe_pool_overlaps(vqe_ctx* c, int bra, int ket, int n_ops, const int32_t* op_offsets,
+                                 const uint64_t* x, const uint64_t* z, const int32_t* ny, const double* cre,
+                                 const double* cim, double* out) {
+    if (!c || !out) return fail(VQE_ERR_INVALID, "null argument");
+    if (n_ops < 0 || (n_ops > 0 && !op_offsets)) return fail(VQE_ERR_INVALID, "null offsets");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, bra);
+    if (rc) return rc;
+    rc = ensure_buf(c, ket);
+    if (rc) return rc;
+    for (int k = 0; k < 2 * n_ops; ++k) out[k] = 0.0;
+    if (n_ops == 0) return VQE_OK;
+    const int n = c->n;
+    const uint64_t full = c->n_amp - 1;
+    // two tiles in shared memory: 2 * 16 * 2^tb <= 227 KB -> tb <= 12
+    const int tb = std::min(std::min(c->tile_bits, 12), n);
+    const int lb = std::min(c->low_bits, tb);
+    const uint64_t lowmask = (1ull << lb) - 1ull;
+    const int n_terms = op_offsets[n_ops];
+    for (int k = 0; k < n_terms; ++k) {
+        if ((x[k] | z[k]) & ~full) return fail(VQE_ERR_INVALID, "pool term %d: mask has bits >= n_qubits", k);
+        if (popc64(x[k] & z[k]) != ny[k]) return fail(VQE_ERR_INVALID, "pool term %d: ny != popcount(x&z)", k);
+    }
+    std::vector<uint64_t> need(n_ops, 0);
+    std::vector<char> done(n_ops, 0);
+    int remaining = 0;
+    for (int o = 0; o < n_ops; ++o) {
+        bool any = false;
+        for (int k = op_offsets[o]; k < op_offsets[o + 1]; ++k) {
+            if (cre[k] == 0.0 && (!cim || cim[k] == 0.0)) continue;
+            need[o] |= x[k];
+            any = true;
+        }
+        if (!any) done[o] = 1;  // identically-zero operator: overlap is exactly 0
+        else ++remaining;
+        if (popc64(need[o] | lowmask) > tb)
+            return fail(VQE_ERR_INVALID, "pool operator %d spans %d X-bits, more than a %d-bit tile", o, popc64(need[o]), tb);
+    }
+    while (remaining) {
+        uint64_t acc = 0;
+        std::vector<int> members;
+        for (int o = 0; o < n_ops; ++o) {
+            if (done[o]) continue;
+            uint64_t u = acc | need[o];
+            if (popc64(u | lowmask) > tb) continue;
+            acc = u;
+            members.push_back(o);
+            done[o] = 1;
+        }
+        TilePlan tp = make_plan(n, acc, tb, lb);
+        for (int o = 0; o < n_ops; ++o) {
+            if (done[o]) continue;
+            if ((need[o] & ~tp.tile_mask) == 0) {
+                members.push_back(o);
+                done[o] = 1;
+            }
+        }
+        remaining -= (int)members.size();
+        std::vector<DevPoolOp> pops;
+        std::vector<DevPoolTerm> pterms;
+        for (int o : members) {
+            DevPoolOp po;
+            po.t_begin = (uint32_t)pterms.size();
+            po.out_index = (uint32_t)o;
+            po.pad = 0;
+            for (int k = op_offsets[o]; k < op_offsets[o + 1]; ++k) {
+                double cr = cre[k], ci = cim ? cim[k] : 0.0;
+                if (cr == 0.0 && ci == 0.0) continue;
+                DevPoolTerm t;
+                t.lx = pext_mask(x[k], tp);
+                t.lz = pext_mask(z[k], tp);
+                t.zout = z[k] & tp.comp_mask;
+                mul_i_pow(cr, ci, ny[k]);
+                t.ar = cr;
+                t.ai = ci;
+                pterms.push_back(t);
+            }
+            po.n_terms = (uint32_t)pterms.size() - po.t_begin;
+            pops.push_back(po);
+        }
+        const int np = (int)pops.size();
+        int gx = tile_grid(c, tp);
+        gx = std::min(gx, c->sm_count);  // 1 CTA per SM (two tiles of shared memory)
+        int gy = std::max(1, std::min((np + 15) / 16, std::max(1, (c->sm_count) / gx)));
+        size_t off_ops = 0, off_terms = (np * sizeof(DevPoolOp) + 15) & ~size_t(15);
+        size_t off_scat = (off_terms + pterms.size() * sizeof(DevPoolTerm) + 15) & ~size_t(15);
+        size_t total = off_scat + tp.scat.size() * sizeof(uint64_t);
+        rc = ensure_stage(c, total);
+        if (rc) return rc;
+        rc = ensure_partial(c, (size_t)gx * np);
+        if (rc) return rc;
+        rc = ensure_result(c, np);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(c->stream));
+        memcpy(c->h_stage + off_ops, pops.data(), np * sizeof(DevPoolOp));
+        memcpy(c->h_stage + off_terms, pterms.data(), pterms.size() * sizeof(DevPoolTerm));
+        memcpy(c->h_stage + off_scat, tp.scat.data(), tp.scat.size() * sizeof(uint64_t));
+        CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
+        TileGeom g;
+        g.comp_mask = tp.comp_mask;
+        g.n_tiles = tp.n_tiles;
+        g.scat = (const uint64_t*)(c->d_stage + off_scat);
+        g.tbits = tp.tbits;
+        g.lbits = tp.lbits;
+        size_t smem = tile_smem(tp.tbits, 2, false);
+        int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << tp.tbits)));
+        {
+            ProfScope prof(c, 3);
+            k_tile_pool<<<dim3(gx, gy, 1), threads, smem, c->stream>>>(
+                c->buf[bra], c->buf[ket], g, (const DevPoolOp*)(c->d_stage + off_ops), np,
+                (const DevPoolTerm*)(c->d_stage + off_terms), c->d_partial);
+            c->launches++;
+        }
+        k_reduce_partials<<<(np + 127) / 128, 128, 0, c->stream>>>(c->d_partial, gx, np, np, c->d_result);
+        c->launches++;
+        CK(cudaMemcpyAsync(c->h_result, c->d_result, np * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+        for (int i = 0; i < np; ++i) {
+            out[2 * pops[i].out_index] = c->h_result[i].x;
+            out[2 * pops[i].out_index + 1] = c->h_result[i].y;
+        }
+    }
+    return VQE_OK;
+}
+
+// ---- reductions ---------------------------------------------------------------------------------
+static int inner_bufs(vqe_ctx* c, const double2* a, const double2* b, double* out) {
+    int blocks = grid_1d(c, c->n_amp, 256);
+    int rc = ensure_partial(c, blocks);
+    if (rc) return rc;
+    k_inner<<<blocks, 256, 0, c->stream>>>(a, b, c->n_amp, c->d_partial);
+    k_reduce_partials<<<1, 32, 0, c->stream>>>(c->d_partial, blocks, 1, 1, c->d_result);
+    c->launches += 2;
+    CK(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    out[0] = c->h_result[0].x;
+    out[1] = c->h_result[0].y;
+    return VQE_OK;
+}
+
+extern "C" int vqe_inner(vqe_ctx* c, int a, int b, double* out) {
+    if (!c || !out) return fail(VQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, a);
+    if (rc) return rc;
+    rc = ensure_buf(c, b);
+    if (rc) return rc;
+    return inner_bufs(c, c->buf[a], c->buf[b], out);
+}
+extern "C" int vqe_norm2(vqe_ctx* c, int b, double* out) {
+    double tmp[2];
+    int rc = vqe_inner(c, b, b, tmp);
+    if (rc) return rc;
+    *out = tmp[0];
+    return VQE_OK;
+}
+extern "C" int vqe_overlap_host(vqe_ctx* c, int b, const double* vec, double* out) {
+    if (!c || !vec || !out) return fail(VQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, b);
+    if (rc) return rc;
+    int tmp = (b == VQE_BUF_WORK) ? VQE_BUF_SIGMA : VQE_BUF_WORK;
+    rc = ensure_buf(c, tmp);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->buf[tmp], vec, c->n_amp * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    return inner_bufs(c, c->buf[tmp], c->buf[b], out);
+}
+
+// ---- exact exponential of an anti-Hermitian Pauli sum --------------------------------------------
+extern "C" int vqe_apply_exp_paulisum(vqe_ctx* c, int n_terms, const uint64_t* x, const uint64_t* z,
+                                      const int32_t* ny, const double* cre, const double* cim, double theta) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    CK(cudaSetDevice(c->device));
+    std::vector<HTerm> terms;
+    int rc = collect_terms(c, n_terms, x, z, ny, cre, cim, terms);
+    if (rc) return rc;
+    if (terms.empty() || theta == 0.0) return VQE_OK;
+    // anti-Hermitian  <=>  every coefficient purely imaginary
+    bool antiherm = true, commute = true;
+    for (const HTerm& t : terms)
+        if (t.cr != 0.0) antiherm = false;
+    for (size_t a = 0; a < terms.size() && commute; ++a)
+        for (size_t b = a + 1; b < terms.size(); ++b)
+            if ((popc64(terms[a].x & terms[b].z) + popc64(terms[a].z & terms[b].x)) & 1) {
+                commute = false;
+                break;
+            }
+    if (antiherm && commute) {
+        // exp(theta * i*ci*P) = exp(-i (-theta ci) P): exact product of rotations
+        std::vector<HostOp> ops;
+        for (const HTerm& t : terms) {
+            HostOp h;
+            memset(&h, 0, sizeof h);
+            h.kind = OP_ROT;
+            h.x = t.x;
+            h.z = t.z;
+            h.ny = t.ny;
+            double ang = -theta * t.ci;
+            h.c = cos(ang);
+            h.s = sin(ang);
+            ops.push_back(h);
+        }
+        return run_ops(c, ops);
+    }
+    // general case: scaled Taylor series  psi <- (sum_m (theta A / s)^m / m!)^s psi
+    vqe_paulisum ps;
+    ps.device = c->device;
+    rc = build_paulisum(&ps, c->n, c->tile_bits, c->low_bits, terms);
+    if (rc == VQE_OK) rc = upload_paulisum(c, &ps);
+    if (rc) { free_paulisum_device(&ps); return rc; }
+    rc = ensure_buf(c, VQE_BUF_SIGMA);
+    if (rc == VQE_OK) rc = ensure_buf(c, VQE_BUF_WORK);
+    if (rc) { free_paulisum_device(&ps); return rc; }
+    double bound = 0.0;
+    for (const HTerm& t : terms) bound += sqrt(t.cr * t.cr + t.ci * t.ci);
+    bound *= fabs(theta);
+    int scale = std::max(1, (int)ceil(bound / 0.5));
+    double2* term = c->buf[VQE_BUF_SIGMA];
+    double2* next = c->buf[VQE_BUF_WORK];
+    double2* psi = c->buf[VQE_BUF_PSI];
+    const int threads = 256, blocks = grid_1d(c, c->n_amp, threads);
+    for (int s = 0; s < scale && rc == VQE_OK; ++s) {
+        CK(cudaMemcpyAsync(term, psi, c->n_amp * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+        for (int m = 1; m <= 40; ++m) {
+            rc = apply_paulisum_bufs(c, next, term, &ps);  // next = A term
+            if (rc) break;
+            // term = (theta / (scale m)) next ; psi += term
+            k_axpby<<<blocks, threads, 0, c->stream>>>(term, next, c->n_amp, theta / (scale * (double)m), 0.0, 0.0, 0.0);
+            k_axpby<<<blocks, threads, 0, c->stream>>>(psi, term, c->n_amp, 1.0, 0.0, 1.0, 0.0);
+            c->launches += 2;
+            double nrm[2];
+            rc = inner_bufs(c, term, term, nrm);
+            if (rc) break;
+            if (nrm[0] < 1e-34) break;  // ||term|| < 1e-17
+        }
+    }
+    free_paulisum_device(&ps);
+    return rc;
+}

@@ -1,0 +1,181 @@
+"""Thin object wrapper over the C ABI (include/vqe_b200.h).
+
+One ``Engine`` = one complex128 state vector resident in HBM plus two scratch
+buffers (sigma, work) allocated on first use.  All arithmetic happens in the
+CUDA library; this module only marshals numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from .lowering import PackedTerms, pack_operator, pack_pool
+
+BUF_PSI, BUF_SIGMA, BUF_WORK = 0, 1, 2
+GATE_X, GATE_H, GATE_RX, GATE_RY, GATE_RZ, GATE_CNOT = range(6)
+GATE_KINDS = {"X": GATE_X, "H": GATE_H, "RX": GATE_RX, "RY": GATE_RY, "RZ": GATE_RZ, "CNOT": GATE_CNOT}
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PauliSum:
+    """Device-resident, X-mask-grouped Pauli sum (Hamiltonian or observable)."""
+
+    def __init__(self, engine, packed: PackedTerms):
+        lib = _lib.load()
+        self._lib = lib
+        self._engine = engine
+        self.n_terms = len(packed)
+        self.handle = C.c_void_p()
+        _lib.check(lib.vqe_paulisum_create(engine.handle, C.byref(self.handle), self.n_terms, _ptr(packed.x),
+                                           _ptr(packed.z), _ptr(packed.ny), _ptr(packed.cre), _ptr(packed.cim)))
+        self.n_groups = lib.vqe_paulisum_groups(self.handle)
+        self.n_passes = lib.vqe_paulisum_passes(self.handle)
+        self._finalizer = weakref.finalize(self, lib.vqe_paulisum_destroy, self.handle)
+
+
+class Engine:
+    def __init__(self, n_qubits: int, device: int = 0):
+        lib = _lib.load()
+        self._lib = lib
+        self.n = int(n_qubits)
+        self.device = int(device)
+        self.handle = C.c_void_p()
+        _lib.check(lib.vqe_create(C.byref(self.handle), self.n, self.device))
+        self._finalizer = weakref.finalize(self, lib.vqe_destroy, self.handle)
+        self._ps_cache = {}
+
+    # -- state ---------------------------------------------------------------
+    def set_basis_state(self, index: int):
+        _lib.check(self._lib.vqe_set_basis_state(self.handle, int(index)))
+
+    def set_state(self, vec, buf=BUF_PSI):
+        v = np.ascontiguousarray(np.asarray(vec, dtype=np.complex128).reshape(-1))
+        if v.shape[0] != 1 << self.n:
+            raise ValueError("state has %d amplitudes, expected 2^%d" % (v.shape[0], self.n))
+        _lib.check(self._lib.vqe_set_state(self.handle, buf, _ptr(v)))
+
+    def get_state(self, buf=BUF_PSI):
+        out = np.empty(1 << self.n, dtype=np.complex128)
+        _lib.check(self._lib.vqe_get_state(self.handle, buf, _ptr(out)))
+        return out
+
+    def copy_buffer(self, dst, src):
+        _lib.check(self._lib.vqe_copy_buffer(self.handle, dst, src))
+
+    # -- state preparation ---------------------------------------------------
+    def apply_rotations(self, x, z, ny, angles):
+        """psi <- prod_k exp(-i angles[k] P_k) psi, k = 0 first."""
+        x = np.ascontiguousarray(x, dtype=np.uint64)
+        z = np.ascontiguousarray(z, dtype=np.uint64)
+        ny = np.ascontiguousarray(ny, dtype=np.int32)
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        if not (x.shape == z.shape == ny.shape == a.shape):
+            raise ValueError("rotation arrays differ in length")
+        _lib.check(self._lib.vqe_apply_pauli_rotations(self.handle, int(x.shape[0]), _ptr(x), _ptr(z), _ptr(ny), _ptr(a)))
+
+    def apply_gates(self, kinds, q0, q1, angles):
+        k = np.ascontiguousarray(kinds, dtype=np.int32)
+        a0 = np.ascontiguousarray(q0, dtype=np.int32)
+        a1 = np.ascontiguousarray(q1, dtype=np.int32)
+        an = np.ascontiguousarray(angles, dtype=np.float64)
+        _lib.check(self._lib.vqe_apply_gates(self.handle, int(k.shape[0]), _ptr(k), _ptr(a0), _ptr(a1), _ptr(an)))
+
+    def apply_exp(self, packed: PackedTerms, theta: float):
+        """psi <- exp(theta * A) psi (exact exponential of the whole generator)."""
+        _lib.check(self._lib.vqe_apply_exp_paulisum(self.handle, len(packed), _ptr(packed.x), _ptr(packed.z),
+                                                    _ptr(packed.ny), _ptr(packed.cre), _ptr(packed.cim), float(theta)))
+
+    # -- observables ---------------------------------------------------------
+    def paulisum(self, operator) -> PauliSum:
+        """Lower + upload ``operator`` once; cached per object identity."""
+        key = id(operator)
+        hit = self._ps_cache.get(key)
+        if hit is not None and hit[0]() is operator:
+            return hit[1]
+        packed = operator if isinstance(operator, PackedTerms) else pack_operator(operator, with_constant=True)
+        ps = PauliSum(self, packed)
+        try:
+            self._ps_cache[key] = (weakref.ref(operator), ps)
+        except TypeError:
+            pass
+        if len(self._ps_cache) > 64:
+            self._ps_cache.pop(next(iter(self._ps_cache)))
+        return ps
+
+    def expectation(self, ps: PauliSum, buf=BUF_PSI) -> complex:
+        out = (C.c_double * 2)()
+        _lib.check(self._lib.vqe_expectation(self.handle, buf, ps.handle, out))
+        return complex(out[0], out[1])
+
+    def apply_paulisum(self, ps: PauliSum, dst=BUF_SIGMA, src=BUF_PSI):
+        _lib.check(self._lib.vqe_apply_paulisum(self.handle, dst, src, ps.handle))
+
+    def pool_overlaps(self, pool: PackedTerms, bra=BUF_SIGMA, ket=BUF_PSI):
+        """-> complex array, out[k] = <bra| A_k |ket> for every pool operator."""
+        n_ops = int(pool.offsets.shape[0]) - 1
+        out = np.zeros(n_ops, dtype=np.complex128)
+        _lib.check(self._lib.vqe_pool_overlaps(self.handle, bra, ket, n_ops, _ptr(pool.offsets), _ptr(pool.x),
+                                               _ptr(pool.z), _ptr(pool.ny), _ptr(pool.cre), _ptr(pool.cim), _ptr(out)))
+        return out
+
+    # -- reductions ----------------------------------------------------------
+    def norm2(self, buf=BUF_PSI) -> float:
+        out = C.c_double()
+        _lib.check(self._lib.vqe_norm2(self.handle, buf, C.byref(out)))
+        return out.value
+
+    def inner(self, a, b) -> complex:
+        out = (C.c_double * 2)()
+        _lib.check(self._lib.vqe_inner(self.handle, a, b, out))
+        return complex(out[0], out[1])
+
+    def overlap_host(self, vec, buf=BUF_PSI) -> complex:
+        v = np.ascontiguousarray(np.asarray(vec, dtype=np.complex128).reshape(-1))
+        out = (C.c_double * 2)()
+        _lib.check(self._lib.vqe_overlap_host(self.handle, buf, _ptr(v), out))
+        return complex(out[0], out[1])
+
+    # -- bookkeeping ---------------------------------------------------------
+    def synchronize(self):
+        _lib.check(self._lib.vqe_synchronize(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.vqe_launch_count(self.handle))
+
+    def profile(self, on: bool):
+        _lib.check(self._lib.vqe_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self, which: int, reset=False):
+        ms, n = C.c_double(), C.c_uint64()
+        _lib.check(self._lib.vqe_profile_read(self.handle, which, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, n.value
+
+    def buffer_ptr(self, buf=BUF_PSI):
+        p, n = C.c_void_p(), C.c_uint64()
+        _lib.check(self._lib.vqe_buffer_ptr(self.handle, buf, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+
+_ENGINES = {}
+
+
+def get_engine(n_qubits: int, device: int = 0) -> Engine:
+    """Process-wide engine per (n_qubits, device): the state buffers are reused
+    across the thousands of objective evaluations of one optimisation."""
+    key = (int(n_qubits), int(device))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = Engine(*key)
+        _ENGINES[key] = eng
+    return eng
+
+
+def release_engines():
+    _ENGINES.clear()

@@ -1,0 +1,203 @@
+"""GPU parity: every C-ABI entry point against the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+from oracle import statevector_oracle as orc
+from tests.helpers import Ham, T, random_antihermitian, random_hermitian, random_pauli, random_state
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def engines(gpu_required):
+    from openvqe_b200.engine import Engine
+    cache = {}
+
+    def get(n):
+        if n not in cache:
+            cache[n] = Engine(n)
+        return cache[n]
+    return get
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 11, 12, 13, 15, 18])
+def test_pauli_rotations_match_oracle(engines, n):
+    from openvqe_b200.lowering import term_masks
+    rng = np.random.default_rng(100 + n)
+    eng = engines(n)
+    psi = random_state(rng, n)
+    eng.set_state(psi)
+    xs, zs, nys, angs = [], [], [], []
+    ref = psi.copy()
+    for k in range(40):
+        op, qb = random_pauli(rng, n, max_weight=min(n, 6))
+        if k % 7 == 3:
+            op = "Z" * len(qb)  # diagonal rotations
+        x, z, ny = term_masks(op, qb, n)
+        a = float(rng.uniform(-1, 1))
+        xs.append(x); zs.append(z); nys.append(ny); angs.append(a)
+        ref = orc.pauli_rotation(ref, x, z, ny, a)
+    eng.apply_rotations(xs, zs, nys, angs)
+    got = eng.get_state()
+    assert np.max(np.abs(got - ref)) < TOL
+    assert abs(eng.norm2() - 1.0) < 1e-12
+
+
+def test_same_xmask_runs_and_zero_angles(engines):
+    """8 strings of a JW double excitation share one X-mask: applied as one register-resident run."""
+    from openvqe_b200.lowering import term_masks
+    n = 10
+    rng = np.random.default_rng(7)
+    eng = engines(n)
+    psi = random_state(rng, n)
+    eng.set_state(psi)
+    ref = psi.copy()
+    xs, zs, nys, angs = [], [], [], []
+    for op in ["XXXY", "XXYX", "XYXX", "YXXX", "YYYX", "YYXY", "YXYY", "XYYY"]:
+        full = op[0] + "ZZ" + op[1] + op[2] + "Z" + op[3]
+        qb = [1, 2, 3, 4, 6, 7, 8]
+        x, z, ny = term_masks(full, qb, n)
+        a = float(rng.uniform(-0.3, 0.3))
+        xs.append(x); zs.append(z); nys.append(ny); angs.append(a)
+        ref = orc.pauli_rotation(ref, x, z, ny, a)
+    xs.append(xs[0]); zs.append(zs[0]); nys.append(nys[0]); angs.append(0.0)  # exact identity
+    eng.apply_rotations(xs, zs, nys, angs)
+    assert np.max(np.abs(eng.get_state() - ref)) < TOL
+
+
+def test_structural_zeros_stay_exact(engines):
+    """Amplitudes outside the reachable sector must remain exactly 0.0."""
+    from openvqe_b200.lowering import term_masks
+    n = 8
+    eng = engines(n)
+    eng.set_basis_state(0b11000000)
+    x, z, ny = term_masks("XZY", [1, 2, 3], n)
+    eng.apply_rotations([x], [z], [ny], [0.37])
+    got = eng.get_state()
+    nz = np.nonzero(got)[0].tolist()
+    assert nz == sorted([0b11000000, 0b11000000 ^ x])
+
+
+@pytest.mark.parametrize("n", [2, 4, 9, 12, 14])
+def test_gates_match_oracle(engines, n):
+    from openvqe_b200.engine import GATE_KINDS
+    rng = np.random.default_rng(200 + n)
+    eng = engines(n)
+    psi = random_state(rng, n)
+    eng.set_state(psi)
+    gates = []
+    for _ in range(60):
+        name = str(rng.choice(["X", "H", "RX", "RY", "RZ", "CNOT"]))
+        if name == "CNOT" and n >= 2:
+            c, t = rng.choice(n, size=2, replace=False).tolist()
+            gates.append(("CNOT", [c, t], None))
+        elif name != "CNOT":
+            gates.append((name, [int(rng.integers(n))], float(rng.uniform(-3, 3))))
+    ref = orc.apply_gates(psi, n, gates)
+    eng.apply_gates([GATE_KINDS[g[0]] for g in gates], [g[1][0] for g in gates],
+                    [g[1][1] if len(g[1]) > 1 else 0 for g in gates], [g[2] or 0.0 for g in gates])
+    assert np.max(np.abs(eng.get_state() - ref)) < TOL
+
+
+@pytest.mark.parametrize("n,nterms", [(1, 3), (3, 10), (6, 60), (10, 200), (12, 400), (14, 300), (16, 100)])
+def test_expectation_matches_oracle(engines, n, nterms):
+    rng = np.random.default_rng(300 + n)
+    eng = engines(n)
+    psi = random_state(rng, n)
+    eng.set_state(psi)
+    ham = random_hermitian(rng, n, nterms, max_weight=min(n, 8), const=0.37)
+    ps = eng.paulisum(ham)
+    got = eng.expectation(ps)
+    ref = orc.expectation(psi, ham)
+    assert abs(got.real - ref) < 1e-11
+    assert abs(got.imag) < 1e-11
+
+
+def test_expectation_complex_coefficients(engines):
+    n = 7
+    rng = np.random.default_rng(5)
+    eng = engines(n)
+    psi = random_state(rng, n)
+    eng.set_state(psi)
+    op = random_antihermitian(rng, n, 30)
+    got = eng.expectation(eng.paulisum(op))
+    ref = np.vdot(psi, orc.apply_pauli_sum(psi, op))
+    assert abs(got - ref) < 1e-11
+
+
+@pytest.mark.parametrize("n,nterms", [(2, 4), (5, 30), (10, 150), (12, 300), (13, 200), (15, 80)])
+def test_apply_paulisum_matches_oracle(engines, n, nterms):
+    from openvqe_b200.engine import BUF_SIGMA
+    rng = np.random.default_rng(400 + n)
+    eng = engines(n)
+    psi = random_state(rng, n)
+    eng.set_state(psi)
+    ham = random_hermitian(rng, n, nterms, max_weight=min(n, 8), const=-1.25)
+    eng.apply_paulisum(eng.paulisum(ham))
+    got = eng.get_state(BUF_SIGMA)
+    ref = orc.apply_pauli_sum(psi, ham)
+    assert np.max(np.abs(got - ref)) < 1e-11
+
+
+@pytest.mark.parametrize("n,npool", [(3, 5), (8, 60), (12, 120), (13, 40), (15, 30)])
+def test_pool_overlaps_match_oracle(engines, n, npool):
+    from openvqe_b200.engine import BUF_SIGMA
+    from openvqe_b200.lowering import pack_pool
+    rng = np.random.default_rng(500 + n)
+    eng = engines(n)
+    psi = random_state(rng, n)
+    eng.set_state(psi)
+    ham = random_hermitian(rng, n, 50, max_weight=min(n, 6))
+    eng.apply_paulisum(eng.paulisum(ham))
+    pool = []
+    for k in range(npool):
+        if k % 9 == 4:
+            pool.append(Ham(n, [T(0.0, "X", [0])]))  # identically-zero operator stays in the pool
+        else:
+            pool.append(random_antihermitian(rng, n, int(rng.integers(1, 9)), max_weight=min(n, 4)))
+    got = eng.pool_overlaps(pack_pool(pool))
+    sig = orc.apply_pauli_sum(psi, ham)
+    ref = np.array([np.vdot(sig, orc.apply_pauli_sum(psi, op)) for op in pool])
+    assert np.max(np.abs(got - ref)) < 1e-11
+    assert got[4] == 0.0
+
+
+@pytest.mark.parametrize("n", [4, 8, 12])
+def test_exact_exponential_matches_expm_multiply(engines, n):
+    from openvqe_b200.lowering import pack_operator
+    rng = np.random.default_rng(600 + n)
+    eng = engines(n)
+    psi = random_state(rng, n)
+    # non-commuting anti-Hermitian generator -> Taylor path
+    gen = random_antihermitian(rng, n, 6, max_weight=min(n, 4))
+    eng.set_state(psi)
+    eng.apply_exp(pack_operator(gen), 0.8)
+    ref = orc.fermionic_adapt_state(psi, [gen], [0.8])
+    assert np.max(np.abs(eng.get_state() - ref)) < 1e-11
+    # commuting strings (same string twice + a disjoint one) -> rotation path
+    gen2 = Ham(n, [T(0.3j, "XY", [0, 1]), T(-0.7j, "Z", [n - 1]), T(0.2j, "XY", [0, 1])])
+    eng.set_state(psi)
+    eng.apply_exp(pack_operator(gen2), -1.1)
+    ref2 = orc.fermionic_adapt_state(psi, [gen2], [-1.1])
+    assert np.max(np.abs(eng.get_state() - ref2)) < 1e-11
+
+
+def test_overlap_and_inner(engines):
+    n = 9
+    rng = np.random.default_rng(11)
+    eng = engines(n)
+    a, b = random_state(rng, n), random_state(rng, n)
+    eng.set_state(a)
+    assert abs(eng.overlap_host(b) - np.vdot(b, a)) < 1e-12
+
+
+def test_error_paths(engines):
+    from openvqe_b200._lib import VQEError
+    eng = engines(3)
+    with pytest.raises(VQEError):
+        eng.set_basis_state(8)
+    with pytest.raises(VQEError):
+        eng.apply_rotations([16], [0], [0], [0.1])  # mask outside the register
+    with pytest.raises(VQEError):
+        eng.apply_rotations([1], [1], [0], [0.1])  # ny inconsistent with masks
