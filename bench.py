@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- UCC energy evaluations per second on the 24-qubit (C4-scale) workload.
+
+A "step" is ONE energy evaluation E(theta) of the Trotterised UCCSD ansatz: |HF> -> 14 112 Pauli rotations
+(1 818 generators) -> <H> over 14 905 Pauli terms in 2 767 X-mask groups, on a 2^24 complex128 state (268 MB,
+larger than the 126 MB L2, so nothing is L2-resident between sweeps).  theta changes every step.
+
+  value   evaluations/s with the Hamiltonian and rotation program resident in HBM (only the angles and the
+          16-byte result cross PCIe), timed with CUDA events on the engine's stream.
+  e2e     the same metric through the reference-facing call EnergyUCC.ucc_action(theta, H, generators, hf)
+          with host objects: lowering (cached), H2D of the operation descriptors, D2H of the energy, every step.
+  N > 1   below 33 qubits the path shards as independent energy evaluations: every rank
+          evaluates its own theta on its own GPU, no data-path collective ("weak" scaling).
+
+`--impl reference` times the CPU port of the reference path (oracle/c, OpenMP over all host cores) on a bounded
+sample of the same workload and scales it to one evaluation.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C4-scale 24-qubit UCCSD energy evaluation (H12/STO-3G stand-in for H2O/6-31G active space): " \
+           "14112 Pauli rotations + <H> over 14905 terms / 2767 X-mask groups"
+
+
+def load_workload():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "h12_sto3g_24q.npz"))
+    w = {k: z[k] for k in z.files}
+    w["n"] = int(w["n"])
+    w["hf_init_sp"] = int(w["hf_init_sp"])
+    w["meta"] = json.loads(str(w["meta"]))
+    return w
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            p = [v.strip() for v in line.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class Packed:
+    pass
+
+
+def packed_from(w, prefix):
+    p = Packed()
+    p.x = np.ascontiguousarray(w[prefix + "_x"], dtype=np.uint64)
+    p.z = np.ascontiguousarray(w[prefix + "_z"], dtype=np.uint64)
+    p.ny = np.ascontiguousarray(w[prefix + "_ny"], dtype=np.int32)
+    if prefix == "ham":
+        p.cre = np.ascontiguousarray(w["ham_cre"], dtype=np.float64)
+        p.cim = np.zeros_like(p.cre)
+    return p
+
+
+def thetas_for(w, n_steps, rank):
+    """A different parameter vector every step (MP2 amplitudes, scaled): nothing can be cached."""
+    base = np.asarray(w["theta_mp2"], dtype=np.float64)
+    n_gen = int(w["rot_owner"].max()) + 1
+    base = np.resize(base, n_gen)
+    base = np.where(base == 0.0, 0.01, base)
+    return [base * (1.0 + 0.003 * (s + 1) + 0.0007 * rank) for s in range(n_steps)]
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(w, n_rot_sample=48, n_term_sample=96):
+    """Time the CPU port on a bounded sample and scale to one full evaluation."""
+    from oracle import c_oracle
+    n = w["n"]
+    rot, ham = packed_from(w, "rot"), packed_from(w, "ham")
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[w["hf_init_sp"]] = 1.0
+    th = thetas_for(w, 1, 0)[0]
+    angles = th[w["rot_owner"]] * w["rot_c"]
+    # spread the sample over the program so that it sees the same mix of X-masks
+    ridx = np.linspace(0, len(angles) - 1, n_rot_sample).astype(int)
+    tidx = np.linspace(0, len(ham.x) - 1, n_term_sample).astype(int)
+    c_oracle.apply_rotations(psi, n, rot.x[ridx[:2]], rot.z[ridx[:2]], rot.ny[ridx[:2]], angles[ridx[:2]])  # warm-up
+    t0 = time.perf_counter()
+    c_oracle.apply_rotations(psi, n, rot.x[ridx], rot.z[ridx], rot.ny[ridx], angles[ridx])
+    t_rot = (time.perf_counter() - t0) / n_rot_sample
+    t0 = time.perf_counter()
+    c_oracle.expectation(psi, n, ham.x[tidx], ham.z[tidx], ham.ny[tidx], ham.cre[tidx], ham.cim[tidx])
+    t_term = (time.perf_counter() - t0) / n_term_sample
+    est = len(angles) * t_rot + len(ham.x) * t_term
+    return {"seconds_per_eval": est, "t_rotation_s": t_rot, "t_term_s": t_term, "cores": c_oracle.threads(),
+            "sample": "%d of %d rotations + %d of %d Hamiltonian terms at 24 qubits (one 2^24 sweep each), scaled "
+                      "linearly to one evaluation" % (n_rot_sample, len(angles), n_term_sample, len(ham.x))}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    w = load_workload()
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(w, 8, 8)
+    ests, last = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = cpu_sample(w, 24, 48)
+        ests.append(last["seconds_per_eval"])
+    sec = float(np.mean(ests))
+    val = 1.0 / sec
+    line = {"impl": "reference", "metric": "ucc_energy_evals_per_s", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",
+            "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": last["cores"], "kind": "port",
+                             "sample": "per step: " + last["sample"] + "; CPU port = oracle/c/vqe_oracle.c (OpenMP), the reference's own myQLM simulator is "
+                               "not installable here", "wall_s": time.perf_counter() - t0},
+            "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def build_host_objects(w):
+    """Duck-typed qat objects (what the reference hands to EnergyUCC.ucc_action) from the packed fixture."""
+    n = w["n"]
+
+    class Term:
+        __slots__ = ("coeff", "op", "qbits")
+
+        def __init__(self, c, op, qb):
+            self.coeff, self.op, self.qbits = c, op, qb
+
+    class Ham:
+        def __init__(self, terms, const=0.0):
+            self.nbqbits, self.terms, self.constant_coeff = n, terms, const
+
+    def term(x, z, c):
+        op, qb = [], []
+        for q in range(n):
+            b = n - 1 - q
+            xb, zb = (int(x) >> b) & 1, (int(z) >> b) & 1
+            if xb or zb:
+                op.append("Y" if xb and zb else ("X" if xb else "Z"))
+                qb.append(q)
+        return Term(float(c), "".join(op), qb)
+
+    hterms, const = [], 0.0
+    for x, z, c in zip(w["ham_x"], w["ham_z"], w["ham_cre"]):
+        if x == 0 and z == 0:
+            const += float(c)
+        else:
+            hterms.append(term(x, z, c))
+    ham = Ham(hterms, const)
+    gens = [[] for _ in range(int(w["rot_owner"].max()) + 1)]
+    for x, z, c, o in zip(w["rot_x"], w["rot_z"], w["rot_c"], w["rot_owner"]):
+        gens[int(o)].append(term(x, z, c))
+    return ham, [Ham(t) for t in gens]
+
+
+def run_ours(args, rank, world, local_rank):
+    from openvqe_b200.engine import Engine
+    from openvqe_b200.lowering import PackedTerms
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = load_workload()
+    n = w["n"]
+    S = 16.0 * (1 << n)
+    eng = Engine(n, device=local_rank)
+    hp = packed_from(w, "ham")
+    ps = eng.paulisum(PackedTerms(n, hp.x, hp.z, hp.ny, hp.cre, hp.cim))
+    rot = packed_from(w, "rot")
+    owner, rc = w["rot_owner"], np.asarray(w["rot_c"], dtype=np.float64)
+    hf = w["hf_init_sp"]
+
+    def step(theta):
+        eng.set_basis_state(hf)
+        eng.apply_rotations(rot.x, rot.z, rot.ny, theta[owner] * rc)
+        return eng.expectation(ps).real
+
+    def barrier():
+        eng.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ths = thetas_for(w, args.warmup + args.steps, rank)
+    for th in ths[:args.warmup]:
+        step(th)
+    # ---- timed: resident inputs -------------------------------------------------------------
+    for k in range(4):
+        eng.profile_read(k, reset=True)
+    eng.profile(True)
+    eng.transfer_bytes(reset=True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    l0 = eng.launch_count
+    eng.timer_begin()
+    energies = [step(th) for th in ths[args.warmup:]]
+    ms = eng.timer_end()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count - l0
+    ms = max_over_ranks(ms)
+    prep_ms, prep_n = eng.profile_read(0)
+    exp_ms, exp_n = eng.profile_read(1)
+    eng.profile(False)
+    value = world * args.steps / (ms / 1e3)
+    # ---- e2e through the reference-facing API ------------------------------------------------
+    from openvqe_b200.ucc_family.get_energy_ucc import EnergyUCC
+    from openvqe_b200 import engine as engine_mod
+    engine_mod._ENGINES[(n, local_rank)] = eng  # the API uses the process-wide engine of this device
+    ham_obj, gen_objs = build_host_objects(w)
+    api = EnergyUCC()
+    import openvqe_b200._hotpath as hot
+    hot_energy = lambda th: hot.ucc_energy(th, ham_obj, gen_objs, hf, device=local_rank)
+    hot_energy(ths[0])  # first call lowers + uploads H (cached afterwards, like the reference's one-time set-up)
+    e_check = hot_energy(ths[args.warmup])
+    assert abs(e_check - energies[0]) < 1e-9, (e_check, energies[0])
+    eng.transfer_bytes(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    eng.timer_begin()
+    log = []
+    for th in ths[args.warmup:]:
+        if local_rank == 0 and world == 1:
+            api.ucc_action(th, ham_obj, gen_objs, hf, log)
+        else:
+            hot_energy(th)
+    ms_e2e = eng.timer_end()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    h2d, d2h = eng.transfer_bytes()
+    ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))
+    e2e_value = world * args.steps / (ms_e2e / 1e3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    peak, peak_src = peaks()
+    n_rot, n_groups = len(rot.x), ps.n_groups
+    prep_alg = n_rot * 2.0 * S * args.steps      # 2*S per rotation
+    exp_alg = n_groups * S * args.steps          # S per X-mask group
+    prep = {"kernel": "k_tile_ops", "bound": "hbm", "achieved": prep_alg / (prep_ms / 1e3) / 1e9, "peak": peak,
+            "unit": "GB/s", "launches_per_step": prep_n / args.steps, "ms_per_step": prep_ms / args.steps,
+            "algorithmic_bytes_per_launch": prep_alg / max(prep_n, 1), "physical_bytes_per_launch": 2.0 * S,
+            "physical_gbs": prep_n * 2.0 * S / (prep_ms / 1e3) / 1e9, "rotations_per_pass": n_rot * args.steps / max(prep_n, 1)}
+    expk = {"kernel": "k_tile_expect", "bound": "hbm", "achieved": exp_alg / (exp_ms / 1e3) / 1e9, "peak": peak,
+            "unit": "GB/s", "launches_per_step": exp_n / args.steps, "ms_per_step": exp_ms / args.steps,
+            "algorithmic_bytes_per_launch": exp_alg / max(exp_n, 1), "physical_bytes_per_launch": S,
+            "physical_gbs": exp_n * S / (exp_ms / 1e3) / 1e9, "groups_per_pass": n_groups * args.steps / max(exp_n, 1)}
+    dom, other = (prep, expk) if prep_ms >= exp_ms else (expk, prep)
+    roofline = dict(dom)
+    roofline["frac"] = dom["achieved"] / peak
+    roofline["traffic"] = None
+    roofline["peak_source"] = peak_src
+    roofline["share_of_step"] = dom["ms_per_step"] / (ms / args.steps)
+    other = dict(other)
+    other["frac"] = other["achieved"] / peak
+    line = {"metric": "ucc_energy_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "qubits": n, "state_bytes": S, "l2_policy": "state (268 MB) larger than L2 (126 MB)",
+                       "parallelism": "replicas: independent energy evaluations per GPU" if world > 1 else "1 GPU",
+                       "energy_first_step": energies[0]},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d / args.steps,
+                    "d2h_bytes_per_step": d2h / args.steps, "ms_per_step": ms_e2e / args.steps,
+                    "api": "openvqe_b200.ucc_family.get_energy_ucc.EnergyUCC.ucc_action"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_other": other}
+    if world == 1 and not args.no_cpu:
+        cb = cpu_sample(w)
+        line["cpu_baseline"] = {"value": 1.0 / cb["seconds_per_eval"], "unit": "evals/s", "cores": cb["cores"],
+                                "kind": "port", "sample": cb["sample"] + "; CPU port = oracle/c/vqe_oracle.c (OpenMP)"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,10 +57,17 @@ int vqe_n_qubits(const vqe_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
 uint64_t vqe_launch_count(const vqe_ctx* ctx);
 /* cumulative device time (ms) of the named kernel class since the last reset, measured with CUDA
- * events on the context's stream when profiling is enabled (bench.py roofline leg).
+ * events recorded around every launch on the context's stream while profiling is enabled (no extra
+ * synchronisation; bench.py roofline leg).
  * which: 0 = state-preparation tile kernel, 1 = expectation kernel, 2 = pauli-sum apply, 3 = pool sweep */
 int vqe_profile_enable(vqe_ctx* ctx, int on);
 int vqe_profile_read(vqe_ctx* ctx, int which, double* ms_total, uint64_t* launches, int reset);
+
+/* Device-side step timer: CUDA events recorded on the context's stream (bench.py times steps with it). */
+int vqe_timer_begin(vqe_ctx* ctx);
+int vqe_timer_end(vqe_ctx* ctx, double* ms);
+/* bytes this context has copied host->device / device->host so far (bench.py e2e accounting) */
+int vqe_transfer_bytes(vqe_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);
 
 /* |psi> = |index>.  Replaces the X-gate Hartree-Fock preparation
  * (openvqe/adapt/fermionic_adapt_vqe.py:183-213, get_energy_qucc.py:40-45). */

@@ -140,19 +140,26 @@ def pool_overlaps(engine, hamiltonian_sp, pool_ops):
     return engine.pool_overlaps(pool, bra=BUF_SIGMA, ket=BUF_PSI)
 
 
-def snap_ties(values, rel=1e-12):
-    """Gradients that are equal in exact arithmetic (spin-complement partners carry
-    +-g) may differ in the last bits after a parallel
-    reduction.  The reference's selection uses float equality with ties resolved to
-    the lowest pool index, so magnitudes within ``rel`` of each other are snapped to
-    the value of their lowest-index member before selection.  Signs are kept."""
-    vals = list(values)
+ZERO_TOL = 1e-14  # Hartree; far below the rounding noise of a 2^n-term fp64 reduction of O(1) values
+
+
+def snap_ties(values, rel=1e-12, zero_tol=ZERO_TOL):
+    """Make the selection robust against reduction-order noise (documented deviation):
+
+    * The reference drops EXACT zeros before sorting (sorted_gradient.py:32,53); in its scipy path
+      symmetry-forbidden gradients are exactly 0.0 and a few more cancel exactly.  A parallel reduction
+      may leave ~1e-17 there, so |g| <= ``zero_tol`` is snapped to 0.0.
+    * Gradients that are equal in exact arithmetic (spin-complement partners carry +-g, SURVEY.md
+      Appendix B item 14) may differ in the last bits.  The reference's selection uses float equality
+      with ties resolved to the lowest pool index, so magnitudes within ``rel`` of each other are
+      snapped to the value of their lowest-index member.  Signs are kept."""
+    vals = [0.0 if abs(v) <= zero_tol else v for v in values]
     order = sorted(range(len(vals)), key=lambda k: -abs(vals[k]))
     i = 0
     while i < len(order):
         j = i + 1
         top = abs(vals[order[i]])
-        while j < len(order) and top - abs(vals[order[j]]) <= rel * top and top > 0:
+        while j < len(order) and top > 0 and top - abs(vals[order[j]]) <= rel * top:
             j += 1
         if j - i > 1:
             members = sorted(order[i:j])

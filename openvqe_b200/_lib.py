@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libvqe_b200.so")
 # every symbol include/vqe_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "vqe_last_error", "vqe_version", "vqe_device_count", "vqe_create", "vqe_destroy", "vqe_n_qubits",
-    "vqe_launch_count", "vqe_profile_enable", "vqe_profile_read", "vqe_set_basis_state", "vqe_set_state",
+    "vqe_launch_count", "vqe_profile_enable", "vqe_profile_read", "vqe_timer_begin", "vqe_timer_end",
+    "vqe_transfer_bytes", "vqe_set_basis_state", "vqe_set_state",
     "vqe_get_state", "vqe_copy_buffer", "vqe_apply_pauli_rotations", "vqe_apply_gates",
     "vqe_paulisum_create", "vqe_paulisum_destroy", "vqe_paulisum_groups", "vqe_paulisum_passes",
     "vqe_expectation", "vqe_apply_paulisum", "vqe_pool_overlaps", "vqe_apply_exp_paulisum",
@@ -52,6 +53,9 @@ def load():
         "vqe_launch_count": (u64, [vp]),
         "vqe_profile_enable": (C.c_int, [vp, C.c_int]),
         "vqe_profile_read": (C.c_int, [vp, C.c_int, P(dbl), P(u64), C.c_int]),
+        "vqe_timer_begin": (C.c_int, [vp]),
+        "vqe_timer_end": (C.c_int, [vp, P(dbl)]),
+        "vqe_transfer_bytes": (C.c_int, [vp, P(u64), P(u64), C.c_int]),
         "vqe_set_basis_state": (C.c_int, [vp, u64]),
         "vqe_set_state": (C.c_int, [vp, C.c_int, vp]),
         "vqe_get_state": (C.c_int, [vp, C.c_int, vp]),

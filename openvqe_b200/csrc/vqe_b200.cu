@@ -680,26 +680,56 @@ struct vqe_ctx {
     uint64_t launches = 0;
     bool profiling = false;
     KernelProf prof[4];
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // step timer
+    std::vector<cudaEvent_t> ev_pool;           // recycled events
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
 };
 
+// Non-intrusive per-kernel timing: when profiling is on, every kernel of a class is bracketed by two
+// events from a pool (no synchronisation); vqe_profile_read resolves them after the fact.
 struct ProfScope {
     vqe_ctx* c;
     int which;
-    ProfScope(vqe_ctx* c_, int w) : c(c_), which(w) {
-        if (c->profiling) cudaEventRecord(c->ev0, c->stream);
-    }
-    ~ProfScope() {
-        c->prof[which].launches++;
-        if (c->profiling) {
-            cudaEventRecord(c->ev1, c->stream);
-            cudaEventSynchronize(c->ev1);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-            c->prof[which].ms += ms;
-        }
-    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(vqe_ctx* c_, int w);
+    ~ProfScope();
 };
+static cudaEvent_t take_event(vqe_ctx* c) {
+    if (!c->ev_pool.empty()) {
+        cudaEvent_t e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+ProfScope::ProfScope(vqe_ctx* c_, int w) : c(c_), which(w) {
+    if (c->profiling) {
+        e0 = take_event(c);
+        e1 = take_event(c);
+        cudaEventRecord(e0, c->stream);
+    }
+}
+ProfScope::~ProfScope() {
+    c->prof[which].launches++;
+    if (c->profiling) {
+        cudaEventRecord(e1, c->stream);
+        c->ev_pending.push_back({which, {e0, e1}});
+    }
+}
+static void resolve_profile(vqe_ctx* c) {
+    if (c->ev_pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& p : c->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.second.first, p.second.second) == cudaSuccess) c->prof[p.first].ms += ms;
+        c->ev_pool.push_back(p.second.first);
+        c->ev_pool.push_back(p.second.second);
+    }
+    c->ev_pending.clear();
+}
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -830,6 +860,8 @@ extern "C" void vqe_destroy(vqe_ctx* c) {
     if (c->h_result) cudaFreeHost(c->h_result);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    resolve_profile(c);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -843,9 +875,34 @@ extern "C" int vqe_profile_enable(vqe_ctx* c, int on) {
 }
 extern "C" int vqe_profile_read(vqe_ctx* c, int which, double* ms_total, uint64_t* launches, int reset) {
     if (!c || which < 0 || which > 3) return fail(VQE_ERR_INVALID, "bad profile slot");
+    resolve_profile(c);
     if (ms_total) *ms_total = c->prof[which].ms;
     if (launches) *launches = c->prof[which].launches;
     if (reset) c->prof[which] = KernelProf();
+    return VQE_OK;
+}
+
+extern "C" int vqe_timer_begin(vqe_ctx* c) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    return VQE_OK;
+}
+extern "C" int vqe_timer_end(vqe_ctx* c, double* ms) {
+    if (!c || !ms) return fail(VQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+    *ms = f;
+    return VQE_OK;
+}
+extern "C" int vqe_transfer_bytes(vqe_ctx* c, uint64_t* h2d, uint64_t* d2h, int reset) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    if (h2d) *h2d = c->h2d_bytes;
+    if (d2h) *d2h = c->d2h_bytes;
+    if (reset) c->h2d_bytes = c->d2h_bytes = 0;
     return VQE_OK;
 }
 
@@ -870,6 +927,7 @@ extern "C" int vqe_set_state(vqe_ctx* c, int b, const double* re_im) {
     CK(cudaSetDevice(c->device));
     int rc = ensure_buf(c, b);
     if (rc) return rc;
+    c->h2d_bytes += c->n_amp * sizeof(double2);
     CK(cudaMemcpyAsync(c->buf[b], re_im, c->n_amp * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return VQE_OK;
@@ -879,6 +937,7 @@ extern "C" int vqe_get_state(vqe_ctx* c, int b, double* re_im) {
     CK(cudaSetDevice(c->device));
     int rc = ensure_buf(c, b);
     if (rc) return rc;
+    c->d2h_bytes += c->n_amp * sizeof(double2);
     CK(cudaMemcpyAsync(re_im, c->buf[b], c->n_amp * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return VQE_OK;
@@ -1015,6 +1074,7 @@ static int run_ops(vqe_ctx* c, const std::vector<HostOp>& ops) {
     if (!mats.empty()) memcpy(c->h_stage + off_mats, mats.data(), mats.size() * sizeof(double));
     for (size_t p = 0; p < passes.size(); ++p)
         memcpy(c->h_stage + scat_off[p], passes[p].tp.scat.data(), passes[p].tp.scat.size() * sizeof(uint64_t));
+    c->h2d_bytes += total;
     CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
     for (size_t p = 0; p < passes.size(); ++p) {
         const Pass& ps = passes[p];
@@ -1350,6 +1410,7 @@ extern "C" int vqe_expectation(vqe_ctx* c, int b, const vqe_paulisum* ps, double
     }
     k_reduce_partials<<<1, 32, 0, c->stream>>>(c->d_partial, (int)total_blocks, 1, 1, c->d_result);
     c->launches++;
+    c->d2h_bytes += sizeof(double2);
     CK(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
@@ -1489,7 +1550,8 @@ extern "C" int vqe_pool_overlaps(vqe_ctx* c, int bra, int ket, int n_ops, const 
         memcpy(c->h_stage + off_ops, pops.data(), np * sizeof(DevPoolOp));
         memcpy(c->h_stage + off_terms, pterms.data(), pterms.size() * sizeof(DevPoolTerm));
         memcpy(c->h_stage + off_scat, tp.scat.data(), tp.scat.size() * sizeof(uint64_t));
-        CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += total;
+    CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
         TileGeom g;
         g.comp_mask = tp.comp_mask;
         g.n_tiles = tp.n_tiles;
@@ -1507,6 +1569,7 @@ extern "C" int vqe_pool_overlaps(vqe_ctx* c, int bra, int ket, int n_ops, const 
         }
         k_reduce_partials<<<(np + 127) / 128, 128, 0, c->stream>>>(c->d_partial, gx, np, np, c->d_result);
         c->launches++;
+        c->d2h_bytes += np * sizeof(double2);
         CK(cudaMemcpyAsync(c->h_result, c->d_result, np * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaGetLastError());
@@ -1526,6 +1589,7 @@ static int inner_bufs(vqe_ctx* c, const double2* a, const double2* b, double* ou
     k_inner<<<blocks, 256, 0, c->stream>>>(a, b, c->n_amp, c->d_partial);
     k_reduce_partials<<<1, 32, 0, c->stream>>>(c->d_partial, blocks, 1, 1, c->d_result);
     c->launches += 2;
+    c->d2h_bytes += sizeof(double2);
     CK(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());

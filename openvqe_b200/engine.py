@@ -157,6 +157,19 @@ class Engine:
         _lib.check(self._lib.vqe_profile_read(self.handle, which, C.byref(ms), C.byref(n), 1 if reset else 0))
         return ms.value, n.value
 
+    def timer_begin(self):
+        _lib.check(self._lib.vqe_timer_begin(self.handle))
+
+    def timer_end(self) -> float:
+        ms = C.c_double()
+        _lib.check(self._lib.vqe_timer_end(self.handle, C.byref(ms)))
+        return ms.value
+
+    def transfer_bytes(self, reset=False):
+        a, b = C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.vqe_transfer_bytes(self.handle, C.byref(a), C.byref(b), 1 if reset else 0))
+        return a.value, b.value
+
     def buffer_ptr(self, buf=BUF_PSI):
         p, n = C.c_void_p(), C.c_uint64()
         _lib.check(self._lib.vqe_buffer_ptr(self.handle, buf, C.byref(p), C.byref(n)))

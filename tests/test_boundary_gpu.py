@@ -1,0 +1,162 @@
+"""GPU parity of the reference-shaped entry points (openvqe_b200.ucc_family / .adapt) against
+(i) outputs of the unmodified reference modules stored in tests/golden (made by oracle/make_golden.py),
+(ii) the CPU oracle on the same inputs.  Tolerance for energies and gradients: 1e-10 Ha (north_star)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import statevector_oracle as orc
+from tests.helpers import FermiOp, Ham, T, ham_from_json, jw_excitation, load_golden, pool_from_json
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def h2(gpu_required):
+    fx = load_golden("h2_631g.json.gz")
+    fx["_ham"] = ham_from_json(fx["hamiltonian"])
+    return fx
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_c1b_h2_sto3g_uccsd_golden_hamiltonian(gpu_required):
+    """Config C1: 4-qubit H2/STO-3G UCCSD through EnergyUCC.ucc_action on the reference's golden Hamiltonian."""
+    from openvqe_b200.ucc_family.get_energy_ucc import EnergyUCC
+    g1 = load_golden("g1_h2_sto3g.json")
+    ham = Ham(4, [T(cr, op, qb) for cr, ci, op, qb in g1["terms"]], g1["constant"])
+    ops = [jw_excitation(4, [2], [0]), jw_excitation(4, [3], [1]), jw_excitation(4, [2, 3], [1, 0])]
+    e = EnergyUCC()
+    log = []
+    assert abs(e.ucc_action([0.0, 0.0, 0.0], ham, ops, 12, log) - (-1.0716472823)) < 1e-9
+    rng = np.random.default_rng(0)
+    for _ in range(64):
+        th = rng.uniform(-0.5, 0.5, 3).tolist()
+        assert abs(e.ucc_action(th, ham, ops, 12, log) - orc.ucc_action(th, ham, ops, 12)) < TOL
+    assert len(log) == 65  # every objective value is appended
+    it, res = quiet(e.get_energies, ham, ops, ops, 12, [0.01] * 3, [0.01] * 3, -1.10531794)
+    assert abs(it["minimum_energy_result1_guess"][0] - (-1.10531794)) < 1e-6  # UCCSD is exact for 2 electrons
+    assert res["len_op1"] == 3 and res["CNOT1"] == 2 * 2 * 4 + 8 * 6
+
+
+def test_ucc_action_matches_reference_outputs(h2):
+    from openvqe_b200.ucc_family.get_energy_ucc import EnergyUCC
+    ops = pool_from_json(8, h2["supccgsd_ansatz"])
+    e = EnergyUCC()
+    for case in h2["ucc_action"]:
+        assert abs(e.ucc_action(case["theta"], h2["_ham"], ops, h2["hf_init_sp"], []) - case["energy"]) < TOL
+    circ = e.prepare_state_ansatz(h2["_ham"], ops, h2["hf_init_sp"], h2["ucc_action"][1]["theta"])
+    from openvqe_b200.common_files.circuit import count
+    gc = h2["ucc_gate_counts"]
+    assert (count("CNOT", circ.ops), count("H", circ.ops), count("_2", circ.ops), count("_4", circ.ops)) == \
+        (gc["CNOT"], gc["H"], gc["_2"], gc["_4"])
+
+
+def test_quccsd_matches_reference_outputs(gpu_required):
+    from openvqe_b200.common_files.circuit import count
+    from openvqe_b200.ucc_family.get_energy_qucc import EnergyUCC
+    fx = load_golden("h4_sto3g.json.gz")
+    ham = ham_from_json(fx["hamiltonian"])
+    ops = [FermiOp(8, ex) for ex in fx["excitations"]]
+    e = EnergyUCC()
+    for case in fx["action_quccsd"]:
+        assert abs(e.action_quccsd(case["theta"], ham, ops, fx["hf_init_sp"], []) - case["energy"]) < TOL
+    circ = e.prepare_state_ansatz(ham, fx["hf_init_sp"], ops, fx["action_quccsd"][0]["theta"])
+    assert count("CNOT", circ.ops) == fx["cnot_count"] == 292
+    with pytest.raises(IndexError):  # fewer parameters than excitations: reference indexes list_theta[i]
+        e.action_quccsd([0.1], ham, ops, fx["hf_init_sp"], [])
+
+
+def test_fermionic_gradients_match_reference_outputs(h2):
+    from openvqe_b200.adapt import fermionic_adapt_vqe as fa
+    pool = pool_from_json(8, h2["spin_complement_gsd"])
+    psi = orc.basis_state(8, h2["hf_init_sp"])
+    lg, nrm, nd, ni = fa.return_gradient_list(pool, h2["_ham"], psi)
+    ref = h2["gradients_at_hf"]
+    assert np.abs(np.array(lg) - np.array(ref["list_grad"])).max() < TOL
+    assert [k for k, v in enumerate(lg) if v == 0] == [k for k, v in enumerate(ref["list_grad"]) if v == 0]
+    assert ni == ref["next_index"] == 38 and abs(nd - ref["next_deriv"]) < TOL and abs(nrm - ref["curr_norm"]) < TOL
+    ga = h2["gradients_at_ansatz"]
+    st = fa.prepare_adapt_state(psi, [pool[i] for i in ga["indices"]], ga["parameters"]).reshape(-1)
+    assert np.abs(st - (np.array(ga["state_re"]) + 1j * np.array(ga["state_im"]))).max() < 1e-12
+    lg2, nrm2, nd2, ni2 = fa.return_gradient_list(pool, h2["_ham"], st)
+    assert np.abs(np.array(lg2) - np.array(ga["list_grad"])).max() < TOL
+    assert ni2 == ga["next_index"]
+    assert abs(fa.compute_gradient_i(38, pool, psi, None, h2["_ham"]) - ref["next_deriv"]) < TOL
+
+
+def test_fermionic_adapt_loop_matches_reference_run(h2):
+    from openvqe_b200.adapt.fermionic_adapt_vqe import fermionic_adapt_vqe
+    pool = pool_from_json(8, h2["spin_complement_gsd"])
+    ham = h2["_ham"]
+    ham.get_matrix = lambda sparse=False: orc.sparse_matrix(ham).toarray()
+    ref_ket = orc.basis_state(8, h2["hf_init_sp"]).reshape(-1, 1)
+    it, res = quiet(fermionic_adapt_vqe, None, None, ref_ket, ham, pool, h2["hf_init_sp"], 1, h2["fci"],
+                    "COBYLA", 1e-6, "norm", 1e-2, 35)
+    ref = h2["fermionic_adapt_run"]
+    assert res["indices"] == ref["result"]["indices"] == [38, 32, 29, 23, 2]
+    for key in ("CNOTs", "Hadamard", "RX", "RY"):
+        assert it[key] == ref["iterations"][key]
+    assert res["Number_CNOT_gates"] == ref["result"]["Number_CNOT_gates"]
+    # same scipy, same objective to 1e-13: trajectories agree far below the optimiser tolerance (1e-6)
+    assert np.abs(np.array(it["energies"]) - np.array(ref["iterations"]["energies"])).max() < 1e-8
+    assert np.abs(np.array(it["norms"]) - np.array(ref["iterations"]["norms"])).max() < 1e-5
+    assert np.abs(np.array(it["fidelity"]) - np.array(ref["iterations"]["fidelity"])).max() < 1e-6
+    assert abs(it["Max_gradients"][0] - ref["iterations"]["Max_gradients"][0]) < TOL
+
+
+def test_qubit_adapt_matches_reference_outputs(h2):
+    from openvqe_b200.adapt import qubit_adapt_vqe as qa
+    pool = pool_from_json(8, h2["qubit_pool_random_seed7"])
+    psi = orc.basis_state(8, h2["hf_init_sp"])
+    g = [qa.calculate_gradient(qa.term_to_matrix_sparse(op), psi, h2["_ham"]) for op in pool[:12]]
+    assert np.abs(np.array(g) - np.array(h2["qubit_gradients_at_hf"][:12])).max() < TOL
+    ga = h2["qubit_gradients_at_ansatz"]
+    st = qa.prepare_adapt_state(psi, [pool[i] for i in ga["indices"]], ga["parameters"]).reshape(-1)
+    assert np.abs(st - (np.array(ga["state_re"]) + 1j * np.array(ga["state_im"]))).max() < 1e-12
+    out = quiet(qa.qubit_adapt_vqe, h2["_ham"], None, psi.reshape(-1, 1), 8, pool, h2["hf_init_sp"], h2["fci"],
+                n_max_grads=1, adapt_conver="norm", adapt_thresh=1e-7, adapt_maxiter=4, tolerance_sim=1e-9,
+                method_sim="BFGS")
+    ref = h2["qubit_adapt_run"]["iterations_sim"]
+    assert out[2] == {} and out[1]["energies"] == []  # loop ended by adapt_maxiter: empty result dict
+    assert np.abs(np.array(out[0]["energies"]) - np.array(ref["energies"])).max() < 1e-8
+    assert np.abs(np.array(out[0]["norms"]) - np.array(ref["norms"])).max() < 1e-6
+    assert abs(out[0]["Max_gradient"][0] - ref["Max_gradient"][0]) < TOL
+    for key in ("CNOTs", "Hadamard", "RX", "RY"):
+        assert out[0][key] == ref[key]
+
+
+def test_h6_twelve_qubit_parity(gpu_required):
+    """Configs C2/C3 scale (12 qubits): gradients of fermionic and qubit pools, states, energies."""
+    from openvqe_b200 import _hotpath
+    from openvqe_b200.adapt import fermionic_adapt_vqe as fa
+    from openvqe_b200.engine import get_engine
+    fx = load_golden("h6_sto3g.json.gz")
+    ham = ham_from_json(fx["hamiltonian"])
+    st = np.array(fx["state"]["state_re"]) + 1j * np.array(fx["state"]["state_im"])
+    for name in ("uccgsd_subset", "spin_complement_gsd_subset"):
+        pool = pool_from_json(12, fx[name])
+        lg, nrm, nd, ni = fa.return_gradient_list(pool, ham, st)
+        ref = fx["gradients_" + name]
+        assert np.abs(np.array(lg) - np.array(ref["list_grad"])).max() < TOL
+        assert abs(nrm - ref["curr_norm"]) < 1e-9
+        # zero pattern: exact zeros of the reference are zeros here (|g| <= 1e-14 is snapped)
+        assert [k for k, v in enumerate(lg) if v == 0] == [k for k, v in enumerate(ref["list_grad"]) if abs(v) <= 1e-14]
+    eng = get_engine(12)
+    yx = pool_from_json(12, fx["yxxx_pool"])
+    eng.set_state(st)
+    gq = 2.0 * np.abs(_hotpath.pool_overlaps(eng, ham, yx))
+    assert np.abs(gq - np.array(fx["qubit_gradients"])).max() < TOL
+    gens = [pool_from_json(12, fx["uccgsd_subset"])[p] for p in fx["state"]["uccgsd_subset_positions"]]
+    st2 = fa.prepare_adapt_state(orc.basis_state(12, fx["hf_init_sp"]), gens, fx["state"]["parameters"]).reshape(-1)
+    assert np.abs(st2 - st).max() < 1e-12
+    ans = [Ham(12, [T(1j * t.coeff, t.op, t.qbits) for t in g.terms]) for g in gens]
+    for case in fx["ucc_action"]:
+        assert abs(fa.ucc_action(ham, ans, fx["hf_init_sp"], case["theta"]) - case["energy"]) < TOL
+    assert abs(_hotpath.basis_energy(ham, fx["hf_init_sp"]) - fx["hf_energy"]) < TOL
