@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvqe_b200.so")
+LIB_PATH = os.environ.get("VQE_B200_LIB") or os.path.join(_HERE, "csrc", "libvqe_b200.so")  # env: A/B testing of builds
 
 # every symbol include/vqe_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [

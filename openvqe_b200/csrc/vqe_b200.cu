@@ -65,7 +65,7 @@ extern "C" int vqe_device_count(void) {
 // ------------------------------------------------------------------------------------------
 // device structures
 // ------------------------------------------------------------------------------------------
-enum { OP_ROT = 0, OP_GATE1 = 1, OP_CNOT = 2 };
+enum { OP_ROT = 0, OP_GATE1 = 1, OP_CNOT = 2, OP_ROTF = 3 };
 
 struct DevOp {       // 64 bytes
     uint32_t lx;     // ROT: local X mask | GATE1: local bit mask | CNOT: local target mask
@@ -73,13 +73,13 @@ struct DevOp {       // 64 bytes
     uint64_t zout;   // ROT: Z mask outside the tile | CNOT: control mask outside the tile
     double c, s;     // ROT: cos, sin
     uint32_t k4;     // ROT: (ny + 3) & 3, the unit phase (-i) * i^ny = i^k4
-    uint32_t pad2;
+    uint32_t jmask;  // ROTF: bit j = parity(u_j & lz), u_j = index bits contributed by the j-th pair of a thread
     uint32_t kind;   // OP_*
     uint32_t hb;     // highest set bit of lx
     uint32_t run;    // ROT: number of consecutive ROT ops (starting here) sharing lx
     uint32_t mat;    // GATE1: index into the matrix array (8 doubles each)
     uint32_t nyodd;  // ROT: ny & 1
-    uint32_t pad;
+    uint32_t imag;   // ROTF: 1 when the unit phase is +-i (ny even)
 };
 
 struct TileGeom {
@@ -99,7 +99,7 @@ struct DevGroup {     // one X-mask group of a Pauli sum inside a pass
 struct DevTerm {      // 32 bytes
     uint64_t zout;
     uint32_t lz;
-    uint32_t pad;
+    uint32_t jmask;   // expectation: bit j = parity(u_j & lz) for the j-th pair (amplitude) of a thread
     double ar, ai;    // expectation: pair weight; apply: c_k * i^ny
 };
 
@@ -206,14 +206,27 @@ __global__ void k_reduce_partials(const double2* partial, int n_blocks, int stri
 // ------------------------------------------------------------------------------------------
 // tile load / store
 // ------------------------------------------------------------------------------------------
+#define LOAD_BATCH 8
 __device__ __forceinline__ void tile_load(double2* tile, const double2* __restrict__ src, const TileGeom& g,
                                           uint64_t base) {
     const uint32_t ts = 1u << g.tbits;
     const uint32_t lmask = (1u << g.lbits) - 1u;
-#pragma unroll 4
-    for (uint32_t k = threadIdx.x; k < ts; k += blockDim.x) {
-        uint64_t gi = base | __ldg(g.scat + (k >> g.lbits)) | (uint64_t)(k & lmask);
-        tile[k] = ld_amp(src + gi);
+    // LOAD_BATCH independent 16-byte loads in flight per thread before the first shared-memory store
+    for (uint32_t k0 = threadIdx.x; k0 < ts; k0 += blockDim.x * LOAD_BATCH) {
+        double2 v[LOAD_BATCH];
+#pragma unroll
+        for (int j = 0; j < LOAD_BATCH; ++j) {
+            const uint32_t k = k0 + j * blockDim.x;
+            if (k < ts) {
+                uint64_t gi = base | __ldg(g.scat + (k >> g.lbits)) | (uint64_t)(k & lmask);
+                v[j] = ld_amp(src + gi);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < LOAD_BATCH; ++j) {
+            const uint32_t k = k0 + j * blockDim.x;
+            if (k < ts) tile[k] = v[j];
+        }
     }
 }
 __device__ __forceinline__ void tile_store(const double2* tile, double2* __restrict__ dst, const TileGeom& g,
@@ -230,7 +243,15 @@ __device__ __forceinline__ void tile_store(const double2* tile, double2* __restr
 // ------------------------------------------------------------------------------------------
 // state preparation: fused rotations / gates on a shared-memory tile
 // ------------------------------------------------------------------------------------------
-#define ROT_PAIRS 4
+#define ROT_PAIRS 4   // fast path: pairs per thread held in registers (512 threads x 4 = half a 2^12 tile)
+#define SLOW_PAIRS 4  // general path
+#define OPTAB_CAP 512
+
+struct FastOp {  // 16 bytes, shared-memory copy of a fast rotation, refreshed per tile
+    double t;       // tan(angle) * (unit-phase sign) * (-1)^popc(base & zout)
+    uint32_t lz;
+    uint32_t meta;  // jmask | imag << 31
+};
 
 __device__ __forceinline__ void rot_update(double2& a, double2& b, const DevOp& op, uint32_t pa) {
     // P psi at l  = i^ny (-1)^pb b ;  at l2 = i^ny (-1)^pa a ;  new = c*old - i s (P psi)
@@ -252,27 +273,19 @@ __device__ __forceinline__ void rot_update(double2& a, double2& b, const DevOp& 
     b = nb;
 }
 
-__global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, TileGeom g,
-                                                  const DevOp* __restrict__ ops, int n_ops,
-                                                  const double* __restrict__ mats) {
-    extern __shared__ double2 tile[];
-    const uint32_t ts = 1u << g.tbits;
+
+// Slow, fully general paths (large-angle / diagonal rotations, one-qubit gates, CNOT).  Kept out of line so
+// that their register needs do not inflate the fast path of k_tile_ops.
+__device__ __noinline__ void slow_rot(double2* tile, const DevOp* __restrict__ ops, int i, uint64_t base, uint32_t ts) {
     const uint32_t half = ts >> 1;
-    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
-        const uint64_t base = pdep64(t, g.comp_mask);
-        tile_load(tile, psi, g, base);
-        int i = 0;
-        while (i < n_ops) {
-            __syncthreads();
-            const DevOp op = ops[i];
-            if (op.kind == OP_ROT) {
+    const DevOp op = ops[i];
                 const int run = (int)op.run;
                 if (op.lx == 0) {
                     // diagonal run: psi[l] *= prod_r (c_r - i s_r (-1)^par_r)
-                    for (uint32_t l0 = threadIdx.x; l0 < ts; l0 += blockDim.x * ROT_PAIRS) {
-                        double2 a[ROT_PAIRS];
+                    for (uint32_t l0 = threadIdx.x; l0 < ts; l0 += blockDim.x * SLOW_PAIRS) {
+                        double2 a[SLOW_PAIRS];
 #pragma unroll
-                        for (int j = 0; j < ROT_PAIRS; ++j) {
+                        for (int j = 0; j < SLOW_PAIRS; ++j) {
                             const uint32_t l = l0 + j * blockDim.x;
                             if (l < ts) a[j] = tile[l];
                         }
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, 
                             const DevOp o2 = ops[i + r];
                             const uint32_t opar = __popcll(base & o2.zout);
 #pragma unroll
-                            for (int j = 0; j < ROT_PAIRS; ++j) {
+                            for (int j = 0; j < SLOW_PAIRS; ++j) {
                                 const uint32_t l = l0 + j * blockDim.x;
                                 const double ss = flipsign(o2.s, __popc(l & o2.lz) + opar);
                                 double2 na;
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, 
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < ROT_PAIRS; ++j) {
+                        for (int j = 0; j < SLOW_PAIRS; ++j) {
                             const uint32_t l = l0 + j * blockDim.x;
                             if (l < ts) tile[l] = a[j];
                         }
@@ -298,11 +311,11 @@ __global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, 
                 } else {
                     // the pairs (l, l^lx) are invariant under every rotation of the run: keep them
                     // in registers and apply the whole run without touching shared memory again
-                    for (uint32_t p0 = threadIdx.x; p0 < half; p0 += blockDim.x * ROT_PAIRS) {
-                        double2 a[ROT_PAIRS], b[ROT_PAIRS];
-                        uint32_t li[ROT_PAIRS];
+                    for (uint32_t p0 = threadIdx.x; p0 < half; p0 += blockDim.x * SLOW_PAIRS) {
+                        double2 a[SLOW_PAIRS], b[SLOW_PAIRS];
+                        uint32_t li[SLOW_PAIRS];
 #pragma unroll
-                        for (int j = 0; j < ROT_PAIRS; ++j) {
+                        for (int j = 0; j < SLOW_PAIRS; ++j) {
                             const uint32_t p = p0 + j * blockDim.x;
                             li[j] = insert0(p, op.hb);
                             if (p < half) {
@@ -314,11 +327,11 @@ __global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, 
                             const DevOp o2 = ops[i + r];
                             const uint32_t opar = __popcll(base & o2.zout);
 #pragma unroll
-                            for (int j = 0; j < ROT_PAIRS; ++j)
+                            for (int j = 0; j < SLOW_PAIRS; ++j)
                                 rot_update(a[j], b[j], o2, (__popc(li[j] & o2.lz) + opar) & 1u);
                         }
 #pragma unroll
-                        for (int j = 0; j < ROT_PAIRS; ++j) {
+                        for (int j = 0; j < SLOW_PAIRS; ++j) {
                             const uint32_t p = p0 + j * blockDim.x;
                             if (p < half) {
                                 tile[li[j]] = a[j];
@@ -327,8 +340,12 @@ __global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, 
                         }
                     }
                 }
-                i += run;
-            } else if (op.kind == OP_GATE1) {
+}
+
+__device__ __noinline__ void slow_gate1(double2* tile, const DevOp* __restrict__ ops, int i, const double* __restrict__ mats,
+                                        uint32_t ts) {
+    const uint32_t half = ts >> 1;
+    const DevOp op = ops[i];
                 const double* m = mats + (size_t)op.mat * 8;
                 const double m00r = m[0], m00i = m[1], m01r = m[2], m01i = m[3];
                 const double m10r = m[4], m10i = m[5], m11r = m[6], m11i = m[7];
@@ -342,8 +359,11 @@ __global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, 
                     tile[l] = na;
                     tile[l2] = nb;
                 }
-                i += 1;
-            } else {  // OP_CNOT
+}
+
+__device__ __noinline__ void slow_cnot(double2* tile, const DevOp* __restrict__ ops, int i, uint64_t base, uint32_t ts) {
+    const uint32_t half = ts >> 1;
+    const DevOp op = ops[i];
                 const bool on = (op.zout == 0) || ((base & op.zout) != 0);
                 if (on) {
                     for (uint32_t p = threadIdx.x; p < half; p += blockDim.x) {
@@ -355,6 +375,229 @@ __global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, 
                         }
                     }
                 }
+}
+
+
+// Fast rotation run in tangent form.  Every rotation of the run acts on the same pairs (l, l^lx):
+//   R = c [[1, -+t], [+-t, 1]]  ->  apply the unnormalised updates with one FMA per component and multiply
+// by prod(c) once at the end of the run.  parity(l & lz) splits into a per-thread part (one popcount per
+// rotation) and a per-pair part that is the same for all threads (host-computed jmask), so a pair costs
+// one LOP3 + four DFMA per rotation.  IMAG: unit phase +-i (ny even) instead of +-1 (ny odd).
+template <bool IMAG>
+__device__ __forceinline__ void rot_fast_run(double2* tile, const FastOp* __restrict__ tab, uint32_t lx, uint32_t hb,
+                                             int run, double cscale, uint32_t half) {
+    const uint32_t l0 = insert0(threadIdx.x, hb);
+    for (uint32_t it = 0; it * blockDim.x * ROT_PAIRS < half; ++it) {
+        double ax[ROT_PAIRS], ay[ROT_PAIRS], bx[ROT_PAIRS], by[ROT_PAIRS];
+#pragma unroll
+        for (int j = 0; j < ROT_PAIRS; ++j) {
+            const uint32_t pidx = threadIdx.x + (it * ROT_PAIRS + j) * blockDim.x;
+            const uint32_t lj = insert0(pidx, hb);
+            ax[j] = ay[j] = bx[j] = by[j] = 0.0;
+            if (pidx < half) {
+                const double2 va = tile[lj], vb = tile[lj ^ lx];
+                ax[j] = va.x; ay[j] = va.y; bx[j] = vb.x; by[j] = vb.y;
+            }
+        }
+#pragma unroll 1
+        for (int r = 0; r < run; ++r) {
+            const FastOp f = tab[r];
+            const uint32_t thi = (uint32_t)__double2hiint(f.t) ^ ((uint32_t)__popc(l0 & f.lz) << 31);
+            const int tlo = __double2loint(f.t);
+            const uint32_t jm = f.meta >> (it * ROT_PAIRS);
+#pragma unroll
+            for (int j = 0; j < ROT_PAIRS; ++j) {
+                const double tj = __hiloint2double((int)(thi ^ ((jm << (31 - j)) & 0x80000000u)), tlo);
+                if (IMAG) {
+                    const double nax = fma(-tj, by[j], ax[j]), nay = fma(tj, bx[j], ay[j]);
+                    const double nbx = fma(-tj, ay[j], bx[j]), nby = fma(tj, ax[j], by[j]);
+                    ax[j] = nax; ay[j] = nay; bx[j] = nbx; by[j] = nby;
+                } else {
+                    const double nax = fma(-tj, bx[j], ax[j]), nay = fma(-tj, by[j], ay[j]);
+                    const double nbx = fma(tj, ax[j], bx[j]), nby = fma(tj, ay[j], by[j]);
+                    ax[j] = nax; ay[j] = nay; bx[j] = nbx; by[j] = nby;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ROT_PAIRS; ++j) {
+            const uint32_t pidx = threadIdx.x + (it * ROT_PAIRS + j) * blockDim.x;
+            const uint32_t lj = insert0(pidx, hb);
+            if (pidx < half) {
+                tile[lj] = make_double2(cscale * ax[j], cscale * ay[j]);
+                tile[lj ^ lx] = make_double2(cscale * bx[j], cscale * by[j]);
+            }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Dedicated kernel for passes that consist only of fast (tangent-form) rotation runs -- the UCC case.
+// Kept separate from the general kernel so that it fits in 64 registers (2 x 512 threads per SM).
+// ------------------------------------------------------------------------------------------
+struct DevRun {        // 32 bytes: one run = consecutive fast rotations with the same lx and phase type
+    uint32_t lx, hb;
+    uint32_t begin, len;   // into the pass-local FastOp table
+    double cscale;         // prod cos(angle)
+    uint32_t imag, pad;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// asynchronous tile load: no register staging, every thread's 16-byte copies are all in flight at once
+__device__ __forceinline__ void tile_load_async(double2* tile, const double2* __restrict__ src, const TileGeom& g,
+                                                uint64_t base) {
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t lmask = (1u << g.lbits) - 1u;
+    for (uint32_t k = threadIdx.x; k < ts; k += blockDim.x) {
+        uint64_t gi = base | __ldg(g.scat + (k >> g.lbits)) | (uint64_t)(k & lmask);
+        cp_async16(tile + k, src + gi);
+    }
+}
+
+template <bool IMAG>
+__device__ __forceinline__ void rot_run4(double2* tile, const FastOp* tab, uint32_t lx, uint32_t hb, int len,
+                                         double cscale, uint32_t half) {
+    // 4 pairs per thread: pair index p_j = tid + j * blockDim
+    const uint32_t l0 = insert0(threadIdx.x, hb);
+    uint32_t jbase = 0;
+    for (uint32_t p0 = threadIdx.x; p0 < half; p0 += 4 * blockDim.x, jbase += 4) {
+        const uint32_t i0 = insert0(p0, hb), i1 = insert0(p0 + blockDim.x, hb);
+        const uint32_t i2 = insert0(p0 + 2 * blockDim.x, hb), i3 = insert0(p0 + 3 * blockDim.x, hb);
+        const bool v1 = p0 + blockDim.x < half, v2 = p0 + 2 * blockDim.x < half, v3 = p0 + 3 * blockDim.x < half;
+        double2 a0 = tile[i0], b0 = tile[i0 ^ lx];
+        double2 a1 = v1 ? tile[i1] : a0, b1 = v1 ? tile[i1 ^ lx] : b0;
+        double2 a2 = v2 ? tile[i2] : a0, b2 = v2 ? tile[i2 ^ lx] : b0;
+        double2 a3 = v3 ? tile[i3] : a0, b3 = v3 ? tile[i3 ^ lx] : b0;
+        // Two rotations per trip with the b registers ping-ponging (b -> c -> b): a is updated in place
+        // (dest = addend), the new partner goes to a fresh register, so no register copies are needed.
+#define ROT_STEP(A, B, C, J, THI, TLO, JM)                                                        \
+    {                                                                                            \
+        const double tj = __hiloint2double((int)((THI) ^ (((JM) << (31 - (J))) & 0x80000000u)), TLO); \
+        if (IMAG) {                                                                              \
+            C.x = fma(-tj, A.y, B.x);                                                            \
+            C.y = fma(tj, A.x, B.y);                                                             \
+            A.x = fma(-tj, B.y, A.x);                                                            \
+            A.y = fma(tj, B.x, A.y);                                                             \
+        } else {                                                                                 \
+            C.x = fma(tj, A.x, B.x);                                                             \
+            C.y = fma(tj, A.y, B.y);                                                             \
+            A.x = fma(-tj, B.x, A.x);                                                            \
+            A.y = fma(-tj, B.y, A.y);                                                            \
+        }                                                                                        \
+    }
+        int r = 0;
+#pragma unroll 1
+        for (; r + 1 < len; r += 2) {
+            const FastOp f = tab[r], h = tab[r + 1];
+            const uint32_t thi = (uint32_t)__double2hiint(f.t) ^ ((uint32_t)__popc(l0 & f.lz) << 31);
+            const uint32_t uhi = (uint32_t)__double2hiint(h.t) ^ ((uint32_t)__popc(l0 & h.lz) << 31);
+            const int tlo = __double2loint(f.t), ulo = __double2loint(h.t);
+            const uint32_t jm = f.meta >> jbase, km = h.meta >> jbase;
+            double2 c0, c1, c2, c3;
+            ROT_STEP(a0, b0, c0, 0, thi, tlo, jm)
+            ROT_STEP(a1, b1, c1, 1, thi, tlo, jm)
+            ROT_STEP(a2, b2, c2, 2, thi, tlo, jm)
+            ROT_STEP(a3, b3, c3, 3, thi, tlo, jm)
+            ROT_STEP(a0, c0, b0, 0, uhi, ulo, km)
+            ROT_STEP(a1, c1, b1, 1, uhi, ulo, km)
+            ROT_STEP(a2, c2, b2, 2, uhi, ulo, km)
+            ROT_STEP(a3, c3, b3, 3, uhi, ulo, km)
+        }
+        if (r < len) {
+            const FastOp f = tab[r];
+            const uint32_t thi = (uint32_t)__double2hiint(f.t) ^ ((uint32_t)__popc(l0 & f.lz) << 31);
+            const int tlo = __double2loint(f.t);
+            const uint32_t jm = f.meta >> jbase;
+            double2 c0, c1, c2, c3;
+            ROT_STEP(a0, b0, c0, 0, thi, tlo, jm)
+            ROT_STEP(a1, b1, c1, 1, thi, tlo, jm)
+            ROT_STEP(a2, b2, c2, 2, thi, tlo, jm)
+            ROT_STEP(a3, b3, c3, 3, thi, tlo, jm)
+            b0 = c0; b1 = c1; b2 = c2; b3 = c3;
+        }
+#undef ROT_STEP
+        tile[i0] = make_double2(cscale * a0.x, cscale * a0.y);
+        tile[i0 ^ lx] = make_double2(cscale * b0.x, cscale * b0.y);
+        if (v1) { tile[i1] = make_double2(cscale * a1.x, cscale * a1.y); tile[i1 ^ lx] = make_double2(cscale * b1.x, cscale * b1.y); }
+        if (v2) { tile[i2] = make_double2(cscale * a2.x, cscale * a2.y); tile[i2 ^ lx] = make_double2(cscale * b2.x, cscale * b2.y); }
+        if (v3) { tile[i3] = make_double2(cscale * a3.x, cscale * a3.y); tile[i3 ^ lx] = make_double2(cscale * b3.x, cscale * b3.y); }
+    }
+}
+
+__global__ void __launch_bounds__(512, 2) k_tile_rot(double2* __restrict__ psi, TileGeom g,
+                                                     const DevOp* __restrict__ ops, int n_ops,
+                                                     const DevRun* __restrict__ runs, int n_runs) {
+    extern __shared__ double2 tile[];
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t half = ts >> 1;
+    FastOp* optab = (FastOp*)(tile + ts);
+    DevRun* srun = (DevRun*)(optab + n_ops);
+    for (int q = threadIdx.x; q < n_runs; q += blockDim.x) srun[q] = runs[q];
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = pdep64(t, g.comp_mask);
+        tile_load_async(tile, psi, g, base);
+        for (int r = threadIdx.x; r < n_ops; r += blockDim.x) {
+            FastOp f;
+            f.t = flipsign(ops[r].s, __popcll(base & ops[r].zout));
+            f.lz = ops[r].lz;
+            f.meta = ops[r].jmask;
+            optab[r] = f;
+        }
+        cp_async_wait_all();
+        for (int q = 0; q < n_runs; ++q) {
+            __syncthreads();
+            const DevRun rn = srun[q];
+            if (rn.imag) rot_run4<true>(tile, optab + rn.begin, rn.lx, rn.hb, (int)rn.len, rn.cscale, half);
+            else rot_run4<false>(tile, optab + rn.begin, rn.lx, rn.hb, (int)rn.len, rn.cscale, half);
+        }
+        __syncthreads();
+        tile_store(tile, psi, g, base);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(512, 2) k_tile_ops(double2* __restrict__ psi, TileGeom g,
+                                                  const DevOp* __restrict__ ops, int n_ops,
+                                                  const double* __restrict__ mats) {
+    extern __shared__ double2 tile[];
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t half = ts >> 1;
+    FastOp* optab = (FastOp*)(tile + ts);  // n_ops entries (host caps n_ops per pass at OPTAB_CAP)
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = pdep64(t, g.comp_mask);
+        // per-tile table of the fast rotations: tangent with the sign of the outside-tile Z parity folded in
+        for (int r = threadIdx.x; r < n_ops; r += blockDim.x) {
+            const DevOp o = ops[r];
+            FastOp f;
+            f.t = flipsign(o.s, __popcll(base & o.zout));
+            f.lz = o.lz;
+            f.meta = o.jmask | (o.imag << 31);
+            optab[r] = f;
+        }
+        tile_load(tile, psi, g, base);
+        int i = 0;
+        while (i < n_ops) {
+            __syncthreads();
+            const uint32_t kind = ops[i].kind;
+            if (kind == OP_ROTF) {
+                // Tangent form (see rot_fast_run): one run = consecutive rotations sharing lx and phase type
+                if (ops[i].imag) rot_fast_run<true>(tile, optab + i, ops[i].lx, ops[i].hb, (int)ops[i].run, ops[i].c, half);
+                else rot_fast_run<false>(tile, optab + i, ops[i].lx, ops[i].hb, (int)ops[i].run, ops[i].c, half);
+                i += (int)ops[i].run;
+            } else if (kind == OP_ROT) {
+                slow_rot(tile, ops, i, base, ts);
+                i += (int)ops[i].run;
+            } else if (kind == OP_GATE1) {
+                slow_gate1(tile, ops, i, mats, ts);
+                i += 1;
+            } else {  // OP_CNOT
+                slow_cnot(tile, ops, i, base, ts);
                 i += 1;
             }
         }
@@ -367,95 +610,117 @@ __global__ void __launch_bounds__(256, 3) k_tile_ops(double2* __restrict__ psi, 
 // ------------------------------------------------------------------------------------------
 // <psi| O |psi> for the X-mask groups of one pass.  grid = (tile workers, group chunks)
 // ------------------------------------------------------------------------------------------
-#define TERM_CAP 1024
+#define TERM_CAP 384    // terms per pass (host splits passes accordingly)
+#define GROUP_CAP 96    // X-mask groups per pass
+#define EXP_PAIRS 4
 
-__global__ void __launch_bounds__(256, 3) k_tile_expect(const double2* __restrict__ psi, TileGeom g,
-                                                     const DevGroup* __restrict__ groups, int n_groups,
-                                                     const DevTerm* __restrict__ terms,
-                                                     double2* __restrict__ partial) {
+// <psi|O|psi> for one pass.  Group headers and term tables are staged in shared memory ONCE per CTA; per tile
+// only the outside-tile Z parity of each term is refreshed (signed coefficient table), the tile itself arrives
+// through cp.async.  A thread keeps EXP_PAIRS pair products w_j = 2 conj(b_j) a_j in registers and streams the
+// group's terms past them: parity(l_j & lz) = parity(l_0 & lz) ^ jmask_j (jmask from the host), so a term costs
+// one popcount per thread plus, per pair, one LOP3 (sign into the coefficient's high word) and one DFMA into
+// an independent accumulator.
+template <bool CPLX>
+__global__ void __launch_bounds__(512, 2) k_tile_expect(const double2* __restrict__ psi, TileGeom g,
+                                                        const DevGroup* __restrict__ groups, int n_groups,
+                                                        const DevTerm* __restrict__ terms,
+                                                        double2* __restrict__ partial) {
     extern __shared__ double2 tile[];
     __shared__ double red[64];
     const uint32_t ts = 1u << g.tbits;
     const uint32_t half = ts >> 1;
-    // shared term cache lives after the tile
-    double2* s_coef = tile + ts;                         // TERM_CAP entries
-    uint32_t* s_lz = (uint32_t*)(s_coef + TERM_CAP);     // TERM_CAP entries
-    // group chunk of this CTA
+    DevTerm* s_term = (DevTerm*)(tile + ts);               // TERM_CAP
+    double2* s_sc = (double2*)(s_term + TERM_CAP);         // TERM_CAP signed coefficients (per tile)
+    DevGroup* s_grp = (DevGroup*)(s_sc + TERM_CAP);        // GROUP_CAP
+    // group chunk of this CTA (blockIdx.y splits the groups of a pass when there are few tiles)
     const int per = (n_groups + gridDim.y - 1) / gridDim.y;
     const int g0 = blockIdx.y * per, g1 = min(n_groups, g0 + per);
+    const int ng = max(0, g1 - g0);
+    uint32_t tb0 = 0, nt = 0;
+    if (ng > 0) {
+        tb0 = groups[g0].t_begin;
+        const DevGroup last = groups[g1 - 1];
+        nt = last.t_begin + last.n_even + last.n_odd - tb0;
+    }
+    for (int q = threadIdx.x; q < ng; q += blockDim.x) s_grp[q] = groups[g0 + q];
+    for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) s_term[k] = terms[tb0 + k];
     double er = 0.0, ei = 0.0;
     for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
         const uint64_t base = pdep64(t, g.comp_mask);
+        __syncthreads();  // previous tile fully consumed (and, first time, the tables are in place)
+        tile_load_async(tile, psi, g, base);
+        for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
+            const uint32_t par = __popcll(base & s_term[k].zout);
+            s_sc[k] = make_double2(flipsign(s_term[k].ar, par), flipsign(s_term[k].ai, par));
+        }
+        cp_async_wait_all();
         __syncthreads();
-        tile_load(tile, psi, g, base);
-        int gi = g0;
-        while (gi < g1) {
-            // take as many whole groups as fit in the term cache
-            int ge = gi;
-            uint32_t nt = 0;
-            const uint32_t tb0 = groups[gi].t_begin;
-            while (ge < g1) {
-                uint32_t k = groups[ge].n_even + groups[ge].n_odd;
-                if (nt + k > TERM_CAP && ge > gi) break;
-                nt += k;
-                ++ge;
-            }
-            __syncthreads();
-            for (uint32_t k = threadIdx.x; k < nt && k < TERM_CAP; k += blockDim.x) {
-                const DevTerm tm = terms[tb0 + k];
-                uint32_t par = __popcll(base & tm.zout) & 1u;
-                s_coef[k] = make_double2(flipsign(tm.ar, par), flipsign(tm.ai, par));
-                s_lz[k] = tm.lz;
-            }
-            __syncthreads();
-            for (int q = gi; q < ge; ++q) {
-                const DevGroup gr = groups[q];
-                const uint32_t off = gr.t_begin - tb0;
-                if (off + gr.n_even + gr.n_odd > TERM_CAP) continue;  // oversize single group: handled by host split
-                if (gr.lx == 0) {
-                    for (uint32_t l = threadIdx.x; l < ts; l += blockDim.x) {
-                        const double2 a = tile[l];
-                        const double w = a.x * a.x + a.y * a.y;
-                        double sr = 0.0, si = 0.0;
-                        for (uint32_t k = 0; k < gr.n_even; ++k) {
-                            uint32_t par = __popc(l & s_lz[off + k]);
-                            const double2 c = s_coef[off + k];
-                            sr += flipsign(c.x, par);
-                            si += flipsign(c.y, par);
+        for (int q = 0; q < ng; ++q) {
+            const uint32_t lx = s_grp[q].lx, hb = s_grp[q].hb;
+            const uint32_t off = s_grp[q].t_begin - tb0;
+            const uint32_t n_even = s_grp[q].n_even, n_odd = s_grp[q].n_odd;
+            const uint32_t count = (lx == 0) ? ts : half;
+            const uint32_t l0 = (lx == 0) ? threadIdx.x : insert0(threadIdx.x, hb);
+            uint32_t jbase = 0;
+            for (uint32_t p0 = threadIdx.x; p0 < count; p0 += EXP_PAIRS * blockDim.x, jbase += EXP_PAIRS) {
+                double wr[EXP_PAIRS], wi[EXP_PAIRS];
+#pragma unroll
+                for (int j = 0; j < EXP_PAIRS; ++j) {
+                    const uint32_t pidx = p0 + j * blockDim.x;
+                    wr[j] = 0.0;
+                    wi[j] = 0.0;
+                    if (pidx < count) {
+                        if (lx == 0) {
+                            const double2 a = tile[pidx];
+                            wr[j] = a.x * a.x + a.y * a.y;
+                        } else {
+                            const uint32_t l = insert0(pidx, hb);
+                            const double2 a = tile[l], b = tile[l ^ lx];
+                            wr[j] = 2.0 * (b.x * a.x + b.y * a.y);  // 2 Re(conj(b) a)
+                            wi[j] = 2.0 * (b.x * a.y - b.y * a.x);  // 2 Im(conj(b) a)
                         }
-                        er += w * sr;
-                        ei += w * si;
-                    }
-                } else {
-                    for (uint32_t p = threadIdx.x; p < half; p += blockDim.x) {
-                        const uint32_t l = insert0(p, gr.hb), l2 = l ^ gr.lx;
-                        const double2 a = tile[l], b = tile[l2];
-                        const double wr = 2.0 * (b.x * a.x + b.y * a.y);  // 2 Re(conj(b) a)
-                        const double wi = 2.0 * (b.x * a.y - b.y * a.x);  // 2 Im(conj(b) a)
-                        double sr = 0.0, si = 0.0, orr = 0.0, oi = 0.0;
-                        uint32_t k = off;
-                        for (uint32_t e = 0; e < gr.n_even; ++e, ++k) {
-                            uint32_t par = __popc(l & s_lz[k]);
-                            const double2 c = s_coef[k];
-                            sr += flipsign(c.x, par);
-                            si += flipsign(c.y, par);
-                        }
-                        for (uint32_t e = 0; e < gr.n_odd; ++e, ++k) {
-                            uint32_t par = __popc(l & s_lz[k]);
-                            const double2 c = s_coef[k];
-                            orr += flipsign(c.x, par);
-                            oi += flipsign(c.y, par);
-                        }
-                        er += wr * sr + wi * orr;
-                        ei += wr * si + wi * oi;
                     }
                 }
+                double accr[EXP_PAIRS], acci[EXP_PAIRS];  // independent FMA chains
+#pragma unroll
+                for (int j = 0; j < EXP_PAIRS; ++j) accr[j] = acci[j] = 0.0;
+                uint32_t k = off;
+                for (uint32_t e = 0; e < n_even; ++e, ++k) {
+                    const double2 c = s_sc[k];
+                    const uint32_t tsign = (uint32_t)__popc(l0 & s_term[k].lz) << 31;
+                    const uint32_t jm = s_term[k].jmask >> jbase;
+                    const uint32_t hr = (uint32_t)__double2hiint(c.x) ^ tsign;
+                    const uint32_t hi = (uint32_t)__double2hiint(c.y) ^ tsign;
+#pragma unroll
+                    for (int j = 0; j < EXP_PAIRS; ++j) {
+                        const uint32_t u = (jm << (31 - j)) & 0x80000000u;
+                        accr[j] = fma(__hiloint2double((int)(hr ^ u), __double2loint(c.x)), wr[j], accr[j]);
+                        if (CPLX) acci[j] = fma(__hiloint2double((int)(hi ^ u), __double2loint(c.y)), wr[j], acci[j]);
+                    }
+                }
+                for (uint32_t e = 0; e < n_odd; ++e, ++k) {
+                    const double2 c = s_sc[k];
+                    const uint32_t tsign = (uint32_t)__popc(l0 & s_term[k].lz) << 31;
+                    const uint32_t jm = s_term[k].jmask >> jbase;
+                    const uint32_t hr = (uint32_t)__double2hiint(c.x) ^ tsign;
+                    const uint32_t hi = (uint32_t)__double2hiint(c.y) ^ tsign;
+#pragma unroll
+                    for (int j = 0; j < EXP_PAIRS; ++j) {
+                        const uint32_t u = (jm << (31 - j)) & 0x80000000u;
+                        accr[j] = fma(__hiloint2double((int)(hr ^ u), __double2loint(c.x)), wi[j], accr[j]);
+                        if (CPLX) acci[j] = fma(__hiloint2double((int)(hi ^ u), __double2loint(c.y)), wi[j], acci[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < EXP_PAIRS; ++j) {
+                    er += accr[j];
+                    if (CPLX) ei += acci[j];
+                }
             }
-            gi = ge;
         }
     }
-    double2 s = block_sum2(er, ei, red);
-    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+    double2 sres = block_sum2(er, ei, red);
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -676,7 +941,7 @@ struct vqe_ctx {
     double2* d_result = nullptr;
     double2* h_result = nullptr;  // pinned
     size_t result_cap = 0;        // in double2
-    int tile_bits = 12, low_bits = 5, threads = 256, ctas_per_sm = 3;
+    int tile_bits = 12, low_bits = 5, threads = 512, ctas_per_sm = 2;
     uint64_t launches = 0;
     bool profiling = false;
     KernelProf prof[4];
@@ -785,7 +1050,7 @@ static int ensure_buf(vqe_ctx* c, int b) {
 
 static size_t tile_smem(int tbits, int n_tiles_in_smem, bool term_cache) {
     size_t s = (size_t)n_tiles_in_smem * (16ull << tbits);
-    if (term_cache) s += TERM_CAP * (sizeof(double2) + sizeof(uint32_t));
+    if (term_cache) s += TERM_CAP * (sizeof(DevTerm) + sizeof(double2)) + GROUP_CAP * sizeof(DevGroup);
     return s;
 }
 
@@ -801,7 +1066,9 @@ static int set_kernel_attrs() {
                                 maxs - (int)fa_.sharedSizeBytes));                               \
     } while (0)
     SET_SMEM(k_tile_ops);
-    SET_SMEM(k_tile_expect);
+    SET_SMEM(k_tile_rot);
+    SET_SMEM(k_tile_expect<false>);
+    SET_SMEM(k_tile_expect<true>);
     SET_SMEM(k_tile_apply);
     SET_SMEM(k_tile_pool);
 #undef SET_SMEM
@@ -829,10 +1096,10 @@ extern "C" int vqe_create(vqe_ctx** out, int n_qubits, int device) {
     c->sm_count = prop.multiProcessorCount;
     c->tile_bits = env_int("VQE_TILE_BITS", 12);
     c->low_bits = env_int("VQE_LOW_BITS", 5);
-    c->threads = env_int("VQE_THREADS", 256);
-    c->ctas_per_sm = env_int("VQE_CTAS_PER_SM", 3);
+    c->threads = env_int("VQE_THREADS", 512);
+    c->ctas_per_sm = env_int("VQE_CTAS_PER_SM", 2);
     if (c->tile_bits < 6 || c->tile_bits > 13) c->tile_bits = 12;
-    if (c->threads < 64 || c->threads > 256 || (c->threads & 31)) c->threads = 256;
+    if (c->threads < 64 || c->threads > 512 || (c->threads & (c->threads - 1))) c->threads = 512;
     if (c->low_bits < 0 || c->low_bits > c->tile_bits) c->low_bits = 5;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
@@ -991,9 +1258,13 @@ static int run_ops(vqe_ctx* c, const std::vector<HostOp>& ops) {
     struct Pass {
         TilePlan tp;
         size_t op_begin, op_end;  // in dev op array
+        size_t run_begin = 0, run_end = 0;  // in dev run array (fast passes only)
+        bool fast = false;
     };
     std::vector<Pass> passes;
     std::vector<DevOp> dops;
+    std::vector<DevRun> druns;
+    auto fast_eligible = [](const HostOp& h) { return h.kind == OP_ROT && h.x != 0 && fabs(h.c) >= 0.3; };
     std::vector<double> mats;
     dops.reserve(ops.size());
     size_t i = 0;
@@ -1003,7 +1274,9 @@ static int run_ops(vqe_ctx* c, const std::vector<HostOp>& ops) {
     while (i < ops.size()) {
         uint64_t need = 0;
         size_t j = i;
-        while (j < ops.size()) {
+        const bool fast0 = fast_eligible(ops[i]);
+        while (j < ops.size() && j - i < OPTAB_CAP) {
+            if (fast_eligible(ops[j]) != fast0) break;  // a pass is either all-fast or general
             uint64_t nb = ops[j].x;  // bits that must be inside the tile
             uint64_t u = need | nb;
             if (popc64(u | lowmask) > tb) break;
@@ -1045,20 +1318,65 @@ static int run_ops(vqe_ctx* c, const std::vector<HostOp>& ops) {
             dops.push_back(d);
         }
         p.op_end = dops.size();
-        // run lengths of consecutive same-lx rotations
+        // classify: small/moderate angles with lx != 0 take the tangent-form fast path
+        const int threads_p = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << p.tp.tbits) / 2));
+        const int tshift = 31 - __builtin_clz((unsigned)threads_p);
+        const int n_j = (int)std::max<uint64_t>(1, ((1ull << p.tp.tbits) / 2) / threads_p);
+        for (size_t k = p.op_begin; k < p.op_end; ++k) {
+            DevOp& d = dops[k];
+            if (d.kind != OP_ROT || d.lx == 0 || fabs(d.c) < 0.3 || n_j > 32) continue;
+            d.kind = OP_ROTF;
+            d.imag = (d.k4 & 1u);
+            double tn = d.s / d.c;
+            if (d.k4 >> 1) tn = -tn;
+            d.s = tn;  // tangent, unit-phase sign folded in
+            uint32_t jm = 0;
+            for (int jj = 0; jj < n_j; ++jj) {
+                uint32_t pj = (uint32_t)jj << tshift;
+                uint32_t uj = ((pj >> d.hb) << (d.hb + 1)) | (pj & ((1u << d.hb) - 1u));
+                if (__builtin_popcount(uj & d.lz) & 1) jm |= 1u << jj;
+            }
+            d.jmask = jm;
+        }
+        // run lengths of consecutive same-lx rotations of the same kind; fast runs carry prod(c) in the head
         for (size_t k = p.op_begin; k < p.op_end;) {
-            if (dops[k].kind != OP_ROT) { ++k; continue; }
+            if (dops[k].kind != OP_ROT && dops[k].kind != OP_ROTF) { ++k; continue; }
             size_t e = k + 1;
-            while (e < p.op_end && dops[e].kind == OP_ROT && dops[e].lx == dops[k].lx) ++e;
+            while (e < p.op_end && dops[e].kind == dops[k].kind && dops[e].lx == dops[k].lx &&
+                   (dops[k].kind != OP_ROTF || dops[e].imag == dops[k].imag)) ++e;
             dops[k].run = (uint32_t)(e - k);
+            if (dops[k].kind == OP_ROTF) {
+                double prod = 1.0;
+                for (size_t q = k; q < e; ++q) prod *= dops[q].c;
+                dops[k].c = prod;
+            }
             k = e;
+        }
+        p.fast = true;
+        for (size_t k = p.op_begin; k < p.op_end; ++k)
+            if (dops[k].kind != OP_ROTF) p.fast = false;
+        if (p.fast) {
+            p.run_begin = druns.size();
+            for (size_t k = p.op_begin; k < p.op_end; k += dops[k].run) {
+                DevRun r;
+                r.lx = dops[k].lx;
+                r.hb = dops[k].hb;
+                r.begin = (uint32_t)(k - p.op_begin);
+                r.len = dops[k].run;
+                r.cscale = dops[k].c;
+                r.imag = dops[k].imag;
+                r.pad = 0;
+                druns.push_back(r);
+            }
+            p.run_end = druns.size();
         }
         passes.push_back(std::move(p));
         i = j;
     }
     // upload: [ops][mats][scat tables]
     size_t off_ops = 0, off_mats = dops.size() * sizeof(DevOp);
-    size_t off_scat = off_mats + mats.size() * sizeof(double);
+    size_t off_runs = (off_mats + mats.size() * sizeof(double) + 15) & ~size_t(15);
+    size_t off_scat = off_runs + druns.size() * sizeof(DevRun);
     off_scat = (off_scat + 15) & ~size_t(15);
     size_t total = off_scat;
     std::vector<size_t> scat_off(passes.size());
@@ -1072,6 +1390,7 @@ static int run_ops(vqe_ctx* c, const std::vector<HostOp>& ops) {
     CK(cudaStreamSynchronize(c->stream));
     memcpy(c->h_stage + off_ops, dops.data(), dops.size() * sizeof(DevOp));
     if (!mats.empty()) memcpy(c->h_stage + off_mats, mats.data(), mats.size() * sizeof(double));
+    if (!druns.empty()) memcpy(c->h_stage + off_runs, druns.data(), druns.size() * sizeof(DevRun));
     for (size_t p = 0; p < passes.size(); ++p)
         memcpy(c->h_stage + scat_off[p], passes[p].tp.scat.data(), passes[p].tp.scat.size() * sizeof(uint64_t));
     c->h2d_bytes += total;
@@ -1084,9 +1403,15 @@ static int run_ops(vqe_ctx* c, const std::vector<HostOp>& ops) {
         g.scat = (const uint64_t*)(c->d_stage + scat_off[p]);
         g.tbits = ps.tp.tbits;
         g.lbits = ps.tp.lbits;
-        size_t smem = tile_smem(ps.tp.tbits, 1, false);
+        size_t smem = tile_smem(ps.tp.tbits, 1, false) + (ps.op_end - ps.op_begin) * sizeof(FastOp) +
+                      (ps.run_end - ps.run_begin) * sizeof(DevRun);
         int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
         ProfScope prof(c, 0);
+        if (ps.fast)
+            k_tile_rot<<<tile_grid(c, ps.tp), threads, smem, c->stream>>>(
+                c->buf[0], g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
+                (const DevRun*)(c->d_stage + off_runs) + ps.run_begin, (int)(ps.run_end - ps.run_begin));
+        else
         k_tile_ops<<<tile_grid(c, ps.tp), threads, smem, c->stream>>>(
             c->buf[0], g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
             (const double*)(c->d_stage + off_mats));
@@ -1165,6 +1490,7 @@ struct PSPass {
     DevTerm* d_terms_expect = nullptr;
     DevTerm* d_terms_apply = nullptr;
     uint64_t* d_scat = nullptr;
+    bool cplx = false;  // some expectation weight has a non-zero imaginary part
 };
 struct vqe_paulisum {
     int n = 0, device = 0, n_groups = 0, tbits = 0;
@@ -1185,7 +1511,7 @@ static void mul_i_pow(double& r, double& i, int k) {
     else if (k == 3) { r = b; i = -a; }
 }
 
-static int build_paulisum(vqe_paulisum* ps, int n, int tbits_max, int low_bits, std::vector<HTerm> terms) {
+static int build_paulisum(vqe_paulisum* ps, int n, int tbits_max, int low_bits, int threads_cfg, std::vector<HTerm> terms) {
     // group by x (stable: keep first-appearance order of groups, term order inside)
     std::vector<uint64_t> xs;
     std::vector<std::vector<HTerm>> grp;
@@ -1229,6 +1555,7 @@ static int build_paulisum(vqe_paulisum* ps, int n, int tbits_max, int low_bits, 
         // seed
         uint64_t need = 0;
         std::vector<size_t> members;
+        size_t n_terms_pass = 0;
         for (size_t g = 0; g < xs.size(); ++g) {
             if (done[g]) continue;
             uint64_t u = need | xs[g];
@@ -1237,17 +1564,20 @@ static int build_paulisum(vqe_paulisum* ps, int n, int tbits_max, int low_bits, 
                     return fail(VQE_ERR_INVALID, "Pauli term with %d X/Y letters exceeds the %d-bit tile", popc64(xs[g]), tb);
                 continue;
             }
+            if (!members.empty() && (n_terms_pass + grp[g].size() > TERM_CAP || members.size() >= GROUP_CAP)) continue;
             need = u;
             members.push_back(g);
+            n_terms_pass += grp[g].size();
             done[g] = 1;
         }
         PSPass p;
         p.tp = make_plan(n, need, tb, lb);
-        // second sweep: anything already inside the final tile mask
+        // second sweep: anything already inside the final tile mask (within the per-pass table capacity)
         for (size_t g = 0; g < xs.size(); ++g) {
             if (done[g]) continue;
-            if ((xs[g] & ~p.tp.tile_mask) == 0) {
+            if ((xs[g] & ~p.tp.tile_mask) == 0 && n_terms_pass + grp[g].size() <= TERM_CAP && members.size() < GROUP_CAP) {
                 members.push_back(g);
+                n_terms_pass += grp[g].size();
                 done[g] = 1;
             }
         }
@@ -1276,6 +1606,21 @@ static int build_paulisum(vqe_paulisum* ps, int n, int tbits_max, int low_bits, 
                     e.ai = t.ci;
                     mul_i_pow(e.ar, e.ai, parity ? t.ny + 1 : t.ny);
                     if (xs[g] == 0) { e.ar = t.cr; e.ai = t.ci; }
+                    if (e.ai != 0.0) p.cplx = true;
+                    {   // per-pair parity bits (see k_tile_expect)
+                        const uint64_t tsz = 1ull << p.tp.tbits;
+                        const uint64_t count = (xs[g] == 0) ? tsz : tsz / 2;
+                        const int thr = (int)std::min<uint64_t>(threads_cfg, std::max<uint64_t>(32, tsz / 2));
+                        const int tshift = 31 - __builtin_clz((unsigned)thr);
+                        const int n_j = (int)std::max<uint64_t>(1, count / thr);
+                        uint32_t jm = 0;
+                        for (int jj = 0; jj < n_j && jj < 32; ++jj) {
+                            uint32_t pj = (uint32_t)jj << tshift;
+                            uint32_t uj = (xs[g] == 0) ? pj : (((pj >> dg.hb) << (dg.hb + 1)) | (pj & ((1u << dg.hb) - 1u)));
+                            if (__builtin_popcount(uj & e.lz) & 1) jm |= 1u << jj;
+                        }
+                        e.jmask = jm;
+                    }
                     p.terms_expect.push_back(e);
                     p.terms_apply.push_back(a);
                     if (parity) dg.n_odd++; else dg.n_even++;
@@ -1344,7 +1689,7 @@ extern "C" int vqe_paulisum_create(vqe_ctx* c, vqe_paulisum** out, int n_terms, 
     if (rc) return rc;
     vqe_paulisum* ps = new vqe_paulisum();
     ps->device = c->device;
-    rc = build_paulisum(ps, c->n, c->tile_bits, c->low_bits, std::move(terms));
+    rc = build_paulisum(ps, c->n, c->tile_bits, c->low_bits, c->threads, std::move(terms));
     if (rc == VQE_OK) rc = upload_paulisum(c, ps);
     if (rc) {
         free_paulisum_device(ps);
@@ -1398,9 +1743,14 @@ extern "C" int vqe_expectation(vqe_ctx* c, int b, const vqe_paulisum* ps, double
         size_t smem = tile_smem(pp.tp.tbits, 1, true);
         int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << pp.tp.tbits) / 2));
         ProfScope prof(c, 1);
-        k_tile_expect<<<grids[p], threads, smem, c->stream>>>(c->buf[b], geom_of(pp), pp.d_groups,
-                                                             (int)pp.groups.size(), pp.d_terms_expect,
-                                                             c->d_partial + off);
+        if (pp.cplx)
+            k_tile_expect<true><<<grids[p], threads, smem, c->stream>>>(c->buf[b], geom_of(pp), pp.d_groups,
+                                                                       (int)pp.groups.size(), pp.d_terms_expect,
+                                                                       c->d_partial + off);
+        else
+            k_tile_expect<false><<<grids[p], threads, smem, c->stream>>>(c->buf[b], geom_of(pp), pp.d_groups,
+                                                                        (int)pp.groups.size(), pp.d_terms_expect,
+                                                                        c->d_partial + off);
         c->launches++;
         off += (size_t)grids[p].x * grids[p].y;
     }
@@ -1665,7 +2015,7 @@ extern "C" int vqe_apply_exp_paulisum(vqe_ctx* c, int n_terms, const uint64_t* x
     // general case: scaled Taylor series  psi <- (sum_m (theta A / s)^m / m!)^s psi
     vqe_paulisum ps;
     ps.device = c->device;
-    rc = build_paulisum(&ps, c->n, c->tile_bits, c->low_bits, terms);
+    rc = build_paulisum(&ps, c->n, c->tile_bits, c->low_bits, c->threads, terms);
     if (rc == VQE_OK) rc = upload_paulisum(c, &ps);
     if (rc) { free_paulisum_device(&ps); return rc; }
     rc = ensure_buf(c, VQE_BUF_SIGMA);
