@@ -190,17 +190,21 @@ __global__ void k_inner(const double2* a, const double2* b, uint64_t n_amp, doub
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-// out[j] = sum_b partial[b * stride + j], fixed order (one thread per j)
+// out[j] = sum_b partial[b * stride + j].  One CTA per output j; thread t adds blocks t, t+T, t+2T, ... in
+// that fixed order, then a fixed-shape shuffle/shared-memory tree combines the T partial sums, so the result
+// is bit-reproducible run to run.
 __global__ void k_reduce_partials(const double2* partial, int n_blocks, int stride, int n_out, double2* out) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double red[64];
+    const int j = blockIdx.x;
     if (j >= n_out) return;
     double re = 0.0, im = 0.0;
-    for (int b = 0; b < n_blocks; ++b) {
+    for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
         double2 p = partial[(size_t)b * stride + j];
         re += p.x;
         im += p.y;
     }
-    out[j] = make_double2(re, im);
+    double2 s = block_sum2(re, im, red);
+    if (threadIdx.x == 0) out[j] = s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1758,7 +1762,7 @@ extern "C" int vqe_expectation(vqe_ctx* c, int b, const vqe_paulisum* ps, double
         out[0] = out[1] = 0.0;
         return VQE_OK;
     }
-    k_reduce_partials<<<1, 32, 0, c->stream>>>(c->d_partial, (int)total_blocks, 1, 1, c->d_result);
+    k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, (int)total_blocks, 1, 1, c->d_result);
     c->launches++;
     c->d2h_bytes += sizeof(double2);
     CK(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
@@ -1917,7 +1921,7 @@ extern "C" int vqe_pool_overlaps(vqe_ctx* c, int bra, int ket, int n_ops, const 
                 (const DevPoolTerm*)(c->d_stage + off_terms), c->d_partial);
             c->launches++;
         }
-        k_reduce_partials<<<(np + 127) / 128, 128, 0, c->stream>>>(c->d_partial, gx, np, np, c->d_result);
+        k_reduce_partials<<<np, 64, 0, c->stream>>>(c->d_partial, gx, np, np, c->d_result);
         c->launches++;
         c->d2h_bytes += np * sizeof(double2);
         CK(cudaMemcpyAsync(c->h_result, c->d_result, np * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
@@ -1937,7 +1941,7 @@ static int inner_bufs(vqe_ctx* c, const double2* a, const double2* b, double* ou
     int rc = ensure_partial(c, blocks);
     if (rc) return rc;
     k_inner<<<blocks, 256, 0, c->stream>>>(a, b, c->n_amp, c->d_partial);
-    k_reduce_partials<<<1, 32, 0, c->stream>>>(c->d_partial, blocks, 1, 1, c->d_result);
+    k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, blocks, 1, 1, c->d_result);
     c->launches += 2;
     c->d2h_bytes += sizeof(double2);
     CK(cudaMemcpyAsync(c->h_result, c->d_result, sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
