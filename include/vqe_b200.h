@@ -59,7 +59,8 @@ uint64_t vqe_launch_count(const vqe_ctx* ctx);
 /* cumulative device time (ms) of the named kernel class since the last reset, measured with CUDA
  * events recorded around every launch on the context's stream while profiling is enabled (no extra
  * synchronisation; bench.py roofline leg).
- * which: 0 = state-preparation tile kernel, 1 = expectation kernel, 2 = pauli-sum apply, 3 = pool sweep */
+ * which: 0 = state-preparation tile kernel, 1 = expectation kernel, 2 = pauli-sum apply, 3 = pool sweep,
+ *        4 = state-preparation peer pass (sharded), 5 = expectation peer pass (sharded) */
 int vqe_profile_enable(vqe_ctx* ctx, int on);
 int vqe_profile_read(vqe_ctx* ctx, int which, double* ms_total, uint64_t* launches, int reset);
 
@@ -128,8 +129,55 @@ int vqe_norm2(vqe_ctx* ctx, int buf, double* out);
 /* out[0] + i out[1] = <a|b> for two device buffers */
 int vqe_inner(vqe_ctx* ctx, int a_buf, int b_buf, double* out_re_im);
 
-/* Raw device pointer / stream of a buffer (for the multi-GPU exchange layer, which wraps the
- * shard in a torch tensor for torch.distributed). */
+/* ------------------------------------------------------------------------------------------------
+ * Sharded state (nothing comparable exists in the reference, which stops at ~24
+ * qubits on one host).  The top n_global index bits -- reference qubits 0 .. n_global-1 -- are the rank;
+ * every rank owns one context holding 2^(n_qubits - n_global) amplitudes.  All entry points above keep
+ * their meaning on a sharded context with FULL-WIDTH masks: rotations / gates / Pauli strings whose
+ * X-mask flips global bits run as "peer passes" -- ONE kernel that stages the same tile of ranks r and
+ * r ^ m in shared memory (the partner's half read and written through peer memory over NVLink), applies
+ * every fusible operation and writes both halves back; the two ranks of a pair split the tiles.  Z
+ * letters on global qubits are per-rank signs and move no data.  Reductions (vqe_expectation,
+ * vqe_pool_overlaps, vqe_norm2, vqe_inner, vqe_overlap_host) return THIS RANK'S PARTIAL SUM; the caller
+ * adds the partials in rank order (torch.distributed all_gather in openvqe_b200/sharded.py).
+ *
+ * Two ways to connect the ranks:
+ *   - one process per GPU: vqe_shard_export -> exchange the 64-byte handles -> vqe_shard_attach_ipc.
+ *     Cross-rank ordering is a device-side flag barrier enqueued on the stream around every peer pass
+ *     (no host round trip, no collective library on the data path).  All ranks must issue the same calls.
+ *   - one process driving all ranks (tests on one GPU; single-process multi-GPU): vqe_shard_attach_local
+ *     and the vqe_group_* entry points, which launch every pass on all ranks and order the ranks'
+ *     streams with CUDA events. */
+#define VQE_IPC_HANDLE_BYTES 64
+#define VQE_SHARD_FLAGS 3 /* `what` id of the barrier flag array; 0..2 are the state buffers */
+int vqe_create_shard(vqe_ctx** out, int n_qubits, int n_global, int rank, int device);
+int vqe_shard_info(const vqe_ctx* ctx, int* n_global, int* rank, int* n_local);
+int vqe_shard_export(vqe_ctx* ctx, int what, void* handle_out /* VQE_IPC_HANDLE_BYTES */);
+int vqe_shard_attach_ipc(vqe_ctx* ctx, int peer_rank, int what, const void* handle);
+int vqe_shard_attach_local(vqe_ctx* ctx, vqe_ctx* peer);
+int vqe_shard_barrier(vqe_ctx* ctx); /* device-side barrier over all ranks, enqueued on the stream */
+int vqe_shard_status(vqe_ctx* ctx);  /* VQE_ERR_CUDA after a barrier timed out (a peer died) */
+
+/* in-process groups: ranks[k] must be rank k, n_ranks = 2^n_global */
+int vqe_group_apply_pauli_rotations(vqe_ctx* const* ranks, int n_ranks, int n_rot, const uint64_t* xmask,
+                                    const uint64_t* zmask, const int32_t* ny, const double* angle);
+int vqe_group_apply_gates(vqe_ctx* const* ranks, int n_ranks, int n_gates, const int32_t* kind,
+                          const int32_t* q0, const int32_t* q1, const double* angle);
+/* ps[k] = the Pauli sum created on ranks[k]; out = sum of the rank partials in rank order */
+int vqe_group_expectation(vqe_ctx* const* ranks, int n_ranks, int buf, const vqe_paulisum* const* ps, double* out_re_im);
+int vqe_group_apply_paulisum(vqe_ctx* const* ranks, int n_ranks, int dst_buf, int src_buf, const vqe_paulisum* const* ps);
+int vqe_group_pool_overlaps(vqe_ctx* const* ranks, int n_ranks, int bra_buf, int ket_buf, int n_ops,
+                            const int32_t* op_offsets, const uint64_t* xmask, const uint64_t* zmask,
+                            const int32_t* ny, const double* cre, const double* cim, double* out);
+
+/* Host-only view of the pass planner (no CUDA call): cuts an ordered rotation list into tile passes for a
+ * state with n_global rank bits.  pass_kind[p]: 0 = local pass, 1 = peer pass between ranks r and
+ * r ^ pass_pattern[p].  At most `cap` passes are written; *n_passes is the full count. */
+int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int low_bits, int n_rot, const uint64_t* xmask,
+                       const uint64_t* zmask, const int32_t* ny, const double* angle, int cap, int32_t* n_passes,
+                       int32_t* pass_kind, uint64_t* pass_pattern, int32_t* pass_n_ops, uint64_t* pass_tile_mask);
+
+/* Raw device pointer / stream of a buffer. */
 int vqe_buffer_ptr(vqe_ctx* ctx, int buf, void** dev_ptr, uint64_t* n_amplitudes);
 int vqe_synchronize(vqe_ctx* ctx);
 

@@ -137,7 +137,23 @@ def pool_overlaps(engine, hamiltonian_sp, pool_ops):
         if len(_PROG_CACHE) >= 256:
             _PROG_CACHE.clear()
         _PROG_CACHE[key] = (list(pool_ops), pool)
+    if replica_split_active(engine):
+        from . import sharded
+        return sharded.replica_pool_overlaps(engine, pool, bra=BUF_SIGMA, ket=BUF_PSI)
     return engine.pool_overlaps(pool, bra=BUF_SIGMA, ket=BUF_PSI)
+
+
+def replica_split_active(engine) -> bool:
+    """True when this process is one of several SPMD ranks (torchrun) working on a state that fits one GPU:
+    the pool sweep is then split over the ranks.  VQE_B200_REPLICA_POOL=0 switches it off."""
+    import os
+    import sys
+    if os.environ.get("VQE_B200_REPLICA_POOL", "1") == "0" or getattr(engine, "n_global", 0):
+        return False
+    if "torch.distributed" not in sys.modules:  # never import torch just to find out nothing is initialised
+        return False
+    from . import sharded
+    return sharded.dist_ready() and sharded._dist().get_world_size() > 1
 
 
 ZERO_TOL = 1e-14  # Hartree; far below the rounding noise of a 2^n-term fp64 reduction of O(1) values

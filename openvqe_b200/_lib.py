@@ -21,7 +21,13 @@ SYMBOLS = [
     "vqe_paulisum_create", "vqe_paulisum_destroy", "vqe_paulisum_groups", "vqe_paulisum_passes",
     "vqe_expectation", "vqe_apply_paulisum", "vqe_pool_overlaps", "vqe_apply_exp_paulisum",
     "vqe_overlap_host", "vqe_norm2", "vqe_inner", "vqe_buffer_ptr", "vqe_synchronize",
+    # sharded state
+    "vqe_create_shard", "vqe_shard_info", "vqe_shard_export", "vqe_shard_attach_ipc", "vqe_shard_attach_local",
+    "vqe_shard_barrier", "vqe_shard_status", "vqe_group_apply_pauli_rotations", "vqe_group_apply_gates",
+    "vqe_group_expectation", "vqe_group_apply_paulisum", "vqe_group_pool_overlaps", "vqe_plan_rotations",
 ]
+IPC_HANDLE_BYTES = 64
+SHARD_FLAGS = 3
 
 
 class VQEError(RuntimeError):
@@ -75,6 +81,20 @@ def load():
         "vqe_inner": (C.c_int, [vp, C.c_int, C.c_int, P(dbl)]),
         "vqe_buffer_ptr": (C.c_int, [vp, C.c_int, P(vp), P(u64)]),
         "vqe_synchronize": (C.c_int, [vp]),
+        "vqe_create_shard": (C.c_int, [P(vp), C.c_int, C.c_int, C.c_int, C.c_int]),
+        "vqe_shard_info": (C.c_int, [vp, P(C.c_int), P(C.c_int), P(C.c_int)]),
+        "vqe_shard_export": (C.c_int, [vp, C.c_int, vp]),
+        "vqe_shard_attach_ipc": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "vqe_shard_attach_local": (C.c_int, [vp, vp]),
+        "vqe_shard_barrier": (C.c_int, [vp]),
+        "vqe_shard_status": (C.c_int, [vp]),
+        "vqe_group_apply_pauli_rotations": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+        "vqe_group_apply_gates": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+        "vqe_group_expectation": (C.c_int, [vp, C.c_int, C.c_int, vp, P(dbl)]),
+        "vqe_group_apply_paulisum": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
+        "vqe_group_pool_overlaps": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+        "vqe_plan_rotations": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int,
+                                         vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -40,13 +40,21 @@ class PauliSum:
 
 
 class Engine:
-    def __init__(self, n_qubits: int, device: int = 0):
+    def __init__(self, n_qubits: int, device: int = 0, n_global: int = 0, rank: int = 0):
+        """``n_global`` > 0 creates ONE RANK of a sharded state (see ``openvqe_b200.sharded``): this context
+        then holds 2^(n_qubits - n_global) amplitudes and its reductions are per-rank partial sums."""
         lib = _lib.load()
         self._lib = lib
         self.n = int(n_qubits)
         self.device = int(device)
+        self.n_global = int(n_global)
+        self.rank = int(rank)
+        self.n_local = self.n - self.n_global
         self.handle = C.c_void_p()
-        _lib.check(lib.vqe_create(C.byref(self.handle), self.n, self.device))
+        if self.n_global:
+            _lib.check(lib.vqe_create_shard(C.byref(self.handle), self.n, self.n_global, self.rank, self.device))
+        else:
+            _lib.check(lib.vqe_create(C.byref(self.handle), self.n, self.device))
         self._finalizer = weakref.finalize(self, lib.vqe_destroy, self.handle)
         self._ps_cache = {}
 
@@ -56,12 +64,12 @@ class Engine:
 
     def set_state(self, vec, buf=BUF_PSI):
         v = np.ascontiguousarray(np.asarray(vec, dtype=np.complex128).reshape(-1))
-        if v.shape[0] != 1 << self.n:
-            raise ValueError("state has %d amplitudes, expected 2^%d" % (v.shape[0], self.n))
+        if v.shape[0] != 1 << self.n_local:
+            raise ValueError("state has %d amplitudes, expected 2^%d" % (v.shape[0], self.n_local))
         _lib.check(self._lib.vqe_set_state(self.handle, buf, _ptr(v)))
 
     def get_state(self, buf=BUF_PSI):
-        out = np.empty(1 << self.n, dtype=np.complex128)
+        out = np.empty(1 << self.n_local, dtype=np.complex128)
         _lib.check(self._lib.vqe_get_state(self.handle, buf, _ptr(out)))
         return out
 
@@ -179,13 +187,19 @@ class Engine:
 _ENGINES = {}
 
 
+_ENGINE_FACTORY = None  # set by openvqe_b200.sharded.enable(): (n_qubits, device) -> Engine or None
+
+
 def get_engine(n_qubits: int, device: int = 0) -> Engine:
     """Process-wide engine per (n_qubits, device): the state buffers are reused
     across the thousands of objective evaluations of one optimisation."""
     key = (int(n_qubits), int(device))
     eng = _ENGINES.get(key)
     if eng is None:
-        eng = Engine(*key)
+        if _ENGINE_FACTORY is not None:
+            eng = _ENGINE_FACTORY(*key)
+        if eng is None:
+            eng = Engine(*key)
         _ENGINES[key] = eng
     return eng
 

@@ -1,0 +1,89 @@
+"""CPU checks of the multi-GPU host logic: the peer-pass planner (pure host code in the C-ABI library), the
+rank-ordered reductions and the replica-mode pool split over a 2-rank gloo group (no GPU, no compute calls into
+the CUDA library)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rot(n, op, qb):
+    from openvqe_b200.lowering import term_masks
+    return term_masks(op, qb, n)
+
+
+def test_planner_local_vs_peer_passes():
+    from openvqe_b200.sharded import plan_rotations
+    n, g = 20, 2  # qubits 0,1 are global (index bits 19, 18); 18 local bits
+    prog = [
+        ("XY", [5, 9]),          # local
+        ("ZXZY", [0, 7, 8, 9]),  # Z on a global qubit only: still local, no traffic
+        ("XZY", [1, 3, 4]),      # X on global qubit 1 -> peer pass, pattern 0b01
+        ("YZZX", [1, 2, 3, 6]),  # same pattern: fused into the same peer pass
+        ("XX", [0, 1]),          # pattern 0b11: a new peer pass
+        ("XY", [10, 11]),        # local again (absorbed by the open peer pass: it costs no extra sweep)
+        ("YX", [0, 12]),         # pattern 0b10
+    ]
+    xs, zs, nys = zip(*[_rot(n, op, qb) for op, qb in prog])
+    passes = plan_rotations(n, g, xs, zs, nys, [0.1] * len(prog))
+    kinds = [p[0] for p in passes]
+    pats = [p[1] for p in passes]
+    assert sum(p[2] for p in passes) == len(prog)           # every rotation exactly once, order kept
+    assert kinds == [1, 1, 1] and pats == [0b01, 0b11, 0b10]
+    assert [p[2] for p in passes] == [4, 2, 1]
+    nl = n - g
+    for (kind, pat, nops, tmask), lo_hi in zip(passes, [(0, 4), (4, 6), (6, 7)]):
+        need = 0
+        for x in xs[lo_hi[0]:lo_hi[1]]:
+            need |= x & ((1 << nl) - 1)
+        assert need & ~tmask == 0                           # every local X bit is inside the tile
+        assert bin(tmask).count("1") == 11 and tmask & 31 == 31   # 12-bit tile minus the virtual shard bit; low 5 bits fixed
+    # without global qubits the same program only has local passes over 12-bit tiles
+    one = plan_rotations(n, 0, xs, zs, nys, [0.1] * len(prog))
+    assert all(p[0] == 0 and p[1] == 0 for p in one) and sum(p[2] for p in one) == len(prog)
+    assert all(bin(p[3]).count("1") == 12 for p in one)
+
+
+def test_planner_zero_angles_dropped_and_capacity_split():
+    from openvqe_b200.sharded import plan_rotations
+    n = 24
+    prog = [("X" * 1, [q]) for q in range(n)]
+    xs, zs, nys = zip(*[_rot(n, op, qb) for op, qb in prog])
+    angles = [0.2] * n
+    angles[3] = 0.0
+    passes = plan_rotations(n, 0, xs, zs, nys, angles)
+    assert sum(p[2] for p in passes) == n - 1
+    assert len(passes) >= 3          # 24 distinct X bits cannot share one 12-bit tile with 5 fixed low bits
+    for p in passes:
+        assert p[0] == 0
+
+
+def test_split_range_and_rank_order_sum():
+    from openvqe_b200.sharded import n_global_for, split_range, sum_in_rank_order
+    for n_items in [0, 1, 7, 285, 3159]:
+        for world in [1, 2, 4, 8]:
+            cover = []
+            for r in range(world):
+                lo, hi = split_range(n_items, world, r)
+                cover.extend(range(lo, hi))
+            assert cover == list(range(n_items))
+    assert [n_global_for(w) for w in (1, 2, 4, 8)] == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        n_global_for(6)
+    rows = np.array([[1e16, 1.0], [1.0, 1.0], [-1e16, 1.0]])
+    assert sum_in_rank_order(rows).tolist() == [0.0, 3.0]    # ((1e16 + 1) - 1e16): the fixed order is part of the contract
+
+
+def test_gloo_world2_host_logic():
+    """Two CPU processes over gloo: all-gather + rank-ordered sums give bit-identical totals on both ranks, and the
+    replica-mode pool sweep (each rank evaluates its slice, slices are gathered) equals the unsplit sweep."""
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(ROOT, "tests", "gloo_worker.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "gloo worker ok" in res.stdout
