@@ -243,7 +243,7 @@ def run_ours(args, rank, world, local_rank):
     for th in ths[:args.warmup]:
         step(th)
     # ---- timed: resident inputs -------------------------------------------------------------
-    for k in range(4):
+    for k in range(6):
         eng.profile_read(k, reset=True)
     eng.profile(True)
     eng.transfer_bytes(reset=True)
@@ -332,6 +332,150 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# C5: synthetic 30-36 qubit UCC rotations + expectation; sharded over the ranks when world > 1
+# ------------------------------------------------------------------------------------------------
+C5_DEFAULT_QUBITS = {1: 33, 2: 34, 4: 35, 8: 36}   # 2^33 amplitudes = 137 GB per GPU at every size (weak scaling)
+
+
+def run_c5(args, rank, world, local_rank):
+    import torch
+    from tools import c5_synthetic as c5
+    from openvqe_b200.engine import Engine
+    from openvqe_b200.lowering import PackedTerms
+    from openvqe_b200 import sharded
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.qubits or C5_DEFAULT_QUBITS.get(world, 33)
+    g = sharded.n_global_for(world)
+    nl = n - g
+    S_local = 16.0 * (1 << nl)
+    eng = sharded.ShardedEngine(n, local_rank) if world > 1 else Engine(n, device=local_rank)
+    gen, ham = c5.generators(n), c5.hamiltonian(n)
+    ps = eng.paulisum(PackedTerms(n, ham["x"], ham["z"], ham["ny"], ham["cre"], np.zeros_like(ham["cre"])))
+    hf = c5.hf_index(n)
+    owner, coeff = gen["owner"], gen["coeff"]
+    plan = sharded.plan_rotations(n, g, gen["x"], gen["z"], gen["ny"], gen["theta"][owner] * coeff)
+    n_local_pass = sum(1 for p in plan if p[0] == 0)
+    n_peer_pass = len(plan) - n_local_pass
+
+    def energy(theta):
+        eng.set_basis_state(hf)
+        eng.apply_rotations(gen["x"], gen["z"], gen["ny"], theta[owner] * coeff)
+        return eng.expectation(ps).real
+
+    fd_h = 1.4901161193847656e-08  # scipy's 2-point step
+
+    def step(theta):
+        e0 = energy(theta)
+        grad = []
+        for j in range(args.grad_components):
+            tj = theta.copy()
+            tj[j] += fd_h
+            grad.append((energy(tj) - e0) / fd_h)
+        return e0, grad
+
+    def barrier():
+        eng.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ths = [gen["theta"] * (1.0 + 0.01 * s) for s in range(args.warmup + args.steps)]
+    for th in ths[:args.warmup]:
+        step(th)
+    norm = eng.norm2()
+    for k in range(6):
+        eng.profile_read(k, reset=True)
+    eng.profile(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    l0 = eng.launch_count
+    eng.timer_begin()
+    t0 = time.perf_counter()
+    results = [step(th) for th in ths[args.warmup:]]
+    ms = eng.timer_end()
+    wall = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count - l0
+    ms = max_over_ranks(max(ms, wall))
+    prof = [eng.profile_read(k) for k in range(6)]
+    eng.profile(False)
+    prof = [(max_over_ranks(m), c) for m, c in prof]
+    verify = None
+    if args.verify and n <= 31:
+        # the same evaluation on ONE unsharded context (rank 0 only; needs 2^n amplitudes next to the shard)
+        if rank == 0:
+            one = Engine(n, device=local_rank)
+            ps1 = one.paulisum(PackedTerms(n, ham["x"], ham["z"], ham["ny"], ham["cre"], np.zeros_like(ham["cre"])))
+            one.set_basis_state(hf)
+            th = ths[args.warmup]
+            one.apply_rotations(gen["x"], gen["z"], gen["ny"], th[owner] * coeff)
+            verify = abs(one.expectation(ps1).real - results[0][0])
+            del one
+        barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    evals = args.steps * (1 + args.grad_components)
+    n_rot = int(np.count_nonzero(gen["theta"][owner] * coeff))
+    # local rotation pass: 2*S_local of HBM per rank; r rotations fused per pass are credited r*2*S
+    loc_ms, loc_n = prof[0]
+    peer_ms, peer_n = prof[4]
+    exl_ms, exl_n = prof[1]
+    exp_ms, exp_n = prof[5]
+    rot_alg = n_rot * 2.0 * S_local * evals
+    roofline = {"kernel": "k_tile_rot (local + peer passes)", "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+                "achieved": rot_alg / max((loc_ms + peer_ms) / 1e3, 1e-9) / 1e9,
+                "algorithmic_bytes_per_launch": rot_alg / max(loc_n + peer_n, 1),
+                "local_pass": {"launches_per_eval": loc_n / evals, "ms_per_launch": loc_ms / max(loc_n, 1),
+                               "physical_gbs": 2.0 * S_local * loc_n / max(loc_ms / 1e3, 1e-9) / 1e9},
+                "traffic": None, "share_of_step": (loc_ms + peer_ms) / ms}
+    roofline["frac"] = roofline["achieved"] / peak
+    nvlink = None
+    if world > 1:
+        # a peer pass moves, per rank, S_local/2 in and S_local/2 out over NVLink for the loads and the same again
+        # for the stores (the partner mirrors it): S_local per direction per pass
+        nvlink = {"kernel": "k_tile_rot peer pass (tiles of ranks r and r^m staged through peer memory)",
+                  "launches_per_eval": peer_n / evals, "ms_per_launch": peer_ms / max(peer_n, 1),
+                  "bytes_per_direction_per_launch": S_local,
+                  "achieved_gbs_per_direction": S_local * peer_n / max(peer_ms / 1e3, 1e-9) / 1e9,
+                  "peak_gbs_per_direction": 900.0, "peak_source": "NVLink 5 nominal per direction per GPU",
+                  "expectation_peer_pass": {"launches_per_eval": exp_n / evals, "ms_per_launch": exp_ms / max(exp_n, 1),
+                                            "achieved_gbs_in": 0.5 * S_local * exp_n / max(exp_ms / 1e3, 1e-9) / 1e9}}
+        nvlink["frac"] = nvlink["achieved_gbs_per_direction"] / 900.0
+    line = {"metric": "ucc_energy_evals_per_s", "value": evals / (ms / 1e3), "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",
+            "config": {"workload": "C5 synthetic %d-qubit UCC energy%s: %d Pauli rotations (256 generators) + <H> over %d terms / "
+                                   "%d X-mask groups, state sharded over %d GPU(s) (top %d qubits global)"
+                                   % (n, " + %d FD gradient component(s)" % args.grad_components if args.grad_components else "",
+                                      n_rot, len(ham["x"]), ham["n_groups"], world, g),
+                       "qubits": n, "shard_bytes": S_local, "l2_policy": "shard (%.0f GB) larger than L2" % (S_local / 1e9),
+                       "parallelism": "state sharded, peer passes over NVLink" if world > 1 else "1 GPU",
+                       "rotation_passes": {"local": n_local_pass, "peer": n_peer_pass},
+                       "expectation_passes": {"local": exl_n / evals, "peer": exp_n / evals},
+                       "energy_first_step": results[0][0], "gradient_first_step": results[0][1], "norm2_after_warmup": norm,
+                       "verify_vs_unsharded_abs_err": verify},
+            "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "nvlink": nvlink,
+            "expectation": {"local_ms_per_eval": exl_ms / evals, "peer_ms_per_eval": exp_ms / evals}}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,12 +483,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4: 24-qubit UCCSD energy (headline; replicas when N > 1).  c5: synthetic 30-36 qubit state SHARDED over the N GPUs")
+    ap.add_argument("--qubits", type=int, default=0, help="c5 only: register size (default 33/34/35/36 for 1/2/4/8 GPUs)")
+    ap.add_argument("--grad-components", type=int, default=0, help="c5 only: forward-difference gradient components per step")
+    ap.add_argument("--verify", action="store_true", help="c5 only, n <= 31: compare with one unsharded context on rank 0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "c5":
+        run_c5(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -197,3 +197,47 @@ def test_two_process_ipc(gpu_required):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "sharded worker ok" in res.stdout
+
+
+@pytest.mark.parametrize("n,g", [(12, 1), (14, 2)])
+def test_c5_synthetic_energy_vs_oracle(groups, n, g):
+    """BASELINE config 5 at a size the oracle finishes in seconds: 256 synthetic generators + 64-group Hamiltonian."""
+    from openvqe_b200.lowering import PackedTerms
+    from tools import c5_synthetic as c5
+    gen, ham = c5.generators(n), c5.hamiltonian(n)
+    ang = gen["theta"][gen["owner"]] * gen["coeff"]
+    hf = c5.hf_index(n)
+    grp = groups(n, g)
+    grp.set_basis_state(hf)
+    grp.apply_rotations(gen["x"], gen["z"], gen["ny"], ang)
+    ps = grp.paulisum(PackedTerms(n, ham["x"], ham["z"], ham["ny"], ham["cre"], np.zeros_like(ham["cre"])))
+    e = grp.expectation(ps)
+    ref = orc.basis_state(n, hf)
+    for x, z, ny, a in zip(gen["x"], gen["z"], gen["ny"], ang):
+        ref = orc.pauli_rotation(ref, int(x), int(z), int(ny), float(a))
+    e_ref = sum(c * np.vdot(ref, orc.apply_pauli(ref, int(x), int(z), int(ny))) for x, z, ny, c in
+                zip(ham["x"], ham["z"], ham["ny"], ham["cre"]))
+    assert np.max(np.abs(grp.get_state() - ref)) < TOL
+    assert abs(e.real - e_ref.real) < 1e-10 and abs(e.imag) < 1e-10   # north_star tolerance: 1e-10 Ha
+    assert abs(grp.norm2() - 1.0) < 1e-12
+
+
+def test_c5_synthetic_sharded_equals_unsharded_at_22_qubits(gpu_required):
+    """Size-independent property at a size the oracle cannot do: 8 virtual ranks vs one context, same energy."""
+    from openvqe_b200.engine import Engine
+    from openvqe_b200.lowering import PackedTerms
+    from openvqe_b200.sharded import ShardGroup
+    from tools import c5_synthetic as c5
+    n = 22
+    gen, ham = c5.generators(n, k_gen=64), c5.hamiltonian(n)
+    ang = gen["theta"][gen["owner"]] * gen["coeff"]
+    hp = PackedTerms(n, ham["x"], ham["z"], ham["ny"], ham["cre"], np.zeros_like(ham["cre"]))
+    out = []
+    for make in (lambda: Engine(n), lambda: ShardGroup(n, 3)):
+        e = make()
+        e.set_basis_state(c5.hf_index(n))
+        e.apply_rotations(gen["x"], gen["z"], gen["ny"], ang)
+        out.append((e.expectation(e.paulisum(hp)), e.norm2()))
+        del e
+    assert abs(out[0][0] - out[1][0]) < 1e-10
+    assert abs(out[0][1] - 1.0) < 1e-12 and abs(out[1][1] - 1.0) < 1e-12
