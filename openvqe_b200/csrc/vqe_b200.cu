@@ -457,11 +457,15 @@ __device__ __forceinline__ void rot_fast_run(double2* tile, const FastOp* __rest
 // Dedicated kernel for passes that consist only of fast (tangent-form) rotation runs -- the UCC case.
 // Kept separate from the general kernel so that it fits in 64 registers (2 x 512 threads per SM).
 // ------------------------------------------------------------------------------------------
-struct DevRun {        // 32 bytes: one run = consecutive fast rotations with the same lx and phase type
+struct DevRun {        // 48 bytes: one run = consecutive fast rotations with the same lx, phase type and pair signs
     uint32_t lx, hb;
     uint32_t begin, len;   // into the pass-local FastOp table
-    double cscale;         // prod cos(angle)
-    uint32_t imag, pad;
+    double cscale;         // 1.0, or the pending product of cosines when it must be applied now (overflow guard)
+    uint32_t imag;
+    uint32_t jm;           // bit j: sign of pair j relative to pair 0, constant over the run (see rot_run4)
+    uint32_t e0, e1, e2;   // ascending tile-bit positions where zeros are inserted into the thread index
+    uint32_t off1, off2;   // tile-index offsets of the thread's pairs: l_j = l_0 | (j&1 ? off1 : 0) | (j&2 ? off2 : 0)
+    uint32_t pad;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -475,83 +479,137 @@ __device__ __forceinline__ void tile_load_async(double2* tile, const Shards& src
     const uint32_t ts = 1u << g.tbits;
     for (uint32_t k = threadIdx.x; k < ts; k += blockDim.x) cp_async16(tile + k, amp_addr(g, src, base, k));
 }
-
-template <bool IMAG>
-__device__ __forceinline__ void rot_run4(double2* tile, const FastOp* tab, uint32_t lx, uint32_t hb, int len,
-                                         double cscale, uint32_t half) {
-    // 4 pairs per thread: pair index p_j = tid + j * blockDim
-    const uint32_t l0 = insert0(threadIdx.x, hb);
-    uint32_t jbase = 0;
-    for (uint32_t p0 = threadIdx.x; p0 < half; p0 += 4 * blockDim.x, jbase += 4) {
-        const uint32_t i0 = insert0(p0, hb), i1 = insert0(p0 + blockDim.x, hb);
-        const uint32_t i2 = insert0(p0 + 2 * blockDim.x, hb), i3 = insert0(p0 + 3 * blockDim.x, hb);
-        const bool v1 = p0 + blockDim.x < half, v2 = p0 + 2 * blockDim.x < half, v3 = p0 + 3 * blockDim.x < half;
-        double2 a0 = tile[i0], b0 = tile[i0 ^ lx];
-        double2 a1 = v1 ? tile[i1] : a0, b1 = v1 ? tile[i1 ^ lx] : b0;
-        double2 a2 = v2 ? tile[i2] : a0, b2 = v2 ? tile[i2 ^ lx] : b0;
-        double2 a3 = v3 ? tile[i3] : a0, b3 = v3 ? tile[i3 ^ lx] : b0;
-        // Two rotations per trip with the b registers ping-ponging (b -> c -> b): a is updated in place
-        // (dest = addend), the new partner goes to a fresh register, so no register copies are needed.
-#define ROT_STEP(A, B, C, J, THI, TLO, JM)                                                        \
-    {                                                                                            \
-        const double tj = __hiloint2double((int)((THI) ^ (((JM) << (31 - (J))) & 0x80000000u)), TLO); \
-        if (IMAG) {                                                                              \
-            C.x = fma(-tj, A.y, B.x);                                                            \
-            C.y = fma(tj, A.x, B.y);                                                             \
-            A.x = fma(-tj, B.y, A.x);                                                            \
-            A.y = fma(tj, B.x, A.y);                                                             \
-        } else {                                                                                 \
-            C.x = fma(tj, A.x, B.x);                                                             \
-            C.y = fma(tj, A.y, B.y);                                                             \
-            A.x = fma(-tj, B.x, A.x);                                                            \
-            A.y = fma(-tj, B.y, A.y);                                                            \
-        }                                                                                        \
-    }
-        int r = 0;
-#pragma unroll 1
-        for (; r + 1 < len; r += 2) {
-            const FastOp f = tab[r], h = tab[r + 1];
-            const uint32_t thi = (uint32_t)__double2hiint(f.t) ^ ((uint32_t)__popc(l0 & f.lz) << 31);
-            const uint32_t uhi = (uint32_t)__double2hiint(h.t) ^ ((uint32_t)__popc(l0 & h.lz) << 31);
-            const int tlo = __double2loint(f.t), ulo = __double2loint(h.t);
-            const uint32_t jm = f.meta >> jbase, km = h.meta >> jbase;
-            double2 c0, c1, c2, c3;
-            ROT_STEP(a0, b0, c0, 0, thi, tlo, jm)
-            ROT_STEP(a1, b1, c1, 1, thi, tlo, jm)
-            ROT_STEP(a2, b2, c2, 2, thi, tlo, jm)
-            ROT_STEP(a3, b3, c3, 3, thi, tlo, jm)
-            ROT_STEP(a0, c0, b0, 0, uhi, ulo, km)
-            ROT_STEP(a1, c1, b1, 1, uhi, ulo, km)
-            ROT_STEP(a2, c2, b2, 2, uhi, ulo, km)
-            ROT_STEP(a3, c3, b3, 3, uhi, ulo, km)
-        }
-        if (r < len) {
-            const FastOp f = tab[r];
-            const uint32_t thi = (uint32_t)__double2hiint(f.t) ^ ((uint32_t)__popc(l0 & f.lz) << 31);
-            const int tlo = __double2loint(f.t);
-            const uint32_t jm = f.meta >> jbase;
-            double2 c0, c1, c2, c3;
-            ROT_STEP(a0, b0, c0, 0, thi, tlo, jm)
-            ROT_STEP(a1, b1, c1, 1, thi, tlo, jm)
-            ROT_STEP(a2, b2, c2, 2, thi, tlo, jm)
-            ROT_STEP(a3, b3, c3, 3, thi, tlo, jm)
-            b0 = c0; b1 = c1; b2 = c2; b3 = c3;
-        }
-#undef ROT_STEP
-        tile[i0] = make_double2(cscale * a0.x, cscale * a0.y);
-        tile[i0 ^ lx] = make_double2(cscale * b0.x, cscale * b0.y);
-        if (v1) { tile[i1] = make_double2(cscale * a1.x, cscale * a1.y); tile[i1 ^ lx] = make_double2(cscale * b1.x, cscale * b1.y); }
-        if (v2) { tile[i2] = make_double2(cscale * a2.x, cscale * a2.y); tile[i2 ^ lx] = make_double2(cscale * b2.x, cscale * b2.y); }
-        if (v3) { tile[i3] = make_double2(cscale * a3.x, cscale * a3.y); tile[i3 ^ lx] = make_double2(cscale * b3.x, cscale * b3.y); }
+__device__ __forceinline__ void tile_store_scaled(const double2* tile, const Shards& dst, const TileGeom& g,
+                                                  uint64_t base, double scale) {
+    const uint32_t ts = 1u << g.tbits;
+#pragma unroll 4
+    for (uint32_t k = threadIdx.x; k < ts; k += blockDim.x) {
+        const double2 v = tile[k];
+        *amp_addr(g, dst, base, k) = make_double2(scale * v.x, scale * v.y);
     }
 }
 
+// One run of tangent-form rotations on 4 register-resident pairs per thread.
+//   R = c [[1, -+t], [+-t, 1]]: the unnormalised update costs one DFMA per real component; the cosines are
+//   collected by the host into ONE scale per pass, applied when the tile is stored (every rotation touches
+//   every amplitude, so the product is common to the whole tile).
+//   The sign (-1)^parity(l & lz) of a pair splits into a per-thread part (one POPC per rotation, folded into
+//   the sign of t) and a per-pair part m_j.  The host picks the two tile bits (off1, off2) that enumerate a
+//   thread's four pairs among the bits where NO string of the run carries an X/Y letter and where the strings'
+//   Z letters agree, so m_j is the same for every rotation of the run (it cuts the run where that fails).  The
+//   partner amplitudes are then kept in the convention b~_j = m_j b_j,
+//       a' = a - (s t) b~ ,  b~' = b~ + (s t) a        (and the analogous form for the +-i phase),
+//   i.e. two sign flips per pair per RUN and nothing per rotation: the loop is LDS + LOP + POPC + 2 integer ops
+//   + 16 DFMA per rotation, FP64-pipe bound.  Two rotations per trip, the b registers ping-ponging (b -> c -> b).
+//   REAL: the tile is known to be purely real and the phase is +-1, so the imaginary halves are skipped.
+template <bool IMAG, bool REAL>
+__device__ __forceinline__ void rot_run4(double2* tile, const FastOp* tab, const DevRun& rn, bool four) {
+    const uint32_t lx = rn.lx;
+    uint32_t l0;
+    if (four) l0 = insert0(insert0(insert0(threadIdx.x, rn.e0), rn.e1), rn.e2);
+    else {
+        if (threadIdx.x >= (1u << rn.pad)) return;  // pad = log2(pairs in the tile) when there is one pair per thread
+        l0 = insert0(threadIdx.x, rn.hb);
+    }
+    const uint32_t i0 = l0, i1 = l0 | rn.off1, i2 = l0 | rn.off2, i3 = l0 | rn.off1 | rn.off2;
+    double2 a0, a1, a2, a3, b0, b1, b2, b3;
+#define ROT_LD(A, B, I)                                                                           \
+    if (REAL) { A.x = tile[I].x; B.x = tile[(I) ^ lx].x; A.y = B.y = 0.0; }                        \
+    else { A = tile[I]; B = tile[(I) ^ lx]; }
+    ROT_LD(a0, b0, i0)
+    if (four) {
+        ROT_LD(a1, b1, i1)
+        ROT_LD(a2, b2, i2)
+        ROT_LD(a3, b3, i3)
+    } else {
+        a1 = a2 = a3 = a0;
+        b1 = b2 = b3 = b0;
+    }
+#undef ROT_LD
+#define ROT_NEG(B) { B.x = -B.x; if (!REAL) B.y = -B.y; }
+    const uint32_t jm = rn.jm;
+    if (jm & 2u) ROT_NEG(b1)
+    if (jm & 4u) ROT_NEG(b2)
+    if (jm & 8u) ROT_NEG(b3)
+#define ROT_STEP(A, B, C, T)                                                                     \
+    {                                                                                            \
+        if (IMAG) {                                                                              \
+            C.x = fma(-T, A.y, B.x);                                                             \
+            C.y = fma(T, A.x, B.y);                                                              \
+            A.x = fma(-T, B.y, A.x);                                                             \
+            A.y = fma(T, B.x, A.y);                                                              \
+        } else {                                                                                 \
+            C.x = fma(T, A.x, B.x);                                                              \
+            A.x = fma(-T, B.x, A.x);                                                             \
+            if (!REAL) {                                                                         \
+                C.y = fma(T, A.y, B.y);                                                          \
+                A.y = fma(-T, B.y, A.y);                                                         \
+            }                                                                                    \
+        }                                                                                        \
+    }
+#define ROT_T(F) __hiloint2double((int)((uint32_t)__double2hiint((F).t) ^ ((uint32_t)__popc(l0 & (F).lz) << 31)), \
+                                  __double2loint((F).t))
+    const int len = (int)rn.len;
+    int r = 0;
+#pragma unroll 1
+    for (; r + 1 < len; r += 2) {
+        const FastOp f = tab[r], h = tab[r + 1];
+        const double tf = ROT_T(f), th = ROT_T(h);
+        double2 c0, c1, c2, c3;
+        ROT_STEP(a0, b0, c0, tf)
+        ROT_STEP(a1, b1, c1, tf)
+        ROT_STEP(a2, b2, c2, tf)
+        ROT_STEP(a3, b3, c3, tf)
+        ROT_STEP(a0, c0, b0, th)
+        ROT_STEP(a1, c1, b1, th)
+        ROT_STEP(a2, c2, b2, th)
+        ROT_STEP(a3, c3, b3, th)
+    }
+    if (r < len) {
+        const FastOp f = tab[r];
+        const double tf = ROT_T(f);
+        double2 c0, c1, c2, c3;
+        ROT_STEP(a0, b0, c0, tf)
+        ROT_STEP(a1, b1, c1, tf)
+        ROT_STEP(a2, b2, c2, tf)
+        ROT_STEP(a3, b3, c3, tf)
+        b0.x = c0.x; b1.x = c1.x; b2.x = c2.x; b3.x = c3.x;
+        if (!REAL) { b0.y = c0.y; b1.y = c1.y; b2.y = c2.y; b3.y = c3.y; }
+    }
+    if (jm & 2u) ROT_NEG(b1)
+    if (jm & 4u) ROT_NEG(b2)
+    if (jm & 8u) ROT_NEG(b3)
+    const double cs = rn.cscale;
+    if (cs != 1.0) {
+        a0.x *= cs; a0.y *= cs; b0.x *= cs; b0.y *= cs;
+        a1.x *= cs; a1.y *= cs; b1.x *= cs; b1.y *= cs;
+        a2.x *= cs; a2.y *= cs; b2.x *= cs; b2.y *= cs;
+        a3.x *= cs; a3.y *= cs; b3.x *= cs; b3.y *= cs;
+    }
+#undef ROT_T
+#undef ROT_STEP
+#undef ROT_NEG
+#define ROT_ST(A, B, I)                                                                           \
+    if (REAL) { tile[I].x = A.x; tile[(I) ^ lx].x = B.x; }                                        \
+    else { tile[I] = A; tile[(I) ^ lx] = B; }
+    ROT_ST(a0, b0, i0)
+    if (four) {
+        ROT_ST(a1, b1, i1)
+        ROT_ST(a2, b2, i2)
+        ROT_ST(a3, b3, i3)
+    }
+#undef ROT_ST
+}
+
+// REAL: the state is known to be purely real on entry and every run of the pass has a +-1 phase (ny odd: the
+// UCC case -- JW images of T - T^dagger), so the imaginary parts stay exactly zero and are never touched.
+template <bool REAL>
 __global__ void __launch_bounds__(512, 2) k_tile_rot(Shards psi, TileGeom g,
                                                      const DevOp* __restrict__ ops, int n_ops,
-                                                     const DevRun* __restrict__ runs, int n_runs) {
+                                                     const DevRun* __restrict__ runs, int n_runs, double pass_scale) {
     extern __shared__ double2 tile[];
     const uint32_t ts = 1u << g.tbits;
-    const uint32_t half = ts >> 1;
+    const bool four = (ts >> 1) == 4u * blockDim.x;  // host guarantees: 4 pairs per thread, or exactly 1
     FastOp* optab = (FastOp*)(tile + ts);
     DevRun* srun = (DevRun*)(optab + n_ops);
     for (int q = threadIdx.x; q < n_runs; q += blockDim.x) srun[q] = runs[q];
@@ -563,18 +621,19 @@ __global__ void __launch_bounds__(512, 2) k_tile_rot(Shards psi, TileGeom g,
             FastOp f;
             f.t = flipsign(ops[r].s, __popcll(sbase & ops[r].zout));
             f.lz = ops[r].lz;
-            f.meta = ops[r].jmask;
+            f.meta = 0;
             optab[r] = f;
         }
         cp_async_wait_all();
         for (int q = 0; q < n_runs; ++q) {
             __syncthreads();
-            const DevRun rn = srun[q];
-            if (rn.imag) rot_run4<true>(tile, optab + rn.begin, rn.lx, rn.hb, (int)rn.len, rn.cscale, half);
-            else rot_run4<false>(tile, optab + rn.begin, rn.lx, rn.hb, (int)rn.len, rn.cscale, half);
+            const DevRun& rn = srun[q];
+            if (REAL) rot_run4<false, true>(tile, optab + rn.begin, rn, four);
+            else if (rn.imag) rot_run4<true, false>(tile, optab + rn.begin, rn, four);
+            else rot_run4<false, false>(tile, optab + rn.begin, rn, four);
         }
         __syncthreads();
-        tile_store(tile, psi, g, base);
+        tile_store_scaled(tile, psi, g, base, pass_scale);
         __syncthreads();
     }
 }
@@ -993,6 +1052,7 @@ struct vqe_ctx {
     int* h_err = nullptr;                   // mapped pinned: set by a barrier that timed out
     int* d_err = nullptr;
     cudaEvent_t ev_bar = nullptr;           // in-process group barrier
+    bool psi_real = false;                  // buffer 0 is known to be purely real (imaginary parts exactly 0.0)
     cudaStream_t stream = nullptr;
     double2* buf[3] = {nullptr, nullptr, nullptr};
     // staging
@@ -1129,7 +1189,8 @@ static int set_kernel_attrs(int device) {
                                 maxs - (int)fa_.sharedSizeBytes));                               \
     } while (0)
     SET_SMEM(k_tile_ops);
-    SET_SMEM(k_tile_rot);
+    SET_SMEM(k_tile_rot<false>);
+    SET_SMEM(k_tile_rot<true>);
     SET_SMEM(k_tile_expect<false>);
     SET_SMEM(k_tile_expect<true>);
     SET_SMEM(k_tile_apply);
@@ -1500,6 +1561,7 @@ extern "C" int vqe_set_basis_state(vqe_ctx* c, uint64_t index) {
     // sharded: only the rank that owns the index holds the 1 (an out-of-range local index leaves the shard zero)
     const uint64_t local = ((int)(index >> c->nl) == c->rank) ? (index & (c->n_amp - 1)) : ~0ull;
     k_zero_set<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[0], c->n_amp, local);
+    c->psi_real = true;
     c->launches++;
     CK(cudaGetLastError());
     return VQE_OK;
@@ -1511,6 +1573,7 @@ extern "C" int vqe_set_state(vqe_ctx* c, int b, const double* re_im) {
     int rc = ensure_buf(c, b);
     if (rc) return rc;
     c->h2d_bytes += c->n_amp * sizeof(double2);
+    if (b == VQE_BUF_PSI) c->psi_real = false;
     CK(cudaMemcpyAsync(c->buf[b], re_im, c->n_amp * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return VQE_OK;
@@ -1533,6 +1596,7 @@ extern "C" int vqe_copy_buffer(vqe_ctx* c, int dst, int src) {
     rc = ensure_buf(c, src);
     if (rc) return rc;
     if (dst == src) return VQE_OK;
+    if (dst == VQE_BUF_PSI) c->psi_real = false;
     CK(cudaMemcpyAsync(c->buf[dst], c->buf[src], c->n_amp * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
     return VQE_OK;
 }
@@ -1542,6 +1606,7 @@ extern "C" int vqe_buffer_ptr(vqe_ctx* c, int b, void** p, uint64_t* n_amp) {
     int rc = ensure_buf(c, b);
     if (rc) return rc;
     *p = c->buf[b];
+    if (b == VQE_BUF_PSI) c->psi_real = false;  // the caller may write through the pointer
     if (n_amp) *n_amp = c->n_amp;
     return VQE_OK;
 }
@@ -1572,6 +1637,7 @@ struct OpPass {
     size_t op_begin, op_end;            // in the dev op array
     size_t run_begin = 0, run_end = 0;  // in the dev run array (fast passes only)
     bool fast = false;
+    double pass_scale = 1.0;            // fast passes: product of the cosines not yet applied by a run
 };
 struct OpPlan {
     std::vector<OpPass> passes;
@@ -1664,7 +1730,7 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
         const int n_j = (int)std::max<uint64_t>(1, ((1ull << p.tp.tbits) / 2) / threads_p);
         for (size_t k = p.op_begin; k < p.op_end; ++k) {
             DevOp& d = dops[k];
-            if (d.kind != OP_ROT || d.lx == 0 || fabs(d.c) < 0.3 || n_j > 32) continue;
+            if (d.kind != OP_ROT || d.lx == 0 || fabs(d.c) < 0.3 || n_j > 16) continue;
             d.kind = OP_ROTF;
             d.imag = (d.k4 & 1u);
             double tn = d.s / d.c;
@@ -1678,6 +1744,8 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
             }
             d.jmask = jm;
         }
+        std::vector<double> rot_cos(p.op_end - p.op_begin);  // per-rotation cosines (the run heads get overwritten below)
+        for (size_t k = p.op_begin; k < p.op_end; ++k) rot_cos[k - p.op_begin] = dops[k].c;
         // run lengths of consecutive same-lx rotations of the same kind; fast runs carry prod(c) in the head
         for (size_t k = p.op_begin; k < p.op_end;) {
             if (dops[k].kind != OP_ROT && dops[k].kind != OP_ROTF) { ++k; continue; }
@@ -1695,20 +1763,85 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
         p.fast = true;
         for (size_t k = p.op_begin; k < p.op_end; ++k)
             if (dops[k].kind != OP_ROTF) p.fast = false;
+        const uint32_t half_p = (1u << p.tp.tbits) >> 1;
+        const bool four = half_p == 4u * (uint32_t)threads_p;
+        if (!(four || half_p <= (uint32_t)threads_p)) p.fast = false;  // k_tile_rot holds 4 pairs per thread, or 1
         if (p.fast) {
             p.run_begin = druns.size();
-            for (size_t k = p.op_begin; k < p.op_end; k += dops[k].run) {
-                DevRun r;
-                r.lx = dops[k].lx;
-                r.hb = dops[k].hb;
-                r.begin = (uint32_t)(k - p.op_begin);
-                r.len = dops[k].run;
-                r.cscale = dops[k].c;
-                r.imag = dops[k].imag;
-                r.pad = 0;
-                druns.push_back(r);
+            double pending = 1.0;  // cosines are applied once per pass (tile store) unless the product gets tiny
+            const size_t druns_mark = druns.size();
+            for (size_t k = p.op_begin; k < p.op_end && p.fast;) {
+                size_t e = k + 1;
+                while (e < p.op_end && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
+                uint32_t d0 = 0, d1 = 0;
+                if (four) {
+                    // the two tile bits that enumerate a thread's pairs: no X/Y letter there, and preferably the
+                    // same Z letter in every string of the run, so the pair signs stay constant (rot_run4)
+                    uint32_t var = 0;
+                    for (size_t q = k; q < e; ++q) var |= dops[q].lz ^ dops[k].lz;
+                    int pick[2], np = 0;
+                    for (int want_var = 0; want_var < 2 && np < 2; ++want_var)
+                        for (int lowpass = 0; lowpass < 2 && np < 2; ++lowpass)  // first bits >= 5 (bank-conflict free), then the rest
+                            for (int b = p.tp.tbits - 1; b >= 0 && np < 2; --b) {
+                                if ((dops[k].lx >> b) & 1u) continue;
+                                if ((int)((var >> b) & 1u) != want_var) continue;
+                                if ((b >= 5) == (lowpass == 1)) continue;
+                                if (np == 1 && pick[0] == b) continue;
+                                pick[np++] = b;
+                            }
+                    if (np < 2) {  // X/Y letters on (almost) every tile bit: leave the pass to the general kernel
+                        p.fast = false;
+                        break;
+                    }
+                    d0 = (uint32_t)std::min(pick[0], pick[1]);
+                    d1 = (uint32_t)std::max(pick[0], pick[1]);
+                }
+                const uint32_t off1 = four ? 1u << d0 : 0u, off2 = four ? 1u << d1 : 0u;
+                auto jm_of = [&](const DevOp& d) {
+                    uint32_t jm = 0;
+                    if (__builtin_popcount(off1 & d.lz) & 1) jm |= 2u | 8u;
+                    if (__builtin_popcount(off2 & d.lz) & 1) jm ^= 4u | 8u;
+                    return jm;
+                };
+                for (size_t q = k; q < e;) {
+                    size_t qe = q + 1;
+                    const uint32_t jm = jm_of(dops[q]);
+                    while (qe < e && jm_of(dops[qe]) == jm) ++qe;
+                    DevRun r;
+                    memset(&r, 0, sizeof r);
+                    r.lx = dops[q].lx;
+                    r.hb = dops[q].hb;
+                    r.begin = (uint32_t)(q - p.op_begin);
+                    r.len = (uint32_t)(qe - q);
+                    r.imag = dops[q].imag;
+                    r.jm = jm;
+                    uint32_t pos[3] = {r.hb, d0, d1};
+                    std::sort(pos, pos + 3);
+                    r.e0 = pos[0]; r.e1 = pos[1]; r.e2 = pos[2];
+                    r.off1 = off1;
+                    r.off2 = off2;
+                    r.pad = 31 - __builtin_clz(half_p ? half_p : 1u);
+                    r.cscale = 1.0;
+                    druns.push_back(r);
+                    q = qe;
+                }
+                k = e;
             }
-            p.run_end = druns.size();
+            if (!p.fast) {
+                druns.resize(druns_mark);
+            } else {
+                // pending product of cosines, run by run
+                for (size_t ri = druns_mark; ri < druns.size(); ++ri) {
+                    DevRun& r = druns[ri];
+                    for (uint32_t w = 0; w < r.len; ++w) pending *= rot_cos[r.begin + w];
+                    if (fabs(pending) < 1e-30) {  // unnormalised amplitudes have grown by 1e30: rescale now
+                        r.cscale = pending;
+                        pending = 1.0;
+                    }
+                }
+                p.pass_scale = pending;
+                p.run_end = druns.size();
+            }
         }
         passes.push_back(std::move(p));
         i = j;
@@ -1751,6 +1884,21 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
         c->h2d_bytes += total;
         CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
     }
+    // Purely real state (set_basis_state, then only +-1-phase fast rotations -- the UCC case): the passes skip the
+    // imaginary halves.  All ranks of a sharded state see the same op list, so the flag stays consistent.
+    std::vector<char> real_pass(passes.size(), 0);
+    {
+        bool real = true;
+        for (vqe_ctx* c : rs.r) real = real && c->psi_real;
+        for (size_t p = 0; p < passes.size(); ++p) {
+            bool keeps = passes[p].fast;
+            for (size_t r = passes[p].run_begin; keeps && r < passes[p].run_end; ++r)
+                if (plan.druns[r].imag) keeps = false;
+            real = real && keeps;
+            real_pass[p] = real ? 1 : 0;
+        }
+        for (vqe_ctx* c : rs.r) c->psi_real = real;
+    }
     bool fenced = false;  // a cross-rank barrier separates the previous pass from the next one
     for (size_t p = 0; p < passes.size(); ++p) {
         const OpPass& ps = passes[p];
@@ -1769,10 +1917,14 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
                           (ps.run_end - ps.run_begin) * sizeof(DevRun);
             int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
             ProfScope prof(c, ps.tp.vbit ? 4 : 0);
-            if (ps.fast)
-                k_tile_rot<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
+            if (ps.fast && real_pass[p])
+                k_tile_rot<true><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                     sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
-                    (const DevRun*)(c->d_stage + off_runs) + ps.run_begin, (int)(ps.run_end - ps.run_begin));
+                    (const DevRun*)(c->d_stage + off_runs) + ps.run_begin, (int)(ps.run_end - ps.run_begin), ps.pass_scale);
+            else if (ps.fast)
+                k_tile_rot<false><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
+                    sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
+                    (const DevRun*)(c->d_stage + off_runs) + ps.run_begin, (int)(ps.run_end - ps.run_begin), ps.pass_scale);
             else
                 k_tile_ops<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                     sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
@@ -1860,6 +2012,15 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
         if (pass_pattern) pass_pattern[p] = plan.passes[p].tp.gpat;
         if (pass_n_ops) pass_n_ops[p] = (int32_t)(plan.passes[p].op_end - plan.passes[p].op_begin);
         if (pass_tile_mask) pass_tile_mask[p] = plan.passes[p].tp.tile_mask;
+    }
+    if (getenv("VQE_DEBUG_PLAN")) {
+        size_t nruns = plan.druns.size(), nfast = 0, lens[9] = {0};
+        for (const OpPass& p : plan.passes) nfast += p.fast ? 1 : 0;
+        for (const DevRun& r : plan.druns) lens[std::min<uint32_t>(r.len, 8)]++;
+        fprintf(stderr, "[plan] passes %zu (fast %zu) ops %zu runs %zu; run-length histogram 1..8+:", plan.passes.size(), nfast,
+                plan.dops.size(), nruns);
+        for (int k = 1; k <= 8; ++k) fprintf(stderr, " %zu", lens[k]);
+        fprintf(stderr, "\n");
     }
     return VQE_OK;
 }
@@ -2296,6 +2457,8 @@ static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* 
         rc = ensure_buf(c, src);
         if (rc) return rc;
     }
+    if (dst == VQE_BUF_PSI)
+        for (vqe_ctx* c : rs.r) c->psi_real = false;
     const size_t n_pass = pss[0]->passes.size();
     if (n_pass == 0) {
         for (vqe_ctx* c : rs.r) {
@@ -2669,6 +2832,7 @@ extern "C" int vqe_apply_exp_paulisum(vqe_ctx* c, int n_terms, const uint64_t* x
         free_paulisum_device(&ps);
         return fail(VQE_ERR_INVALID, "exact exponential of non-commuting strings is not available on a sharded state");
     }
+    c->psi_real = false;
     double2* term = c->buf[VQE_BUF_SIGMA];
     double2* next = c->buf[VQE_BUF_WORK];
     double2* psi = c->buf[VQE_BUF_PSI];
