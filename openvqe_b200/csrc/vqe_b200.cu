@@ -101,12 +101,15 @@ struct Shards {
     double2* p1;
 };
 
-struct DevGroup {     // one X-mask group of a Pauli sum inside a pass
+struct DevGroup {     // 40 bytes: one X-mask group of a Pauli sum inside a pass
     uint32_t lx, hb;
     uint32_t t_begin;  // first term (index into the pass-local term list)
     uint32_t n_even;   // terms with even ny come first, then n_odd terms with odd ny
     uint32_t n_odd;
     uint32_t pad;
+    // k_tile_expect: inside each parity block the terms are sorted by sign class (see the kernel);
+    // lx != 0: cnt[0..3] = even-ny classes, cnt[4..7] = odd-ny classes; lx == 0: cnt[0..7] = the 8 classes
+    uint16_t cnt[8];
 };
 struct DevTerm {      // 32 bytes
     uint64_t zout;
@@ -457,15 +460,27 @@ __device__ __forceinline__ void rot_fast_run(double2* tile, const FastOp* __rest
 // Dedicated kernel for passes that consist only of fast (tangent-form) rotation runs -- the UCC case.
 // Kept separate from the general kernel so that it fits in 64 registers (2 x 512 threads per SM).
 // ------------------------------------------------------------------------------------------
-struct DevRun {        // 48 bytes: one run = consecutive fast rotations with the same lx, phase type and pair signs
-    uint32_t lx, hb;
-    uint32_t begin, len;   // into the pass-local FastOp table
+// k_tile_rot works on ORBITS: a thread holds the 8 amplitudes x_beta = psi[l0 ^ beta0 v0 ^ beta1 v1 ^ beta2 v2]
+// (v_i = tile-index vectors chosen by the host, l0 = the coset representative with zeros at the 3 pivot bits).
+// Any rotation whose X-mask lies in span(v0, v1, v2) acts inside the orbit, so up to three different generators
+// (24 Pauli strings) are applied between one shared-memory load and store of the amplitudes.
+struct RotOp {         // 32 bytes, shared-memory copy of a fast rotation, refreshed per tile
+    double t;          // tan(angle) * (unit-phase sign) * (-1)^popc(outside-tile index bits & z)
+    uint32_t lz;       // Z letters inside the tile
+    uint32_t mq[3];    // sign words (0 or 0x80000000): parity(v_i & lz), the sign step along orbit direction i
+    uint32_t pad[2];
+};
+struct DevSub {        // 16 bytes: consecutive fast rotations with the same orbit pattern and phase type
+    uint32_t begin, len;   // into the pass-local RotOp table
+    uint32_t c;            // pairs are (beta, beta ^ c), c in 1..7 (orbit coordinates of the X-mask)
+    uint32_t imag;         // unit phase +-i (ny even) instead of +-1
+};
+struct DevSuper {      // 64 bytes: one shared-memory round trip
+    uint32_t e0, e1, e2;   // ascending pivot positions: zeros are inserted there into the thread index
+    uint32_t sub_begin, sub_count;
+    uint32_t hb_log;       // tiles with one pair per thread: log2(pairs in the tile)
     double cscale;         // 1.0, or the pending product of cosines when it must be applied now (overflow guard)
-    uint32_t imag;
-    uint32_t jm;           // bit j: sign of pair j relative to pair 0, constant over the run (see rot_run4)
-    uint32_t e0, e1, e2;   // ascending tile-bit positions where zeros are inserted into the thread index
-    uint32_t off1, off2;   // tile-index offsets of the thread's pairs: l_j = l_0 | (j&1 ? off1 : 0) | (j&2 ? off2 : 0)
-    uint32_t pad;
+    uint32_t off[8];       // off[beta] = XOR of the v_i selected by beta
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -489,152 +504,183 @@ __device__ __forceinline__ void tile_store_scaled(const double2* tile, const Sha
     }
 }
 
-// One run of tangent-form rotations on 4 register-resident pairs per thread.
-//   R = c [[1, -+t], [+-t, 1]]: the unnormalised update costs one DFMA per real component; the cosines are
-//   collected by the host into ONE scale per pass, applied when the tile is stored (every rotation touches
-//   every amplitude, so the product is common to the whole tile).
-//   The sign (-1)^parity(l & lz) of a pair splits into a per-thread part (one POPC per rotation, folded into
-//   the sign of t) and a per-pair part m_j.  The host picks the two tile bits (off1, off2) that enumerate a
-//   thread's four pairs among the bits where NO string of the run carries an X/Y letter and where the strings'
-//   Z letters agree, so m_j is the same for every rotation of the run (it cuts the run where that fails).  The
-//   partner amplitudes are then kept in the convention b~_j = m_j b_j,
-//       a' = a - (s t) b~ ,  b~' = b~ + (s t) a        (and the analogous form for the +-i phase),
-//   i.e. two sign flips per pair per RUN and nothing per rotation: the loop is LDS + LOP + POPC + 2 integer ops
-//   + 16 DFMA per rotation, FP64-pipe bound.  Two rotations per trip, the b registers ping-ponging (b -> c -> b).
-//   REAL: the tile is known to be purely real and the phase is +-1, so the imaginary halves are skipped.
-template <bool IMAG, bool REAL>
-__device__ __forceinline__ void rot_run4(double2* tile, const FastOp* tab, const DevRun& rn, bool four) {
-    const uint32_t lx = rn.lx;
-    uint32_t l0;
-    if (four) l0 = insert0(insert0(insert0(threadIdx.x, rn.e0), rn.e1), rn.e2);
-    else {
-        if (threadIdx.x >= (1u << rn.pad)) return;  // pad = log2(pairs in the tile) when there is one pair per thread
-        l0 = insert0(threadIdx.x, rn.hb);
-    }
-    const uint32_t i0 = l0, i1 = l0 | rn.off1, i2 = l0 | rn.off2, i3 = l0 | rn.off1 | rn.off2;
-    double2 a0, a1, a2, a3, b0, b1, b2, b3;
-#define ROT_LD(A, B, I)                                                                           \
-    if (REAL) { A.x = tile[I].x; B.x = tile[(I) ^ lx].x; A.y = B.y = 0.0; }                        \
-    else { A = tile[I]; B = tile[(I) ^ lx]; }
-    ROT_LD(a0, b0, i0)
-    if (four) {
-        ROT_LD(a1, b1, i1)
-        ROT_LD(a2, b2, i2)
-        ROT_LD(a3, b3, i3)
-    } else {
-        a1 = a2 = a3 = a0;
-        b1 = b2 = b3 = b0;
-    }
-#undef ROT_LD
-#define ROT_NEG(B) { B.x = -B.x; if (!REAL) B.y = -B.y; }
-    const uint32_t jm = rn.jm;
-    if (jm & 2u) ROT_NEG(b1)
-    if (jm & 4u) ROT_NEG(b2)
-    if (jm & 8u) ROT_NEG(b3)
-#define ROT_STEP(A, B, C, T)                                                                     \
+// One sub-run on the 8-amplitude orbit of a thread: the rotations pair (beta, beta ^ C).
+//   Tangent form R = c [[1, -+t], [+-t, 1]]: the unnormalised update costs one DFMA per real component; the
+//   cosines are collected by the host into ONE scale per pass, applied when the tile is stored (every rotation
+//   touches every amplitude, so the product is common to the whole tile).
+//   Sign of pair beta (the element whose bit ctz(C) is clear): (-1)^parity(l & lz) = s(thread) * prod_i mq_i^beta_i:
+//   one POPC per rotation for s and three XORs for the four pair variants of t -- no per-pair work besides the
+//   DFMAs: LDS.128 x2 + 8 integer + 16 DFMA per rotation (8 DFMA when REAL), FP64-pipe bound.
+//   REAL: the tile is purely real and the phase is +-1: the imaginary halves are skipped.
+//   Two rotations per trip with the partner registers ping-ponging (b -> tmp -> b): no register copies.
+template <int C, bool IMAG, bool REAL>
+__device__ __forceinline__ void orbit_sub(double2 (&x)[8], const RotOp* __restrict__ tab, int len, uint32_t l0) {
+    constexpr int K = (C & 1) ? 0 : ((C & 2) ? 1 : 2);              // pivot coordinate: a-side has beta_K = 0
+    constexpr int I = (K == 0) ? 1 : 0, J = (K == 2) ? 1 : 2;       // the two free coordinates, I < J
+    constexpr int A0 = 0, A1 = 1 << I, A2 = 1 << J, A3 = (1 << I) | (1 << J);  // a-side elements, pair index = beta_I + 2 beta_J
+#define ORB_STEP(A, B, D, T)                                                                      \
     {                                                                                            \
         if (IMAG) {                                                                              \
-            C.x = fma(-T, A.y, B.x);                                                             \
-            C.y = fma(T, A.x, B.y);                                                              \
+            D.x = fma(-T, A.y, B.x);                                                             \
+            D.y = fma(T, A.x, B.y);                                                              \
             A.x = fma(-T, B.y, A.x);                                                             \
             A.y = fma(T, B.x, A.y);                                                              \
         } else {                                                                                 \
-            C.x = fma(T, A.x, B.x);                                                              \
+            D.x = fma(T, A.x, B.x);                                                              \
             A.x = fma(-T, B.x, A.x);                                                             \
             if (!REAL) {                                                                         \
-                C.y = fma(T, A.y, B.y);                                                          \
+                D.y = fma(T, A.y, B.y);                                                          \
                 A.y = fma(-T, B.y, A.y);                                                         \
             }                                                                                    \
         }                                                                                        \
     }
-#define ROT_T(F) __hiloint2double((int)((uint32_t)__double2hiint((F).t) ^ ((uint32_t)__popc(l0 & (F).lz) << 31)), \
-                                  __double2loint((F).t))
-    const int len = (int)rn.len;
+#define ORB_SIGNS(F, T0, T1, T2, T3)                                                              \
+    double T0, T1, T2, T3;                                                                        \
+    {                                                                                            \
+        const uint32_t hi = (uint32_t)__double2hiint((F).t) ^ ((uint32_t)__popc(l0 & (F).lz) << 31); \
+        const int lo = __double2loint((F).t);                                                    \
+        T0 = __hiloint2double((int)hi, lo);                                                      \
+        T1 = __hiloint2double((int)(hi ^ (F).mq[I]), lo);                                        \
+        T2 = __hiloint2double((int)(hi ^ (F).mq[J]), lo);                                        \
+        T3 = __hiloint2double((int)(hi ^ (F).mq[I] ^ (F).mq[J]), lo);                            \
+    }
+    double2 d0, d1, d2, d3;
     int r = 0;
 #pragma unroll 1
     for (; r + 1 < len; r += 2) {
-        const FastOp f = tab[r], h = tab[r + 1];
-        const double tf = ROT_T(f), th = ROT_T(h);
-        double2 c0, c1, c2, c3;
-        ROT_STEP(a0, b0, c0, tf)
-        ROT_STEP(a1, b1, c1, tf)
-        ROT_STEP(a2, b2, c2, tf)
-        ROT_STEP(a3, b3, c3, tf)
-        ROT_STEP(a0, c0, b0, th)
-        ROT_STEP(a1, c1, b1, th)
-        ROT_STEP(a2, c2, b2, th)
-        ROT_STEP(a3, c3, b3, th)
+        const RotOp f = tab[r], h = tab[r + 1];
+        ORB_SIGNS(f, t0, t1, t2, t3)
+        ORB_SIGNS(h, u0, u1, u2, u3)
+        ORB_STEP(x[A0], x[A0 ^ C], d0, t0)
+        ORB_STEP(x[A1], x[A1 ^ C], d1, t1)
+        ORB_STEP(x[A2], x[A2 ^ C], d2, t2)
+        ORB_STEP(x[A3], x[A3 ^ C], d3, t3)
+        ORB_STEP(x[A0], d0, x[A0 ^ C], u0)
+        ORB_STEP(x[A1], d1, x[A1 ^ C], u1)
+        ORB_STEP(x[A2], d2, x[A2 ^ C], u2)
+        ORB_STEP(x[A3], d3, x[A3 ^ C], u3)
     }
     if (r < len) {
-        const FastOp f = tab[r];
-        const double tf = ROT_T(f);
-        double2 c0, c1, c2, c3;
-        ROT_STEP(a0, b0, c0, tf)
-        ROT_STEP(a1, b1, c1, tf)
-        ROT_STEP(a2, b2, c2, tf)
-        ROT_STEP(a3, b3, c3, tf)
-        b0.x = c0.x; b1.x = c1.x; b2.x = c2.x; b3.x = c3.x;
-        if (!REAL) { b0.y = c0.y; b1.y = c1.y; b2.y = c2.y; b3.y = c3.y; }
+        const RotOp f = tab[r];
+        ORB_SIGNS(f, t0, t1, t2, t3)
+        ORB_STEP(x[A0], x[A0 ^ C], d0, t0)
+        ORB_STEP(x[A1], x[A1 ^ C], d1, t1)
+        ORB_STEP(x[A2], x[A2 ^ C], d2, t2)
+        ORB_STEP(x[A3], x[A3 ^ C], d3, t3)
+        x[A0 ^ C].x = d0.x; x[A1 ^ C].x = d1.x; x[A2 ^ C].x = d2.x; x[A3 ^ C].x = d3.x;
+        if (!REAL) { x[A0 ^ C].y = d0.y; x[A1 ^ C].y = d1.y; x[A2 ^ C].y = d2.y; x[A3 ^ C].y = d3.y; }
     }
-    if (jm & 2u) ROT_NEG(b1)
-    if (jm & 4u) ROT_NEG(b2)
-    if (jm & 8u) ROT_NEG(b3)
-    const double cs = rn.cscale;
-    if (cs != 1.0) {
-        a0.x *= cs; a0.y *= cs; b0.x *= cs; b0.y *= cs;
-        a1.x *= cs; a1.y *= cs; b1.x *= cs; b1.y *= cs;
-        a2.x *= cs; a2.y *= cs; b2.x *= cs; b2.y *= cs;
-        a3.x *= cs; a3.y *= cs; b3.x *= cs; b3.y *= cs;
-    }
-#undef ROT_T
-#undef ROT_STEP
-#undef ROT_NEG
-#define ROT_ST(A, B, I)                                                                           \
-    if (REAL) { tile[I].x = A.x; tile[(I) ^ lx].x = B.x; }                                        \
-    else { tile[I] = A; tile[(I) ^ lx] = B; }
-    ROT_ST(a0, b0, i0)
-    if (four) {
-        ROT_ST(a1, b1, i1)
-        ROT_ST(a2, b2, i2)
-        ROT_ST(a3, b3, i3)
-    }
-#undef ROT_ST
+#undef ORB_SIGNS
+#undef ORB_STEP
 }
 
-// REAL: the state is known to be purely real on entry and every run of the pass has a +-1 phase (ny odd: the
+template <bool IMAG, bool REAL>
+__device__ __forceinline__ void orbit_dispatch(double2 (&x)[8], const RotOp* __restrict__ tab, int len, uint32_t l0, uint32_t c) {
+    switch (c) {  // warp-uniform
+        case 1: orbit_sub<1, IMAG, REAL>(x, tab, len, l0); break;
+        case 2: orbit_sub<2, IMAG, REAL>(x, tab, len, l0); break;
+        case 3: orbit_sub<3, IMAG, REAL>(x, tab, len, l0); break;
+        case 4: orbit_sub<4, IMAG, REAL>(x, tab, len, l0); break;
+        case 5: orbit_sub<5, IMAG, REAL>(x, tab, len, l0); break;
+        case 6: orbit_sub<6, IMAG, REAL>(x, tab, len, l0); break;
+        default: orbit_sub<7, IMAG, REAL>(x, tab, len, l0); break;
+    }
+}
+
+// tiles with a single pair per thread (registers of fewer than 12 local qubits: tests and tiny molecules)
+template <bool REAL>
+__device__ __forceinline__ void rot_sub1(double2* tile, const RotOp* __restrict__ tab, const DevSub& sb, uint32_t lx, uint32_t hb,
+                                         uint32_t n_pairs, double cs) {
+    if (threadIdx.x >= n_pairs) return;
+    const uint32_t l0 = insert0(threadIdx.x, hb);
+    double2 a = tile[l0], b = tile[l0 ^ lx];
+    for (uint32_t r = 0; r < sb.len; ++r) {
+        const RotOp f = tab[r];
+        const double t = flipsign(f.t, __popc(l0 & f.lz));
+        double2 na, nb;
+        if (sb.imag && !REAL) {
+            nb.x = fma(-t, a.y, b.x); nb.y = fma(t, a.x, b.y);
+            na.x = fma(-t, b.y, a.x); na.y = fma(t, b.x, a.y);
+        } else {
+            nb.x = fma(t, a.x, b.x); nb.y = fma(t, a.y, b.y);
+            na.x = fma(-t, b.x, a.x); na.y = fma(-t, b.y, a.y);
+        }
+        a = na;
+        b = nb;
+    }
+    if (cs != 1.0) { a.x *= cs; a.y *= cs; b.x *= cs; b.y *= cs; }
+    tile[l0] = a;
+    tile[l0 ^ lx] = b;
+}
+
+// REAL: the state is known to be purely real on entry and every rotation of the pass has a +-1 phase (ny odd: the
 // UCC case -- JW images of T - T^dagger), so the imaginary parts stay exactly zero and are never touched.
 template <bool REAL>
 __global__ void __launch_bounds__(512, 2) k_tile_rot(Shards psi, TileGeom g,
                                                      const DevOp* __restrict__ ops, int n_ops,
-                                                     const DevRun* __restrict__ runs, int n_runs, double pass_scale) {
+                                                     const DevSuper* __restrict__ supers, int n_supers,
+                                                     const DevSub* __restrict__ subs, int n_subs, double pass_scale) {
     extern __shared__ double2 tile[];
     const uint32_t ts = 1u << g.tbits;
-    const bool four = (ts >> 1) == 4u * blockDim.x;  // host guarantees: 4 pairs per thread, or exactly 1
-    FastOp* optab = (FastOp*)(tile + ts);
-    DevRun* srun = (DevRun*)(optab + n_ops);
-    for (int q = threadIdx.x; q < n_runs; q += blockDim.x) srun[q] = runs[q];
+    const bool four = (ts >> 1) == 4u * blockDim.x;  // host guarantees: 4 pairs (one orbit) per thread, or at most 1 pair
+    RotOp* optab = (RotOp*)(tile + ts);
+    DevSuper* ssup = (DevSuper*)(optab + n_ops);
+    DevSub* ssub = (DevSub*)(ssup + n_supers);
+    for (int q = threadIdx.x; q < n_supers; q += blockDim.x) ssup[q] = supers[q];
+    for (int q = threadIdx.x; q < n_subs; q += blockDim.x) ssub[q] = subs[q];
+    for (int r = threadIdx.x; r < n_ops; r += blockDim.x) {  // tile-independent part of the table
+        RotOp f;
+        f.t = 0.0;
+        f.lz = ops[r].lz;
+        f.mq[0] = (ops[r].jmask & 1u) << 31;
+        f.mq[1] = (ops[r].jmask & 2u) << 30;
+        f.mq[2] = (ops[r].jmask & 4u) << 29;
+        f.pad[0] = f.pad[1] = 0;
+        optab[r] = f;
+    }
     for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
         const uint64_t base = tile_base(g, t);
         const uint64_t sbase = base | g.sign_base;
+        __syncthreads();
         tile_load_async(tile, psi, g, base);
-        for (int r = threadIdx.x; r < n_ops; r += blockDim.x) {
-            FastOp f;
-            f.t = flipsign(ops[r].s, __popcll(sbase & ops[r].zout));
-            f.lz = ops[r].lz;
-            f.meta = 0;
-            optab[r] = f;
-        }
+        for (int r = threadIdx.x; r < n_ops; r += blockDim.x)
+            optab[r].t = flipsign(ops[r].s, __popcll(sbase & ops[r].zout));
         cp_async_wait_all();
-        for (int q = 0; q < n_runs; ++q) {
+        for (int q = 0; q < n_supers; ++q) {
             __syncthreads();
-            const DevRun& rn = srun[q];
-            if (REAL) rot_run4<false, true>(tile, optab + rn.begin, rn, four);
-            else if (rn.imag) rot_run4<true, false>(tile, optab + rn.begin, rn, four);
-            else rot_run4<false, false>(tile, optab + rn.begin, rn, four);
+            const DevSuper& su = ssup[q];
+            if (four) {
+                const uint32_t l0 = insert0(insert0(insert0(threadIdx.x, su.e0), su.e1), su.e2);
+                double2 x[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (REAL) { x[b].x = tile[l0 ^ su.off[b]].x; x[b].y = 0.0; }
+                    else x[b] = tile[l0 ^ su.off[b]];
+                }
+                for (uint32_t sidx = 0; sidx < su.sub_count; ++sidx) {
+                    const DevSub sb = ssub[su.sub_begin + sidx];
+                    if (REAL) orbit_dispatch<false, true>(x, optab + sb.begin, (int)sb.len, l0, sb.c);
+                    else if (sb.imag) orbit_dispatch<true, false>(x, optab + sb.begin, (int)sb.len, l0, sb.c);
+                    else orbit_dispatch<false, false>(x, optab + sb.begin, (int)sb.len, l0, sb.c);
+                }
+                const double cs = su.cscale;
+                if (cs != 1.0) {
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) { x[b].x *= cs; x[b].y *= cs; }
+                }
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (REAL) tile[l0 ^ su.off[b]].x = x[b].x;
+                    else tile[l0 ^ su.off[b]] = x[b];
+                }
+            } else {
+                // one sub-run per round trip: su.off[1] = the X-mask, su.e0 = its highest bit
+                const DevSub sb = ssub[su.sub_begin];
+                rot_sub1<REAL>(tile, optab + sb.begin, sb, su.off[1], su.e0, 1u << su.hb_log, su.cscale);
+            }
         }
         __syncthreads();
         tile_store_scaled(tile, psi, g, base, pass_scale);
-        __syncthreads();
     }
 }
 
@@ -693,10 +739,13 @@ __global__ void __launch_bounds__(512, 2) k_tile_ops(Shards psi, TileGeom g,
 
 // <psi|O|psi> for one pass.  Group headers and term tables are staged in shared memory ONCE per CTA; per tile
 // only the outside-tile Z parity of each term is refreshed (signed coefficient table), the tile itself arrives
-// through cp.async.  A thread keeps EXP_PAIRS pair products w_j = 2 conj(b_j) a_j in registers and streams the
-// group's terms past them: parity(l_j & lz) = parity(l_0 & lz) ^ jmask_j (jmask from the host), so a term costs
-// one popcount per thread plus, per pair, one LOP3 (sign into the coefficient's high word) and one DFMA into
-// an independent accumulator.
+// through cp.async.
+//   A thread holds 4 pair products w_j = 2 conj(b_j) a_j of a group (8 densities |a_j|^2 for the diagonal group).
+//   The sign of term t on pair j is (-1)^parity(l_j & lz_t) = s_t(thread) * (-1)^(j . q_t), where q_t are the
+//   strings' Z letters on the two (three) tile bits that enumerate the thread's pairs: only 4 (8) sign CLASSES
+//   exist.  So the thread Walsh-Hadamard-transforms its pair products once per group, W_q = sum_j (-1)^(j.q) w_j,
+//   the host sorts the terms of a group by class, and a term costs ONE DFMA per thread:
+//       E += (c_t s_t) * W_{q_t}            (LDS coefficient + LDS lz + LOP + POPC + 2 integer ops + DFMA).
 template <bool CPLX>
 __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
                                                         const DevGroup* __restrict__ groups, int n_groups,
@@ -722,6 +771,20 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
     for (int q = threadIdx.x; q < ng; q += blockDim.x) s_grp[q] = groups[g0 + q];
     for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) s_term[k] = terms[tb0 + k];
     double er = 0.0, ei = 0.0;
+    const uint32_t bd = blockDim.x;
+#define EXP_TERM(W)                                                                                        \
+    {                                                                                                      \
+        const uint32_t sg = (uint32_t)__popc(l0 & s_term[k].lz) << 31;                                      \
+        if (CPLX) {                                                                                        \
+            const double2 c = s_sc[k];                                                                     \
+            er = fma(__hiloint2double((int)((uint32_t)__double2hiint(c.x) ^ sg), __double2loint(c.x)), W, er); \
+            ei = fma(__hiloint2double((int)((uint32_t)__double2hiint(c.y) ^ sg), __double2loint(c.y)), W, ei); \
+        } else {                                                                                           \
+            const double c = s_sc[k].x;                                                                    \
+            er = fma(__hiloint2double((int)((uint32_t)__double2hiint(c) ^ sg), __double2loint(c)), W, er);   \
+        }                                                                                                  \
+        ++k;                                                                                               \
+    }
     for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
         const uint64_t base = tile_base(g, t);
         const uint64_t sbase = base | g.sign_base;
@@ -734,69 +797,87 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
         cp_async_wait_all();
         __syncthreads();
         for (int q = 0; q < ng; ++q) {
-            const uint32_t lx = s_grp[q].lx, hb = s_grp[q].hb;
-            const uint32_t off = s_grp[q].t_begin - tb0;
-            const uint32_t n_even = s_grp[q].n_even, n_odd = s_grp[q].n_odd;
-            const uint32_t count = (lx == 0) ? ts : half;
-            const uint32_t l0 = (lx == 0) ? threadIdx.x : insert0(threadIdx.x, hb);
-            uint32_t jbase = 0;
-            for (uint32_t p0 = threadIdx.x; p0 < count; p0 += EXP_PAIRS * blockDim.x, jbase += EXP_PAIRS) {
-                double wr[EXP_PAIRS], wi[EXP_PAIRS];
+            const DevGroup& G = s_grp[q];
+            const uint32_t lx = G.lx, hb = G.hb;
+            uint32_t k = G.t_begin - tb0;
+            if (lx == 0) {
+                // diagonal group: 8 densities per thread, 8 sign classes
+                const uint32_t kstart = k;
+                for (uint32_t p0 = threadIdx.x; p0 < ts; p0 += 8 * bd) {
+                    double v[8];
 #pragma unroll
-                for (int j = 0; j < EXP_PAIRS; ++j) {
-                    const uint32_t pidx = p0 + j * blockDim.x;
-                    wr[j] = 0.0;
-                    wi[j] = 0.0;
-                    if (pidx < count) {
-                        if (lx == 0) {
-                            const double2 a = tile[pidx];
-                            wr[j] = a.x * a.x + a.y * a.y;
-                        } else {
-                            const uint32_t l = insert0(pidx, hb);
-                            const double2 a = tile[l], b = tile[l ^ lx];
-                            wr[j] = 2.0 * (b.x * a.x + b.y * a.y);  // 2 Re(conj(b) a)
-                            wi[j] = 2.0 * (b.x * a.y - b.y * a.x);  // 2 Im(conj(b) a)
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t l = p0 + j * bd;
+                        v[j] = 0.0;
+                        if (l < ts) {
+                            const double2 a = tile[l];
+                            v[j] = fma(a.x, a.x, a.y * a.y);
                         }
                     }
-                }
-                double accr[EXP_PAIRS], acci[EXP_PAIRS];  // independent FMA chains
 #pragma unroll
-                for (int j = 0; j < EXP_PAIRS; ++j) accr[j] = acci[j] = 0.0;
-                uint32_t k = off;
-                for (uint32_t e = 0; e < n_even; ++e, ++k) {
-                    const double2 c = s_sc[k];
-                    const uint32_t tsign = (uint32_t)__popc(l0 & s_term[k].lz) << 31;
-                    const uint32_t jm = s_term[k].jmask >> jbase;
-                    const uint32_t hr = (uint32_t)__double2hiint(c.x) ^ tsign;
-                    const uint32_t hi = (uint32_t)__double2hiint(c.y) ^ tsign;
+                    for (int st = 1; st < 8; st <<= 1)
 #pragma unroll
-                    for (int j = 0; j < EXP_PAIRS; ++j) {
-                        const uint32_t u = (jm << (31 - j)) & 0x80000000u;
-                        accr[j] = fma(__hiloint2double((int)(hr ^ u), __double2loint(c.x)), wr[j], accr[j]);
-                        if (CPLX) acci[j] = fma(__hiloint2double((int)(hi ^ u), __double2loint(c.y)), wr[j], acci[j]);
+                        for (int j = 0; j < 8; ++j)
+                            if (!(j & st)) {
+                                const double u = v[j], w = v[j | st];
+                                v[j] = u + w;
+                                v[j | st] = u - w;
+                            }
+                    const uint32_t l0 = p0;
+                    k = kstart;
+#pragma unroll
+                    for (int cls = 0; cls < 8; ++cls) {
+                        const uint32_t n = G.cnt[cls];
+                        for (uint32_t e = 0; e < n; ++e) EXP_TERM(v[cls])
                     }
                 }
-                for (uint32_t e = 0; e < n_odd; ++e, ++k) {
-                    const double2 c = s_sc[k];
-                    const uint32_t tsign = (uint32_t)__popc(l0 & s_term[k].lz) << 31;
-                    const uint32_t jm = s_term[k].jmask >> jbase;
-                    const uint32_t hr = (uint32_t)__double2hiint(c.x) ^ tsign;
-                    const uint32_t hi = (uint32_t)__double2hiint(c.y) ^ tsign;
+            } else {
+                const uint32_t kstart = k;
+                const bool any_odd = G.n_odd != 0;
+                for (uint32_t p0 = threadIdx.x; p0 < half; p0 += 4 * bd) {
+                    double wr[4], wi[4];
 #pragma unroll
-                    for (int j = 0; j < EXP_PAIRS; ++j) {
-                        const uint32_t u = (jm << (31 - j)) & 0x80000000u;
-                        accr[j] = fma(__hiloint2double((int)(hr ^ u), __double2loint(c.x)), wi[j], accr[j]);
-                        if (CPLX) acci[j] = fma(__hiloint2double((int)(hi ^ u), __double2loint(c.y)), wi[j], acci[j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t pidx = p0 + j * bd;
+                        wr[j] = wi[j] = 0.0;
+                        if (pidx < half) {
+                            const uint32_t l = insert0(pidx, hb);
+                            const double2 a = tile[l], b = tile[l ^ lx];
+                            wr[j] = 2.0 * fma(b.x, a.x, b.y * a.y);   // 2 Re(conj(b) a)
+                            wi[j] = 2.0 * fma(b.x, a.y, -b.y * a.x);  // 2 Im(conj(b) a)
+                        }
                     }
-                }
 #pragma unroll
-                for (int j = 0; j < EXP_PAIRS; ++j) {
-                    er += accr[j];
-                    if (CPLX) ei += acci[j];
+                    for (int st = 1; st < 4; st <<= 1)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (!(j & st)) {
+                                const double u = wr[j], w = wr[j | st];
+                                wr[j] = u + w;
+                                wr[j | st] = u - w;
+                                const double ui = wi[j], wq = wi[j | st];
+                                wi[j] = ui + wq;
+                                wi[j | st] = ui - wq;
+                            }
+                    const uint32_t l0 = insert0(p0, hb);
+                    k = kstart;
+#pragma unroll
+                    for (int cls = 0; cls < 4; ++cls) {
+                        const uint32_t n = G.cnt[cls];
+                        for (uint32_t e = 0; e < n; ++e) EXP_TERM(wr[cls])
+                    }
+                    if (any_odd) {
+#pragma unroll
+                        for (int cls = 0; cls < 4; ++cls) {
+                            const uint32_t n = G.cnt[4 + cls];
+                            for (uint32_t e = 0; e < n; ++e) EXP_TERM(wi[cls])
+                        }
+                    }
                 }
             }
         }
     }
+#undef EXP_TERM
     double2 sres = block_sum2(er, ei, red);
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
 }
@@ -1635,14 +1716,17 @@ static int tile_grid(const vqe_ctx* c, uint64_t n_tiles) {
 struct OpPass {
     TilePlan tp;
     size_t op_begin, op_end;            // in the dev op array
-    size_t run_begin = 0, run_end = 0;  // in the dev run array (fast passes only)
+    size_t sup_begin = 0, sup_end = 0;  // fast passes: shared-memory round trips (orbits) ...
+    size_t sub_begin = 0, sub_end = 0;  // ... and their sub-runs
     bool fast = false;
+    bool has_imag = false;              // some rotation of a fast pass has a +-i phase
     double pass_scale = 1.0;            // fast passes: product of the cosines not yet applied by a run
 };
 struct OpPlan {
     std::vector<OpPass> passes;
     std::vector<DevOp> dops;
-    std::vector<DevRun> druns;
+    std::vector<DevSuper> dsupers;
+    std::vector<DevSub> dsubs;
     std::vector<double> mats;
 };
 
@@ -1655,7 +1739,8 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                     OpPlan& out) {
     std::vector<OpPass>& passes = out.passes;
     std::vector<DevOp>& dops = out.dops;
-    std::vector<DevRun>& druns = out.druns;
+    std::vector<DevSuper>& dsupers = out.dsupers;
+    std::vector<DevSub>& dsubs = out.dsubs;
     std::vector<double>& mats = out.mats;
     dops.reserve(ops.size());
     size_t i = 0;
@@ -1767,81 +1852,107 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
         const bool four = half_p == 4u * (uint32_t)threads_p;
         if (!(four || half_p <= (uint32_t)threads_p)) p.fast = false;  // k_tile_rot holds 4 pairs per thread, or 1
         if (p.fast) {
-            p.run_begin = druns.size();
+            p.sup_begin = dsupers.size();
+            p.sub_begin = dsubs.size();
             double pending = 1.0;  // cosines are applied once per pass (tile store) unless the product gets tiny
-            const size_t druns_mark = druns.size();
-            for (size_t k = p.op_begin; k < p.op_end && p.fast;) {
-                size_t e = k + 1;
-                while (e < p.op_end && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
-                uint32_t d0 = 0, d1 = 0;
-                if (four) {
-                    // the two tile bits that enumerate a thread's pairs: no X/Y letter there, and preferably the
-                    // same Z letter in every string of the run, so the pair signs stay constant (rot_run4)
-                    uint32_t var = 0;
-                    for (size_t q = k; q < e; ++q) var |= dops[q].lz ^ dops[k].lz;
-                    int pick[2], np = 0;
-                    for (int want_var = 0; want_var < 2 && np < 2; ++want_var)
-                        for (int lowpass = 0; lowpass < 2 && np < 2; ++lowpass)  // first bits >= 5 (bank-conflict free), then the rest
-                            for (int b = p.tp.tbits - 1; b >= 0 && np < 2; --b) {
-                                if ((dops[k].lx >> b) & 1u) continue;
-                                if ((int)((var >> b) & 1u) != want_var) continue;
-                                if ((b >= 5) == (lowpass == 1)) continue;
-                                if (np == 1 && pick[0] == b) continue;
-                                pick[np++] = b;
-                            }
-                    if (np < 2) {  // X/Y letters on (almost) every tile bit: leave the pass to the general kernel
-                        p.fast = false;
-                        break;
-                    }
-                    d0 = (uint32_t)std::min(pick[0], pick[1]);
-                    d1 = (uint32_t)std::max(pick[0], pick[1]);
+            auto close_scale = [&](DevSuper& su, size_t first_sub) {
+                for (size_t q = first_sub; q < dsubs.size(); ++q)
+                    for (uint32_t w = 0; w < dsubs[q].len; ++w) pending *= rot_cos[dsubs[q].begin + w];
+                su.cscale = 1.0;
+                if (fabs(pending) < 1e-30) {  // unnormalised amplitudes have grown by 1e30: rescale now
+                    su.cscale = pending;
+                    pending = 1.0;
                 }
-                const uint32_t off1 = four ? 1u << d0 : 0u, off2 = four ? 1u << d1 : 0u;
-                auto jm_of = [&](const DevOp& d) {
-                    uint32_t jm = 0;
-                    if (__builtin_popcount(off1 & d.lz) & 1) jm |= 2u | 8u;
-                    if (__builtin_popcount(off2 & d.lz) & 1) jm ^= 4u | 8u;
-                    return jm;
+            };
+            size_t k = p.op_begin;
+            while (k < p.op_end) {
+                DevSuper su;
+                memset(&su, 0, sizeof su);
+                su.sub_begin = (uint32_t)(dsubs.size() - p.sub_begin);
+                su.hb_log = 31 - __builtin_clz(half_p ? half_p : 1u);
+                const size_t first_sub = dsubs.size();
+                if (!four) {  // one pair per thread: every same-X-mask run is its own round trip
+                    size_t e = k + 1;
+                    while (e < p.op_end && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
+                    dsubs.push_back({(uint32_t)(k - p.op_begin), (uint32_t)(e - k), 1u, dops[k].imag});
+                    if (dops[k].imag) p.has_imag = true;
+                    su.e0 = dops[k].hb;
+                    su.off[1] = dops[k].lx;
+                    su.sub_count = 1;
+                    close_scale(su, first_sub);
+                    dsupers.push_back(su);
+                    k = e;
+                    continue;
+                }
+                // orbit basis: v = X-masks as given, r = reduced forms (zero at the earlier pivots), T = coordinates of r in v
+                uint32_t v[3] = {0, 0, 0}, rr[3] = {0, 0, 0}, T[3] = {0, 0, 0}, piv[3] = {0, 0, 0};
+                int dim = 0;
+                auto reduce = [&](uint32_t w, uint32_t& coord) {
+                    coord = 0;
+                    for (int a2 = 0; a2 < dim; ++a2)
+                        if ((w >> piv[a2]) & 1u) {
+                            w ^= rr[a2];
+                            coord ^= T[a2];
+                        }
+                    return w;
                 };
-                for (size_t q = k; q < e;) {
-                    size_t qe = q + 1;
-                    const uint32_t jm = jm_of(dops[q]);
-                    while (qe < e && jm_of(dops[qe]) == jm) ++qe;
-                    DevRun r;
-                    memset(&r, 0, sizeof r);
-                    r.lx = dops[q].lx;
-                    r.hb = dops[q].hb;
-                    r.begin = (uint32_t)(q - p.op_begin);
-                    r.len = (uint32_t)(qe - q);
-                    r.imag = dops[q].imag;
-                    r.jm = jm;
-                    uint32_t pos[3] = {r.hb, d0, d1};
-                    std::sort(pos, pos + 3);
-                    r.e0 = pos[0]; r.e1 = pos[1]; r.e2 = pos[2];
-                    r.off1 = off1;
-                    r.off2 = off2;
-                    r.pad = 31 - __builtin_clz(half_p ? half_p : 1u);
-                    r.cscale = 1.0;
-                    druns.push_back(r);
-                    q = qe;
-                }
-                k = e;
-            }
-            if (!p.fast) {
-                druns.resize(druns_mark);
-            } else {
-                // pending product of cosines, run by run
-                for (size_t ri = druns_mark; ri < druns.size(); ++ri) {
-                    DevRun& r = druns[ri];
-                    for (uint32_t w = 0; w < r.len; ++w) pending *= rot_cos[r.begin + w];
-                    if (fabs(pending) < 1e-30) {  // unnormalised amplitudes have grown by 1e30: rescale now
-                        r.cscale = pending;
-                        pending = 1.0;
+                auto pick_pivot = [&](uint32_t res) {
+                    for (int b2 = p.tp.tbits - 1; b2 >= 5; --b2)
+                        if ((res >> b2) & 1u) return (uint32_t)b2;  // bits >= 5 keep the shared-memory accesses conflict free
+                    return (uint32_t)(31 - __builtin_clz(res));
+                };
+                while (k < p.op_end) {
+                    size_t e = k + 1;
+                    while (e < p.op_end && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
+                    uint32_t coord = 0;
+                    const uint32_t res = reduce(dops[k].lx, coord);
+                    uint32_t cpat = coord;
+                    if (res != 0) {
+                        if (dim == 3) break;  // a fourth independent X-mask: next round trip
+                        v[dim] = dops[k].lx;
+                        rr[dim] = res;
+                        T[dim] = coord ^ (1u << dim);
+                        piv[dim] = pick_pivot(res);
+                        cpat = 1u << dim;
+                        ++dim;
                     }
+                    dsubs.push_back({(uint32_t)(k - p.op_begin), (uint32_t)(e - k), cpat, dops[k].imag});
+                    if (dops[k].imag) p.has_imag = true;
+                    k = e;
                 }
-                p.pass_scale = pending;
-                p.run_end = druns.size();
+                for (int b2 = p.tp.tbits - 1; b2 >= 0 && dim < 3; --b2) {  // fill up with free single bits
+                    bool is_piv = false;
+                    for (int a2 = 0; a2 < dim; ++a2) is_piv = is_piv || piv[a2] == (uint32_t)b2;
+                    if (is_piv) continue;
+                    uint32_t coord = 0;
+                    const uint32_t res = reduce(1u << b2, coord);
+                    if (res == 0) continue;
+                    v[dim] = 1u << b2;
+                    rr[dim] = res;
+                    T[dim] = coord ^ (1u << dim);
+                    piv[dim] = pick_pivot(res);
+                    ++dim;
+                }
+                uint32_t ps3[3] = {piv[0], piv[1], piv[2]};
+                std::sort(ps3, ps3 + 3);
+                su.e0 = ps3[0]; su.e1 = ps3[1]; su.e2 = ps3[2];
+                for (uint32_t b2 = 0; b2 < 8; ++b2)
+                    su.off[b2] = ((b2 & 1u) ? v[0] : 0u) ^ ((b2 & 2u) ? v[1] : 0u) ^ ((b2 & 4u) ? v[2] : 0u);
+                su.sub_count = (uint32_t)(dsubs.size() - first_sub);
+                // sign step of every rotation along the three orbit directions (RotOp::mq)
+                for (size_t q = first_sub; q < dsubs.size(); ++q)
+                    for (uint32_t w = 0; w < dsubs[q].len; ++w) {
+                        DevOp& d = dops[p.op_begin + dsubs[q].begin + w];
+                        d.jmask = 0;
+                        for (int a2 = 0; a2 < 3; ++a2)
+                            if (__builtin_popcount(v[a2] & d.lz) & 1) d.jmask |= 1u << a2;
+                    }
+                close_scale(su, first_sub);
+                dsupers.push_back(su);
             }
+            p.pass_scale = pending;
+            p.sup_end = dsupers.size();
+            p.sub_end = dsubs.size();
         }
         passes.push_back(std::move(p));
         i = j;
@@ -1862,7 +1973,8 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
     // upload: [ops][mats][runs][scat tables]
     size_t off_ops = 0, off_mats = plan.dops.size() * sizeof(DevOp);
     size_t off_runs = (off_mats + plan.mats.size() * sizeof(double) + 15) & ~size_t(15);
-    size_t off_scat = off_runs + plan.druns.size() * sizeof(DevRun);
+    size_t off_subs = off_runs + plan.dsupers.size() * sizeof(DevSuper);
+    size_t off_scat = off_subs + plan.dsubs.size() * sizeof(DevSub);
     off_scat = (off_scat + 15) & ~size_t(15);
     size_t total = off_scat;
     std::vector<size_t> scat_off(passes.size());
@@ -1878,7 +1990,8 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
         CK(cudaStreamSynchronize(c->stream));
         memcpy(c->h_stage + off_ops, plan.dops.data(), plan.dops.size() * sizeof(DevOp));
         if (!plan.mats.empty()) memcpy(c->h_stage + off_mats, plan.mats.data(), plan.mats.size() * sizeof(double));
-        if (!plan.druns.empty()) memcpy(c->h_stage + off_runs, plan.druns.data(), plan.druns.size() * sizeof(DevRun));
+        if (!plan.dsupers.empty()) memcpy(c->h_stage + off_runs, plan.dsupers.data(), plan.dsupers.size() * sizeof(DevSuper));
+        if (!plan.dsubs.empty()) memcpy(c->h_stage + off_subs, plan.dsubs.data(), plan.dsubs.size() * sizeof(DevSub));
         for (size_t p = 0; p < passes.size(); ++p)
             memcpy(c->h_stage + scat_off[p], passes[p].tp.scat.data(), passes[p].tp.scat.size() * sizeof(uint64_t));
         c->h2d_bytes += total;
@@ -1891,10 +2004,7 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
         bool real = true;
         for (vqe_ctx* c : rs.r) real = real && c->psi_real;
         for (size_t p = 0; p < passes.size(); ++p) {
-            bool keeps = passes[p].fast;
-            for (size_t r = passes[p].run_begin; keeps && r < passes[p].run_end; ++r)
-                if (plan.druns[r].imag) keeps = false;
-            real = real && keeps;
+            real = real && passes[p].fast && !passes[p].has_imag;
             real_pass[p] = real ? 1 : 0;
         }
         for (vqe_ctx* c : rs.r) c->psi_real = real;
@@ -1913,18 +2023,22 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
             rc = make_geom(c, ps.tp, (const uint64_t*)(c->d_stage + scat_off[p]), VQE_BUF_PSI, g, sh);
             if (rc) return rc;
             if (g.n_tiles == 0) continue;
-            size_t smem = tile_smem(ps.tp.tbits, 1, false) + (ps.op_end - ps.op_begin) * sizeof(FastOp) +
-                          (ps.run_end - ps.run_begin) * sizeof(DevRun);
+            size_t smem = tile_smem(ps.tp.tbits, 1, false) +
+                          (ps.fast ? (ps.op_end - ps.op_begin) * sizeof(RotOp) + (ps.sup_end - ps.sup_begin) * sizeof(DevSuper) +
+                                         (ps.sub_end - ps.sub_begin) * sizeof(DevSub)
+                                   : (ps.op_end - ps.op_begin) * sizeof(FastOp));
             int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
             ProfScope prof(c, ps.tp.vbit ? 4 : 0);
             if (ps.fast && real_pass[p])
                 k_tile_rot<true><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                     sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
-                    (const DevRun*)(c->d_stage + off_runs) + ps.run_begin, (int)(ps.run_end - ps.run_begin), ps.pass_scale);
+                    (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
+                    (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin), ps.pass_scale);
             else if (ps.fast)
                 k_tile_rot<false><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                     sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
-                    (const DevRun*)(c->d_stage + off_runs) + ps.run_begin, (int)(ps.run_end - ps.run_begin), ps.pass_scale);
+                    (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
+                    (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin), ps.pass_scale);
             else
                 k_tile_ops<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                     sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
@@ -2014,11 +2128,11 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
         if (pass_tile_mask) pass_tile_mask[p] = plan.passes[p].tp.tile_mask;
     }
     if (getenv("VQE_DEBUG_PLAN")) {
-        size_t nruns = plan.druns.size(), nfast = 0, lens[9] = {0};
+        size_t nruns = plan.dsubs.size(), nfast = 0, lens[9] = {0};
         for (const OpPass& p : plan.passes) nfast += p.fast ? 1 : 0;
-        for (const DevRun& r : plan.druns) lens[std::min<uint32_t>(r.len, 8)]++;
-        fprintf(stderr, "[plan] passes %zu (fast %zu) ops %zu runs %zu; run-length histogram 1..8+:", plan.passes.size(), nfast,
-                plan.dops.size(), nruns);
+        for (const DevSub& r : plan.dsubs) lens[std::min<uint32_t>(r.len, 8)]++;
+        fprintf(stderr, "[plan] passes %zu (fast %zu) ops %zu round trips %zu sub-runs %zu; sub-run-length histogram 1..8+:",
+                plan.passes.size(), nfast, plan.dops.size(), plan.dsupers.size(), nruns);
         for (int k = 1; k <= 8; ++k) fprintf(stderr, " %zu", lens[k]);
         fprintf(stderr, "\n");
     }
@@ -2197,6 +2311,11 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             dg.lx = plan_lx(xs[g], p.tp);
             dg.hb = dg.lx ? 31 - __builtin_clz(dg.lx) : 0;
             dg.t_begin = (uint32_t)p.terms_expect.size();
+            struct Sorted {
+                int key;  // parity * 8 + sign class
+                DevTerm e, a;
+            };
+            std::vector<Sorted> sorted;
             for (int parity = 0; parity < 2; ++parity) {
                 for (const HTerm& t : grp[g]) {
                     if ((t.ny & 1) != parity) continue;
@@ -2230,10 +2349,19 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
                         }
                         e.jmask = jm;
                     }
-                    p.terms_expect.push_back(e);
-                    p.terms_apply.push_back(a);
+                    // sign class = Z letters on the tile bits that enumerate a thread's pairs (k_tile_expect)
+                    const int cls = (xs[g] == 0) ? (int)(((e.jmask >> 1) & 1u) | (((e.jmask >> 2) & 1u) << 1) | (((e.jmask >> 4) & 1u) << 2))
+                                                 : (int)(((e.jmask >> 1) & 1u) | (((e.jmask >> 2) & 1u) << 1));
+                    sorted.push_back({parity * 8 + cls, e, a});
                     if (parity) dg.n_odd++; else dg.n_even++;
                 }
+            }
+            std::stable_sort(sorted.begin(), sorted.end(), [](const Sorted& u, const Sorted& v) { return u.key < v.key; });
+            for (const Sorted& sd : sorted) {
+                p.terms_expect.push_back(sd.e);
+                p.terms_apply.push_back(sd.a);
+                const int parity = sd.key >> 3, cls = sd.key & 7;
+                dg.cnt[(xs[g] == 0) ? cls : parity * 4 + cls]++;
             }
             p.groups.push_back(dg);
         }
