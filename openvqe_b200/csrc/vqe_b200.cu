@@ -475,9 +475,31 @@ struct DevSub {        // 16 bytes: consecutive fast rotations with the same orb
     uint32_t c;            // pairs are (beta, beta ^ c), c in 1..7 (orbit coordinates of the X-mask)
     uint32_t imag;         // unit phase +-i (ny even) instead of +-1
 };
-struct DevSuper {      // 64 bytes: one shared-memory round trip
+// COLLAPSED runs.  Rotations with the same X-mask and phase type act in the same 2-d planes (a, b = a ^ lx) and
+// commute, so their angles ADD: a run of R strings is ONE plane rotation by Phi(l) = sum_r (+-)phi_r, the signs
+// being the strings' Z parities at l.  All parities agree with the first string's except on the few tile bits D
+// where the strings' Z letters differ, so Phi(l) = (-1)^parity(l & lz_1) * F[l restricted to D]: the host tabulates
+// cos F, sin F per pattern.  For the JW image of a fermionic excitation F vanishes for all but one occupation
+// pattern -- the 8 strings of a double excitation touch 1/8 of the amplitude pairs, once.
+struct DevColEntry {   // 32 bytes
+    double c, s;       // cos F, sin F of this pattern
+    uint32_t pat;      // the pattern as tile-index bits (a-side: the highest X bit is clear)
+    uint32_t pad[3];
+};
+struct DevCol {        // 64 bytes
+    uint64_t zout;         // Z letters outside the tile (same for every string of the run)
+    uint32_t lx, lz;       // X-mask; Z letters of the first string inside the tile
+    uint32_t n_active;     // patterns with a non-zero angle
+    uint32_t nd;           // fixed positions (D and the highest X bit), ascending in dpos
+    uint32_t dpos[6];
+    uint32_t ent_begin;    // into the pass-local entry table
+    uint32_t free_log;     // log2(number of a-side indices per pattern)
+    uint32_t imag;
+    uint32_t pad;
+};
+struct DevSuper {      // 64 bytes: one shared-memory round trip (orbit), or one collapsed run
     uint32_t e0, e1, e2;   // ascending pivot positions: zeros are inserted there into the thread index
-    uint32_t sub_begin, sub_count;
+    uint32_t sub_begin, sub_count;   // collapsed run: sub_count = 0xffffffff, sub_begin = index of its DevCol
     uint32_t hb_log;       // tiles with one pair per thread: log2(pairs in the tile)
     double cscale;         // 1.0, or the pending product of cosines when it must be applied now (overflow guard)
     uint32_t off[8];       // off[beta] = XOR of the v_i selected by beta
@@ -619,15 +641,22 @@ template <bool REAL>
 __global__ void __launch_bounds__(512, 2) k_tile_rot(Shards psi, TileGeom g,
                                                      const DevOp* __restrict__ ops, int n_ops,
                                                      const DevSuper* __restrict__ supers, int n_supers,
-                                                     const DevSub* __restrict__ subs, int n_subs, double pass_scale) {
+                                                     const DevSub* __restrict__ subs, int n_subs,
+                                                     const DevCol* __restrict__ cols, int n_cols,
+                                                     const DevColEntry* __restrict__ ents, int n_ents, double pass_scale) {
     extern __shared__ double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     const bool four = (ts >> 1) == 4u * blockDim.x;  // host guarantees: 4 pairs (one orbit) per thread, or at most 1 pair
     RotOp* optab = (RotOp*)(tile + ts);
     DevSuper* ssup = (DevSuper*)(optab + n_ops);
-    DevSub* ssub = (DevSub*)(ssup + n_supers);
+    DevCol* scol = (DevCol*)(ssup + n_supers);
+    DevColEntry* sent = (DevColEntry*)(scol + n_cols);
+    DevSub* ssub = (DevSub*)(sent + n_ents);
+    uint32_t* scsign = (uint32_t*)(ssub + n_subs);  // per tile: outside-tile Z parity of every collapsed run
     for (int q = threadIdx.x; q < n_supers; q += blockDim.x) ssup[q] = supers[q];
     for (int q = threadIdx.x; q < n_subs; q += blockDim.x) ssub[q] = subs[q];
+    for (int q = threadIdx.x; q < n_cols; q += blockDim.x) scol[q] = cols[q];
+    for (int q = threadIdx.x; q < n_ents; q += blockDim.x) sent[q] = ents[q];
     for (int r = threadIdx.x; r < n_ops; r += blockDim.x) {  // tile-independent part of the table
         RotOp f;
         f.t = 0.0;
@@ -645,11 +674,44 @@ __global__ void __launch_bounds__(512, 2) k_tile_rot(Shards psi, TileGeom g,
         tile_load_async(tile, psi, g, base);
         for (int r = threadIdx.x; r < n_ops; r += blockDim.x)
             optab[r].t = flipsign(ops[r].s, __popcll(sbase & ops[r].zout));
+        for (int r = threadIdx.x; r < n_cols; r += blockDim.x) scsign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
         cp_async_wait_all();
         for (int q = 0; q < n_supers; ++q) {
             __syncthreads();
             const DevSuper& su = ssup[q];
-            if (four) {
+            if (su.sub_count == 0xffffffffu) {
+                // collapsed run: one plane rotation per ACTIVE (pattern, free index) pair
+                const DevCol& co = scol[su.sub_begin];
+                const uint32_t items = co.n_active << co.free_log;
+                const uint32_t fmask = (1u << co.free_log) - 1u;
+                const uint32_t tsig = scsign[su.sub_begin];
+                for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+                    const DevColEntry en = sent[co.ent_begin + (it >> co.free_log)];
+                    uint32_t l = it & fmask;
+#pragma unroll
+                    for (int d = 0; d < 6; ++d)
+                        if (d < (int)co.nd) l = insert0(l, co.dpos[d]);
+                    l |= en.pat;
+                    const double sn = flipsign(en.s, tsig + (uint32_t)__popc(l & co.lz));
+                    if (REAL) {
+                        const double a = tile[l].x, b = tile[l ^ co.lx].x;
+                        tile[l].x = fma(en.c, a, -sn * b);
+                        tile[l ^ co.lx].x = fma(en.c, b, sn * a);
+                    } else {
+                        const double2 a = tile[l], b = tile[l ^ co.lx];
+                        double2 na, nb;
+                        if (co.imag) {  // a' = c a + i s b, b' = c b + i s a
+                            na.x = fma(en.c, a.x, -sn * b.y); na.y = fma(en.c, a.y, sn * b.x);
+                            nb.x = fma(en.c, b.x, -sn * a.y); nb.y = fma(en.c, b.y, sn * a.x);
+                        } else {        // a' = c a - s b, b' = c b + s a
+                            na.x = fma(en.c, a.x, -sn * b.x); na.y = fma(en.c, a.y, -sn * b.y);
+                            nb.x = fma(en.c, b.x, sn * a.x); nb.y = fma(en.c, b.y, sn * a.y);
+                        }
+                        tile[l] = na;
+                        tile[l ^ co.lx] = nb;
+                    }
+                }
+            } else if (four) {
                 const uint32_t l0 = insert0(insert0(insert0(threadIdx.x, su.e0), su.e1), su.e2);
                 double2 x[8];
 #pragma unroll
@@ -735,6 +797,25 @@ __global__ void __launch_bounds__(512, 2) k_tile_ops(Shards psi, TileGeom g,
 // ------------------------------------------------------------------------------------------
 #define TERM_CAP 384    // terms per pass (host splits passes accordingly)
 #define GROUP_CAP 96    // X-mask groups per pass
+#define GCOL_ENT_CAP 384  // (pattern, weight) entries of collapsed groups per pass
+
+// COLLAPSED group of an expectation pass (the analogue of DevCol): the Z-variants of an X-mask group differ only on
+// a few tile bits D, so sum_t c_t (-1)^parity(l & z_t) = (-1)^parity(l & z_1) * F[l restricted to D] with F tabulated
+// by the host.  For the two-body terms of a molecular Hamiltonian F vanishes on most occupation patterns, so only
+// the ACTIVE (pattern, free index) pairs are visited: one pair product and one DFMA each.
+struct DevGColEntry {  // 32 bytes
+    double fr, fi;     // weights of 2 Re(conj(b) a) and 2 Im(conj(b) a)
+    uint32_t pat;      // pattern as tile-index bits (a-side)
+    uint32_t pad[3];
+};
+struct DevGCol {       // 64 bytes
+    uint64_t zout;     // Z letters outside the tile (same for every term of the group)
+    uint32_t lz;       // Z letters of the first term inside the tile
+    uint32_t n_active, nd;
+    uint32_t dpos[6];
+    uint32_t ent_begin, free_log;
+    uint32_t pad[3];
+};
 #define EXP_PAIRS 4
 
 // <psi|O|psi> for one pass.  Group headers and term tables are staged in shared memory ONCE per CTA; per tile
@@ -750,6 +831,8 @@ template <bool CPLX>
 __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
                                                         const DevGroup* __restrict__ groups, int n_groups,
                                                         const DevTerm* __restrict__ terms,
+                                                        const DevGCol* __restrict__ gcols, int n_gcols,
+                                                        const DevGColEntry* __restrict__ gents, int n_gents,
                                                         double2* __restrict__ partial) {
     extern __shared__ double2 tile[];
     __shared__ double red[64];
@@ -758,6 +841,10 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
     DevTerm* s_term = (DevTerm*)(tile + ts);               // TERM_CAP
     double2* s_sc = (double2*)(s_term + TERM_CAP);         // TERM_CAP signed coefficients (per tile)
     DevGroup* s_grp = (DevGroup*)(s_sc + TERM_CAP);        // GROUP_CAP
+    DevGCol* s_gcol = (DevGCol*)(s_grp + GROUP_CAP);       // GROUP_CAP
+    DevGColEntry* s_gent = (DevGColEntry*)(s_gcol + GROUP_CAP);  // GCOL_ENT_CAP
+    for (int q = threadIdx.x; q < n_gcols; q += blockDim.x) s_gcol[q] = gcols[q];
+    for (int q = threadIdx.x; q < n_gents; q += blockDim.x) s_gent[q] = gents[q];
     // group chunk of this CTA (blockIdx.y splits the groups of a pass when there are few tiles)
     const int per = (n_groups + gridDim.y - 1) / gridDim.y;
     const int g0 = blockIdx.y * per, g1 = min(n_groups, g0 + per);
@@ -800,7 +887,25 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
             const DevGroup& G = s_grp[q];
             const uint32_t lx = G.lx, hb = G.hb;
             uint32_t k = G.t_begin - tb0;
-            if (lx == 0) {
+            if (G.pad != 0) {
+                // collapsed group: only the active (pattern, free index) pairs
+                const DevGCol& co = s_gcol[G.pad - 1];
+                const uint32_t items = co.n_active << co.free_log;
+                const uint32_t fmask = (1u << co.free_log) - 1u;
+                const uint32_t tsig = (uint32_t)__popcll(sbase & co.zout);
+                for (uint32_t it = threadIdx.x; it < items; it += bd) {
+                    const DevGColEntry en = s_gent[co.ent_begin + (it >> co.free_log)];
+                    uint32_t l = it & fmask;
+#pragma unroll
+                    for (int d = 0; d < 6; ++d)
+                        if (d < (int)co.nd) l = insert0(l, co.dpos[d]);
+                    l |= en.pat;
+                    const double2 a = tile[l], b = tile[l ^ lx];
+                    const double wr = 2.0 * fma(b.x, a.x, b.y * a.y);
+                    const double wi = 2.0 * fma(b.x, a.y, -b.y * a.x);
+                    er += flipsign(fma(en.fr, wr, en.fi * wi), tsig + (uint32_t)__popc(l & co.lz));
+                }
+            } else if (lx == 0) {
                 // diagonal group: 8 densities per thread, 8 sign classes
                 const uint32_t kstart = k;
                 for (uint32_t p0 = threadIdx.x; p0 < ts; p0 += 8 * bd) {
@@ -1254,7 +1359,9 @@ static int ensure_buf(vqe_ctx* c, int b) {
 
 static size_t tile_smem(int tbits, int n_tiles_in_smem, bool term_cache) {
     size_t s = (size_t)n_tiles_in_smem * (16ull << tbits);
-    if (term_cache) s += TERM_CAP * (sizeof(DevTerm) + sizeof(double2)) + GROUP_CAP * sizeof(DevGroup);
+    if (term_cache)
+        s += TERM_CAP * (sizeof(DevTerm) + sizeof(double2)) + GROUP_CAP * (sizeof(DevGroup) + sizeof(DevGCol)) +
+             GCOL_ENT_CAP * sizeof(DevGColEntry);
     return s;
 }
 
@@ -1705,6 +1812,7 @@ struct HostOp {
     double c, s;
     int ny;
     double m[8];
+    double ang;          // ROT: the rotation angle itself (collapsed runs add angles)
 };
 
 static int tile_grid(const vqe_ctx* c, uint64_t n_tiles) {
@@ -1718,6 +1826,8 @@ struct OpPass {
     size_t op_begin, op_end;            // in the dev op array
     size_t sup_begin = 0, sup_end = 0;  // fast passes: shared-memory round trips (orbits) ...
     size_t sub_begin = 0, sub_end = 0;  // ... and their sub-runs
+    size_t col_begin = 0, col_end = 0;  // collapsed runs ...
+    size_t ent_begin = 0, ent_end = 0;  // ... and their (pattern, cos, sin) entries
     bool fast = false;
     bool has_imag = false;              // some rotation of a fast pass has a +-i phase
     double pass_scale = 1.0;            // fast passes: product of the cosines not yet applied by a run
@@ -1727,6 +1837,8 @@ struct OpPlan {
     std::vector<DevOp> dops;
     std::vector<DevSuper> dsupers;
     std::vector<DevSub> dsubs;
+    std::vector<DevCol> dcols;
+    std::vector<DevColEntry> dents;
     std::vector<double> mats;
 };
 
@@ -1741,6 +1853,8 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
     std::vector<DevOp>& dops = out.dops;
     std::vector<DevSuper>& dsupers = out.dsupers;
     std::vector<DevSub>& dsubs = out.dsubs;
+    std::vector<DevCol>& dcols = out.dcols;
+    std::vector<DevColEntry>& dents = out.dents;
     std::vector<double>& mats = out.mats;
     dops.reserve(ops.size());
     size_t i = 0;
@@ -1854,7 +1968,84 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
         if (p.fast) {
             p.sup_begin = dsupers.size();
             p.sub_begin = dsubs.size();
+            p.col_begin = dcols.size();
+            p.ent_begin = dents.size();
             double pending = 1.0;  // cosines are applied once per pass (tile store) unless the product gets tiny
+            // Try to collapse the same-X-mask run [k, e) into one plane rotation with a tabulated angle (see DevCol).
+            // Returns 0 = not collapsible / not worth it, 1 = emitted, 2 = the angles cancel everywhere (identity).
+            auto try_collapse = [&](size_t k, size_t e) -> int {
+                const size_t R = e - k;
+                if (R < 2) return 0;
+                uint32_t D = 0;
+                for (size_t q = k; q < e; ++q) {
+                    if (dops[q].zout != dops[k].zout) return 0;
+                    D |= dops[q].lz ^ dops[k].lz;
+                }
+                const uint32_t hb = dops[k].hb;
+                const uint32_t E = D | (1u << hb);
+                const int ne = __builtin_popcount(E);
+                if (ne > 6) return 0;
+                std::vector<uint32_t> epos;
+                for (int b2 = 0; b2 < p.tp.tbits; ++b2)
+                    if ((E >> b2) & 1u) epos.push_back((uint32_t)b2);
+                double scale = 0.0;
+                for (size_t q = k; q < e; ++q) scale += fabs(ops[i + (q - p.op_begin)].ang);
+                std::vector<DevColEntry> ent;
+                for (uint32_t pi = 0; pi < (1u << ne); ++pi) {
+                    uint32_t pat = 0;
+                    for (int b2 = 0; b2 < ne; ++b2)
+                        if ((pi >> b2) & 1u) pat |= 1u << epos[b2];
+                    if ((pat >> hb) & 1u) continue;  // a-side only
+                    double F = 0.0;
+                    for (size_t q = k; q < e; ++q) {
+                        const double kap = (dops[q].k4 >> 1) ? -1.0 : 1.0;
+                        const double sg = (__builtin_popcount(pat & (dops[q].lz ^ dops[k].lz)) & 1) ? -1.0 : 1.0;
+                        F += kap * sg * ops[i + (q - p.op_begin)].ang;
+                    }
+                    if (fabs(F) <= 1e-15 * scale) continue;  // exact cancellation up to rounding: identity on this pattern
+                    DevColEntry en;
+                    memset(&en, 0, sizeof en);
+                    en.c = cos(F);
+                    en.s = sin(F);
+                    en.pat = pat;
+                    ent.push_back(en);
+                }
+                if (ent.empty()) return 2;
+                // shared-memory budget of the pass for collapsed-run tables (the tile itself takes 64 KiB of the ~113)
+                const size_t need_bytes = sizeof(DevCol) + 4 + sizeof(DevSuper) + ent.size() * sizeof(DevColEntry);
+                if ((dcols.size() - p.col_begin) * (sizeof(DevCol) + 4 + sizeof(DevSuper)) +
+                        (dents.size() - p.ent_begin) * sizeof(DevColEntry) + need_bytes > 24 * 1024)
+                    return 0;
+                const double cost_col = (double)ent.size() * (double)(1u << (p.tp.tbits - ne)) * 35.0;
+                const double cost_seq = (double)R * (double)half_p * 6.0;
+                if (cost_col >= cost_seq) return 0;
+                DevCol co;
+                memset(&co, 0, sizeof co);
+                co.zout = dops[k].zout;
+                co.lx = dops[k].lx;
+                co.lz = dops[k].lz;
+                co.n_active = (uint32_t)ent.size();
+                co.nd = (uint32_t)ne;
+                for (int b2 = 0; b2 < ne; ++b2) co.dpos[b2] = epos[b2];
+                co.ent_begin = (uint32_t)(dents.size() - p.ent_begin);
+                co.free_log = (uint32_t)(p.tp.tbits - ne);
+                co.imag = dops[k].imag;
+                if (co.imag) p.has_imag = true;
+                DevSuper su;
+                memset(&su, 0, sizeof su);
+                su.sub_begin = (uint32_t)(dcols.size() - p.col_begin);
+                su.sub_count = 0xffffffffu;
+                su.cscale = 1.0;
+                dcols.push_back(co);
+                dents.insert(dents.end(), ent.begin(), ent.end());
+                dsupers.push_back(su);
+                return 1;
+            };
+            auto run_end_of = [&](size_t k) {
+                size_t e = k + 1;
+                while (e < p.op_end && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
+                return e;
+            };
             auto close_scale = [&](DevSuper& su, size_t first_sub) {
                 for (size_t q = first_sub; q < dsubs.size(); ++q)
                     for (uint32_t w = 0; w < dsubs[q].len; ++w) pending *= rot_cos[dsubs[q].begin + w];
@@ -1865,7 +2056,17 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                 }
             };
             size_t k = p.op_begin;
+            std::vector<char> col_state(p.op_end - p.op_begin, 0);  // per run head: 0 unknown, 1 tried and refused
             while (k < p.op_end) {
+                {
+                    const size_t e = run_end_of(k);
+                    const int cr = try_collapse(k, e);
+                    if (cr != 0) {
+                        k = e;
+                        continue;
+                    }
+                    col_state[k - p.op_begin] = 1;
+                }
                 DevSuper su;
                 memset(&su, 0, sizeof su);
                 su.sub_begin = (uint32_t)(dsubs.size() - p.sub_begin);
@@ -1904,6 +2105,20 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                 while (k < p.op_end) {
                     size_t e = k + 1;
                     while (e < p.op_end && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
+                    if (!col_state[k - p.op_begin] && dsubs.size() > first_sub) {
+                        // a collapsible run ends this round trip (it is emitted by the outer loop)
+                        const size_t mark_c = dcols.size(), mark_e = dents.size(), mark_s = dsupers.size();
+                        const bool imag_before = p.has_imag;
+                        const int cr = try_collapse(k, e);
+                        if (cr != 0) {
+                            dcols.resize(mark_c);
+                            dents.resize(mark_e);
+                            dsupers.resize(mark_s);
+                            p.has_imag = imag_before;
+                            break;
+                        }
+                        col_state[k - p.op_begin] = 1;
+                    }
                     uint32_t coord = 0;
                     const uint32_t res = reduce(dops[k].lx, coord);
                     uint32_t cpat = coord;
@@ -1953,6 +2168,8 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
             p.pass_scale = pending;
             p.sup_end = dsupers.size();
             p.sub_end = dsubs.size();
+            p.col_end = dcols.size();
+            p.ent_end = dents.size();
         }
         passes.push_back(std::move(p));
         i = j;
@@ -1974,7 +2191,9 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
     size_t off_ops = 0, off_mats = plan.dops.size() * sizeof(DevOp);
     size_t off_runs = (off_mats + plan.mats.size() * sizeof(double) + 15) & ~size_t(15);
     size_t off_subs = off_runs + plan.dsupers.size() * sizeof(DevSuper);
-    size_t off_scat = off_subs + plan.dsubs.size() * sizeof(DevSub);
+    size_t off_cols = off_subs + plan.dsubs.size() * sizeof(DevSub);
+    size_t off_ents = off_cols + plan.dcols.size() * sizeof(DevCol);
+    size_t off_scat = off_ents + plan.dents.size() * sizeof(DevColEntry);
     off_scat = (off_scat + 15) & ~size_t(15);
     size_t total = off_scat;
     std::vector<size_t> scat_off(passes.size());
@@ -1992,6 +2211,8 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
         if (!plan.mats.empty()) memcpy(c->h_stage + off_mats, plan.mats.data(), plan.mats.size() * sizeof(double));
         if (!plan.dsupers.empty()) memcpy(c->h_stage + off_runs, plan.dsupers.data(), plan.dsupers.size() * sizeof(DevSuper));
         if (!plan.dsubs.empty()) memcpy(c->h_stage + off_subs, plan.dsubs.data(), plan.dsubs.size() * sizeof(DevSub));
+        if (!plan.dcols.empty()) memcpy(c->h_stage + off_cols, plan.dcols.data(), plan.dcols.size() * sizeof(DevCol));
+        if (!plan.dents.empty()) memcpy(c->h_stage + off_ents, plan.dents.data(), plan.dents.size() * sizeof(DevColEntry));
         for (size_t p = 0; p < passes.size(); ++p)
             memcpy(c->h_stage + scat_off[p], passes[p].tp.scat.data(), passes[p].tp.scat.size() * sizeof(uint64_t));
         c->h2d_bytes += total;
@@ -2025,7 +2246,8 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
             if (g.n_tiles == 0) continue;
             size_t smem = tile_smem(ps.tp.tbits, 1, false) +
                           (ps.fast ? (ps.op_end - ps.op_begin) * sizeof(RotOp) + (ps.sup_end - ps.sup_begin) * sizeof(DevSuper) +
-                                         (ps.sub_end - ps.sub_begin) * sizeof(DevSub)
+                                         (ps.sub_end - ps.sub_begin) * sizeof(DevSub) + (ps.col_end - ps.col_begin) * (sizeof(DevCol) + 4) +
+                                         (ps.ent_end - ps.ent_begin) * sizeof(DevColEntry)
                                    : (ps.op_end - ps.op_begin) * sizeof(FastOp));
             int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
             ProfScope prof(c, ps.tp.vbit ? 4 : 0);
@@ -2033,12 +2255,16 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
                 k_tile_rot<true><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                     sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
                     (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
-                    (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin), ps.pass_scale);
+                    (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
+                    (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
+                    (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale);
             else if (ps.fast)
                 k_tile_rot<false><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                     sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
                     (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
-                    (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin), ps.pass_scale);
+                    (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
+                    (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
+                    (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale);
             else
                 k_tile_ops<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                     sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
@@ -2082,6 +2308,7 @@ static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const u
         h.ny = ny[k];
         h.c = cos(angle[k]);
         h.s = sin(angle[k]);
+        h.ang = angle[k];
         ops.push_back(h);
     }
     return run_ops(rs, ops);
@@ -2115,6 +2342,7 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
         h.ny = ny[k];
         h.c = cos(angle[k]);
         h.s = sin(angle[k]);
+        h.ang = angle[k];
         ops.push_back(h);
     }
     OpPlan plan;
@@ -2131,8 +2359,8 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
         size_t nruns = plan.dsubs.size(), nfast = 0, lens[9] = {0};
         for (const OpPass& p : plan.passes) nfast += p.fast ? 1 : 0;
         for (const DevSub& r : plan.dsubs) lens[std::min<uint32_t>(r.len, 8)]++;
-        fprintf(stderr, "[plan] passes %zu (fast %zu) ops %zu round trips %zu sub-runs %zu; sub-run-length histogram 1..8+:",
-                plan.passes.size(), nfast, plan.dops.size(), plan.dsupers.size(), nruns);
+        fprintf(stderr, "[plan] passes %zu (fast %zu) ops %zu segments %zu (collapsed runs %zu, %zu active patterns) sub-runs %zu; sub-run-length histogram 1..8+:",
+                plan.passes.size(), nfast, plan.dops.size(), plan.dsupers.size(), plan.dcols.size(), plan.dents.size(), nruns);
         for (int k = 1; k <= 8; ++k) fprintf(stderr, " %zu", lens[k]);
         fprintf(stderr, "\n");
     }
@@ -2203,6 +2431,10 @@ struct PSPass {
     std::vector<DevGroup> groups;
     std::vector<DevTerm> terms_expect;  // pair weights (expectation)
     std::vector<DevTerm> terms_apply;   // c_k i^ny   (apply)
+    std::vector<DevGCol> gcols;         // collapsed groups (expectation)
+    std::vector<DevGColEntry> gents;
+    DevGCol* d_gcols = nullptr;
+    DevGColEntry* d_gents = nullptr;
     // device copies
     DevGroup* d_groups = nullptr;
     DevTerm* d_terms_expect = nullptr;
@@ -2305,6 +2537,7 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             }
         }
         remaining -= members.size();
+        std::vector<size_t> pending_groups;
         for (size_t g : members) {
             DevGroup dg;
             memset(&dg, 0, sizeof dg);
@@ -2364,8 +2597,79 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
                 dg.cnt[(xs[g] == 0) ? cls : parity * 4 + cls]++;
             }
             p.groups.push_back(dg);
+            pending_groups.push_back(p.groups.size() - 1);
+        }
+        // collapse groups whose Z-variants differ on few tile bits (needs real weights: decided once p.cplx is known)
+        for (size_t gi2 : pending_groups) {
+            DevGroup& dg = p.groups[gi2];
+            const uint32_t nt = dg.n_even + dg.n_odd;
+            if (p.cplx || dg.lx == 0 || nt < 2 || p.gcols.size() >= GROUP_CAP) continue;
+            const DevTerm* te = p.terms_expect.data() + dg.t_begin;
+            uint32_t D = 0;
+            bool same_out = true;
+            for (uint32_t q = 0; q < nt; ++q) {
+                D |= te[q].lz ^ te[0].lz;
+                same_out = same_out && te[q].zout == te[0].zout;
+            }
+            const uint32_t E = D | (1u << dg.hb);
+            const int ne = __builtin_popcount(E);
+            if (!same_out || ne > 6) continue;
+            std::vector<uint32_t> epos;
+            for (int b2 = 0; b2 < p.tp.tbits; ++b2)
+                if ((E >> b2) & 1u) epos.push_back((uint32_t)b2);
+            double scale = 0.0;
+            for (uint32_t q = 0; q < nt; ++q) scale += fabs(te[q].ar);
+            std::vector<DevGColEntry> ent;
+            for (uint32_t pi = 0; pi < (1u << ne); ++pi) {
+                uint32_t pat = 0;
+                for (int b2 = 0; b2 < ne; ++b2)
+                    if ((pi >> b2) & 1u) pat |= 1u << epos[b2];
+                if ((pat >> dg.hb) & 1u) continue;  // a-side only
+                double fr = 0.0, fi = 0.0;
+                for (uint32_t q = 0; q < nt; ++q) {
+                    const double sg = (__builtin_popcount(pat & (te[q].lz ^ te[0].lz)) & 1) ? -1.0 : 1.0;
+                    if (q < dg.n_even) fr += sg * te[q].ar;
+                    else fi += sg * te[q].ar;
+                }
+                if (fabs(fr) <= 1e-15 * scale) fr = 0.0;
+                if (fabs(fi) <= 1e-15 * scale) fi = 0.0;
+                if (fr == 0.0 && fi == 0.0) continue;
+                DevGColEntry en;
+                memset(&en, 0, sizeof en);
+                en.fr = fr;
+                en.fi = fi;
+                en.pat = pat;
+                ent.push_back(en);
+            }
+            // cost model (instructions per thread): ~35 per active pair vs ~40 + 2 per term for every 4 pairs
+            const double cost_col = (double)ent.size() * (double)(1u << (p.tp.tbits - ne)) * 35.0;
+            const double cost_cls = (double)(1u << (p.tp.tbits - 1)) / 4.0 * (150.0 + 10.0 * nt);
+            if (cost_col >= cost_cls || p.gents.size() + ent.size() > GCOL_ENT_CAP) continue;
+            DevGCol co;
+            memset(&co, 0, sizeof co);
+            co.zout = te[0].zout;
+            co.lz = te[0].lz;
+            co.n_active = (uint32_t)ent.size();
+            co.nd = (uint32_t)ne;
+            for (int b2 = 0; b2 < ne; ++b2) co.dpos[b2] = epos[b2];
+            co.ent_begin = (uint32_t)p.gents.size();
+            co.free_log = (uint32_t)(p.tp.tbits - ne);
+            p.gcols.push_back(co);
+            p.gents.insert(p.gents.end(), ent.begin(), ent.end());
+            dg.pad = (uint32_t)p.gcols.size();  // index + 1
         }
         ps->passes.push_back(std::move(p));
+    }
+    if (getenv("VQE_DEBUG_PLAN")) {
+        size_t ng = 0, nc = 0, ne = 0, nt = 0;
+        for (const PSPass& p : ps->passes) {
+            ng += p.groups.size();
+            nc += p.gcols.size();
+            ne += p.gents.size();
+            nt += p.terms_expect.size();
+        }
+        fprintf(stderr, "[paulisum] passes %zu groups %zu terms %zu; collapsed groups %zu with %zu active patterns\n",
+                ps->passes.size(), ng, nt, nc, ne);
     }
     return VQE_OK;
 }
@@ -2376,6 +2680,10 @@ static void free_paulisum_device(vqe_paulisum* ps) {
         if (p.d_terms_expect) cudaFree(p.d_terms_expect);
         if (p.d_terms_apply) cudaFree(p.d_terms_apply);
         if (p.d_scat) cudaFree(p.d_scat);
+        if (p.d_gcols) cudaFree(p.d_gcols);
+        if (p.d_gents) cudaFree(p.d_gents);
+        p.d_gcols = nullptr;
+        p.d_gents = nullptr;
         p.d_groups = nullptr;
         p.d_terms_expect = p.d_terms_apply = nullptr;
         p.d_scat = nullptr;
@@ -2392,6 +2700,10 @@ static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
         CK(cudaMemcpy(p.d_terms_expect, p.terms_expect.data(), p.terms_expect.size() * sizeof(DevTerm), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(p.d_terms_apply, p.terms_apply.data(), p.terms_apply.size() * sizeof(DevTerm), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(p.d_scat, p.tp.scat.data(), p.tp.scat.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&p.d_gcols, std::max<size_t>(1, p.gcols.size()) * sizeof(DevGCol)));
+        CK(cudaMalloc((void**)&p.d_gents, std::max<size_t>(1, p.gents.size()) * sizeof(DevGColEntry)));
+        CK(cudaMemcpy(p.d_gcols, p.gcols.data(), p.gcols.size() * sizeof(DevGCol), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p.d_gents, p.gents.data(), p.gents.size() * sizeof(DevGColEntry), cudaMemcpyHostToDevice));
     }
     return VQE_OK;
 }
@@ -2511,11 +2823,13 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             if (pp.cplx)
                 k_tile_expect<true><<<grids[k][p], threads, smem, c->stream>>>(shards[k][p], geoms[k][p], pp.d_groups,
                                                                               (int)pp.groups.size(), pp.d_terms_expect,
-                                                                              c->d_partial + off[k]);
+                                                                              pp.d_gcols, (int)pp.gcols.size(), pp.d_gents,
+                                                                              (int)pp.gents.size(), c->d_partial + off[k]);
             else
                 k_tile_expect<false><<<grids[k][p], threads, smem, c->stream>>>(shards[k][p], geoms[k][p], pp.d_groups,
                                                                                (int)pp.groups.size(), pp.d_terms_expect,
-                                                                               c->d_partial + off[k]);
+                                                                               pp.d_gcols, (int)pp.gcols.size(), pp.d_gents,
+                                                                               (int)pp.gents.size(), c->d_partial + off[k]);
             c->launches++;
             CK(cudaGetLastError());
             off[k] += (size_t)grids[k][p].x * grids[k][p].y;
@@ -2939,6 +3253,7 @@ extern "C" int vqe_apply_exp_paulisum(vqe_ctx* c, int n_terms, const uint64_t* x
             double ang = -theta * t.ci;
             h.c = cos(ang);
             h.s = sin(ang);
+            h.ang = ang;
             ops.push_back(h);
         }
         return run_ops(c, ops);

@@ -66,6 +66,52 @@ def test_same_xmask_runs_and_zero_angles(engines):
     assert np.max(np.abs(eng.get_state() - ref)) < TOL
 
 
+@pytest.mark.parametrize("n,real_start", [(6, False), (10, True), (12, False), (13, True), (14, False)])
+def test_collapsed_runs_jw_excitations(engines, n, real_start):
+    """Same-X-mask runs are collapsed into ONE plane rotation with a tabulated angle (the 8 strings of a JW double
+    excitation touch 1/8 of the pairs).  Checked on a complex random state (general kernel variant) and on a basis
+    state (purely-real variant), for +-1 phases (ny odd) and +-i phases (ny even), against string-by-string oracle."""
+    from openvqe_b200.lowering import pack_operator, term_masks
+    from tests.helpers import jw_excitation
+    rng = np.random.default_rng(900 + n)
+    eng = engines(n)
+    xs, zs, nys, angs = [], [], [], []
+    for g in range(12):
+        if g % 4 == 3:
+            p, q = sorted(rng.choice(n, size=2, replace=False).tolist())
+            pk = pack_operator(jw_excitation(n, [q], [p]))
+        else:
+            p, q, r, s = sorted(rng.choice(n, size=4, replace=False).tolist())
+            pk = pack_operator(jw_excitation(n, [r, s], [p, q]))
+        th = float(rng.uniform(-0.8, 0.8))
+        for k in range(len(pk)):
+            xs.append(int(pk.x[k])); zs.append(int(pk.z[k])); nys.append(int(pk.ny[k])); angs.append(th * float(pk.cre[k]))
+        if g % 3 == 1 and not real_start:
+            # a run of even-ny strings on the same X-mask: XXXX, XXYY, YYXX, XYXY with a common Z chain (+-i phases)
+            for op in ["XXXX", "XXYY", "YYXX", "XYXY"]:
+                qb = list(range(p, q)) + [q] if False else [p, q, r, s] if g % 4 != 3 else None
+                if qb is None:
+                    break
+                x, z, ny = term_masks(op, qb, n)
+                xs.append(x); zs.append(z); nys.append(ny); angs.append(float(rng.uniform(-0.4, 0.4)))
+    if real_start:
+        hf = ((1 << (n // 2)) - 1) << (n - n // 2)
+        eng.set_basis_state(hf)
+        ref = orc.basis_state(n, hf)
+    else:
+        ref = random_state(rng, n)
+        eng.set_state(ref)
+    for x, z, ny, a in zip(xs, zs, nys, angs):
+        ref = orc.pauli_rotation(ref, x, z, ny, a)
+    eng.apply_rotations(xs, zs, nys, angs)
+    got = eng.get_state()
+    assert np.max(np.abs(got - ref)) < TOL
+    if real_start:
+        assert np.all(got.imag == 0.0)
+        # occupation patterns a fermionic excitation cannot reach stay EXACTLY zero
+        assert np.all(got[np.abs(ref) < 1e-13] == 0.0)
+
+
 def test_structural_zeros_stay_exact(engines):
     """Amplitudes outside the reachable sector must remain exactly 0.0."""
     from openvqe_b200.lowering import term_masks
