@@ -86,13 +86,10 @@ def test_collapsed_runs_jw_excitations(engines, n, real_start):
         th = float(rng.uniform(-0.8, 0.8))
         for k in range(len(pk)):
             xs.append(int(pk.x[k])); zs.append(int(pk.z[k])); nys.append(int(pk.ny[k])); angs.append(th * float(pk.cre[k]))
-        if g % 3 == 1 and not real_start:
-            # a run of even-ny strings on the same X-mask: XXXX, XXYY, YYXX, XYXY with a common Z chain (+-i phases)
+        if g % 3 == 1 and g % 4 != 3 and not real_start:
+            # a run of even-ny strings on the same X-mask (+-i phases): collapsed with the imaginary-phase formula
             for op in ["XXXX", "XXYY", "YYXX", "XYXY"]:
-                qb = list(range(p, q)) + [q] if False else [p, q, r, s] if g % 4 != 3 else None
-                if qb is None:
-                    break
-                x, z, ny = term_masks(op, qb, n)
+                x, z, ny = term_masks(op, [p, q, r, s], n)
                 xs.append(x); zs.append(z); nys.append(ny); angs.append(float(rng.uniform(-0.4, 0.4)))
     if real_start:
         hf = ((1 << (n // 2)) - 1) << (n - n // 2)
