@@ -2018,7 +2018,10 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                     return 0;
                 const double cost_col = (double)ent.size() * (double)(1u << (p.tp.tbits - ne)) * 35.0;
                 const double cost_seq = (double)R * (double)half_p * 6.0;
-                if (cost_col >= cost_seq) return 0;
+                // patterns with an exactly vanishing angle are left untouched by the collapsed form (structural zeros
+                // stay exact), so it is preferred up to twice the sequential cost
+                const bool has_identity = ent.size() < (size_t)(1u << (ne - 1));
+                if (cost_col >= (has_identity ? 2.0 : 1.0) * cost_seq) return 0;
                 DevCol co;
                 memset(&co, 0, sizeof co);
                 co.zout = dops[k].zout;
@@ -2503,38 +2506,67 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
     std::vector<char> done(xs.size(), 0);
     size_t remaining = xs.size();
     while (remaining) {
-        // seed: first-fit over the groups that share the seed's global X pattern (0 = local pass, m = peer pass r<->r^m)
+        // Choose the tile bits of this pass greedily for COVERAGE (the Pauli sum is uploaded once and evaluated
+        // thousands of times, so every pass saved is a full sweep over the state saved per evaluation):
+        // seed with the first open group, then repeatedly add the bit that completes the most open groups; when no
+        // single bit completes one, take the open group that needs the fewest new bits.  Only groups that share the
+        // seed's global X pattern can join (0 = local pass, m = peer pass between ranks r and r ^ m).
         uint64_t need = 0, pat = 0;
-        std::vector<size_t> members;
-        size_t n_terms_pass = 0;
-        for (size_t g = 0; g < xs.size(); ++g) {
-            if (done[g]) continue;
-            const uint64_t xg = xs[g] >> nl;
-            if (members.empty()) pat = xg;
-            else if (xg != pat) continue;
-            uint64_t u = need | (xs[g] & lfull);
-            if (!plan_fits(u, lowmask, tbits_max, nl, pat != 0)) {
-                if (members.empty())
-                    return fail(VQE_ERR_INVALID, "Pauli term with %d local X/Y letters exceeds the %d-bit tile",
-                                popc64(xs[g] & lfull), std::min(tbits_max, nl));
+        size_t seed = xs.size();
+        for (size_t g = 0; g < xs.size(); ++g)
+            if (!done[g]) { seed = g; break; }
+        pat = xs[seed] >> nl;
+        need = xs[seed] & lfull;
+        if (!plan_fits(need, lowmask, tbits_max, nl, pat != 0))
+            return fail(VQE_ERR_INVALID, "Pauli term with %d local X/Y letters exceeds the %d-bit tile",
+                        popc64(need), std::min(tbits_max, nl));
+        std::vector<size_t> open;  // open groups of this pattern
+        for (size_t g = 0; g < xs.size(); ++g)
+            if (!done[g] && (xs[g] >> nl) == pat) open.push_back(g);
+        const int cap_bits = std::min(tbits_max - (pat ? 1 : 0), nl);
+        for (;;) {
+            const uint64_t have = need | lowmask;
+            if (popc64(have) >= cap_bits) break;
+            // gain of every single bit: open groups that become fully covered
+            int best_bit = -1;
+            size_t best_gain = 0;
+            for (int b2 = 0; b2 < nl; ++b2) {
+                if ((have >> b2) & 1ull) continue;
+                const uint64_t with = have | (1ull << b2);
+                size_t gain = 0;
+                for (size_t g : open) {
+                    const uint64_t xl = xs[g] & lfull;
+                    if ((xl & ~with) == 0 && (xl & ~have) != 0) ++gain;
+                }
+                if (gain > best_gain) { best_gain = gain; best_bit = b2; }
+            }
+            if (best_bit >= 0) {
+                need |= 1ull << best_bit;
                 continue;
             }
-            if (!members.empty() && (n_terms_pass + grp[g].size() > TERM_CAP || members.size() >= GROUP_CAP)) continue;
-            need = u;
-            members.push_back(g);
-            n_terms_pass += grp[g].size();
-            done[g] = 1;
+            // no single bit completes a group: the open group with the fewest missing bits that still fits
+            size_t best_g = xs.size();
+            int best_missing = 1 << 30;
+            for (size_t g : open) {
+                const uint64_t xl = xs[g] & lfull;
+                const int missing = popc64(xl & ~have);
+                if (missing == 0 || popc64(have | xl) > cap_bits) continue;
+                if (missing < best_missing) { best_missing = missing; best_g = g; }
+            }
+            if (best_g == xs.size()) break;
+            need |= xs[best_g] & lfull;
         }
         PSPass p;
         p.tp = make_plan(nl, need, tbits_max, lb, pat);
-        // second sweep: anything already inside the final tile mask (within the per-pass table capacity)
-        for (size_t g = 0; g < xs.size(); ++g) {
-            if (done[g] || (xs[g] >> nl) != pat) continue;
-            if ((xs[g] & lfull & ~p.tp.tile_mask) == 0 && n_terms_pass + grp[g].size() <= TERM_CAP && members.size() < GROUP_CAP) {
-                members.push_back(g);
-                n_terms_pass += grp[g].size();
-                done[g] = 1;
-            }
+        std::vector<size_t> members;
+        size_t n_terms_pass = 0;
+        // everything inside the final tile mask (within the per-pass table capacity); the seed always goes first
+        for (size_t g : open) {
+            if ((xs[g] & lfull & ~p.tp.tile_mask) != 0) continue;
+            if (!members.empty() && (n_terms_pass + grp[g].size() > TERM_CAP || members.size() >= GROUP_CAP)) continue;
+            members.push_back(g);
+            n_terms_pass += grp[g].size();
+            done[g] = 1;
         }
         remaining -= members.size();
         std::vector<size_t> pending_groups;
