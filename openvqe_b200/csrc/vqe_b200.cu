@@ -638,7 +638,7 @@ __device__ __forceinline__ void rot_sub1(double2* tile, const RotOp* __restrict_
 // REAL: the state is known to be purely real on entry and every rotation of the pass has a +-1 phase (ny odd: the
 // UCC case -- JW images of T - T^dagger), so the imaginary parts stay exactly zero and are never touched.
 template <bool REAL>
-__global__ void __launch_bounds__(512, 2) k_tile_rot(Shards psi, TileGeom g,
+__global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, TileGeom g,
                                                      const DevOp* __restrict__ ops, int n_ops,
                                                      const DevSuper* __restrict__ supers, int n_supers,
                                                      const DevSub* __restrict__ subs, int n_subs,
@@ -796,8 +796,8 @@ __global__ void __launch_bounds__(512, 2) k_tile_ops(Shards psi, TileGeom g,
 // <psi| O |psi> for the X-mask groups of one pass.  grid = (tile workers, group chunks)
 // ------------------------------------------------------------------------------------------
 #define TERM_CAP 384    // terms per pass (host splits passes accordingly)
-#define GROUP_CAP 96    // X-mask groups per pass
-#define GCOL_ENT_CAP 384  // (pattern, weight) entries of collapsed groups per pass
+#define GROUP_CAP 80    // X-mask groups per pass
+#define GCOL_ENT_CAP 128  // (pattern, weight) entries of collapsed groups per pass
 
 // COLLAPSED group of an expectation pass (the analogue of DevCol): the Z-variants of an X-mask group differ only on
 // a few tile bits D, so sum_t c_t (-1)^parity(l & z_t) = (-1)^parity(l & z_1) * F[l restricted to D] with F tabulated
@@ -808,6 +808,18 @@ struct DevGColEntry {  // 32 bytes
     uint32_t pat;      // pattern as tile-index bits (a-side)
     uint32_t pad[3];
 };
+// Flat work list of a pass: every collapsed group with at least 256 free indices per pattern is cut into entries of
+// exactly 256 (pattern, free index) pairs, and the threads of a CTA walk the concatenated list -- no per-group
+// loop, no idle threads when a group has fewer pairs than the CTA has threads.
+struct DevFlat {       // 48 bytes
+    double fr, fi;     // weights of 2 Re(conj(b) a) and 2 Im(conj(b) a)
+    uint64_t zout;     // Z letters outside the tile
+    uint32_t lx, lz;   // X-mask, Z letters of the group's first term inside the tile
+    uint32_t pat;      // pattern bits | free-index bits above the low 8 (already deposited)
+    uint32_t nd;       // number of fixed positions (<= 4)
+    uint16_t himask[4];  // ~((1 << pos) - 1) for the fixed positions, ascending: insert0(l, pos) = l + (l & himask)
+};
+#define FLAT_CAP 320   // entries per pass (15 KiB)
 struct DevGCol {       // 64 bytes
     uint64_t zout;     // Z letters outside the tile (same for every term of the group)
     uint32_t lz;       // Z letters of the first term inside the tile
@@ -833,6 +845,7 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
                                                         const DevTerm* __restrict__ terms,
                                                         const DevGCol* __restrict__ gcols, int n_gcols,
                                                         const DevGColEntry* __restrict__ gents, int n_gents,
+                                                        const DevFlat* __restrict__ flats, int n_flats,
                                                         double2* __restrict__ partial) {
     extern __shared__ double2 tile[];
     __shared__ double red[64];
@@ -843,8 +856,15 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
     DevGroup* s_grp = (DevGroup*)(s_sc + TERM_CAP);        // GROUP_CAP
     DevGCol* s_gcol = (DevGCol*)(s_grp + GROUP_CAP);       // GROUP_CAP
     DevGColEntry* s_gent = (DevGColEntry*)(s_gcol + GROUP_CAP);  // GCOL_ENT_CAP
+    DevFlat* s_flat = (DevFlat*)(s_gent + GCOL_ENT_CAP);         // FLAT_CAP
+    uint32_t* s_fsig = (uint32_t*)(s_flat + FLAT_CAP);           // FLAT_CAP: per tile, outside-tile parity of every entry
     for (int q = threadIdx.x; q < n_gcols; q += blockDim.x) s_gcol[q] = gcols[q];
     for (int q = threadIdx.x; q < n_gents; q += blockDim.x) s_gent[q] = gents[q];
+    // this CTA's share of the flat list (blockIdx.y splits it like the groups)
+    const int fper = (n_flats + gridDim.y - 1) / gridDim.y;
+    const int f0 = min(n_flats, (int)blockIdx.y * fper), f1 = min(n_flats, f0 + fper);
+    const int nfl = f1 - f0;
+    for (int q = threadIdx.x; q < nfl; q += blockDim.x) s_flat[q] = flats[f0 + q];
     // group chunk of this CTA (blockIdx.y splits the groups of a pass when there are few tiles)
     const int per = (n_groups + gridDim.y - 1) / gridDim.y;
     const int g0 = blockIdx.y * per, g1 = min(n_groups, g0 + per);
@@ -881,10 +901,25 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
             const uint32_t par = __popcll(sbase & s_term[k].zout);
             s_sc[k] = make_double2(flipsign(s_term[k].ar, par), flipsign(s_term[k].ai, par));
         }
+        for (int q = threadIdx.x; q < nfl; q += blockDim.x) s_fsig[q] = (uint32_t)__popcll(sbase & s_flat[q].zout);
         cp_async_wait_all();
         __syncthreads();
+        // flat list of the collapsed groups: 256 (pattern, free index) pairs per entry
+        for (uint32_t it = threadIdx.x; it < ((uint32_t)nfl << 8); it += bd) {
+            const DevFlat& fe = s_flat[it >> 8];
+            uint32_t l = it & 255u;
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                if (d < (int)fe.nd) l += l & fe.himask[d];
+            l |= fe.pat;
+            const double2 a = tile[l], b = tile[l ^ fe.lx];
+            const double wr = 2.0 * fma(b.x, a.x, b.y * a.y);
+            const double wi = 2.0 * fma(b.x, a.y, -b.y * a.x);
+            er += flipsign(fma(fe.fr, wr, fe.fi * wi), s_fsig[it >> 8] + (uint32_t)__popc(l & fe.lz));
+        }
         for (int q = 0; q < ng; ++q) {
             const DevGroup& G = s_grp[q];
+            if (G.pad == 0xffffffffu) continue;  // in the flat list
             const uint32_t lx = G.lx, hb = G.hb;
             uint32_t k = G.t_begin - tb0;
             if (G.pad != 0) {
@@ -1361,7 +1396,7 @@ static size_t tile_smem(int tbits, int n_tiles_in_smem, bool term_cache) {
     size_t s = (size_t)n_tiles_in_smem * (16ull << tbits);
     if (term_cache)
         s += TERM_CAP * (sizeof(DevTerm) + sizeof(double2)) + GROUP_CAP * (sizeof(DevGroup) + sizeof(DevGCol)) +
-             GCOL_ENT_CAP * sizeof(DevGColEntry);
+             GCOL_ENT_CAP * sizeof(DevGColEntry) + FLAT_CAP * (sizeof(DevFlat) + 4);
     return s;
 }
 
@@ -1815,8 +1850,8 @@ struct HostOp {
     double ang;          // ROT: the rotation angle itself (collapsed runs add angles)
 };
 
-static int tile_grid(const vqe_ctx* c, uint64_t n_tiles) {
-    uint64_t cap = (uint64_t)c->sm_count * c->ctas_per_sm;
+static int tile_grid(const vqe_ctx* c, uint64_t n_tiles, int ctas_per_sm = 0) {
+    uint64_t cap = (uint64_t)c->sm_count * (ctas_per_sm ? ctas_per_sm : c->ctas_per_sm);
     return (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, cap));
 }
 
@@ -2255,7 +2290,7 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
             int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
             ProfScope prof(c, ps.tp.vbit ? 4 : 0);
             if (ps.fast && real_pass[p])
-                k_tile_rot<true><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
+                k_tile_rot<true><<<tile_grid(c, g.n_tiles, (smem <= 74 * 1024 && env_int("VQE_REAL_CTAS", 3) == 3) ? 3 : 0), threads, smem, c->stream>>>(
                     sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
                     (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
                     (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
@@ -2436,6 +2471,8 @@ struct PSPass {
     std::vector<DevTerm> terms_apply;   // c_k i^ny   (apply)
     std::vector<DevGCol> gcols;         // collapsed groups (expectation)
     std::vector<DevGColEntry> gents;
+    std::vector<DevFlat> flats;
+    DevFlat* d_flats = nullptr;
     DevGCol* d_gcols = nullptr;
     DevGColEntry* d_gents = nullptr;
     // device copies
@@ -2676,7 +2713,32 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             // cost model (instructions per thread): ~35 per active pair vs ~40 + 2 per term for every 4 pairs
             const double cost_col = (double)ent.size() * (double)(1u << (p.tp.tbits - ne)) * 35.0;
             const double cost_cls = (double)(1u << (p.tp.tbits - 1)) / 4.0 * (150.0 + 10.0 * nt);
-            if (cost_col >= cost_cls || p.gents.size() + ent.size() > GCOL_ENT_CAP) continue;
+            if (cost_col >= cost_cls) continue;
+            const int free_log = p.tp.tbits - ne;
+            if (ne <= 4 && free_log >= 8 && p.flats.size() + (ent.size() << (free_log - 8)) <= FLAT_CAP) {
+                // flat work list: one entry per 256 free indices of every active pattern
+                for (const DevGColEntry& en : ent)
+                    for (uint32_t hi = 0; hi < (1u << (free_log - 8)); ++hi) {
+                        DevFlat fl;
+                        memset(&fl, 0, sizeof fl);
+                        fl.fr = en.fr;
+                        fl.fi = en.fi;
+                        fl.zout = te[0].zout;
+                        fl.lx = dg.lx;
+                        fl.lz = te[0].lz;
+                        fl.nd = (uint32_t)ne;
+                        uint32_t fhi = hi << 8;  // deposit the high free-index bits now
+                        for (int b2 = 0; b2 < ne; ++b2) {
+                            fl.himask[b2] = (uint16_t)(~((1u << epos[b2]) - 1u) & 0xffffu);
+                            fhi += fhi & ~((1u << epos[b2]) - 1u);
+                        }
+                        fl.pat = en.pat | fhi;
+                        p.flats.push_back(fl);
+                    }
+                dg.pad = 0xffffffffu;
+                continue;
+            }
+            if (p.gents.size() + ent.size() > GCOL_ENT_CAP) continue;
             DevGCol co;
             memset(&co, 0, sizeof co);
             co.zout = te[0].zout;
@@ -2693,15 +2755,16 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
         ps->passes.push_back(std::move(p));
     }
     if (getenv("VQE_DEBUG_PLAN")) {
-        size_t ng = 0, nc = 0, ne = 0, nt = 0;
+        size_t ng = 0, nc = 0, ne = 0, nt = 0, nfl = 0;
         for (const PSPass& p : ps->passes) {
             ng += p.groups.size();
             nc += p.gcols.size();
+            nfl += p.flats.size();
             ne += p.gents.size();
             nt += p.terms_expect.size();
         }
-        fprintf(stderr, "[paulisum] passes %zu groups %zu terms %zu; collapsed groups %zu with %zu active patterns\n",
-                ps->passes.size(), ng, nt, nc, ne);
+        fprintf(stderr, "[paulisum] passes %zu groups %zu terms %zu; collapsed groups (per-group path) %zu with %zu active patterns; flat entries %zu\n",
+                ps->passes.size(), ng, nt, nc, ne, nfl);
     }
     return VQE_OK;
 }
@@ -2712,6 +2775,8 @@ static void free_paulisum_device(vqe_paulisum* ps) {
         if (p.d_terms_expect) cudaFree(p.d_terms_expect);
         if (p.d_terms_apply) cudaFree(p.d_terms_apply);
         if (p.d_scat) cudaFree(p.d_scat);
+        if (p.d_flats) cudaFree(p.d_flats);
+        p.d_flats = nullptr;
         if (p.d_gcols) cudaFree(p.d_gcols);
         if (p.d_gents) cudaFree(p.d_gents);
         p.d_gcols = nullptr;
@@ -2736,6 +2801,8 @@ static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
         CK(cudaMalloc((void**)&p.d_gents, std::max<size_t>(1, p.gents.size()) * sizeof(DevGColEntry)));
         CK(cudaMemcpy(p.d_gcols, p.gcols.data(), p.gcols.size() * sizeof(DevGCol), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(p.d_gents, p.gents.data(), p.gents.size() * sizeof(DevGColEntry), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&p.d_flats, std::max<size_t>(1, p.flats.size()) * sizeof(DevFlat)));
+        CK(cudaMemcpy(p.d_flats, p.flats.data(), p.flats.size() * sizeof(DevFlat), cudaMemcpyHostToDevice));
     }
     return VQE_OK;
 }
@@ -2856,12 +2923,14 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                 k_tile_expect<true><<<grids[k][p], threads, smem, c->stream>>>(shards[k][p], geoms[k][p], pp.d_groups,
                                                                               (int)pp.groups.size(), pp.d_terms_expect,
                                                                               pp.d_gcols, (int)pp.gcols.size(), pp.d_gents,
-                                                                              (int)pp.gents.size(), c->d_partial + off[k]);
+                                                                              (int)pp.gents.size(), pp.d_flats, (int)pp.flats.size(),
+                                                                              c->d_partial + off[k]);
             else
                 k_tile_expect<false><<<grids[k][p], threads, smem, c->stream>>>(shards[k][p], geoms[k][p], pp.d_groups,
                                                                                (int)pp.groups.size(), pp.d_terms_expect,
                                                                                pp.d_gcols, (int)pp.gcols.size(), pp.d_gents,
-                                                                               (int)pp.gents.size(), c->d_partial + off[k]);
+                                                                               (int)pp.gents.size(), pp.d_flats, (int)pp.flats.size(),
+                                                                               c->d_partial + off[k]);
             c->launches++;
             CK(cudaGetLastError());
             off[k] += (size_t)grids[k][p].x * grids[k][p].y;
