@@ -297,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
     n_rot, n_groups = len(rot.x), ps.n_groups
     prep_alg = n_rot * 2.0 * S * args.steps      # 2*S per rotation
     exp_alg = n_groups * S * args.steps          # S per X-mask group
-    prep = {"kernel": "k_tile_ops", "bound": "hbm", "achieved": prep_alg / (prep_ms / 1e3) / 1e9, "peak": peak,
+    prep = {"kernel": "k_tile_rot", "bound": "hbm", "achieved": prep_alg / (prep_ms / 1e3) / 1e9, "peak": peak,
             "unit": "GB/s", "launches_per_step": prep_n / args.steps, "ms_per_step": prep_ms / args.steps,
             "algorithmic_bytes_per_launch": prep_alg / max(prep_n, 1), "physical_bytes_per_launch": 2.0 * S,
             "physical_gbs": prep_n * 2.0 * S / (prep_ms / 1e3) / 1e9, "rotations_per_pass": n_rot * args.steps / max(prep_n, 1)}
@@ -308,7 +308,15 @@ def run_ours(args, rank, world, local_rank):
     dom, other = (prep, expk) if prep_ms >= exp_ms else (expk, prep)
     roofline = dict(dom)
     roofline["frac"] = dom["achieved"] / peak
+    # DRAM bytes per launch of that kernel from the committed ncu capture of this same command (profiles/)
     roofline["traffic"] = None
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tr = json.load(f).get(dom["kernel"])
+        if tr:
+            roofline["traffic"] = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+            roofline["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_ncu_traffic.json"
     roofline["peak_source"] = peak_src
     roofline["share_of_step"] = dom["ms_per_step"] / (ms / args.steps)
     other = dict(other)
