@@ -490,8 +490,8 @@ struct DevCol {        // 64 bytes
     uint64_t zout;         // Z letters outside the tile (same for every string of the run)
     uint32_t lx, lz;       // X-mask; Z letters of the first string inside the tile
     uint32_t n_active;     // patterns with a non-zero angle
-    uint32_t nd;           // fixed positions (D and the highest X bit), ascending in dpos
-    uint32_t dpos[6];
+    uint32_t nd;           // fixed positions (D and the highest X bit), ascending
+    uint32_t dpos[6];      // as masks ~((1 << pos) - 1): insert0(l, pos) = l + (l & mask)
     uint32_t ent_begin;    // into the pass-local entry table
     uint32_t free_log;     // log2(number of a-side indices per pattern)
     uint32_t imag;
@@ -515,6 +515,69 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void tile_load_async(double2* tile, const Shards& src, const TileGeom& g, uint64_t base) {
     const uint32_t ts = 1u << g.tbits;
     for (uint32_t k = threadIdx.x; k < ts; k += blockDim.x) cp_async16(tile + k, amp_addr(g, src, base, k));
+}
+// Per-thread address pieces of the tile gather.  Element k = tid + j * blockDim of a tile sits at amplitude index
+// base | scat[k >> lbits] | (k & lmask); the deposit `scat` is bitwise, so with a power-of-two block size it splits
+// into a per-thread constant (a_fix, one global load per kernel) and a per-j constant (s_boff[j], shared memory):
+// the per-element address is one 64-bit OR and one add instead of a table load and a handful of shifts.
+struct TileAddr {
+    uint64_t a_fix;
+    bool fast;
+};
+__device__ __forceinline__ TileAddr tile_addr_init(const TileGeom& g, uint64_t* s_boff /* >= 16 entries */) {
+    TileAddr ta;
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t top = g.tbits - 1u;
+    ta.fast = (ts % blockDim.x == 0) && (ts / blockDim.x <= 16u) && (blockDim.x >> g.lbits) >= 1u &&
+              (!g.vbit || blockDim.x <= (1u << top));
+    ta.a_fix = 0;
+    if (ta.fast) {
+        const uint32_t lmask = (1u << g.lbits) - 1u;
+        if (threadIdx.x < ts / blockDim.x) {
+            uint32_t kk = threadIdx.x * blockDim.x;
+            if (g.vbit) kk &= (1u << top) - 1u;
+            s_boff[threadIdx.x] = __ldg(g.scat + (kk >> g.lbits));
+        }
+        ta.a_fix = __ldg(g.scat + (threadIdx.x >> g.lbits)) | (uint64_t)(threadIdx.x & lmask);
+    }
+    __syncthreads();
+    return ta;
+}
+__device__ __forceinline__ double2* amp_addr_fast(const TileGeom& g, const Shards& sh, const TileAddr& ta,
+                                                  const uint64_t* s_boff, uint64_t base, uint32_t j) {
+    double2* p = (g.vbit && ((j * blockDim.x) >> (g.tbits - 1u))) ? sh.p1 : sh.p0;
+    return p + (base | ta.a_fix | s_boff[j]);
+}
+__device__ __forceinline__ void tile_load_async_fast(double2* tile, const Shards& src, const TileGeom& g, const TileAddr& ta,
+                                                     const uint64_t* s_boff, uint64_t base) {
+    if (!ta.fast) {
+        tile_load_async(tile, src, g, base);
+        return;
+    }
+    const uint32_t nj = (1u << g.tbits) / blockDim.x;
+    for (uint32_t j = 0; j < nj; ++j)
+        cp_async16(tile + threadIdx.x + j * blockDim.x, amp_addr_fast(g, src, ta, s_boff, base, j));
+}
+__device__ __forceinline__ void tile_store_scaled_fast(const double2* tile, const Shards& dst, const TileGeom& g,
+                                                       const TileAddr& ta, const uint64_t* s_boff, uint64_t base,
+                                                       double scale) {
+    const uint32_t ts = 1u << g.tbits;
+    if (!ta.fast) {
+        for (uint32_t k = threadIdx.x; k < ts; k += blockDim.x) {
+            const double2 v = tile[k];
+            *amp_addr(g, dst, base, k) = make_double2(scale * v.x, scale * v.y);
+        }
+        return;
+    }
+    const uint32_t nj = ts / blockDim.x;
+    if (scale == 1.0) {  // every run collapsed: nothing to rescale
+        for (uint32_t j = 0; j < nj; ++j) *amp_addr_fast(g, dst, ta, s_boff, base, j) = tile[threadIdx.x + j * blockDim.x];
+    } else {
+        for (uint32_t j = 0; j < nj; ++j) {
+            const double2 v = tile[threadIdx.x + j * blockDim.x];
+            *amp_addr_fast(g, dst, ta, s_boff, base, j) = make_double2(scale * v.x, scale * v.y);
+        }
+    }
 }
 __device__ __forceinline__ void tile_store_scaled(const double2* tile, const Shards& dst, const TileGeom& g,
                                                   uint64_t base, double scale) {
@@ -653,6 +716,8 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
     DevColEntry* sent = (DevColEntry*)(scol + n_cols);
     DevSub* ssub = (DevSub*)(sent + n_ents);
     uint32_t* scsign = (uint32_t*)(ssub + n_subs);  // per tile: outside-tile Z parity of every collapsed run
+    __shared__ uint64_t s_boff[16];
+    const TileAddr ta = tile_addr_init(g, s_boff);
     for (int q = threadIdx.x; q < n_supers; q += blockDim.x) ssup[q] = supers[q];
     for (int q = threadIdx.x; q < n_subs; q += blockDim.x) ssub[q] = subs[q];
     for (int q = threadIdx.x; q < n_cols; q += blockDim.x) scol[q] = cols[q];
@@ -671,7 +736,7 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
         const uint64_t base = tile_base(g, t);
         const uint64_t sbase = base | g.sign_base;
         __syncthreads();
-        tile_load_async(tile, psi, g, base);
+        tile_load_async_fast(tile, psi, g, ta, s_boff, base);
         for (int r = threadIdx.x; r < n_ops; r += blockDim.x)
             optab[r].t = flipsign(ops[r].s, __popcll(sbase & ops[r].zout));
         for (int r = threadIdx.x; r < n_cols; r += blockDim.x) scsign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
@@ -688,9 +753,7 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
                 for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
                     const DevColEntry en = sent[co.ent_begin + (it >> co.free_log)];
                     uint32_t l = it & fmask;
-#pragma unroll
-                    for (int d = 0; d < 6; ++d)
-                        if (d < (int)co.nd) l = insert0(l, co.dpos[d]);
+                    for (uint32_t d = 0; d < co.nd; ++d) l += l & co.dpos[d];
                     l |= en.pat;
                     const double sn = flipsign(en.s, tsig + (uint32_t)__popc(l & co.lz));
                     if (REAL) {
@@ -742,7 +805,7 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
             }
         }
         __syncthreads();
-        tile_store_scaled(tile, psi, g, base, pass_scale);
+        tile_store_scaled_fast(tile, psi, g, ta, s_boff, base, pass_scale);
     }
 }
 
@@ -861,6 +924,8 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
     for (int q = threadIdx.x; q < n_gcols; q += blockDim.x) s_gcol[q] = gcols[q];
     for (int q = threadIdx.x; q < n_gents; q += blockDim.x) s_gent[q] = gents[q];
     // this CTA's share of the flat list (blockIdx.y splits it like the groups)
+    __shared__ uint64_t s_boff[16];
+    const TileAddr ta = tile_addr_init(g, s_boff);
     const int fper = (n_flats + gridDim.y - 1) / gridDim.y;
     const int f0 = min(n_flats, (int)blockIdx.y * fper), f1 = min(n_flats, f0 + fper);
     const int nfl = f1 - f0;
@@ -896,7 +961,7 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
         const uint64_t base = tile_base(g, t);
         const uint64_t sbase = base | g.sign_base;
         __syncthreads();  // previous tile fully consumed (and, first time, the tables are in place)
-        tile_load_async(tile, psi, g, base);
+        tile_load_async_fast(tile, psi, g, ta, s_boff, base);
         for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
             const uint32_t par = __popcll(sbase & s_term[k].zout);
             s_sc[k] = make_double2(flipsign(s_term[k].ar, par), flipsign(s_term[k].ai, par));
@@ -2064,7 +2129,7 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                 co.lz = dops[k].lz;
                 co.n_active = (uint32_t)ent.size();
                 co.nd = (uint32_t)ne;
-                for (int b2 = 0; b2 < ne; ++b2) co.dpos[b2] = epos[b2];
+                for (int b2 = 0; b2 < ne; ++b2) co.dpos[b2] = ~((1u << epos[b2]) - 1u);
                 co.ent_begin = (uint32_t)(dents.size() - p.ent_begin);
                 co.free_log = (uint32_t)(p.tp.tbits - ne);
                 co.imag = dops[k].imag;
