@@ -753,7 +753,15 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
                 for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
                     const DevColEntry en = sent[co.ent_begin + (it >> co.free_log)];
                     uint32_t l = it & fmask;
-                    for (uint32_t d = 0; d < co.nd; ++d) l += l & co.dpos[d];
+                    // deposit the free index around the fixed positions (unused slots hold a zero mask)
+                    l += l & co.dpos[0];
+                    l += l & co.dpos[1];
+                    l += l & co.dpos[2];
+                    l += l & co.dpos[3];
+                    if (co.nd > 4) {
+                        l += l & co.dpos[4];
+                        l += l & co.dpos[5];
+                    }
                     l |= en.pat;
                     const double sn = flipsign(en.s, tsig + (uint32_t)__popc(l & co.lz));
                     if (REAL) {
@@ -874,13 +882,13 @@ struct DevGColEntry {  // 32 bytes
 // Flat work list of a pass: every collapsed group with at least 256 free indices per pattern is cut into entries of
 // exactly 256 (pattern, free index) pairs, and the threads of a CTA walk the concatenated list -- no per-group
 // loop, no idle threads when a group has fewer pairs than the CTA has threads.
-struct DevFlat {       // 48 bytes
-    double fr, fi;     // weights of 2 Re(conj(b) a) and 2 Im(conj(b) a)
-    uint64_t zout;     // Z letters outside the tile
+struct DevFlat {       // 32 bytes
     uint32_t lx, lz;   // X-mask, Z letters of the group's first term inside the tile
     uint32_t pat;      // pattern bits | free-index bits above the low 8 (already deposited)
-    uint32_t nd;       // number of fixed positions (<= 4)
-    uint16_t himask[4];  // ~((1 << pos) - 1) for the fixed positions, ascending: insert0(l, pos) = l + (l & himask)
+    uint32_t zsel;     // index of the entry's outside-tile Z mask in the pass's zout table
+    uint16_t himask[4];  // ~((1 << pos) - 1) for the (up to 4) fixed positions, ascending, 0 when unused:
+                         // insert0(l, pos) = l + (l & himask)
+    double fr;         // weight of Re(conj(b) a), factor 2 included
 };
 #define FLAT_CAP 320   // entries per pass (15 KiB)
 struct DevGCol {       // 64 bytes
@@ -909,6 +917,7 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
                                                         const DevGCol* __restrict__ gcols, int n_gcols,
                                                         const DevGColEntry* __restrict__ gents, int n_gents,
                                                         const DevFlat* __restrict__ flats, int n_flats,
+                                                        const uint64_t* __restrict__ fzout,
                                                         double2* __restrict__ partial) {
     extern __shared__ double2 tile[];
     __shared__ double red[64];
@@ -920,7 +929,7 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
     DevGCol* s_gcol = (DevGCol*)(s_grp + GROUP_CAP);       // GROUP_CAP
     DevGColEntry* s_gent = (DevGColEntry*)(s_gcol + GROUP_CAP);  // GCOL_ENT_CAP
     DevFlat* s_flat = (DevFlat*)(s_gent + GCOL_ENT_CAP);         // FLAT_CAP
-    uint32_t* s_fsig = (uint32_t*)(s_flat + FLAT_CAP);           // FLAT_CAP: per tile, outside-tile parity of every entry
+    double* s_ffr = (double*)(s_flat + FLAT_CAP);                // FLAT_CAP: per tile, weight with the outside-tile parity folded in
     for (int q = threadIdx.x; q < n_gcols; q += blockDim.x) s_gcol[q] = gcols[q];
     for (int q = threadIdx.x; q < n_gents; q += blockDim.x) s_gent[q] = gents[q];
     // this CTA's share of the flat list (blockIdx.y splits it like the groups)
@@ -966,21 +975,23 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
             const uint32_t par = __popcll(sbase & s_term[k].zout);
             s_sc[k] = make_double2(flipsign(s_term[k].ar, par), flipsign(s_term[k].ai, par));
         }
-        for (int q = threadIdx.x; q < nfl; q += blockDim.x) s_fsig[q] = (uint32_t)__popcll(sbase & s_flat[q].zout);
+        for (int q = threadIdx.x; q < nfl; q += blockDim.x)
+            s_ffr[q] = flipsign(s_flat[q].fr, __popcll(sbase & fzout[s_flat[q].zsel]));
         cp_async_wait_all();
         __syncthreads();
         // flat list of the collapsed groups: 256 (pattern, free index) pairs per entry
         for (uint32_t it = threadIdx.x; it < ((uint32_t)nfl << 8); it += bd) {
             const DevFlat& fe = s_flat[it >> 8];
+            const uint2 hm = *reinterpret_cast<const uint2*>(fe.himask);
             uint32_t l = it & 255u;
-#pragma unroll
-            for (int d = 0; d < 4; ++d)
-                if (d < (int)fe.nd) l += l & fe.himask[d];
+            l += l & (hm.x & 0xffffu);
+            l += l & (hm.x >> 16);
+            l += l & (hm.y & 0xffffu);
+            l += l & (hm.y >> 16);
             l |= fe.pat;
             const double2 a = tile[l], b = tile[l ^ fe.lx];
-            const double wr = 2.0 * fma(b.x, a.x, b.y * a.y);
-            const double wi = 2.0 * fma(b.x, a.y, -b.y * a.x);
-            er += flipsign(fma(fe.fr, wr, fe.fi * wi), s_fsig[it >> 8] + (uint32_t)__popc(l & fe.lz));
+            const double w = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
+            er = fma(flipsign(s_ffr[it >> 8], __popc(l & fe.lz)), w, er);
         }
         for (int q = 0; q < ng; ++q) {
             const DevGroup& G = s_grp[q];
@@ -1461,7 +1472,7 @@ static size_t tile_smem(int tbits, int n_tiles_in_smem, bool term_cache) {
     size_t s = (size_t)n_tiles_in_smem * (16ull << tbits);
     if (term_cache)
         s += TERM_CAP * (sizeof(DevTerm) + sizeof(double2)) + GROUP_CAP * (sizeof(DevGroup) + sizeof(DevGCol)) +
-             GCOL_ENT_CAP * sizeof(DevGColEntry) + FLAT_CAP * (sizeof(DevFlat) + 4);
+             GCOL_ENT_CAP * sizeof(DevGColEntry) + FLAT_CAP * (sizeof(DevFlat) + 8);
     return s;
 }
 
@@ -2537,7 +2548,9 @@ struct PSPass {
     std::vector<DevGCol> gcols;         // collapsed groups (expectation)
     std::vector<DevGColEntry> gents;
     std::vector<DevFlat> flats;
+    std::vector<uint64_t> fzout;        // distinct outside-tile Z masks of the flat entries
     DevFlat* d_flats = nullptr;
+    uint64_t* d_fzout = nullptr;
     DevGCol* d_gcols = nullptr;
     DevGColEntry* d_gents = nullptr;
     // device copies
@@ -2780,18 +2793,21 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             const double cost_cls = (double)(1u << (p.tp.tbits - 1)) / 4.0 * (150.0 + 10.0 * nt);
             if (cost_col >= cost_cls) continue;
             const int free_log = p.tp.tbits - ne;
-            if (ne <= 4 && free_log >= 8 && p.flats.size() + (ent.size() << (free_log - 8)) <= FLAT_CAP) {
+            bool any_fi = false;
+            for (const DevGColEntry& en : ent) any_fi = any_fi || en.fi != 0.0;
+            if (!any_fi && ne <= 4 && free_log >= 8 && p.flats.size() + (ent.size() << (free_log - 8)) <= FLAT_CAP) {
                 // flat work list: one entry per 256 free indices of every active pattern
+                uint32_t zsel = 0;
+                while (zsel < p.fzout.size() && p.fzout[zsel] != te[0].zout) ++zsel;
+                if (zsel == p.fzout.size()) p.fzout.push_back(te[0].zout);
                 for (const DevGColEntry& en : ent)
                     for (uint32_t hi = 0; hi < (1u << (free_log - 8)); ++hi) {
                         DevFlat fl;
                         memset(&fl, 0, sizeof fl);
-                        fl.fr = en.fr;
-                        fl.fi = en.fi;
-                        fl.zout = te[0].zout;
+                        fl.fr = 2.0 * en.fr;
+                        fl.zsel = zsel;
                         fl.lx = dg.lx;
                         fl.lz = te[0].lz;
-                        fl.nd = (uint32_t)ne;
                         uint32_t fhi = hi << 8;  // deposit the high free-index bits now
                         for (int b2 = 0; b2 < ne; ++b2) {
                             fl.himask[b2] = (uint16_t)(~((1u << epos[b2]) - 1u) & 0xffffu);
@@ -2841,7 +2857,9 @@ static void free_paulisum_device(vqe_paulisum* ps) {
         if (p.d_terms_apply) cudaFree(p.d_terms_apply);
         if (p.d_scat) cudaFree(p.d_scat);
         if (p.d_flats) cudaFree(p.d_flats);
+        if (p.d_fzout) cudaFree(p.d_fzout);
         p.d_flats = nullptr;
+        p.d_fzout = nullptr;
         if (p.d_gcols) cudaFree(p.d_gcols);
         if (p.d_gents) cudaFree(p.d_gents);
         p.d_gcols = nullptr;
@@ -2868,6 +2886,8 @@ static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
         CK(cudaMemcpy(p.d_gents, p.gents.data(), p.gents.size() * sizeof(DevGColEntry), cudaMemcpyHostToDevice));
         CK(cudaMalloc((void**)&p.d_flats, std::max<size_t>(1, p.flats.size()) * sizeof(DevFlat)));
         CK(cudaMemcpy(p.d_flats, p.flats.data(), p.flats.size() * sizeof(DevFlat), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&p.d_fzout, std::max<size_t>(1, p.fzout.size()) * sizeof(uint64_t)));
+        CK(cudaMemcpy(p.d_fzout, p.fzout.data(), p.fzout.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
     }
     return VQE_OK;
 }
@@ -2989,13 +3009,13 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                                                                               (int)pp.groups.size(), pp.d_terms_expect,
                                                                               pp.d_gcols, (int)pp.gcols.size(), pp.d_gents,
                                                                               (int)pp.gents.size(), pp.d_flats, (int)pp.flats.size(),
-                                                                              c->d_partial + off[k]);
+                                                                              pp.d_fzout, c->d_partial + off[k]);
             else
                 k_tile_expect<false><<<grids[k][p], threads, smem, c->stream>>>(shards[k][p], geoms[k][p], pp.d_groups,
                                                                                (int)pp.groups.size(), pp.d_terms_expect,
                                                                                pp.d_gcols, (int)pp.gcols.size(), pp.d_gents,
                                                                                (int)pp.gents.size(), pp.d_flats, (int)pp.flats.size(),
-                                                                               c->d_partial + off[k]);
+                                                                               pp.d_fzout, c->d_partial + off[k]);
             c->launches++;
             CK(cudaGetLastError());
             off[k] += (size_t)grids[k][p].x * grids[k][p].y;
