@@ -261,6 +261,37 @@ def run_ours(args, rank, world, local_rank):
     exp_ms, exp_n = eng.profile_read(1)
     eng.profile(False)
     value = world * args.steps / (ms / 1e3)
+    # ---- second half of the BASELINE metric: ADAPT pool-gradient sweep time ------------------------
+    # sigma = H psi once, then <sigma|A_k|psi> for every operator of the pool in one batched sweep (reference
+    # fermionic_adapt_vqe.py:77-122).  Pool = the 1 818 UCCSD generators of the workload (as T - T^dagger);
+    # psi = the state of the last evaluation.  Not part of the timed steps above.
+    pool_sweep = None
+    if rank == 0 and not args.no_pool:
+        from openvqe_b200.engine import BUF_PSI, BUF_SIGMA
+        n_gen = int(owner.max()) + 1
+        offs = np.zeros(n_gen + 1, dtype=np.int32)
+        np.add.at(offs, owner + 1, 1)
+        offs = np.cumsum(offs).astype(np.int32)
+        pool = PackedTerms(n, rot.x, rot.z, rot.ny, np.zeros_like(rc), rc, offs)  # i * (real coefficient) * P: anti-Hermitian
+        eng.apply_paulisum(ps, dst=BUF_SIGMA, src=BUF_PSI)
+        eng.pool_overlaps(pool, bra=BUF_SIGMA, ket=BUF_PSI)  # warm-up
+        eng.synchronize()
+        for k in range(6):
+            eng.profile_read(k, reset=True)
+        eng.profile(True)
+        t0 = time.perf_counter()
+        eng.apply_paulisum(ps, dst=BUF_SIGMA, src=BUF_PSI)
+        ov = eng.pool_overlaps(pool, bra=BUF_SIGMA, ket=BUF_PSI)
+        sweep_s = time.perf_counter() - t0
+        ap_ms, ap_n = eng.profile_read(2)
+        po_ms, po_n = eng.profile_read(3)
+        eng.profile(False)
+        grads = 2.0 * ov.real
+        pool_groups = len(set(zip(owner.tolist(), rot.x.tolist())))
+        pool_sweep = {"qubits": n, "pool_size": n_gen, "pool_strings": int(len(rot.x)), "seconds": sweep_s,
+                      "sigma_ms": ap_ms, "sigma_passes": ap_n, "sweep_ms": po_ms, "sweep_passes": po_n,
+                      "algorithmic_gbs": (2.0 * pool_groups * S + (ps.n_groups + 1) * S) / max(sweep_s, 1e-9) / 1e9,
+                      "max_abs_gradient": float(np.max(np.abs(grads))), "gradient_norm": float(np.sqrt(np.sum(grads ** 2)))}
     # ---- e2e through the reference-facing API ------------------------------------------------
     from openvqe_b200.ucc_family.get_energy_ucc import EnergyUCC
     from openvqe_b200 import engine as engine_mod
@@ -288,6 +319,39 @@ def run_ours(args, rank, world, local_rank):
     h2d, d2h = eng.transfer_bytes()
     ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))
     e2e_value = world * args.steps / (ms_e2e / 1e3)
+    # ---- BASELINE config 4 names QUCCSD: the same excitations through EnergyUCC.action_quccsd ------------------
+    # (gate-defined ansatz of reference get_energy_qucc.py:11-56; every excitation template is applied as one
+    # tabulated plane rotation).  One gate-by-gate evaluation is timed beside it for comparison.
+    quccsd = None
+    if rank == 0 and not args.no_pool:
+        from openvqe_b200.ucc_family.get_energy_qucc import EnergyUCC as EnergyQUCC
+
+        class _Exc:
+            def __init__(self, qbits):
+                self.nbqbits, self.terms = n, [type("T", (), {"qbits": qbits})()]
+
+        exc = []
+        for o in range(int(owner.max()) + 1):
+            xm = int(rot.x[np.argmax(owner == o)])
+            qs = sorted(n - 1 - b for b in range(n) if (xm >> b) & 1)
+            exc.append(_Exc([qs[2], qs[3], qs[0], qs[1]] if len(qs) == 4 else [qs[1], qs[0]]))
+        qapi = EnergyQUCC()
+        qth = ths[args.warmup]
+        qapi.action_quccsd(qth, ham_obj, exc, hf, [])  # warm-up
+        eng.synchronize()
+        t0 = time.perf_counter()
+        reps = max(1, args.steps)
+        for k in range(reps):
+            e_q = qapi.action_quccsd(ths[args.warmup + k % args.steps], ham_obj, exc, hf, [])
+        t_tab = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        hot.prepare_quccsd_state(eng, n, hf, exc, qth, use_tables=False)
+        e_gate = float(eng.expectation(eng.paulisum(ham_obj)).real)
+        t_gate = time.perf_counter() - t0
+        e_tab = qapi.action_quccsd(qth, ham_obj, exc, hf, [])
+        quccsd = {"api": "openvqe_b200.ucc_family.get_energy_qucc.EnergyUCC.action_quccsd", "excitations": len(exc),
+                  "evals_per_s": 1.0 / t_tab, "ms_per_eval": t_tab * 1e3, "gate_by_gate_ms_per_eval": t_gate * 1e3,
+                  "abs_diff_vs_gate_by_gate": abs(e_tab - e_gate), "energy": e_tab}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -330,7 +394,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps, "ms_per_step": ms_e2e / args.steps,
                     "api": "openvqe_b200.ucc_family.get_energy_ucc.EnergyUCC.ucc_action"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_other": other}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_other": other,
+            "adapt_pool_sweep": pool_sweep, "quccsd": quccsd}
     if world == 1 and not args.no_cpu:
         cb = cpu_sample(w)
         line["cpu_baseline"] = {"value": 1.0 / cb["seconds_per_eval"], "unit": "evals/s", "cores": cb["cores"],
@@ -491,6 +556,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pool", action="store_true", help="skip the ADAPT pool-gradient sweep timing")
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4: 24-qubit UCCSD energy (headline; replicas when N > 1).  c5: synthetic 30-36 qubit state SHARDED over the N GPUs")
     ap.add_argument("--qubits", type=int, default=0, help="c5 only: register size (default 33/34/35/36 for 1/2/4/8 GPUs)")

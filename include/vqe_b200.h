@@ -92,6 +92,18 @@ int vqe_apply_pauli_rotations(vqe_ctx* ctx, int n_rot, const uint64_t* xmask, co
 int vqe_apply_gates(vqe_ctx* ctx, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
                     const double* angle);
 
+/* Tabulated plane rotations.  Operation k couples every pair of basis states (l, l ^ xmask[k]); for each listed
+ * a-side pattern p (bits inside xmask[k], its highest bit clear; entries tab_offsets[k] .. tab_offsets[k+1]-1)
+ * the pairs with (l & xmask[k]) == p rotate as  a' = cos a - sin b,  b' = sin a + cos b;  unlisted patterns are
+ * left untouched.  This is the exact unitary of a gate template that only couples states differing by a fixed
+ * X-mask -- the QUCCSD excitation circuits of openvqe/common_files/circuit.py:13-93 (run at
+ * get_energy_qucc.py:50-55) are of this form -- applied in ONE sweep over 2^-k of the pairs instead of gate by
+ * gate.  Not available for X-masks that touch a global qubit of a sharded state (use vqe_apply_gates there). */
+int vqe_apply_plane_rotations(vqe_ctx* ctx, int n_ops, const uint64_t* xmask, const int32_t* tab_offsets,
+                              const uint64_t* pattern, const double* cosv, const double* sinv);
+/* buf <- (re + i im) * buf  (global phase or scale) */
+int vqe_scale_state(vqe_ctx* ctx, int buf, double re, double im);
+
 /* Device-resident Pauli sum  O = sum_k (cre_k + i cim_k) P_k, grouped by X-mask at creation.
  * Replaces the `observable=hamiltonian_sp` argument of the OBS job (get_energy_ucc.py:47) and the
  * 2^n x 2^n scipy matrices hamiltonian_sparse / cluster_ops_sparse (fermionic_adapt_vqe.py:77-122). */

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .common_files.circuit import quccsd_circuit
+from .common_files.circuit import hf_index, quccsd_circuit, quccsd_plane_ops
 from .engine import BUF_PSI, BUF_SIGMA, GATE_KINDS, get_engine
 from .lowering import PackedTerms, pack_operator, pack_pool
 
@@ -100,13 +100,36 @@ def apply_gate_list(engine, gates):
     engine.apply_gates(kinds, q0, q1, ang)
 
 
+def prepare_quccsd_state(engine, n, hf_init_sp, cluster_ops, theta, use_tables=True):
+    """|psi> of the gate-defined QUCCSD ansatz (reference get_energy_qucc.py:38-51).  Every excitation template is
+    applied as ONE tabulated plane rotation (the exact unitary of its gate list, see common_files/circuit.py); if
+    some excitation is not of that form, or touches a global qubit of a sharded state, the gate list is executed."""
+    list_exci = [list(op.terms[0].qbits) for op in cluster_ops]
+    if len(theta) < len(list_exci):
+        raise IndexError("list index out of range")  # as the reference's list_theta[i] (circuit.py:95-106)
+    ops = quccsd_plane_ops(n, list_exci, theta) if use_tables else None
+    n_global = getattr(engine, "n_global", 0)
+    if ops is not None and n_global:
+        top = max(int(x).bit_length() for x in ops[0]) if len(ops[0]) else 0
+        if top > n - n_global:
+            ops = None
+    if ops is None:
+        circ = quccsd_circuit(n, hf_init_sp, cluster_ops, theta)
+        engine.set_basis_state(0)
+        apply_gate_list(engine, circ.gates)
+        return
+    x, offs, pat, cosv, sinv, phase = ops
+    engine.set_basis_state(hf_index(n, hf_init_sp))
+    engine.apply_plane_rotations(x, offs, pat, cosv, sinv)
+    if phase != 1.0:
+        engine.scale_state(phase)
+
+
 def quccsd_energy(theta, hamiltonian_sp, cluster_ops, hf_init_sp, device=0):
     """E(theta) of the gate-defined QUCCSD ansatz (reference get_energy_qucc.py:11-56)."""
     n = hamiltonian_sp.nbqbits
     engine = get_engine(n, device)
-    circ = quccsd_circuit(n, hf_init_sp, cluster_ops, theta)
-    engine.set_basis_state(0)
-    apply_gate_list(engine, circ.gates)
+    prepare_quccsd_state(engine, n, hf_init_sp, cluster_ops, theta)
     return float(engine.expectation(engine.paulisum(hamiltonian_sp)).real)
 
 

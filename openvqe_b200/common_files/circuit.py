@@ -153,3 +153,181 @@ def quccsd_circuit(nbqbits, hf_init_sp, cluster_ops, theta):
     gates = hf_gates(nbqbits, hf_init_sp, padded=False)
     gates += efficient_fermionic_ansatz_gates(list_exci, theta)
     return CircuitSummary(nbqbits, gates)
+
+
+# ---- the QUCCSD templates as tabulated plane rotations ------------------------------------------
+# Both templates only couple basis states that differ on ALL their core qubits (2 for a single, 4 for a double):
+# their unitary is a set of plane rotations on the pairs (p, p ^ 1..1), one angle per occupation pattern, times a
+# global phase.  The CNOT ladders of reference circuit.py:21-23/36-38 and :51-60/82-90 act only on the qubits strictly
+# between the core qubits, which the core never touches, and are undone gate by gate at the end of the template: they
+# cancel (the reference's "fermionic" excitation is a qubit excitation).  The angle of every pattern is linear in
+# theta; the coefficients are derived ONCE from the template's own 2^k x 2^k unitary, built here from the gate
+# matrices (myQLM conventions: RY(t) = exp(-i t Y / 2), RZ(t) = diag(e^{-it/2}, e^{it/2}), CNOT(control, target)),
+# so the engine applies exactly the unitary of the gate list -- in one sweep per excitation instead of ~30.
+def _gate_matrix(name, angle):
+    import numpy as np
+    if name == "X":
+        return np.array([[0, 1], [1, 0]], dtype=complex)
+    if name == "H":
+        return np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2.0)
+    c, s = np.cos(angle / 2.0), np.sin(angle / 2.0)
+    if name == "RX":
+        return np.array([[c, -1j * s], [-1j * s, c]], dtype=complex)
+    if name == "RY":
+        return np.array([[c, -s], [s, c]], dtype=complex)
+    if name == "RZ":
+        return np.array([[np.exp(-0.5j * angle), 0], [0, np.exp(0.5j * angle)]], dtype=complex)
+    raise ValueError(name)
+
+
+def _template_unitary(k, gates):
+    """2^k x 2^k unitary of a gate list on k role qubits (role 0 = most significant bit)."""
+    import numpy as np
+    dim = 1 << k
+    u = np.eye(dim, dtype=complex)
+    idx = np.arange(dim)
+    for name, qb, angle in gates:
+        if name == "CNOT":
+            cbit, tbit = 1 << (k - 1 - qb[0]), 1 << (k - 1 - qb[1])
+            perm = np.where(idx & cbit, idx ^ tbit, idx)
+            u = u[perm, :]
+        else:
+            m = _gate_matrix(name, angle)
+            bit = 1 << (k - 1 - qb[0])
+            lo, hi = idx[(idx & bit) == 0], idx[(idx & bit) == 0] | bit
+            new = u.copy()
+            new[lo, :] = m[0, 0] * u[lo, :] + m[0, 1] * u[hi, :]
+            new[hi, :] = m[1, 0] * u[lo, :] + m[1, 1] * u[hi, :]
+            u = new
+    return u
+
+
+def _template_table(k, builder):
+    """-> (coef[2^(k-1)], phase_per_theta...) : angle of the pair (p, p ^ (2^k - 1)), p < 2^(k-1), is coef[p] * theta
+    with a' = cos a - sin b, b' = sin a + cos b (a at p); ``phase`` is the template's global phase (theta-independent).
+    Returns None when the template is not of that form (then the gate list is executed as is)."""
+    import numpy as np
+    dim, full = 1 << k, (1 << k) - 1
+    out = []
+    for theta in (0.05, 0.1):
+        u = _template_unitary(k, builder(list(range(k)), theta))
+        phase = u[0, 0] / abs(u[0, 0])
+        v = u / phase
+        if np.abs(v.imag).max() > 1e-13:
+            return None
+        v = v.real
+        mask = np.ones((dim, dim), dtype=bool)
+        ang = np.zeros(dim // 2)
+        for p in range(dim // 2):
+            q = p ^ full
+            mask[p, p] = mask[q, q] = mask[p, q] = mask[q, p] = False
+            if abs(v[p, p] - v[q, q]) > 1e-13 or abs(v[p, q] + v[q, p]) > 1e-13:
+                return None
+            ang[p] = np.arctan2(v[q, p], v[p, p])
+        if np.abs(v[mask]).max() > 1e-13:
+            return None
+        out.append((ang / theta, phase))
+    if np.abs(out[0][0] - out[1][0]).max() > 1e-9 or abs(out[0][1] - out[1][1]) > 1e-13:
+        return None
+    return np.round(out[1][0] * 2.0) / 2.0, complex(out[1][1])   # coefficients are multiples of 1/2
+
+
+_TEMPLATES = {}
+
+
+def template_tables():
+    """{2: (coef, phase), 4: (coef, phase)} of the single / double excitation templates (None if not tabulable)."""
+    if not _TEMPLATES:
+        _TEMPLATES[2] = _template_table(2, single_excitation_gates)
+        _TEMPLATES[4] = _template_table(4, double_excitation_gates)
+    return _TEMPLATES
+
+
+def _ladders_cancel(exci):
+    """The ladder qubits (strictly between e0, e1 and between e2, e3) must not be core qubits."""
+    if len(exci) == 2:
+        return exci[0] != exci[1]
+    e0, e1, e2, e3 = exci
+    if len({e0, e1, e2, e3}) != 4:
+        return False
+    core = (e0, e1, e2, e3)
+    return not any(e0 < q < e1 or e2 < q < e3 for q in core)
+
+
+_PLANE_PROGRAMS = {}
+
+
+def _plane_program(nbqbits, list_exci):
+    """Theta-independent part of ``quccsd_plane_ops`` (cached per excitation list): X-masks, table offsets, a-side
+    patterns, the angle coefficient and owner of every entry, and the number of single excitations (global phase)."""
+    import numpy as np
+    key = (nbqbits, tuple(tuple(int(q) for q in e) for e in list_exci))
+    hit = _PLANE_PROGRAMS.get(key)
+    if hit is not None:
+        return hit
+    tabs = template_tables()
+    xs, offs, pats, coefs, owner = [], [0], [], [], []
+    phase_counts = {}
+    prog = None
+    ok = True
+    for i, exci in enumerate(key[1]):
+        k = len(exci)
+        tab = tabs.get(k)
+        if tab is None or not _ladders_cancel(exci) or min(exci) < 0 or max(exci) >= nbqbits:
+            ok = False
+            break
+        coef, ph = tab
+        bits = [1 << (nbqbits - 1 - q) for q in exci]   # index bit of every role qubit
+        x = 0
+        for b in bits:
+            x |= b
+        top = 1 << (x.bit_length() - 1)
+        for p in range(1 << (k - 1)):
+            if coef[p] == 0.0:
+                continue
+            pat = 0
+            for r in range(k):
+                if (p >> (k - 1 - r)) & 1:
+                    pat |= bits[r]
+            c = float(coef[p])
+            if pat & top:           # the engine's a-side has the highest X bit clear: swap the roles of a and b
+                pat ^= x
+                c = -c
+            pats.append(pat)
+            coefs.append(c)
+            owner.append(i)
+        xs.append(x)
+        offs.append(len(pats))
+        phase_counts[ph] = phase_counts.get(ph, 0) + 1
+    if ok:
+        prog = (np.array(xs, dtype=np.uint64), np.array(offs, dtype=np.int32), np.array(pats, dtype=np.uint64),
+                np.array(coefs, dtype=np.float64), np.array(owner, dtype=np.int64), phase_counts)
+    if len(_PLANE_PROGRAMS) > 64:
+        _PLANE_PROGRAMS.clear()
+    _PLANE_PROGRAMS[key] = prog
+    return prog
+
+
+def quccsd_plane_ops(nbqbits, list_exci, list_theta):
+    """The QUCCSD ansatz (reference circuit.py:95-106) as tabulated plane rotations for
+    ``Engine.apply_plane_rotations``: -> (xmask, offsets, pattern, cos, sin, global_phase), or None when some
+    excitation is not of the tabulable form (the caller then executes the gate list)."""
+    import numpy as np
+    prog = _plane_program(nbqbits, list_exci)
+    if prog is None:
+        return None
+    xs, offs, pats, coefs, owner, phase_counts = prog
+    theta = np.asarray([float(t) for t in list_theta[:len(list_exci)]], dtype=np.float64)
+    ang = coefs * theta[owner]
+    phase = 1.0 + 0.0j
+    for ph, cnt in phase_counts.items():
+        phase *= ph ** cnt
+    return xs, offs, pats, np.cos(ang), np.sin(ang), phase
+
+
+def hf_index(nbqbits, hf_init_sp):
+    """Basis index prepared by the reference's unpadded X gates (get_energy_qucc.py:40-45)."""
+    idx = 0
+    for name, qb, _ in hf_gates(nbqbits, hf_init_sp, padded=False):
+        idx |= 1 << (nbqbits - 1 - qb[0])
+    return idx

@@ -65,7 +65,7 @@ extern "C" int vqe_device_count(void) {
 // ------------------------------------------------------------------------------------------
 // device structures
 // ------------------------------------------------------------------------------------------
-enum { OP_ROT = 0, OP_GATE1 = 1, OP_CNOT = 2, OP_ROTF = 3 };
+enum { OP_ROT = 0, OP_GATE1 = 1, OP_CNOT = 2, OP_ROTF = 3, OP_PLANE = 4 };
 
 struct DevOp {       // 64 bytes
     uint32_t lx;     // ROT: local X mask | GATE1: local bit mask | CNOT: local target mask
@@ -1918,12 +1918,16 @@ extern "C" int vqe_synchronize(vqe_ctx* c) {
 
 // ---- generic op program ---------------------------------------------------------------------
 struct HostOp {
-    int kind;
-    uint64_t x, z;       // ROT: masks | GATE1: x = bit | CNOT: x = target bit, z = control bit
-    double c, s;
-    int ny;
-    double m[8];
-    double ang;          // ROT: the rotation angle itself (collapsed runs add angles)
+    int kind = 0;
+    uint64_t x = 0, z = 0;  // ROT: masks | GATE1: x = bit | CNOT: x = target bit, z = control bit
+    double c = 0.0, s = 0.0;
+    int ny = 0;
+    double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double ang = 0.0;    // ROT: the rotation angle itself (collapsed runs add angles)
+    // PLANE: tabulated plane rotation.  For every listed a-side pattern p (bits inside x, highest x bit clear) the
+    // pairs (l, l ^ x) with (l & x) == p rotate:  a' = c a - s b,  b' = s a + c b.  Unlisted patterns are untouched.
+    std::vector<uint64_t> ppat;
+    std::vector<double> pcos, psin;
 };
 
 static int tile_grid(const vqe_ctx* c, uint64_t n_tiles, int ctas_per_sm = 0) {
@@ -1953,7 +1957,9 @@ struct OpPlan {
     std::vector<double> mats;
 };
 
-static bool fast_eligible(const HostOp& h) { return h.kind == OP_ROT && h.x != 0 && fabs(h.c) >= 0.3; }
+static bool fast_eligible(const HostOp& h) {
+    return (h.kind == OP_ROT && h.x != 0 && fabs(h.c) >= 0.3) || h.kind == OP_PLANE;
+}
 
 // Greedy, order-preserving: a pass takes consecutive ops while the union of their LOCAL X bits fits the tile and
 // their GLOBAL X parts are 0 or one common pattern m (then the pass is a peer pass between ranks r and r^m and
@@ -2019,6 +2025,12 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                 d.nyodd = h.ny & 1;
                 d.hb = d.lx ? 31 - __builtin_clz(d.lx) : 0;
                 d.run = 1;
+            } else if (h.kind == OP_PLANE) {
+                d.kind = OP_ROTF;          // lives in fast passes; emitted as a ready-made collapsed run
+                d.lx = plan_lx(h.x, p.tp);
+                d.hb = 31 - __builtin_clz(d.lx);
+                d.c = 1.0;
+                d.nyodd = 0xffffffffu;     // marker: tabulated plane rotation (see is_plane below)
             } else if (h.kind == OP_GATE1) {
                 d.lx = plan_lx(h.x, p.tp);
                 d.hb = 31 - __builtin_clz(d.lx);
@@ -2071,11 +2083,17 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
             k = e;
         }
         p.fast = true;
-        for (size_t k = p.op_begin; k < p.op_end; ++k)
+        bool any_plane = false;
+        for (size_t k = p.op_begin; k < p.op_end; ++k) {
             if (dops[k].kind != OP_ROTF) p.fast = false;
+            if (dops[k].nyodd == 0xffffffffu) any_plane = true;
+        }
+        auto is_plane = [&](size_t k) { return dops[k].nyodd == 0xffffffffu; };
         const uint32_t half_p = (1u << p.tp.tbits) >> 1;
         const bool four = half_p == 4u * (uint32_t)threads_p;
         if (!(four || half_p <= (uint32_t)threads_p)) p.fast = false;  // k_tile_rot holds 4 pairs per thread, or 1
+        if (any_plane && !p.fast)
+            return fail(VQE_ERR_INVALID, "tabulated plane rotations need the default tile configuration");
         if (p.fast) {
             p.sup_begin = dsupers.size();
             p.sub_begin = dsubs.size();
@@ -2157,8 +2175,44 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
             };
             auto run_end_of = [&](size_t k) {
                 size_t e = k + 1;
-                while (e < p.op_end && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
+                while (e < p.op_end && !is_plane(e) && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
                 return e;
+            };
+            // a tabulated plane rotation is a ready-made collapsed run (no parity factor: lz = 0, zout = 0)
+            auto emit_plane = [&](size_t k) -> int {
+                const HostOp& h = ops[i + (k - p.op_begin)];
+                const uint32_t lx = dops[k].lx;
+                const int ne = __builtin_popcount(lx);
+                if (ne > 6 || ne > p.tp.tbits) return fail(VQE_ERR_INVALID, "plane rotation on %d qubits (max 6)", ne);
+                DevCol co;
+                memset(&co, 0, sizeof co);
+                co.lx = lx;
+                co.n_active = (uint32_t)h.ppat.size();
+                co.nd = (uint32_t)ne;
+                int b3 = 0;
+                for (int b2 = 0; b2 < p.tp.tbits; ++b2)
+                    if ((lx >> b2) & 1u) co.dpos[b3++] = ~((1u << b2) - 1u);
+                co.ent_begin = (uint32_t)(dents.size() - p.ent_begin);
+                co.free_log = (uint32_t)(p.tp.tbits - ne);
+                for (size_t q = 0; q < h.ppat.size(); ++q) {
+                    DevColEntry en;
+                    memset(&en, 0, sizeof en);
+                    en.c = h.pcos[q];
+                    en.s = h.psin[q];
+                    en.pat = plan_lx(h.ppat[q], p.tp);
+                    if ((en.pat >> dops[k].hb) & 1u)  // keep the a-side convention "highest tile X bit clear"
+                        return fail(VQE_ERR_INVALID, "plane rotation pattern must leave the highest X bit clear");
+                    dents.push_back(en);
+                }
+                if (h.ppat.empty()) return VQE_OK;  // identity
+                DevSuper su;
+                memset(&su, 0, sizeof su);
+                su.sub_begin = (uint32_t)(dcols.size() - p.col_begin);
+                su.sub_count = 0xffffffffu;
+                su.cscale = 1.0;
+                dcols.push_back(co);
+                dsupers.push_back(su);
+                return VQE_OK;
             };
             auto close_scale = [&](DevSuper& su, size_t first_sub) {
                 for (size_t q = first_sub; q < dsubs.size(); ++q)
@@ -2172,6 +2226,12 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
             size_t k = p.op_begin;
             std::vector<char> col_state(p.op_end - p.op_begin, 0);  // per run head: 0 unknown, 1 tried and refused
             while (k < p.op_end) {
+                if (is_plane(k)) {
+                    const int prc = emit_plane(k);
+                    if (prc) return prc;
+                    ++k;
+                    continue;
+                }
                 {
                     const size_t e = run_end_of(k);
                     const int cr = try_collapse(k, e);
@@ -2187,8 +2247,7 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                 su.hb_log = 31 - __builtin_clz(half_p ? half_p : 1u);
                 const size_t first_sub = dsubs.size();
                 if (!four) {  // one pair per thread: every same-X-mask run is its own round trip
-                    size_t e = k + 1;
-                    while (e < p.op_end && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
+                    const size_t e = run_end_of(k);
                     dsubs.push_back({(uint32_t)(k - p.op_begin), (uint32_t)(e - k), 1u, dops[k].imag});
                     if (dops[k].imag) p.has_imag = true;
                     su.e0 = dops[k].hb;
@@ -2217,8 +2276,8 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                     return (uint32_t)(31 - __builtin_clz(res));
                 };
                 while (k < p.op_end) {
-                    size_t e = k + 1;
-                    while (e < p.op_end && dops[e].lx == dops[k].lx && dops[e].imag == dops[k].imag) ++e;
+                    if (is_plane(k)) break;  // emitted by the outer loop
+                    size_t e = run_end_of(k);
                     if (!col_state[k - p.op_begin] && dsubs.size() > first_sub) {
                         // a collapsible run ends this round trip (it is emitted by the outer loop)
                         const size_t mark_c = dcols.size(), mark_e = dents.size(), mark_s = dsupers.size();
@@ -2414,8 +2473,7 @@ static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const u
         if ((xmask[k] | zmask[k]) & ~full) return fail(VQE_ERR_INVALID, "rotation %d: mask has bits >= n_qubits", k);
         if (popc64(xmask[k] & zmask[k]) != ny[k]) return fail(VQE_ERR_INVALID, "rotation %d: ny != popcount(x&z)", k);
         if (angle[k] == 0.0) continue;  // exact identity
-        HostOp h;
-        memset(&h, 0, sizeof h);
+        HostOp h = HostOp();
         h.kind = OP_ROT;
         h.x = xmask[k];
         h.z = zmask[k];
@@ -2448,8 +2506,7 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
     std::vector<HostOp> ops;
     for (int k = 0; k < n_rot; ++k) {
         if (angle[k] == 0.0) continue;
-        HostOp h;
-        memset(&h, 0, sizeof h);
+        HostOp h = HostOp();
         h.kind = OP_ROT;
         h.x = xmask[k];
         h.z = zmask[k];
@@ -2481,6 +2538,52 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
     return VQE_OK;
 }
 
+// Tabulated plane rotations: the unitary of a gate template that only couples basis states differing by a fixed
+// X-mask, given as (pattern, cos, sin) per coupled pair class.  Replaces the gate-by-gate execution of the QUCCSD
+// excitation circuits (openvqe/common_files/circuit.py:13-93 as run at get_energy_qucc.py:50-55): the host derives
+// the table of a template once from its 2- or 4-qubit unitary (openvqe_b200/common_files/circuit.py).
+extern "C" int vqe_apply_plane_rotations(vqe_ctx* c, int n_ops, const uint64_t* xmask, const int32_t* tab_offsets,
+                                         const uint64_t* pattern, const double* cosv, const double* sinv) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    if (n_ops < 0 || (n_ops > 0 && (!xmask || !tab_offsets))) return fail(VQE_ERR_INVALID, "null array");
+    const uint64_t full = (1ull << c->n) - 1ull;
+    std::vector<HostOp> ops;
+    ops.reserve(n_ops);
+    for (int k = 0; k < n_ops; ++k) {
+        if (xmask[k] == 0 || (xmask[k] & ~full)) return fail(VQE_ERR_INVALID, "plane rotation %d: bad X-mask", k);
+        if (c->g && (xmask[k] >> c->nl))
+            return fail(VQE_ERR_INVALID, "plane rotation %d touches a global qubit of a sharded state (use vqe_apply_gates)", k);
+        const uint64_t top = 1ull << (63 - __builtin_clzll(xmask[k]));
+        HostOp h = HostOp();
+        h.kind = OP_PLANE;
+        h.x = xmask[k];
+        for (int q = tab_offsets[k]; q < tab_offsets[k + 1]; ++q) {
+            if ((pattern[q] & ~xmask[k]) || (pattern[q] & top))
+                return fail(VQE_ERR_INVALID, "plane rotation %d: pattern must lie inside the X-mask with its highest bit clear", k);
+            if (sinv[q] == 0.0 && cosv[q] == 1.0) continue;  // identity on this pattern
+            h.ppat.push_back(pattern[q]);
+            h.pcos.push_back(cosv[q]);
+            h.psin.push_back(sinv[q]);
+        }
+        if (h.ppat.empty()) continue;
+        ops.push_back(h);
+    }
+    return run_ops(c, ops);
+}
+
+// psi <- (re + i im) psi  (global phase / scale; the QUCCSD single-excitation template carries e^{i pi/4})
+extern "C" int vqe_scale_state(vqe_ctx* c, int b, double re, double im) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, b);
+    if (rc) return rc;
+    if (b == VQE_BUF_PSI && im != 0.0) c->psi_real = false;
+    k_axpby<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[b], c->buf[b], c->n_amp, re, im, 0.0, 0.0);
+    c->launches++;
+    CK(cudaGetLastError());
+    return VQE_OK;
+}
+
 static RankSet rankset_of(vqe_ctx* const* ranks, int n_ranks) {
     RankSet rs;
     for (int k = 0; ranks && k < n_ranks; ++k) rs.r.push_back(ranks[k]);
@@ -2503,8 +2606,7 @@ static int gates_impl(RankSet& rs, int n_gates, const int32_t* kind, const int32
     const double r2 = 0.70710678118654752440;
     for (int k = 0; k < n_gates; ++k) {
         if (q0[k] < 0 || q0[k] >= c->n) return fail(VQE_ERR_INVALID, "gate %d: qubit %d out of range", k, q0[k]);
-        HostOp h;
-        memset(&h, 0, sizeof h);
+        HostOp h = HostOp();
         h.x = 1ull << (c->n - 1 - q0[k]);
         double th = angle ? angle[k] : 0.0;
         double cs = cos(0.5 * th), sn = sin(0.5 * th);
@@ -3430,8 +3532,7 @@ extern "C" int vqe_apply_exp_paulisum(vqe_ctx* c, int n_terms, const uint64_t* x
         // exp(theta * i*ci*P) = exp(-i (-theta ci) P): exact product of rotations
         std::vector<HostOp> ops;
         for (const HTerm& t : terms) {
-            HostOp h;
-            memset(&h, 0, sizeof h);
+            HostOp h = HostOp();
             h.kind = OP_ROT;
             h.x = t.x;
             h.z = t.z;

@@ -94,6 +94,20 @@ class Engine:
         an = np.ascontiguousarray(angles, dtype=np.float64)
         _lib.check(self._lib.vqe_apply_gates(self.handle, int(k.shape[0]), _ptr(k), _ptr(a0), _ptr(a1), _ptr(an)))
 
+    def apply_plane_rotations(self, xmask, offsets, pattern, cosv, sinv):
+        """Tabulated plane rotations (see include/vqe_b200.h): op k couples (l, l ^ xmask[k]); for every listed
+        a-side pattern the pairs rotate by (cos, sin)."""
+        x = np.ascontiguousarray(xmask, dtype=np.uint64)
+        o = np.ascontiguousarray(offsets, dtype=np.int32)
+        p = np.ascontiguousarray(pattern, dtype=np.uint64)
+        c = np.ascontiguousarray(cosv, dtype=np.float64)
+        s = np.ascontiguousarray(sinv, dtype=np.float64)
+        _lib.check(self._lib.vqe_apply_plane_rotations(self.handle, int(x.shape[0]), _ptr(x), _ptr(o), _ptr(p), _ptr(c), _ptr(s)))
+
+    def scale_state(self, factor: complex, buf=BUF_PSI):
+        f = complex(factor)
+        _lib.check(self._lib.vqe_scale_state(self.handle, buf, f.real, f.imag))
+
     def apply_exp(self, packed: PackedTerms, theta: float):
         """psi <- exp(theta * A) psi (exact exponential of the whole generator)."""
         _lib.check(self._lib.vqe_apply_exp_paulisum(self.handle, len(packed), _ptr(packed.x), _ptr(packed.z),

@@ -160,3 +160,37 @@ def test_h6_twelve_qubit_parity(gpu_required):
     for case in fx["ucc_action"]:
         assert abs(fa.ucc_action(ham, ans, fx["hf_init_sp"], case["theta"]) - case["energy"]) < TOL
     assert abs(_hotpath.basis_energy(ham, fx["hf_init_sp"]) - fx["hf_energy"]) < TOL
+
+
+@pytest.mark.parametrize("n", [6, 8, 12, 13])
+def test_quccsd_templates_as_plane_rotations_equal_the_gate_list(gpu_required, n):
+    """Every QUCCSD excitation template is applied as one tabulated plane rotation (its exact unitary): the state
+    must equal the gate-by-gate execution on the GPU and the oracle's gate-level simulation, global phase included."""
+    from openvqe_b200 import _hotpath
+    from openvqe_b200.engine import Engine
+    from tests.helpers import FermiOp
+    rng = np.random.default_rng(40 + n)
+    ops = []
+    n_occ = n // 2
+    for _ in range(10):
+        i, j = sorted(rng.choice(n_occ, size=2, replace=False).tolist())
+        a, b = sorted((n_occ + rng.choice(n - n_occ, size=2, replace=False)).tolist())
+        ops.append(FermiOp(n, [a, b, i, j]))       # myQLM layout: virtuals first
+        ops.append(FermiOp(n, [int(rng.integers(n_occ, n)), int(rng.integers(n_occ))]))
+    ops.append(FermiOp(n, [0, 1, n - 2, n - 1]))   # ascending layout with long ladders
+    ops.append(FermiOp(n, [1, n - 1]))             # single with a ladder
+    theta = rng.uniform(-0.6, 0.6, size=len(ops)).tolist()
+    hf = ((1 << n_occ) - 1) << (n - n_occ)
+    eng = Engine(n)
+    _hotpath.prepare_quccsd_state(eng, n, hf, ops, theta, use_tables=True)
+    fast = eng.get_state()
+    _hotpath.prepare_quccsd_state(eng, n, hf, ops, theta, use_tables=False)
+    gates = eng.get_state()
+    ref = orc.quccsd_state(n, hf, ops, theta)
+    assert np.max(np.abs(fast - gates)) < 1e-12
+    assert np.max(np.abs(fast - ref)) < 1e-12
+    # an excitation whose ladder runs over one of its own core qubits is not tabulable: gate list, same answer
+    odd = ops + [FermiOp(n, [0, 3, 2, 4])] if n > 4 else ops
+    th2 = theta + [0.3]
+    _hotpath.prepare_quccsd_state(eng, n, hf, odd, th2, use_tables=True)
+    assert np.max(np.abs(eng.get_state() - orc.quccsd_state(n, hf, odd, th2))) < 1e-12
