@@ -1101,13 +1101,31 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
 // ------------------------------------------------------------------------------------------
 // dst (+)= O src for the groups of one pass.  One CTA per tile (persistent over tiles).
 // ------------------------------------------------------------------------------------------
-#define APPLY_PER_THREAD 16
-__global__ void __launch_bounds__(512) k_tile_apply(Shards src, Shards dst, TileGeom g, const DevGroup* __restrict__ groups, int n_groups,
-                                                    const DevTerm* __restrict__ terms, int accumulate) {
+#define APPLY_PER_THREAD 8   // 512 threads x 8 = one 2^12 tile
+// Collapsed group of an apply pass: (O psi)[l] gets psi[m] * (-1)^parity(m & lz_1) * F[m restricted to D] from the
+// source index m = l ^ lx, with F (complex, 2^nd entries, nd <= 4) tabulated by the host -- zero for the occupation
+// patterns the group does not couple, which are skipped.  The table index of element l = tid + j * blockDim splits
+// into a per-thread part and a per-j part (pjpack, 4 bits per j, the X-mask's own pattern folded in).
+struct DevAGroup {     // 48 bytes
+    uint64_t zout;
+    uint32_t lx, lz;
+    uint32_t nd;
+    uint32_t dpos[4];  // positions of D, ascending
+    uint32_t tab_begin;
+    uint64_t pjpack;
+};
+__global__ void __launch_bounds__(512, 2) k_tile_apply(Shards src, Shards dst, TileGeom g, const DevGroup* __restrict__ groups, int n_groups,
+                                                       const DevTerm* __restrict__ terms, const DevAGroup* __restrict__ agroups,
+                                                       const double2* __restrict__ atab, int n_atab, int accumulate) {
     extern __shared__ double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     double2* s_coef = tile + ts;
     uint32_t* s_lz = (uint32_t*)(s_coef + TERM_CAP);
+    double2* s_atab = (double2*)(s_lz + TERM_CAP);          // GROUP_CAP * 16
+    DevAGroup* s_agrp = (DevAGroup*)(s_atab + GROUP_CAP * 16);  // GROUP_CAP
+    for (int q = threadIdx.x; q < n_atab; q += blockDim.x) s_atab[q] = atab[q];
+    for (int q = threadIdx.x; q < n_groups; q += blockDim.x) s_agrp[q] = agroups[q];
+    const uint32_t tshift = 31 - __clz(blockDim.x);
     for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
         const uint64_t base = tile_base(g, t);
         const uint64_t sbase = base | g.sign_base;
@@ -1116,6 +1134,31 @@ __global__ void __launch_bounds__(512) k_tile_apply(Shards src, Shards dst, Tile
         double2 acc[APPLY_PER_THREAD];
 #pragma unroll
         for (int j = 0; j < APPLY_PER_THREAD; ++j) acc[j] = make_double2(0.0, 0.0);
+        __syncthreads();
+        // collapsed groups: table look-up per element, only coupled patterns do work
+        for (int q = 0; q < n_groups; ++q) {
+            const DevAGroup& ag = s_agrp[q];
+            if (ag.nd == 0xffffffffu) continue;  // not collapsed: term loop below
+            uint32_t pit = 0;
+            for (uint32_t d = 0; d < ag.nd; ++d) pit |= ((threadIdx.x >> ag.dpos[d]) & 1u) << d;
+            const uint32_t tsig = (uint32_t)__popcll(sbase & ag.zout);
+            const double2* tab = s_atab + ag.tab_begin;
+            const uint64_t pj = ag.pjpack;
+#pragma unroll
+            for (int j = 0; j < APPLY_PER_THREAD; ++j) {
+                const uint32_t l = threadIdx.x + ((uint32_t)j << tshift);
+                if (l < ts) {
+                    const double2 f = tab[pit ^ (uint32_t)((pj >> (4 * j)) & 15ull)];
+                    if (f.x != 0.0 || f.y != 0.0) {
+                        const uint32_t m = l ^ ag.lx;
+                        const uint32_t sg = tsig + (uint32_t)__popc(m & ag.lz);
+                        const double2 v = tile[m];
+                        acc[j].x += flipsign(f.x * v.x - f.y * v.y, sg);
+                        acc[j].y += flipsign(f.x * v.y + f.y * v.x, sg);
+                    }
+                }
+            }
+        }
         int gi = 0;
         while (gi < n_groups) {
             int ge = gi;
@@ -1136,6 +1179,7 @@ __global__ void __launch_bounds__(512) k_tile_apply(Shards src, Shards dst, Tile
             }
             __syncthreads();
             for (int q = gi; q < ge; ++q) {
+                if (s_agrp[q].nd != 0xffffffffu) continue;  // done above
                 const DevGroup gr = groups[q];
                 const uint32_t off = gr.t_begin - tb0;
                 const uint32_t nk = gr.n_even + gr.n_odd;
@@ -1184,7 +1228,10 @@ __global__ void __launch_bounds__(512) k_tile_apply(Shards src, Shards dst, Tile
 struct DevPoolOp {
     uint32_t t_begin, n_terms;  // terms of this operator (pass-local list)
     uint32_t out_index;         // pool index
-    uint32_t pad;
+    uint32_t col;               // 0, or 1 + index of the operator's collapsed form (DevGCol with lx in pad[0]):
+                                // all strings share one X-mask, their Z letters differ on <= 5 tile bits, so
+                                // A_k psi at source index m is psi[m] * (-1)^parity(m & lz_1) * F[m restricted to D]
+                                // and only the patterns with F != 0 are visited (2 of 16 for a JW double excitation)
 };
 struct DevPoolTerm {  // 32 bytes
     uint64_t zout;
@@ -1194,6 +1241,7 @@ struct DevPoolTerm {  // 32 bytes
 
 __global__ void __launch_bounds__(512) k_tile_pool(Shards bra, Shards ket, TileGeom g, const DevPoolOp* __restrict__ pops, int n_pops,
                                                    const DevPoolTerm* __restrict__ terms,
+                                                   const DevGCol* __restrict__ pcols, const DevGColEntry* __restrict__ pents,
                                                    double2* __restrict__ partial /* [gridDim.x][n_pops] */) {
     extern __shared__ double2 tile[];
     const uint32_t ts = 1u << g.tbits;
@@ -1217,6 +1265,32 @@ __global__ void __launch_bounds__(512) k_tile_pool(Shards bra, Shards ket, TileG
         for (int o = o0 + warp; o < o1; o += nwarps) {
             const DevPoolOp po = pops[o];
             double re = 0.0, im = 0.0;
+            if (po.col) {
+                const DevGCol co = pcols[po.col - 1];
+                const uint32_t lx = co.pad[0];
+                const uint32_t items = co.n_active << co.free_log;
+                const uint32_t fmask = (1u << co.free_log) - 1u;
+                const uint32_t tsig = (uint32_t)__popcll(sbase & co.zout);
+                for (uint32_t it = lane; it < items; it += 32) {
+                    const DevGColEntry en = pents[co.ent_begin + (it >> co.free_log)];
+                    uint32_t m = it & fmask;
+                    m += m & co.dpos[0];
+                    m += m & co.dpos[1];
+                    m += m & co.dpos[2];
+                    m += m & co.dpos[3];
+                    if (co.nd > 4) {
+                        m += m & co.dpos[4];
+                        m += m & co.dpos[5];
+                    }
+                    m |= en.pat;
+                    const double2 v = tket[m];
+                    const double2 b = tb[m ^ lx];
+                    const double pr = b.x * v.x + b.y * v.y, pi = b.x * v.y - b.y * v.x;  // conj(b) * v
+                    const uint32_t sg = tsig + (uint32_t)__popc(m & co.lz);
+                    re += flipsign(en.fr * pr - en.fi * pi, sg);
+                    im += flipsign(en.fr * pi + en.fi * pr, sg);
+                }
+            }
             for (uint32_t k = 0; k < po.n_terms; ++k) {
                 const DevPoolTerm tm = terms[po.t_begin + k];
                 const uint32_t opar = __popcll(sbase & tm.zout) & 1u;
@@ -1530,7 +1604,7 @@ static int create_ctx(vqe_ctx** out, int n_qubits, int n_global, int rank, int d
     c->low_bits = env_int("VQE_LOW_BITS", 5);
     c->threads = env_int("VQE_THREADS", 512);
     c->ctas_per_sm = env_int("VQE_CTAS_PER_SM", 2);
-    if (c->tile_bits < 6 || c->tile_bits > 13) c->tile_bits = 12;
+    if (c->tile_bits < 6 || c->tile_bits > 12) c->tile_bits = 12;
     if (c->threads < 64 || c->threads > 512 || (c->threads & (c->threads - 1))) c->threads = 512;
     if (c->low_bits < 0 || c->low_bits > c->tile_bits) c->low_bits = 5;
     int rc = VQE_OK;
@@ -2500,7 +2574,7 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
                                   int32_t* pass_n_ops, uint64_t* pass_tile_mask) {
     if (n_qubits < 1 || n_qubits > 40 || n_global < 0 || n_global > 6 || n_global >= n_qubits)
         return fail(VQE_ERR_INVALID, "bad qubit counts");
-    if (tile_bits < 6 || tile_bits > 13) tile_bits = 12;
+    if (tile_bits < 6 || tile_bits > 12) tile_bits = 12;
     if (low_bits < 0 || low_bits > tile_bits) low_bits = 5;
     if (!n_passes || n_rot < 0 || (n_rot > 0 && (!xmask || !zmask || !ny || !angle))) return fail(VQE_ERR_INVALID, "null array");
     std::vector<HostOp> ops;
@@ -2651,6 +2725,10 @@ struct PSPass {
     std::vector<DevGColEntry> gents;
     std::vector<DevFlat> flats;
     std::vector<uint64_t> fzout;        // distinct outside-tile Z masks of the flat entries
+    std::vector<DevAGroup> agroups;     // apply: one per group (nd = 0xffffffff: not collapsed)
+    std::vector<double2> atab;          // apply: coupling tables of the collapsed groups
+    DevAGroup* d_agroups = nullptr;
+    double2* d_atab = nullptr;
     DevFlat* d_flats = nullptr;
     uint64_t* d_fzout = nullptr;
     DevGCol* d_gcols = nullptr;
@@ -2935,6 +3013,66 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             p.gents.insert(p.gents.end(), ent.begin(), ent.end());
             dg.pad = (uint32_t)p.gcols.size();  // index + 1
         }
+        // apply (sigma = O psi): coupling tables of the groups whose Z-variants differ on <= 4 tile bits
+        {
+            const uint32_t ts_p = 1u << p.tp.tbits;
+            uint32_t thr = std::min<uint32_t>(512u, std::max<uint32_t>(32u, ts_p));
+            while (thr * APPLY_PER_THREAD < ts_p) thr *= 2;
+            const uint32_t tshift = 31 - __builtin_clz(thr);
+            for (size_t gi2 = 0; gi2 < p.groups.size(); ++gi2) {
+                const DevGroup& dg = p.groups[gi2];
+                const uint32_t nt = dg.n_even + dg.n_odd;
+                DevAGroup ag;
+                memset(&ag, 0, sizeof ag);
+                ag.nd = 0xffffffffu;
+                const DevTerm* ta = p.terms_apply.data() + dg.t_begin;
+                uint32_t D = 0;
+                bool same_out = nt > 0;
+                for (uint32_t q = 0; q < nt; ++q) {
+                    D |= ta[q].lz ^ ta[0].lz;
+                    same_out = same_out && ta[q].zout == ta[0].zout;
+                }
+                const int nd = __builtin_popcount(D);
+                if (same_out && nd <= 4 && p.atab.size() + (1u << nd) <= (size_t)GROUP_CAP * 16) {
+                    std::vector<uint32_t> dpos;
+                    for (int b2 = 0; b2 < p.tp.tbits; ++b2)
+                        if ((D >> b2) & 1u) dpos.push_back((uint32_t)b2);
+                    double scale = 0.0;
+                    for (uint32_t q = 0; q < nt; ++q) scale += fabs(ta[q].ar) + fabs(ta[q].ai);
+                    ag.zout = ta[0].zout;
+                    ag.lx = dg.lx;
+                    ag.lz = ta[0].lz;
+                    ag.nd = (uint32_t)nd;
+                    for (int b2 = 0; b2 < nd; ++b2) ag.dpos[b2] = dpos[b2];
+                    ag.tab_begin = (uint32_t)p.atab.size();
+                    auto pext_d = [&](uint32_t v) {
+                        uint32_t o = 0;
+                        for (int b2 = 0; b2 < nd; ++b2) o |= ((v >> dpos[b2]) & 1u) << b2;
+                        return o;
+                    };
+                    for (uint32_t pi = 0; pi < (1u << nd); ++pi) {
+                        uint32_t pat = 0;
+                        for (int b2 = 0; b2 < nd; ++b2)
+                            if ((pi >> b2) & 1u) pat |= 1u << dpos[b2];
+                        double fr = 0.0, fi = 0.0;
+                        for (uint32_t q = 0; q < nt; ++q) {
+                            const double sg = (__builtin_popcount(pat & (ta[q].lz ^ ta[0].lz)) & 1) ? -1.0 : 1.0;
+                            fr += sg * ta[q].ar;
+                            fi += sg * ta[q].ai;
+                        }
+                        if (fabs(fr) <= 1e-15 * scale) fr = 0.0;
+                        if (fabs(fi) <= 1e-15 * scale) fi = 0.0;
+                        p.atab.push_back(make_double2(fr, fi));
+                    }
+                    // table index of element l = tid | (j << tshift): pext_D(l ^ lx) = pext_D(tid) ^ pjpack[j]
+                    uint64_t pk = 0;
+                    for (uint32_t j = 0; j < 16; ++j)
+                        pk |= (uint64_t)((pext_d(j << tshift) ^ pext_d(dg.lx)) & 15u) << (4 * j);
+                    ag.pjpack = pk;
+                }
+                p.agroups.push_back(ag);
+            }
+        }
         ps->passes.push_back(std::move(p));
     }
     if (getenv("VQE_DEBUG_PLAN")) {
@@ -2960,6 +3098,10 @@ static void free_paulisum_device(vqe_paulisum* ps) {
         if (p.d_scat) cudaFree(p.d_scat);
         if (p.d_flats) cudaFree(p.d_flats);
         if (p.d_fzout) cudaFree(p.d_fzout);
+        if (p.d_agroups) cudaFree(p.d_agroups);
+        if (p.d_atab) cudaFree(p.d_atab);
+        p.d_agroups = nullptr;
+        p.d_atab = nullptr;
         p.d_flats = nullptr;
         p.d_fzout = nullptr;
         if (p.d_gcols) cudaFree(p.d_gcols);
@@ -2988,6 +3130,10 @@ static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
         CK(cudaMemcpy(p.d_gents, p.gents.data(), p.gents.size() * sizeof(DevGColEntry), cudaMemcpyHostToDevice));
         CK(cudaMalloc((void**)&p.d_flats, std::max<size_t>(1, p.flats.size()) * sizeof(DevFlat)));
         CK(cudaMemcpy(p.d_flats, p.flats.data(), p.flats.size() * sizeof(DevFlat), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&p.d_agroups, std::max<size_t>(1, p.agroups.size()) * sizeof(DevAGroup)));
+        CK(cudaMalloc((void**)&p.d_atab, std::max<size_t>(1, p.atab.size()) * sizeof(double2)));
+        CK(cudaMemcpy(p.d_agroups, p.agroups.data(), p.agroups.size() * sizeof(DevAGroup), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p.d_atab, p.atab.data(), p.atab.size() * sizeof(double2), cudaMemcpyHostToDevice));
         CK(cudaMalloc((void**)&p.d_fzout, std::max<size_t>(1, p.fzout.size()) * sizeof(uint64_t)));
         CK(cudaMemcpy(p.d_fzout, p.fzout.data(), p.fzout.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
     }
@@ -3214,13 +3360,15 @@ static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* 
             if (rc == VQE_OK) rc = make_geom(c, pp.tp, pp.d_scat, dst, g, sdst);
             if (rc) return rc;
             if (g.n_tiles == 0) continue;
-            size_t smem = tile_smem(pp.tp.tbits, 1, true);
+            size_t smem = (16ull << pp.tp.tbits) + TERM_CAP * (sizeof(double2) + 4) + GROUP_CAP * 16 * sizeof(double2) +
+                          GROUP_CAP * sizeof(DevAGroup);
             uint64_t ts = 1ull << pp.tp.tbits;
             int threads = (int)std::min<uint64_t>(512, std::max<uint64_t>(32, ts));
-            while ((uint64_t)threads * APPLY_PER_THREAD < ts) threads *= 2;  // ts <= 8192 = 512*16
+            while ((uint64_t)threads * APPLY_PER_THREAD < ts) threads *= 2;  // ts <= 4096 = 512*8
             ProfScope prof(c, 2);
             k_tile_apply<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(ssrc, sdst, g, pp.d_groups,
                                                                                (int)pp.groups.size(), pp.d_terms_apply,
+                                                                               pp.d_agroups, pp.d_atab, (int)pp.atab.size(),
                                                                                p == 0 ? 0 : 1);
             c->launches++;
             CK(cudaGetLastError());
@@ -3346,12 +3494,15 @@ static int pool_impl(RankSet& rs, int bra, int ket, int n_ops, const int32_t* op
         remaining -= members.size();
         std::vector<DevPoolOp> pops;
         std::vector<DevPoolTerm> pterms;
+        std::vector<DevGCol> pcols;
+        std::vector<DevGColEntry> pents;
         for (size_t q : members) {
             const int o = subs[q].op;
             DevPoolOp po;
             po.t_begin = (uint32_t)pterms.size();
             po.out_index = (uint32_t)o;
-            po.pad = 0;
+            po.col = 0;
+            const size_t terms_mark = pterms.size();
             for (int k = op_offsets[o]; k < op_offsets[o + 1]; ++k) {
                 double cr = cre[k], ci = cim ? cim[k] : 0.0;
                 if ((cr == 0.0 && ci == 0.0) || (x[k] >> nl) != pat) continue;
@@ -3365,11 +3516,65 @@ static int pool_impl(RankSet& rs, int bra, int ket, int n_ops, const int32_t* op
                 pterms.push_back(t);
             }
             po.n_terms = (uint32_t)pterms.size() - po.t_begin;
+            // collapsed form (see DevPoolOp::col)
+            if (po.n_terms >= 2) {
+                const DevPoolTerm* te = pterms.data() + terms_mark;
+                uint32_t D = 0;
+                bool same = true;
+                for (uint32_t k2 = 0; k2 < po.n_terms; ++k2) {
+                    same = same && te[k2].lx == te[0].lx && te[k2].zout == te[0].zout;
+                    D |= te[k2].lz ^ te[0].lz;
+                }
+                const int ne = __builtin_popcount(D);
+                if (same && ne <= 5) {
+                    std::vector<uint32_t> epos;
+                    for (int b2 = 0; b2 < tp.tbits; ++b2)
+                        if ((D >> b2) & 1u) epos.push_back((uint32_t)b2);
+                    double scale = 0.0;
+                    for (uint32_t k2 = 0; k2 < po.n_terms; ++k2) scale += fabs(te[k2].ar) + fabs(te[k2].ai);
+                    DevGCol co;
+                    memset(&co, 0, sizeof co);
+                    co.zout = te[0].zout;
+                    co.lz = te[0].lz;
+                    co.pad[0] = te[0].lx;
+                    co.nd = (uint32_t)ne;
+                    for (int b2 = 0; b2 < ne; ++b2) co.dpos[b2] = ~((1u << epos[b2]) - 1u);
+                    co.ent_begin = (uint32_t)pents.size();
+                    co.free_log = (uint32_t)(tp.tbits - ne);
+                    for (uint32_t pi = 0; pi < (1u << ne); ++pi) {
+                        uint32_t pat2 = 0;
+                        for (int b2 = 0; b2 < ne; ++b2)
+                            if ((pi >> b2) & 1u) pat2 |= 1u << epos[b2];
+                        double fr = 0.0, fi = 0.0;
+                        for (uint32_t k2 = 0; k2 < po.n_terms; ++k2) {
+                            const double sg = (__builtin_popcount(pat2 & (te[k2].lz ^ te[0].lz)) & 1) ? -1.0 : 1.0;
+                            fr += sg * te[k2].ar;
+                            fi += sg * te[k2].ai;
+                        }
+                        if (fabs(fr) <= 1e-15 * scale) fr = 0.0;
+                        if (fabs(fi) <= 1e-15 * scale) fi = 0.0;
+                        if (fr == 0.0 && fi == 0.0) continue;
+                        DevGColEntry en;
+                        memset(&en, 0, sizeof en);
+                        en.fr = fr;
+                        en.fi = fi;
+                        en.pat = pat2;
+                        pents.push_back(en);
+                    }
+                    co.n_active = (uint32_t)pents.size() - co.ent_begin;
+                    pcols.push_back(co);
+                    po.col = (uint32_t)pcols.size();
+                    pterms.resize(terms_mark);  // the strings are folded into the table
+                    po.n_terms = 0;
+                }
+            }
             pops.push_back(po);
         }
         const int np = (int)pops.size();
         size_t off_ops = 0, off_terms = (np * sizeof(DevPoolOp) + 15) & ~size_t(15);
-        size_t off_scat = (off_terms + pterms.size() * sizeof(DevPoolTerm) + 15) & ~size_t(15);
+        size_t off_pcols = (off_terms + pterms.size() * sizeof(DevPoolTerm) + 15) & ~size_t(15);
+        size_t off_pents = off_pcols + pcols.size() * sizeof(DevGCol);
+        size_t off_scat = (off_pents + pents.size() * sizeof(DevGColEntry) + 15) & ~size_t(15);
         size_t total = off_scat + tp.scat.size() * sizeof(uint64_t);
         if (tp.vbit) {
             rc = rank_barrier(rs);
@@ -3396,6 +3601,8 @@ static int pool_impl(RankSet& rs, int bra, int ket, int n_ops, const int32_t* op
             CK(cudaStreamSynchronize(c->stream));
             memcpy(c->h_stage + off_ops, pops.data(), np * sizeof(DevPoolOp));
             memcpy(c->h_stage + off_terms, pterms.data(), pterms.size() * sizeof(DevPoolTerm));
+            if (!pcols.empty()) memcpy(c->h_stage + off_pcols, pcols.data(), pcols.size() * sizeof(DevGCol));
+            if (!pents.empty()) memcpy(c->h_stage + off_pents, pents.data(), pents.size() * sizeof(DevGColEntry));
             memcpy(c->h_stage + off_scat, tp.scat.data(), tp.scat.size() * sizeof(uint64_t));
             c->h2d_bytes += total;
             CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
@@ -3406,7 +3613,8 @@ static int pool_impl(RankSet& rs, int bra, int ket, int n_ops, const int32_t* op
                 ProfScope prof(c, 3);
                 k_tile_pool<<<dim3(gx, gy, 1), threads, smem, c->stream>>>(
                     sbra, sket, g, (const DevPoolOp*)(c->d_stage + off_ops), np,
-                    (const DevPoolTerm*)(c->d_stage + off_terms), c->d_partial);
+                    (const DevPoolTerm*)(c->d_stage + off_terms), (const DevGCol*)(c->d_stage + off_pcols),
+                    (const DevGColEntry*)(c->d_stage + off_pents), c->d_partial);
                 c->launches++;
             }
             k_reduce_partials<<<np, 64, 0, c->stream>>>(c->d_partial, gx, np, np, c->d_result);
