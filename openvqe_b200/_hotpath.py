@@ -85,7 +85,7 @@ def prepare_ucc_state(engine, cluster_ops_sp, hf_init_sp, theta):
     engine.apply_rotations(prog.x, prog.z, prog.ny, angles)
 
 
-def ucc_energy(theta, hamiltonian_sp, cluster_ops_sp, hf_init_sp, device=0):
+def ucc_energy(theta, hamiltonian_sp, cluster_ops_sp, hf_init_sp, device=None):
     """E(theta) of the Trotterised UCC ansatz (reference get_energy_ucc.py:8-50)."""
     engine = get_engine(hamiltonian_sp.nbqbits, device)
     prepare_ucc_state(engine, cluster_ops_sp, hf_init_sp, theta)
@@ -125,7 +125,7 @@ def prepare_quccsd_state(engine, n, hf_init_sp, cluster_ops, theta, use_tables=T
         engine.scale_state(phase)
 
 
-def quccsd_energy(theta, hamiltonian_sp, cluster_ops, hf_init_sp, device=0):
+def quccsd_energy(theta, hamiltonian_sp, cluster_ops, hf_init_sp, device=None):
     """E(theta) of the gate-defined QUCCSD ansatz (reference get_energy_qucc.py:11-56)."""
     n = hamiltonian_sp.nbqbits
     engine = get_engine(n, device)
@@ -133,7 +133,7 @@ def quccsd_energy(theta, hamiltonian_sp, cluster_ops, hf_init_sp, device=0):
     return float(engine.expectation(engine.paulisum(hamiltonian_sp)).real)
 
 
-def basis_energy(hamiltonian_sp, hf_init_sp, device=0):
+def basis_energy(hamiltonian_sp, hf_init_sp, device=None):
     """<HF|H|HF> (reference hf_energy, fermionic_adapt_vqe.py:216-238)."""
     engine = get_engine(hamiltonian_sp.nbqbits, device)
     engine.set_basis_state(int(hf_init_sp))
@@ -207,3 +207,66 @@ def snap_ties(values, rel=1e-12, zero_tol=ZERO_TOL):
                 vals[k] = mag if vals[k] >= 0 else -mag
         i = j
     return vals
+
+
+FD_STEP = 1.4901161193847656e-08  # scipy's absolute 2-point step for BFGS with jac=None (sqrt of machine epsilon)
+
+
+def replica_world():
+    """(rank, world) of the SPMD replica group, or (0, 1) outside torchrun / when switched off."""
+    import os
+    import sys
+    if os.environ.get("VQE_B200_REPLICA_FD", "1") == "0" or "torch.distributed" not in sys.modules:
+        return 0, 1
+    from . import sharded
+    if not sharded.dist_ready():
+        return 0, 1
+    dist = sharded._dist()
+    return dist.get_rank(), dist.get_world_size()
+
+
+def distributed_fd(action, energies):
+    """Finite-difference gradient of a BFGS run spread over the SPMD ranks.
+
+    ``action(theta)`` is the energy WITHOUT the bookkeeping append.  Returns ``(fun, jac)`` for
+    ``scipy.optimize.minimize``: ``fun`` appends to ``energies`` like the reference's objective; ``jac`` is scipy's own
+    2-point forward difference -- same absolute step, same (x + h) - x denominator, evaluation order f(x),
+    f(x + h e_0), f(x + h e_1), ... -- but every rank evaluates only its slice of the n displaced points on its own
+    GPU and the values are all-gathered, so the gradient, the optimiser trajectory and the ``energies`` list are the
+    ones of the serial run.  Outside a replica group ``jac`` is None and scipy differences serially."""
+    rank, world = replica_world()
+    last = {}
+
+    def fun(theta):
+        x = np.array(theta, dtype=np.float64)
+        v = action(x)
+        energies.append(v)
+        last["x"], last["f"] = x, v
+        return v
+
+    if world == 1:
+        return fun, None
+    from . import sharded
+
+    def jac(theta):
+        x0 = np.array(theta, dtype=np.float64)
+        if "x" in last and np.array_equal(last["x"], x0):
+            f0 = last["f"]
+        else:
+            f0 = action(x0)
+        n = x0.shape[0]
+        lo, hi = sharded.split_range(n, world, rank)
+        width = max(sharded.split_range(n, world, r)[1] - sharded.split_range(n, world, r)[0] for r in range(world))
+        mine = np.zeros(width, dtype=np.float64)
+        for i in range(lo, hi):
+            xi = x0.copy()
+            xi[i] = x0[i] + FD_STEP
+            mine[i - lo] = action(xi)
+        rows = sharded.allgather_f64(mine)
+        vals = np.concatenate([rows[r, :sharded.split_range(n, world, r)[1] - sharded.split_range(n, world, r)[0]]
+                               for r in range(world)])
+        energies.extend(float(v) for v in vals)
+        dx = (x0 + FD_STEP) - x0
+        return (vals - f0) / dx
+
+    return fun, jac

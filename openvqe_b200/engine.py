@@ -204,10 +204,22 @@ _ENGINES = {}
 _ENGINE_FACTORY = None  # set by openvqe_b200.sharded.enable(): (n_qubits, device) -> Engine or None
 
 
-def get_engine(n_qubits: int, device: int = 0) -> Engine:
+def default_device() -> int:
+    """Device of this process: VQE_B200_DEVICE, else LOCAL_RANK (one process per GPU under torchrun), else 0."""
+    import os
+    v = os.environ.get("VQE_B200_DEVICE", os.environ.get("LOCAL_RANK", "0"))
+    try:
+        dev = int(v)
+    except ValueError:
+        dev = 0
+    n = _lib.load().vqe_device_count()
+    return dev % n if n > 0 else dev
+
+
+def get_engine(n_qubits: int, device=None) -> Engine:
     """Process-wide engine per (n_qubits, device): the state buffers are reused
     across the thousands of objective evaluations of one optimisation."""
-    key = (int(n_qubits), int(device))
+    key = (int(n_qubits), default_device() if device is None else int(device))
     eng = _ENGINES.get(key)
     if eng is None:
         if _ENGINE_FACTORY is not None:

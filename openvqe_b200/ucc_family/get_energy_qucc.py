@@ -44,12 +44,16 @@ class EnergyUCC:
         print("tolerance= ", tolerance)
         print("method= ", method)
         energies1, energies2 = [], []
+        # under torchrun the finite-difference evaluations of every BFGS gradient are spread over the ranks
+        # (identical trajectory and energies list, see _hotpath.distributed_fd); serially jac is None as in the reference
+        fun1, jac1 = _hotpath.distributed_fd(
+            lambda theta: _hotpath.quccsd_energy(theta, hamiltonian_sp, cluster_ops, hf_init_sp), energies1)
+        fun2, jac2 = _hotpath.distributed_fd(
+            lambda theta: _hotpath.quccsd_energy(theta, hamiltonian_sp, cluster_ops, hf_init_sp), energies2)
         opt_result1 = scipy.optimize.minimize(
-            lambda theta: self.action_quccsd(theta, hamiltonian_sp, cluster_ops, hf_init_sp, energies1),
-            x0=theta_current1, method=method, tol=tolerance, options={"maxiter": 50000, "disp": True})
+            fun1, x0=theta_current1, jac=jac1, method=method, tol=tolerance, options={"maxiter": 50000, "disp": True})
         opt_result2 = scipy.optimize.minimize(
-            lambda theta: self.action_quccsd(theta, hamiltonian_sp, cluster_ops, hf_init_sp, energies2),
-            x0=theta_current2, method=method, tol=tolerance, options={"maxiter": 50000, "disp": True})
+            fun2, x0=theta_current2, jac=jac2, method=method, tol=tolerance, options={"maxiter": 50000, "disp": True})
         theta_optimized_result1 = [opt_result1.x[k] for k in range(len(theta_current1))]
         theta_optimized_result2 = [opt_result2.x[k] for k in range(len(theta_current2))]
         circ1 = self.prepare_state_ansatz(hamiltonian_sp, hf_init_sp, cluster_ops, theta_optimized_result1)

@@ -60,6 +60,26 @@ def main():
     assert _hotpath.replica_split_active(eng)
     os.environ["VQE_B200_REPLICA_POOL"] = "0"
     assert not _hotpath.replica_split_active(eng)
+    # finite-difference gradients of a BFGS run spread over the ranks: same trajectory, same energies list
+    import scipy.optimize
+    os.environ.pop("VQE_B200_REPLICA_POOL", None)
+    w = np.linspace(0.5, 1.5, 7)
+
+    def action(x):
+        return float(np.sum(w * np.cos(x - 0.3 * w)) + 0.05 * np.sum(x ** 4))
+
+    x0 = np.linspace(-0.4, 0.6, 7)
+    e_par, e_ser = [], []
+    fun, jac = _hotpath.distributed_fd(action, e_par)
+    assert jac is not None
+    r_par = scipy.optimize.minimize(fun, x0=x0, jac=jac, method="BFGS", tol=1e-6)
+    os.environ["VQE_B200_REPLICA_FD"] = "0"
+    fun_s, jac_s = _hotpath.distributed_fd(action, e_ser)
+    assert jac_s is None
+    r_ser = scipy.optimize.minimize(fun_s, x0=x0, jac=None, method="BFGS", tol=1e-6)
+    os.environ.pop("VQE_B200_REPLICA_FD")
+    assert np.array_equal(r_par.x, r_ser.x) and r_par.fun == r_ser.fun and r_par.nit == r_ser.nit
+    assert e_par == e_ser and len(e_par) > 20
     dist.barrier()
     if rank == 0:
         print("gloo worker ok", flush=True)
