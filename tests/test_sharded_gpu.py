@@ -243,3 +243,14 @@ def test_c5_synthetic_sharded_equals_unsharded_at_22_qubits(gpu_required):
         del e
     assert abs(out[0][0] - out[1][0]) < 1e-10
     assert abs(out[0][1] - 1.0) < 1e-12 and abs(out[1][1] - 1.0) < 1e-12
+
+
+def test_replica_mode_two_ranks(gpu_required):
+    """n <= 33: SPMD replicas under torchrun -- the BFGS finite-difference evaluations and the ADAPT pool sweep are
+    split over the ranks and must reproduce the single-process run bit for bit (energies list, optimum, gradients)."""
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(ROOT, "tests", "replica_worker.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "replica worker ok" in res.stdout
