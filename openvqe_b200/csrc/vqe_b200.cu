@@ -1101,122 +1101,116 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
 // ------------------------------------------------------------------------------------------
 // dst (+)= O src for the groups of one pass.  One CTA per tile (persistent over tiles).
 // ------------------------------------------------------------------------------------------
-#define APPLY_PER_THREAD 8   // 512 threads x 8 = one 2^12 tile
-// Collapsed group of an apply pass: (O psi)[l] gets psi[m] * (-1)^parity(m & lz_1) * F[m restricted to D] from the
-// source index m = l ^ lx, with F (complex, 2^nd entries, nd <= 4) tabulated by the host -- zero for the occupation
-// patterns the group does not couple, which are skipped.  The table index of element l = tid + j * blockDim splits
-// into a per-thread part and a per-j part (pjpack, 4 bits per j, the X-mask's own pattern folded in).
-struct DevAGroup {     // 48 bytes
-    uint64_t zout;
-    uint32_t lx, lz;
-    uint32_t nd;
-    uint32_t dpos[4];  // positions of D, ascending
-    uint32_t tab_begin;
-    uint64_t pjpack;
+// sigma (+)= O psi for the groups of one pass.  One CTA of up to 1024 threads per SM holds the source tile AND an
+// accumulator tile in shared memory and walks the groups one after the other (a barrier between two groups: inside a
+// group every destination element is written by exactly one thread, so the accumulation is conflict free and its
+// order is fixed -> bit-reproducible).
+//   Collapsed groups (Z-variants differ on <= 4 tile bits): the host tabulates the complex coupling F per source
+//   occupation pattern and lists only the patterns with F != 0, cut into entries of 256 (pattern, free index) pairs:
+//       acc[m ^ lx] += (-1)^parity(m & lz_1) * F * psi[m]           one visit per COUPLED source amplitude.
+//   Other groups (diagonal group, groups dressed with many number operators): one thread per destination element,
+//   loop over the group's terms with popcount signs.
+struct DevAFlat {      // 48 bytes
+    double fr, fi;     // coupling of this source pattern (c_k i^ny summed over the group's strings, relative signs in)
+    uint32_t lx, lz;   // X-mask, Z letters of the group's first term inside the tile
+    uint32_t pat;      // source pattern bits | free-index bits above the low 8 (already deposited)
+    uint32_t zsel;     // index into the pass's table of outside-tile Z masks
+    uint16_t himask[4];
+    uint32_t pad[2];
 };
-__global__ void __launch_bounds__(512, 2) k_tile_apply(Shards src, Shards dst, TileGeom g, const DevGroup* __restrict__ groups, int n_groups,
-                                                       const DevTerm* __restrict__ terms, const DevAGroup* __restrict__ agroups,
-                                                       const double2* __restrict__ atab, int n_atab, int accumulate) {
+#define AFLAT_CAP 1024
+__global__ void __launch_bounds__(1024, 1) k_tile_apply(Shards src, Shards dst, TileGeom g, const DevGroup* __restrict__ groups,
+                                                        int n_groups, const DevTerm* __restrict__ terms,
+                                                        const DevAFlat* __restrict__ aflat, const uint32_t* __restrict__ aoff,
+                                                        const uint64_t* __restrict__ azout, int accumulate) {
     extern __shared__ double2 tile[];
     const uint32_t ts = 1u << g.tbits;
-    double2* s_coef = tile + ts;
-    uint32_t* s_lz = (uint32_t*)(s_coef + TERM_CAP);
-    double2* s_atab = (double2*)(s_lz + TERM_CAP);          // GROUP_CAP * 16
-    DevAGroup* s_agrp = (DevAGroup*)(s_atab + GROUP_CAP * 16);  // GROUP_CAP
-    for (int q = threadIdx.x; q < n_atab; q += blockDim.x) s_atab[q] = atab[q];
-    for (int q = threadIdx.x; q < n_groups; q += blockDim.x) s_agrp[q] = agroups[q];
-    const uint32_t tshift = 31 - __clz(blockDim.x);
+    double2* acc = tile + ts;
+    double2* s_coef = acc + ts;                                  // TERM_CAP
+    uint32_t* s_lz = (uint32_t*)(s_coef + TERM_CAP);             // TERM_CAP
+    DevAFlat* s_fl = (DevAFlat*)(s_lz + TERM_CAP);               // AFLAT_CAP
+    double2* s_ff = (double2*)(s_fl + AFLAT_CAP);                // AFLAT_CAP: per tile, F with the outside parity folded in
+    uint32_t* s_off = (uint32_t*)(s_ff + AFLAT_CAP);             // GROUP_CAP + 1
+    const uint32_t bd = blockDim.x;
+    const uint32_t n_fl = aoff[n_groups];
+    for (uint32_t q = threadIdx.x; q < n_fl; q += bd) s_fl[q] = aflat[q];
+    for (uint32_t q = threadIdx.x; q <= (uint32_t)n_groups; q += bd) s_off[q] = aoff[q];
     for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
         const uint64_t base = tile_base(g, t);
         const uint64_t sbase = base | g.sign_base;
-        __syncthreads();
-        tile_load(tile, src, g, base);
-        double2 acc[APPLY_PER_THREAD];
-#pragma unroll
-        for (int j = 0; j < APPLY_PER_THREAD; ++j) acc[j] = make_double2(0.0, 0.0);
-        __syncthreads();
-        // collapsed groups: table look-up per element, only coupled patterns do work
-        for (int q = 0; q < n_groups; ++q) {
-            const DevAGroup& ag = s_agrp[q];
-            if (ag.nd == 0xffffffffu) continue;  // not collapsed: term loop below
-            uint32_t pit = 0;
-            for (uint32_t d = 0; d < ag.nd; ++d) pit |= ((threadIdx.x >> ag.dpos[d]) & 1u) << d;
-            const uint32_t tsig = (uint32_t)__popcll(sbase & ag.zout);
-            const double2* tab = s_atab + ag.tab_begin;
-            const uint64_t pj = ag.pjpack;
-#pragma unroll
-            for (int j = 0; j < APPLY_PER_THREAD; ++j) {
-                const uint32_t l = threadIdx.x + ((uint32_t)j << tshift);
-                if (l < ts) {
-                    const double2 f = tab[pit ^ (uint32_t)((pj >> (4 * j)) & 15ull)];
-                    if (f.x != 0.0 || f.y != 0.0) {
-                        const uint32_t m = l ^ ag.lx;
-                        const uint32_t sg = tsig + (uint32_t)__popc(m & ag.lz);
-                        const double2 v = tile[m];
-                        acc[j].x += flipsign(f.x * v.x - f.y * v.y, sg);
-                        acc[j].y += flipsign(f.x * v.y + f.y * v.x, sg);
-                    }
-                }
-            }
+        __syncthreads();  // previous tile stored (and, first time, the tables are in place)
+        tile_load_async(tile, src, g, base);
+        for (uint32_t k = threadIdx.x; k < ts; k += bd) acc[k] = make_double2(0.0, 0.0);
+        for (uint32_t q = threadIdx.x; q < n_fl; q += bd) {
+            const uint32_t par = __popcll(sbase & azout[s_fl[q].zsel]);
+            s_ff[q] = make_double2(flipsign(s_fl[q].fr, par), flipsign(s_fl[q].fi, par));
         }
-        int gi = 0;
-        while (gi < n_groups) {
-            int ge = gi;
-            uint32_t nt = 0;
-            const uint32_t tb0 = groups[gi].t_begin;
-            while (ge < n_groups) {
-                uint32_t k = groups[ge].n_even + groups[ge].n_odd;
-                if (nt + k > TERM_CAP && ge > gi) break;
-                nt += k;
-                ++ge;
-            }
-            __syncthreads();
-            for (uint32_t k = threadIdx.x; k < nt && k < TERM_CAP; k += blockDim.x) {
-                const DevTerm tm = terms[tb0 + k];
-                uint32_t par = __popcll(sbase & tm.zout) & 1u;
-                s_coef[k] = make_double2(flipsign(tm.ar, par), flipsign(tm.ai, par));
-                s_lz[k] = tm.lz;
-            }
-            __syncthreads();
-            for (int q = gi; q < ge; ++q) {
-                if (s_agrp[q].nd != 0xffffffffu) continue;  // done above
+        cp_async_wait_all();
+        __syncthreads();
+        for (int q = 0; q < n_groups; ++q) {
+            const uint32_t e0 = s_off[q], e1 = s_off[q + 1];
+            if (e1 > e0) {
+                const uint32_t items = (e1 - e0) << 8;
+                for (uint32_t it = threadIdx.x; it < items; it += bd) {
+                    const uint32_t ei = e0 + (it >> 8);
+                    const DevAFlat& fe = s_fl[ei];
+                    const uint2 hm = *reinterpret_cast<const uint2*>(fe.himask);
+                    uint32_t m = it & 255u;
+                    m += m & (hm.x & 0xffffu);
+                    m += m & (hm.x >> 16);
+                    m += m & (hm.y & 0xffffu);
+                    m += m & (hm.y >> 16);
+                    m |= fe.pat;
+                    const double2 f = s_ff[ei];
+                    const double2 v = tile[m];
+                    const uint32_t sg = (uint32_t)__popc(m & fe.lz);
+                    double2* a = acc + (m ^ fe.lx);
+                    double2 o = *a;
+                    o.x += flipsign(f.x * v.x - f.y * v.y, sg);
+                    o.y += flipsign(f.x * v.y + f.y * v.x, sg);
+                    *a = o;
+                }
+            } else {
                 const DevGroup gr = groups[q];
-                const uint32_t off = gr.t_begin - tb0;
                 const uint32_t nk = gr.n_even + gr.n_odd;
-                if (off + nk > TERM_CAP) continue;
-#pragma unroll
-                for (int j = 0; j < APPLY_PER_THREAD; ++j) {
-                    const uint32_t l = threadIdx.x + j * blockDim.x;
-                    if (l < ts) {
+                for (uint32_t k0 = 0; k0 < nk; k0 += TERM_CAP) {  // (groups are split at TERM_CAP terms by the host)
+                    const uint32_t nn = min(nk - k0, (uint32_t)TERM_CAP);
+                    __syncthreads();
+                    for (uint32_t k = threadIdx.x; k < nn; k += bd) {
+                        const DevTerm tm = terms[gr.t_begin + k0 + k];
+                        const uint32_t par = __popcll(sbase & tm.zout) & 1u;
+                        s_coef[k] = make_double2(flipsign(tm.ar, par), flipsign(tm.ai, par));
+                        s_lz[k] = tm.lz;
+                    }
+                    __syncthreads();
+                    for (uint32_t l = threadIdx.x; l < ts; l += bd) {
                         const uint32_t sidx = l ^ gr.lx;
                         double sr = 0.0, si = 0.0;
-                        for (uint32_t k = 0; k < nk; ++k) {
-                            uint32_t par = __popc(sidx & s_lz[off + k]);
-                            const double2 c = s_coef[off + k];
+                        for (uint32_t k = 0; k < nn; ++k) {
+                            const uint32_t par = __popc(sidx & s_lz[k]);
+                            const double2 c = s_coef[k];
                             sr += flipsign(c.x, par);
                             si += flipsign(c.y, par);
                         }
                         const double2 v = tile[sidx];
-                        acc[j].x += sr * v.x - si * v.y;
-                        acc[j].y += sr * v.y + si * v.x;
+                        double2 o = acc[l];
+                        o.x += sr * v.x - si * v.y;
+                        o.y += sr * v.y + si * v.x;
+                        acc[l] = o;
                     }
                 }
             }
-            gi = ge;
+            __syncthreads();
         }
-#pragma unroll
-        for (int j = 0; j < APPLY_PER_THREAD; ++j) {
-            const uint32_t l = threadIdx.x + j * blockDim.x;
-            if (l < ts) {
-                double2* dp = amp_addr(g, dst, base, l);
-                double2 o = acc[j];
-                if (accumulate) {
-                    double2 d = *dp;
-                    o.x += d.x;
-                    o.y += d.y;
-                }
-                *dp = o;
+        for (uint32_t k = threadIdx.x; k < ts; k += bd) {
+            double2* dp = amp_addr(g, dst, base, k);
+            double2 o = acc[k];
+            if (accumulate) {
+                const double2 d = *dp;
+                o.x += d.x;
+                o.y += d.y;
             }
+            *dp = o;
         }
     }
 }
@@ -2725,10 +2719,12 @@ struct PSPass {
     std::vector<DevGColEntry> gents;
     std::vector<DevFlat> flats;
     std::vector<uint64_t> fzout;        // distinct outside-tile Z masks of the flat entries
-    std::vector<DevAGroup> agroups;     // apply: one per group (nd = 0xffffffff: not collapsed)
-    std::vector<double2> atab;          // apply: coupling tables of the collapsed groups
-    DevAGroup* d_agroups = nullptr;
-    double2* d_atab = nullptr;
+    std::vector<DevAFlat> aflat;        // apply: flat entries of the collapsed groups, group after group
+    std::vector<uint32_t> aoff;         // apply: groups.size() + 1 offsets into aflat (empty range: term loop)
+    std::vector<uint64_t> azout;        // apply: distinct outside-tile Z masks
+    DevAFlat* d_aflat = nullptr;
+    uint32_t* d_aoff = nullptr;
+    uint64_t* d_azout = nullptr;
     DevFlat* d_flats = nullptr;
     uint64_t* d_fzout = nullptr;
     DevGCol* d_gcols = nullptr;
@@ -3013,18 +3009,12 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             p.gents.insert(p.gents.end(), ent.begin(), ent.end());
             dg.pad = (uint32_t)p.gcols.size();  // index + 1
         }
-        // apply (sigma = O psi): coupling tables of the groups whose Z-variants differ on <= 4 tile bits
+        // apply (sigma = O psi): flat entries of the groups whose Z-variants differ on <= 4 tile bits
         {
-            const uint32_t ts_p = 1u << p.tp.tbits;
-            uint32_t thr = std::min<uint32_t>(512u, std::max<uint32_t>(32u, ts_p));
-            while (thr * APPLY_PER_THREAD < ts_p) thr *= 2;
-            const uint32_t tshift = 31 - __builtin_clz(thr);
+            p.aoff.push_back(0);
             for (size_t gi2 = 0; gi2 < p.groups.size(); ++gi2) {
                 const DevGroup& dg = p.groups[gi2];
                 const uint32_t nt = dg.n_even + dg.n_odd;
-                DevAGroup ag;
-                memset(&ag, 0, sizeof ag);
-                ag.nd = 0xffffffffu;
                 const DevTerm* ta = p.terms_apply.data() + dg.t_begin;
                 uint32_t D = 0;
                 bool same_out = nt > 0;
@@ -3033,23 +3023,16 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
                     same_out = same_out && ta[q].zout == ta[0].zout;
                 }
                 const int nd = __builtin_popcount(D);
-                if (same_out && nd <= 4 && p.atab.size() + (1u << nd) <= (size_t)GROUP_CAP * 16) {
+                const int free_log = p.tp.tbits - nd;
+                if (same_out && nd <= 4 && free_log >= 8) {
                     std::vector<uint32_t> dpos;
                     for (int b2 = 0; b2 < p.tp.tbits; ++b2)
                         if ((D >> b2) & 1u) dpos.push_back((uint32_t)b2);
                     double scale = 0.0;
                     for (uint32_t q = 0; q < nt; ++q) scale += fabs(ta[q].ar) + fabs(ta[q].ai);
-                    ag.zout = ta[0].zout;
-                    ag.lx = dg.lx;
-                    ag.lz = ta[0].lz;
-                    ag.nd = (uint32_t)nd;
-                    for (int b2 = 0; b2 < nd; ++b2) ag.dpos[b2] = dpos[b2];
-                    ag.tab_begin = (uint32_t)p.atab.size();
-                    auto pext_d = [&](uint32_t v) {
-                        uint32_t o = 0;
-                        for (int b2 = 0; b2 < nd; ++b2) o |= ((v >> dpos[b2]) & 1u) << b2;
-                        return o;
-                    };
+                    std::vector<DevAFlat> ent;
+                    uint32_t zsel = 0;
+                    while (zsel < p.azout.size() && p.azout[zsel] != ta[0].zout) ++zsel;
                     for (uint32_t pi = 0; pi < (1u << nd); ++pi) {
                         uint32_t pat = 0;
                         for (int b2 = 0; b2 < nd; ++b2)
@@ -3062,15 +3045,38 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
                         }
                         if (fabs(fr) <= 1e-15 * scale) fr = 0.0;
                         if (fabs(fi) <= 1e-15 * scale) fi = 0.0;
-                        p.atab.push_back(make_double2(fr, fi));
+                        if (fr == 0.0 && fi == 0.0) continue;
+                        for (uint32_t hi = 0; hi < (1u << (free_log - 8)); ++hi) {
+                            DevAFlat fl;
+                            memset(&fl, 0, sizeof fl);
+                            fl.fr = fr;
+                            fl.fi = fi;
+                            fl.lx = dg.lx;
+                            fl.lz = ta[0].lz;
+                            fl.zsel = zsel;
+                            uint32_t fhi = hi << 8;
+                            for (int b2 = 0; b2 < nd; ++b2) {
+                                fl.himask[b2] = (uint16_t)(~((1u << dpos[b2]) - 1u) & 0xffffu);
+                                fhi += fhi & ~((1u << dpos[b2]) - 1u);
+                            }
+                            fl.pat = pat | fhi;
+                            ent.push_back(fl);
+                        }
                     }
-                    // table index of element l = tid | (j << tshift): pext_D(l ^ lx) = pext_D(tid) ^ pjpack[j]
-                    uint64_t pk = 0;
-                    for (uint32_t j = 0; j < 16; ++j)
-                        pk |= (uint64_t)((pext_d(j << tshift) ^ pext_d(dg.lx)) & 15u) << (4 * j);
-                    ag.pjpack = pk;
+                    // an all-zero group contributes nothing; keep one zero entry so that it is not sent to the term loop
+                    if (ent.empty()) {
+                        DevAFlat fl;
+                        memset(&fl, 0, sizeof fl);
+                        fl.lx = dg.lx;
+                        fl.zsel = zsel;
+                        ent.push_back(fl);
+                    }
+                    if (p.aflat.size() + ent.size() <= AFLAT_CAP) {
+                        if (zsel == p.azout.size()) p.azout.push_back(ta[0].zout);
+                        p.aflat.insert(p.aflat.end(), ent.begin(), ent.end());
+                    }
                 }
-                p.agroups.push_back(ag);
+                p.aoff.push_back((uint32_t)p.aflat.size());
             }
         }
         ps->passes.push_back(std::move(p));
@@ -3098,10 +3104,12 @@ static void free_paulisum_device(vqe_paulisum* ps) {
         if (p.d_scat) cudaFree(p.d_scat);
         if (p.d_flats) cudaFree(p.d_flats);
         if (p.d_fzout) cudaFree(p.d_fzout);
-        if (p.d_agroups) cudaFree(p.d_agroups);
-        if (p.d_atab) cudaFree(p.d_atab);
-        p.d_agroups = nullptr;
-        p.d_atab = nullptr;
+        if (p.d_aflat) cudaFree(p.d_aflat);
+        if (p.d_aoff) cudaFree(p.d_aoff);
+        if (p.d_azout) cudaFree(p.d_azout);
+        p.d_aflat = nullptr;
+        p.d_aoff = nullptr;
+        p.d_azout = nullptr;
         p.d_flats = nullptr;
         p.d_fzout = nullptr;
         if (p.d_gcols) cudaFree(p.d_gcols);
@@ -3130,10 +3138,12 @@ static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
         CK(cudaMemcpy(p.d_gents, p.gents.data(), p.gents.size() * sizeof(DevGColEntry), cudaMemcpyHostToDevice));
         CK(cudaMalloc((void**)&p.d_flats, std::max<size_t>(1, p.flats.size()) * sizeof(DevFlat)));
         CK(cudaMemcpy(p.d_flats, p.flats.data(), p.flats.size() * sizeof(DevFlat), cudaMemcpyHostToDevice));
-        CK(cudaMalloc((void**)&p.d_agroups, std::max<size_t>(1, p.agroups.size()) * sizeof(DevAGroup)));
-        CK(cudaMalloc((void**)&p.d_atab, std::max<size_t>(1, p.atab.size()) * sizeof(double2)));
-        CK(cudaMemcpy(p.d_agroups, p.agroups.data(), p.agroups.size() * sizeof(DevAGroup), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(p.d_atab, p.atab.data(), p.atab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&p.d_aflat, std::max<size_t>(1, p.aflat.size()) * sizeof(DevAFlat)));
+        CK(cudaMalloc((void**)&p.d_aoff, std::max<size_t>(1, p.aoff.size()) * sizeof(uint32_t)));
+        CK(cudaMalloc((void**)&p.d_azout, std::max<size_t>(1, p.azout.size()) * sizeof(uint64_t)));
+        CK(cudaMemcpy(p.d_aflat, p.aflat.data(), p.aflat.size() * sizeof(DevAFlat), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p.d_aoff, p.aoff.data(), p.aoff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p.d_azout, p.azout.data(), p.azout.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CK(cudaMalloc((void**)&p.d_fzout, std::max<size_t>(1, p.fzout.size()) * sizeof(uint64_t)));
         CK(cudaMemcpy(p.d_fzout, p.fzout.data(), p.fzout.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
     }
@@ -3360,16 +3370,15 @@ static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* 
             if (rc == VQE_OK) rc = make_geom(c, pp.tp, pp.d_scat, dst, g, sdst);
             if (rc) return rc;
             if (g.n_tiles == 0) continue;
-            size_t smem = (16ull << pp.tp.tbits) + TERM_CAP * (sizeof(double2) + 4) + GROUP_CAP * 16 * sizeof(double2) +
-                          GROUP_CAP * sizeof(DevAGroup);
+            size_t smem = 2 * (16ull << pp.tp.tbits) + TERM_CAP * (sizeof(double2) + 4) +
+                          AFLAT_CAP * (sizeof(DevAFlat) + sizeof(double2)) + (GROUP_CAP + 1) * 4;
             uint64_t ts = 1ull << pp.tp.tbits;
-            int threads = (int)std::min<uint64_t>(512, std::max<uint64_t>(32, ts));
-            while ((uint64_t)threads * APPLY_PER_THREAD < ts) threads *= 2;  // ts <= 4096 = 512*8
+            int threads = (int)std::min<uint64_t>(1024, std::max<uint64_t>(32, ts / 2));
             ProfScope prof(c, 2);
-            k_tile_apply<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(ssrc, sdst, g, pp.d_groups,
-                                                                               (int)pp.groups.size(), pp.d_terms_apply,
-                                                                               pp.d_agroups, pp.d_atab, (int)pp.atab.size(),
-                                                                               p == 0 ? 0 : 1);
+            k_tile_apply<<<tile_grid(c, g.n_tiles, 1), threads, smem, c->stream>>>(ssrc, sdst, g, pp.d_groups,
+                                                                                  (int)pp.groups.size(), pp.d_terms_apply,
+                                                                                  pp.d_aflat, pp.d_aoff, pp.d_azout,
+                                                                                  p == 0 ? 0 : 1);
             c->launches++;
             CK(cudaGetLastError());
         }

@@ -54,6 +54,27 @@ def main():
     import openvqe_b200.sharded as sh
     rows = sh.allgather_f64([e.real])
     assert rows[0, 0] == rows[1, 0]
+    # drop-in: after sharded.enable() the reference-shaped entry points run on the sharded state
+    from openvqe_b200 import engine as engine_mod
+    from openvqe_b200.ucc_family.get_energy_ucc import EnergyUCC
+    from tests.helpers import jw_excitation
+    del eng
+    os.environ["VQE_B200_DEVICE"] = str(device)
+    sh.enable(min_qubits=12)
+    n2 = 12
+    gens = []
+    for _ in range(6):
+        p_, q_, r_, s_ = sorted(rng.choice(n2, size=4, replace=False).tolist())
+        gens.append(jw_excitation(n2, [r_, s_], [p_, q_]))
+    gens.append(jw_excitation(n2, [7], [0]))  # a single that flips the global qubit
+    ham2 = random_hermitian(rng, n2, 120, max_weight=6, const=-0.25)
+    th = rng.uniform(-0.3, 0.3, size=len(gens)).tolist()
+    hf2 = 0b111111000000
+    e_api = EnergyUCC().ucc_action(th, ham2, gens, hf2, [])
+    assert isinstance(engine_mod.get_engine(n2), sh.ShardedEngine)
+    e_orc = orc.ucc_action(th, ham2, gens, hf2)
+    assert abs(e_api - e_orc) < 1e-10, (e_api, e_orc)
+    sh.disable()
     dist.barrier()
     if rank == 0:
         print("sharded worker ok: |dpsi| = %.2e, E = %.12f (oracle %.12f)" % (err, e.real, e_ref), flush=True)
