@@ -885,7 +885,8 @@ struct DevGColEntry {  // 32 bytes
 struct DevFlat {       // 32 bytes
     uint32_t lx, lz;   // X-mask, Z letters of the group's first term inside the tile
     uint32_t pat;      // pattern bits | free-index bits above the low 8 (already deposited)
-    uint32_t zsel;     // index of the entry's outside-tile Z mask in the pass's zout table
+    uint32_t zsel;     // bits 0-15: index of the entry's outside-tile Z mask in the pass's zout table;
+                       // bits 16-23 / 24-31: tile-bit position of free-index bit 6 / 7 after the deposit
     uint16_t himask[4];  // ~((1 << pos) - 1) for the (up to 4) fixed positions, ascending, 0 when unused:
                          // insert0(l, pos) = l + (l & himask)
     double fr;         // weight of Re(conj(b) a), factor 2 included
@@ -976,22 +977,33 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
             s_sc[k] = make_double2(flipsign(s_term[k].ar, par), flipsign(s_term[k].ai, par));
         }
         for (int q = threadIdx.x; q < nfl; q += blockDim.x)
-            s_ffr[q] = flipsign(s_flat[q].fr, __popcll(sbase & fzout[s_flat[q].zsel]));
+            s_ffr[q] = flipsign(s_flat[q].fr, __popcll(sbase & fzout[s_flat[q].zsel & 0xffffu]));
         cp_async_wait_all();
         __syncthreads();
         // flat list of the collapsed groups: 256 (pattern, free index) pairs per entry
-        for (uint32_t it = threadIdx.x; it < ((uint32_t)nfl << 8); it += bd) {
-            const DevFlat& fe = s_flat[it >> 8];
+        // a work unit = 4 pairs of one entry (free-index bits 6 and 7 enumerate them): the entry is read and the low
+        // six free bits are deposited once per unit
+        for (uint32_t u = threadIdx.x; u < ((uint32_t)nfl << 6); u += bd) {
+            const DevFlat& fe = s_flat[u >> 6];
             const uint2 hm = *reinterpret_cast<const uint2*>(fe.himask);
-            uint32_t l = it & 255u;
+            uint32_t l = u & 63u;
             l += l & (hm.x & 0xffffu);
             l += l & (hm.x >> 16);
             l += l & (hm.y & 0xffffu);
             l += l & (hm.y >> 16);
             l |= fe.pat;
-            const double2 a = tile[l], b = tile[l ^ fe.lx];
-            const double w = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
-            er = fma(flipsign(s_ffr[it >> 8], __popc(l & fe.lz)), w, er);
+            const uint32_t lx = fe.lx, lz = fe.lz;
+            const uint32_t b6 = 1u << ((fe.zsel >> 16) & 0xffu), b7 = 1u << (fe.zsel >> 24);
+            const double fr = s_ffr[u >> 6];
+            double part = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t lj = l | ((j & 1) ? b6 : 0u) | ((j & 2) ? b7 : 0u);
+                const double2 a = tile[lj], b = tile[lj ^ lx];
+                const double w = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
+                part += flipsign(w, __popc(lj & lz));
+            }
+            er = fma(fr, part, er);
         }
         for (int q = 0; q < ng; ++q) {
             const DevGroup& G = s_grp[q];
@@ -2985,10 +2997,15 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
                         fl.lx = dg.lx;
                         fl.lz = te[0].lz;
                         uint32_t fhi = hi << 8;  // deposit the high free-index bits now
+                        uint32_t d6 = 1u << 6, d7 = 1u << 7;
                         for (int b2 = 0; b2 < ne; ++b2) {
-                            fl.himask[b2] = (uint16_t)(~((1u << epos[b2]) - 1u) & 0xffffu);
-                            fhi += fhi & ~((1u << epos[b2]) - 1u);
+                            const uint32_t hm = ~((1u << epos[b2]) - 1u);
+                            fl.himask[b2] = (uint16_t)(hm & 0xffffu);
+                            fhi += fhi & hm;
+                            d6 += d6 & hm;
+                            d7 += d7 & hm;
                         }
+                        fl.zsel = zsel | ((uint32_t)__builtin_ctz(d6) << 16) | ((uint32_t)__builtin_ctz(d7) << 24);
                         fl.pat = en.pat | fhi;
                         p.flats.push_back(fl);
                     }
