@@ -441,11 +441,19 @@ def run_c5(args, rank, world, local_rank):
         return eng.expectation(ps).real
 
     fd_h = 1.4901161193847656e-08  # scipy's 2-point step
+    # gradient components: generators that excite occupied -> virtual orbitals of the reference determinant first
+    # (the others have an exactly vanishing first-order effect on |HF>)
+    occ_mask = ((1 << (n // 2)) - 1) << (n - n // 2)
+    first = {}
+    for r_, o_ in enumerate(owner.tolist()):
+        first.setdefault(o_, int(gen["x"][r_]))
+    acting = [j for j, xm in sorted(first.items()) if 2 * bin(xm & occ_mask).count("1") == bin(xm).count("1")]
+    grad_idx = (acting + [j for j in sorted(first) if j not in acting])[:args.grad_components]
 
     def step(theta):
         e0 = energy(theta)
         grad = []
-        for j in range(args.grad_components):
+        for j in grad_idx:
             tj = theta.copy()
             tj[j] += fd_h
             grad.append((energy(tj) - e0) / fd_h)
@@ -540,7 +548,8 @@ def run_c5(args, rank, world, local_rank):
                        "parallelism": "state sharded, peer passes over NVLink" if world > 1 else "1 GPU",
                        "rotation_passes": {"local": n_local_pass, "peer": n_peer_pass},
                        "expectation_passes": {"local": exl_n / evals, "peer": exp_n / evals},
-                       "energy_first_step": results[0][0], "gradient_first_step": results[0][1], "norm2_after_warmup": norm,
+                       "energy_first_step": results[0][0], "gradient_first_step": results[0][1],
+                       "gradient_components": grad_idx, "norm2_after_warmup": norm,
                        "verify_vs_unsharded_abs_err": verify},
             "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "nvlink": nvlink,
             "expectation": {"local_ms_per_eval": exl_ms / evals, "peer_ms_per_eval": exp_ms / evals}}
