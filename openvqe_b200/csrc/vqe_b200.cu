@@ -1,24 +1,28 @@
 // vqe_b200.cu -- B200-native (sm_100a) state-vector engine for the OpenVQE hot path.
 //
-// Everything here is HBM-bound complex128 streaming work (0.2 flop/byte): no tensor cores.
+// Everything here is streaming complex128 work on a state vector (0.2 flop/byte at face value): no tensor cores.
 // Design:
-//   * The state lives in HBM as interleaved complex128.  Every kernel works on TILES: a tile is
-//     the set of 2^T amplitudes obtained by fixing all index bits outside a chosen set of T
-//     "tile bits".  The low L tile bits are always index bits 0..L-1, so a tile is a gather of
-//     2^(T-L) contiguous 16*2^L-byte segments (coalesced 16-byte loads, 512 B per warp request).
-//   * A CTA stages one tile in shared memory, applies EVERY consecutive operation whose X-mask
-//     lies inside the tile bits (Z-masks may touch any bit: bits outside the tile only contribute
-//     a per-tile sign), and writes the tile back: r rotations per HBM pass instead of one.
-//     Consecutive rotations with the same X-mask act on the same amplitude pairs and are applied
-//     in registers without touching shared memory again (8 Pauli strings of a JW double
-//     excitation -> one sweep).
-//   * <psi|H|psi>, H|psi> and the ADAPT pool sweep use the same tiles: H is grouped by X-mask,
-//     the groups are packed into passes by covering their X-masks with tile-bit sets, and all
-//     Z-variants of a group are accumulated in registers with popcount signs.  Reductions are
-//     fp64 warp-shuffle + block + fixed-order final pass (bit-reproducible run to run).
+//   * The state lives in HBM as interleaved complex128.  Every kernel works on TILES: a tile is the set of 2^T
+//     amplitudes obtained by fixing all index bits outside a chosen set of T "tile bits".  The low L tile bits
+//     are always index bits 0..L-1, so a tile is a gather of 2^(T-L) contiguous 16*2^L-byte segments (coalesced
+//     16-byte accesses, 512 B per warp request, cp.async into shared memory).
+//   * A CTA stages one tile in shared memory, applies EVERY consecutive operation whose X-mask lies inside the
+//     tile bits (Z-masks may touch any bit: bits outside the tile only contribute a per-tile sign), and writes the
+//     tile back: r rotations per HBM pass instead of one.
+//   * Rotations with the same X-mask act in the same planes and commute: a run of them is COLLAPSED into one plane
+//     rotation whose angle is tabulated per occupation pattern (the 8 strings of a JW double excitation touch 1/8
+//     of the pairs, once); what does not collapse is applied on 8-amplitude ORBITS held in registers (up to three
+//     generators per shared-memory round trip).  The QUCCSD gate templates are tabulated plane rotations too.
+//   * <psi|H|psi>, H|psi> and the ADAPT pool sweep use the same tiles: H is grouped by X-mask, the groups are packed
+//     into passes by covering their X-masks with tile-bit sets, a group's Z-variants are tabulated per occupation
+//     pattern and only the coupled patterns are visited.  Reductions are fp64 warp-shuffle + block + fixed-order
+//     final pass (bit-reproducible run to run).
+//   * Sharded states: the top index bits are the rank; operations that flip a global bit run as PEER PASSES -- the
+//     same kernels on tiles with one virtual bit that selects between this rank's HBM and the partner's shard
+//     (peer memory over NVLink), ordered by a device-side flag barrier.
 //   * Persistent grids sized from the SM count; one stream per context.
 //
-// No CPU fallback: every entry point needs a CUDA device.
+// No CPU fallback: every entry point that computes needs a CUDA device.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -579,16 +583,6 @@ __device__ __forceinline__ void tile_store_scaled_fast(const double2* tile, cons
         }
     }
 }
-__device__ __forceinline__ void tile_store_scaled(const double2* tile, const Shards& dst, const TileGeom& g,
-                                                  uint64_t base, double scale) {
-    const uint32_t ts = 1u << g.tbits;
-#pragma unroll 4
-    for (uint32_t k = threadIdx.x; k < ts; k += blockDim.x) {
-        const double2 v = tile[k];
-        *amp_addr(g, dst, base, k) = make_double2(scale * v.x, scale * v.y);
-    }
-}
-
 // One sub-run on the 8-amplitude orbit of a thread: the rotations pair (beta, beta ^ C).
 //   Tangent form R = c [[1, -+t], [+-t, 1]]: the unnormalised update costs one DFMA per real component; the
 //   cosines are collected by the host into ONE scale per pass, applied when the tile is stored (every rotation
@@ -1982,6 +1976,7 @@ extern "C" int vqe_copy_buffer(vqe_ctx* c, int dst, int src) {
 extern "C" int vqe_buffer_ptr(vqe_ctx* c, int b, void** p, uint64_t* n_amp) {
     if (!c || !p) return fail(VQE_ERR_INVALID, "null argument");
     CK(cudaSetDevice(c->device));
+    if (b < 0 || b > 2) return fail(VQE_ERR_INVALID, "bad buffer id %d", b);
     int rc = ensure_buf(c, b);
     if (rc) return rc;
     *p = c->buf[b];

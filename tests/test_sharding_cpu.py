@@ -87,3 +87,37 @@ def test_gloo_world2_host_logic():
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "gloo worker ok" in res.stdout
+
+
+def test_quccsd_template_tables_match_the_gate_level_oracle():
+    """Host logic of the QUCCSD fast path (no GPU): the (pattern, cos, sin) tables derived from the templates' own
+    unitaries, applied with numpy, reproduce the oracle's gate-by-gate state -- ladders, both index layouts and the
+    global phase of the single-excitation template included."""
+    from openvqe_b200.common_files import circuit
+    from oracle import statevector_oracle as orc
+    from tests.helpers import FermiOp
+    tabs = circuit.template_tables()
+    assert tabs[2] is not None and tabs[4] is not None
+    assert sorted(abs(c) for c in tabs[4][0]) == [0.5] * 7 + [4.5]      # the reference's double template: 7 pairs turn by theta/2, one by 4.5 theta
+    n = 8
+    rng = np.random.default_rng(3)
+    ops = [FermiOp(n, [5, 7, 0, 2]), FermiOp(n, [6, 1]), FermiOp(n, [0, 3, 4, 7]), FermiOp(n, [2, 6]), FermiOp(n, [4, 5, 2, 3])]
+    theta = rng.uniform(-0.9, 0.9, size=len(ops)).tolist()
+    hf = 0b11110000
+    x, offs, pat, cosv, sinv, phase = circuit.quccsd_plane_ops(n, [list(o.terms[0].qbits) for o in ops], theta)
+    psi = orc.basis_state(n, circuit.hf_index(n, hf))
+    idx = np.arange(1 << n)
+    for k in range(len(x)):
+        xm = int(x[k])
+        new = psi.copy()
+        for q in range(offs[k], offs[k + 1]):
+            a_idx = idx[(idx & xm) == int(pat[q])]
+            b_idx = a_idx ^ xm
+            new[a_idx] = cosv[q] * psi[a_idx] - sinv[q] * psi[b_idx]
+            new[b_idx] = sinv[q] * psi[a_idx] + cosv[q] * psi[b_idx]
+        psi = new
+    psi = psi * phase
+    ref = orc.quccsd_state(n, hf, ops, theta)
+    assert np.max(np.abs(psi - ref)) < 1e-13
+    # a template whose ladder runs over one of its own core qubits is not tabulable
+    assert circuit.quccsd_plane_ops(n, [[0, 3, 2, 4]], [0.1]) is None
