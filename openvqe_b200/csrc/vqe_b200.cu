@@ -98,6 +98,20 @@ struct TileGeom {
     uint32_t vbit;         // 1: the top tile bit is VIRTUAL -- it selects the shard (0: p0 = lower rank, 1: p1 = r ^ m)
 };
 
+// Peer pass, "gather" form.  When the operations of a peer pass couple only a fraction of the partner's amplitudes
+// (collapsed runs: 1/8 of them for a JW double excitation), moving whole half-tiles over NVLink is wasteful.
+// Instead every rank keeps ALL of its own tiles, first gathers from the partner's shard just the amplitudes its own
+// results depend on (host-computed dependency closure, in groups of 4 = 64 bytes) into a local staging buffer
+// (k_gather_need, remote READS only), and after a barrier runs the pass on super-tiles whose partner half is filled
+// from the staging buffer and whose own half alone is written back (local HBM only).  Both ranks of a pair compute
+// the coupled pairs redundantly; nothing is written remotely.
+struct GatherGeom {
+    const double2* stage;   // staging buffer: [tile of the chunk][need group][4]
+    const uint16_t* need;   // needed groups of the partner half (tile-local index / 4), ascending
+    uint32_t n_need;        // 0: not a gather launch
+    uint32_t own_half;      // 0: this rank's amplitudes are the lower half of the super-tile, 1: the upper half
+};
+
 // The two shards a launch touches.  Local passes: p0 = own shard, p1 unused.  Peer passes (vbit): p0 = shard of
 // min(r, r^m), p1 = shard of max(r, r^m); one of them is this rank's HBM, the other a peer mapping over NVLink.
 struct Shards {
@@ -694,8 +708,23 @@ __device__ __forceinline__ void rot_sub1(double2* tile, const RotOp* __restrict_
 
 // REAL: the state is known to be purely real on entry and every rotation of the pass has a +-1 phase (ny odd: the
 // UCC case -- JW images of T - T^dagger), so the imaginary parts stay exactly zero and are never touched.
+// phase A of a gather-form peer pass: copy the needed partner amplitudes of tiles [g.tile_first, +g.n_tiles) into
+// the local staging buffer
+__global__ void k_gather_need(Shards psi, TileGeom g, GatherGeom gg, double2* __restrict__ stage_out) {
+    const uint32_t top = g.tbits - 1u;
+    const uint32_t par_off = gg.own_half ? 0u : (1u << top);
+    const uint64_t per_tile = (uint64_t)gg.n_need * 4u;
+    const uint64_t total = per_tile * g.n_tiles;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = i / per_tile;
+        const uint32_t q = (uint32_t)(i - t * per_tile);
+        const uint32_t k = par_off + (uint32_t)gg.need[q >> 2] * 4u + (q & 3u);
+        stage_out[i] = *amp_addr(g, psi, tile_base(g, t), k);
+    }
+}
+
 template <bool REAL>
-__global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, TileGeom g,
+__global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, TileGeom g, GatherGeom gg,
                                                      const DevOp* __restrict__ ops, int n_ops,
                                                      const DevSuper* __restrict__ supers, int n_supers,
                                                      const DevSub* __restrict__ subs, int n_subs,
@@ -730,7 +759,21 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
         const uint64_t base = tile_base(g, t);
         const uint64_t sbase = base | g.sign_base;
         __syncthreads();
-        tile_load_async_fast(tile, psi, g, ta, s_boff, base);
+        if (gg.n_need) {
+            // gather form: own half from the own shard, partner half = zeros + the staged amplitudes
+            const uint32_t half_t = ts >> 1;
+            const uint32_t own_off = gg.own_half ? half_t : 0u, par_off = gg.own_half ? 0u : half_t;
+            for (uint32_t k = threadIdx.x; k < half_t; k += blockDim.x) {
+                cp_async16(tile + own_off + k, amp_addr(g, psi, base, own_off + k));
+                tile[par_off + k] = make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+            const double2* st = gg.stage + t * (uint64_t)gg.n_need * 4u;
+            for (uint32_t q = threadIdx.x; q < gg.n_need * 4u; q += blockDim.x)
+                cp_async16(tile + par_off + (uint32_t)gg.need[q >> 2] * 4u + (q & 3u), st + q);
+        } else {
+            tile_load_async_fast(tile, psi, g, ta, s_boff, base);
+        }
         for (int r = threadIdx.x; r < n_ops; r += blockDim.x)
             optab[r].t = flipsign(ops[r].s, __popcll(sbase & ops[r].zout));
         for (int r = threadIdx.x; r < n_cols; r += blockDim.x) scsign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
@@ -807,7 +850,16 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
             }
         }
         __syncthreads();
-        tile_store_scaled_fast(tile, psi, g, ta, s_boff, base, pass_scale);
+        if (gg.n_need) {
+            const uint32_t half_t = ts >> 1;
+            const uint32_t own_off = gg.own_half ? half_t : 0u;
+            for (uint32_t k = threadIdx.x; k < half_t; k += blockDim.x) {
+                const double2 v = tile[own_off + k];
+                *amp_addr(g, psi, base, own_off + k) = make_double2(pass_scale * v.x, pass_scale * v.y);
+            }
+        } else {
+            tile_store_scaled_fast(tile, psi, g, ta, s_boff, base, pass_scale);
+        }
     }
 }
 
@@ -1357,7 +1409,12 @@ static uint32_t plan_lz(uint64_t z, const TilePlan& tp) {
     return o;
 }
 static uint64_t plan_zout(uint64_t z, const TilePlan& tp) {
-    return (z & tp.comp_mask) | ((z >> tp.nl) << tp.nl);
+    uint64_t zg = z >> tp.nl;
+    // peer pass: the sign base is the LOWER rank of the pair, whose top pattern bit is always clear, so a Z letter
+    // there never contributes (its effect on the higher rank is the virtual bit of lz).  Dropping it keeps the
+    // outside-tile masks of the strings of one generator identical, which lets them collapse.
+    if (tp.vbit) zg &= ~(1ull << (63 - __builtin_clzll(tp.gpat)));
+    return (z & tp.comp_mask) | (zg << tp.nl);
 }
 
 // finalize a plan from a set of required LOCAL bits: add low bits first, then fill up to tbits_max
@@ -1424,6 +1481,8 @@ struct vqe_ctx {
     int* d_err = nullptr;
     cudaEvent_t ev_bar = nullptr;           // in-process group barrier
     bool psi_real = false;                  // buffer 0 is known to be purely real (imaginary parts exactly 0.0)
+    double2* gstage = nullptr;              // staging buffer of gather-form peer passes
+    size_t gstage_cap = 0;                  // in amplitudes
     cudaStream_t stream = nullptr;
     double2* buf[3] = {nullptr, nullptr, nullptr};
     // staging
@@ -1657,6 +1716,7 @@ static void free_ctx(vqe_ctx* c) {
     if (c->flags) cudaFree(c->flags);
     if (c->d_peer_flags) cudaFree(c->d_peer_flags);
     if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->gstage) cudaFree(c->gstage);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->d_partial) cudaFree(c->d_partial);
@@ -2020,6 +2080,9 @@ struct OpPass {
     size_t ent_begin = 0, ent_end = 0;  // ... and their (pattern, cos, sin) entries
     bool fast = false;
     bool has_imag = false;              // some rotation of a fast pass has a +-i phase
+    // gather-form peer pass (see GatherGeom): groups of 4 partner amplitudes each rank's results depend on
+    bool gather = false;
+    std::vector<uint16_t> need_lo, need_hi;  // needed by the lower / the higher rank of a pair
     double pass_scale = 1.0;            // fast passes: product of the cosines not yet applied by a run
 };
 struct OpPlan {
@@ -2418,6 +2481,55 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
             p.sub_end = dsubs.size();
             p.col_end = dcols.size();
             p.ent_end = dents.size();
+            if (p.tp.vbit && p.tp.tbits >= 3 && env_int("VQE_PEER_GATHER", 1)) {
+                // dependency closure, walking the segments backwards: which amplitudes of the partner half does a
+                // rank need (before the pass) to compute the final values of its own half?
+                const uint32_t tsz = 1u << p.tp.tbits, hbit = tsz >> 1;
+                auto closure = [&](uint32_t own_half, std::vector<uint16_t>& out) {
+                    std::vector<char> R(tsz, 0);
+                    for (uint32_t l = 0; l < tsz; ++l) R[l] = ((l & hbit) ? 1u : 0u) == own_half;
+                    auto pull = [&](uint32_t u, uint32_t v) {
+                        if (R[u] | R[v]) R[u] = R[v] = 1;
+                    };
+                    for (size_t si = p.sup_end; si-- > p.sup_begin;) {
+                        const DevSuper& su = dsupers[si];
+                        if (su.sub_count == 0xffffffffu) {
+                            const DevCol& co = dcols[p.col_begin + su.sub_begin];
+                            for (uint32_t e2 = 0; e2 < co.n_active; ++e2) {
+                                const uint32_t pat = dents[p.ent_begin + co.ent_begin + e2].pat;
+                                for (uint32_t f = 0; f < (1u << co.free_log); ++f) {
+                                    uint32_t l = f;
+                                    for (uint32_t d = 0; d < co.nd; ++d) l += l & co.dpos[d];
+                                    l |= pat;
+                                    pull(l, l ^ co.lx);
+                                }
+                            }
+                        } else {
+                            for (uint32_t sb = su.sub_count; sb-- > 0;) {
+                                const DevSub& sub = dsubs[p.sub_begin + su.sub_begin + sb];
+                                const uint32_t lxs = four ? su.off[sub.c & 7u] : su.off[1];
+                                for (uint32_t l = 0; l < tsz; ++l)
+                                    if (!(l & (1u << (31 - __builtin_clz(lxs))))) pull(l, l ^ lxs);
+                            }
+                        }
+                    }
+                    out.clear();
+                    const uint32_t par = own_half ? 0u : hbit;
+                    for (uint32_t gidx = 0; gidx < hbit / 4; ++gidx) {
+                        bool any = false;
+                        for (uint32_t e2 = 0; e2 < 4; ++e2) any = any || R[par + gidx * 4 + e2];
+                        if (any) out.push_back((uint16_t)gidx);
+                    }
+                };
+                closure(0, p.need_lo);
+                closure(1, p.need_hi);
+                const size_t half_groups = hbit / 4;
+                p.gather = !p.need_lo.empty() && !p.need_hi.empty() && 2 * p.need_lo.size() <= half_groups &&
+                           2 * p.need_hi.size() <= half_groups;
+                if (getenv("VQE_DEBUG_PLAN") && atoi(getenv("VQE_DEBUG_PLAN")) > 1)
+                    fprintf(stderr, "[plan] peer pass: %zu segments, need_lo %zu need_hi %zu of %zu groups -> %s\n",
+                            p.sup_end - p.sup_begin, p.need_lo.size(), p.need_hi.size(), half_groups, p.gather ? "gather" : "exchange");
+            }
         }
         passes.push_back(std::move(p));
         i = j;
@@ -2444,11 +2556,16 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
     size_t off_scat = off_ents + plan.dents.size() * sizeof(DevColEntry);
     off_scat = (off_scat + 15) & ~size_t(15);
     size_t total = off_scat;
-    std::vector<size_t> scat_off(passes.size());
+    std::vector<size_t> scat_off(passes.size()), need_off(passes.size(), 0);
     for (size_t p = 0; p < passes.size(); ++p) {
         scat_off[p] = total;
         total += passes[p].tp.scat.size() * sizeof(uint64_t);
     }
+    for (size_t p = 0; p < passes.size(); ++p)
+        if (passes[p].gather) {  // [need_lo][need_hi], 16-byte aligned
+            need_off[p] = total;
+            total += ((passes[p].need_lo.size() + passes[p].need_hi.size()) * sizeof(uint16_t) + 15) & ~size_t(15);
+        }
     for (vqe_ctx* c : rs.r) {
         CK(cudaSetDevice(c->device));
         rc = ensure_stage(c, total);
@@ -2463,6 +2580,12 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
         if (!plan.dents.empty()) memcpy(c->h_stage + off_ents, plan.dents.data(), plan.dents.size() * sizeof(DevColEntry));
         for (size_t p = 0; p < passes.size(); ++p)
             memcpy(c->h_stage + scat_off[p], passes[p].tp.scat.data(), passes[p].tp.scat.size() * sizeof(uint64_t));
+        for (size_t p = 0; p < passes.size(); ++p)
+            if (passes[p].gather) {
+                memcpy(c->h_stage + need_off[p], passes[p].need_lo.data(), passes[p].need_lo.size() * sizeof(uint16_t));
+                memcpy(c->h_stage + need_off[p] + passes[p].need_lo.size() * sizeof(uint16_t), passes[p].need_hi.data(),
+                       passes[p].need_hi.size() * sizeof(uint16_t));
+            }
         c->h2d_bytes += total;
         CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, c->stream));
     }
@@ -2478,12 +2601,105 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
         }
         for (vqe_ctx* c : rs.r) c->psi_real = real;
     }
+    // one launch of the pass kernel on one rank (gg.n_need != 0: gather form over the tiles of the current chunk)
+    auto launch_pass = [&](vqe_ctx* c, size_t p, const TileGeom& g, const Shards& sh, const GatherGeom& gg) -> int {
+        const OpPass& ps = passes[p];
+        size_t smem = tile_smem(ps.tp.tbits, 1, false) +
+                      (ps.fast ? (ps.op_end - ps.op_begin) * sizeof(RotOp) + (ps.sup_end - ps.sup_begin) * sizeof(DevSuper) +
+                                     (ps.sub_end - ps.sub_begin) * sizeof(DevSub) + (ps.col_end - ps.col_begin) * (sizeof(DevCol) + 4) +
+                                     (ps.ent_end - ps.ent_begin) * sizeof(DevColEntry)
+                               : (ps.op_end - ps.op_begin) * sizeof(FastOp));
+        int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
+        ProfScope prof(c, ps.tp.vbit ? 4 : 0);
+        if (ps.fast && real_pass[p])
+            k_tile_rot<true><<<tile_grid(c, g.n_tiles, (smem <= 74 * 1024 && env_int("VQE_REAL_CTAS", 3) == 3) ? 3 : 0), threads, smem, c->stream>>>(
+                sh, g, gg, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
+                (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
+                (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
+                (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
+                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale);
+        else if (ps.fast)
+            k_tile_rot<false><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
+                sh, g, gg, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
+                (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
+                (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
+                (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
+                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale);
+        else
+            k_tile_ops<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
+                sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
+                (const double*)(c->d_stage + off_mats));
+        c->launches++;
+        CK(cudaGetLastError());
+        return VQE_OK;
+    };
+    const GatherGeom no_gather = {nullptr, nullptr, 0u, 0u};
     bool fenced = false;  // a cross-rank barrier separates the previous pass from the next one
     for (size_t p = 0; p < passes.size(); ++p) {
         const OpPass& ps = passes[p];
         if (ps.tp.vbit && !fenced) {
             rc = rank_barrier(rs);  // the partner's earlier writes to its shard are complete
             if (rc) return rc;
+        }
+        if (ps.tp.vbit && ps.gather && ps.fast) {
+            // gather form: [gather the needed partner amplitudes of a chunk of tiles | barrier | run the pass on the
+            // chunk, own half written back locally]; nothing is written remotely, so no barrier is needed afterwards
+            const size_t n_need_max = std::max(ps.need_lo.size(), ps.need_hi.size());
+            const uint64_t per_tile = (uint64_t)n_need_max * 4;                      // amplitudes per tile
+            const uint64_t cap_amp = std::max<uint64_t>(per_tile, std::min<uint64_t>(
+                (uint64_t)env_int("VQE_GATHER_STAGE_MB", 16384) * (1ull << 20) / sizeof(double2), (rs.r[0]->n_amp / 8) + per_tile));
+            const uint64_t chunk_tiles = std::max<uint64_t>(1, std::min<uint64_t>(ps.tp.n_tiles, cap_amp / per_tile));
+            for (vqe_ctx* c : rs.r) {
+                CK(cudaSetDevice(c->device));
+                if (c->gstage_cap < chunk_tiles * per_tile) {
+                    if (c->gstage) cudaFree(c->gstage);
+                    c->gstage = nullptr;
+                    c->gstage_cap = 0;
+                    cudaError_t e = cudaMalloc((void**)&c->gstage, chunk_tiles * per_tile * sizeof(double2));
+                    if (e != cudaSuccess)
+                        return fail(VQE_ERR_NOMEM, "staging buffer of a gather-form peer pass (%.1f GB) failed: %s; set VQE_PEER_GATHER=0",
+                                    chunk_tiles * per_tile * 16.0 / 1e9, cudaGetErrorString(e));
+                    c->gstage_cap = chunk_tiles * per_tile;
+                }
+            }
+            for (uint64_t t0 = 0; t0 < ps.tp.n_tiles; t0 += chunk_tiles) {
+                const uint64_t nt = std::min<uint64_t>(chunk_tiles, ps.tp.n_tiles - t0);
+                std::vector<TileGeom> gs(rs.r.size());
+                std::vector<Shards> shs(rs.r.size());
+                std::vector<GatherGeom> ggs(rs.r.size());
+                for (size_t k = 0; k < rs.r.size(); ++k) {
+                    vqe_ctx* c = rs.r[k];
+                    CK(cudaSetDevice(c->device));
+                    rc = make_geom(c, ps.tp, (const uint64_t*)(c->d_stage + scat_off[p]), VQE_BUF_PSI, gs[k], shs[k]);
+                    if (rc) return rc;
+                    gs[k].n_tiles = nt;      // every rank walks ALL its tiles, chunk by chunk
+                    gs[k].tile_first = t0;
+                    gs[k].tile_stride = 1;
+                    const int partner = c->rank ^ (int)ps.tp.gpat;
+                    const bool is_hi = c->rank > partner;
+                    const std::vector<uint16_t>& need = is_hi ? ps.need_hi : ps.need_lo;
+                    ggs[k].stage = c->gstage;
+                    ggs[k].need = (const uint16_t*)(c->d_stage + need_off[p]) + (is_hi ? ps.need_lo.size() : 0);
+                    ggs[k].n_need = (uint32_t)need.size();
+                    ggs[k].own_half = is_hi ? 1u : 0u;
+                    const uint64_t total_amp = (uint64_t)need.size() * 4 * nt;
+                    const int blocks = (int)std::min<uint64_t>((total_amp + 255) / 256, (uint64_t)c->sm_count * 16);
+                    ProfScope prof(c, 4);
+                    k_gather_need<<<std::max(1, blocks), 256, 0, c->stream>>>(shs[k], gs[k], ggs[k], c->gstage);
+                    c->launches++;
+                    CK(cudaGetLastError());
+                }
+                rc = rank_barrier(rs);  // every rank has read what it needs before anyone overwrites its tiles
+                if (rc) return rc;
+                for (size_t k = 0; k < rs.r.size(); ++k) {
+                    vqe_ctx* c = rs.r[k];
+                    CK(cudaSetDevice(c->device));
+                    rc = launch_pass(c, p, gs[k], shs[k], ggs[k]);
+                    if (rc) return rc;
+                }
+            }
+            fenced = false;
+            continue;
         }
         for (vqe_ctx* c : rs.r) {
             CK(cudaSetDevice(c->device));
@@ -2492,33 +2708,8 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
             rc = make_geom(c, ps.tp, (const uint64_t*)(c->d_stage + scat_off[p]), VQE_BUF_PSI, g, sh);
             if (rc) return rc;
             if (g.n_tiles == 0) continue;
-            size_t smem = tile_smem(ps.tp.tbits, 1, false) +
-                          (ps.fast ? (ps.op_end - ps.op_begin) * sizeof(RotOp) + (ps.sup_end - ps.sup_begin) * sizeof(DevSuper) +
-                                         (ps.sub_end - ps.sub_begin) * sizeof(DevSub) + (ps.col_end - ps.col_begin) * (sizeof(DevCol) + 4) +
-                                         (ps.ent_end - ps.ent_begin) * sizeof(DevColEntry)
-                                   : (ps.op_end - ps.op_begin) * sizeof(FastOp));
-            int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
-            ProfScope prof(c, ps.tp.vbit ? 4 : 0);
-            if (ps.fast && real_pass[p])
-                k_tile_rot<true><<<tile_grid(c, g.n_tiles, (smem <= 74 * 1024 && env_int("VQE_REAL_CTAS", 3) == 3) ? 3 : 0), threads, smem, c->stream>>>(
-                    sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
-                    (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
-                    (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
-                    (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
-                    (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale);
-            else if (ps.fast)
-                k_tile_rot<false><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
-                    sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
-                    (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
-                    (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
-                    (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
-                    (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale);
-            else
-                k_tile_ops<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
-                    sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
-                    (const double*)(c->d_stage + off_mats));
-            c->launches++;
-            CK(cudaGetLastError());
+            rc = launch_pass(c, p, g, sh, no_gather);
+            if (rc) return rc;
         }
         fenced = false;
         if (ps.tp.vbit) {
@@ -2608,7 +2799,18 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
         fprintf(stderr, "[plan] passes %zu (fast %zu) ops %zu segments %zu (collapsed runs %zu, %zu active patterns) sub-runs %zu; sub-run-length histogram 1..8+:",
                 plan.passes.size(), nfast, plan.dops.size(), plan.dsupers.size(), plan.dcols.size(), plan.dents.size(), nruns);
         for (int k = 1; k <= 8; ++k) fprintf(stderr, " %zu", lens[k]);
-        fprintf(stderr, "\n");
+        size_t npeer = 0, ngather = 0;
+        double frac = 0.0;
+        for (const OpPass& p : plan.passes) {
+            if (!p.tp.vbit) continue;
+            ++npeer;
+            if (p.gather) {
+                ++ngather;
+                frac += (double)std::max(p.need_lo.size(), p.need_hi.size()) * 4.0 / (double)((1u << p.tp.tbits) >> 1);
+            }
+        }
+        fprintf(stderr, "; peer passes %zu, gather form %zu (mean needed fraction of the partner half %.3f)\n", npeer, ngather,
+                ngather ? frac / ngather : 0.0);
     }
     return VQE_OK;
 }
