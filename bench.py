@@ -434,6 +434,7 @@ def run_c5(args, rank, world, local_rank):
     plan = sharded.plan_rotations(n, g, gen["x"], gen["z"], gen["ny"], gen["theta"][owner] * coeff)
     n_local_pass = sum(1 for p in plan if p[0] == 0)
     n_peer_pass = len(plan) - n_local_pass
+    n_gather_pass = sum(1 for p in plan if p[0] == 2)
 
     def energy(theta):
         eng.set_basis_state(hf)
@@ -546,7 +547,7 @@ def run_c5(args, rank, world, local_rank):
                                       n_rot, len(ham["x"]), ham["n_groups"], world, g),
                        "qubits": n, "shard_bytes": S_local, "l2_policy": "shard (%.0f GB) larger than L2" % (S_local / 1e9),
                        "parallelism": "state sharded, peer passes over NVLink" if world > 1 else "1 GPU",
-                       "rotation_passes": {"local": n_local_pass, "peer": n_peer_pass},
+                       "rotation_passes": {"local": n_local_pass, "peer": n_peer_pass, "peer_in_gather_form": n_gather_pass},
                        "expectation_passes": {"local": exl_n / evals, "peer": exp_n / evals},
                        "energy_first_step": results[0][0], "gradient_first_step": results[0][1],
                        "gradient_components": grad_idx, "norm2_after_warmup": norm,

@@ -183,8 +183,10 @@ int vqe_group_pool_overlaps(vqe_ctx* const* ranks, int n_ranks, int bra_buf, int
                             const int32_t* ny, const double* cre, const double* cim, double* out);
 
 /* Host-only view of the pass planner (no CUDA call): cuts an ordered rotation list into tile passes for a
- * state with n_global rank bits.  pass_kind[p]: 0 = local pass, 1 = peer pass between ranks r and
- * r ^ pass_pattern[p].  At most `cap` passes are written; *n_passes is the full count. */
+ * state with n_global rank bits.  pass_kind[p]: 0 = local pass, 1 / 2 = peer pass between ranks r and
+ * r ^ pass_pattern[p] in exchange form (half-tiles read and written through peer memory) / in gather form (only the
+ * partner amplitudes a rank's results depend on are fetched; all writes local).  At most `cap` passes are written;
+ * *n_passes is the full count. */
 int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int low_bits, int n_rot, const uint64_t* xmask,
                        const uint64_t* zmask, const int32_t* ny, const double* angle, int cap, int32_t* n_passes,
                        int32_t* pass_kind, uint64_t* pass_pattern, int32_t* pass_n_ops, uint64_t* pass_tile_mask);

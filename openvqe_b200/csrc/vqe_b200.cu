@@ -2759,7 +2759,8 @@ extern "C" int vqe_apply_pauli_rotations(vqe_ctx* c, int n_rot, const uint64_t* 
 }
 // Host-only view of the pass planner (no CUDA call): how an ordered rotation list is cut into tile passes for
 // a state of n_qubits with n_global rank bits.  Used by the CPU tests of the sharding logic and by bench.py to
-// report local / peer pass counts.  pass_kind: 0 = local pass, 1 = peer pass (pattern in pass_pattern).
+// report local / peer pass counts.  pass_kind: 0 = local pass, 1 = peer pass in exchange form, 2 = peer pass in
+// gather form (pattern in pass_pattern).
 extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int low_bits, int n_rot,
                                   const uint64_t* xmask, const uint64_t* zmask, const int32_t* ny, const double* angle,
                                   int cap, int32_t* n_passes, int32_t* pass_kind, uint64_t* pass_pattern,
@@ -2787,7 +2788,7 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
     if (rc) return rc;
     *n_passes = (int32_t)plan.passes.size();
     for (size_t p = 0; p < plan.passes.size() && (int)p < cap; ++p) {
-        if (pass_kind) pass_kind[p] = plan.passes[p].tp.vbit ? 1 : 0;
+        if (pass_kind) pass_kind[p] = plan.passes[p].tp.vbit ? (plan.passes[p].gather ? 2 : 1) : 0;
         if (pass_pattern) pass_pattern[p] = plan.passes[p].tp.gpat;
         if (pass_n_ops) pass_n_ops[p] = (int32_t)(plan.passes[p].op_end - plan.passes[p].op_begin);
         if (pass_tile_mask) pass_tile_mask[p] = plan.passes[p].tp.tile_mask;

@@ -290,7 +290,7 @@ class ShardGroup:
 
 def plan_rotations(n_qubits, n_global, x, z, ny, angles, tile_bits=12, low_bits=5):
     """Host-only view of the pass planner: list of (kind, pattern, n_ops, tile_mask) per pass, kind 0 = local,
-    1 = peer pass between ranks r and r ^ pattern.  No GPU needed."""
+    1 = peer pass between ranks r and r ^ pattern in exchange form, 2 = the same in gather form.  No GPU needed."""
     lib = _lib.load()
     x = np.ascontiguousarray(x, dtype=np.uint64)
     z = np.ascontiguousarray(z, dtype=np.uint64)

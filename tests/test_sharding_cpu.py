@@ -48,6 +48,32 @@ def test_planner_local_vs_peer_passes():
     assert all(bin(p[3]).count("1") == 12 for p in one)
 
 
+def test_planner_gather_form_for_collapsed_excitations():
+    """JW excitations collapse to one plane rotation per generator; a peer pass made of them runs in gather form
+    (kind 2), a peer pass with a lone Pauli string that flips a global qubit keeps the exchange form (kind 1)."""
+    from openvqe_b200.lowering import pack_operator
+    from openvqe_b200.sharded import plan_rotations
+    from tests.helpers import jw_excitation
+    n, g = 20, 2
+    xs, zs, nys, angs = [], [], [], []
+    def add(cre, ann):
+        pk = pack_operator(jw_excitation(n, cre, ann))
+        xs.extend(int(v) for v in pk.x); zs.extend(int(v) for v in pk.z); nys.extend(int(v) for v in pk.ny)
+        angs.extend(0.1 * float(c) for c in pk.cre)
+
+    for cre, ann in (([9, 12], [0, 5]), ([15], [1]), ([10, 11], [6, 7])):
+        add(cre, ann)
+    kinds = [p[0] for p in plan_rotations(n, g, xs, zs, nys, angs)]
+    assert kinds and all(k in (0, 2) for k in kinds) and 2 in kinds
+    # a generator that flips BOTH global qubits keeps per-string outside-tile signs: not collapsed, exchange form
+    add([8, 19], [0, 1])
+    assert plan_rotations(n, g, xs, zs, nys, angs)[-1][0] == 1
+    # so does a lone Pauli string on a global qubit
+    x, z, ny = _rot(n, "XZY", [1, 3, 4])
+    kinds = [p[0] for p in plan_rotations(n, g, xs + [x], zs + [z], nys + [ny], angs + [0.3])]
+    assert kinds[-1] == 1
+
+
 def test_planner_zero_angles_dropped_and_capacity_split():
     from openvqe_b200.sharded import plan_rotations
     n = 24
