@@ -494,6 +494,46 @@ def run_c5(args, rank, world, local_rank):
     prof = [eng.profile_read(k) for k in range(6)]
     eng.profile(False)
     prof = [(max_over_ranks(m), c) for m, c in prof]
+    # ---- e2e: the same evaluations through the reference-facing call EnergyUCC.ucc_action with host objects ------
+    # (every rank makes the same call; the sharded engine is the process-wide engine of this register size)
+    from openvqe_b200 import engine as engine_mod
+    from openvqe_b200.ucc_family.get_energy_ucc import EnergyUCC
+
+    class _Term:
+        __slots__ = ("coeff", "op", "qbits")
+
+        def __init__(self, c, op, qb):
+            self.coeff, self.op, self.qbits = c, op, qb
+
+    class _Ham:
+        def __init__(self, terms, const=0.0):
+            self.nbqbits, self.terms, self.constant_coeff = n, terms, const
+
+    hterms, hconst = [], 0.0
+    for cf, op, qb in c5.to_terms(n, ham, "cre"):
+        if op:
+            hterms.append(_Term(cf, op, qb))
+        else:
+            hconst += cf
+    ham_obj = _Ham(hterms, hconst)
+    gens = [[] for _ in range(gen["n_generators"])]
+    for (cf, op, qb), o in zip(c5.to_terms(n, gen, "coeff"), owner.tolist()):
+        gens[o].append(_Term(cf, op, qb))
+    gen_objs = [_Ham(t) for t in gens]
+    os.environ["VQE_B200_DEVICE"] = str(local_rank)
+    engine_mod._ENGINES[(n, engine_mod.default_device())] = eng
+    api = EnergyUCC()
+    e_api = api.ucc_action(ths[args.warmup], ham_obj, gen_objs, hf, [])  # lowers + uploads H once (cached afterwards)
+    assert abs(e_api - results[0][0]) < 1e-9, (e_api, results[0][0])
+    eng.transfer_bytes(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for th in ths[args.warmup:]:
+        api.ucc_action(th, ham_obj, gen_objs, hf, [])
+    eng.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    h2d, d2h = eng.transfer_bytes()
+    barrier()
     verify = None
     if args.verify and n <= 31:
         # the same evaluation on ONE unsharded context (rank 0 only; needs 2^n amplitudes next to the shard)
@@ -552,7 +592,10 @@ def run_c5(args, rank, world, local_rank):
                        "energy_first_step": results[0][0], "gradient_first_step": results[0][1],
                        "gradient_components": grad_idx, "norm2_after_warmup": norm,
                        "verify_vs_unsharded_abs_err": verify},
-            "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "nvlink": nvlink,
+            "e2e": {"value": args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": h2d / args.steps,
+                    "d2h_bytes_per_step": d2h / args.steps, "ms_per_step": e2e_s * 1e3 / args.steps,
+                    "api": "openvqe_b200.ucc_family.get_energy_ucc.EnergyUCC.ucc_action (sharded engine)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "nvlink": nvlink,
             "expectation": {"local_ms_per_eval": exl_ms / evals, "peer_ms_per_eval": exp_ms / evals}}
     print(json.dumps(line), flush=True)
     if dist is not None:
