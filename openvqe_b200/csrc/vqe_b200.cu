@@ -96,6 +96,7 @@ struct TileGeom {
     uint64_t tile_first;   // tile numbers walked: tile_first + k * tile_stride, k < n_tiles
     uint32_t tile_stride;
     uint32_t vbit;         // 1: the top tile bit is VIRTUAL -- it selects the shard (0: p0 = lower rank, 1: p1 = r ^ m)
+    uint32_t bulk;         // 1: stage the tile with bulk asynchronous copies (cp.async.bulk, one per contiguous segment)
 };
 
 // Peer pass, "gather" form.  When the operations of a peer pass couple only a fraction of the partner's amplitudes
@@ -566,6 +567,45 @@ __device__ __forceinline__ double2* amp_addr_fast(const TileGeom& g, const Shard
     double2* p = (g.vbit && ((j * blockDim.x) >> (g.tbits - 1u))) ? sh.p1 : sh.p0;
     return p + (base | ta.a_fix | s_boff[j]);
 }
+// ---- bulk asynchronous tile load (TMA engine, 1-d form): a tile is 2^(T-L) contiguous segments of 16 * 2^L bytes,
+// each fetched by ONE cp.async.bulk that signals an mbarrier with its byte count; the threads only wait on the
+// barrier's phase.  No per-thread address arithmetic, no registers, copies in flight while the per-tile tables are
+// refreshed.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    // bounded spin: a protocol error must never hang the GPU (the results would then be wrong and the tests say so)
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+        if (ok) return;
+    }
+}
+__device__ __forceinline__ void tile_load_bulk(double2* tile, const Shards& src, const TileGeom& g, uint64_t base, uint64_t* bar) {
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t nseg = ts >> g.lbits;
+    const uint32_t seg_bytes = 16u << g.lbits;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to the tile come first
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, ts * 16u);
+    for (uint32_t sgm = threadIdx.x; sgm < nseg; sgm += blockDim.x) {
+        const uint32_t k = sgm << g.lbits;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(tile + k)),
+                     "l"(amp_addr(g, src, base, k)), "r"(seg_bytes), "r"(smem_u32(bar))
+                     : "memory");
+    }
+}
+
 __device__ __forceinline__ void tile_load_async_fast(double2* tile, const Shards& src, const TileGeom& g, const TileAddr& ta,
                                                      const uint64_t* s_boff, uint64_t base) {
     if (!ta.fast) {
@@ -740,6 +780,10 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
     DevSub* ssub = (DevSub*)(sent + n_ents);
     uint32_t* scsign = (uint32_t*)(ssub + n_subs);  // per tile: outside-tile Z parity of every collapsed run
     __shared__ uint64_t s_boff[16];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const bool bulk = g.bulk && !gg.n_need;
+    uint32_t mphase = 0;
+    if (bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
     const TileAddr ta = tile_addr_init(g, s_boff);
     for (int q = threadIdx.x; q < n_supers; q += blockDim.x) ssup[q] = supers[q];
     for (int q = threadIdx.x; q < n_subs; q += blockDim.x) ssub[q] = subs[q];
@@ -771,13 +815,20 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
             const double2* st = gg.stage + t * (uint64_t)gg.n_need * 4u;
             for (uint32_t q = threadIdx.x; q < gg.n_need * 4u; q += blockDim.x)
                 cp_async16(tile + par_off + (uint32_t)gg.need[q >> 2] * 4u + (q & 3u), st + q);
+        } else if (bulk) {
+            tile_load_bulk(tile, psi, g, base, &s_mbar);
         } else {
             tile_load_async_fast(tile, psi, g, ta, s_boff, base);
         }
         for (int r = threadIdx.x; r < n_ops; r += blockDim.x)
             optab[r].t = flipsign(ops[r].s, __popcll(sbase & ops[r].zout));
         for (int r = threadIdx.x; r < n_cols; r += blockDim.x) scsign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
-        cp_async_wait_all();
+        if (bulk) {
+            mbar_wait(&s_mbar, mphase);
+            mphase ^= 1u;
+        } else {
+            cp_async_wait_all();
+        }
         for (int q = 0; q < n_supers; ++q) {
             __syncthreads();
             const DevSuper& su = ssup[q];
@@ -981,6 +1032,9 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
     for (int q = threadIdx.x; q < n_gents; q += blockDim.x) s_gent[q] = gents[q];
     // this CTA's share of the flat list (blockIdx.y splits it like the groups)
     __shared__ uint64_t s_boff[16];
+    __shared__ __align__(8) uint64_t s_mbar;
+    uint32_t mphase = 0;
+    if (g.bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
     const TileAddr ta = tile_addr_init(g, s_boff);
     const int fper = (n_flats + gridDim.y - 1) / gridDim.y;
     const int f0 = min(n_flats, (int)blockIdx.y * fper), f1 = min(n_flats, f0 + fper);
@@ -1017,14 +1071,20 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
         const uint64_t base = tile_base(g, t);
         const uint64_t sbase = base | g.sign_base;
         __syncthreads();  // previous tile fully consumed (and, first time, the tables are in place)
-        tile_load_async_fast(tile, psi, g, ta, s_boff, base);
+        if (g.bulk) tile_load_bulk(tile, psi, g, base, &s_mbar);
+        else tile_load_async_fast(tile, psi, g, ta, s_boff, base);
         for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
             const uint32_t par = __popcll(sbase & s_term[k].zout);
             s_sc[k] = make_double2(flipsign(s_term[k].ar, par), flipsign(s_term[k].ai, par));
         }
         for (int q = threadIdx.x; q < nfl; q += blockDim.x)
             s_ffr[q] = flipsign(s_flat[q].fr, __popcll(sbase & fzout[s_flat[q].zsel & 0xffffu]));
-        cp_async_wait_all();
+        if (g.bulk) {
+            mbar_wait(&s_mbar, mphase);
+            mphase ^= 1u;
+        } else {
+            cp_async_wait_all();
+        }
         __syncthreads();
         // flat list of the collapsed groups: 256 (pattern, free index) pairs per entry
         // a work unit = 4 pairs of one entry (free-index bits 6 and 7 enumerate them): the entry is read and the low
@@ -1913,6 +1973,7 @@ static int make_geom(const vqe_ctx* c, const TilePlan& tp, const uint64_t* d_sca
     g.tbits = tp.tbits;
     g.lbits = tp.lbits;
     g.vbit = tp.vbit ? 1u : 0u;
+    g.bulk = (tp.lbits >= 3 && env_int("VQE_BULK", 1)) ? 1u : 0u;  // segments of at least 128 bytes
     if (!tp.vbit) {
         g.n_tiles = tp.n_tiles;
         g.tile_first = 0;
