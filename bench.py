@@ -12,6 +12,14 @@ larger than the 126 MB L2, so nothing is L2-resident between sweeps).  theta cha
   N > 1   below 33 qubits the path shards as independent energy evaluations: every rank
           evaluates its own theta on its own GPU, no data-path collective ("weak" scaling).
 
+The line also carries `adapt_pool_sweep` (sigma = H psi plus <sigma|A_k|psi> for the 1 818-operator pool of the
+workload, the second half of BASELINE's metric) and `quccsd` (the same excitations through the gate-defined
+EnergyUCC.action_quccsd, BASELINE config 4), both outside the timed steps.
+
+`--workload c5 [--qubits n] [--grad-components k] [--verify]`: the synthetic C5 program (tools/c5_synthetic.py) on a
+state SHARDED over the N ranks (33/34/35/36 qubits for 1/2/4/8 GPUs = 137 GB per GPU): local-pass HBM GB/s, peer-pass
+NVLink figures, pass counts by form, e2e through EnergyUCC.ucc_action on the sharded engine.
+
 `--impl reference` times the CPU port of the reference path (oracle/c, OpenMP over all host cores) on a bounded
 sample of the same workload and scales it to one evaluation.
 """

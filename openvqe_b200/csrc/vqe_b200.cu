@@ -606,6 +606,22 @@ __device__ __forceinline__ void tile_load_bulk(double2* tile, const Shards& src,
     }
 }
 
+// bulk asynchronous tile store: one cp.async.bulk per segment, shared -> global; returns once the copies have READ
+// the shared-memory tile (it may then be refilled), the global writes complete in the background
+__device__ __forceinline__ void tile_store_bulk(const double2* tile, const Shards& dst, const TileGeom& g, uint64_t base) {
+    const uint32_t nseg = (1u << g.tbits) >> g.lbits;
+    const uint32_t seg_bytes = 16u << g.lbits;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tile was written through the generic proxy
+    for (uint32_t sgm = threadIdx.x; sgm < nseg; sgm += blockDim.x) {
+        const uint32_t k = sgm << g.lbits;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(amp_addr(g, dst, base, k)),
+                     "r"(smem_u32(tile + k)), "r"(seg_bytes)
+                     : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void tile_load_async_fast(double2* tile, const Shards& src, const TileGeom& g, const TileAddr& ta,
                                                      const uint64_t* s_boff, uint64_t base) {
     if (!ta.fast) {
@@ -908,10 +924,13 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
                 const double2 v = tile[own_off + k];
                 *amp_addr(g, psi, base, own_off + k) = make_double2(pass_scale * v.x, pass_scale * v.y);
             }
+        } else if (bulk && pass_scale == 1.0) {
+            tile_store_bulk(tile, psi, g, base);
         } else {
             tile_store_scaled_fast(tile, psi, g, ta, s_boff, base, pass_scale);
         }
     }
+    if (bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores have landed
 }
 
 __global__ void __launch_bounds__(512, 2) k_tile_ops(Shards psi, TileGeom g,
