@@ -1541,6 +1541,8 @@ struct KernelProf {
 };
 
 #define MAX_RANKS 64
+struct PlanCache;                      // cached pass plan of the last rotation program (defined with the planner)
+static void free_plan_cache(PlanCache* pc);
 struct vqe_ctx {
     int n = 0, device = 0, sm_count = 148;
     uint64_t n_amp = 0;  // amplitudes held by THIS context (2^nl)
@@ -1560,6 +1562,7 @@ struct vqe_ctx {
     int* d_err = nullptr;
     cudaEvent_t ev_bar = nullptr;           // in-process group barrier
     bool psi_real = false;                  // buffer 0 is known to be purely real (imaginary parts exactly 0.0)
+    PlanCache* plan_cache = nullptr;        // see rotations_impl
     double2* gstage = nullptr;              // staging buffer of gather-form peer passes
     size_t gstage_cap = 0;                  // in amplitudes
     cudaStream_t stream = nullptr;
@@ -1795,6 +1798,7 @@ static void free_ctx(vqe_ctx* c) {
     if (c->flags) cudaFree(c->flags);
     if (c->d_peer_flags) cudaFree(c->d_peer_flags);
     if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->plan_cache) free_plan_cache(c->plan_cache);
     if (c->gstage) cudaFree(c->gstage);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
@@ -2173,6 +2177,19 @@ struct OpPlan {
     std::vector<DevCol> dcols;
     std::vector<DevColEntry> dents;
     std::vector<double> mats;
+    // what a re-use of the plan with new angles needs (see refresh_plan)
+    struct ColRecipe {
+        uint32_t first_op, n_str;   // strings of the run: dops[first_op .. first_op + n_str)
+        uint32_t pat_begin, n_pat;  // its a-side patterns in col_pats
+    };
+    struct ColPat {
+        uint32_t signmask;          // bit q set: string q enters the pattern's angle with a minus sign
+        int32_t ent;                // index into dents, or -1 when the angle vanishes on this pattern
+    };
+    std::vector<ColRecipe> recipes;
+    std::vector<ColPat> col_pats;
+    std::vector<double> rot_cos;    // cosine of every dop (fast passes)
+    bool cacheable = true;
 };
 
 static bool fast_eligible(const HostOp& h) {
@@ -2286,6 +2303,7 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
         }
         std::vector<double> rot_cos(p.op_end - p.op_begin);  // per-rotation cosines (the run heads get overwritten below)
         for (size_t k = p.op_begin; k < p.op_end; ++k) rot_cos[k - p.op_begin] = dops[k].c;
+        out.rot_cos.insert(out.rot_cos.end(), rot_cos.begin(), rot_cos.end());
         // run lengths of consecutive same-lx rotations of the same kind; fast runs carry prod(c) in the head
         for (size_t k = p.op_begin; k < p.op_end;) {
             if (dops[k].kind != OP_ROT && dops[k].kind != OP_ROTF) { ++k; continue; }
@@ -2338,18 +2356,23 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                 double scale = 0.0;
                 for (size_t q = k; q < e; ++q) scale += fabs(ops[i + (q - p.op_begin)].ang);
                 std::vector<DevColEntry> ent;
+                std::vector<OpPlan::ColPat> pats;  // recipe of the run: sign masks of all a-side patterns
+                if (R > 32) out.cacheable = false;
                 for (uint32_t pi = 0; pi < (1u << ne); ++pi) {
                     uint32_t pat = 0;
                     for (int b2 = 0; b2 < ne; ++b2)
                         if ((pi >> b2) & 1u) pat |= 1u << epos[b2];
                     if ((pat >> hb) & 1u) continue;  // a-side only
                     double F = 0.0;
+                    uint32_t signmask = 0;
                     for (size_t q = k; q < e; ++q) {
-                        const double kap = (dops[q].k4 >> 1) ? -1.0 : 1.0;
-                        const double sg = (__builtin_popcount(pat & (dops[q].lz ^ dops[k].lz)) & 1) ? -1.0 : 1.0;
-                        F += kap * sg * ops[i + (q - p.op_begin)].ang;
+                        const bool neg = ((dops[q].k4 >> 1) & 1u) != (uint32_t)(__builtin_popcount(pat & (dops[q].lz ^ dops[k].lz)) & 1);
+                        if (neg && q - k < 32) signmask |= 1u << (q - k);
+                        F += (neg ? -1.0 : 1.0) * ops[i + (q - p.op_begin)].ang;
                     }
-                    if (fabs(F) <= 1e-15 * scale) continue;  // exact cancellation up to rounding: identity on this pattern
+                    const bool active = fabs(F) > 1e-15 * scale;  // else: exact cancellation up to rounding, identity
+                    pats.push_back({signmask, active ? (int32_t)ent.size() : -1});
+                    if (!active) continue;
                     DevColEntry en;
                     memset(&en, 0, sizeof en);
                     en.c = cos(F);
@@ -2357,7 +2380,18 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                     en.pat = pat;
                     ent.push_back(en);
                 }
-                if (ent.empty()) return 2;
+                auto record = [&](bool emitted) {
+                    OpPlan::ColRecipe rcp = {(uint32_t)k, (uint32_t)R, (uint32_t)out.col_pats.size(), (uint32_t)pats.size()};
+                    for (OpPlan::ColPat cp : pats) {
+                        if (cp.ent >= 0) cp.ent = emitted ? cp.ent + (int32_t)dents.size() : -2;  // -2: active but not emitted
+                        out.col_pats.push_back(cp);
+                    }
+                    out.recipes.push_back(rcp);
+                };
+                if (ent.empty()) {
+                    record(false);
+                    return 2;
+                }
                 // shared-memory budget of the pass for collapsed-run tables (the tile itself takes 64 KiB of the ~113)
                 const size_t need_bytes = sizeof(DevCol) + 4 + sizeof(DevSuper) + ent.size() * sizeof(DevColEntry);
                 if ((dcols.size() - p.col_begin) * (sizeof(DevCol) + 4 + sizeof(DevSuper)) +
@@ -2386,6 +2420,7 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                 su.sub_begin = (uint32_t)(dcols.size() - p.col_begin);
                 su.sub_count = 0xffffffffu;
                 su.cscale = 1.0;
+                record(true);
                 dcols.push_back(co);
                 dents.insert(dents.end(), ent.begin(), ent.end());
                 dsupers.push_back(su);
@@ -2499,12 +2534,15 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                     if (!col_state[k - p.op_begin] && dsubs.size() > first_sub) {
                         // a collapsible run ends this round trip (it is emitted by the outer loop)
                         const size_t mark_c = dcols.size(), mark_e = dents.size(), mark_s = dsupers.size();
+                        const size_t mark_r = out.recipes.size(), mark_p = out.col_pats.size();
                         const bool imag_before = p.has_imag;
                         const int cr = try_collapse(k, e);
                         if (cr != 0) {
                             dcols.resize(mark_c);
                             dents.resize(mark_e);
                             dsupers.resize(mark_s);
+                            out.recipes.resize(mark_r);
+                            out.col_pats.resize(mark_p);
                             p.has_imag = imag_before;
                             break;
                         }
@@ -2618,6 +2656,8 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
 }
 
 // plan + upload + launch an ordered op list on buffer 0 of every rank in the set
+static int launch_plan(RankSet& rs, const OpPlan& plan);
+
 static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
     int rc = check_rankset(rs);
     if (rc) return rc;
@@ -2626,6 +2666,12 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
     OpPlan plan;
     rc = plan_ops(c0->n, c0->nl, c0->tile_bits, c0->low_bits, c0->threads, ops, plan);
     if (rc) return rc;
+    return launch_plan(rs, plan);
+}
+
+// upload + launch a planned op list on buffer 0 of every rank in the set
+static int launch_plan(RankSet& rs, const OpPlan& plan) {
+    int rc = VQE_OK;
     const std::vector<OpPass>& passes = plan.passes;
     // upload: [ops][mats][runs][scat tables]
     size_t off_ops = 0, off_mats = plan.dops.size() * sizeof(DevOp);
@@ -2806,6 +2852,67 @@ static int run_ops(vqe_ctx* c, const std::vector<HostOp>& ops) {
     return run_ops(rs, ops);
 }
 
+// ---- plan cache ------------------------------------------------------------------------------------
+// A VQE optimisation applies the SAME rotation program thousands of times with different angles.  The pass plan
+// (tile bit sets, segments, collapsed runs and their pattern sign masks, orbit bases, gather sets) depends only on the
+// masks and on which rotations are dropped (angle 0) or need the general path (|cos| < 0.3), so it is kept and only
+// the angle-dependent numbers are recomputed: the signed tangents, the (cos, sin) of every collapsed pattern and the
+// pending cosine products.  If a pattern whose angle vanished before does not vanish now (or vice versa) the plan is
+// rebuilt.
+struct PlanCache {
+    std::vector<uint64_t> x, z;
+    std::vector<int32_t> ny;
+    std::vector<uint8_t> cls;   // per rotation: 0 = angle 0 (dropped), 1 = fast
+    OpPlan plan;
+    bool valid = false;
+};
+static void free_plan_cache(PlanCache* pc) { delete pc; }
+
+// angles of the kept rotations (cos, sin, angle) -> angle-dependent fields of a cached plan; false: structure changed
+static bool refresh_plan(OpPlan& plan, const std::vector<double>& ang, const std::vector<double>& cs, const std::vector<double>& sn) {
+    if (plan.dops.size() != ang.size()) return false;
+    for (size_t k = 0; k < plan.dops.size(); ++k) {
+        DevOp& d = plan.dops[k];
+        double tn = sn[k] / cs[k];
+        if (d.k4 >> 1) tn = -tn;
+        d.s = tn;
+        plan.rot_cos[k] = cs[k];
+    }
+    for (const OpPlan::ColRecipe& rcp : plan.recipes) {
+        double scale = 0.0;
+        for (uint32_t q = 0; q < rcp.n_str; ++q) scale += fabs(ang[rcp.first_op + q]);
+        for (uint32_t pi = 0; pi < rcp.n_pat; ++pi) {
+            const OpPlan::ColPat& cp = plan.col_pats[rcp.pat_begin + pi];
+            double F = 0.0;
+            for (uint32_t q = 0; q < rcp.n_str; ++q) F += ((cp.signmask >> q) & 1u) ? -ang[rcp.first_op + q] : ang[rcp.first_op + q];
+            const bool active = fabs(F) > 1e-15 * scale;
+            if (active != (cp.ent >= 0)) return false;
+            if (active) {
+                plan.dents[cp.ent].c = cos(F);
+                plan.dents[cp.ent].s = sin(F);
+            }
+        }
+    }
+    for (OpPass& p : plan.passes) {
+        double pending = 1.0;
+        for (size_t si = p.sup_begin; si < p.sup_end; ++si) {
+            DevSuper& su = plan.dsupers[si];
+            if (su.sub_count == 0xffffffffu) continue;
+            for (uint32_t sb = 0; sb < su.sub_count; ++sb) {
+                const DevSub& sub = plan.dsubs[p.sub_begin + su.sub_begin + sb];
+                for (uint32_t w = 0; w < sub.len; ++w) pending *= plan.rot_cos[p.op_begin + sub.begin + w];
+            }
+            su.cscale = 1.0;
+            if (fabs(pending) < 1e-30) {
+                su.cscale = pending;
+                pending = 1.0;
+            }
+        }
+        p.pass_scale = pending;
+    }
+    return true;
+}
+
 static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const uint64_t* zmask, const int32_t* ny,
                           const double* angle) {
     int rc0 = check_rankset(rs);
@@ -2813,23 +2920,68 @@ static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const u
     vqe_ctx* c = rs.r[0];
     if (n_rot < 0 || (n_rot > 0 && (!xmask || !zmask || !ny || !angle))) return fail(VQE_ERR_INVALID, "null array");
     const uint64_t full = (1ull << c->n) - 1ull;
+    // angle-dependent numbers of the kept rotations, and the class of every rotation
+    std::vector<double> ang, cs, sn;
+    std::vector<uint8_t> cls(n_rot);
+    ang.reserve(n_rot);
+    cs.reserve(n_rot);
+    sn.reserve(n_rot);
+    bool all_fast = true;
+    for (int k = 0; k < n_rot; ++k) {
+        if (angle[k] == 0.0) {  // exact identity
+            cls[k] = 0;
+            continue;
+        }
+        const double cv = cos(angle[k]);
+        ang.push_back(angle[k]);
+        cs.push_back(cv);
+        sn.push_back(sin(angle[k]));
+        cls[k] = (xmask[k] != 0 && fabs(cv) >= 0.3) ? 1 : 2;
+        if (cls[k] == 2) all_fast = false;
+    }
+    PlanCache* pc = c->plan_cache;
+    const bool use_cache = env_int("VQE_PLAN_CACHE", 1) != 0;
+    if (use_cache && all_fast && pc && pc->valid && (int)pc->cls.size() == n_rot &&
+        memcmp(pc->cls.data(), cls.data(), n_rot) == 0 && memcmp(pc->x.data(), xmask, n_rot * sizeof(uint64_t)) == 0 &&
+        memcmp(pc->z.data(), zmask, n_rot * sizeof(uint64_t)) == 0 && memcmp(pc->ny.data(), ny, n_rot * sizeof(int32_t)) == 0) {
+        if (refresh_plan(pc->plan, ang, cs, sn)) return launch_plan(rs, pc->plan);
+        pc->valid = false;  // a pattern's angle (stopped) vanishing: rebuild below
+    }
     std::vector<HostOp> ops;
-    ops.reserve(n_rot);
+    ops.reserve(ang.size());
+    size_t j = 0;
     for (int k = 0; k < n_rot; ++k) {
         if ((xmask[k] | zmask[k]) & ~full) return fail(VQE_ERR_INVALID, "rotation %d: mask has bits >= n_qubits", k);
         if (popc64(xmask[k] & zmask[k]) != ny[k]) return fail(VQE_ERR_INVALID, "rotation %d: ny != popcount(x&z)", k);
-        if (angle[k] == 0.0) continue;  // exact identity
+        if (cls[k] == 0) continue;
         HostOp h = HostOp();
         h.kind = OP_ROT;
         h.x = xmask[k];
         h.z = zmask[k];
         h.ny = ny[k];
-        h.c = cos(angle[k]);
-        h.s = sin(angle[k]);
-        h.ang = angle[k];
+        h.c = cs[j];
+        h.s = sn[j];
+        h.ang = ang[j];
+        ++j;
         ops.push_back(h);
     }
-    return run_ops(rs, ops);
+    if (ops.empty()) return VQE_OK;
+    if (!(use_cache && all_fast)) return run_ops(rs, ops);
+    if (!pc) pc = c->plan_cache = new PlanCache();
+    pc->valid = false;
+    pc->plan = OpPlan();
+    int rc = plan_ops(c->n, c->nl, c->tile_bits, c->low_bits, c->threads, ops, pc->plan);
+    if (rc) return rc;
+    bool fast_only = pc->plan.cacheable && pc->plan.rot_cos.size() == pc->plan.dops.size();
+    for (const OpPass& p : pc->plan.passes) fast_only = fast_only && p.fast;
+    if (fast_only) {
+        pc->x.assign(xmask, xmask + n_rot);
+        pc->z.assign(zmask, zmask + n_rot);
+        pc->ny.assign(ny, ny + n_rot);
+        pc->cls = cls;
+        pc->valid = true;
+    }
+    return launch_plan(rs, pc->plan);
 }
 extern "C" int vqe_apply_pauli_rotations(vqe_ctx* c, int n_rot, const uint64_t* xmask, const uint64_t* zmask,
                                          const int32_t* ny, const double* angle) {

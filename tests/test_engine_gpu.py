@@ -109,6 +109,46 @@ def test_collapsed_runs_jw_excitations(engines, n, real_start):
         assert np.all(got[np.abs(ref) < 1e-13] == 0.0)
 
 
+def test_plan_cache_reuse_and_invalidation(engines):
+    """The pass plan of a rotation program is cached and re-used with new angles; it must be rebuilt when a collapsed
+    pattern stops (or starts) cancelling, when a rotation is dropped (angle 0) and when the masks change."""
+    from openvqe_b200.lowering import pack_operator, term_masks
+    from tests.helpers import jw_excitation
+    n = 12
+    rng = np.random.default_rng(77)
+    eng = engines(n)
+    xs, zs, nys, base = [], [], [], []
+    for cre, ann in (([7], [2]), ([8, 11], [0, 3]), ([6, 9], [1, 4])):
+        pk = pack_operator(jw_excitation(n, cre, ann))
+        xs += [int(v) for v in pk.x]; zs += [int(v) for v in pk.z]; nys += [int(v) for v in pk.ny]
+        base += [float(c) for c in pk.cre]
+    base = np.array(base)
+
+    def check(angles, masks=None):
+        mx, mz, mny = masks or (xs, zs, nys)
+        psi = random_state(rng, n)
+        eng.set_state(psi)
+        eng.apply_rotations(mx, mz, mny, angles)
+        ref = psi.copy()
+        for x, z, ny, a in zip(mx, mz, mny, angles):
+            if a != 0.0:
+                ref = orc.pauli_rotation(ref, x, z, ny, a)
+        assert np.max(np.abs(eng.get_state() - ref)) < TOL
+
+    check(0.2 * base)                      # builds the plan (every generator collapses to one pattern)
+    check(-0.55 * base)                    # same structure: cached plan, new angles
+    broken = 0.3 * base
+    broken[1] *= 0.25                      # the two strings of the single no longer cancel on |00>,|11>
+    check(broken)
+    check(0.4 * base)                      # ... and cancel again
+    dropped = 0.1 * base
+    dropped[3] = 0.0                       # one string of a double dropped
+    check(dropped)
+    x2, z2, ny2 = term_masks("XZY", [0, 5, 10], n)
+    check(np.append(0.2 * base, 0.7), (xs + [x2], zs + [z2], nys + [ny2]))   # other masks
+    check(0.2 * base)
+
+
 def test_structural_zeros_stay_exact(engines):
     """Amplitudes outside the reachable sector must remain exactly 0.0."""
     from openvqe_b200.lowering import term_masks
