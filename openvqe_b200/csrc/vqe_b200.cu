@@ -2218,8 +2218,17 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
         uint64_t need = 0, pat = 0, ctrl_glob = 0;
         size_t j = i;
         const bool fast0 = fast_eligible(ops[i]);
+        size_t tab_bytes = 0;  // shared-memory tables of the pass next to the 64 KiB tile (227 KiB per CTA at most)
         while (j < ops.size() && j - i < OPTAB_CAP) {
             if (fast_eligible(ops[j]) != fast0) break;  // a pass is either all-fast or general
+            {
+                // worst case per op: RotOp + its own segment descriptor + sub-run; a plane rotation brings its table
+                const size_t op_bytes = ops[j].kind == OP_PLANE
+                                            ? sizeof(RotOp) + sizeof(DevSuper) + sizeof(DevCol) + 4 + ops[j].ppat.size() * sizeof(DevColEntry)
+                                            : sizeof(RotOp) + sizeof(DevSuper) + sizeof(DevSub);
+                if (j > i && tab_bytes + op_bytes > 96 * 1024) break;
+                tab_bytes += op_bytes;
+            }
             const uint64_t xg = ops[j].x >> nl;
             uint64_t npat = pat;
             if (xg) {

@@ -194,3 +194,23 @@ def test_quccsd_templates_as_plane_rotations_equal_the_gate_list(gpu_required, n
     th2 = theta + [0.3]
     _hotpath.prepare_quccsd_state(eng, n, hf, odd, th2, use_tables=True)
     assert np.max(np.abs(eng.get_state() - orc.quccsd_state(n, hf, odd, th2))) < 1e-12
+
+
+def test_quccsd_many_excitations_on_few_qubits(gpu_required):
+    """Hundreds of excitation templates whose X-masks all fit one tile: the planner must cut passes by the size of
+    their shared-memory tables, not only by tile bits."""
+    from openvqe_b200 import _hotpath
+    from openvqe_b200.engine import Engine
+    n = 10
+    rng = np.random.default_rng(8)
+    ops = []
+    for _ in range(420):
+        i, j = sorted(rng.choice(5, size=2, replace=False).tolist())
+        a, b = sorted((5 + rng.choice(5, size=2, replace=False)).tolist())
+        ops.append(FermiOp(n, [a, b, i, j]))
+    theta = rng.uniform(-0.2, 0.2, size=len(ops)).tolist()
+    hf = 0b1111100000
+    eng = Engine(n)
+    _hotpath.prepare_quccsd_state(eng, n, hf, ops, theta, use_tables=True)
+    ref = orc.quccsd_state(n, hf, ops, theta)
+    assert np.max(np.abs(eng.get_state() - ref)) < 1e-11
