@@ -274,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
     # fermionic_adapt_vqe.py:77-122).  Pool = the 1 818 UCCSD generators of the workload (as T - T^dagger);
     # psi = the state of the last evaluation.  Not part of the timed steps above.
     pool_sweep = None
-    if rank == 0 and not args.no_pool:
+    if rank == 0 and world == 1 and not args.no_pool:
         from openvqe_b200.engine import BUF_PSI, BUF_SIGMA
         n_gen = int(owner.max()) + 1
         offs = np.zeros(n_gen + 1, dtype=np.int32)
@@ -331,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
     # (gate-defined ansatz of reference get_energy_qucc.py:11-56; every excitation template is applied as one
     # tabulated plane rotation).  One gate-by-gate evaluation is timed beside it for comparison.
     quccsd = None
-    if rank == 0 and not args.no_pool:
+    if rank == 0 and world == 1 and not args.no_pool:
         from openvqe_b200.ucc_family.get_energy_qucc import EnergyUCC as EnergyQUCC
 
         class _Exc:
