@@ -86,6 +86,12 @@ int vqe_copy_buffer(vqe_ctx* ctx, int dst_buf, int src_buf);
 int vqe_apply_pauli_rotations(vqe_ctx* ctx, int n_rot, const uint64_t* xmask, const uint64_t* zmask,
                               const int32_t* ny, const double* angle);
 
+/* The same ordered product on any buffer of the context (VQE_BUF_*).  Used by the opt-in adjoint gradient
+ * (openvqe_b200/_hotpath.py: ucc_energy_and_gradient), whose co-state H|psi> lives in VQE_BUF_SIGMA; the reference
+ * differentiates by finite differences only (get_energy_ucc.py:158-166). */
+int vqe_apply_pauli_rotations_buf(vqe_ctx* ctx, int buf, int n_rot, const uint64_t* xmask, const uint64_t* zmask,
+                                  const int32_t* ny, const double* angle);
+
 /* Gate-level circuit (reference qubit numbering, qubit 0 = MSB).  q1 is used by CNOT only.
  * Replaces the QUCCSD excitation circuits of openvqe/common_files/circuit.py:13-106 as
  * executed at get_energy_qucc.py:50-55. */

@@ -209,6 +209,83 @@ def snap_ties(values, rel=1e-12, zero_tol=ZERO_TOL):
     return vals
 
 
+def _strings_commute(x, z):
+    """True when the Pauli strings (x_k, z_k) commute pairwise."""
+    n = len(x)
+    for a in range(n):
+        for b in range(a + 1, n):
+            if (bin(int(x[a]) & int(z[b])).count("1") + bin(int(z[a]) & int(x[b])).count("1")) & 1:
+                return False
+    return True
+
+
+def ucc_energy_and_gradient(theta, hamiltonian_sp, cluster_ops_sp, hf_init_sp, device=None):
+    """E(theta) and dE/dtheta of the Trotterised UCC ansatz by ADJOINT differentiation: one forward state preparation,
+    the co-state lambda = H psi, then one reverse sweep that peels the generators off both vectors,
+
+        dE/dtheta_j = 2 Re <lambda_j| (-i G_j) |psi_j> = 2 Im <lambda_j| G_j |psi_j>,
+        psi_{j-1} = U_j^-1 psi_j,   lambda_{j-1} = U_j^-1 lambda_j,
+
+    instead of the n+1 energy evaluations of the reference's finite differences (get_energy_ucc.py:158-166).  A
+    generator whose strings do not commute is peeled string by string (the derivative of the ordered product).  Opt-in
+    (SURVEY.md section 8f item 2): it changes the optimiser's trajectory at the level of the finite-difference error,
+    so the drop-in drivers use it only when VQE_B200_ADJOINT=1."""
+    from .lowering import PackedTerms
+    engine = get_engine(hamiltonian_sp.nbqbits, device)
+    n = hamiltonian_sp.nbqbits
+    m = min(len(cluster_ops_sp), len(theta))
+    th = np.asarray(theta, dtype=np.float64)
+    grad = np.zeros(len(theta), dtype=np.float64)
+    prepare_ucc_state(engine, cluster_ops_sp, hf_init_sp, theta)
+    ps = engine.paulisum(hamiltonian_sp)
+    energy = float(engine.expectation(ps).real)
+    if m == 0:
+        return energy, grad
+    engine.apply_paulisum(ps, dst=BUF_SIGMA, src=BUF_PSI)
+    for j in range(m - 1, -1, -1):
+        p = packed(cluster_ops_sp[j])
+        keep = (p.cre != 0) | (p.cim != 0)
+        x, z, ny, c = p.x[keep], p.z[keep], p.ny[keep], p.cre[keep]
+        if len(x) == 0:
+            continue
+        blocks = [slice(0, len(x))] if _strings_commute(x, z) else [slice(k, k + 1) for k in range(len(x) - 1, -1, -1)]
+        for blk in blocks:
+            bx, bz, bny, bc = x[blk], z[blk], ny[blk], c[blk]
+            op = PackedTerms(n, bx, bz, bny, bc, np.zeros_like(bc), np.array([0, len(bx)], dtype=np.int32))
+            ov = engine.pool_overlaps(op, bra=BUF_SIGMA, ket=BUF_PSI)[0]
+            grad[j] += 2.0 * ov.imag
+            # undo the block on both vectors: reverse order, negated angles
+            ang = -(th[j] * bc)[::-1]
+            rx, rz, rny = bx[::-1], bz[::-1], bny[::-1]
+            engine.apply_rotations(rx, rz, rny, ang, buf=BUF_PSI)
+            engine.apply_rotations(rx, rz, rny, ang, buf=BUF_SIGMA)
+    return energy, grad
+
+
+def adjoint_enabled() -> bool:
+    import os
+    return os.environ.get("VQE_B200_ADJOINT", "0") == "1"
+
+
+def adjoint_fun_jac(hamiltonian_sp, cluster_ops_sp, hf_init_sp, energies):
+    """(fun, jac) for scipy.optimize.minimize backed by ``ucc_energy_and_gradient`` (one adjoint sweep serves both)."""
+    last = {}
+
+    def both(theta):
+        x = np.array(theta, dtype=np.float64)
+        if "x" not in last or not np.array_equal(last["x"], x):
+            last["x"] = x
+            last["e"], last["g"] = ucc_energy_and_gradient(x, hamiltonian_sp, cluster_ops_sp, hf_init_sp)
+        return last["e"], last["g"]
+
+    def fun(theta):
+        e = both(theta)[0]
+        energies.append(e)
+        return e
+
+    return fun, lambda theta: both(theta)[1].copy()
+
+
 FD_STEP = 1.4901161193847656e-08  # scipy's absolute 2-point step for BFGS with jac=None (sqrt of machine epsilon)
 
 

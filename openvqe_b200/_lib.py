@@ -25,7 +25,7 @@ SYMBOLS = [
     "vqe_create_shard", "vqe_shard_info", "vqe_shard_export", "vqe_shard_attach_ipc", "vqe_shard_attach_local",
     "vqe_shard_barrier", "vqe_shard_status", "vqe_group_apply_pauli_rotations", "vqe_group_apply_gates",
     "vqe_group_expectation", "vqe_group_apply_paulisum", "vqe_group_pool_overlaps", "vqe_plan_rotations",
-    "vqe_apply_plane_rotations", "vqe_scale_state",
+    "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf",
 ]
 IPC_HANDLE_BYTES = 64
 SHARD_FLAGS = 3
@@ -69,6 +69,7 @@ def load():
         "vqe_copy_buffer": (C.c_int, [vp, C.c_int, C.c_int]),
         "vqe_apply_pauli_rotations": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
         "vqe_apply_gates": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
+        "vqe_apply_pauli_rotations_buf": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
         "vqe_paulisum_create": (C.c_int, [vp, P(vp), C.c_int, vp, vp, vp, vp, vp]),
         "vqe_paulisum_destroy": (None, [vp]),
         "vqe_paulisum_groups": (C.c_int, [vp]),

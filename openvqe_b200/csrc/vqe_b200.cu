@@ -2665,7 +2665,7 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
 }
 
 // plan + upload + launch an ordered op list on buffer 0 of every rank in the set
-static int launch_plan(RankSet& rs, const OpPlan& plan);
+static int launch_plan(RankSet& rs, const OpPlan& plan, int buf = VQE_BUF_PSI);
 
 static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
     int rc = check_rankset(rs);
@@ -2679,8 +2679,13 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
 }
 
 // upload + launch a planned op list on buffer 0 of every rank in the set
-static int launch_plan(RankSet& rs, const OpPlan& plan) {
+static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
     int rc = VQE_OK;
+    for (vqe_ctx* c : rs.r) {
+        CK(cudaSetDevice(c->device));
+        rc = ensure_buf(c, buf);
+        if (rc) return rc;
+    }
     const std::vector<OpPass>& passes = plan.passes;
     // upload: [ops][mats][runs][scat tables]
     size_t off_ops = 0, off_mats = plan.dops.size() * sizeof(DevOp);
@@ -2728,13 +2733,14 @@ static int launch_plan(RankSet& rs, const OpPlan& plan) {
     // imaginary halves.  All ranks of a sharded state see the same op list, so the flag stays consistent.
     std::vector<char> real_pass(passes.size(), 0);
     {
-        bool real = true;
+        bool real = buf == VQE_BUF_PSI;  // the flag is only tracked for the state buffer
         for (vqe_ctx* c : rs.r) real = real && c->psi_real;
         for (size_t p = 0; p < passes.size(); ++p) {
             real = real && passes[p].fast && !passes[p].has_imag;
             real_pass[p] = real ? 1 : 0;
         }
-        for (vqe_ctx* c : rs.r) c->psi_real = real;
+        if (buf == VQE_BUF_PSI)
+            for (vqe_ctx* c : rs.r) c->psi_real = real;
     }
     // one launch of the pass kernel on one rank (gg.n_need != 0: gather form over the tiles of the current chunk)
     auto launch_pass = [&](vqe_ctx* c, size_t p, const TileGeom& g, const Shards& sh, const GatherGeom& gg) -> int {
@@ -2805,7 +2811,7 @@ static int launch_plan(RankSet& rs, const OpPlan& plan) {
                 for (size_t k = 0; k < rs.r.size(); ++k) {
                     vqe_ctx* c = rs.r[k];
                     CK(cudaSetDevice(c->device));
-                    rc = make_geom(c, ps.tp, (const uint64_t*)(c->d_stage + scat_off[p]), VQE_BUF_PSI, gs[k], shs[k]);
+                    rc = make_geom(c, ps.tp, (const uint64_t*)(c->d_stage + scat_off[p]), buf, gs[k], shs[k]);
                     if (rc) return rc;
                     gs[k].n_tiles = nt;      // every rank walks ALL its tiles, chunk by chunk
                     gs[k].tile_first = t0;
@@ -2840,7 +2846,7 @@ static int launch_plan(RankSet& rs, const OpPlan& plan) {
             CK(cudaSetDevice(c->device));
             TileGeom g;
             Shards sh;
-            rc = make_geom(c, ps.tp, (const uint64_t*)(c->d_stage + scat_off[p]), VQE_BUF_PSI, g, sh);
+            rc = make_geom(c, ps.tp, (const uint64_t*)(c->d_stage + scat_off[p]), buf, g, sh);
             if (rc) return rc;
             if (g.n_tiles == 0) continue;
             rc = launch_pass(c, p, g, sh, no_gather);
@@ -2923,9 +2929,10 @@ static bool refresh_plan(OpPlan& plan, const std::vector<double>& ang, const std
 }
 
 static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const uint64_t* zmask, const int32_t* ny,
-                          const double* angle) {
+                          const double* angle, int buf = VQE_BUF_PSI) {
     int rc0 = check_rankset(rs);
     if (rc0) return rc0;
+    if (buf < 0 || buf > 2) return fail(VQE_ERR_INVALID, "bad buffer id %d", buf);
     vqe_ctx* c = rs.r[0];
     if (n_rot < 0 || (n_rot > 0 && (!xmask || !zmask || !ny || !angle))) return fail(VQE_ERR_INVALID, "null array");
     const uint64_t full = (1ull << c->n) - 1ull;
@@ -2953,7 +2960,7 @@ static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const u
     if (use_cache && all_fast && pc && pc->valid && (int)pc->cls.size() == n_rot &&
         memcmp(pc->cls.data(), cls.data(), n_rot) == 0 && memcmp(pc->x.data(), xmask, n_rot * sizeof(uint64_t)) == 0 &&
         memcmp(pc->z.data(), zmask, n_rot * sizeof(uint64_t)) == 0 && memcmp(pc->ny.data(), ny, n_rot * sizeof(int32_t)) == 0) {
-        if (refresh_plan(pc->plan, ang, cs, sn)) return launch_plan(rs, pc->plan);
+        if (refresh_plan(pc->plan, ang, cs, sn)) return launch_plan(rs, pc->plan, buf);
         pc->valid = false;  // a pattern's angle (stopped) vanishing: rebuild below
     }
     std::vector<HostOp> ops;
@@ -2975,7 +2982,12 @@ static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const u
         ops.push_back(h);
     }
     if (ops.empty()) return VQE_OK;
-    if (!(use_cache && all_fast)) return run_ops(rs, ops);
+    if (!(use_cache && all_fast)) {
+        OpPlan plan;
+        int rcp = plan_ops(c->n, c->nl, c->tile_bits, c->low_bits, c->threads, ops, plan);
+        if (rcp) return rcp;
+        return launch_plan(rs, plan, buf);
+    }
     if (!pc) pc = c->plan_cache = new PlanCache();
     pc->valid = false;
     pc->plan = OpPlan();
@@ -2990,13 +3002,20 @@ static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const u
         pc->cls = cls;
         pc->valid = true;
     }
-    return launch_plan(rs, pc->plan);
+    return launch_plan(rs, pc->plan, buf);
 }
 extern "C" int vqe_apply_pauli_rotations(vqe_ctx* c, int n_rot, const uint64_t* xmask, const uint64_t* zmask,
                                          const int32_t* ny, const double* angle) {
     RankSet rs;
     rs.r.push_back(c);
     return rotations_impl(rs, n_rot, xmask, zmask, ny, angle);
+}
+// the same ordered product applied to any of the context's buffers (adjoint gradient: the co-state lives in sigma)
+extern "C" int vqe_apply_pauli_rotations_buf(vqe_ctx* c, int buf, int n_rot, const uint64_t* xmask, const uint64_t* zmask,
+                                             const int32_t* ny, const double* angle) {
+    RankSet rs;
+    rs.r.push_back(c);
+    return rotations_impl(rs, n_rot, xmask, zmask, ny, angle, buf);
 }
 // Host-only view of the pass planner (no CUDA call): how an ordered rotation list is cut into tile passes for
 // a state of n_qubits with n_global rank bits.  Used by the CPU tests of the sharding logic and by bench.py to

@@ -77,15 +77,19 @@ class Engine:
         _lib.check(self._lib.vqe_copy_buffer(self.handle, dst, src))
 
     # -- state preparation ---------------------------------------------------
-    def apply_rotations(self, x, z, ny, angles):
-        """psi <- prod_k exp(-i angles[k] P_k) psi, k = 0 first."""
+    def apply_rotations(self, x, z, ny, angles, buf=BUF_PSI):
+        """buf <- prod_k exp(-i angles[k] P_k) buf, k = 0 first (buf = the state unless told otherwise)."""
         x = np.ascontiguousarray(x, dtype=np.uint64)
         z = np.ascontiguousarray(z, dtype=np.uint64)
         ny = np.ascontiguousarray(ny, dtype=np.int32)
         a = np.ascontiguousarray(angles, dtype=np.float64)
         if not (x.shape == z.shape == ny.shape == a.shape):
             raise ValueError("rotation arrays differ in length")
-        _lib.check(self._lib.vqe_apply_pauli_rotations(self.handle, int(x.shape[0]), _ptr(x), _ptr(z), _ptr(ny), _ptr(a)))
+        if buf == BUF_PSI:
+            _lib.check(self._lib.vqe_apply_pauli_rotations(self.handle, int(x.shape[0]), _ptr(x), _ptr(z), _ptr(ny), _ptr(a)))
+        else:
+            _lib.check(self._lib.vqe_apply_pauli_rotations_buf(self.handle, int(buf), int(x.shape[0]), _ptr(x), _ptr(z),
+                                                               _ptr(ny), _ptr(a)))
 
     def apply_gates(self, kinds, q0, q1, angles):
         k = np.ascontiguousarray(kinds, dtype=np.int32)

@@ -47,6 +47,9 @@ class EnergyUCC:
             lambda theta: _hotpath.ucc_energy(theta, hamiltonian_sp, cluster_ops_sp, hf_init_sp), energies_1)
         fun2, jac2 = _hotpath.distributed_fd(
             lambda theta: _hotpath.ucc_energy(theta, hamiltonian_sp, pool_generator, hf_init_sp), energies_2)
+        if _hotpath.adjoint_enabled():  # opt-in: analytic gradients from one adjoint sweep (not the reference's trajectory)
+            fun1, jac1 = _hotpath.adjoint_fun_jac(hamiltonian_sp, cluster_ops_sp, hf_init_sp, energies_1)
+            fun2, jac2 = _hotpath.adjoint_fun_jac(hamiltonian_sp, pool_generator, hf_init_sp, energies_2)
         opt_result1 = scipy.optimize.minimize(
             fun1, x0=theta_current1, jac=jac1, method=method, tol=tolerance, options={"maxiter": 50000, "disp": True})
         opt_result2 = scipy.optimize.minimize(

@@ -214,3 +214,38 @@ def test_quccsd_many_excitations_on_few_qubits(gpu_required):
     _hotpath.prepare_quccsd_state(eng, n, hf, ops, theta, use_tables=True)
     ref = orc.quccsd_state(n, hf, ops, theta)
     assert np.max(np.abs(eng.get_state() - ref)) < 1e-11
+
+
+def test_adjoint_gradient_matches_finite_differences(gpu_required, h2):
+    """Opt-in adjoint gradient (one forward + one reverse sweep) against central differences of the energy entry
+    point, for generators with commuting strings (sUPCCGSD) and with non-commuting strings (spin-complement GSD)."""
+    from openvqe_b200 import _hotpath
+    ham = h2["_ham"]
+    rng = np.random.default_rng(21)
+    for key, count in (("supccgsd_ansatz", 12), ("spin_complement_gsd", 14)):
+        ops = [op * 1j if key == "spin_complement_gsd" else op for op in pool_from_json(8, h2[key])]
+        ops = [op for op in ops if any(abs(complex(t.coeff)) > 0 for t in op.terms)][:count]
+        if key == "spin_complement_gsd":  # generators must be Hermitian with real coefficients, as algorithms/ucc.py:31 makes them
+            ops = [Ham(8, [T((complex(t.coeff)).real, t.op, t.qbits) for t in op.terms]) for op in ops]
+        theta = rng.uniform(-0.4, 0.4, size=len(ops))
+        e, g = _hotpath.ucc_energy_and_gradient(theta, ham, ops, h2["hf_init_sp"])
+        assert abs(e - orc.ucc_action(theta, ham, ops, h2["hf_init_sp"])) < TOL
+        h = 1e-5
+        for j in range(len(ops)):
+            tp, tm = theta.copy(), theta.copy()
+            tp[j] += h
+            tm[j] -= h
+            fd = (orc.ucc_action(tp, ham, ops, h2["hf_init_sp"]) - orc.ucc_action(tm, ham, ops, h2["hf_init_sp"])) / (2 * h)
+            assert abs(g[j] - fd) < 5e-9, (key, j, g[j], fd)
+
+
+def test_adjoint_opt_in_reaches_the_same_minimum(gpu_required, h2, monkeypatch):
+    ham = h2["_ham"]
+    ops = pool_from_json(8, h2["supccgsd_ansatz"])[:6]
+    from openvqe_b200.ucc_family.get_energy_ucc import EnergyUCC
+    th0 = [0.01] * len(ops)
+    _, res_fd = quiet(EnergyUCC().get_energies, ham, ops, ops, h2["hf_init_sp"], th0, th0, h2["fci"])
+    monkeypatch.setenv("VQE_B200_ADJOINT", "1")
+    it_ad, res_ad = quiet(EnergyUCC().get_energies, ham, ops, ops, h2["hf_init_sp"], th0, th0, h2["fci"])
+    assert abs(min(res_fd["energies_1"]) - it_ad["minimum_energy_result1_guess"][0]) < 1e-6
+    assert len(res_ad["energies_1"]) < len(res_fd["energies_1"]) / 3     # no finite-difference evaluations
