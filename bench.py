@@ -64,12 +64,18 @@ class ClockSampler:
 
     def __init__(self, device):
         self.proc = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            pass
+        for interval in ("50", "100"):  # 100 ms is the proven setting; 50 gives more samples inside a short timed region
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.FIELDS,
+                                              "--format=csv,noheader,nounits", "-lms", interval],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except OSError:
+                self.proc = None
+                break
+            time.sleep(0.15)
+            if self.proc.poll() is None:
+                break  # still looping: accepted
+            self.proc = None
 
     def stop(self):
         if self.proc is None:
