@@ -1531,6 +1531,15 @@ static TilePlan make_plan(int nl, uint64_t need_mask, int tbits_max, int low_bit
     return tp;
 }
 // capacity test used by the pass builders: do these local bits (plus the fixed low bits) fit?
+static bool plan_fits(uint64_t need_local, uint64_t lowmask, int tbits_max, int nl, bool vbit);
+// The fixed low tile bits are a coalescing preference (512-byte segments), not a requirement: an operator with many
+// X/Y letters on high qubits gets a tile with a smaller floor (shorter segments).  Largest floor <= lb_max for which
+// `need_local` fits the tile, or -1 when it cannot fit at all (more X/Y letters than tile bits).
+static int fit_low_bits(uint64_t need_local, int lb_max, int tbits_max, int nl, bool vbit) {
+    for (int lb = lb_max; lb >= 0; --lb)
+        if (plan_fits(need_local, (1ull << lb) - 1ull, tbits_max, nl, vbit)) return lb;
+    return -1;
+}
 static bool plan_fits(uint64_t need_local, uint64_t lowmask, int tbits_max, int nl, bool vbit) {
     return popc64(need_local | lowmask) <= std::min(tbits_max - (vbit ? 1 : 0), nl);
 }
@@ -2214,10 +2223,18 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
     const int lb = std::min(low_bits, std::min(tile_bits, nl));
     const uint64_t lowmask = (1ull << lb) - 1ull;
     (void)n;
+    const int lb_default = lb;
+    const uint64_t lowmask_default = lowmask;
     while (i < ops.size()) {
         uint64_t need = 0, pat = 0, ctrl_glob = 0;
         size_t j = i;
         const bool fast0 = fast_eligible(ops[i]);
+        // low-bit floor of this pass: the default unless the first operation alone needs more room
+        int lb = fit_low_bits(ops[i].x & lfull, lb_default, tile_bits, nl, (ops[i].x >> nl) != 0);
+        if (lb < 0)
+            return fail(VQE_ERR_INVALID, "operation %zu touches %d local X-bits, more than a %d-bit tile can hold", i,
+                        popc64(ops[i].x & lfull), std::min(tile_bits, nl));
+        const uint64_t lowmask = lb == lb_default ? lowmask_default : ((1ull << lb) - 1ull);
         size_t tab_bytes = 0;  // shared-memory tables of the pass next to the 64 KiB tile (227 KiB per CTA at most)
         while (j < ops.size() && j - i < OPTAB_CAP) {
             if (fast_eligible(ops[j]) != fast0) break;  // a pass is either all-fast or general
@@ -3278,15 +3295,17 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             if (!done[g]) { seed = g; break; }
         pat = xs[seed] >> nl;
         need = xs[seed] & lfull;
-        if (!plan_fits(need, lowmask, tbits_max, nl, pat != 0))
+        const int lb_pass = fit_low_bits(need, lb, tbits_max, nl, pat != 0);  // smaller floor for wide seeds
+        if (lb_pass < 0)
             return fail(VQE_ERR_INVALID, "Pauli term with %d local X/Y letters exceeds the %d-bit tile",
                         popc64(need), std::min(tbits_max, nl));
+        const uint64_t lowmask_pass = (1ull << lb_pass) - 1ull;
         std::vector<size_t> open;  // open groups of this pattern
         for (size_t g = 0; g < xs.size(); ++g)
             if (!done[g] && (xs[g] >> nl) == pat) open.push_back(g);
         const int cap_bits = std::min(tbits_max - (pat ? 1 : 0), nl);
         for (;;) {
-            const uint64_t have = need | lowmask;
+            const uint64_t have = need | lowmask_pass;
             if (popc64(have) >= cap_bits) break;
             // gain of every single bit: open groups that become fully covered
             int best_bit = -1;
@@ -3318,7 +3337,7 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             need |= xs[best_g] & lfull;
         }
         PSPass p;
-        p.tp = make_plan(nl, need, tbits_max, lb, pat);
+        p.tp = make_plan(nl, need, tbits_max, lb_pass, pat);
         std::vector<size_t> members;
         size_t n_terms_pass = 0;
         // everything inside the final tile mask (within the per-pass table capacity); the seed always goes first
@@ -3948,7 +3967,7 @@ static int pool_impl(RankSet& rs, int bra, int ket, int n_ops, const int32_t* op
             subs[q].need |= x[k] & lfull;
         }
         for (size_t q = first; q < subs.size(); ++q)
-            if (!plan_fits(subs[q].need, lowmask, tbm, nl, subs[q].pat != 0))
+            if (fit_low_bits(subs[q].need, lb, tbm, nl, subs[q].pat != 0) < 0)
                 return fail(VQE_ERR_INVALID, "pool operator %d spans %d local X-bits, more than the tile holds", o,
                             popc64(subs[q].need));
     }
@@ -3957,17 +3976,22 @@ static int pool_impl(RankSet& rs, int bra, int ket, int n_ops, const int32_t* op
     while (remaining) {
         uint64_t acc = 0, pat = 0;
         std::vector<size_t> members;
+        int lb_pass = lb;
+        uint64_t lowmask_pass = lowmask;
         for (size_t q = 0; q < subs.size(); ++q) {
             if (done[q]) continue;
-            if (members.empty()) pat = subs[q].pat;
-            else if (subs[q].pat != pat) continue;
+            if (members.empty()) {
+                pat = subs[q].pat;
+                lb_pass = fit_low_bits(subs[q].need, lb, tbm, nl, pat != 0);  // >= 0, checked above
+                lowmask_pass = (1ull << lb_pass) - 1ull;
+            } else if (subs[q].pat != pat) continue;
             uint64_t u = acc | subs[q].need;
-            if (!plan_fits(u, lowmask, tbm, nl, pat != 0)) continue;
+            if (!plan_fits(u, lowmask_pass, tbm, nl, pat != 0)) continue;
             acc = u;
             members.push_back(q);
             done[q] = 1;
         }
-        TilePlan tp = make_plan(nl, acc, tbm, lb, pat);
+        TilePlan tp = make_plan(nl, acc, tbm, lb_pass, pat);
         for (size_t q = 0; q < subs.size(); ++q) {
             if (done[q] || subs[q].pat != pat) continue;
             if ((subs[q].need & ~tp.tile_mask) == 0) {

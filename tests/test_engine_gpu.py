@@ -284,3 +284,38 @@ def test_error_paths(engines):
         eng.apply_rotations([16], [0], [0], [0.1])  # mask outside the register
     with pytest.raises(VQEError):
         eng.apply_rotations([1], [1], [0], [0.1])  # ny inconsistent with masks
+
+
+@pytest.mark.parametrize("n", [13, 16, 18])
+def test_wide_pauli_strings_get_a_smaller_low_bit_floor(engines, n):
+    """Strings with 8-12 X/Y letters on high qubits (eight-letter qubit pools, generic circuits) do not fit a tile
+    with 5 fixed low bits: the planner gives such a pass shorter contiguous segments instead of refusing."""
+    from openvqe_b200.engine import BUF_SIGMA
+    from openvqe_b200.lowering import pack_pool, term_masks
+    rng = np.random.default_rng(3100 + n)
+    eng = engines(n)
+    psi = random_state(rng, n)
+    eng.set_state(psi)
+    ref = psi.copy()
+    xs, zs, nys, angs, terms = [], [], [], [], []
+    for k in range(14):
+        w = int(rng.integers(8, min(n - 2, 12) + 1))
+        qb = sorted(rng.choice(n - 2, size=w, replace=False).tolist())       # qubits 0 .. n-3: the high index bits
+        op = "".join(rng.choice(list("XY"), size=w))
+        x, z, ny = term_masks(op, qb, n)
+        a = float(rng.uniform(-0.6, 0.6))
+        xs.append(x); zs.append(z); nys.append(ny); angs.append(a)
+        terms.append(T(float(rng.normal()), op, qb))
+        ref = orc.pauli_rotation(ref, x, z, ny, a)
+    eng.apply_rotations(xs, zs, nys, angs)
+    assert np.max(np.abs(eng.get_state() - ref)) < TOL
+    ham = Ham(n, terms, 0.1)
+    got = eng.expectation(eng.paulisum(ham))
+    assert abs(got.real - orc.expectation(ref, ham)) < 1e-11 and abs(got.imag) < 1e-11
+    eng.apply_paulisum(eng.paulisum(ham))
+    assert np.max(np.abs(eng.get_state(BUF_SIGMA) - orc.apply_pauli_sum(ref, ham))) < 1e-11
+    pool = [Ham(n, [T(1j * t.coeff, t.op, t.qbits)]) for t in terms[:6]]
+    ov = eng.pool_overlaps(pack_pool(pool))
+    sig = orc.apply_pauli_sum(ref, ham)
+    want = np.array([np.vdot(sig, orc.apply_pauli_sum(ref, op)) for op in pool])
+    assert np.max(np.abs(ov - want)) < 1e-11
