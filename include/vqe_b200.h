@@ -197,6 +197,13 @@ int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int low_bits, 
                        const uint64_t* zmask, const int32_t* ny, const double* angle, int cap, int32_t* n_passes,
                        int32_t* pass_kind, uint64_t* pass_pattern, int32_t* pass_n_ops, uint64_t* pass_tile_mask);
 
+/* Host-only view of the Pauli-sum planner (no CUDA call): X-mask grouping and packing of the groups into tile
+ * passes (what vqe_paulisum_create builds).  *n_groups = distinct X-masks, *n_passes = state sweeps per evaluation;
+ * per pass (at most `cap` written): number of groups, number of terms, tile-bit mask. */
+int vqe_plan_paulisum(int n_qubits, int n_global, int tile_bits, int low_bits, int n_terms, const uint64_t* xmask,
+                      const uint64_t* zmask, const int32_t* ny, const double* cre, const double* cim, int32_t* n_groups,
+                      int32_t* n_passes, int cap, int32_t* pass_groups, int32_t* pass_terms, uint64_t* pass_tile_mask);
+
 /* Raw device pointer / stream of a buffer. */
 int vqe_buffer_ptr(vqe_ctx* ctx, int buf, void** dev_ptr, uint64_t* n_amplitudes);
 int vqe_synchronize(vqe_ctx* ctx);

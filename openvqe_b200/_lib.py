@@ -25,7 +25,7 @@ SYMBOLS = [
     "vqe_create_shard", "vqe_shard_info", "vqe_shard_export", "vqe_shard_attach_ipc", "vqe_shard_attach_local",
     "vqe_shard_barrier", "vqe_shard_status", "vqe_group_apply_pauli_rotations", "vqe_group_apply_gates",
     "vqe_group_expectation", "vqe_group_apply_paulisum", "vqe_group_pool_overlaps", "vqe_plan_rotations",
-    "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf",
+    "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf", "vqe_plan_paulisum",
 ]
 IPC_HANDLE_BYTES = 64
 SHARD_FLAGS = 3
@@ -99,6 +99,8 @@ def load():
         "vqe_scale_state": (C.c_int, [vp, C.c_int, dbl, dbl]),
         "vqe_plan_rotations": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int,
                                          vp, vp, vp, vp, vp]),
+        "vqe_plan_paulisum": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp,
+                                        C.c_int, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

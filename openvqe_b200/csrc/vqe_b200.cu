@@ -3070,6 +3070,27 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
         if (pass_n_ops) pass_n_ops[p] = (int32_t)(plan.passes[p].op_end - plan.passes[p].op_begin);
         if (pass_tile_mask) pass_tile_mask[p] = plan.passes[p].tp.tile_mask;
     }
+    if (getenv("VQE_DEBUG_PLAN") && atoi(getenv("VQE_DEBUG_PLAN")) >= 3) {
+        for (size_t pi = 0; pi < plan.passes.size(); ++pi) {
+            const OpPass& p = plan.passes[pi];
+            size_t ncol = 0, norb = 0, items = 0, nsub = 0, nrot_orb = 0;
+            for (size_t si = p.sup_begin; si < p.sup_end; ++si) {
+                const DevSuper& su = plan.dsupers[si];
+                if (su.sub_count == 0xffffffffu) {
+                    ++ncol;
+                    const DevCol& co = plan.dcols[p.col_begin + su.sub_begin];
+                    items += (size_t)co.n_active << co.free_log;
+                } else {
+                    ++norb;
+                    nsub += su.sub_count;
+                    for (uint32_t sb = 0; sb < su.sub_count; ++sb) nrot_orb += plan.dsubs[p.sub_begin + su.sub_begin + sb].len;
+                }
+            }
+            fprintf(stderr, "[rotpass] %zu ops %zu supers %zu col %zu items %zu orb %zu subs %zu orbrots %zu lbits %d tbits %d scale %d\n", pi,
+                    p.op_end - p.op_begin, p.sup_end - p.sup_begin, ncol, items, norb, nsub, nrot_orb, p.tp.lbits, p.tp.tbits,
+                    p.pass_scale != 1.0);
+        }
+    }
     if (getenv("VQE_DEBUG_PLAN")) {
         size_t nruns = plan.dsubs.size(), nfast = 0, lens[9] = {0};
         for (const OpPass& p : plan.passes) nfast += p.fast ? 1 : 0;
@@ -3682,6 +3703,58 @@ extern "C" int vqe_paulisum_create(vqe_ctx* c, vqe_paulisum** out, int n_terms, 
         return rc;
     }
     *out = ps;
+    return VQE_OK;
+}
+// Host-only view of the Pauli-sum planner (no CUDA call): how a Pauli sum is grouped by X-mask and packed into tile
+// passes for a state of n_qubits with n_global rank bits.  Used by the CPU tests of the host logic and by the
+// profiling notes (per-pass statistics on stderr with VQE_DEBUG_PLAN >= 3).
+extern "C" int vqe_plan_paulisum(int n_qubits, int n_global, int tile_bits, int low_bits, int n_terms, const uint64_t* x,
+                                 const uint64_t* z, const int32_t* ny, const double* cre, const double* cim,
+                                 int32_t* n_groups, int32_t* n_passes, int cap, int32_t* pass_groups, int32_t* pass_terms,
+                                 uint64_t* pass_tile_mask) {
+    if (n_qubits < 1 || n_qubits > 40 || n_global < 0 || n_global > 6 || n_global >= n_qubits)
+        return fail(VQE_ERR_INVALID, "bad qubit counts");
+    if (tile_bits < 6 || tile_bits > 12) tile_bits = 12;
+    if (low_bits < 0 || low_bits > tile_bits) low_bits = 5;
+    vqe_ctx fake;
+    fake.n = n_qubits;
+    std::vector<HTerm> terms;
+    int rc = collect_terms(&fake, n_terms, x, z, ny, cre, cim, terms);
+    if (rc) return rc;
+    vqe_paulisum ps;
+    rc = build_paulisum(&ps, n_qubits, n_qubits - n_global, tile_bits, low_bits, 512, std::move(terms));
+    if (rc) return rc;
+    if (n_groups) *n_groups = ps.n_groups;
+    if (n_passes) *n_passes = (int32_t)ps.passes.size();
+    for (size_t p = 0; p < ps.passes.size(); ++p) {
+        const PSPass& pp = ps.passes[p];
+        if ((int)p < cap) {
+            if (pass_groups) pass_groups[p] = (int32_t)pp.groups.size();
+            if (pass_terms) pass_terms[p] = (int32_t)pp.terms_expect.size();
+            if (pass_tile_mask) pass_tile_mask[p] = pp.tp.tile_mask;
+        }
+        if (getenv("VQE_DEBUG_PLAN") && atoi(getenv("VQE_DEBUG_PLAN")) >= 3) {
+            size_t n_flatg = 0, n_colg = 0, n_clsg = 0, cls_terms = 0, diag_terms = 0, col_items = 0, aflat_groups = 0, aterm = 0;
+            for (size_t gi = 0; gi < pp.groups.size(); ++gi) {
+                const DevGroup& dg = pp.groups[gi];
+                if (dg.pad == 0xffffffffu) ++n_flatg;
+                else if (dg.pad) {
+                    ++n_colg;
+                    const DevGCol& co = pp.gcols[dg.pad - 1];
+                    col_items += (size_t)co.n_active << co.free_log;
+                } else if (dg.lx == 0) diag_terms += dg.n_even + dg.n_odd;
+                else {
+                    ++n_clsg;
+                    cls_terms += dg.n_even + dg.n_odd;
+                }
+                if (pp.aoff[gi + 1] > pp.aoff[gi]) ++aflat_groups;
+                else aterm += dg.n_even + dg.n_odd;
+            }
+            fprintf(stderr, "[pspass] %zu groups %zu terms %zu flatg %zu flats %zu colg %zu colitems %zu clsg %zu clsterms %zu diagterms %zu aflatg %zu aflats %zu aterms %zu lbits %d tbits %d vbit %d\n",
+                    p, pp.groups.size(), pp.terms_expect.size(), n_flatg, pp.flats.size(), n_colg, col_items, n_clsg, cls_terms,
+                    diag_terms, aflat_groups, pp.aflat.size(), aterm, pp.tp.lbits, pp.tp.tbits, (int)pp.tp.vbit);
+        }
+    }
     return VQE_OK;
 }
 extern "C" void vqe_paulisum_destroy(vqe_paulisum* ps) {
