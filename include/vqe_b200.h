@@ -204,6 +204,15 @@ int vqe_plan_paulisum(int n_qubits, int n_global, int tile_bits, int low_bits, i
                       const uint64_t* zmask, const int32_t* ny, const double* cre, const double* cim, int32_t* n_groups,
                       int32_t* n_passes, int cap, int32_t* pass_groups, int32_t* pass_terms, uint64_t* pass_tile_mask);
 
+/* Host-only interpreter of the "lean" passes of a Pauli sum (no CUDA call; test support): walks the entry tables
+ * vqe_paulisum_create would upload, with the decode routine the kernels use, on a HOST state of rank `rank`.
+ * *out_re = sum over the lean X-mask groups of <psi|O_g|psi>; sigma (optional, may be NULL) += O_lean psi;
+ * n_lean_terms / n_fat_terms = Pauli strings handled by lean passes / left to the general passes. */
+int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int tile_bits, int low_bits, int n_terms, const uint64_t* xmask,
+                        const uint64_t* zmask, const int32_t* ny, const double* cre, const double* cim,
+                        const double* psi_re_im, double* out_re, int32_t* n_lean_terms, int32_t* n_fat_terms,
+                        double* sigma_re_im);
+
 /* Raw device pointer / stream of a buffer. */
 int vqe_buffer_ptr(vqe_ctx* ctx, int buf, void** dev_ptr, uint64_t* n_amplitudes);
 int vqe_synchronize(vqe_ctx* ctx);

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vqe_create_shard", "vqe_shard_info", "vqe_shard_export", "vqe_shard_attach_ipc", "vqe_shard_attach_local",
     "vqe_shard_barrier", "vqe_shard_status", "vqe_group_apply_pauli_rotations", "vqe_group_apply_gates",
     "vqe_group_expectation", "vqe_group_apply_paulisum", "vqe_group_pool_overlaps", "vqe_plan_rotations",
-    "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf", "vqe_plan_paulisum",
+    "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf", "vqe_plan_paulisum", "vqe_debug_lean_host",
 ]
 IPC_HANDLE_BYTES = 64
 SHARD_FLAGS = 3
@@ -101,6 +101,8 @@ def load():
                                          vp, vp, vp, vp, vp]),
         "vqe_plan_paulisum": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp,
                                         C.c_int, vp, vp, vp]),
+        "vqe_debug_lean_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
+                                          P(dbl), P(i32), P(i32), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -579,8 +579,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    // bounded spin: a protocol error must never hang the GPU (the results would then be wrong and the tests say so)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t phase) {
+    // bounded spin: a protocol error must never hang the GPU.  Returns false on a timeout; every caller then raises the
+    // context's device error flag (vqe_ctx::d_err = 2), which vqe_synchronize / the reductions / vqe_shard_status report.
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         uint32_t ok;
         asm volatile(
@@ -588,8 +589,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(phase)
             : "memory");
-        if (ok) return;
+        if (ok) return true;
     }
+    return false;
 }
 __device__ __forceinline__ void tile_load_bulk(double2* tile, const Shards& src, const TileGeom& g, uint64_t base, uint64_t* bar) {
     const uint32_t ts = 1u << g.tbits;
@@ -785,7 +787,8 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
                                                      const DevSuper* __restrict__ supers, int n_supers,
                                                      const DevSub* __restrict__ subs, int n_subs,
                                                      const DevCol* __restrict__ cols, int n_cols,
-                                                     const DevColEntry* __restrict__ ents, int n_ents, double pass_scale) {
+                                                     const DevColEntry* __restrict__ ents, int n_ents, double pass_scale,
+                                                     int* __restrict__ err) {
     extern __shared__ double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     const bool four = (ts >> 1) == 4u * blockDim.x;  // host guarantees: 4 pairs (one orbit) per thread, or at most 1 pair
@@ -840,7 +843,7 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
             optab[r].t = flipsign(ops[r].s, __popcll(sbase & ops[r].zout));
         for (int r = threadIdx.x; r < n_cols; r += blockDim.x) scsign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
         if (bulk) {
-            mbar_wait(&s_mbar, mphase);
+            if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
             mphase ^= 1u;
         } else {
             cp_async_wait_all();
@@ -929,6 +932,153 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
         } else {
             tile_store_scaled_fast(tile, psi, g, ta, s_boff, base, pass_scale);
         }
+    }
+    if (bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores have landed
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-parallel tile base.  base = pdep(tile number, comp_mask): lane i owns the i-th set bit of comp_mask (found once
+// per kernel), a tile costs one shift/and per lane and two warp-wide OR reductions (REDUX) instead of a serial
+// bit loop in every thread.
+// ------------------------------------------------------------------------------------------
+struct BaseLane {
+    uint32_t pos;   // index-bit position of this lane's bit of comp_mask
+    uint32_t act;   // 0: comp_mask has fewer set bits than this lane's number
+};
+__device__ __forceinline__ BaseLane base_lane_init(const TileGeom& g) {
+    BaseLane bl;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t m = g.comp_mask;
+    for (uint32_t i = 0; i < lane && m; ++i) m &= m - 1;  // drop the lane lowest set bits
+    bl.act = m ? 1u : 0u;
+    bl.pos = m ? (uint32_t)(__ffsll((long long)m) - 1) : 0u;
+    return bl;
+}
+__device__ __forceinline__ uint64_t tile_base_warp(const TileGeom& g, const BaseLane& bl, uint64_t t) {
+    const uint64_t tnum = g.tile_first + t * g.tile_stride;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t bit = (bl.act && ((tnum >> lane) & 1ull)) ? (1ull << bl.pos) : 0ull;
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)bit);
+    const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(bit >> 32));
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_tile_col: passes that consist ONLY of collapsed runs / tabulated plane rotations (every pass of a UCCSD or
+// QUCCSD program).  A collapsed JW double excitation is 256 plane rotations per 4096-amplitude tile, so the kernel is
+// built around the per-run cost: 256-thread CTAs (one item per thread, three CTAs per SM, 8-warp barriers), the
+// descriptor read and the index deposit of run q+1 are issued BEFORE the barrier that ends run q, so the chain
+// between two barriers is  LDS pair -> 3 FP64 ops -> STS pair.
+// ------------------------------------------------------------------------------------------
+struct ColItem {
+    uint32_t l, lx;      // a-side tile index, X-mask
+    double c, sn;        // cos, signed sin
+    uint32_t imag, valid;
+    uint32_t items;      // items of the run (for the threads that own more than one)
+};
+__device__ __forceinline__ uint32_t col_deposit(const DevCol& co, uint32_t f) {
+    uint32_t l = f;
+    l += l & co.dpos[0];
+    l += l & co.dpos[1];
+    l += l & co.dpos[2];
+    l += l & co.dpos[3];
+    if (co.nd > 4) {
+        l += l & co.dpos[4];
+        l += l & co.dpos[5];
+    }
+    return l;
+}
+__device__ __forceinline__ ColItem col_prep(const DevCol* scol, const DevColEntry* sent, const uint32_t* scsign, int q, int n_cols,
+                                            uint32_t it) {
+    ColItem ci;
+    ci.valid = 0;
+    ci.l = ci.lx = ci.imag = ci.items = 0;
+    ci.c = 1.0;
+    ci.sn = 0.0;
+    if (q >= n_cols) return ci;
+    const DevCol& co = scol[q];
+    const uint32_t items = co.n_active << co.free_log;
+    ci.items = items;
+    if (it >= items) return ci;
+    const DevColEntry& en = sent[co.ent_begin + (it >> co.free_log)];
+    const uint32_t l = col_deposit(co, it & ((1u << co.free_log) - 1u)) | en.pat;
+    ci.l = l;
+    ci.lx = co.lx;
+    ci.c = en.c;
+    ci.sn = flipsign(en.s, scsign[q] + (uint32_t)__popc(l & co.lz));
+    ci.imag = co.imag;
+    ci.valid = 1;
+    return ci;
+}
+template <bool REAL>
+__device__ __forceinline__ void col_apply(double2* tile, const ColItem& ci) {
+    if (REAL) {
+        const double a = tile[ci.l].x, b = tile[ci.l ^ ci.lx].x;
+        tile[ci.l].x = fma(ci.c, a, -ci.sn * b);
+        tile[ci.l ^ ci.lx].x = fma(ci.c, b, ci.sn * a);
+    } else {
+        const double2 a = tile[ci.l], b = tile[ci.l ^ ci.lx];
+        double2 na, nb;
+        if (ci.imag) {  // a' = c a + i s b, b' = c b + i s a
+            na.x = fma(ci.c, a.x, -ci.sn * b.y); na.y = fma(ci.c, a.y, ci.sn * b.x);
+            nb.x = fma(ci.c, b.x, -ci.sn * a.y); nb.y = fma(ci.c, b.y, ci.sn * a.x);
+        } else {        // a' = c a - s b, b' = c b + s a
+            na.x = fma(ci.c, a.x, -ci.sn * b.x); na.y = fma(ci.c, a.y, -ci.sn * b.y);
+            nb.x = fma(ci.c, b.x, ci.sn * a.x); nb.y = fma(ci.c, b.y, ci.sn * a.y);
+        }
+        tile[ci.l] = na;
+        tile[ci.l ^ ci.lx] = nb;
+    }
+}
+template <bool REAL>
+__global__ void __launch_bounds__(256, 3) k_tile_col(Shards psi, TileGeom g, const DevCol* __restrict__ cols, int n_cols,
+                                                     const DevColEntry* __restrict__ ents, int n_ents, int* __restrict__ err) {
+    extern __shared__ double2 tile[];
+    const uint32_t ts = 1u << g.tbits;
+    DevCol* scol = (DevCol*)(tile + ts);
+    DevColEntry* sent = (DevColEntry*)(scol + n_cols);
+    uint32_t* scsign = (uint32_t*)(sent + n_ents);  // per tile: outside-tile Z parity of every run
+    __shared__ uint64_t s_boff[16];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const bool bulk = g.bulk != 0;
+    uint32_t mphase = 0;
+    if (bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
+    const TileAddr ta = tile_addr_init(g, s_boff);
+    for (int q = threadIdx.x; q < n_cols; q += blockDim.x) scol[q] = cols[q];
+    for (int q = threadIdx.x; q < n_ents; q += blockDim.x) sent[q] = ents[q];
+    const BaseLane bl = base_lane_init(g);
+    const uint32_t bd = blockDim.x;
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = tile_base_warp(g, bl, t);
+        const uint64_t sbase = base | g.sign_base;
+        __syncthreads();  // the previous tile has left shared memory (bulk store has read it); tables are in place
+        if (bulk) tile_load_bulk(tile, psi, g, base, &s_mbar);
+        else tile_load_async_fast(tile, psi, g, ta, s_boff, base);
+        for (int r = threadIdx.x; r < n_cols; r += bd) scsign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
+        __syncthreads();  // scsign visible
+        ColItem cur = col_prep(scol, sent, scsign, 0, n_cols, threadIdx.x);
+        if (bulk) {
+            if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
+            mphase ^= 1u;
+        } else {
+            cp_async_wait_all();
+            __syncthreads();
+        }
+        for (int q = 0; q < n_cols; ++q) {
+            const uint32_t items = cur.items;
+            // first item of this thread: prepared before the barrier; the next run's first item is prepared while
+            // this run's shared-memory loads are in flight
+            ColItem nxt = col_prep(scol, sent, scsign, q + 1, n_cols, threadIdx.x);
+            if (cur.valid) col_apply<REAL>(tile, cur);
+            for (uint32_t it = threadIdx.x + bd; it < items; it += bd) {
+                const ColItem ci = col_prep(scol, sent, scsign, q, n_cols, it);
+                col_apply<REAL>(tile, ci);
+            }
+            cur = nxt;
+            __syncthreads();
+        }
+        if (bulk) tile_store_bulk(tile, psi, g, base);
+        else tile_store_scaled_fast(tile, psi, g, ta, s_boff, base, 1.0);
     }
     if (bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores have landed
 }
@@ -1035,7 +1185,7 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
                                                         const DevGColEntry* __restrict__ gents, int n_gents,
                                                         const DevFlat* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout,
-                                                        double2* __restrict__ partial) {
+                                                        double2* __restrict__ partial, int* __restrict__ err) {
     extern __shared__ double2 tile[];
     __shared__ double red[64];
     const uint32_t ts = 1u << g.tbits;
@@ -1099,7 +1249,7 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
         for (int q = threadIdx.x; q < nfl; q += blockDim.x)
             s_ffr[q] = flipsign(s_flat[q].fr, __popcll(sbase & fzout[s_flat[q].zsel & 0xffffu]));
         if (g.bulk) {
-            mbar_wait(&s_mbar, mphase);
+            if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
             mphase ^= 1u;
         } else {
             cp_async_wait_all();
@@ -1453,6 +1603,256 @@ __global__ void __launch_bounds__(512) k_tile_pool(Shards bra, Shards ket, TileG
 }
 
 // ------------------------------------------------------------------------------------------
+// LEAN Pauli-sum passes.  An X-mask group of a real Hamiltonian whose Z-variants differ from the first string only
+//   (i) on the group's own X positions (XX/YY/XY families of one excitation), and
+//   (ii) by at most ONE further Z letter (number-operator dressing n_r of a one-body term)
+// is a function  F(l) = (-1)^parity(l & z_1) * [ beta_0(pi) + sum_r beta_r(pi) (-1)^(l_r) ]  of the occupation pattern pi
+// on the X positions: the host tabulates it per a-side pattern, drops the patterns where it vanishes (most of them:
+// particle-number and spin symmetry) and cuts every active pattern into ENTRIES of 256 (pattern, free index) pairs.
+// Entries live in global memory (read through L1 with warp-uniform 16-byte loads), so a lean pass needs no
+// shared-memory tables besides the tile: 3 CTAs of 256 threads per SM.
+//   expectation: one WARP per entry, 8 pairs per lane: index deposit and sign work once per 8 pairs;
+//   sigma = O psi: one THREAD per pair, groups separated by barriers (conflict-free, fixed accumulation order).
+// Everything is kept in the byte-offset domain (tile index * 16 < 65536) so that an index is used as an address.
+// ------------------------------------------------------------------------------------------
+struct DevFlat2 {           // 48 bytes = 3 x uint4
+    double fr;              // plain entry: 2 * beta_0(pattern); additive entry: 2.0 (the weight comes from the tables)
+    uint16_t lx16, lz16;    // X-mask | Z letters of the group's first string inside the tile        (byte offsets)
+    uint16_t pat16, zsel;   // a-side pattern (byte offset) | index into the pass's outside-tile Z masks
+    uint16_t hm16[4];       // deposit masks of the X positions for the lane's five free-index bits (byte-offset domain)
+    uint16_t jsign, tab;    // bit j = parity(o_j & z_1) | 0xffff: plain, else offset (doubles) of T_lo[32] in the table array
+    uint16_t hi0, bidx;     // additive: offset of this chunk's T_hi[8] | index of the pattern's per-tile constant
+    uint16_t o16[8];        // byte offset of free-index bits 5.. for j = 0..7 (chunk bits included)
+};
+static_assert(sizeof(DevFlat2) == 48, "DevFlat2 layout");
+struct DevAddPat {          // 16 bytes: per-tile constant of an additive pattern
+    double beta0;           // beta_0 + sum over outside-tile r of beta_r (-1)^(bit r of the tile base)
+    uint32_t out_begin, out_count;
+};
+struct DevAddOut {          // 16 bytes
+    double c;
+    uint64_t zrel;          // outside-tile Z mask relative to the group's first string
+};
+struct LeanUnit {           // decoded entry, per lane
+    uint32_t v;             // byte offset of the lane's a-side element for j = 0 (pattern included)
+    uint32_t lx16, s0, jsign, tab, hi0, bidx;
+    uint32_t o[8];
+    double fr;
+};
+__host__ __device__ __forceinline__ void lean_decode(const uint4& q0, const uint4& q1, const uint4& q2, uint32_t lane, LeanUnit& u) {
+#ifdef __CUDA_ARCH__
+    u.fr = __hiloint2double((int)q0.y, (int)q0.x);
+#else
+    uint64_t bits = ((uint64_t)q0.y << 32) | q0.x;
+    memcpy(&u.fr, &bits, 8);
+#endif
+    u.lx16 = q0.z & 0xffffu;
+    const uint32_t lz16 = q0.z >> 16, pat16 = q0.w & 0xffffu;
+    uint32_t v = lane << 4;
+    v += v & (q1.x & 0xffffu);
+    v += v & (q1.x >> 16);
+    v += v & (q1.y & 0xffffu);
+    v += v & (q1.y >> 16);
+    v |= pat16;
+    u.v = v;
+#ifdef __CUDA_ARCH__
+    u.s0 = (uint32_t)__popc(v & lz16);
+#else
+    u.s0 = (uint32_t)__builtin_popcount(v & lz16);
+#endif
+    u.jsign = q1.z & 0xffffu;
+    u.tab = q1.z >> 16;
+    u.hi0 = q1.w & 0xffffu;
+    u.bidx = q1.w >> 16;
+    u.o[0] = q2.x & 0xffffu; u.o[1] = q2.x >> 16;
+    u.o[2] = q2.y & 0xffffu; u.o[3] = q2.y >> 16;
+    u.o[4] = q2.z & 0xffffu; u.o[5] = q2.z >> 16;
+    u.o[6] = q2.w & 0xffffu; u.o[7] = q2.w >> 16;
+}
+
+// per-tile constants of the additive patterns (one thread per pattern, while the tile load is in flight)
+__device__ __forceinline__ void lean_betas(double* s_beta, const DevAddPat* __restrict__ addpat, int n_addpat,
+                                           const DevAddOut* __restrict__ addout, uint64_t sbase) {
+    for (int k = threadIdx.x; k < n_addpat; k += blockDim.x) {
+        const DevAddPat ap = addpat[k];
+        double b = ap.beta0;
+        for (uint32_t q = 0; q < ap.out_count; ++q) {
+            const DevAddOut ao = addout[ap.out_begin + q];
+            b += flipsign(ao.c, (uint32_t)__popcll(sbase & ao.zrel));
+        }
+        s_beta[k] = b;
+    }
+}
+
+template <bool REAL>
+__global__ void __launch_bounds__(256, 3) k_expect_lean(Shards psi, TileGeom g, const DevFlat2* __restrict__ flats, int n_flats,
+                                                        const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
+                                                        const DevAddPat* __restrict__ addpat, int n_addpat,
+                                                        const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
+                                                        int* __restrict__ err) {
+    extern __shared__ double2 tile[];
+    __shared__ double red[64];
+    __shared__ uint64_t s_boff[16];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const uint32_t ts = 1u << g.tbits;
+    double* s_beta = (double*)(tile + ts);
+    const bool bulk = g.bulk != 0;
+    uint32_t mphase = 0;
+    if (bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
+    const TileAddr ta = tile_addr_init(g, s_boff);
+    const BaseLane bl = base_lane_init(g);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // blockIdx.y splits the entry list (states with few tiles)
+    const int fper = (n_flats + gridDim.y - 1) / gridDim.y;
+    const int f0 = min(n_flats, (int)blockIdx.y * fper), f1 = min(n_flats, f0 + fper);
+    const char* tb = (const char*)tile;
+    double er = 0.0;
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = tile_base_warp(g, bl, t);
+        const uint64_t sbase = base | g.sign_base;
+        __syncthreads();  // previous tile fully consumed
+        if (bulk) tile_load_bulk(tile, psi, g, base, &s_mbar);
+        else tile_load_async_fast(tile, psi, g, ta, s_boff, base);
+        lean_betas(s_beta, addpat, n_addpat, addout, sbase);
+        if (bulk) {
+            if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
+            mphase ^= 1u;
+        } else {
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        for (int e = f0 + (int)warp; e < f1; e += (int)nw) {
+            const uint4* ep = reinterpret_cast<const uint4*>(flats + e);
+            const uint4 q0 = __ldg(ep), q1 = __ldg(ep + 1), q2 = __ldg(ep + 2);
+            LeanUnit u;
+            lean_decode(q0, q1, q2, lane, u);
+            const uint32_t sg = u.s0 + (uint32_t)__popcll(sbase & __ldg(fzout + (q0.w >> 16)));
+            double part = 0.0;
+            if (u.tab == 0xffffu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t off = u.v | u.o[j];
+                    double w;
+                    if (REAL) {
+                        w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
+                    } else {
+                        const double2 a = *reinterpret_cast<const double2*>(tb + off);
+                        const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
+                        w = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
+                    }
+                    part += flipsign(w, u.jsign >> j);
+                }
+            } else {
+                const double gl = s_beta[u.bidx] + __ldg(addtab + u.tab + lane);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t off = u.v | u.o[j];
+                    double w;
+                    if (REAL) {
+                        w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
+                    } else {
+                        const double2 a = *reinterpret_cast<const double2*>(tb + off);
+                        const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
+                        w = fma(b.x, a.x, b.y * a.y);
+                    }
+                    part = fma(flipsign(w, u.jsign >> j), gl + __ldg(addtab + u.hi0 + j), part);
+                }
+            }
+            er = fma(u.fr, flipsign(part, sg), er);
+        }
+    }
+    double2 sres = block_sum2(er, 0.0, red);
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
+}
+
+// sigma (+)= O psi for a lean pass.  The CTA holds the source tile and an accumulator tile (REAL: real parts only,
+// 32 KiB -> two CTAs per SM) and walks the groups in order: one thread per (pattern, free index) pair,
+//     acc[l ^ x] += G(l) psi[l],   acc[l] += G(l) psi[l ^ x]        (even-ny strings: the same weight both ways)
+// with a barrier between two groups (inside a group every accumulator element is touched by one thread).
+template <bool REAL>
+__global__ void __launch_bounds__(512, REAL ? 2 : 1) k_apply_lean(Shards src, Shards dst, TileGeom g, const DevFlat2* __restrict__ flats,
+                                                                  const uint32_t* __restrict__ goff, int n_groups,
+                                                                  const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
+                                                                  const DevAddPat* __restrict__ addpat, int n_addpat,
+                                                                  const DevAddOut* __restrict__ addout, int accumulate,
+                                                                  int* __restrict__ err) {
+    extern __shared__ double2 tile[];
+    __shared__ uint64_t s_boff[16];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const uint32_t ts = 1u << g.tbits;
+    double* accr = (double*)(tile + ts);              // REAL: ts doubles
+    double2* accc = (double2*)(tile + ts);            // else: ts double2
+    double* s_beta = REAL ? (accr + ts) : (double*)(accc + ts);
+    const bool bulk = g.bulk != 0;
+    uint32_t mphase = 0;
+    if (bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
+    const TileAddr ta = tile_addr_init(g, s_boff);
+    const BaseLane bl = base_lane_init(g);
+    const uint32_t bd = blockDim.x, lane = threadIdx.x & 31u;
+    const char* tb = (const char*)tile;
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = tile_base_warp(g, bl, t);
+        const uint64_t sbase = base | g.sign_base;
+        __syncthreads();  // previous tile written out
+        if (bulk) tile_load_bulk(tile, src, g, base, &s_mbar);
+        else tile_load_async_fast(tile, src, g, ta, s_boff, base);
+        for (uint32_t k = threadIdx.x; k < ts; k += bd) {
+            if (REAL) accr[k] = 0.0;
+            else accc[k] = make_double2(0.0, 0.0);
+        }
+        lean_betas(s_beta, addpat, n_addpat, addout, sbase);
+        if (bulk) {
+            if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
+            mphase ^= 1u;
+        } else {
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        for (int gi = 0; gi < n_groups; ++gi) {
+            const uint32_t e0 = __ldg(goff + gi), e1 = __ldg(goff + gi + 1);
+            const uint32_t items = (e1 - e0) << 8;
+            for (uint32_t it = threadIdx.x; it < items; it += bd) {
+                const uint32_t e = e0 + (it >> 8), j = (it >> 5) & 7u;
+                const uint4* ep = reinterpret_cast<const uint4*>(flats + e);
+                const uint4 q0 = __ldg(ep), q1 = __ldg(ep + 1), q2 = __ldg(ep + 2);
+                LeanUnit u;
+                lean_decode(q0, q1, q2, lane, u);
+                const uint32_t oj = (j & 1u) ? ((j & 2u) ? ((j & 4u) ? u.o[7] : u.o[3]) : ((j & 4u) ? u.o[5] : u.o[1]))
+                                             : ((j & 2u) ? ((j & 4u) ? u.o[6] : u.o[2]) : ((j & 4u) ? u.o[4] : u.o[0]));
+                const uint32_t off = u.v | oj, offb = off ^ u.lx16;
+                const uint32_t sg = u.s0 + (u.jsign >> j) + (uint32_t)__popcll(sbase & __ldg(fzout + (q0.w >> 16)));
+                double gw = 0.5 * u.fr;  // the expectation weight carries the factor 2 of the pair
+                if (u.tab != 0xffffu) gw *= s_beta[u.bidx] + __ldg(addtab + u.tab + lane) + __ldg(addtab + u.hi0 + j);
+                gw = flipsign(gw, sg);
+                if (REAL) {
+                    const double a = *reinterpret_cast<const double*>(tb + off), b = *reinterpret_cast<const double*>(tb + offb);
+                    accr[offb >> 4] = fma(gw, a, accr[offb >> 4]);
+                    accr[off >> 4] = fma(gw, b, accr[off >> 4]);
+                } else {
+                    const double2 a = *reinterpret_cast<const double2*>(tb + off), b = *reinterpret_cast<const double2*>(tb + offb);
+                    double2 ob = accc[offb >> 4], oa = accc[off >> 4];
+                    ob.x = fma(gw, a.x, ob.x); ob.y = fma(gw, a.y, ob.y);
+                    oa.x = fma(gw, b.x, oa.x); oa.y = fma(gw, b.y, oa.y);
+                    accc[offb >> 4] = ob;
+                    accc[off >> 4] = oa;
+                }
+            }
+            __syncthreads();
+        }
+        for (uint32_t k = threadIdx.x; k < ts; k += bd) {
+            double2* dp = amp_addr(g, dst, base, k);
+            double2 o = REAL ? make_double2(accr[k], 0.0) : accc[k];
+            if (accumulate) {
+                const double2 d = *dp;
+                o.x += d.x;
+                o.y += d.y;
+            }
+            *dp = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 struct TilePlan {
@@ -1714,9 +2114,15 @@ static int set_kernel_attrs(int device) {
     SET_SMEM(k_tile_ops);
     SET_SMEM(k_tile_rot<false>);
     SET_SMEM(k_tile_rot<true>);
+    SET_SMEM(k_tile_col<false>);
+    SET_SMEM(k_tile_col<true>);
     SET_SMEM(k_tile_expect<false>);
     SET_SMEM(k_tile_expect<true>);
     SET_SMEM(k_tile_apply);
+    SET_SMEM(k_expect_lean<false>);
+    SET_SMEM(k_expect_lean<true>);
+    SET_SMEM(k_apply_lean<false>);
+    SET_SMEM(k_apply_lean<true>);
     SET_SMEM(k_tile_pool);
 #undef SET_SMEM
     if (device >= 0 && device < 64) g_attr_done[device] = true;
@@ -1768,17 +2174,22 @@ static int create_ctx(vqe_ctx** out, int n_qubits, int n_global, int rank, int d
         if ((rc = set_kernel_attrs(device))) break;
         if ((rc = ensure_buf(c, VQE_BUF_PSI))) break;
         if ((rc = ensure_result(c, 64))) break;
+        // device error flag (mapped pinned host memory): 1 = a cross-rank barrier timed out, 2 = a bulk tile copy never
+        // signalled its mbarrier.  Checked by vqe_synchronize, the reductions and vqe_shard_status.
+        if (cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+            rc = fail(VQE_ERR_CUDA, "error flag allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        *c->h_err = 0;
+        if (cudaHostGetDevicePointer((void**)&c->d_err, c->h_err, 0) != cudaSuccess) {
+            rc = fail(VQE_ERR_CUDA, "cudaHostGetDevicePointer failed");
+            break;
+        }
         if (c->world > 1) {
             if (cudaMalloc((void**)&c->flags, MAX_RANKS * sizeof(uint64_t)) != cudaSuccess ||
                 cudaMemset(c->flags, 0, MAX_RANKS * sizeof(uint64_t)) != cudaSuccess ||
-                cudaMalloc((void**)&c->d_peer_flags, MAX_RANKS * sizeof(uint64_t*)) != cudaSuccess ||
-                cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+                cudaMalloc((void**)&c->d_peer_flags, MAX_RANKS * sizeof(uint64_t*)) != cudaSuccess) {
                 rc = fail(VQE_ERR_CUDA, "barrier flag allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-                break;
-            }
-            *c->h_err = 0;
-            if (cudaHostGetDevicePointer((void**)&c->d_err, c->h_err, 0) != cudaSuccess) {
-                rc = fail(VQE_ERR_CUDA, "cudaHostGetDevicePointer failed");
                 break;
             }
             c->peer_flags[c->rank] = c->flags;
@@ -1954,7 +2365,9 @@ extern "C" int vqe_shard_barrier(vqe_ctx* c) {
 }
 extern "C" int vqe_shard_status(vqe_ctx* c) {
     if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
-    if (c->h_err && *(volatile int*)c->h_err) return fail(VQE_ERR_CUDA, "rank %d: a cross-rank barrier timed out (peer lost)", c->rank);
+    if (c->h_err && *(volatile int*)c->h_err == 1) return fail(VQE_ERR_CUDA, "rank %d: a cross-rank barrier timed out (peer lost)", c->rank);
+    if (c->h_err && *(volatile int*)c->h_err)
+        return fail(VQE_ERR_CUDA, "rank %d: a bulk tile copy never completed (mbarrier wait timed out); results are invalid", c->rank);
     return VQE_OK;
 }
 
@@ -2141,7 +2554,7 @@ extern "C" int vqe_synchronize(vqe_ctx* c) {
     if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    return VQE_OK;
+    return vqe_shard_status(c);
 }
 
 // ---- generic op program ---------------------------------------------------------------------
@@ -2769,20 +3182,35 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                                : (ps.op_end - ps.op_begin) * sizeof(FastOp));
         int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
         ProfScope prof(c, ps.tp.vbit ? 4 : 0);
-        if (ps.fast && real_pass[p])
+        const bool all_col = ps.fast && ps.sub_end == ps.sub_begin && ps.col_end > ps.col_begin && gg.n_need == 0 &&
+                             ps.pass_scale == 1.0 && (ps.sup_end - ps.sup_begin) == (ps.col_end - ps.col_begin) &&
+                             env_int("VQE_COL_KERNEL", 1) != 0;
+        if (all_col) {
+            // every segment is a collapsed run / tabulated plane rotation: the lean kernel (256 threads, 3 CTAs per SM)
+            const int n_cols = (int)(ps.col_end - ps.col_begin), n_ents = (int)(ps.ent_end - ps.ent_begin);
+            const size_t smem_c = tile_smem(ps.tp.tbits, 1, false) + (size_t)n_cols * (sizeof(DevCol) + 4) + (size_t)n_ents * sizeof(DevColEntry);
+            const int thr = (int)std::min<uint64_t>(256, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
+            const int grid = tile_grid(c, g.n_tiles, smem_c <= 74 * 1024 ? 3 : 2);
+            if (real_pass[p])
+                k_tile_col<true><<<grid, thr, smem_c, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                                                                  (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
+            else
+                k_tile_col<false><<<grid, thr, smem_c, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                                                                   (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
+        } else if (ps.fast && real_pass[p])
             k_tile_rot<true><<<tile_grid(c, g.n_tiles, (smem <= 74 * 1024 && env_int("VQE_REAL_CTAS", 3) == 3) ? 3 : 0), threads, smem, c->stream>>>(
                 sh, g, gg, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
                 (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
                 (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
                 (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
-                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale);
+                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale, c->d_err);
         else if (ps.fast)
             k_tile_rot<false><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                 sh, g, gg, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
                 (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
                 (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
                 (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
-                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale);
+                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale, c->d_err);
         else
             k_tile_ops<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                 sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
@@ -3243,6 +3671,19 @@ struct PSPass {
     DevTerm* d_terms_apply = nullptr;
     uint64_t* d_scat = nullptr;
     bool cplx = false;  // some expectation weight has a non-zero imaginary part
+    // lean pass (see DevFlat2): every group is tabulated per occupation pattern; none of the tables above is used
+    bool lean = false;
+    std::vector<DevFlat2> flats2;       // entries, group after group
+    std::vector<uint32_t> goff;         // n_lean_groups + 1 offsets into flats2 (sigma = O psi walks the groups)
+    std::vector<double> addtab;         // T_lo[32] + T_hi[...] of every additive pattern
+    std::vector<DevAddPat> addpat;
+    std::vector<DevAddOut> addout;
+    size_t lean_terms = 0;              // Pauli strings folded into the entries (statistics)
+    DevFlat2* d_flats2 = nullptr;
+    uint32_t* d_goff = nullptr;
+    double* d_addtab = nullptr;
+    DevAddPat* d_addpat = nullptr;
+    DevAddOut* d_addout = nullptr;
 };
 struct vqe_paulisum {
     int n = 0, nl = 0, device = 0, n_groups = 0;
@@ -3261,6 +3702,195 @@ static void mul_i_pow(double& r, double& i, int k) {
     if (k == 1) { r = -b; i = a; }
     else if (k == 2) { r = -a; i = -b; }
     else if (k == 3) { r = b; i = -a; }
+}
+
+// ---- lean groups (DevFlat2) -----------------------------------------------------------------------
+#define LEAN_ENT_CAP 8192     // entries per lean pass (384 KiB of descriptors, streamed through L1/L2)
+#define LEAN_PAT_CAP 1024     // additive patterns per lean pass (per-tile constants in shared memory: 8 KiB)
+#define LEAN_TAB_CAP 60000    // doubles in the additive tables of a pass (16-bit offsets)
+
+// pass-independent part of the eligibility test (full-width masks)
+static bool lean_eligible(uint64_t x, const std::vector<HTerm>& terms, int nl, int tbits) {
+    if (x == 0 || (x >> nl) != 0 || terms.empty()) return false;
+    const int nx = popc64(x);
+    if (nx > 4 || tbits - nx < 8) return false;
+    for (const HTerm& t : terms) {
+        if (t.ci != 0.0 || (t.ny & 1)) return false;
+        if (popc64((t.z ^ terms[0].z) & ~x) > 1) return false;
+    }
+    return true;
+}
+
+// Lower one eligible group into entries of pass p (appended; nothing is appended when the pass capacities would be
+// exceeded -> false).  See the comment block above DevFlat2 for the algebra.
+static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& terms) {
+    const TilePlan& tp = p.tp;
+    const uint32_t lx = plan_lx(x, tp);
+    const int nx = __builtin_popcount(lx);
+    const int tb = tp.tbits, free_log = tb - nx;
+    const uint32_t hb = 31 - __builtin_clz(lx);
+    std::vector<uint32_t> xpos, fpos;
+    for (int b = 0; b < tb; ++b) ((lx >> b) & 1u ? xpos : fpos).push_back((uint32_t)b);
+    const uint32_t lz0 = plan_lz(terms[0].z, tp);
+    const uint64_t zout0 = plan_zout(terms[0].z, tp);
+    struct LT {
+        double w;
+        uint32_t dx;      // Z difference to the first string on the X positions
+        int r;            // further in-tile Z letter (tile bit), or -1
+        uint64_t dout;    // further outside-tile Z letter (mask), or 0
+    };
+    std::vector<LT> lt;
+    double scale = 0.0;
+    for (const HTerm& t : terms) {
+        LT e;
+        double wr = t.cr, wi = 0.0;
+        mul_i_pow(wr, wi, t.ny);  // even ny: real
+        e.w = wr;
+        const uint32_t dl = plan_lz(t.z, tp) ^ lz0;
+        e.dx = dl & lx;
+        const uint32_t dr = dl & ~lx;
+        e.dout = plan_zout(t.z, tp) ^ zout0;
+        if (__builtin_popcount(dr) + popc64(e.dout) > 1) return false;  // cannot happen for eligible groups
+        e.r = dr ? __builtin_ctz(dr) : -1;
+        scale += fabs(e.w);
+        lt.push_back(e);
+    }
+    auto pdep_free = [&](uint32_t v) {
+        uint32_t o = 0;
+        for (size_t k = 0; k < fpos.size(); ++k)
+            if ((v >> k) & 1u) o |= 1u << fpos[k];
+        return o;
+    };
+    std::vector<DevFlat2> ents;
+    std::vector<double> tabs;
+    std::vector<DevAddPat> pats;
+    std::vector<DevAddOut> outs;
+    uint32_t zsel = 0;
+    while (zsel < p.fzout.size() && p.fzout[zsel] != zout0) ++zsel;
+    const uint32_t n_chunks = 1u << (free_log - 8);
+    for (uint32_t pi = 0; pi < (1u << nx); ++pi) {
+        uint32_t pat = 0;
+        for (int b = 0; b < nx; ++b)
+            if ((pi >> b) & 1u) pat |= 1u << xpos[b];
+        if ((pat >> hb) & 1u) continue;  // a-side only
+        double beta0 = 0.0;
+        std::vector<double> beta_r(tb, 0.0);
+        std::vector<std::pair<uint64_t, double>> bout;
+        for (const LT& e : lt) {
+            const double val = (__builtin_popcount(pat & e.dx) & 1) ? -e.w : e.w;
+            if (e.r >= 0) beta_r[e.r] += val;
+            else if (e.dout) {
+                size_t q = 0;
+                while (q < bout.size() && bout[q].first != e.dout) ++q;
+                if (q == bout.size()) bout.push_back({e.dout, 0.0});
+                bout[q].second += val;
+            } else beta0 += val;
+        }
+        const double tiny = 1e-15 * scale;
+        if (fabs(beta0) <= tiny) beta0 = 0.0;
+        bool any_r = false;
+        for (double& b : beta_r) {
+            if (fabs(b) <= tiny) b = 0.0;
+            any_r = any_r || b != 0.0;
+        }
+        std::vector<std::pair<uint64_t, double>> bout2;
+        for (auto& bo : bout)
+            if (fabs(bo.second) > tiny) bout2.push_back(bo);
+        const bool additive = any_r || !bout2.empty();
+        if (!additive && beta0 == 0.0) continue;  // the group does not couple this occupation pattern
+        uint32_t tab = 0xffffu, bidx = 0;
+        if (additive) {
+            tab = (uint32_t)(p.addtab.size() + tabs.size());
+            bidx = (uint32_t)(p.addpat.size() + pats.size());
+            for (uint32_t v = 0; v < 32; ++v) {
+                double acc = 0.0;
+                for (int k = 0; k < 5 && k < free_log; ++k) acc += ((v >> k) & 1u) ? -beta_r[fpos[k]] : beta_r[fpos[k]];
+                tabs.push_back(acc);
+            }
+            for (uint32_t u2 = 0; u2 < (1u << (free_log - 5)); ++u2) {
+                double acc = 0.0;
+                for (int k = 5; k < free_log; ++k) acc += ((u2 >> (k - 5)) & 1u) ? -beta_r[fpos[k]] : beta_r[fpos[k]];
+                tabs.push_back(acc);
+            }
+            DevAddPat ap;
+            ap.beta0 = beta0;
+            ap.out_begin = (uint32_t)(p.addout.size() + outs.size());
+            ap.out_count = (uint32_t)bout2.size();
+            for (auto& bo : bout2) outs.push_back({bo.second, bo.first});
+            pats.push_back(ap);
+        }
+        for (uint32_t ch = 0; ch < n_chunks; ++ch) {
+            DevFlat2 fl;
+            memset(&fl, 0, sizeof fl);
+            fl.fr = additive ? 2.0 : 2.0 * beta0;
+            fl.lx16 = (uint16_t)(lx << 4);
+            fl.lz16 = (uint16_t)(lz0 << 4);
+            fl.pat16 = (uint16_t)(pat << 4);
+            fl.zsel = (uint16_t)zsel;
+            for (int k = 0; k < 4; ++k) fl.hm16[k] = k < nx ? (uint16_t)(~((1u << (xpos[k] + 4)) - 1u) & 0xffffu) : 0;
+            uint32_t js = 0;
+            for (uint32_t j = 0; j < 8; ++j) {
+                const uint32_t oj = pdep_free((ch << 8) | (j << 5));
+                fl.o16[j] = (uint16_t)(oj << 4);
+                if (__builtin_popcount(oj & lz0) & 1) js |= 1u << j;
+            }
+            fl.jsign = (uint16_t)js;
+            fl.tab = (uint16_t)tab;
+            fl.hi0 = additive ? (uint16_t)(tab + 32 + (ch << 3)) : 0;
+            fl.bidx = (uint16_t)bidx;
+            ents.push_back(fl);
+        }
+    }
+    if (!p.flats2.empty() && (p.flats2.size() + ents.size() > LEAN_ENT_CAP || p.addpat.size() + pats.size() > LEAN_PAT_CAP ||
+                              p.addtab.size() + tabs.size() > LEAN_TAB_CAP))
+        return false;
+    if (p.addtab.size() + tabs.size() > LEAN_TAB_CAP || p.addpat.size() + pats.size() > 0xffffu || zsel > 0xfffeu) return false;
+    if (zsel == p.fzout.size()) p.fzout.push_back(zout0);
+    if (p.goff.empty()) p.goff.push_back(0);
+    p.flats2.insert(p.flats2.end(), ents.begin(), ents.end());
+    p.goff.push_back((uint32_t)p.flats2.size());
+    p.addtab.insert(p.addtab.end(), tabs.begin(), tabs.end());
+    p.addpat.insert(p.addpat.end(), pats.begin(), pats.end());
+    p.addout.insert(p.addout.end(), outs.begin(), outs.end());
+    p.lean_terms += terms.size();
+    return true;
+}
+
+// Tile bits of a pass, chosen greedily for COVERAGE: seed with `need`, repeatedly add the bit that completes the most
+// open groups; when no single bit completes one, take the open group that needs the fewest new bits.
+static uint64_t cover_greedy(const std::vector<uint64_t>& xs, const std::vector<size_t>& open, uint64_t need, uint64_t lowmask_pass,
+                             int cap_bits, int nl, uint64_t lfull) {
+    for (;;) {
+        const uint64_t have = need | lowmask_pass;
+        if (popc64(have) >= cap_bits) break;
+        int best_bit = -1;
+        size_t best_gain = 0;
+        for (int b2 = 0; b2 < nl; ++b2) {
+            if ((have >> b2) & 1ull) continue;
+            const uint64_t with = have | (1ull << b2);
+            size_t gain = 0;
+            for (size_t g : open) {
+                const uint64_t xl = xs[g] & lfull;
+                if ((xl & ~with) == 0 && (xl & ~have) != 0) ++gain;
+            }
+            if (gain > best_gain) { best_gain = gain; best_bit = b2; }
+        }
+        if (best_bit >= 0) {
+            need |= 1ull << best_bit;
+            continue;
+        }
+        size_t best_g = xs.size();
+        int best_missing = 1 << 30;
+        for (size_t g : open) {
+            const uint64_t xl = xs[g] & lfull;
+            const int missing = popc64(xl & ~have);
+            if (missing == 0 || popc64(have | xl) > cap_bits) continue;
+            if (missing < best_missing) { best_missing = missing; best_g = g; }
+        }
+        if (best_g == xs.size()) break;
+        need |= xs[best_g] & lfull;
+    }
+    return need;
 }
 
 static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int low_bits, int threads_cfg,
@@ -3304,6 +3934,47 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
     }
     std::vector<char> done(xs.size(), 0);
     size_t remaining = xs.size();
+    // ---- lean passes first: every group that can be tabulated per occupation pattern (all two-body groups and the
+    // number-operator-dressed one-body groups of a molecular Hamiltonian).  No per-pass term tables, so a pass takes
+    // EVERY open group its tile bits cover.
+    if (env_int("VQE_EXP_LEAN", 1) != 0) {
+        const int tb_local = std::min(tbits_max, nl);
+        std::vector<char> lean_ok(xs.size(), 0);
+        size_t n_lean = 0;
+        for (size_t g = 0; g < xs.size(); ++g) {
+            lean_ok[g] = lean_eligible(xs[g], grp[g], nl, tb_local) ? 1 : 0;
+            n_lean += lean_ok[g];
+        }
+        while (n_lean) {
+            size_t seed = xs.size();
+            for (size_t g = 0; g < xs.size(); ++g)
+                if (!done[g] && lean_ok[g]) { seed = g; break; }
+            if (seed == xs.size()) break;
+            uint64_t need = xs[seed] & lfull;
+            const int lb_pass = fit_low_bits(need, lb, tbits_max, nl, false);
+            if (lb_pass < 0) { lean_ok[seed] = 0; --n_lean; continue; }
+            std::vector<size_t> open;
+            for (size_t g = 0; g < xs.size(); ++g)
+                if (!done[g] && lean_ok[g]) open.push_back(g);
+            need = cover_greedy(xs, open, need, (1ull << lb_pass) - 1ull, tb_local, nl, lfull);
+            PSPass p;
+            p.lean = true;
+            p.tp = make_plan(nl, need, tbits_max, lb_pass, 0);
+            size_t taken = 0;
+            for (size_t g : open) {
+                if ((xs[g] & lfull & ~p.tp.tile_mask) != 0) continue;
+                if (!lower_lean_group(p, xs[g], grp[g])) {
+                    if (p.flats2.empty() && g == seed) { lean_ok[g] = 0; --n_lean; }  // cannot be lowered at all: fat path
+                    continue;
+                }
+                done[g] = 1;
+                ++taken;
+                --n_lean;
+            }
+            remaining -= taken;
+            if (taken) ps->passes.push_back(std::move(p));
+        }
+    }
     while (remaining) {
         // Choose the tile bits of this pass greedily for COVERAGE (the Pauli sum is uploaded once and evaluated
         // thousands of times, so every pass saved is a full sweep over the state saved per evaluation):
@@ -3627,6 +4298,16 @@ static void free_paulisum_device(vqe_paulisum* ps) {
         p.d_azout = nullptr;
         p.d_flats = nullptr;
         p.d_fzout = nullptr;
+        if (p.d_flats2) cudaFree(p.d_flats2);
+        if (p.d_goff) cudaFree(p.d_goff);
+        if (p.d_addtab) cudaFree(p.d_addtab);
+        if (p.d_addpat) cudaFree(p.d_addpat);
+        if (p.d_addout) cudaFree(p.d_addout);
+        p.d_flats2 = nullptr;
+        p.d_goff = nullptr;
+        p.d_addtab = nullptr;
+        p.d_addpat = nullptr;
+        p.d_addout = nullptr;
         if (p.d_gcols) cudaFree(p.d_gcols);
         if (p.d_gents) cudaFree(p.d_gents);
         p.d_gcols = nullptr;
@@ -3637,8 +4318,25 @@ static void free_paulisum_device(vqe_paulisum* ps) {
     }
 }
 
+template <class T>
+static int upload_vec(T** dptr, const std::vector<T>& v) {
+    CK(cudaMalloc((void**)dptr, std::max<size_t>(1, v.size()) * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return VQE_OK;
+}
 static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
     for (PSPass& p : ps->passes) {
+        if (p.lean) {
+            int rc = upload_vec(&p.d_flats2, p.flats2);
+            if (rc == VQE_OK) rc = upload_vec(&p.d_goff, p.goff);
+            if (rc == VQE_OK) rc = upload_vec(&p.d_addtab, p.addtab);
+            if (rc == VQE_OK) rc = upload_vec(&p.d_addpat, p.addpat);
+            if (rc == VQE_OK) rc = upload_vec(&p.d_addout, p.addout);
+            if (rc == VQE_OK) rc = upload_vec(&p.d_fzout, p.fzout);
+            if (rc == VQE_OK) rc = upload_vec(&p.d_scat, p.tp.scat);
+            if (rc) return rc;
+            continue;
+        }
         CK(cudaMalloc((void**)&p.d_groups, p.groups.size() * sizeof(DevGroup)));
         CK(cudaMalloc((void**)&p.d_terms_expect, std::max<size_t>(1, p.terms_expect.size()) * sizeof(DevTerm)));
         CK(cudaMalloc((void**)&p.d_terms_apply, std::max<size_t>(1, p.terms_apply.size()) * sizeof(DevTerm)));
@@ -3729,11 +4427,17 @@ extern "C" int vqe_plan_paulisum(int n_qubits, int n_global, int tile_bits, int 
     for (size_t p = 0; p < ps.passes.size(); ++p) {
         const PSPass& pp = ps.passes[p];
         if ((int)p < cap) {
-            if (pass_groups) pass_groups[p] = (int32_t)pp.groups.size();
-            if (pass_terms) pass_terms[p] = (int32_t)pp.terms_expect.size();
+            if (pass_groups) pass_groups[p] = pp.lean ? (int32_t)pp.goff.size() - 1 : (int32_t)pp.groups.size();
+            if (pass_terms) pass_terms[p] = pp.lean ? (int32_t)pp.lean_terms : (int32_t)pp.terms_expect.size();
             if (pass_tile_mask) pass_tile_mask[p] = pp.tp.tile_mask;
         }
-        if (getenv("VQE_DEBUG_PLAN") && atoi(getenv("VQE_DEBUG_PLAN")) >= 3) {
+        if (getenv("VQE_DEBUG_PLAN") && atoi(getenv("VQE_DEBUG_PLAN")) >= 3 && pp.lean) {
+            size_t n_add = 0;
+            for (const DevFlat2& fl : pp.flats2) n_add += fl.tab != 0xffffu;
+            fprintf(stderr, "[pspass] %zu LEAN groups %zu terms %zu entries %zu (additive %zu) addpat %zu addout %zu tab %zu lbits %d tbits %d\n", p,
+                    pp.goff.size() - 1, pp.lean_terms, pp.flats2.size(), n_add, pp.addpat.size(), pp.addout.size(), pp.addtab.size(),
+                    pp.tp.lbits, pp.tp.tbits);
+        } else if (getenv("VQE_DEBUG_PLAN") && atoi(getenv("VQE_DEBUG_PLAN")) >= 3) {
             size_t n_flatg = 0, n_colg = 0, n_clsg = 0, cls_terms = 0, diag_terms = 0, col_items = 0, aflat_groups = 0, aterm = 0;
             for (size_t gi = 0; gi < pp.groups.size(); ++gi) {
                 const DevGroup& dg = pp.groups[gi];
@@ -3755,6 +4459,97 @@ extern "C" int vqe_plan_paulisum(int n_qubits, int n_global, int tile_bits, int 
                     diag_terms, aflat_groups, pp.aflat.size(), aterm, pp.tp.lbits, pp.tp.tbits, (int)pp.tp.vbit);
         }
     }
+    return VQE_OK;
+}
+// Host-only interpreter of the LEAN passes of a Pauli sum (no CUDA call): evaluates  sum over the lean groups of
+// <psi|O_g|psi>  and, when sigma is given, accumulates  sigma += O_lean psi,  by walking the same entry tables with the
+// same decode routine (lean_decode) the kernels k_expect_lean / k_apply_lean use.  Lets the CPU test-suite check the table
+// construction (patterns, deposits, signs, additive tables, outside-tile constants) against the oracle without a GPU.
+// psi / sigma: 2^(n_qubits - n_global) interleaved complex amplitudes of rank `rank`.
+extern "C" int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int tile_bits, int low_bits, int n_terms, const uint64_t* x,
+                                   const uint64_t* z, const int32_t* ny, const double* cre, const double* cim,
+                                   const double* psi_re_im, double* out_re, int32_t* n_lean_terms, int32_t* n_fat_terms,
+                                   double* sigma_re_im) {
+    if (n_qubits < 1 || n_qubits > 30 || n_global < 0 || n_global >= n_qubits) return fail(VQE_ERR_INVALID, "bad qubit counts");
+    if (tile_bits < 6 || tile_bits > 12) tile_bits = 12;
+    if (low_bits < 0 || low_bits > tile_bits) low_bits = 5;
+    if (!psi_re_im || !out_re) return fail(VQE_ERR_INVALID, "null argument");
+    vqe_ctx fake;
+    fake.n = n_qubits;
+    std::vector<HTerm> terms;
+    int rc = collect_terms(&fake, n_terms, x, z, ny, cre, cim, terms);
+    if (rc) return rc;
+    vqe_paulisum ps;
+    const int nl = n_qubits - n_global;
+    rc = build_paulisum(&ps, n_qubits, nl, tile_bits, low_bits, 512, std::move(terms));
+    if (rc) return rc;
+    const double2* psi = reinterpret_cast<const double2*>(psi_re_im);
+    double2* sigma = reinterpret_cast<double2*>(sigma_re_im);
+    const uint64_t sign_base = (uint64_t)rank << nl;
+    double total = 0.0;
+    size_t lean_terms = 0, fat_terms = 0;
+    for (const PSPass& p : ps.passes) {
+        if (!p.lean) {
+            fat_terms += p.terms_expect.size();
+            continue;
+        }
+        lean_terms += p.lean_terms;
+        const uint32_t ts = 1u << p.tp.tbits;
+        std::vector<double2> tile(ts), acc(ts);
+        std::vector<uint64_t> addr(ts);
+        std::vector<double> beta(p.addpat.size());
+        const uint32_t lmask = (1u << p.tp.lbits) - 1u;
+        for (uint64_t t = 0; t < p.tp.n_tiles; ++t) {
+            uint64_t base = 0, v = t, m = p.tp.comp_mask;
+            while (m) {  // pdep
+                const uint64_t low = m & (0 - m);
+                if (v & 1) base |= low;
+                v >>= 1;
+                m ^= low;
+            }
+            const uint64_t sbase = base | sign_base;
+            for (uint32_t k = 0; k < ts; ++k) {
+                addr[k] = base | p.tp.scat[k >> p.tp.lbits] | (uint64_t)(k & lmask);
+                tile[k] = psi[addr[k]];
+                acc[k] = make_double2(0.0, 0.0);
+            }
+            for (size_t k = 0; k < p.addpat.size(); ++k) {
+                double b = p.addpat[k].beta0;
+                for (uint32_t q = 0; q < p.addpat[k].out_count; ++q) {
+                    const DevAddOut& ao = p.addout[p.addpat[k].out_begin + q];
+                    b += (popc64(sbase & ao.zrel) & 1) ? -ao.c : ao.c;
+                }
+                beta[k] = b;
+            }
+            for (size_t e = 0; e < p.flats2.size(); ++e) {
+                uint4 q[3];
+                memcpy(q, &p.flats2[e], sizeof(DevFlat2));
+                const uint32_t par_out = (uint32_t)popc64(sbase & p.fzout[q[0].w >> 16]);
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    LeanUnit u;
+                    lean_decode(q[0], q[1], q[2], lane, u);
+                    for (uint32_t j = 0; j < 8; ++j) {
+                        const uint32_t off = u.v | u.o[j], offb = off ^ u.lx16;
+                        const double2 a = tile[off >> 4], b = tile[offb >> 4];
+                        double gw = 0.5 * u.fr;
+                        if (u.tab != 0xffffu) gw *= beta[u.bidx] + p.addtab[u.tab + lane] + p.addtab[u.hi0 + j];
+                        if ((u.s0 + (u.jsign >> j) + par_out) & 1u) gw = -gw;
+                        total += 2.0 * gw * (b.x * a.x + b.y * a.y);
+                        acc[offb >> 4].x += gw * a.x; acc[offb >> 4].y += gw * a.y;
+                        acc[off >> 4].x += gw * b.x; acc[off >> 4].y += gw * b.y;
+                    }
+                }
+            }
+            if (sigma)
+                for (uint32_t k = 0; k < ts; ++k) {
+                    sigma[addr[k]].x += acc[k].x;
+                    sigma[addr[k]].y += acc[k].y;
+                }
+        }
+    }
+    *out_re = total;
+    if (n_lean_terms) *n_lean_terms = (int32_t)lean_terms;
+    if (n_fat_terms) *n_fat_terms = (int32_t)fat_terms;
     return VQE_OK;
 }
 extern "C" void vqe_paulisum_destroy(vqe_paulisum* ps) {
@@ -3788,6 +4583,8 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
         if (rc) return rc;
     }
     const size_t n_pass = pss[0]->passes.size();
+    bool real_state = b == VQE_BUF_PSI;  // the purely-real flag is only tracked for the state buffer
+    for (vqe_ctx* c : rs.r) real_state = real_state && c->psi_real;
     // per rank: grids and partial-sum layout (consecutive blocks of every pass this rank launches)
     std::vector<std::vector<dim3>> grids(nr, std::vector<dim3>(n_pass));
     std::vector<std::vector<TileGeom>> geoms(nr, std::vector<TileGeom>(n_pass));
@@ -3803,9 +4600,9 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                 grids[k][p] = dim3(0, 0, 1);
                 continue;
             }
-            int gx = tile_grid(c, geoms[k][p].n_tiles);
-            int want = std::max(1, (c->sm_count * c->ctas_per_sm) / gx);
-            int gy = std::max(1, std::min<int>((int)pp.groups.size(), want));
+            int gx = tile_grid(c, geoms[k][p].n_tiles, pp.lean ? 3 : 0);
+            int want = std::max(1, (c->sm_count * (pp.lean ? 3 : c->ctas_per_sm)) / gx);
+            int gy = std::max(1, std::min<int>(pp.lean ? (int)((pp.flats2.size() + 7) / 8) : (int)pp.groups.size(), want));
             grids[k][p] = dim3(gx, gy, 1);
             total_blocks[k] += (size_t)gx * gy;
         }
@@ -3829,18 +4626,28 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             size_t smem = tile_smem(pp.tp.tbits, 1, true);
             int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << pp.tp.tbits) / 2));
             ProfScope prof(c, vbit ? 5 : 1);
-            if (pp.cplx)
+            if (pp.lean) {
+                const size_t smem_l = tile_smem(pp.tp.tbits, 1, false) + pp.addpat.size() * sizeof(double);
+                if (real_state)
+                    k_expect_lean<true><<<grids[k][p], 256, smem_l, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
+                                                                                pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
+                                                                                pp.d_addout, c->d_partial + off[k], c->d_err);
+                else
+                    k_expect_lean<false><<<grids[k][p], 256, smem_l, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
+                                                                                 pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
+                                                                                 pp.d_addout, c->d_partial + off[k], c->d_err);
+            } else if (pp.cplx)
                 k_tile_expect<true><<<grids[k][p], threads, smem, c->stream>>>(shards[k][p], geoms[k][p], pp.d_groups,
                                                                               (int)pp.groups.size(), pp.d_terms_expect,
                                                                               pp.d_gcols, (int)pp.gcols.size(), pp.d_gents,
                                                                               (int)pp.gents.size(), pp.d_flats, (int)pp.flats.size(),
-                                                                              pp.d_fzout, c->d_partial + off[k]);
+                                                                              pp.d_fzout, c->d_partial + off[k], c->d_err);
             else
                 k_tile_expect<false><<<grids[k][p], threads, smem, c->stream>>>(shards[k][p], geoms[k][p], pp.d_groups,
                                                                                (int)pp.groups.size(), pp.d_terms_expect,
                                                                                pp.d_gcols, (int)pp.gcols.size(), pp.d_gents,
                                                                                (int)pp.gents.size(), pp.d_flats, (int)pp.flats.size(),
-                                                                               pp.d_fzout, c->d_partial + off[k]);
+                                                                               pp.d_fzout, c->d_partial + off[k], c->d_err);
             c->launches++;
             CK(cudaGetLastError());
             off[k] += (size_t)grids[k][p].x * grids[k][p].y;
@@ -3910,6 +4717,8 @@ static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* 
         rc = ensure_buf(c, src);
         if (rc) return rc;
     }
+    bool real_src = src == VQE_BUF_PSI;  // lean passes have real weights: a purely real source gives a purely real sigma
+    for (vqe_ctx* c : rs.r) real_src = real_src && c->psi_real;
     if (dst == VQE_BUF_PSI)
         for (vqe_ctx* c : rs.r) c->psi_real = false;
     const size_t n_pass = pss[0]->passes.size();
@@ -3942,6 +4751,24 @@ static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* 
             uint64_t ts = 1ull << pp.tp.tbits;
             int threads = (int)std::min<uint64_t>(1024, std::max<uint64_t>(32, ts / 2));
             ProfScope prof(c, 2);
+            if (pp.lean) {
+                const int n_lg = (int)pp.goff.size() - 1;
+                const int thr = (int)std::min<uint64_t>(512, std::max<uint64_t>(32, ts / 2));
+                if (real_src) {
+                    const size_t smem_l = (16ull << pp.tp.tbits) + (8ull << pp.tp.tbits) + pp.addpat.size() * sizeof(double);
+                    k_apply_lean<true><<<tile_grid(c, g.n_tiles, 2), thr, smem_l, c->stream>>>(
+                        ssrc, sdst, g, pp.d_flats2, pp.d_goff, n_lg, pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
+                        pp.d_addout, p == 0 ? 0 : 1, c->d_err);
+                } else {
+                    const size_t smem_l = 2 * (16ull << pp.tp.tbits) + pp.addpat.size() * sizeof(double);
+                    k_apply_lean<false><<<tile_grid(c, g.n_tiles, 1), thr, smem_l, c->stream>>>(
+                        ssrc, sdst, g, pp.d_flats2, pp.d_goff, n_lg, pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
+                        pp.d_addout, p == 0 ? 0 : 1, c->d_err);
+                }
+                c->launches++;
+                CK(cudaGetLastError());
+                continue;
+            }
             k_tile_apply<<<tile_grid(c, g.n_tiles, 1), threads, smem, c->stream>>>(ssrc, sdst, g, pp.d_groups,
                                                                                   (int)pp.groups.size(), pp.d_terms_apply,
                                                                                   pp.d_aflat, pp.d_aoff, pp.d_azout,
