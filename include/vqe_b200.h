@@ -70,6 +70,10 @@ int vqe_timer_end(vqe_ctx* ctx, double* ms);
 /* bytes this context has copied host->device / device->host so far (bench.py e2e accounting) */
 int vqe_transfer_bytes(vqe_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);
 
+/* bytes this rank has read from partner shards in gather-form peer passes so far (sharded states; bench.py NVLink
+ * accounting: the dependency closure of a pass decides how many partner amplitudes are fetched) */
+int vqe_peer_bytes(vqe_ctx* ctx, uint64_t* gathered, int reset);
+
 /* |psi> = |index>.  Replaces the X-gate Hartree-Fock preparation
  * (openvqe/adapt/fermionic_adapt_vqe.py:183-213, get_energy_qucc.py:40-45). */
 int vqe_set_basis_state(vqe_ctx* ctx, uint64_t index);

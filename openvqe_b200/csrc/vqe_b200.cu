@@ -1993,6 +1993,7 @@ struct vqe_ctx {
     std::vector<cudaEvent_t> ev_pool;           // recycled events
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    uint64_t gather_bytes = 0;   // bytes read from partner shards by k_gather_need (gather-form peer passes)
 };
 
 // Non-intrusive per-kernel timing: when profiling is on, every kernel of a class is bracketed by two
@@ -2484,6 +2485,13 @@ extern "C" int vqe_transfer_bytes(vqe_ctx* c, uint64_t* h2d, uint64_t* d2h, int 
     if (h2d) *h2d = c->h2d_bytes;
     if (d2h) *d2h = c->d2h_bytes;
     if (reset) c->h2d_bytes = c->d2h_bytes = 0;
+    return VQE_OK;
+}
+
+extern "C" int vqe_peer_bytes(vqe_ctx* c, uint64_t* gathered, int reset) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    if (gathered) *gathered = c->gather_bytes;
+    if (reset) c->gather_bytes = 0;
     return VQE_OK;
 }
 
@@ -3271,6 +3279,7 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                     const uint64_t total_amp = (uint64_t)need.size() * 4 * nt;
                     const int blocks = (int)std::min<uint64_t>((total_amp + 255) / 256, (uint64_t)c->sm_count * 16);
                     ProfScope prof(c, 4);
+                    c->gather_bytes += total_amp * sizeof(double2);
                     k_gather_need<<<std::max(1, blocks), 256, 0, c->stream>>>(shs[k], gs[k], ggs[k], c->gstage);
                     c->launches++;
                     CK(cudaGetLastError());

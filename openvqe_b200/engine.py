@@ -196,6 +196,12 @@ class Engine:
         _lib.check(self._lib.vqe_transfer_bytes(self.handle, C.byref(a), C.byref(b), 1 if reset else 0))
         return a.value, b.value
 
+    def gather_bytes(self, reset=False) -> int:
+        """Bytes this rank has fetched from partner shards in gather-form peer passes (sharded states)."""
+        g = C.c_uint64()
+        _lib.check(self._lib.vqe_peer_bytes(self.handle, C.byref(g), 1 if reset else 0))
+        return g.value
+
     def buffer_ptr(self, buf=BUF_PSI):
         p, n = C.c_void_p(), C.c_uint64()
         _lib.check(self._lib.vqe_buffer_ptr(self.handle, buf, C.byref(p), C.byref(n)))

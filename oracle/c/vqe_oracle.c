@@ -24,6 +24,17 @@ int orc_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU baseline sets its thread count explicitly */
+int orc_set_threads(int n_threads) {
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+    return omp_get_max_threads();
+#else
+    (void)n_threads;
+    return 1;
+#endif
+}
+
 void orc_basis_state(double* psi, int n, uint64_t index) {
     const uint64_t dim = 1ull << n;
 #pragma omp parallel for schedule(static)

@@ -24,6 +24,8 @@ def load():
     lib = C.CDLL(LIB_PATH)
     vp, u64, i32, dbl = C.c_void_p, C.c_uint64, C.c_int32, C.c_double
     lib.orc_threads.restype = C.c_int
+    lib.orc_set_threads.restype = C.c_int
+    lib.orc_set_threads.argtypes = [C.c_int]
     lib.orc_basis_state.argtypes = [vp, C.c_int, u64]
     lib.orc_pauli_rotation.argtypes = [vp, C.c_int, u64, u64, C.c_int, dbl]
     lib.orc_pauli_expectation.argtypes = [vp, C.c_int, u64, u64, C.c_int, vp]
@@ -44,6 +46,17 @@ def _p(a):
 
 def threads():
     return int(load().orc_threads())
+
+
+def set_threads(n_threads=None):
+    """Use n_threads OpenMP threads (default: every host core this process may run on), whatever OMP_NUM_THREADS
+    says -- torchrun pins it to 1 for every rank.  Returns the thread count now in effect."""
+    if n_threads is None:
+        try:
+            n_threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n_threads = os.cpu_count() or 1
+    return int(load().orc_set_threads(int(n_threads)))
 
 
 def _arrs(x, z, ny, *rest):
