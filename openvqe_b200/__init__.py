@@ -9,7 +9,8 @@ Layout (only what the hot path needs):
   ucc_family/      mirrors openvqe.ucc_family (EnergyUCC for UCC and QUCCSD)
   adapt/           mirrors openvqe.adapt (fermionic_adapt_vqe, qubit_adapt_vqe)
   common_files/    host helpers with reference-identical semantics (sorted_gradient, circuit)
-  dist/            multi-GPU layer (one process per GPU, torch.distributed)
+  sharded.py       multi-GPU layer: states sharded over 2/4/8 GPUs (one process per GPU, CUDA IPC + device-side
+                   barriers), opt-in SPMD replica mode below that
 
 There is NO CPU fallback: every numeric entry point needs the CUDA library and a GPU.
 """

@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 
 from .common_files.circuit import hf_index, quccsd_circuit, quccsd_plane_ops
-from .engine import BUF_PSI, BUF_SIGMA, GATE_KINDS, get_engine
+from .engine import BUF_PSI, BUF_SIGMA, GATE_KINDS, get_engine, operator_fingerprint
 from .lowering import PackedTerms, pack_operator, pack_pool
 
 _PACK_CACHE = {}
@@ -20,13 +20,14 @@ def packed(op) -> PackedTerms:
     """Lowered form of one operator, cached per object (the same generator objects
     are passed on every one of the thousands of objective evaluations)."""
     key = id(op)
+    mark = operator_fingerprint(op)
     hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] is op:
+    if hit is not None and hit[0] is op and hit[2] == mark:
         return hit[1]
     p = pack_operator(op)
     if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
         _PACK_CACHE.clear()
-    _PACK_CACHE[key] = (op, p)  # strong ref: the id cannot be recycled while cached
+    _PACK_CACHE[key] = (op, p, mark)  # strong ref: the id cannot be recycled while cached
     return p
 
 
@@ -56,15 +57,25 @@ class RotationProgram:
 _PROG_CACHE = {}
 
 
+def _spot_marks(ops):
+    """Fingerprints of up to 10 operators spread over the list (O(1) per call): operators are treated as immutable,
+    as the reference treats them; this catches the common ways of breaking that (a rebuilt or rescaled generator)."""
+    n = len(ops)
+    if n == 0:
+        return ()
+    step = max(1, n // 9)
+    return tuple(operator_fingerprint(ops[k]) for k in sorted(set(list(range(0, n, step))[:9] + [n - 1])))
+
+
 def rotation_program(ops) -> RotationProgram:
     key = tuple(id(o) for o in ops)
     hit = _PROG_CACHE.get(key)
-    if hit is not None and all(a is b for a, b in zip(hit[0], ops)):
+    if hit is not None and all(a is b for a, b in zip(hit[0], ops)) and hit[2] == _spot_marks(ops):
         return hit[1]
     prog = RotationProgram(ops)
     if len(_PROG_CACHE) >= 256:
         _PROG_CACHE.clear()
-    _PROG_CACHE[key] = (list(ops), prog)
+    _PROG_CACHE[key] = (list(ops), prog, _spot_marks(ops))
     return prog
 
 
@@ -153,13 +164,13 @@ def pool_overlaps(engine, hamiltonian_sp, pool_ops):
     engine.apply_paulisum(engine.paulisum(hamiltonian_sp), dst=BUF_SIGMA, src=BUF_PSI)
     key = ("pool",) + tuple(id(o) for o in pool_ops)
     hit = _PROG_CACHE.get(key)
-    if hit is not None and all(a is b for a, b in zip(hit[0], pool_ops)):
+    if hit is not None and all(a is b for a, b in zip(hit[0], pool_ops)) and hit[2] == _spot_marks(pool_ops):
         pool = hit[1]
     else:
         pool = pack_pool(pool_ops)
         if len(_PROG_CACHE) >= 256:
             _PROG_CACHE.clear()
-        _PROG_CACHE[key] = (list(pool_ops), pool)
+        _PROG_CACHE[key] = (list(pool_ops), pool, _spot_marks(pool_ops))
     if replica_split_active(engine):
         from . import sharded
         return sharded.replica_pool_overlaps(engine, pool, bra=BUF_SIGMA, ket=BUF_PSI)
@@ -167,16 +178,15 @@ def pool_overlaps(engine, hamiltonian_sp, pool_ops):
 
 
 def replica_split_active(engine) -> bool:
-    """True when this process is one of several SPMD ranks (torchrun) working on a state that fits one GPU:
-    the pool sweep is then split over the ranks.  VQE_B200_REPLICA_POOL=0 switches it off."""
+    """True when the caller has OPTED IN to SPMD replica mode (``sharded.enable_replica()`` or VQE_B200_REPLICA=1),
+    this process is one of several ranks and the state fits one GPU: the pool sweep is then split over the ranks.
+    Never on by default -- under torchrun ranks often work on different problems (a geometry scan, rank-0-only ADAPT),
+    and splitting would then mix gradients of different Hamiltonians or deadlock.  VQE_B200_REPLICA_POOL=0 keeps the
+    finite-difference split but not the pool split."""
     import os
-    import sys
     if os.environ.get("VQE_B200_REPLICA_POOL", "1") == "0" or getattr(engine, "n_global", 0):
         return False
-    if "torch.distributed" not in sys.modules:  # never import torch just to find out nothing is initialised
-        return False
-    from . import sharded
-    return sharded.dist_ready() and sharded._dist().get_world_size() > 1
+    return replica_world(which=None)[1] > 1
 
 
 ZERO_TOL = 1e-14  # Hartree; far below the rounding noise of a 2^n-term fp64 reduction of O(1) values
@@ -289,17 +299,22 @@ def adjoint_fun_jac(hamiltonian_sp, cluster_ops_sp, hf_init_sp, energies):
 FD_STEP = 1.4901161193847656e-08  # scipy's absolute 2-point step for BFGS with jac=None (sqrt of machine epsilon)
 
 
-def replica_world():
-    """(rank, world) of the SPMD replica group, or (0, 1) outside torchrun / when switched off."""
+def replica_world(which="fd"):
+    """(rank, world) of the SPMD replica group, or (0, 1) when replica mode is off.  Replica mode is OPT-IN:
+    ``openvqe_b200.sharded.enable_replica(group)`` or the environment variable VQE_B200_REPLICA=1 (every rank must then
+    run the same problem in lockstep)."""
     import os
     import sys
-    if os.environ.get("VQE_B200_REPLICA_FD", "1") == "0" or "torch.distributed" not in sys.modules:
-        return 0, 1
     from . import sharded
-    if not sharded.dist_ready():
+    if not (sharded.replica_enabled() or os.environ.get("VQE_B200_REPLICA", "0") == "1"):
+        return 0, 1
+    if which == "fd" and os.environ.get("VQE_B200_REPLICA_FD", "1") == "0":
+        return 0, 1
+    if "torch.distributed" not in sys.modules or not sharded.dist_ready():
         return 0, 1
     dist = sharded._dist()
-    return dist.get_rank(), dist.get_world_size()
+    group = sharded.replica_group()
+    return dist.get_rank(group), dist.get_world_size(group)
 
 
 def distributed_fd(action, energies):
@@ -316,32 +331,42 @@ def distributed_fd(action, energies):
 
     def fun(theta):
         x = np.array(theta, dtype=np.float64)
+        if "x" in last and last.get("pending") and np.array_equal(last["x"], x):
+            last["pending"] = False      # already evaluated (and appended) by jac at this point
+            return last["f"]
         v = action(x)
         energies.append(v)
-        last["x"], last["f"] = x, v
+        last["x"], last["f"], last["pending"] = x, v, False
         return v
 
     if world == 1:
         return fun, None
     from . import sharded
+    group = sharded.replica_group()
 
     def jac(theta):
         x0 = np.array(theta, dtype=np.float64)
-        if "x" in last and np.array_equal(last["x"], x0):
-            f0 = last["f"]
-        else:
-            f0 = action(x0)
+        if not ("x" in last and np.array_equal(last["x"], x0)):
+            # scipy asked for the gradient at a point it has not evaluated yet: evaluate and append f(x) FIRST, as the
+            # serial finite-difference path does, and let the following fun(x) reuse it without appending again
+            fun(x0)
+            last["pending"] = True
+        f0 = last["f"]
         n = x0.shape[0]
-        lo, hi = sharded.split_range(n, world, rank)
-        width = max(sharded.split_range(n, world, r)[1] - sharded.split_range(n, world, r)[0] for r in range(world))
-        mine = np.zeros(width, dtype=np.float64)
-        for i in range(lo, hi):
-            xi = x0.copy()
-            xi[i] = x0[i] + FD_STEP
-            mine[i - lo] = action(xi)
-        rows = sharded.allgather_f64(mine)
-        vals = np.concatenate([rows[r, :sharded.split_range(n, world, r)[1] - sharded.split_range(n, world, r)[0]]
-                               for r in range(world)])
+        if not sharded.ranks_agree(x0.tobytes(), group):
+            # the ranks are not running the same problem: every rank differences serially (same decision everywhere)
+            vals = np.array([action(np.where(np.arange(n) == i, x0 + FD_STEP, x0)) for i in range(n)])
+        else:
+            lo, hi = sharded.split_range(n, world, rank)
+            width = max(sharded.split_range(n, world, r)[1] - sharded.split_range(n, world, r)[0] for r in range(world))
+            mine = np.zeros(width, dtype=np.float64)
+            for i in range(lo, hi):
+                xi = x0.copy()
+                xi[i] = x0[i] + FD_STEP
+                mine[i - lo] = action(xi)
+            rows = sharded.allgather_f64(mine, group)
+            vals = np.concatenate([rows[r, :sharded.split_range(n, world, r)[1] - sharded.split_range(n, world, r)[0]]
+                                   for r in range(world)])
         energies.extend(float(v) for v in vals)
         dx = (x0 + FD_STEP) - x0
         return (vals - f0) / dx

@@ -23,6 +23,19 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def operator_fingerprint(op):
+    """Cheap content mark of a duck-typed operator for the identity-keyed caches: term-list identity and length, first
+    and last term.  O(1); catches a replaced or truncated/extended term list and edited end terms."""
+    terms = getattr(op, "terms", None)
+    if terms is None:
+        return None
+    n = len(terms)
+    if n == 0:
+        return (id(terms), 0)
+    a, b = terms[0], terms[-1]
+    return (id(terms), n, complex(a.coeff), a.op, complex(b.coeff), b.op, getattr(op, "constant_coeff", None))
+
+
 class PauliSum:
     """Device-resident, X-mask-grouped Pauli sum (Hamiltonian or observable)."""
 
@@ -119,15 +132,18 @@ class Engine:
 
     # -- observables ---------------------------------------------------------
     def paulisum(self, operator) -> PauliSum:
-        """Lower + upload ``operator`` once; cached per object identity."""
+        """Lower + upload ``operator`` once; cached per object identity plus a cheap fingerprint of its term list
+        (operators are treated as immutable, like the reference treats them; replacing the term list or editing its
+        ends is noticed, an in-place edit in the middle is not)."""
         key = id(operator)
+        mark = operator_fingerprint(operator)
         hit = self._ps_cache.get(key)
-        if hit is not None and hit[0]() is operator:
+        if hit is not None and hit[0]() is operator and hit[2] == mark:
             return hit[1]
         packed = operator if isinstance(operator, PackedTerms) else pack_operator(operator, with_constant=True)
         ps = PauliSum(self, packed)
         try:
-            self._ps_cache[key] = (weakref.ref(operator), ps)
+            self._ps_cache[key] = (weakref.ref(operator), ps, mark)
         except TypeError:
             pass
         if len(self._ps_cache) > 64:

@@ -81,13 +81,49 @@ def n_global_for(world: int) -> int:
     return g
 
 
+# ---- replica mode (states that fit one GPU): OPT-IN ---------------------------------------------------------
+_REPLICA = {"on": False, "group": None}
+
+
+def enable_replica(group=None):
+    """Opt in to SPMD replica mode: every rank of ``group`` (default: the world group) runs the SAME problem in
+    lockstep; the ADAPT pool sweep and the finite-difference evaluations of every BFGS gradient are then split over
+    the ranks.  Off by default: ranks of a torchrun job often work on different problems."""
+    _REPLICA["on"], _REPLICA["group"] = True, group
+
+
+def disable_replica():
+    _REPLICA["on"], _REPLICA["group"] = False, None
+
+
+def replica_enabled() -> bool:
+    return bool(_REPLICA["on"])
+
+
+def replica_group():
+    return _REPLICA["group"]
+
+
+def ranks_agree(payload: bytes, group=None) -> bool:
+    """True when every rank of the group passed the same bytes (CRC-32 + length all-gathered): the guard of every
+    replica-mode split -- ranks that turn out to work on different inputs fall back to the serial path together."""
+    import zlib
+    rows = allgather_f64([float(zlib.crc32(payload)), float(len(payload))], group)
+    return bool(np.all(rows == rows[0]))
+
+
 def replica_pool_overlaps(engine, pool: PackedTerms, bra=BUF_SIGMA, ket=BUF_PSI, group=None):
     """Pool sweep of a state that fits one GPU, split over the ranks (n <= 33): every rank
     holds the same psi and sigma (SPMD: same calls, deterministic kernels), evaluates a contiguous slice of the
     pool and the slices are all-gathered.  No state traffic."""
     dist = _dist()
+    if group is None:
+        group = replica_group()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n_ops = int(pool.offsets.shape[0]) - 1
+    sig = b"".join(np.ascontiguousarray(a).tobytes() for a in (pool.offsets, pool.x, pool.z, pool.cre, pool.cim))
+    if not ranks_agree(sig, group):  # different pools on different ranks: not SPMD, every rank sweeps its own pool
+        return engine.pool_overlaps(pool, bra=bra, ket=ket)
     lo, hi = split_range(n_ops, world, rank)
     width = max(split_range(n_ops, world, r)[1] - split_range(n_ops, world, r)[0] for r in range(world))
     mine = np.zeros(2 * width, dtype=np.float64)
@@ -121,7 +157,8 @@ class ShardedEngine(Engine):
         rank = dist.get_rank(group)
         super().__init__(n_qubits, device, n_global=n_global_for(world), rank=rank)
         self.world = world
-        self._connect([BUF_PSI] + ([BUF_SIGMA] if attach_scratch else []))
+        self._attached = [BUF_PSI] + ([BUF_SIGMA] if attach_scratch else [])
+        self._connect(self._attached)
 
     def _connect(self, bufs):
         """Export this rank's shard(s) and flag array as CUDA IPC handles, all-gather them, map the peers'."""
@@ -148,6 +185,30 @@ class ShardedEngine(Engine):
             v = v[self.rank << self.n_local:(self.rank + 1) << self.n_local]
         super().set_state(v, buf)
 
+    def get_local_state(self, buf=BUF_PSI):
+        """This rank's shard (2^n_local amplitudes)."""
+        return super().get_state(buf)
+
+    def get_state(self, buf=BUF_PSI):
+        """The FULL state vector, all-gathered over the ranks (what the reference-shaped helpers expect from
+        ``get_state``).  Refused above 30 qubits (16 GiB per host copy): use ``get_local_state``."""
+        if self.n > 30:
+            raise _lib.VQEError("sharded state of %d qubits: the full vector does not fit a host array; "
+                                "use get_local_state() for this rank's shard" % self.n)
+        mine = super().get_state(buf)
+        rows = allgather_f64(mine.view(np.float64), self.group)
+        return rows.reshape(-1).view(np.complex128)
+
+    def _need_scratch(self, what):
+        if BUF_SIGMA not in self._attached:
+            raise _lib.VQEError("%s needs a second state buffer on every rank, which is not attached for this sharded state "
+                                "(shards of 2^%d amplitudes: two of them do not fit one GPU); ADAPT sweeps are available on "
+                                "sharded states with n_local <= 32" % (what, self.n_local))
+
+    def apply_paulisum(self, ps, dst=BUF_SIGMA, src=BUF_PSI):
+        self._need_scratch("sigma = H psi")
+        return super().apply_paulisum(ps, dst, src)
+
     def barrier(self):
         _lib.check(self._lib.vqe_shard_barrier(self.handle))
 
@@ -161,6 +222,8 @@ class ShardedEngine(Engine):
         return complex(t[0], t[1])
 
     def pool_overlaps(self, pool: PackedTerms, bra=BUF_SIGMA, ket=BUF_PSI):
+        if BUF_SIGMA in (bra, ket):
+            self._need_scratch("the ADAPT pool sweep")
         part = super().pool_overlaps(pool, bra, ket)
         return self._total(part.view(np.float64)).view(np.complex128)
 
@@ -187,7 +250,9 @@ def enable(min_qubits: int = 34, group=None):
     process after ``torch.distributed.init_process_group``."""
     def factory(n_qubits, device):
         if n_qubits >= min_qubits and dist_ready() and _dist().get_world_size(group) > 1:
-            return ShardedEngine(n_qubits, device, group=group, attach_scratch=n_qubits <= 32)
+            world = _dist().get_world_size(group)
+            # sigma is attached whenever two shards fit one GPU (2 x 2^32 x 16 B = 137 GB of 180 GB)
+            return ShardedEngine(n_qubits, device, group=group, attach_scratch=n_qubits - n_global_for(world) <= 32)
         return None
     engine_mod._ENGINE_FACTORY = factory
 

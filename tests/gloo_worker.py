@@ -57,9 +57,19 @@ def main():
     assert np.array_equal(split, full)
     # the hot-path switch sees the initialised group
     from openvqe_b200 import _hotpath
+    assert not _hotpath.replica_split_active(eng)           # replica mode is opt-in
+    assert _hotpath.distributed_fd(lambda x: 0.0, [])[1] is None
+    sharded.enable_replica()
     assert _hotpath.replica_split_active(eng)
     os.environ["VQE_B200_REPLICA_POOL"] = "0"
     assert not _hotpath.replica_split_active(eng)
+    # ranks that disagree on the inputs are detected (and fall back to the unsplit path together)
+    assert sharded.ranks_agree(b"same")
+    assert not sharded.ranks_agree(b"rank%d" % rank)
+    other = pack_pool(ops[:7] if rank == 0 else ops[1:8])
+    eng2 = StubEngine(psi, sigma, ops)
+    sharded.replica_pool_overlaps(eng2, other)
+    assert eng2.calls == [7]                                # not split: every rank swept its own 7 operators
     # finite-difference gradients of a BFGS run spread over the ranks: same trajectory, same energies list
     import scipy.optimize
     os.environ.pop("VQE_B200_REPLICA_POOL", None)

@@ -16,6 +16,8 @@ def main():
     import torch.distributed as dist
     dist.init_process_group("gloo")
     rank = dist.get_rank()
+    from openvqe_b200 import sharded
+    sharded.enable_replica()   # opt-in: every rank runs the same problem in lockstep
     from openvqe_b200.adapt import fermionic_adapt_vqe as fa
     from openvqe_b200.ucc_family.get_energy_ucc import EnergyUCC
     from oracle import statevector_oracle as orc
