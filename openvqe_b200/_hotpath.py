@@ -151,6 +151,24 @@ def basis_energy(hamiltonian_sp, hf_init_sp, device=None):
     return float(engine.expectation(engine.paulisum(hamiltonian_sp)).real)
 
 
+_MATLIST_CACHE = {}
+
+
+def operators_of_matrices(mats):
+    """Pauli-list operators of a list of 2^n x 2^n matrices (reference cluster_ops_sparse); the converted LIST is cached
+    per list contents so that the pool lowering cache keyed on operator identity keeps hitting."""
+    from .lowering import operator_from_matrix
+    key = tuple(id(m) for m in mats)
+    hit = _MATLIST_CACHE.get(key)
+    if hit is not None and all(a is b for a, b in zip(hit[0], mats)):
+        return hit[1]
+    ops = [operator_from_matrix(m) for m in mats]
+    if len(_MATLIST_CACHE) >= 16:
+        _MATLIST_CACHE.clear()
+    _MATLIST_CACHE[key] = (list(mats), ops)
+    return ops
+
+
 def load_reference_ket(engine, reference_ket):
     """Accept the reference's 2^n x 1 scipy-sparse / dense column or a flat vector."""
     if hasattr(reference_ket, "toarray"):

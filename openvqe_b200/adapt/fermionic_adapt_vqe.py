@@ -10,10 +10,12 @@ changes is where the arithmetic runs:
   scipy expm_multiply per ansatz operator           exact generator exponential on the device
   dense eigh + sample loop (fidelity)               host eigh (n <= 14) + device overlap
 
-The 2^n x 2^n scipy matrices (``hamiltonian_sparse``, ``cluster_ops_sparse``) are still
-accepted but never touched: everything is derived from the Pauli lists ``hamiltonian_sp`` /
-``cluster_ops_sp`` (the same operators, reference molecule_factory_with_sparse.py:339, :615).
-Helpers that take sparse matrices in the reference take the Pauli operators instead.
+The 2^n x 2^n scipy matrices (``hamiltonian_sparse``, ``cluster_ops_sparse``) of the main entry point are accepted
+but never touched: everything is derived from the Pauli lists ``hamiltonian_sp`` / ``cluster_ops_sp`` (the same
+operators, reference molecule_factory_with_sparse.py:339, :615).  The module-level helpers whose reference signature
+takes ONLY matrices (``prepare_adapt_state``, ``compute_gradient_i``, ``return_gradient_list``) accept either the
+Pauli-list operators or, up to 14 qubits, the reference's matrices -- a matrix is decomposed into its Pauli list once
+(``lowering.operator_from_matrix``, cached per object) and then handled by the same kernels.
 """
 import numpy as np
 import scipy.optimize
@@ -22,28 +24,22 @@ from .. import _hotpath
 from ..common_files.circuit import CircuitSummary, count, hf_gates, ucc_circuit
 from ..common_files.sorted_gradient import abs_sort_desc, corresponding_index, index_without_0, value_without_0
 from ..engine import BUF_PSI, get_engine
-from ..lowering import pack_operator
+from ..lowering import as_operator, is_matrix, pack_operator
 
 FIDELITY_MAX_QUBITS = 14  # dense eigh is O(8^n): skipped above this, fidelity reported as nan
 
 
-def _is_matrix(obj):
-    return hasattr(obj, "shape") and not hasattr(obj, "terms")
-
-
 def prepare_adapt_state(reference_ket, spmat_ops, parameters):
     """psi = prod_k exp(theta_k A_k) |ref>, exact exponential of each generator
-    (reference fermionic_adapt_vqe.py:12-38).  ``spmat_ops`` are the anti-Hermitian
-    Pauli-sum generators (cluster_ops_sp entries), not scipy matrices.  Returns the
+    (reference fermionic_adapt_vqe.py:12-38).  ``spmat_ops``: the anti-Hermitian generators as Pauli-sum operators
+    (cluster_ops_sp entries) or as the reference's scipy matrices (cluster_ops_sparse entries, n <= 14).  Returns the
     state as a dense column vector; it also stays resident on the device."""
-    if len(spmat_ops) and _is_matrix(spmat_ops[0]):
-        raise TypeError("openvqe_b200 works from Pauli lists: pass cluster_ops_sp entries, not 2^n x 2^n matrices")
     ket = reference_ket.toarray() if hasattr(reference_ket, "toarray") else np.asarray(reference_ket)
     n = int(np.log2(ket.reshape(-1).shape[0]))
     engine = get_engine(n)
     _hotpath.load_reference_ket(engine, ket)
     for k in range(len(parameters)):
-        engine.apply_exp(_hotpath.packed(spmat_ops[k]), float(parameters[k]))
+        engine.apply_exp(_hotpath.packed(as_operator(spmat_ops[k])), float(parameters[k]))
     return engine.get_state().reshape(-1, 1)
 
 
@@ -52,25 +48,39 @@ def _gradients_on_device(engine, cluster_ops_sp, hamiltonian_sp):
     return _hotpath.snap_ties((2.0 * ov.real).tolist())
 
 
-def compute_gradient_i(i, cluster_ops_sp, v, sig=None, hamiltonian_sp=None):
-    """g_i = 2 Re <H v| A_i |v> (reference :41-74) for one pool operator; ``v`` is a
-    state vector, ``hamiltonian_sp`` the Pauli-list Hamiltonian."""
-    if hamiltonian_sp is None:
-        raise TypeError("compute_gradient_i needs hamiltonian_sp (the engine forms H|v> itself)")
-    engine = get_engine(hamiltonian_sp.nbqbits)
+def compute_gradient_i(i, cluster_ops_sparse, v, sig=None, hamiltonian_sp=None):
+    """g_i = 2 Re <sig| A_i |v> (reference :41-74) for one pool operator.  ``cluster_ops_sparse``: Pauli-sum operators or
+    the reference's matrices; ``v``: state vector; ``sig``: H v as the caller computed it (reference call form), or
+    None together with ``hamiltonian_sp`` (Pauli list or matrix) to let the engine form H v."""
+    from ..engine import BUF_SIGMA
+    op = as_operator(cluster_ops_sparse[i])
+    engine = get_engine(op.nbqbits)
     _hotpath.load_reference_ket(engine, v)
-    return _gradients_on_device(engine, [cluster_ops_sp[i]], hamiltonian_sp)[0]
+    if sig is not None:
+        s = sig.toarray() if hasattr(sig, "toarray") else np.asarray(sig)
+        engine.set_state(np.asarray(s, dtype=np.complex128).reshape(-1), BUF_SIGMA)
+        ov = engine.pool_overlaps(_hotpath.pack_pool([op]), bra=BUF_SIGMA, ket=BUF_PSI)
+        gi = 2.0 * complex(ov[0])
+        assert np.isclose(gi.imag, 0)  # as the reference (:72)
+        return _hotpath.snap_ties([gi.real])[0]
+    if hamiltonian_sp is None:
+        raise TypeError("compute_gradient_i needs sig (= H v) or hamiltonian_sp")
+    return _gradients_on_device(engine, [op], as_operator(hamiltonian_sp))[0]
 
 
-def return_gradient_list(cluster_ops_sp, hamiltonian_sp, curr_state):
+def return_gradient_list(cluster_ops_sparse, hamiltonian_sparse, curr_state):
     """Whole-pool gradient sweep (reference :77-122): returns ``list_grad`` (|g_k|),
-    ``curr_norm`` (sum g_k^2, not yet square-rooted), the signed maximum and its index."""
-    if _is_matrix(hamiltonian_sp) or (len(cluster_ops_sp) and _is_matrix(cluster_ops_sp[0])):
-        raise TypeError("openvqe_b200 works from Pauli lists: pass hamiltonian_sp / cluster_ops_sp")
-    engine = get_engine(hamiltonian_sp.nbqbits)
+    ``curr_norm`` (sum g_k^2, not yet square-rooted), the signed maximum and its index.  Operators and Hamiltonian
+    as Pauli lists (any size) or as the reference's scipy matrices (n <= 14)."""
+    ham = as_operator(hamiltonian_sparse)
+    if len(cluster_ops_sparse) and is_matrix(cluster_ops_sparse[0]):
+        ops = _hotpath.operators_of_matrices(cluster_ops_sparse)
+    else:
+        ops = cluster_ops_sparse
+    engine = get_engine(ham.nbqbits)
     if curr_state is not None:
         _hotpath.load_reference_ket(engine, curr_state)
-    return _gradient_summary(_gradients_on_device(engine, cluster_ops_sp, hamiltonian_sp))
+    return _gradient_summary(_gradients_on_device(engine, ops, ham))
 
 
 def _gradient_summary(grads):

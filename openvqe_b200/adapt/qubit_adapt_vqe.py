@@ -15,7 +15,7 @@ from .. import _hotpath
 from ..common_files.circuit import CircuitSummary, count, hf_gates, ucc_circuit
 from ..common_files.sorted_gradient import abs_sort_desc, corresponding_index, index_without_0, value_without_0
 from ..engine import get_engine
-from ..lowering import pack_operator
+from ..lowering import MATRIX_MAX_QUBITS, as_operator, matrix_of, pack_operator
 
 
 def _hermitian_rotation_form(operator):
@@ -48,22 +48,25 @@ def prepare_adapt_state(reference_state, ansatz, coefficients):
 
 
 def term_to_matrix_sparse(spin_operator):
-    """The reference builds the 2^n x 2^n matrix of a pool operator here (:81-123).  The engine never
-    needs it: the operator itself is handed through (it is lowered to bit masks, once, inside
-    ``calculate_gradient``), so ``calculate_gradient(term_to_matrix_sparse(op), state, H)`` keeps working."""
+    """2^n x 2^n scipy CSR matrix of a pool operator (reference :81-123), built from its bit masks instead of a kron
+    chain and tagged with the operator it came from, so ``calculate_gradient(term_to_matrix_sparse(op), state, H)``
+    costs no decomposition.  Above 14 qubits the matrix is not built: the operator itself is handed through (the
+    engine entry points take either)."""
     if not hasattr(spin_operator, "terms"):
         raise TypeError("term_to_matrix_sparse expects a Pauli-sum operator with .terms")
-    return spin_operator
+    if int(spin_operator.nbqbits) > MATRIX_MAX_QUBITS:
+        return spin_operator
+    return matrix_of(spin_operator)
 
 
-def calculate_gradient(operator, state, hamiltonian_sp):
-    """2 |<state| H A |state>| (reference :126-150); ``operator`` is a pool operator (or
-    what term_to_matrix_sparse returned), ``hamiltonian_sp`` the Pauli-list Hamiltonian."""
-    if hasattr(hamiltonian_sp, "shape") and not hasattr(hamiltonian_sp, "terms"):
-        raise TypeError("openvqe_b200 works from Pauli lists: pass hamiltonian_sp, not its sparse matrix")
-    engine = get_engine(hamiltonian_sp.nbqbits)
+def calculate_gradient(sparse_operator, state, sparse_hamiltonian):
+    """2 |<state| H A |state>| (reference :126-150).  ``sparse_operator`` / ``sparse_hamiltonian``: the reference's
+    scipy matrices (n <= 14; decomposed into Pauli lists once, cached) or the Pauli-sum operators themselves."""
+    ham = as_operator(sparse_hamiltonian)
+    op = as_operator(sparse_operator)
+    engine = get_engine(ham.nbqbits)
     _hotpath.load_reference_ket(engine, state)
-    ov = _hotpath.pool_overlaps(engine, hamiltonian_sp, [operator])
+    ov = _hotpath.pool_overlaps(engine, ham, [op])
     return 2 * float(np.abs(ov[0]))
 
 

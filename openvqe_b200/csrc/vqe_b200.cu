@@ -1083,6 +1083,104 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(Shards psi, TileGeom g, con
     if (bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores have landed
 }
 
+// ------------------------------------------------------------------------------------------
+// Tile ring.  One persistent CTA per SM owns NSLOT shared-memory tile slots (3 x 64 KiB).  Warp 0 is the copy issuer:
+// bulk loads (cp.async.bulk + mbarrier complete_tx) run two tiles ahead of the arithmetic and the bulk store of tile k
+// drains while tile k+1 is being worked on, so HBM traffic and arithmetic overlap by construction instead of relying on
+// several resident CTAs happening to be in different phases.
+//   iteration k (slot k % NSLOT):  wait full[slot] -> arithmetic on the slot -> (store: fence, barrier, warp 0 issues
+//   the bulk store and commits) -> warp 0 waits until the store of tile k-1 has READ its slot and refills that slot
+//   with tile k+2.
+// ------------------------------------------------------------------------------------------
+#define NSLOT 3
+__device__ __forceinline__ void ring_issue_load(double2* slot, const Shards& src, const TileGeom& g, uint64_t base, uint64_t* bar) {
+    // called by all 32 lanes of warp 0
+    const uint32_t ts = 1u << g.tbits;
+    const uint32_t nseg = ts >> g.lbits;
+    const uint32_t seg_bytes = 16u << g.lbits;
+    const uint32_t lane = threadIdx.x & 31u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to the slot come first
+    if (lane == 0) mbar_arrive_expect_tx(bar, ts * 16u);
+    for (uint32_t sgm = lane; sgm < nseg; sgm += 32u) {
+        const uint32_t k = sgm << g.lbits;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(slot + k)),
+                     "l"(amp_addr(g, src, base, k)), "r"(seg_bytes), "r"(smem_u32(bar))
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void ring_issue_store(const double2* slot, const Shards& dst, const TileGeom& g, uint64_t base) {
+    // called by all 32 lanes of warp 0, after every writer has executed fence.proxy.async and the CTA barrier
+    const uint32_t nseg = (1u << g.tbits) >> g.lbits;
+    const uint32_t seg_bytes = 16u << g.lbits;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t sgm = lane; sgm < nseg; sgm += 32u) {
+        const uint32_t k = sgm << g.lbits;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(amp_addr(g, dst, base, k)),
+                     "r"(smem_u32(slot + k)), "r"(seg_bytes)
+                     : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// Collapsed-run passes on the tile ring (see k_tile_col for the per-run arithmetic).  blockDim = 256 when every run has
+// at most 256 items per tile (JW doubles), 512 otherwise.
+template <bool REAL>
+__global__ void __launch_bounds__(512, 1) k_col_pipe(Shards psi, TileGeom g, const DevCol* __restrict__ cols, int n_cols,
+                                                     const DevColEntry* __restrict__ ents, int n_ents, int* __restrict__ err) {
+    extern __shared__ double2 smem_tiles[];
+    const uint32_t ts = 1u << g.tbits;
+    DevCol* scol = (DevCol*)(smem_tiles + (size_t)NSLOT * ts);
+    DevColEntry* sent = (DevColEntry*)(scol + n_cols);
+    uint32_t* scsign = (uint32_t*)(sent + n_ents);  // [2][n_cols]: outside-tile Z parity of every run, double-buffered per tile
+    __shared__ __align__(8) uint64_t s_full[NSLOT];
+    const uint32_t warp = threadIdx.x >> 5, bd = blockDim.x;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < NSLOT; ++i) mbar_init(&s_full[i], 1);
+    for (int q = threadIdx.x; q < n_cols; q += bd) scol[q] = cols[q];
+    for (int q = threadIdx.x; q < n_ents; q += bd) sent[q] = ents[q];
+    const BaseLane bl = base_lane_init(g);
+    const uint64_t n_my = g.n_tiles > blockIdx.x ? (g.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    __syncthreads();  // barriers initialised, tables in place
+    if (warp == 0)
+        for (uint64_t k = 0; k < 2 && k < n_my; ++k)
+            ring_issue_load(smem_tiles + (size_t)(k % NSLOT) * ts, psi, g, tile_base_warp(g, bl, blockIdx.x + k * gridDim.x), &s_full[k % NSLOT]);
+    for (uint64_t k = 0; k < n_my; ++k) {
+        const uint32_t sl = (uint32_t)(k % NSLOT);
+        double2* tile = smem_tiles + (size_t)sl * ts;
+        const uint64_t base = tile_base_warp(g, bl, blockIdx.x + k * gridDim.x);
+        const uint64_t sbase = base | g.sign_base;
+        uint32_t* csign = scsign + (k & 1u) * n_cols;
+        for (int r = threadIdx.x; r < n_cols; r += bd) csign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
+        __syncthreads();  // signs of this tile visible (the other half of the double buffer may still be read by stragglers)
+        ColItem cur = col_prep(scol, sent, csign, 0, n_cols, threadIdx.x);
+        if (!mbar_wait(&s_full[sl], (uint32_t)((k / NSLOT) & 1u)) && err) *err = 2;
+        for (int q = 0; q < n_cols; ++q) {
+            const uint32_t items = cur.items;
+            ColItem nxt = col_prep(scol, sent, csign, q + 1, n_cols, threadIdx.x);
+            if (cur.valid) col_apply<REAL>(tile, cur);
+            for (uint32_t it = threadIdx.x + bd; it < items; it += bd) {
+                const ColItem ci = col_prep(scol, sent, csign, q, n_cols, it);
+                col_apply<REAL>(tile, ci);
+            }
+            cur = nxt;
+            if (q + 1 == n_cols) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes -> the bulk store
+            __syncthreads();
+        }
+        if (n_cols == 0) __syncthreads();  // (VQE_DEBUG_SKELETON: copy skeleton only)
+        if (warp == 0) {
+            ring_issue_store(tile, psi, g, base);
+            if (k + 2 < n_my) {
+                // the slot of tile k-1 is refilled with tile k+2 once its store has read shared memory
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                ring_issue_load(smem_tiles + (size_t)((k + 2) % NSLOT) * ts, psi, g,
+                                tile_base_warp(g, bl, blockIdx.x + (k + 2) * gridDim.x), &s_full[(k + 2) % NSLOT]);
+            }
+        }
+    }
+    if (warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores have landed
+}
+
 __global__ void __launch_bounds__(512, 2) k_tile_ops(Shards psi, TileGeom g,
                                                   const DevOp* __restrict__ ops, int n_ops,
                                                   const double* __restrict__ mats) {
@@ -1765,6 +1863,90 @@ __global__ void __launch_bounds__(256, 3) k_expect_lean(Shards psi, TileGeom g, 
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
 }
 
+// The same evaluation on the tile ring (one persistent CTA per SM, loads three tiles ahead of the arithmetic).
+__device__ __forceinline__ void ring_issue_load(double2* slot, const Shards& src, const TileGeom& g, uint64_t base, uint64_t* bar);
+template <bool REAL>
+__device__ __forceinline__ double lean_entry(const char* tb, const DevFlat2* __restrict__ flats, int e, uint32_t lane, uint64_t sbase,
+                                             const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
+                                             const double* s_beta) {
+    const uint4* ep = reinterpret_cast<const uint4*>(flats + e);
+    const uint4 q0 = __ldg(ep), q1 = __ldg(ep + 1), q2 = __ldg(ep + 2);
+    LeanUnit u;
+    lean_decode(q0, q1, q2, lane, u);
+    const uint32_t sg = u.s0 + (uint32_t)__popcll(sbase & __ldg(fzout + (q0.w >> 16)));
+    double part = 0.0;
+    if (u.tab == 0xffffu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t off = u.v | u.o[j];
+            double w;
+            if (REAL) {
+                w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
+            } else {
+                const double2 a = *reinterpret_cast<const double2*>(tb + off);
+                const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
+                w = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
+            }
+            part += flipsign(w, u.jsign >> j);
+        }
+    } else {
+        const double gl = s_beta[u.bidx] + __ldg(addtab + u.tab + lane);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t off = u.v | u.o[j];
+            double w;
+            if (REAL) {
+                w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
+            } else {
+                const double2 a = *reinterpret_cast<const double2*>(tb + off);
+                const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
+                w = fma(b.x, a.x, b.y * a.y);
+            }
+            part = fma(flipsign(w, u.jsign >> j), gl + __ldg(addtab + u.hi0 + j), part);
+        }
+    }
+    return u.fr * flipsign(part, sg);
+}
+template <bool REAL>
+__global__ void __launch_bounds__(512, 1) k_expect_pipe(Shards psi, TileGeom g, const DevFlat2* __restrict__ flats, int n_flats,
+                                                        const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
+                                                        const DevAddPat* __restrict__ addpat, int n_addpat,
+                                                        const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
+                                                        int* __restrict__ err) {
+    extern __shared__ double2 smem_tiles[];
+    __shared__ double red[64];
+    __shared__ __align__(8) uint64_t s_full[3];
+    const uint32_t ts = 1u << g.tbits;
+    double* s_beta = (double*)(smem_tiles + (size_t)3 * ts);  // [2][n_addpat], double-buffered per tile
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], 1);
+    const BaseLane bl = base_lane_init(g);
+    const int fper = (n_flats + gridDim.y - 1) / gridDim.y;
+    const int f0 = min(n_flats, (int)blockIdx.y * fper), f1 = min(n_flats, f0 + fper);
+    const uint64_t n_my = g.n_tiles > blockIdx.x ? (g.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    __syncthreads();
+    if (warp == 0)
+        for (uint64_t k = 0; k < 3 && k < n_my; ++k)
+            ring_issue_load(smem_tiles + (size_t)k * ts, psi, g, tile_base_warp(g, bl, blockIdx.x + k * gridDim.x), &s_full[k]);
+    double er = 0.0;
+    for (uint64_t k = 0; k < n_my; ++k) {
+        const uint32_t sl = (uint32_t)(k % 3);
+        const char* tb = (const char*)(smem_tiles + (size_t)sl * ts);
+        const uint64_t sbase = tile_base_warp(g, bl, blockIdx.x + k * gridDim.x) | g.sign_base;
+        double* beta = s_beta + (k & 1u) * n_addpat;
+        lean_betas(beta, addpat, n_addpat, addout, sbase);
+        __syncthreads();  // constants visible; every warp has left tile k-1 (its slot may be refilled below)
+        if (warp == 0 && k >= 1 && k + 2 < n_my)
+            ring_issue_load(smem_tiles + (size_t)((k + 2) % 3) * ts, psi, g, tile_base_warp(g, bl, blockIdx.x + (k + 2) * gridDim.x),
+                            &s_full[(k + 2) % 3]);
+        if (!mbar_wait(&s_full[sl], (uint32_t)((k / 3) & 1u)) && err) *err = 2;
+        for (int e = f0 + (int)warp; e < f1; e += (int)nw) er += lean_entry<REAL>(tb, flats, e, lane, sbase, fzout, addtab, beta);
+    }
+    double2 sres = block_sum2(er, 0.0, red);
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
+}
+
 // sigma (+)= O psi for a lean pass.  The CTA holds the source tile and an accumulator tile (REAL: real parts only,
 // 32 KiB -> two CTAs per SM) and walks the groups in order: one thread per (pattern, free index) pair,
 //     acc[l ^ x] += G(l) psi[l],   acc[l] += G(l) psi[l ^ x]        (even-ny strings: the same weight both ways)
@@ -2117,6 +2299,10 @@ static int set_kernel_attrs(int device) {
     SET_SMEM(k_tile_rot<true>);
     SET_SMEM(k_tile_col<false>);
     SET_SMEM(k_tile_col<true>);
+    SET_SMEM(k_col_pipe<false>);
+    SET_SMEM(k_col_pipe<true>);
+    SET_SMEM(k_expect_pipe<false>);
+    SET_SMEM(k_expect_pipe<true>);
     SET_SMEM(k_tile_expect<false>);
     SET_SMEM(k_tile_expect<true>);
     SET_SMEM(k_tile_apply);
@@ -3199,7 +3385,25 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
             const size_t smem_c = tile_smem(ps.tp.tbits, 1, false) + (size_t)n_cols * (sizeof(DevCol) + 4) + (size_t)n_ents * sizeof(DevColEntry);
             const int thr = (int)std::min<uint64_t>(256, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
             const int grid = tile_grid(c, g.n_tiles, smem_c <= 74 * 1024 ? 3 : 2);
-            if (real_pass[p])
+            const size_t smem_p = (size_t)NSLOT * tile_smem(ps.tp.tbits, 1, false) + (size_t)n_cols * (sizeof(DevCol) + 8) +
+                                  (size_t)n_ents * sizeof(DevColEntry);
+            if (g.bulk && smem_p <= 226 * 1024 && env_int("VQE_PIPE", 1) != 0) {
+                // tile ring: one persistent CTA per SM, loads two tiles ahead, stores draining behind
+                uint32_t max_items = 0;
+                for (size_t q = ps.col_begin; q < ps.col_end; ++q)
+                    max_items = std::max(max_items, plan.dcols[q].n_active << plan.dcols[q].free_log);
+                const int thr_p = (int)std::min<uint64_t>(max_items <= 256 ? 256 : 512, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
+                const int grid_p = tile_grid(c, g.n_tiles, 1);
+                if (env_int("VQE_DEBUG_SKELETON", 0))  // measurement aid: loads and stores only, no arithmetic (results are wrong)
+                    k_col_pipe<true><<<grid_p, thr_p, smem_p, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, 0,
+                                                                          (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, 0, c->d_err);
+                else if (real_pass[p])
+                    k_col_pipe<true><<<grid_p, thr_p, smem_p, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                                                                          (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
+                else
+                    k_col_pipe<false><<<grid_p, thr_p, smem_p, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                                                                           (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
+            } else if (real_pass[p])
                 k_tile_col<true><<<grid, thr, smem_c, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                   (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
             else
@@ -4609,8 +4813,10 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                 grids[k][p] = dim3(0, 0, 1);
                 continue;
             }
-            int gx = tile_grid(c, geoms[k][p].n_tiles, pp.lean ? 3 : 0);
-            int want = std::max(1, (c->sm_count * (pp.lean ? 3 : c->ctas_per_sm)) / gx);
+            const bool pipe = pp.lean && geoms[k][p].bulk && env_int("VQE_PIPE", 1) != 0 &&
+                              3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double) <= 226 * 1024;
+            int gx = tile_grid(c, geoms[k][p].n_tiles, pipe ? 1 : (pp.lean ? 3 : 0));
+            int want = std::max(1, (c->sm_count * (pipe ? 1 : (pp.lean ? 3 : c->ctas_per_sm))) / gx);
             int gy = std::max(1, std::min<int>(pp.lean ? (int)((pp.flats2.size() + 7) / 8) : (int)pp.groups.size(), want));
             grids[k][p] = dim3(gx, gy, 1);
             total_blocks[k] += (size_t)gx * gy;
@@ -4635,7 +4841,25 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             size_t smem = tile_smem(pp.tp.tbits, 1, true);
             int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << pp.tp.tbits) / 2));
             ProfScope prof(c, vbit ? 5 : 1);
-            if (pp.lean) {
+            const bool pipe = pp.lean && geoms[k][p].bulk && env_int("VQE_PIPE", 1) != 0 &&
+                              3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double) <= 226 * 1024;
+            if (pipe) {
+                const size_t smem_p = 3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double);
+                int thr_p = env_int("VQE_EXP_THREADS", 512);
+                if (thr_p < 32 || thr_p > 512 || (thr_p & 31)) thr_p = 512;
+                if (env_int("VQE_DEBUG_SKELETON", 0))  // measurement aid: loads only (results are wrong)
+                    k_expect_pipe<true><<<grids[k][p], thr_p, smem_p, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, 0,
+                                                                                  pp.d_fzout, pp.d_addtab, pp.d_addpat, 0,
+                                                                                  pp.d_addout, c->d_partial + off[k], c->d_err);
+                else if (real_state)
+                    k_expect_pipe<true><<<grids[k][p], thr_p, smem_p, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
+                                                                                  pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
+                                                                                  pp.d_addout, c->d_partial + off[k], c->d_err);
+                else
+                    k_expect_pipe<false><<<grids[k][p], thr_p, smem_p, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
+                                                                                   pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
+                                                                                   pp.d_addout, c->d_partial + off[k], c->d_err);
+            } else if (pp.lean) {
                 const size_t smem_l = tile_smem(pp.tp.tbits, 1, false) + pp.addpat.size() * sizeof(double);
                 if (real_state)
                     k_expect_lean<true><<<grids[k][p], 256, smem_l, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),

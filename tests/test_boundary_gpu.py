@@ -249,3 +249,47 @@ def test_adjoint_opt_in_reaches_the_same_minimum(gpu_required, h2, monkeypatch):
     it_ad, res_ad = quiet(EnergyUCC().get_energies, ham, ops, ops, h2["hf_init_sp"], th0, th0, h2["fci"])
     assert abs(min(res_fd["energies_1"]) - it_ad["minimum_energy_result1_guess"][0]) < 1e-6
     assert len(res_ad["energies_1"]) < len(res_fd["energies_1"]) / 3     # no finite-difference evaluations
+
+
+def test_helpers_accept_the_reference_matrix_arguments(gpu_required, h2):
+    """The module-level ADAPT helpers keep the reference's call forms (fermionic_adapt_vqe.py:12-122,
+    qubit_adapt_vqe.py:81-150): 2^n x 2^n scipy matrices for the pool operators, the Hamiltonian and sigma = H v.  A matrix
+    is decomposed into its Pauli list once; results equal the scipy arithmetic the reference performs on them."""
+    import scipy.sparse.linalg
+    from openvqe_b200.adapt import fermionic_adapt_vqe as fa
+    from openvqe_b200.adapt import qubit_adapt_vqe as qa
+    from openvqe_b200 import lowering
+    ham = h2["_ham"]
+    pool = pool_from_json(8, h2["spin_complement_gsd"])
+    H = orc.sparse_matrix(ham)
+    mats = [orc.sparse_matrix(op) for op in pool]
+    psi = orc.basis_state(8, h2["hf_init_sp"])
+    # reference arithmetic, verbatim
+    v = scipy.sparse.csc_matrix(psi.reshape(-1, 1))
+    v = scipy.sparse.linalg.expm_multiply(0.13 * mats[38], v.toarray())
+    v = scipy.sparse.linalg.expm_multiply(-0.07 * mats[32], v)
+    sig = H.dot(v)
+    g_ref = [2 * (sig.transpose().conj().dot(m.dot(v)))[0, 0].real for m in mats]
+    # the same calls on the engine
+    st = fa.prepare_adapt_state(psi.reshape(-1, 1), mats, [0.13, -0.07])
+    assert np.max(np.abs(st - v)) < 1e-12
+    lg, nrm, nd, ni = fa.return_gradient_list(mats, H, st)
+    assert np.max(np.abs(np.array(lg) - np.abs(g_ref))) < TOL
+    assert ni == int(np.argmax(np.abs(_hotpath_snap(g_ref)))) and abs(nd - g_ref[ni]) < TOL
+    for i in (2, 23, 38):
+        assert abs(fa.compute_gradient_i(i, mats, st, sig) - g_ref[i]) < TOL            # reference call form: sig given
+        assert abs(fa.compute_gradient_i(i, pool, st, None, hamiltonian_sp=ham) - g_ref[i]) < TOL
+    # matrix <-> Pauli list round trip, and the qubit-ADAPT helpers
+    assert abs(lowering.matrix_of(lowering.operator_from_matrix(H)) - H).max() < 1e-13
+    qpool = pool_from_json(8, h2["qubit_pool_random_seed7"]) if "qubit_pool_random_seed7" in h2 else None
+    if qpool:
+        for op in qpool[:6]:
+            A = qa.term_to_matrix_sparse(op)
+            ref = 2 * np.abs((st.conj().T @ (H @ (A @ st)))[0, 0])
+            assert abs(qa.calculate_gradient(A, st, H) - ref) < TOL                      # matrices, as the reference passes them
+            assert abs(qa.calculate_gradient(op, st, ham) - ref) < TOL                   # Pauli lists
+
+
+def _hotpath_snap(values):
+    from openvqe_b200._hotpath import snap_ties
+    return snap_ties(list(values))
