@@ -217,6 +217,12 @@ int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int tile_bits, int
                         const double* psi_re_im, double* out_re, int32_t* n_lean_terms, int32_t* n_fat_terms,
                         double* sigma_re_im);
 
+/* Host-only check (no CUDA call; test support) of the tensor-map (TMA) form of the tile plan that covers the local
+ * index bits `need_mask`: emulates the box traversal of every request and compares with the gather addresses of the
+ * tile.  Returns the number of mismatching elements (0 = consistent), -1 when the plan keeps per-segment copies. */
+int vqe_debug_tma_check(int n_local, uint64_t need_mask, int tile_bits, int low_bits, int max_tiles, int32_t* n_req,
+                        int32_t* dims_used);
+
 /* Raw device pointer / stream of a buffer. */
 int vqe_buffer_ptr(vqe_ctx* ctx, int buf, void** dev_ptr, uint64_t* n_amplitudes);
 int vqe_synchronize(vqe_ctx* ctx);

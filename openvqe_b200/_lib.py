@@ -25,7 +25,7 @@ SYMBOLS = [
     "vqe_create_shard", "vqe_shard_info", "vqe_shard_export", "vqe_shard_attach_ipc", "vqe_shard_attach_local",
     "vqe_shard_barrier", "vqe_shard_status", "vqe_group_apply_pauli_rotations", "vqe_group_apply_gates",
     "vqe_group_expectation", "vqe_group_apply_paulisum", "vqe_group_pool_overlaps", "vqe_plan_rotations",
-    "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf", "vqe_plan_paulisum", "vqe_debug_lean_host", "vqe_peer_bytes",
+    "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf", "vqe_plan_paulisum", "vqe_debug_lean_host", "vqe_peer_bytes", "vqe_debug_tma_check",
 ]
 IPC_HANDLE_BYTES = 64
 SHARD_FLAGS = 3
@@ -101,6 +101,7 @@ def load():
                                          vp, vp, vp, vp, vp]),
         "vqe_plan_paulisum": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp,
                                         C.c_int, vp, vp, vp]),
+        "vqe_debug_tma_check": (C.c_int, [C.c_int, u64, C.c_int, C.c_int, C.c_int, P(i32), P(i32)]),
         "vqe_peer_bytes": (C.c_int, [vp, P(u64), C.c_int]),
         "vqe_debug_lean_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                           P(dbl), P(i32), P(i32), vp]),

@@ -23,6 +23,7 @@
 //   * Persistent grids sized from the SM count; one stream per context.
 //
 // No CPU fallback: every entry point that computes needs a CUDA device.
+#include <cuda.h>  // CUtensorMap (the encoder entry point is fetched at run time, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -86,6 +87,20 @@ struct DevOp {       // 64 bytes
     uint32_t imag;   // ROTF: 1 when the unit phase is +-i (ny even)
 };
 
+// Tensor-map form of a tile (TMA, cp.async.bulk.tensor).  The shard is described to the TMA unit as a <= 5-dimensional
+// array of doubles whose dimensions start at the runs of adjacent tile bits: dimension i covers the index bits
+// [shift[i], shift[i+1]), its box is the run of tile bits at its start.  One request then fetches the whole tile (or, when
+// the tile bits form more than five runs, the part selected by the remaining high tile bits: n_req <= 16 requests)
+// instead of one bulk copy per 512-byte segment -- the TMA unit serves a request in ~40 cycles whatever its size, so
+// per-segment copies cap a tile pass at about half of the HBM bandwidth.
+struct TmaGeom {
+    uint32_t shift[5];     // first index bit of dimension i
+    uint32_t cmask[5];     // (1 << number of index bits covered by dimension i) - 1
+    uint32_t n_req;        // requests per tile
+    uint32_t req_amps;     // amplitudes per request
+    uint64_t req_bits[16]; // index bits of request r (its pattern on the tile bits beyond the fifth run)
+};
+
 struct TileGeom {
     uint64_t comp_mask;  // (shard-)local index bits NOT in the tile
     uint64_t n_tiles;    // number of tiles THIS launch walks
@@ -97,6 +112,8 @@ struct TileGeom {
     uint32_t tile_stride;
     uint32_t vbit;         // 1: the top tile bit is VIRTUAL -- it selects the shard (0: p0 = lower rank, 1: p1 = r ^ m)
     uint32_t bulk;         // 1: stage the tile with bulk asynchronous copies (cp.async.bulk, one per contiguous segment)
+    uint32_t tma;          // 1: stage the tile with tensor-map requests (tg + the CUtensorMap kernel parameter)
+    TmaGeom tg;
 };
 
 // Peer pass, "gather" form.  When the operations of a peer pass couple only a fraction of the partner's amplitudes
@@ -624,6 +641,37 @@ __device__ __forceinline__ void tile_store_bulk(const double2* tile, const Shard
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// ---- tensor-map tile load / store: issued by ONE thread -------------------------------------------------------------
+__device__ __forceinline__ void tma_coords(const TmaGeom& tg, uint64_t idx, int (&c)[5]) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) c[i] = (int)((uint32_t)(idx >> tg.shift[i]) & tg.cmask[i]);
+    c[0] <<= 1;  // dimension 0 counts doubles (re, im)
+}
+__device__ __forceinline__ void tma_load_tile(double2* tile, const CUtensorMap* tm, const TileGeom& g, uint64_t base, uint64_t* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to the slot come first
+    mbar_arrive_expect_tx(bar, 16u << g.tbits);
+    for (uint32_t r = 0; r < g.tg.n_req; ++r) {
+        int c[5];
+        tma_coords(g.tg, base | g.tg.req_bits[r], c);
+        asm volatile(
+            "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                smem_u32(tile + (size_t)r * g.tg.req_amps)),
+            "l"(tm), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(smem_u32(bar))
+            : "memory");
+    }
+}
+// the caller has made the tile's generic writes visible to the async proxy (fence.proxy.async by the writers + barrier)
+__device__ __forceinline__ void tma_store_tile(const double2* tile, const CUtensorMap* tm, const TileGeom& g, uint64_t base) {
+    for (uint32_t r = 0; r < g.tg.n_req; ++r) {
+        int c[5];
+        tma_coords(g.tg, base | g.tg.req_bits[r], c);
+        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tm), "r"(c[0]),
+                     "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(smem_u32(tile + (size_t)r * g.tg.req_amps))
+                     : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 __device__ __forceinline__ void tile_load_async_fast(double2* tile, const Shards& src, const TileGeom& g, const TileAddr& ta,
                                                      const uint64_t* s_boff, uint64_t base) {
     if (!ta.fast) {
@@ -789,7 +837,7 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
                                                      const DevCol* __restrict__ cols, int n_cols,
                                                      const DevColEntry* __restrict__ ents, int n_ents, double pass_scale,
                                                      int* __restrict__ err) {
-    extern __shared__ double2 tile[];
+    extern __shared__ __align__(128) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     const bool four = (ts >> 1) == 4u * blockDim.x;  // host guarantees: 4 pairs (one orbit) per thread, or at most 1 pair
     RotOp* optab = (RotOp*)(tile + ts);
@@ -1031,16 +1079,18 @@ __device__ __forceinline__ void col_apply(double2* tile, const ColItem& ci) {
     }
 }
 template <bool REAL>
-__global__ void __launch_bounds__(256, 3) k_tile_col(Shards psi, TileGeom g, const DevCol* __restrict__ cols, int n_cols,
+__global__ void __launch_bounds__(256, 3) k_tile_col(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
+                                                     const DevCol* __restrict__ cols, int n_cols,
                                                      const DevColEntry* __restrict__ ents, int n_ents, int* __restrict__ err) {
-    extern __shared__ double2 tile[];
+    extern __shared__ __align__(128) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     DevCol* scol = (DevCol*)(tile + ts);
     DevColEntry* sent = (DevColEntry*)(scol + n_cols);
     uint32_t* scsign = (uint32_t*)(sent + n_ents);  // per tile: outside-tile Z parity of every run
     __shared__ uint64_t s_boff[16];
     __shared__ __align__(8) uint64_t s_mbar;
-    const bool bulk = g.bulk != 0;
+    const bool tma = g.tma != 0;
+    const bool bulk = g.bulk != 0 || tma;
     uint32_t mphase = 0;
     if (bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
     const TileAddr ta = tile_addr_init(g, s_boff);
@@ -1052,7 +1102,9 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(Shards psi, TileGeom g, con
         const uint64_t base = tile_base_warp(g, bl, t);
         const uint64_t sbase = base | g.sign_base;
         __syncthreads();  // the previous tile has left shared memory (bulk store has read it); tables are in place
-        if (bulk) tile_load_bulk(tile, psi, g, base, &s_mbar);
+        if (tma) {
+            if (threadIdx.x == 0) tma_load_tile(tile, &tmap, g, base, &s_mbar);
+        } else if (bulk) tile_load_bulk(tile, psi, g, base, &s_mbar);
         else tile_load_async_fast(tile, psi, g, ta, s_boff, base);
         for (int r = threadIdx.x; r < n_cols; r += bd) scsign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
         __syncthreads();  // scsign visible
@@ -1075,9 +1127,15 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(Shards psi, TileGeom g, con
                 col_apply<REAL>(tile, ci);
             }
             cur = nxt;
+            if (tma && q + 1 == n_cols) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes -> the TMA store
             __syncthreads();
         }
-        if (bulk) tile_store_bulk(tile, psi, g, base);
+        if (tma) {
+            if (threadIdx.x == 0) {
+                tma_store_tile(tile, &tmap, g, base);
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else if (bulk) tile_store_bulk(tile, psi, g, base);
         else tile_store_scaled_fast(tile, psi, g, ta, s_boff, base, 1.0);
     }
     if (bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores have landed
@@ -1093,8 +1151,13 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(Shards psi, TileGeom g, con
 //   with tile k+2.
 // ------------------------------------------------------------------------------------------
 #define NSLOT 3
-__device__ __forceinline__ void ring_issue_load(double2* slot, const Shards& src, const TileGeom& g, uint64_t base, uint64_t* bar) {
+__device__ __forceinline__ void ring_issue_load(double2* slot, const Shards& src, const TileGeom& g, uint64_t base, uint64_t* bar,
+                                                const CUtensorMap* tm) {
     // called by all 32 lanes of warp 0
+    if (g.tma) {
+        if ((threadIdx.x & 31u) == 0) tma_load_tile(slot, tm, g, base, bar);
+        return;
+    }
     const uint32_t ts = 1u << g.tbits;
     const uint32_t nseg = ts >> g.lbits;
     const uint32_t seg_bytes = 16u << g.lbits;
@@ -1109,8 +1172,13 @@ __device__ __forceinline__ void ring_issue_load(double2* slot, const Shards& src
                      : "memory");
     }
 }
-__device__ __forceinline__ void ring_issue_store(const double2* slot, const Shards& dst, const TileGeom& g, uint64_t base) {
+__device__ __forceinline__ void ring_issue_store(const double2* slot, const Shards& dst, const TileGeom& g, uint64_t base,
+                                                 const CUtensorMap* tm) {
     // called by all 32 lanes of warp 0, after every writer has executed fence.proxy.async and the CTA barrier
+    if (g.tma) {
+        if ((threadIdx.x & 31u) == 0) tma_store_tile(slot, tm, g, base);
+        return;
+    }
     const uint32_t nseg = (1u << g.tbits) >> g.lbits;
     const uint32_t seg_bytes = 16u << g.lbits;
     const uint32_t lane = threadIdx.x & 31u;
@@ -1126,9 +1194,10 @@ __device__ __forceinline__ void ring_issue_store(const double2* slot, const Shar
 // Collapsed-run passes on the tile ring (see k_tile_col for the per-run arithmetic).  blockDim = 256 when every run has
 // at most 256 items per tile (JW doubles), 512 otherwise.
 template <bool REAL>
-__global__ void __launch_bounds__(512, 1) k_col_pipe(Shards psi, TileGeom g, const DevCol* __restrict__ cols, int n_cols,
+__global__ void __launch_bounds__(512, 1) k_col_pipe(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
+                                                     const DevCol* __restrict__ cols, int n_cols,
                                                      const DevColEntry* __restrict__ ents, int n_ents, int* __restrict__ err) {
-    extern __shared__ double2 smem_tiles[];
+    extern __shared__ __align__(128) double2 smem_tiles[];
     const uint32_t ts = 1u << g.tbits;
     DevCol* scol = (DevCol*)(smem_tiles + (size_t)NSLOT * ts);
     DevColEntry* sent = (DevColEntry*)(scol + n_cols);
@@ -1144,7 +1213,7 @@ __global__ void __launch_bounds__(512, 1) k_col_pipe(Shards psi, TileGeom g, con
     __syncthreads();  // barriers initialised, tables in place
     if (warp == 0)
         for (uint64_t k = 0; k < 2 && k < n_my; ++k)
-            ring_issue_load(smem_tiles + (size_t)(k % NSLOT) * ts, psi, g, tile_base_warp(g, bl, blockIdx.x + k * gridDim.x), &s_full[k % NSLOT]);
+            ring_issue_load(smem_tiles + (size_t)(k % NSLOT) * ts, psi, g, tile_base_warp(g, bl, blockIdx.x + k * gridDim.x), &s_full[k % NSLOT], &tmap);
     for (uint64_t k = 0; k < n_my; ++k) {
         const uint32_t sl = (uint32_t)(k % NSLOT);
         double2* tile = smem_tiles + (size_t)sl * ts;
@@ -1169,12 +1238,12 @@ __global__ void __launch_bounds__(512, 1) k_col_pipe(Shards psi, TileGeom g, con
         }
         if (n_cols == 0) __syncthreads();  // (VQE_DEBUG_SKELETON: copy skeleton only)
         if (warp == 0) {
-            ring_issue_store(tile, psi, g, base);
+            ring_issue_store(tile, psi, g, base, &tmap);
             if (k + 2 < n_my) {
                 // the slot of tile k-1 is refilled with tile k+2 once its store has read shared memory
+                const uint64_t base2 = tile_base_warp(g, bl, blockIdx.x + (k + 2) * gridDim.x);
                 asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                ring_issue_load(smem_tiles + (size_t)((k + 2) % NSLOT) * ts, psi, g,
-                                tile_base_warp(g, bl, blockIdx.x + (k + 2) * gridDim.x), &s_full[(k + 2) % NSLOT]);
+                ring_issue_load(smem_tiles + (size_t)((k + 2) % NSLOT) * ts, psi, g, base2, &s_full[(k + 2) % NSLOT], &tmap);
             }
         }
     }
@@ -1184,7 +1253,7 @@ __global__ void __launch_bounds__(512, 1) k_col_pipe(Shards psi, TileGeom g, con
 __global__ void __launch_bounds__(512, 2) k_tile_ops(Shards psi, TileGeom g,
                                                   const DevOp* __restrict__ ops, int n_ops,
                                                   const double* __restrict__ mats) {
-    extern __shared__ double2 tile[];
+    extern __shared__ __align__(128) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     const uint32_t half = ts >> 1;
     FastOp* optab = (FastOp*)(tile + ts);  // n_ops entries (host caps n_ops per pass at OPTAB_CAP)
@@ -1284,7 +1353,7 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
                                                         const DevFlat* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout,
                                                         double2* __restrict__ partial, int* __restrict__ err) {
-    extern __shared__ double2 tile[];
+    extern __shared__ __align__(128) double2 tile[];
     __shared__ double red[64];
     const uint32_t ts = 1u << g.tbits;
     const uint32_t half = ts >> 1;
@@ -1508,7 +1577,7 @@ __global__ void __launch_bounds__(1024, 1) k_tile_apply(Shards src, Shards dst, 
                                                         int n_groups, const DevTerm* __restrict__ terms,
                                                         const DevAFlat* __restrict__ aflat, const uint32_t* __restrict__ aoff,
                                                         const uint64_t* __restrict__ azout, int accumulate) {
-    extern __shared__ double2 tile[];
+    extern __shared__ __align__(128) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     double2* acc = tile + ts;
     double2* s_coef = acc + ts;                                  // TERM_CAP
@@ -1622,7 +1691,7 @@ __global__ void __launch_bounds__(512) k_tile_pool(Shards bra, Shards ket, TileG
                                                    const DevPoolTerm* __restrict__ terms,
                                                    const DevGCol* __restrict__ pcols, const DevGColEntry* __restrict__ pents,
                                                    double2* __restrict__ partial /* [gridDim.x][n_pops] */) {
-    extern __shared__ double2 tile[];
+    extern __shared__ __align__(128) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     double2* tbra = tile;
     double2* tket = tile + ts;
@@ -1783,18 +1852,20 @@ __device__ __forceinline__ void lean_betas(double* s_beta, const DevAddPat* __re
 }
 
 template <bool REAL>
-__global__ void __launch_bounds__(256, 3) k_expect_lean(Shards psi, TileGeom g, const DevFlat2* __restrict__ flats, int n_flats,
+__global__ void __launch_bounds__(256, 3) k_expect_lean(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
+                                                        const DevFlat2* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
                                                         const DevAddPat* __restrict__ addpat, int n_addpat,
                                                         const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
                                                         int* __restrict__ err) {
-    extern __shared__ double2 tile[];
+    extern __shared__ __align__(128) double2 tile[];
     __shared__ double red[64];
     __shared__ uint64_t s_boff[16];
     __shared__ __align__(8) uint64_t s_mbar;
     const uint32_t ts = 1u << g.tbits;
     double* s_beta = (double*)(tile + ts);
-    const bool bulk = g.bulk != 0;
+    const bool tma = g.tma != 0;
+    const bool bulk = g.bulk != 0 || tma;
     uint32_t mphase = 0;
     if (bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
     const TileAddr ta = tile_addr_init(g, s_boff);
@@ -1809,7 +1880,9 @@ __global__ void __launch_bounds__(256, 3) k_expect_lean(Shards psi, TileGeom g, 
         const uint64_t base = tile_base_warp(g, bl, t);
         const uint64_t sbase = base | g.sign_base;
         __syncthreads();  // previous tile fully consumed
-        if (bulk) tile_load_bulk(tile, psi, g, base, &s_mbar);
+        if (tma) {
+            if (threadIdx.x == 0) tma_load_tile(tile, &tmap, g, base, &s_mbar);
+        } else if (bulk) tile_load_bulk(tile, psi, g, base, &s_mbar);
         else tile_load_async_fast(tile, psi, g, ta, s_boff, base);
         lean_betas(s_beta, addpat, n_addpat, addout, sbase);
         if (bulk) {
@@ -1864,7 +1937,6 @@ __global__ void __launch_bounds__(256, 3) k_expect_lean(Shards psi, TileGeom g, 
 }
 
 // The same evaluation on the tile ring (one persistent CTA per SM, loads three tiles ahead of the arithmetic).
-__device__ __forceinline__ void ring_issue_load(double2* slot, const Shards& src, const TileGeom& g, uint64_t base, uint64_t* bar);
 template <bool REAL>
 __device__ __forceinline__ double lean_entry(const char* tb, const DevFlat2* __restrict__ flats, int e, uint32_t lane, uint64_t sbase,
                                              const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
@@ -1908,12 +1980,13 @@ __device__ __forceinline__ double lean_entry(const char* tb, const DevFlat2* __r
     return u.fr * flipsign(part, sg);
 }
 template <bool REAL>
-__global__ void __launch_bounds__(512, 1) k_expect_pipe(Shards psi, TileGeom g, const DevFlat2* __restrict__ flats, int n_flats,
+__global__ void __launch_bounds__(512, 1) k_expect_pipe(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
+                                                        const DevFlat2* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
                                                         const DevAddPat* __restrict__ addpat, int n_addpat,
                                                         const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
                                                         int* __restrict__ err) {
-    extern __shared__ double2 smem_tiles[];
+    extern __shared__ __align__(128) double2 smem_tiles[];
     __shared__ double red[64];
     __shared__ __align__(8) uint64_t s_full[3];
     const uint32_t ts = 1u << g.tbits;
@@ -1928,7 +2001,7 @@ __global__ void __launch_bounds__(512, 1) k_expect_pipe(Shards psi, TileGeom g, 
     __syncthreads();
     if (warp == 0)
         for (uint64_t k = 0; k < 3 && k < n_my; ++k)
-            ring_issue_load(smem_tiles + (size_t)k * ts, psi, g, tile_base_warp(g, bl, blockIdx.x + k * gridDim.x), &s_full[k]);
+            ring_issue_load(smem_tiles + (size_t)k * ts, psi, g, tile_base_warp(g, bl, blockIdx.x + k * gridDim.x), &s_full[k], &tmap);
     double er = 0.0;
     for (uint64_t k = 0; k < n_my; ++k) {
         const uint32_t sl = (uint32_t)(k % 3);
@@ -1939,7 +2012,7 @@ __global__ void __launch_bounds__(512, 1) k_expect_pipe(Shards psi, TileGeom g, 
         __syncthreads();  // constants visible; every warp has left tile k-1 (its slot may be refilled below)
         if (warp == 0 && k >= 1 && k + 2 < n_my)
             ring_issue_load(smem_tiles + (size_t)((k + 2) % 3) * ts, psi, g, tile_base_warp(g, bl, blockIdx.x + (k + 2) * gridDim.x),
-                            &s_full[(k + 2) % 3]);
+                            &s_full[(k + 2) % 3], &tmap);
         if (!mbar_wait(&s_full[sl], (uint32_t)((k / 3) & 1u)) && err) *err = 2;
         for (int e = f0 + (int)warp; e < f1; e += (int)nw) er += lean_entry<REAL>(tb, flats, e, lane, sbase, fzout, addtab, beta);
     }
@@ -1952,20 +2025,22 @@ __global__ void __launch_bounds__(512, 1) k_expect_pipe(Shards psi, TileGeom g, 
 //     acc[l ^ x] += G(l) psi[l],   acc[l] += G(l) psi[l ^ x]        (even-ny strings: the same weight both ways)
 // with a barrier between two groups (inside a group every accumulator element is touched by one thread).
 template <bool REAL>
-__global__ void __launch_bounds__(512, REAL ? 2 : 1) k_apply_lean(Shards src, Shards dst, TileGeom g, const DevFlat2* __restrict__ flats,
+__global__ void __launch_bounds__(512, REAL ? 2 : 1) k_apply_lean(const __grid_constant__ CUtensorMap tmap, Shards src, Shards dst, TileGeom g,
+                                                                  const DevFlat2* __restrict__ flats,
                                                                   const uint32_t* __restrict__ goff, int n_groups,
                                                                   const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
                                                                   const DevAddPat* __restrict__ addpat, int n_addpat,
                                                                   const DevAddOut* __restrict__ addout, int accumulate,
                                                                   int* __restrict__ err) {
-    extern __shared__ double2 tile[];
+    extern __shared__ __align__(128) double2 tile[];
     __shared__ uint64_t s_boff[16];
     __shared__ __align__(8) uint64_t s_mbar;
     const uint32_t ts = 1u << g.tbits;
     double* accr = (double*)(tile + ts);              // REAL: ts doubles
     double2* accc = (double2*)(tile + ts);            // else: ts double2
     double* s_beta = REAL ? (accr + ts) : (double*)(accc + ts);
-    const bool bulk = g.bulk != 0;
+    const bool tma = g.tma != 0;
+    const bool bulk = g.bulk != 0 || tma;
     uint32_t mphase = 0;
     if (bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
     const TileAddr ta = tile_addr_init(g, s_boff);
@@ -1976,7 +2051,9 @@ __global__ void __launch_bounds__(512, REAL ? 2 : 1) k_apply_lean(Shards src, Sh
         const uint64_t base = tile_base_warp(g, bl, t);
         const uint64_t sbase = base | g.sign_base;
         __syncthreads();  // previous tile written out
-        if (bulk) tile_load_bulk(tile, src, g, base, &s_mbar);
+        if (tma) {
+            if (threadIdx.x == 0) tma_load_tile(tile, &tmap, g, base, &s_mbar);
+        } else if (bulk) tile_load_bulk(tile, src, g, base, &s_mbar);
         else tile_load_async_fast(tile, src, g, ta, s_boff, base);
         for (uint32_t k = threadIdx.x; k < ts; k += bd) {
             if (REAL) accr[k] = 0.0;
@@ -2632,6 +2709,172 @@ static int make_geom(const vqe_ctx* c, const TilePlan& tp, const uint64_t* d_sca
     if (!sh.p0 || !sh.p1)
         return fail(VQE_ERR_INVALID, "rank %d: buffer %d of rank %d is not attached (vqe_shard_attach_*)", c->rank, buf, partner);
     return VQE_OK;
+}
+
+// ---- tensor maps ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+struct TmaShape {
+    bool ok = false;
+    TmaGeom tg;
+    cuuint64_t gdim[5];
+    cuuint64_t gstride[4];
+    cuuint32_t box[5];
+};
+// Host-only: the tensor-map shape of a local tile plan (see TmaGeom).  ok = false: keep the per-segment bulk copies.
+static TmaShape plan_tma(const TilePlan& tp) {
+    TmaShape sh;
+    memset(&sh.tg, 0, sizeof sh.tg);
+    if (tp.vbit || tp.bits.empty() || tp.nl > 36) return sh;
+    // runs of adjacent tile bits; a run is cut where a box would exceed 256 elements (dimension 0 counts doubles)
+    struct Run { int start, len; };
+    std::vector<Run> runs;
+    for (int b : tp.bits) {
+        const bool adjacent = !runs.empty() && runs.back().start + runs.back().len == b;
+        const int cap = (runs.size() == 1 && runs[0].start == 0) ? 7 : 8;  // the run at bit 0 is dimension 0: 2^(len+1) doubles
+        if (adjacent && runs.back().len < cap) runs.back().len++;
+        else runs.push_back({b, 1});
+    }
+    // dimensions: breakpoints at 0 and at the start of the first (up to) five runs
+    std::vector<int> starts, blog;
+    size_t used_runs = 0;
+    if (runs[0].start != 0) { starts.push_back(0); blog.push_back(0); }
+    while (used_runs < runs.size() && starts.size() < 5) {
+        starts.push_back(runs[used_runs].start);
+        blog.push_back(runs[used_runs].len);
+        ++used_runs;
+    }
+    // tile bits of the remaining runs select the request
+    std::vector<int> extra;
+    for (size_t r = used_runs; r < runs.size(); ++r)
+        for (int k = 0; k < runs[r].len; ++k) extra.push_back(runs[r].start + k);
+    if (extra.size() > 4) return sh;
+    const int nd = (int)starts.size();
+    for (int i = 0; i < 5; ++i) {
+        if (i < nd) {
+            const int lo = starts[i], hi = (i + 1 < nd) ? starts[i + 1] : tp.nl;
+            const int span = hi - lo;
+            if (span > 31 || (i == 0 && span > 30)) {
+                return sh;  // (a dimension holds at most 2^32 elements; such plans keep the bulk-copy path)
+            }
+            sh.tg.shift[i] = (uint32_t)lo;
+            sh.tg.cmask[i] = (uint32_t)((1ull << span) - 1ull);
+            sh.gdim[i] = (i == 0) ? (2ull << span) : (1ull << span);
+            sh.box[i] = (i == 0) ? (2u << blog[i]) : (1u << blog[i]);
+            if (i > 0) sh.gstride[i - 1] = 16ull << lo;
+        } else {
+            sh.tg.shift[i] = 0;
+            sh.tg.cmask[i] = 0;  // coordinate 0
+            sh.gdim[i] = 1;
+            sh.box[i] = 1;
+            sh.gstride[i - 1] = 16ull << tp.nl;
+        }
+    }
+    sh.tg.n_req = 1u << extra.size();
+    sh.tg.req_amps = (1u << tp.tbits) >> extra.size();
+    for (uint32_t r = 0; r < sh.tg.n_req; ++r) {
+        uint64_t bits = 0;
+        for (size_t k = 0; k < extra.size(); ++k)
+            if ((r >> k) & 1u) bits |= 1ull << extra[k];
+        sh.tg.req_bits[r] = bits;
+    }
+    sh.ok = true;
+    return sh;
+}
+// Fill g.tma / g.tg and encode the tensor map of buffer `ptr` for this plan; leaves g.tma = 0 when the plan has no
+// tensor-map form, the driver entry point is missing, or VQE_TMA=0.
+static void make_tmap(const TilePlan& tp, double2* ptr, TileGeom& g, CUtensorMap* map) {
+    memset(map, 0, sizeof *map);
+    g.tma = 0;
+    memset(&g.tg, 0, sizeof g.tg);
+    if (!env_int("VQE_TMA", 1) || !ptr) return;
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return;
+    const TmaShape sh = plan_tma(tp);
+    if (!sh.ok) return;
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)ptr, sh.gdim, sh.gstride, sh.box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return;
+    g.tg = sh.tg;
+    g.tma = 1;
+}
+
+// Host-only check of the tensor-map form of a tile plan (no CUDA call; CPU tests): emulates the TMA box traversal
+// (dimension 0 fastest, element = one double) for every request of up to `max_tiles` tiles and compares the global
+// element index of every tile element with the gather address the per-segment path uses.  Returns the number of
+// mismatching elements, or -1 when the plan has no tensor-map form.  *n_req / *rank_used describe the shape.
+extern "C" int vqe_debug_tma_check(int n_local, uint64_t need_mask, int tile_bits, int low_bits, int max_tiles, int32_t* n_req,
+                                   int32_t* dims_used) {
+    if (n_local < 1 || n_local > 40) return fail(VQE_ERR_INVALID, "bad n_local");
+    if (tile_bits < 1 || tile_bits > 12) tile_bits = 12;
+    const TilePlan tp = make_plan(n_local, need_mask, tile_bits, std::max(0, std::min(low_bits, tile_bits)), 0);
+    const TmaShape sh = plan_tma(tp);
+    if (!sh.ok) return -1;
+    if (n_req) *n_req = (int32_t)sh.tg.n_req;
+    if (dims_used) {
+        int d = 0;
+        for (int i = 0; i < 5; ++i) d += sh.gdim[i] > 1 ? 1 : 0;
+        *dims_used = d;
+    }
+    // constraints of cuTensorMapEncodeTiled
+    for (int i = 0; i < 5; ++i) {
+        if (sh.box[i] == 0 || sh.box[i] > 256 || sh.gdim[i] == 0 || sh.gdim[i] > (1ull << 32)) return 1 << 30;
+        if (i > 0 && ((sh.gstride[i - 1] & 15ull) || sh.gstride[i - 1] >= (1ull << 40))) return 1 << 30;
+    }
+    if ((sh.box[0] * 8) % 16) return 1 << 30;
+    const uint32_t ts = 1u << tp.tbits, lmask = (1u << tp.lbits) - 1u;
+    int bad = 0;
+    const uint64_t n_tiles = std::min<uint64_t>(tp.n_tiles, (uint64_t)std::max(1, max_tiles));
+    for (uint64_t k = 0; k < n_tiles; ++k) {
+        const uint64_t t = (n_tiles == tp.n_tiles) ? k : (k * 2654435761ull) % tp.n_tiles;  // spread the sample
+        uint64_t base = 0, v = t, m = tp.comp_mask;
+        while (m) {
+            const uint64_t low = m & (0 - m);
+            if (v & 1) base |= low;
+            v >>= 1;
+            m ^= low;
+        }
+        uint32_t local = 0;  // tile-local element (in doubles: 2 per amplitude)
+        for (uint32_t r = 0; r < sh.tg.n_req; ++r) {
+            const uint64_t idx = base | sh.tg.req_bits[r];
+            int64_t c[5];
+            for (int i = 0; i < 5; ++i) c[i] = (int64_t)((uint32_t)(idx >> sh.tg.shift[i]) & sh.tg.cmask[i]);
+            c[0] <<= 1;
+            for (uint32_t e4 = 0; e4 < sh.box[4]; ++e4)
+                for (uint32_t e3 = 0; e3 < sh.box[3]; ++e3)
+                    for (uint32_t e2 = 0; e2 < sh.box[2]; ++e2)
+                        for (uint32_t e1 = 0; e1 < sh.box[1]; ++e1)
+                            for (uint32_t e0 = 0; e0 < sh.box[0]; ++e0, ++local) {
+                                const uint64_t byte = (uint64_t)(c[0] + e0) * 8ull + (uint64_t)(c[1] + e1) * sh.gstride[0] +
+                                                      (uint64_t)(c[2] + e2) * sh.gstride[1] + (uint64_t)(c[3] + e3) * sh.gstride[2] +
+                                                      (uint64_t)(c[4] + e4) * sh.gstride[3];
+                                if ((uint64_t)(c[0] + e0) >= sh.gdim[0] || (uint64_t)(c[1] + e1) >= sh.gdim[1] ||
+                                    (uint64_t)(c[2] + e2) >= sh.gdim[2] || (uint64_t)(c[3] + e3) >= sh.gdim[3] ||
+                                    (uint64_t)(c[4] + e4) >= sh.gdim[4]) { ++bad; continue; }
+                                const uint32_t kk = local >> 1;  // amplitude inside the tile
+                                const uint64_t want = (base | tp.scat[kk >> tp.lbits] | (uint64_t)(kk & lmask)) * 16ull + (local & 1u) * 8ull;
+                                if (byte != want) ++bad;
+                            }
+        }
+        if (local != 2 * ts) bad += 1000000;
+    }
+    return bad;
 }
 
 extern "C" int vqe_n_qubits(const vqe_ctx* c) { return c ? c->n : 0; }
@@ -3387,7 +3630,10 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
             const int grid = tile_grid(c, g.n_tiles, smem_c <= 74 * 1024 ? 3 : 2);
             const size_t smem_p = (size_t)NSLOT * tile_smem(ps.tp.tbits, 1, false) + (size_t)n_cols * (sizeof(DevCol) + 8) +
                                   (size_t)n_ents * sizeof(DevColEntry);
-            if (g.bulk && smem_p <= 226 * 1024 && env_int("VQE_PIPE", 1) != 0) {
+            TileGeom gt = g;
+            CUtensorMap tmap;
+            make_tmap(ps.tp, ps.tp.vbit ? nullptr : sh.p0, gt, &tmap);
+            if ((gt.bulk || gt.tma) && smem_p <= 226 * 1024 && env_int("VQE_PIPE", 0) != 0) {
                 // tile ring: one persistent CTA per SM, loads two tiles ahead, stores draining behind
                 uint32_t max_items = 0;
                 for (size_t q = ps.col_begin; q < ps.col_end; ++q)
@@ -3395,19 +3641,19 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                 const int thr_p = (int)std::min<uint64_t>(max_items <= 256 ? 256 : 512, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
                 const int grid_p = tile_grid(c, g.n_tiles, 1);
                 if (env_int("VQE_DEBUG_SKELETON", 0))  // measurement aid: loads and stores only, no arithmetic (results are wrong)
-                    k_col_pipe<true><<<grid_p, thr_p, smem_p, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, 0,
+                    k_col_pipe<true><<<grid_p, thr_p, smem_p, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, 0,
                                                                           (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, 0, c->d_err);
                 else if (real_pass[p])
-                    k_col_pipe<true><<<grid_p, thr_p, smem_p, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                    k_col_pipe<true><<<grid_p, thr_p, smem_p, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                           (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
                 else
-                    k_col_pipe<false><<<grid_p, thr_p, smem_p, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                    k_col_pipe<false><<<grid_p, thr_p, smem_p, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                            (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
             } else if (real_pass[p])
-                k_tile_col<true><<<grid, thr, smem_c, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                k_tile_col<true><<<grid, thr, smem_c, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                   (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
             else
-                k_tile_col<false><<<grid, thr, smem_c, c->stream>>>(sh, g, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                k_tile_col<false><<<grid, thr, smem_c, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                    (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
         } else if (ps.fast && real_pass[p])
             k_tile_rot<true><<<tile_grid(c, g.n_tiles, (smem <= 74 * 1024 && env_int("VQE_REAL_CTAS", 3) == 3) ? 3 : 0), threads, smem, c->stream>>>(
@@ -4813,7 +5059,7 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                 grids[k][p] = dim3(0, 0, 1);
                 continue;
             }
-            const bool pipe = pp.lean && geoms[k][p].bulk && env_int("VQE_PIPE", 1) != 0 &&
+            const bool pipe = pp.lean && geoms[k][p].bulk && env_int("VQE_PIPE", 0) != 0 &&
                               3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double) <= 226 * 1024;
             int gx = tile_grid(c, geoms[k][p].n_tiles, pipe ? 1 : (pp.lean ? 3 : 0));
             int want = std::max(1, (c->sm_count * (pipe ? 1 : (pp.lean ? 3 : c->ctas_per_sm))) / gx);
@@ -4841,32 +5087,35 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             size_t smem = tile_smem(pp.tp.tbits, 1, true);
             int threads = (int)std::min<uint64_t>(c->threads, std::max<uint64_t>(32, (1ull << pp.tp.tbits) / 2));
             ProfScope prof(c, vbit ? 5 : 1);
-            const bool pipe = pp.lean && geoms[k][p].bulk && env_int("VQE_PIPE", 1) != 0 &&
+            CUtensorMap tmap;
+            memset(&tmap, 0, sizeof tmap);
+            if (pp.lean) make_tmap(pp.tp, vbit ? nullptr : shards[k][p].p0, geoms[k][p], &tmap);
+            const bool pipe = pp.lean && (geoms[k][p].bulk || geoms[k][p].tma) && env_int("VQE_PIPE", 0) != 0 &&
                               3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double) <= 226 * 1024;
             if (pipe) {
                 const size_t smem_p = 3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double);
                 int thr_p = env_int("VQE_EXP_THREADS", 512);
                 if (thr_p < 32 || thr_p > 512 || (thr_p & 31)) thr_p = 512;
                 if (env_int("VQE_DEBUG_SKELETON", 0))  // measurement aid: loads only (results are wrong)
-                    k_expect_pipe<true><<<grids[k][p], thr_p, smem_p, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, 0,
+                    k_expect_pipe<true><<<grids[k][p], thr_p, smem_p, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2, 0,
                                                                                   pp.d_fzout, pp.d_addtab, pp.d_addpat, 0,
                                                                                   pp.d_addout, c->d_partial + off[k], c->d_err);
                 else if (real_state)
-                    k_expect_pipe<true><<<grids[k][p], thr_p, smem_p, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
+                    k_expect_pipe<true><<<grids[k][p], thr_p, smem_p, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
                                                                                   pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
                                                                                   pp.d_addout, c->d_partial + off[k], c->d_err);
                 else
-                    k_expect_pipe<false><<<grids[k][p], thr_p, smem_p, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
+                    k_expect_pipe<false><<<grids[k][p], thr_p, smem_p, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
                                                                                    pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
                                                                                    pp.d_addout, c->d_partial + off[k], c->d_err);
             } else if (pp.lean) {
                 const size_t smem_l = tile_smem(pp.tp.tbits, 1, false) + pp.addpat.size() * sizeof(double);
                 if (real_state)
-                    k_expect_lean<true><<<grids[k][p], 256, smem_l, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
+                    k_expect_lean<true><<<grids[k][p], 256, smem_l, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
                                                                                 pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
                                                                                 pp.d_addout, c->d_partial + off[k], c->d_err);
                 else
-                    k_expect_lean<false><<<grids[k][p], 256, smem_l, c->stream>>>(shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
+                    k_expect_lean<false><<<grids[k][p], 256, smem_l, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
                                                                                  pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
                                                                                  pp.d_addout, c->d_partial + off[k], c->d_err);
             } else if (pp.cplx)
@@ -4985,17 +5234,19 @@ static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* 
             int threads = (int)std::min<uint64_t>(1024, std::max<uint64_t>(32, ts / 2));
             ProfScope prof(c, 2);
             if (pp.lean) {
+                CUtensorMap tmap;
+                make_tmap(pp.tp, vbit ? nullptr : ssrc.p0, g, &tmap);
                 const int n_lg = (int)pp.goff.size() - 1;
                 const int thr = (int)std::min<uint64_t>(512, std::max<uint64_t>(32, ts / 2));
                 if (real_src) {
                     const size_t smem_l = (16ull << pp.tp.tbits) + (8ull << pp.tp.tbits) + pp.addpat.size() * sizeof(double);
                     k_apply_lean<true><<<tile_grid(c, g.n_tiles, 2), thr, smem_l, c->stream>>>(
-                        ssrc, sdst, g, pp.d_flats2, pp.d_goff, n_lg, pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
+                        tmap, ssrc, sdst, g, pp.d_flats2, pp.d_goff, n_lg, pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
                         pp.d_addout, p == 0 ? 0 : 1, c->d_err);
                 } else {
                     const size_t smem_l = 2 * (16ull << pp.tp.tbits) + pp.addpat.size() * sizeof(double);
                     k_apply_lean<false><<<tile_grid(c, g.n_tiles, 1), thr, smem_l, c->stream>>>(
-                        ssrc, sdst, g, pp.d_flats2, pp.d_goff, n_lg, pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
+                        tmap, ssrc, sdst, g, pp.d_flats2, pp.d_goff, n_lg, pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
                         pp.d_addout, p == 0 ? 0 : 1, c->d_err);
                 }
                 c->launches++;

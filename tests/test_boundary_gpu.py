@@ -271,7 +271,7 @@ def test_helpers_accept_the_reference_matrix_arguments(gpu_required, h2):
     sig = H.dot(v)
     g_ref = [2 * (sig.transpose().conj().dot(m.dot(v)))[0, 0].real for m in mats]
     # the same calls on the engine
-    st = fa.prepare_adapt_state(psi.reshape(-1, 1), mats, [0.13, -0.07])
+    st = fa.prepare_adapt_state(psi.reshape(-1, 1), [mats[38], mats[32]], [0.13, -0.07])
     assert np.max(np.abs(st - v)) < 1e-12
     lg, nrm, nd, ni = fa.return_gradient_list(mats, H, st)
     assert np.max(np.abs(np.array(lg) - np.abs(g_ref))) < TOL
