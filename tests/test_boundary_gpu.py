@@ -293,3 +293,70 @@ def test_helpers_accept_the_reference_matrix_arguments(gpu_required, h2):
 def _hotpath_snap(values):
     from openvqe_b200._hotpath import snap_ties
     return snap_ties(list(values))
+
+
+def test_h6_full_pools_match_the_reference_sweep(gpu_required):
+    """Configs C2 / C3 with the FULL 12-qubit pools (round 1 used every 9th / 3rd operator): uccgsd 3 159 operators,
+    spin_complement_gsd 714, sUPCCGSD (k = 2) 60 and the 285-operator YXXX pool, generated by openvqe_b200.common_files.pools
+    and swept on the GPU, against the unmodified reference return_gradient_list / calculate_gradient run on the reference's own
+    pools (tests/golden/h6_full_pools.npz, oracle/make_golden_r2.py).  Gradients to 1e-10, zero pattern, arg-max, ties."""
+    import os
+    from openvqe_b200 import _hotpath
+    from openvqe_b200.adapt import fermionic_adapt_vqe as fa
+    from openvqe_b200.common_files import pools
+    from openvqe_b200.engine import get_engine
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h6_full_pools.npz"))
+    fx = load_golden("h6_sto3g.json.gz")
+    ham = ham_from_json(fx["hamiltonian"])
+    st = np.array(fx["state"]["state_re"]) + 1j * np.array(fx["state"]["state_im"])
+    for name, make in (("uccgsd", lambda: pools.uccgsd(6, 6, "JW")), ("spin_complement_gsd", lambda: pools.spin_complement_gsd(6, 6, "JW")),
+                       ("singlet_upccgsd_k2", lambda: pools.singlet_upccgsd(6, "JW", 1))):
+        size, _, ops = make()
+        lg, nrm, nd, ni = fa.return_gradient_list(ops, ham, st)
+        ref = gold[name + "_list_grad"]
+        ref_nrm, ref_nd, ref_ni = gold[name + "_summary"]
+        assert len(lg) == size == len(ref)
+        assert np.abs(np.array(lg) - ref).max() < TOL, name
+        assert abs(nrm - ref_nrm) < 1e-9 and abs(nd - ref_nd) < TOL and ni == int(ref_ni), name
+        # exact zeros of the reference's serial scipy sums are zeros here (|g| <= 1e-14 is snapped, DESIGN.md section 4)
+        assert [k for k, v in enumerate(lg) if v == 0] == [k for k, v in enumerate(ref) if abs(v) <= 1e-14], name
+        # the selection helpers see the same ordering: sorted non-zero values and their pool indices
+        vals, idx = fa.print_gradient_lists_and_indices(lg)
+        vals_ref, idx_ref = fa.print_gradient_lists_and_indices(_hotpath.snap_ties(list(ref)))
+        assert idx == idx_ref and np.abs(np.array(vals) - np.array(vals_ref)).max() < TOL, name
+    eng = get_engine(12)
+    _, yxxx = pools.generate_yxxx_pool(12)
+    eng.set_state(st)
+    gq = 2.0 * np.abs(_hotpath.pool_overlaps(eng, ham, yxxx))
+    assert np.abs(gq - gold["yxxx_gradients"]).max() < TOL
+
+
+def test_quccsd_get_energies_matches_the_reference_driver(gpu_required):
+    """SURVEY row a3 for the QUCCSD driver (reference get_energy_qucc.py:136-244): both BFGS runs on H4/STO-3G against the
+    outputs of the unmodified reference driver run through the qat stand-in (tests/golden/h4_get_energies.json): result keys,
+    CNOT counts, operator counts, optimal energies (1e-8: two independent BFGS trajectories with finite-difference
+    gradients) and the first objective values (1e-10: same theta, same circuit)."""
+    import json
+    import os
+    from openvqe_b200.ucc_family.get_energy_qucc import EnergyUCC
+    fx = load_golden("h4_sto3g.json.gz")
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h4_get_energies.json")) as f:
+        ref = json.load(f)
+    ham = ham_from_json(fx["hamiltonian"])
+    ops = [FermiOp(8, ex) for ex in fx["excitations"]]
+    it, res = quiet(EnergyUCC().get_energies, ham, ops, fx["hf_init_sp"], ref["theta_current1"], ref["theta_current2"], fx["fci"])
+    assert set(it) == set(ref["iterations"]) and set(res) == set(ref["result"])
+    assert res["CNOT1"] == ref["result"]["CNOT1"] == 292 and res["CNOT2"] == ref["result"]["CNOT2"] == 292
+    assert res["len_op1"] == ref["result"]["len_op1"] == 26 and res["len_op2"] == ref["result"]["len_op2"] == 26
+    for k in ("1", "2"):
+        e_ref = ref["iterations"]["minimum_energy_result%s_guess" % k][0]
+        assert abs(it["minimum_energy_result%s_guess" % k][0] - e_ref) < 1e-8
+        assert abs(res["energies%s_substracted_from_FCI" % k] - ref["result"]["energies%s_substracted_from_FCI" % k]) < 1e-8
+        mine, theirs = res["energies_" + k], ref["result"]["energies_" + k]
+        # the first gradient (27 evaluations: f(x), then one displaced point per parameter) is evaluated at identical points
+        assert np.abs(np.array(mine[:27]) - np.array(theirs[:27])).max() < TOL
+        assert abs(len(mine) - len(theirs)) <= 0.25 * len(theirs)
+        th, th_ref = it["theta_optimized_result" + k][0], ref["iterations"]["theta_optimized_result" + k][0]
+        assert len(th) == len(th_ref) == 26 and np.abs(np.array(th) - np.array(th_ref)).max() < 5e-3
+    # the optimum found from the MP2 guess is the G4-class energy of the notebook (10^-3: different operator order, SURVEY V9)
+    assert abs(it["minimum_energy_result1_guess"][0] - (-2.1770061634841933)) < 1e-3
