@@ -1,2 +1,2 @@
-"""TEST INFRASTRUCTURE ONLY -- empty stand-in so that the reference's
-``import matplotlib`` (plot helpers, never on the hot path) succeeds."""
+"""TEST INFRASTRUCTURE ONLY -- import stand-in for matplotlib (absent in the build image): the reference's facade
+(openvqe/algorithms/algorithm.py:1) imports pyplot at module level; nothing here draws anything."""

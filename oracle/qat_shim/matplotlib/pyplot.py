@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- plotting is out of scope."""
+"""TEST INFRASTRUCTURE ONLY -- no-op stand-in for matplotlib.pyplot (see matplotlib/__init__.py)."""
 
 
 def __getattr__(name):

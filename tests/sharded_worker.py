@@ -41,10 +41,11 @@ def main():
         ref = orc.pauli_rotation(ref, x, z, ny, a)
     eng.apply_rotations(xs, zs, nys, angs)
     eng.barrier()
-    mine = eng.get_state()
+    mine = eng.get_local_state()
     nl = n - 1
     err = np.max(np.abs(mine - ref[rank << nl:(rank + 1) << nl]))
     assert err < 1e-12, err
+    assert np.max(np.abs(eng.get_state() - ref)) < 1e-12   # get_state all-gathers the full vector (reference-shaped helpers)
     assert abs(eng.norm2() - 1.0) < 1e-12
     ham = random_hermitian(rng, n, 200, max_weight=6, const=0.5)
     e = eng.expectation(eng.paulisum(ham))
