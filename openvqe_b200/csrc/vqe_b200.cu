@@ -113,8 +113,16 @@ struct TileGeom {
     uint32_t vbit;         // 1: the top tile bit is VIRTUAL -- it selects the shard (0: p0 = lower rank, 1: p1 = r ^ m)
     uint32_t bulk;         // 1: stage the tile with bulk asynchronous copies (cp.async.bulk, one per contiguous segment)
     uint32_t tma;          // 1: stage the tile with tensor-map requests (tg + the CUtensorMap kernel parameter)
+    uint32_t swz;          // 0x70 when the tile sits in shared memory in the TMA 128-byte swizzle (the 16-byte chunk index of
+                           // an element, byte-offset bits 4-6, is XORed with bits 7-9): whatever tile bits an operation
+                           // fixes, a warp's 32 elements then spread over all eight chunk positions (no bank conflicts
+                           // beyond the 16-byte stride itself).  0: natural layout.
     TmaGeom tg;
 };
+// byte offset of a tile element in the (possibly swizzled) shared-memory tile; linear over XOR
+__host__ __device__ __forceinline__ uint32_t swz_off(uint32_t off, uint32_t swz) { return off ^ ((off >> 3) & swz); }
+// the same on element indices
+__host__ __device__ __forceinline__ uint32_t swz_idx(uint32_t l, uint32_t swz) { return l ^ ((l >> 3) & (swz >> 4)); }
 
 // Peer pass, "gather" form.  When the operations of a peer pass couple only a fraction of the partner's amplitudes
 // (collapsed runs: 1/8 of them for a JW double excitation), moving whole half-tiles over NVLink is wasteful.
@@ -837,7 +845,7 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
                                                      const DevCol* __restrict__ cols, int n_cols,
                                                      const DevColEntry* __restrict__ ents, int n_ents, double pass_scale,
                                                      int* __restrict__ err) {
-    extern __shared__ __align__(128) double2 tile[];
+    extern __shared__ __align__(1024) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     const bool four = (ts >> 1) == 4u * blockDim.x;  // host guarantees: 4 pairs (one orbit) per thread, or at most 1 pair
     RotOp* optab = (RotOp*)(tile + ts);
@@ -1018,54 +1026,99 @@ __device__ __forceinline__ uint64_t tile_base_warp(const TileGeom& g, const Base
 // descriptor read and the index deposit of run q+1 are issued BEFORE the barrier that ends run q, so the chain
 // between two barriers is  LDS pair -> 3 FP64 ops -> STS pair.
 // ------------------------------------------------------------------------------------------
+// Per-run descriptor in shared memory (64 bytes, built once per CTA from DevCol + the run's first table entry).  Runs with
+// a single active pattern -- every JW single / double excitation -- never touch the entry table again.
+struct ColLite {
+    double c, s;             // cos, sin of entry 0
+    uint32_t lxs, lz;        // X-mask as an element index in the tile's shared-memory layout (swizzled when the tile is) | Z letters
+    uint32_t pat, items;     // pattern of entry 0 | n_active << free_log
+    uint32_t dm[6];          // deposit masks of the fixed positions, ascending, 0 when unused
+    uint32_t free_log;
+    uint32_t meta;           // bit 0: unit phase +-i | bit 1: single active pattern | bits 16..: first entry of the run
+};
+static_assert(sizeof(ColLite) == 64, "ColLite layout");
 struct ColItem {
-    uint32_t l, lx;      // a-side tile index, X-mask
+    uint32_t ls, lxs;    // a-side element (shared-memory layout) | X-mask (shared-memory layout)
     double c, sn;        // cos, signed sin
     uint32_t imag, valid;
     uint32_t items;      // items of the run (for the threads that own more than one)
 };
-__device__ __forceinline__ uint32_t col_deposit(const DevCol& co, uint32_t f) {
-    uint32_t l = f;
-    l += l & co.dpos[0];
-    l += l & co.dpos[1];
-    l += l & co.dpos[2];
-    l += l & co.dpos[3];
-    if (co.nd > 4) {
-        l += l & co.dpos[4];
-        l += l & co.dpos[5];
+__device__ __forceinline__ void col_lite_build(ColLite* lite, const DevCol* __restrict__ cols, const DevColEntry* __restrict__ ents,
+                                               int n_cols, uint32_t swz) {
+    for (int q = threadIdx.x; q < n_cols; q += blockDim.x) {
+        const DevCol co = cols[q];
+        const DevColEntry e0 = ents[co.ent_begin];
+        ColLite L;
+        L.c = e0.c;
+        L.s = e0.s;
+        L.lxs = swz_idx(co.lx, swz);
+        L.lz = co.lz;
+        L.pat = e0.pat;
+        L.items = co.n_active << co.free_log;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) L.dm[d] = co.dpos[d];
+        L.free_log = co.free_log;
+        L.meta = (co.imag & 1u) | (co.n_active == 1u ? 2u : 0u) | (co.ent_begin << 16);
+        lite[q] = L;
     }
-    return l;
 }
-__device__ __forceinline__ ColItem col_prep(const DevCol* scol, const DevColEntry* sent, const uint32_t* scsign, int q, int n_cols,
-                                            uint32_t it) {
+__device__ __forceinline__ ColItem col_prep(const ColLite* lite, const DevColEntry* sent, const uint32_t* csign, int q, int n_cols,
+                                            uint32_t it, uint32_t swz) {
     ColItem ci;
     ci.valid = 0;
-    ci.l = ci.lx = ci.imag = ci.items = 0;
+    ci.ls = ci.lxs = ci.imag = ci.items = 0;
     ci.c = 1.0;
     ci.sn = 0.0;
     if (q >= n_cols) return ci;
-    const DevCol& co = scol[q];
-    const uint32_t items = co.n_active << co.free_log;
-    ci.items = items;
-    if (it >= items) return ci;
-    const DevColEntry& en = sent[co.ent_begin + (it >> co.free_log)];
-    const uint32_t l = col_deposit(co, it & ((1u << co.free_log) - 1u)) | en.pat;
-    ci.l = l;
-    ci.lx = co.lx;
-    ci.c = en.c;
-    ci.sn = flipsign(en.s, scsign[q] + (uint32_t)__popc(l & co.lz));
-    ci.imag = co.imag;
-    ci.valid = 1;
+    const ColLite& L = lite[q];
+    ci.items = L.items;
+    ci.valid = it < L.items ? 1u : 0u;
+    uint32_t l = it & ((1u << L.free_log) - 1u);
+    l += l & L.dm[0];
+    l += l & L.dm[1];
+    l += l & L.dm[2];
+    l += l & L.dm[3];
+    l += l & L.dm[4];
+    l += l & L.dm[5];
+    double c = L.c, sv = L.s;
+    uint32_t pat = L.pat;
+    if (!(L.meta & 2u) && ci.valid) {  // several active patterns (tabulated plane rotations): this item's entry
+        const DevColEntry& en = sent[(L.meta >> 16) + (it >> L.free_log)];
+        c = en.c;
+        sv = en.s;
+        pat = en.pat;
+    }
+    l |= pat;
+    ci.ls = swz_idx(l, swz);
+    ci.lxs = L.lxs;
+    ci.c = c;
+    ci.sn = flipsign(sv, csign[q] + (uint32_t)__popc(l & L.lz));
+    ci.imag = L.meta & 1u;
     return ci;
 }
+// one plane rotation; LOADS first, so that the caller's index work for the next run overlaps their latency
 template <bool REAL>
-__device__ __forceinline__ void col_apply(double2* tile, const ColItem& ci) {
+struct ColPair {
+    double2 a, b;
+};
+template <bool REAL>
+__device__ __forceinline__ void col_load(const double2* tile, const ColItem& ci, ColPair<REAL>& pr) {
     if (REAL) {
-        const double a = tile[ci.l].x, b = tile[ci.l ^ ci.lx].x;
-        tile[ci.l].x = fma(ci.c, a, -ci.sn * b);
-        tile[ci.l ^ ci.lx].x = fma(ci.c, b, ci.sn * a);
+        pr.a.x = tile[ci.ls].x;
+        pr.b.x = tile[ci.ls ^ ci.lxs].x;
+        pr.a.y = pr.b.y = 0.0;
     } else {
-        const double2 a = tile[ci.l], b = tile[ci.l ^ ci.lx];
+        pr.a = tile[ci.ls];
+        pr.b = tile[ci.ls ^ ci.lxs];
+    }
+}
+template <bool REAL>
+__device__ __forceinline__ void col_store(double2* tile, const ColItem& ci, const ColPair<REAL>& pr) {
+    const double2 a = pr.a, b = pr.b;
+    if (REAL) {
+        tile[ci.ls].x = fma(ci.c, a.x, -ci.sn * b.x);
+        tile[ci.ls ^ ci.lxs].x = fma(ci.c, b.x, ci.sn * a.x);
+    } else {
         double2 na, nb;
         if (ci.imag) {  // a' = c a + i s b, b' = c b + i s a
             na.x = fma(ci.c, a.x, -ci.sn * b.y); na.y = fma(ci.c, a.y, ci.sn * b.x);
@@ -1074,19 +1127,42 @@ __device__ __forceinline__ void col_apply(double2* tile, const ColItem& ci) {
             na.x = fma(ci.c, a.x, -ci.sn * b.x); na.y = fma(ci.c, a.y, -ci.sn * b.y);
             nb.x = fma(ci.c, b.x, ci.sn * a.x); nb.y = fma(ci.c, b.y, ci.sn * a.y);
         }
-        tile[ci.l] = na;
-        tile[ci.l ^ ci.lx] = nb;
+        tile[ci.ls] = na;
+        tile[ci.ls ^ ci.lxs] = nb;
+    }
+}
+// all runs of a pass on the tile in shared memory; ends with a CTA barrier (every thread has passed `fence` before it)
+template <bool REAL>
+__device__ __forceinline__ void col_runs(double2* tile, const ColLite* lite, const DevColEntry* sent, const uint32_t* csign, int n_cols,
+                                         uint32_t swz, bool fence, ColItem cur) {
+    const uint32_t bd = blockDim.x;
+    for (int q = 0; q < n_cols; ++q) {
+        const uint32_t items = cur.items;
+        ColPair<REAL> pr;
+        if (cur.valid) col_load<REAL>(tile, cur, pr);
+        const ColItem nxt = col_prep(lite, sent, csign, q + 1, n_cols, threadIdx.x, swz);  // overlaps the loads above
+        if (cur.valid) col_store<REAL>(tile, cur, pr);
+        for (uint32_t it = threadIdx.x + bd; it < items; it += bd) {
+            const ColItem ci = col_prep(lite, sent, csign, q, n_cols, it, swz);
+            ColPair<REAL> p2;
+            col_load<REAL>(tile, ci, p2);
+            col_store<REAL>(tile, ci, p2);
+        }
+        cur = nxt;
+        if (fence && q + 1 == n_cols) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes -> the async-proxy store
+        __syncthreads();
     }
 }
 template <bool REAL>
 __global__ void __launch_bounds__(256, 3) k_tile_col(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
                                                      const DevCol* __restrict__ cols, int n_cols,
                                                      const DevColEntry* __restrict__ ents, int n_ents, int* __restrict__ err) {
-    extern __shared__ __align__(128) double2 tile[];
+    extern __shared__ __align__(1024) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
-    DevCol* scol = (DevCol*)(tile + ts);
-    DevColEntry* sent = (DevColEntry*)(scol + n_cols);
-    uint32_t* scsign = (uint32_t*)(sent + n_ents);  // per tile: outside-tile Z parity of every run
+    ColLite* lite = (ColLite*)(tile + ts);
+    DevColEntry* sent = (DevColEntry*)(lite + n_cols);
+    uint64_t* szout = (uint64_t*)(sent + n_ents);
+    uint32_t* scsign = (uint32_t*)(szout + n_cols);  // per tile: outside-tile Z parity of every run
     __shared__ uint64_t s_boff[16];
     __shared__ __align__(8) uint64_t s_mbar;
     const bool tma = g.tma != 0;
@@ -1094,7 +1170,8 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(const __grid_constant__ CUt
     uint32_t mphase = 0;
     if (bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
     const TileAddr ta = tile_addr_init(g, s_boff);
-    for (int q = threadIdx.x; q < n_cols; q += blockDim.x) scol[q] = cols[q];
+    col_lite_build(lite, cols, ents, n_cols, g.swz);
+    for (int q = threadIdx.x; q < n_cols; q += blockDim.x) szout[q] = cols[q].zout;
     for (int q = threadIdx.x; q < n_ents; q += blockDim.x) sent[q] = ents[q];
     const BaseLane bl = base_lane_init(g);
     const uint32_t bd = blockDim.x;
@@ -1106,9 +1183,9 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(const __grid_constant__ CUt
             if (threadIdx.x == 0) tma_load_tile(tile, &tmap, g, base, &s_mbar);
         } else if (bulk) tile_load_bulk(tile, psi, g, base, &s_mbar);
         else tile_load_async_fast(tile, psi, g, ta, s_boff, base);
-        for (int r = threadIdx.x; r < n_cols; r += bd) scsign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
+        for (int r = threadIdx.x; r < n_cols; r += bd) scsign[r] = (uint32_t)__popcll(sbase & szout[r]) & 1u;
         __syncthreads();  // scsign visible
-        ColItem cur = col_prep(scol, sent, scsign, 0, n_cols, threadIdx.x);
+        const ColItem first = col_prep(lite, sent, scsign, 0, n_cols, threadIdx.x, g.swz);
         if (bulk) {
             if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
             mphase ^= 1u;
@@ -1116,20 +1193,7 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(const __grid_constant__ CUt
             cp_async_wait_all();
             __syncthreads();
         }
-        for (int q = 0; q < n_cols; ++q) {
-            const uint32_t items = cur.items;
-            // first item of this thread: prepared before the barrier; the next run's first item is prepared while
-            // this run's shared-memory loads are in flight
-            ColItem nxt = col_prep(scol, sent, scsign, q + 1, n_cols, threadIdx.x);
-            if (cur.valid) col_apply<REAL>(tile, cur);
-            for (uint32_t it = threadIdx.x + bd; it < items; it += bd) {
-                const ColItem ci = col_prep(scol, sent, scsign, q, n_cols, it);
-                col_apply<REAL>(tile, ci);
-            }
-            cur = nxt;
-            if (tma && q + 1 == n_cols) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes -> the TMA store
-            __syncthreads();
-        }
+        col_runs<REAL>(tile, lite, sent, scsign, n_cols, g.swz, tma, first);
         if (tma) {
             if (threadIdx.x == 0) {
                 tma_store_tile(tile, &tmap, g, base);
@@ -1197,16 +1261,18 @@ template <bool REAL>
 __global__ void __launch_bounds__(512, 1) k_col_pipe(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
                                                      const DevCol* __restrict__ cols, int n_cols,
                                                      const DevColEntry* __restrict__ ents, int n_ents, int* __restrict__ err) {
-    extern __shared__ __align__(128) double2 smem_tiles[];
+    extern __shared__ __align__(1024) double2 smem_tiles[];
     const uint32_t ts = 1u << g.tbits;
-    DevCol* scol = (DevCol*)(smem_tiles + (size_t)NSLOT * ts);
-    DevColEntry* sent = (DevColEntry*)(scol + n_cols);
-    uint32_t* scsign = (uint32_t*)(sent + n_ents);  // [2][n_cols]: outside-tile Z parity of every run, double-buffered per tile
+    ColLite* lite = (ColLite*)(smem_tiles + (size_t)NSLOT * ts);
+    DevColEntry* sent = (DevColEntry*)(lite + n_cols);
+    uint64_t* szout = (uint64_t*)(sent + n_ents);
+    uint32_t* scsign = (uint32_t*)(szout + n_cols);  // [2][n_cols]: outside-tile Z parity of every run, double-buffered per tile
     __shared__ __align__(8) uint64_t s_full[NSLOT];
     const uint32_t warp = threadIdx.x >> 5, bd = blockDim.x;
     if (threadIdx.x == 0)
         for (int i = 0; i < NSLOT; ++i) mbar_init(&s_full[i], 1);
-    for (int q = threadIdx.x; q < n_cols; q += bd) scol[q] = cols[q];
+    col_lite_build(lite, cols, ents, n_cols, g.swz);
+    for (int q = threadIdx.x; q < n_cols; q += bd) szout[q] = cols[q].zout;
     for (int q = threadIdx.x; q < n_ents; q += bd) sent[q] = ents[q];
     const BaseLane bl = base_lane_init(g);
     const uint64_t n_my = g.n_tiles > blockIdx.x ? (g.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -1220,22 +1286,11 @@ __global__ void __launch_bounds__(512, 1) k_col_pipe(const __grid_constant__ CUt
         const uint64_t base = tile_base_warp(g, bl, blockIdx.x + k * gridDim.x);
         const uint64_t sbase = base | g.sign_base;
         uint32_t* csign = scsign + (k & 1u) * n_cols;
-        for (int r = threadIdx.x; r < n_cols; r += bd) csign[r] = (uint32_t)__popcll(sbase & scol[r].zout) & 1u;
+        for (int r = threadIdx.x; r < n_cols; r += bd) csign[r] = (uint32_t)__popcll(sbase & szout[r]) & 1u;
         __syncthreads();  // signs of this tile visible (the other half of the double buffer may still be read by stragglers)
-        ColItem cur = col_prep(scol, sent, csign, 0, n_cols, threadIdx.x);
+        const ColItem first = col_prep(lite, sent, csign, 0, n_cols, threadIdx.x, g.swz);
         if (!mbar_wait(&s_full[sl], (uint32_t)((k / NSLOT) & 1u)) && err) *err = 2;
-        for (int q = 0; q < n_cols; ++q) {
-            const uint32_t items = cur.items;
-            ColItem nxt = col_prep(scol, sent, csign, q + 1, n_cols, threadIdx.x);
-            if (cur.valid) col_apply<REAL>(tile, cur);
-            for (uint32_t it = threadIdx.x + bd; it < items; it += bd) {
-                const ColItem ci = col_prep(scol, sent, csign, q, n_cols, it);
-                col_apply<REAL>(tile, ci);
-            }
-            cur = nxt;
-            if (q + 1 == n_cols) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes -> the bulk store
-            __syncthreads();
-        }
+        col_runs<REAL>(tile, lite, sent, csign, n_cols, g.swz, true, first);
         if (n_cols == 0) __syncthreads();  // (VQE_DEBUG_SKELETON: copy skeleton only)
         if (warp == 0) {
             ring_issue_store(tile, psi, g, base, &tmap);
@@ -1253,7 +1308,7 @@ __global__ void __launch_bounds__(512, 1) k_col_pipe(const __grid_constant__ CUt
 __global__ void __launch_bounds__(512, 2) k_tile_ops(Shards psi, TileGeom g,
                                                   const DevOp* __restrict__ ops, int n_ops,
                                                   const double* __restrict__ mats) {
-    extern __shared__ __align__(128) double2 tile[];
+    extern __shared__ __align__(1024) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     const uint32_t half = ts >> 1;
     FastOp* optab = (FastOp*)(tile + ts);  // n_ops entries (host caps n_ops per pass at OPTAB_CAP)
@@ -1353,7 +1408,7 @@ __global__ void __launch_bounds__(512, 2) k_tile_expect(Shards psi, TileGeom g,
                                                         const DevFlat* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout,
                                                         double2* __restrict__ partial, int* __restrict__ err) {
-    extern __shared__ __align__(128) double2 tile[];
+    extern __shared__ __align__(1024) double2 tile[];
     __shared__ double red[64];
     const uint32_t ts = 1u << g.tbits;
     const uint32_t half = ts >> 1;
@@ -1577,7 +1632,7 @@ __global__ void __launch_bounds__(1024, 1) k_tile_apply(Shards src, Shards dst, 
                                                         int n_groups, const DevTerm* __restrict__ terms,
                                                         const DevAFlat* __restrict__ aflat, const uint32_t* __restrict__ aoff,
                                                         const uint64_t* __restrict__ azout, int accumulate) {
-    extern __shared__ __align__(128) double2 tile[];
+    extern __shared__ __align__(1024) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     double2* acc = tile + ts;
     double2* s_coef = acc + ts;                                  // TERM_CAP
@@ -1691,7 +1746,7 @@ __global__ void __launch_bounds__(512) k_tile_pool(Shards bra, Shards ket, TileG
                                                    const DevPoolTerm* __restrict__ terms,
                                                    const DevGCol* __restrict__ pcols, const DevGColEntry* __restrict__ pents,
                                                    double2* __restrict__ partial /* [gridDim.x][n_pops] */) {
-    extern __shared__ __align__(128) double2 tile[];
+    extern __shared__ __align__(1024) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
     double2* tbra = tile;
     double2* tket = tile + ts;
@@ -1801,7 +1856,7 @@ struct DevAddOut {          // 16 bytes
     uint64_t zrel;          // outside-tile Z mask relative to the group's first string
 };
 struct LeanUnit {           // decoded entry, per lane
-    uint32_t v;             // byte offset of the lane's a-side element for j = 0 (pattern included)
+    uint32_t v;             // byte offset of the lane's a-side element for j = 0 (pattern included), NATURAL layout
     uint32_t lx16, s0, jsign, tab, hi0, bidx;
     uint32_t o[8];
     double fr;
@@ -1851,6 +1906,70 @@ __device__ __forceinline__ void lean_betas(double* s_beta, const DevAddPat* __re
     }
 }
 
+// Entries e0, e0 + stride, ... < e1 of one warp on one tile.  The descriptor (3 x 16 bytes through L1) and the
+// outside-tile Z mask of entry k+1 are fetched while entry k is evaluated.  Offsets are used in the tile's shared-memory
+// layout: with the 128-byte swizzle (swz = 0x70) the lane part is swizzled here, once per entry; the per-j offsets and the
+// X-mask were swizzled by the host (the map is linear over XOR).
+template <bool REAL>
+__device__ __forceinline__ double lean_entries(const char* tb, const DevFlat2* __restrict__ flats, int e0, int e1, int stride,
+                                               uint32_t lane, uint64_t sbase, const uint64_t* __restrict__ fzout,
+                                               const double* __restrict__ addtab, const double* s_beta, uint32_t swz) {
+    double er = 0.0;
+    if (e0 >= e1) return er;
+    const uint4* ep = reinterpret_cast<const uint4*>(flats + e0);
+    uint4 q0 = __ldg(ep), q1 = __ldg(ep + 1), q2 = __ldg(ep + 2);
+    uint64_t zo = __ldg(fzout + (q0.w >> 16));
+    for (int e = e0; e < e1; e += stride) {
+        uint4 n0 = q0, n1 = q1, n2 = q2;
+        uint64_t nzo = zo;
+        if (e + stride < e1) {
+            const uint4* np = reinterpret_cast<const uint4*>(flats + e + stride);
+            n0 = __ldg(np);
+            n1 = __ldg(np + 1);
+            n2 = __ldg(np + 2);
+        }
+        LeanUnit u;
+        lean_decode(q0, q1, q2, lane, u);
+        const uint32_t sg = u.s0 + (uint32_t)__popcll(sbase & zo);
+        const uint32_t vs = swz_off(u.v, swz);
+        double part = 0.0;
+        if (u.tab == 0xffffu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t off = vs ^ u.o[j];
+                double w;
+                if (REAL) {
+                    w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
+                } else {
+                    const double2 a = *reinterpret_cast<const double2*>(tb + off);
+                    const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
+                    w = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
+                }
+                part += flipsign(w, u.jsign >> j);
+            }
+        } else {
+            const double gl = s_beta[u.bidx] + __ldg(addtab + u.tab + lane);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t off = vs ^ u.o[j];
+                double w;
+                if (REAL) {
+                    w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
+                } else {
+                    const double2 a = *reinterpret_cast<const double2*>(tb + off);
+                    const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
+                    w = fma(b.x, a.x, b.y * a.y);
+                }
+                part = fma(flipsign(w, u.jsign >> j), gl + __ldg(addtab + u.hi0 + j), part);
+            }
+        }
+        er = fma(u.fr, flipsign(part, sg), er);
+        if (e + stride < e1) nzo = __ldg(fzout + (n0.w >> 16));
+        q0 = n0; q1 = n1; q2 = n2;
+        zo = nzo;
+    }
+    return er;
+}
 template <bool REAL>
 __global__ void __launch_bounds__(256, 3) k_expect_lean(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
                                                         const DevFlat2* __restrict__ flats, int n_flats,
@@ -1858,7 +1977,7 @@ __global__ void __launch_bounds__(256, 3) k_expect_lean(const __grid_constant__ 
                                                         const DevAddPat* __restrict__ addpat, int n_addpat,
                                                         const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
                                                         int* __restrict__ err) {
-    extern __shared__ __align__(128) double2 tile[];
+    extern __shared__ __align__(1024) double2 tile[];
     __shared__ double red[64];
     __shared__ uint64_t s_boff[16];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -1892,45 +2011,7 @@ __global__ void __launch_bounds__(256, 3) k_expect_lean(const __grid_constant__ 
             cp_async_wait_all();
         }
         __syncthreads();
-        for (int e = f0 + (int)warp; e < f1; e += (int)nw) {
-            const uint4* ep = reinterpret_cast<const uint4*>(flats + e);
-            const uint4 q0 = __ldg(ep), q1 = __ldg(ep + 1), q2 = __ldg(ep + 2);
-            LeanUnit u;
-            lean_decode(q0, q1, q2, lane, u);
-            const uint32_t sg = u.s0 + (uint32_t)__popcll(sbase & __ldg(fzout + (q0.w >> 16)));
-            double part = 0.0;
-            if (u.tab == 0xffffu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t off = u.v | u.o[j];
-                    double w;
-                    if (REAL) {
-                        w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
-                    } else {
-                        const double2 a = *reinterpret_cast<const double2*>(tb + off);
-                        const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
-                        w = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
-                    }
-                    part += flipsign(w, u.jsign >> j);
-                }
-            } else {
-                const double gl = s_beta[u.bidx] + __ldg(addtab + u.tab + lane);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t off = u.v | u.o[j];
-                    double w;
-                    if (REAL) {
-                        w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
-                    } else {
-                        const double2 a = *reinterpret_cast<const double2*>(tb + off);
-                        const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
-                        w = fma(b.x, a.x, b.y * a.y);
-                    }
-                    part = fma(flipsign(w, u.jsign >> j), gl + __ldg(addtab + u.hi0 + j), part);
-                }
-            }
-            er = fma(u.fr, flipsign(part, sg), er);
-        }
+        er += lean_entries<REAL>(tb, flats, f0 + (int)warp, f1, (int)nw, lane, sbase, fzout, addtab, s_beta, g.swz);
     }
     double2 sres = block_sum2(er, 0.0, red);
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
@@ -1938,55 +2019,13 @@ __global__ void __launch_bounds__(256, 3) k_expect_lean(const __grid_constant__ 
 
 // The same evaluation on the tile ring (one persistent CTA per SM, loads three tiles ahead of the arithmetic).
 template <bool REAL>
-__device__ __forceinline__ double lean_entry(const char* tb, const DevFlat2* __restrict__ flats, int e, uint32_t lane, uint64_t sbase,
-                                             const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
-                                             const double* s_beta) {
-    const uint4* ep = reinterpret_cast<const uint4*>(flats + e);
-    const uint4 q0 = __ldg(ep), q1 = __ldg(ep + 1), q2 = __ldg(ep + 2);
-    LeanUnit u;
-    lean_decode(q0, q1, q2, lane, u);
-    const uint32_t sg = u.s0 + (uint32_t)__popcll(sbase & __ldg(fzout + (q0.w >> 16)));
-    double part = 0.0;
-    if (u.tab == 0xffffu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t off = u.v | u.o[j];
-            double w;
-            if (REAL) {
-                w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
-            } else {
-                const double2 a = *reinterpret_cast<const double2*>(tb + off);
-                const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
-                w = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
-            }
-            part += flipsign(w, u.jsign >> j);
-        }
-    } else {
-        const double gl = s_beta[u.bidx] + __ldg(addtab + u.tab + lane);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t off = u.v | u.o[j];
-            double w;
-            if (REAL) {
-                w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
-            } else {
-                const double2 a = *reinterpret_cast<const double2*>(tb + off);
-                const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
-                w = fma(b.x, a.x, b.y * a.y);
-            }
-            part = fma(flipsign(w, u.jsign >> j), gl + __ldg(addtab + u.hi0 + j), part);
-        }
-    }
-    return u.fr * flipsign(part, sg);
-}
-template <bool REAL>
 __global__ void __launch_bounds__(512, 1) k_expect_pipe(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
                                                         const DevFlat2* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
                                                         const DevAddPat* __restrict__ addpat, int n_addpat,
                                                         const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
                                                         int* __restrict__ err) {
-    extern __shared__ __align__(128) double2 smem_tiles[];
+    extern __shared__ __align__(1024) double2 smem_tiles[];
     __shared__ double red[64];
     __shared__ __align__(8) uint64_t s_full[3];
     const uint32_t ts = 1u << g.tbits;
@@ -2014,7 +2053,7 @@ __global__ void __launch_bounds__(512, 1) k_expect_pipe(const __grid_constant__ 
             ring_issue_load(smem_tiles + (size_t)((k + 2) % 3) * ts, psi, g, tile_base_warp(g, bl, blockIdx.x + (k + 2) * gridDim.x),
                             &s_full[(k + 2) % 3], &tmap);
         if (!mbar_wait(&s_full[sl], (uint32_t)((k / 3) & 1u)) && err) *err = 2;
-        for (int e = f0 + (int)warp; e < f1; e += (int)nw) er += lean_entry<REAL>(tb, flats, e, lane, sbase, fzout, addtab, beta);
+        er += lean_entries<REAL>(tb, flats, f0 + (int)warp, f1, (int)nw, lane, sbase, fzout, addtab, beta, g.swz);
     }
     double2 sres = block_sum2(er, 0.0, red);
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
@@ -2032,7 +2071,7 @@ __global__ void __launch_bounds__(512, REAL ? 2 : 1) k_apply_lean(const __grid_c
                                                                   const DevAddPat* __restrict__ addpat, int n_addpat,
                                                                   const DevAddOut* __restrict__ addout, int accumulate,
                                                                   int* __restrict__ err) {
-    extern __shared__ __align__(128) double2 tile[];
+    extern __shared__ __align__(1024) double2 tile[];
     __shared__ uint64_t s_boff[16];
     __shared__ __align__(8) uint64_t s_mbar;
     const uint32_t ts = 1u << g.tbits;
@@ -2078,7 +2117,7 @@ __global__ void __launch_bounds__(512, REAL ? 2 : 1) k_apply_lean(const __grid_c
                 lean_decode(q0, q1, q2, lane, u);
                 const uint32_t oj = (j & 1u) ? ((j & 2u) ? ((j & 4u) ? u.o[7] : u.o[3]) : ((j & 4u) ? u.o[5] : u.o[1]))
                                              : ((j & 2u) ? ((j & 4u) ? u.o[6] : u.o[2]) : ((j & 4u) ? u.o[4] : u.o[0]));
-                const uint32_t off = u.v | oj, offb = off ^ u.lx16;
+                const uint32_t off = swz_off(u.v, g.swz) ^ oj, offb = off ^ u.lx16;  // oj, lx16: swizzled by the host
                 const uint32_t sg = u.s0 + (u.jsign >> j) + (uint32_t)__popcll(sbase & __ldg(fzout + (q0.w >> 16)));
                 double gw = 0.5 * u.fr;  // the expectation weight carries the factor 2 of the pair
                 if (u.tab != 0xffffu) gw *= s_beta[u.bidx] + __ldg(addtab + u.tab + lane) + __ldg(addtab + u.hi0 + j);
@@ -2100,7 +2139,8 @@ __global__ void __launch_bounds__(512, REAL ? 2 : 1) k_apply_lean(const __grid_c
         }
         for (uint32_t k = threadIdx.x; k < ts; k += bd) {
             double2* dp = amp_addr(g, dst, base, k);
-            double2 o = REAL ? make_double2(accr[k], 0.0) : accc[k];
+            const uint32_t ks = swz_idx(k, g.swz);  // the accumulator uses the source tile's layout
+            double2 o = REAL ? make_double2(accr[ks], 0.0) : accc[ks];
             if (accumulate) {
                 const double2 d = *dp;
                 o.x += d.x;
@@ -2683,6 +2723,9 @@ static int make_geom(const vqe_ctx* c, const TilePlan& tp, const uint64_t* d_sca
     g.lbits = tp.lbits;
     g.vbit = tp.vbit ? 1u : 0u;
     g.bulk = (tp.lbits >= 3 && env_int("VQE_BULK", 1)) ? 1u : 0u;  // segments of at least 128 bytes
+    g.tma = 0;
+    g.swz = 0;
+    memset(&g.tg, 0, sizeof g.tg);
     if (!tp.vbit) {
         g.n_tiles = tp.n_tiles;
         g.tile_first = 0;
@@ -2731,25 +2774,30 @@ static PFN_tmapEncodeTiled tmap_encoder() {
 }
 struct TmaShape {
     bool ok = false;
+    bool swizzled = false;
     TmaGeom tg;
     cuuint64_t gdim[5];
     cuuint64_t gstride[4];
     cuuint32_t box[5];
 };
 // Host-only: the tensor-map shape of a local tile plan (see TmaGeom).  ok = false: keep the per-segment bulk copies.
-static TmaShape plan_tma(const TilePlan& tp) {
+static TmaShape plan_tma(const TilePlan& tp, bool swizzle) {
     TmaShape sh;
     memset(&sh.tg, 0, sizeof sh.tg);
+    sh.swizzled = false;
     if (tp.vbit || tp.bits.empty() || tp.nl > 36) return sh;
+    if (swizzle && tp.lbits < 3) return sh;  // the 128-byte swizzle needs the three lowest index bits in the tile
     // runs of adjacent tile bits; a run is cut where a box would exceed 256 elements (dimension 0 counts doubles)
     struct Run { int start, len; };
     std::vector<Run> runs;
     for (int b : tp.bits) {
         const bool adjacent = !runs.empty() && runs.back().start + runs.back().len == b;
-        const int cap = (runs.size() == 1 && runs[0].start == 0) ? 7 : 8;  // the run at bit 0 is dimension 0: 2^(len+1) doubles
+        // the run at bit 0 is dimension 0 and counts doubles: at most 2^(7+1) of them; swizzled: exactly 8 amplitudes = 128 bytes
+        const int cap = (runs.size() == 1 && runs[0].start == 0) ? (swizzle ? 3 : 7) : 8;
         if (adjacent && runs.back().len < cap) runs.back().len++;
         else runs.push_back({b, 1});
     }
+    sh.swizzled = swizzle;
     // dimensions: breakpoints at 0 and at the start of the first (up to) five runs
     std::vector<int> starts, blog;
     size_t used_runs = 0;
@@ -2798,21 +2846,32 @@ static TmaShape plan_tma(const TilePlan& tp) {
 }
 // Fill g.tma / g.tg and encode the tensor map of buffer `ptr` for this plan; leaves g.tma = 0 when the plan has no
 // tensor-map form, the driver entry point is missing, or VQE_TMA=0.
-static void make_tmap(const TilePlan& tp, double2* ptr, TileGeom& g, CUtensorMap* map) {
+// would make_tmap(tp, ..., swizzle) succeed?  (plan-time decision of the lean Pauli-sum passes, whose entry tables are
+// pre-swizzled)
+static bool tma_available(const TilePlan& tp, bool swizzle) {
+    return env_int("VQE_TMA", 1) && tmap_encoder() && plan_tma(tp, swizzle).ok;
+}
+// swizzle: -1 = swizzled when the plan allows it, 0 = natural layout, 1 = swizzled or nothing
+static void make_tmap(const TilePlan& tp, double2* ptr, TileGeom& g, CUtensorMap* map, int swizzle = -1) {
     memset(map, 0, sizeof *map);
     g.tma = 0;
+    g.swz = 0;
     memset(&g.tg, 0, sizeof g.tg);
     if (!env_int("VQE_TMA", 1) || !ptr) return;
     PFN_tmapEncodeTiled enc = tmap_encoder();
     if (!enc) return;
-    const TmaShape sh = plan_tma(tp);
+    if (!env_int("VQE_SWIZZLE", 1) && swizzle < 0) swizzle = 0;
+    TmaShape sh = plan_tma(tp, swizzle != 0);
+    if (!sh.ok && swizzle < 0) sh = plan_tma(tp, false);
     if (!sh.ok) return;
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)ptr, sh.gdim, sh.gstride, sh.box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     sh.swizzled ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return;
     g.tg = sh.tg;
     g.tma = 1;
+    g.swz = sh.swizzled ? 0x70u : 0u;
 }
 
 // Host-only check of the tensor-map form of a tile plan (no CUDA call; CPU tests): emulates the TMA box traversal
@@ -2823,8 +2882,10 @@ extern "C" int vqe_debug_tma_check(int n_local, uint64_t need_mask, int tile_bit
                                    int32_t* dims_used) {
     if (n_local < 1 || n_local > 40) return fail(VQE_ERR_INVALID, "bad n_local");
     if (tile_bits < 1 || tile_bits > 12) tile_bits = 12;
+    const bool want_swz = max_tiles < 0;  // negative max_tiles: check the 128-byte-swizzled shape
+    max_tiles = max_tiles < 0 ? -max_tiles : max_tiles;
     const TilePlan tp = make_plan(n_local, need_mask, tile_bits, std::max(0, std::min(low_bits, tile_bits)), 0);
-    const TmaShape sh = plan_tma(tp);
+    const TmaShape sh = plan_tma(tp, want_swz);
     if (!sh.ok) return -1;
     if (n_req) *n_req = (int32_t)sh.tg.n_req;
     if (dims_used) {
@@ -3625,10 +3686,10 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
         if (all_col) {
             // every segment is a collapsed run / tabulated plane rotation: the lean kernel (256 threads, 3 CTAs per SM)
             const int n_cols = (int)(ps.col_end - ps.col_begin), n_ents = (int)(ps.ent_end - ps.ent_begin);
-            const size_t smem_c = tile_smem(ps.tp.tbits, 1, false) + (size_t)n_cols * (sizeof(DevCol) + 4) + (size_t)n_ents * sizeof(DevColEntry);
+            const size_t smem_c = tile_smem(ps.tp.tbits, 1, false) + (size_t)n_cols * (sizeof(ColLite) + 8 + 4) + (size_t)n_ents * sizeof(DevColEntry);
             const int thr = (int)std::min<uint64_t>(256, std::max<uint64_t>(32, (1ull << ps.tp.tbits) / 2));
             const int grid = tile_grid(c, g.n_tiles, smem_c <= 74 * 1024 ? 3 : 2);
-            const size_t smem_p = (size_t)NSLOT * tile_smem(ps.tp.tbits, 1, false) + (size_t)n_cols * (sizeof(DevCol) + 8) +
+            const size_t smem_p = (size_t)NSLOT * tile_smem(ps.tp.tbits, 1, false) + (size_t)n_cols * (sizeof(ColLite) + 8 + 8) +
                                   (size_t)n_ents * sizeof(DevColEntry);
             TileGeom gt = g;
             CUtensorMap tmap;
@@ -4132,6 +4193,7 @@ struct PSPass {
     bool cplx = false;  // some expectation weight has a non-zero imaginary part
     // lean pass (see DevFlat2): every group is tabulated per occupation pattern; none of the tables above is used
     bool lean = false;
+    bool swz = false;                   // the entries' per-j offsets and X-masks are stored in the 128-byte-swizzled layout
     std::vector<DevFlat2> flats2;       // entries, group after group
     std::vector<uint32_t> goff;         // n_lean_groups + 1 offsets into flats2 (sigma = O psi walks the groups)
     std::vector<double> addtab;         // T_lo[32] + T_hi[...] of every additive pattern
@@ -4281,8 +4343,9 @@ static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& te
         for (uint32_t ch = 0; ch < n_chunks; ++ch) {
             DevFlat2 fl;
             memset(&fl, 0, sizeof fl);
+            const uint32_t sw = p.swz ? 0x70u : 0u;
             fl.fr = additive ? 2.0 : 2.0 * beta0;
-            fl.lx16 = (uint16_t)(lx << 4);
+            fl.lx16 = (uint16_t)swz_off(lx << 4, sw);
             fl.lz16 = (uint16_t)(lz0 << 4);
             fl.pat16 = (uint16_t)(pat << 4);
             fl.zsel = (uint16_t)zsel;
@@ -4290,7 +4353,7 @@ static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& te
             uint32_t js = 0;
             for (uint32_t j = 0; j < 8; ++j) {
                 const uint32_t oj = pdep_free((ch << 8) | (j << 5));
-                fl.o16[j] = (uint16_t)(oj << 4);
+                fl.o16[j] = (uint16_t)swz_off(oj << 4, sw);
                 if (__builtin_popcount(oj & lz0) & 1) js |= 1u << j;
             }
             fl.jsign = (uint16_t)js;
@@ -4353,7 +4416,7 @@ static uint64_t cover_greedy(const std::vector<uint64_t>& xs, const std::vector<
 }
 
 static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int low_bits, int threads_cfg,
-                          std::vector<HTerm> terms) {
+                          std::vector<HTerm> terms, bool host_only = false) {
     // group by x (stable: keep first-appearance order of groups, term order inside)
     std::vector<uint64_t> xs;
     std::vector<std::vector<HTerm>> grp;
@@ -4419,6 +4482,7 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             PSPass p;
             p.lean = true;
             p.tp = make_plan(nl, need, tbits_max, lb_pass, 0);
+            p.swz = env_int("VQE_SWIZZLE", 1) != 0 && (host_only ? plan_tma(p.tp, true).ok : tma_available(p.tp, true));
             size_t taken = 0;
             for (size_t g : open) {
                 if ((xs[g] & lfull & ~p.tp.tile_mask) != 0) continue;
@@ -4879,7 +4943,7 @@ extern "C" int vqe_plan_paulisum(int n_qubits, int n_global, int tile_bits, int 
     int rc = collect_terms(&fake, n_terms, x, z, ny, cre, cim, terms);
     if (rc) return rc;
     vqe_paulisum ps;
-    rc = build_paulisum(&ps, n_qubits, n_qubits - n_global, tile_bits, low_bits, 512, std::move(terms));
+    rc = build_paulisum(&ps, n_qubits, n_qubits - n_global, tile_bits, low_bits, 512, std::move(terms), true);
     if (rc) return rc;
     if (n_groups) *n_groups = ps.n_groups;
     if (n_passes) *n_passes = (int32_t)ps.passes.size();
@@ -4940,7 +5004,7 @@ extern "C" int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int til
     if (rc) return rc;
     vqe_paulisum ps;
     const int nl = n_qubits - n_global;
-    rc = build_paulisum(&ps, n_qubits, nl, tile_bits, low_bits, 512, std::move(terms));
+    rc = build_paulisum(&ps, n_qubits, nl, tile_bits, low_bits, 512, std::move(terms), true);
     if (rc) return rc;
     const double2* psi = reinterpret_cast<const double2*>(psi_re_im);
     double2* sigma = reinterpret_cast<double2*>(sigma_re_im);
@@ -4967,9 +5031,10 @@ extern "C" int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int til
                 m ^= low;
             }
             const uint64_t sbase = base | sign_base;
+            const uint32_t sw = p.swz ? 0x70u : 0u;   // the kernels see the tile in the TMA 128-byte swizzle
             for (uint32_t k = 0; k < ts; ++k) {
-                addr[k] = base | p.tp.scat[k >> p.tp.lbits] | (uint64_t)(k & lmask);
-                tile[k] = psi[addr[k]];
+                addr[swz_idx(k, sw)] = base | p.tp.scat[k >> p.tp.lbits] | (uint64_t)(k & lmask);
+                tile[swz_idx(k, sw)] = psi[base | p.tp.scat[k >> p.tp.lbits] | (uint64_t)(k & lmask)];
                 acc[k] = make_double2(0.0, 0.0);
             }
             for (size_t k = 0; k < p.addpat.size(); ++k) {
@@ -4988,7 +5053,7 @@ extern "C" int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int til
                     LeanUnit u;
                     lean_decode(q[0], q[1], q[2], lane, u);
                     for (uint32_t j = 0; j < 8; ++j) {
-                        const uint32_t off = u.v | u.o[j], offb = off ^ u.lx16;
+                        const uint32_t off = swz_off(u.v, sw) ^ u.o[j], offb = off ^ u.lx16;
                         const double2 a = tile[off >> 4], b = tile[offb >> 4];
                         double gw = 0.5 * u.fr;
                         if (u.tab != 0xffffu) gw *= beta[u.bidx] + p.addtab[u.tab + lane] + p.addtab[u.hi0 + j];
@@ -5089,7 +5154,12 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             ProfScope prof(c, vbit ? 5 : 1);
             CUtensorMap tmap;
             memset(&tmap, 0, sizeof tmap);
-            if (pp.lean) make_tmap(pp.tp, vbit ? nullptr : shards[k][p].p0, geoms[k][p], &tmap);
+            if (pp.lean) {
+                make_tmap(pp.tp, vbit ? nullptr : shards[k][p].p0, geoms[k][p], &tmap, pp.swz ? 1 : 0);
+                if (pp.swz && !geoms[k][p].tma)
+                    return fail(VQE_ERR_CUDA, "the Pauli sum was lowered for tensor-map (TMA) tile loads, which are not available now "
+                                              "(VQE_TMA / VQE_SWIZZLE changed after vqe_paulisum_create?)");
+            }
             const bool pipe = pp.lean && (geoms[k][p].bulk || geoms[k][p].tma) && env_int("VQE_PIPE", 0) != 0 &&
                               3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double) <= 226 * 1024;
             if (pipe) {
@@ -5235,7 +5305,9 @@ static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* 
             ProfScope prof(c, 2);
             if (pp.lean) {
                 CUtensorMap tmap;
-                make_tmap(pp.tp, vbit ? nullptr : ssrc.p0, g, &tmap);
+                make_tmap(pp.tp, vbit ? nullptr : ssrc.p0, g, &tmap, pp.swz ? 1 : 0);
+                if (pp.swz && !g.tma)
+                    return fail(VQE_ERR_CUDA, "the Pauli sum was lowered for tensor-map (TMA) tile loads, which are not available now");
                 const int n_lg = (int)pp.goff.size() - 1;
                 const int thr = (int)std::min<uint64_t>(512, std::max<uint64_t>(32, ts / 2));
                 if (real_src) {
