@@ -42,7 +42,9 @@ typedef struct vqe_paulisum vqe_paulisum; /* device-resident, X-mask-grouped Pau
 enum { VQE_GATE_X = 0, VQE_GATE_H = 1, VQE_GATE_RX = 2, VQE_GATE_RY = 3, VQE_GATE_RZ = 4, VQE_GATE_CNOT = 5 };
 
 /* state buffers inside a context */
-enum { VQE_BUF_PSI = 0, VQE_BUF_SIGMA = 1, VQE_BUF_WORK = 2 };
+/* VQE_BUF_AUX is a fourth, rank-local vector (never an operand of a peer pass of a sharded state): it keeps the
+ * Lanczos ground state that replaces the dense eigh of fermionic_adapt_vqe.py:474 for the fidelity */
+enum { VQE_BUF_PSI = 0, VQE_BUF_SIGMA = 1, VQE_BUF_WORK = 2, VQE_BUF_AUX = 3 };
 
 const char* vqe_last_error(void);
 int vqe_version(void);
@@ -113,6 +115,10 @@ int vqe_apply_plane_rotations(vqe_ctx* ctx, int n_ops, const uint64_t* xmask, co
                               const uint64_t* pattern, const double* cosv, const double* sinv);
 /* buf <- (re + i im) * buf  (global phase or scale) */
 int vqe_scale_state(vqe_ctx* ctx, int buf, double re, double im);
+/* dst <- alpha * x + beta * dst on two buffers of the context (the vector updates of the Lanczos iteration that
+ * replaces np.linalg.eigh(hamiltonian_sp.get_matrix()), fermionic_adapt_vqe.py:474, and of the Taylor form of
+ * expm_multiply, fermionic_adapt_vqe.py:35-38, when it is driven from the host on a sharded state) */
+int vqe_axpby(vqe_ctx* ctx, int dst_buf, int x_buf, double alpha_re, double alpha_im, double beta_re, double beta_im);
 
 /* Device-resident Pauli sum  O = sum_k (cre_k + i cim_k) P_k, grouped by X-mask at creation.
  * Replaces the `observable=hamiltonian_sp` argument of the OBS job (get_energy_ucc.py:47) and the

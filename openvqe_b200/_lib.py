@@ -26,6 +26,7 @@ SYMBOLS = [
     "vqe_shard_barrier", "vqe_shard_status", "vqe_group_apply_pauli_rotations", "vqe_group_apply_gates",
     "vqe_group_expectation", "vqe_group_apply_paulisum", "vqe_group_pool_overlaps", "vqe_plan_rotations",
     "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf", "vqe_plan_paulisum", "vqe_debug_lean_host", "vqe_peer_bytes", "vqe_debug_tma_check",
+    "vqe_axpby",
 ]
 IPC_HANDLE_BYTES = 64
 SHARD_FLAGS = 3
@@ -97,6 +98,7 @@ def load():
         "vqe_group_pool_overlaps": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
         "vqe_apply_plane_rotations": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
         "vqe_scale_state": (C.c_int, [vp, C.c_int, dbl, dbl]),
+        "vqe_axpby": (C.c_int, [vp, C.c_int, C.c_int, dbl, dbl, dbl, dbl]),
         "vqe_plan_rotations": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int,
                                          vp, vp, vp, vp, vp]),
         "vqe_plan_paulisum": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp,

@@ -8,7 +8,7 @@ changes is where the arithmetic runs:
   sig = H_sparse.dot(psi); |pool| sparse matvecs    one H|psi> kernel + one batched pool sweep
   build_ucc_ansatz + myQLM simulator (energies)     Pauli-rotation tile kernel + expectation kernel
   scipy expm_multiply per ansatz operator           exact generator exponential on the device
-  dense eigh + sample loop (fidelity)               host eigh (n <= 14) + device overlap
+  dense eigh + sample loop (fidelity)               host eigh (n <= 14) / device Lanczos above + device overlap
 
 The 2^n x 2^n scipy matrices (``hamiltonian_sparse``, ``cluster_ops_sparse``) of the main entry point are accepted
 but never touched: everything is derived from the Pauli lists ``hamiltonian_sp`` / ``cluster_ops_sp`` (the same
@@ -26,7 +26,8 @@ from ..common_files.sorted_gradient import abs_sort_desc, corresponding_index, i
 from ..engine import BUF_PSI, get_engine
 from ..lowering import as_operator, is_matrix, pack_operator
 
-FIDELITY_MAX_QUBITS = 14  # dense eigh is O(8^n): skipped above this, fidelity reported as nan
+FIDELITY_MAX_QUBITS = 14  # dense eigh is O(8^n): above this the ground state comes from a Lanczos iteration on the device
+LANCZOS_MAX_QUBITS = 31   # four resident vectors (psi, sigma, work, ground state): 4 x 34 GB at 31 qubits
 
 
 def prepare_adapt_state(reference_ket, spmat_ops, parameters):
@@ -157,14 +158,18 @@ def get_statevector(result, nbqbits):
 
 
 def fun_fidelity(circ, eigenvalues, eigenvectors, nbqbits):
-    """|<gs|psi_circ>|^2 (reference :331-361); the overlap is reduced on the device."""
-    ee = eigenvectors[:, np.argmin(eigenvalues)]
+    """|<gs|psi_circ>|^2 (reference :331-361); the overlap is reduced on the device.  ``eigenvectors`` is the reference's
+    dense eigenvector matrix or a ``ground_state.DeviceGroundState`` (vector resident in the engine's aux buffer)."""
     engine = get_engine(nbqbits)
+    on_device = hasattr(eigenvectors, "fidelity")
+    ee = None if on_device else eigenvectors[:, np.argmin(eigenvalues)]
     form = getattr(circ, "rotation_form", None)
     if form is not None:
         _hotpath.prepare_ucc_state(engine, form[0], form[1], form[2])
     else:
         _circuit_state(engine, circ)
+    if on_device:
+        return eigenvectors.fidelity(BUF_PSI)
     return abs(engine.overlap_host(ee, BUF_PSI)) ** 2
 
 
@@ -185,6 +190,11 @@ def fermionic_adapt_vqe(hamiltonian_sparse, cluster_ops_sparse, reference_ket, h
     engine = get_engine(nbqbits)
     if nbqbits <= FIDELITY_MAX_QUBITS and hasattr(hamiltonian_sp, "get_matrix"):
         eigenvalues, eigenvectors = np.linalg.eigh(hamiltonian_sp.get_matrix())
+    elif nbqbits <= LANCZOS_MAX_QUBITS and not getattr(engine, "n_global", 0):
+        # lowest eigenpair of the HF state's symmetry sector by Lanczos on the device (ground_state.py)
+        from ..ground_state import lanczos_ground_state
+        eigenvectors = lanczos_ground_state(engine, hamiltonian_sp, int(hf_init_sp))
+        eigenvalues = np.array([eigenvectors.energy])
     else:
         eigenvalues = eigenvectors = None  # fidelity reported as nan
     hf_state = prepare_hf_state(hf_init_sp, cluster_ops_sp)

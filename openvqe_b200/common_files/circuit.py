@@ -44,6 +44,17 @@ class CircuitSummary:
                 key = keys[ident]
             self.ops.append(GateOp(key, qbits, name, angle))
 
+    def to_job(self, job_type="SAMPLE", observable=None, **kw):
+        """myQLM's ``Circuit.to_job`` shape, for ``openvqe_b200.qpu.B200QPU().submit(...)``."""
+        return CircuitJob(self, job_type, observable)
+
+
+class CircuitJob:
+    __slots__ = ("circuit", "job_type", "observable")
+
+    def __init__(self, circuit, job_type, observable):
+        self.circuit, self.job_type, self.observable = circuit, job_type, observable
+
 
 def count(gate, mylist):
     """Number of ops whose string contains ``gate='<GATE>'`` (lower-case names

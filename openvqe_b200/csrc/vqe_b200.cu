@@ -2274,7 +2274,7 @@ struct vqe_ctx {
     double2* gstage = nullptr;              // staging buffer of gather-form peer passes
     size_t gstage_cap = 0;                  // in amplitudes
     cudaStream_t stream = nullptr;
-    double2* buf[3] = {nullptr, nullptr, nullptr};
+    double2* buf[4] = {nullptr, nullptr, nullptr, nullptr};  // psi, sigma, work + aux (local only: never a peer-pass operand)
     // staging
     char* h_stage = nullptr;
     char* d_stage = nullptr;
@@ -2380,7 +2380,7 @@ static int ensure_result(vqe_ctx* c, size_t n) {
     return VQE_OK;
 }
 static int ensure_buf(vqe_ctx* c, int b) {
-    if (b < 0 || b > 2) return fail(VQE_ERR_INVALID, "bad buffer id %d", b);
+    if (b < 0 || b > 3) return fail(VQE_ERR_INVALID, "bad buffer id %d", b);
     if (c->buf[b]) return VQE_OK;
     cudaError_t e = cudaMalloc((void**)&c->buf[b], c->n_amp * sizeof(double2));
     if (e != cudaSuccess) {
@@ -2517,6 +2517,7 @@ static void free_ctx(vqe_ctx* c) {
             if (c->peer_buf[b][r] && c->peer_ipc[b][r]) cudaIpcCloseMemHandle(c->peer_buf[b][r]);
         if (c->buf[b]) cudaFree(c->buf[b]);
     }
+    if (c->buf[3]) cudaFree(c->buf[3]);
     for (int r = 0; r < MAX_RANKS; ++r)
         if (c->peer_flags[r] && c->peer_flags_ipc[r]) cudaIpcCloseMemHandle(c->peer_flags[r]);
     if (c->flags) cudaFree(c->flags);
@@ -2713,6 +2714,7 @@ static int rank_barrier(RankSet& rs) {
 // per-rank launch geometry of a plan
 static double2* shard_ptr(const vqe_ctx* c, int buf, int rank) {
     if (rank == c->rank) return c->buf[buf];
+    if (buf > 2) return nullptr;  // the aux buffer is not shared between ranks
     if (c->peer_ctx[rank]) return c->peer_ctx[rank]->buf[buf];
     return c->peer_buf[buf][rank];
 }
@@ -3040,7 +3042,7 @@ extern "C" int vqe_copy_buffer(vqe_ctx* c, int dst, int src) {
 extern "C" int vqe_buffer_ptr(vqe_ctx* c, int b, void** p, uint64_t* n_amp) {
     if (!c || !p) return fail(VQE_ERR_INVALID, "null argument");
     CK(cudaSetDevice(c->device));
-    if (b < 0 || b > 2) return fail(VQE_ERR_INVALID, "bad buffer id %d", b);
+    if (b < 0 || b > 3) return fail(VQE_ERR_INVALID, "bad buffer id %d", b);
     int rc = ensure_buf(c, b);
     if (rc) return rc;
     *p = c->buf[b];
@@ -3897,7 +3899,7 @@ static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const u
                           const double* angle, int buf = VQE_BUF_PSI) {
     int rc0 = check_rankset(rs);
     if (rc0) return rc0;
-    if (buf < 0 || buf > 2) return fail(VQE_ERR_INVALID, "bad buffer id %d", buf);
+    if (buf < 0 || buf > 3) return fail(VQE_ERR_INVALID, "bad buffer id %d", buf);
     vqe_ctx* c = rs.r[0];
     if (n_rot < 0 || (n_rot > 0 && (!xmask || !zmask || !ny || !angle))) return fail(VQE_ERR_INVALID, "null array");
     const uint64_t full = (1ull << c->n) - 1ull;
@@ -4103,6 +4105,22 @@ extern "C" int vqe_scale_state(vqe_ctx* c, int b, double re, double im) {
     if (rc) return rc;
     if (b == VQE_BUF_PSI && im != 0.0) c->psi_real = false;
     k_axpby<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[b], c->buf[b], c->n_amp, re, im, 0.0, 0.0);
+    c->launches++;
+    CK(cudaGetLastError());
+    return VQE_OK;
+}
+
+// dst = alpha * x + beta * dst on two buffers of the context (BLAS-1 helper of the Lanczos ground state and of the
+// host-driven Taylor exponential on sharded states; purely local, no peer traffic)
+extern "C" int vqe_axpby(vqe_ctx* c, int dst, int x, double a_re, double a_im, double b_re, double b_im) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_buf(c, dst);
+    if (rc) return rc;
+    rc = ensure_buf(c, x);
+    if (rc) return rc;
+    if (dst == VQE_BUF_PSI) c->psi_real = false;
+    k_axpby<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[dst], c->buf[x], c->n_amp, a_re, a_im, b_re, b_im);
     c->launches++;
     CK(cudaGetLastError());
     return VQE_OK;

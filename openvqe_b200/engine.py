@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from .lowering import PackedTerms, pack_operator, pack_pool
 
-BUF_PSI, BUF_SIGMA, BUF_WORK = 0, 1, 2
+BUF_PSI, BUF_SIGMA, BUF_WORK, BUF_AUX = 0, 1, 2, 3
 GATE_X, GATE_H, GATE_RX, GATE_RY, GATE_RZ, GATE_CNOT = range(6)
 GATE_KINDS = {"X": GATE_X, "H": GATE_H, "RX": GATE_RX, "RY": GATE_RY, "RZ": GATE_RZ, "CNOT": GATE_CNOT}
 
@@ -124,6 +124,11 @@ class Engine:
     def scale_state(self, factor: complex, buf=BUF_PSI):
         f = complex(factor)
         _lib.check(self._lib.vqe_scale_state(self.handle, buf, f.real, f.imag))
+
+    def axpby(self, dst, x, alpha: complex = 1.0, beta: complex = 1.0):
+        """buffer dst <- alpha * buffer x + beta * buffer dst (rank-local)."""
+        a, b = complex(alpha), complex(beta)
+        _lib.check(self._lib.vqe_axpby(self.handle, int(dst), int(x), a.real, a.imag, b.real, b.imag))
 
     def apply_exp(self, packed: PackedTerms, theta: float):
         """psi <- exp(theta * A) psi (exact exponential of the whole generator)."""

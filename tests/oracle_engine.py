@@ -30,7 +30,7 @@ class OracleEngine:
     def __init__(self, n_qubits, device=0):
         self.n = self.n_local = int(n_qubits)
         self.device = device
-        self.buf = {k: np.zeros(1 << self.n, dtype=np.complex128) for k in range(3)}
+        self.buf = {k: np.zeros(1 << self.n, dtype=np.complex128) for k in range(4)}
         self.launch_count = 0
 
     # -- state
@@ -48,6 +48,9 @@ class OracleEngine:
 
     def scale_state(self, factor, buf=0):
         self.buf[buf] = self.buf[buf] * complex(factor)
+
+    def axpby(self, dst, x, alpha=1.0, beta=1.0):
+        self.buf[dst] = complex(alpha) * self.buf[x] + complex(beta) * self.buf[dst]
 
     # -- state preparation
     def apply_rotations(self, x, z, ny, angles, buf=0):
