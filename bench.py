@@ -2,9 +2,12 @@
 """bench.py -- UCC energy evaluations per second on the 24-qubit (C4-scale) workload, ADAPT pool-gradient sweep
 time vs qubits, and the fraction of the HBM roofline the two hot kernels reach.
 
-A "step" is ONE energy evaluation E(theta) of the Trotterised UCCSD ansatz: |HF> -> 14 112 Pauli rotations
-(1 818 generators) -> <H> over 14 905 Pauli terms in 2 767 X-mask groups, on a 2^24 complex128 state (268 MB,
-larger than the 126 MB L2, so nothing is L2-resident between sweeps).  theta changes every step.
+A "step" is ONE energy evaluation E(theta) of the Trotterised UCCSD ansatz on the 24-qubit instance BASELINE.json names
+for config C4 -- H2O / 6-31G, O 1s frozen, (8e,12o): |HF> -> 11 008 Pauli rotations (1 424 generators) -> <H> over 8 921
+Pauli terms in 1 567 X-mask groups -- on a 2^24 complex128 state (268 MB, larger than the 126 MB L2, so nothing is
+L2-resident between sweeps).  theta changes every step.  `--molecule h12` selects the round-1 stand-in instead (H12
+chain / STO-3G: 14 112 rotations, 1 818 generators, 14 905 terms in 2 767 groups); the default N = 1 run reports it under
+`h12_standin` for continuity with round 1.
 
   value     evaluations/s with the Hamiltonian and rotation program resident in HBM (only the angles and the
             16-byte result cross PCIe), timed with CUDA events on the engine's stream, per-launch profiling OFF.
@@ -21,14 +24,14 @@ larger than the 126 MB L2, so nothing is L2-resident between sweeps).  theta cha
             carries `sharded_c5`: the synthetic C5 program on a state SHARDED over the N ranks (33 + log2 N qubits =
             137 GB per GPU; one energy + one forward-difference gradient component; sharded == unsharded check at 30 q).
 
-Beside the headline: `adapt_pool_sweep` (sigma = H psi + <sigma|A_k|psi> for the 1 818-operator pool at 24 qubits,
+Beside the headline: `adapt_pool_sweep` (sigma = H psi + <sigma|A_k|psi> for the pool of the workload's generators at 24 qubits,
 with the CPU port timed on a sample beside it), `adapt_pool_sweep_12q` (the reference-shaped return_gradient_list on
 the H6 fixture against the oracle's scipy restatement of the reference code), `qubit_sweep` (energy evaluation and pool
 sweep at 12...30 qubits, GPU and CPU port) and `quccsd` (the same excitations through EnergyUCC.action_quccsd).
 
 `--impl reference` times the CPU port of the reference path (oracle/c, OpenMP over all host cores, thread count set
 explicitly because torchrun exports OMP_NUM_THREADS=1): every timed step is ONE FULL evaluation of the same workload
-(all 14 112 rotations and all 14 905 terms, one 2^24 sweep each -- the cost structure of the reference's simulator).
+(all rotations and all Hamiltonian terms, one 2^24 sweep each -- the cost structure of the reference's simulator).
 """
 from __future__ import annotations
 
@@ -44,23 +47,34 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "C4-scale 24-qubit UCCSD energy evaluation (H12/STO-3G stand-in for H2O/6-31G active space): " \
-           "14112 Pauli rotations + <H> over 14905 terms / 2767 X-mask groups"
+# 24-qubit workloads (packed fixtures, tests/golden): the molecule BASELINE.json names for config C4 and the round-1 stand-in
+MOLECULES = {
+    "h2o": ("h2o_631g_24q.npz", "C4: H2O/6-31G, O 1s frozen, (8e,12o) active space, 24-qubit UCCSD energy evaluation"),
+    "h12": ("h12_sto3g_24q.npz", "C4-scale stand-in of round 1: H12 chain/STO-3G, 24-qubit UCCSD energy evaluation"),
+}
 NCU_TRAFFIC = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
 
 
-def load_workload():
-    z = np.load(os.path.join(ROOT, "tests", "golden", "h12_sto3g_24q.npz"))
+def load_workload(molecule=None):
+    """The packed 24-qubit problem instance: default = the molecule BASELINE.json names (VQE_BENCH_MOLECULE / --molecule
+    select the round-1 H12 stand-in instead)."""
+    molecule = (molecule or os.environ.get("VQE_BENCH_MOLECULE", "h2o")).lower()
+    fname, label = MOLECULES[molecule]
+    z = np.load(os.path.join(ROOT, "tests", "golden", fname))
     w = {k: z[k] for k in z.files}
     w["n"] = int(w["n"])
     w["hf_init_sp"] = int(w["hf_init_sp"])
     w["meta"] = json.loads(str(w["meta"]))
+    w["molecule"] = molecule
+    w["label"] = "%s: %d Pauli rotations (%d generators) + <H> over %d terms / %d X-mask groups" % (
+        label, len(w["rot_x"]), int(w["rot_owner"].max()) + 1, len(w["ham_x"]), len(set(w["ham_x"].tolist())))
     return w
 
 
-def config_for(n, world):
+def config_for(w, world):
     """The `config` object of the JSON line -- identical for the repo arm and the reference arm."""
-    return {"workload": WORKLOAD, "qubits": n, "state_bytes": 16.0 * (1 << n),
+    n = w["n"]
+    return {"workload": w["label"], "molecule": w["molecule"], "qubits": n, "state_bytes": 16.0 * (1 << n),
             "l2_policy": "state (268 MB) larger than L2 (126 MB)",
             "parallelism": "replicas: independent energy evaluations per GPU" if world > 1 else "1 GPU"}
 
@@ -213,7 +227,7 @@ def run_reference(args, rank, world):
         return
     from oracle import c_oracle
     cores = c_oracle.set_threads()
-    w = load_workload()
+    w = load_workload(args.molecule)
     n = w["n"]
     rot, ham = packed_from(w, "rot"), packed_from(w, "ham")
     owner, rc = w["rot_owner"], np.asarray(w["rot_c"], dtype=np.float64)
@@ -236,7 +250,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "ucc_energy_evals_per_s", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
             "steps": len(secs), "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)",
-            "data": "synthetic", "config": config_for(n, world), "energy_first_step": energies[0],
+            "data": "synthetic", "config": config_for(w, world), "energy_first_step": energies[0],
             "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port",
                              "sample": "every timed step is one FULL evaluation (14112 rotations + 14905 terms, one 2^24 sweep each); "
                                        "CPU port = oracle/c/vqe_oracle.c (OpenMP, %d threads set explicitly), the reference's own myQLM "
@@ -382,6 +396,36 @@ def qubit_sweep(device, sizes, with_cpu=True):
     return out
 
 
+def quick_value(molecule, device, steps, warmup):
+    """Device-timed evaluations/s of another 24-qubit instance (same step as the headline, resident inputs)."""
+    from openvqe_b200.engine import Engine
+    from openvqe_b200.lowering import PackedTerms
+    w = load_workload(molecule)
+    n = w["n"]
+    eng = Engine(n, device=device)
+    hp, rot = packed_from(w, "ham"), packed_from(w, "rot")
+    ps = eng.paulisum(PackedTerms(n, hp.x, hp.z, hp.ny, hp.cre, hp.cim))
+    owner, rc = w["rot_owner"], np.asarray(w["rot_c"], dtype=np.float64)
+    ths = thetas_for(w, warmup + steps, 0)
+    energies = []
+
+    def step(theta):
+        eng.set_basis_state(w["hf_init_sp"])
+        eng.apply_rotations(rot.x, rot.z, rot.ny, theta[owner] * rc)
+        return eng.expectation(ps).real
+
+    for th in ths[:warmup]:
+        step(th)
+    eng.synchronize()
+    l0 = eng.launch_count
+    eng.timer_begin()
+    for th in ths[warmup:]:
+        energies.append(step(th))
+    ms = eng.timer_end()
+    return {"workload": w["label"], "ms_per_step": ms / steps, "evals_per_s": steps / (ms / 1e3),
+            "gpu_launches": int(eng.launch_count - l0), "energy_first_step": energies[0]}
+
+
 def run_ours(args, rank, world, local_rank):
     from openvqe_b200.engine import BUF_PSI, BUF_SIGMA, Engine
     from openvqe_b200.lowering import PackedTerms
@@ -391,7 +435,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    w = load_workload()
+    w = load_workload(args.molecule)
     n = w["n"]
     S = 16.0 * (1 << n)
     eng = Engine(n, device=local_rank)
@@ -599,7 +643,7 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": "ucc_energy_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",
-            "config": config_for(n, world), "energy_first_step": energies[0],
+            "config": config_for(w, world), "energy_first_step": energies[0],
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps, "ms_per_step": ms_e2e / args.steps,
                     "api": "openvqe_b200.ucc_family.get_energy_ucc.EnergyUCC.ucc_action"},
@@ -608,6 +652,8 @@ def run_ours(args, rank, world, local_rank):
             "adapt_pool_sweep": pool_sweep, "adapt_pool_sweep_12q": sweep12, "qubit_sweep": qsweep, "quccsd": quccsd}
     if sharded is not None:
         line["sharded_c5"] = sharded
+    if world == 1 and not args.no_pool and w["molecule"] != "h12":
+        line["h12_standin"] = quick_value("h12", local_rank, args.steps, args.warmup)
     if world == 1 and not args.no_cpu:
         cb = cpu_sample(w)
         line["cpu_baseline"] = {"value": 1.0 / cb["seconds_per_eval"], "unit": "evals/s", "cores": cb["cores"],
@@ -862,6 +908,8 @@ def main():
     ap.add_argument("--no-pool", action="store_true", help="skip the ADAPT pool-gradient sweep / QUCCSD / qubit-sweep legs")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 12...30-qubit sweep")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded C5 leg")
+    ap.add_argument("--molecule", default=None, choices=sorted(MOLECULES),
+                    help="24-qubit instance of the c4 workload (default: VQE_BENCH_MOLECULE or h2o, the molecule BASELINE names)")
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4: 24-qubit UCCSD energy (headline; replicas when N > 1, plus the sharded C5 leg).  c5: only the "
                          "synthetic 30-36 qubit state SHARDED over the N GPUs")

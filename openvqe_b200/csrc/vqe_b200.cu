@@ -820,21 +820,64 @@ __device__ __forceinline__ void rot_sub1(double2* tile, const RotOp* __restrict_
     tile[l0 ^ lx] = b;
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-parallel tile base.  base = pdep(tile number, comp_mask): lane i owns the i-th set bit of comp_mask (found once
+// per kernel), a tile costs one shift/and per lane and two warp-wide OR reductions (REDUX) instead of a serial
+// bit loop in every thread.
+// ------------------------------------------------------------------------------------------
+struct BaseLane {
+    uint32_t pos;   // index-bit position of this lane's bit of comp_mask
+    uint32_t act;   // 0: comp_mask has fewer set bits than this lane's number
+};
+__device__ __forceinline__ BaseLane base_lane_init(const TileGeom& g) {
+    BaseLane bl;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t m = g.comp_mask;
+    for (uint32_t i = 0; i < lane && m; ++i) m &= m - 1;  // drop the lane lowest set bits
+    bl.act = m ? 1u : 0u;
+    bl.pos = m ? (uint32_t)(__ffsll((long long)m) - 1) : 0u;
+    return bl;
+}
+__device__ __forceinline__ uint64_t tile_base_warp(const TileGeom& g, const BaseLane& bl, uint64_t t) {
+    const uint64_t tnum = g.tile_first + t * g.tile_stride;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t bit = (bl.act && ((tnum >> lane) & 1ull)) ? (1ull << bl.pos) : 0ull;
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)bit);
+    const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(bit >> 32));
+    return ((uint64_t)hi << 32) | lo;
+}
+
 // REAL: the state is known to be purely real on entry and every rotation of the pass has a +-1 phase (ny odd: the
 // UCC case -- JW images of T - T^dagger), so the imaginary parts stay exactly zero and are never touched.
 // phase A of a gather-form peer pass: copy the needed partner amplitudes of tiles [g.tile_first, +g.n_tiles) into
 // the local staging buffer
-__global__ void k_gather_need(Shards psi, TileGeom g, GatherGeom gg, double2* __restrict__ stage_out) {
-    const uint32_t top = g.tbits - 1u;
-    const uint32_t par_off = gg.own_half ? 0u : (1u << top);
-    const uint64_t per_tile = (uint64_t)gg.n_need * 4u;
-    const uint64_t total = per_tile * g.n_tiles;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t t = i / per_tile;
-        const uint32_t q = (uint32_t)(i - t * per_tile);
-        const uint32_t k = par_off + (uint32_t)gg.need[q >> 2] * 4u + (q & 3u);
-        stage_out[i] = *amp_addr(g, psi, tile_base(g, t), k);
+// One WARP per tile: the lanes walk the tile's need groups, one group = 64 contiguous bytes = four independent 16-byte
+// loads in flight per lane (remote reads over NVLink have microseconds of latency: the copy is latency-bound, not
+// issue-bound); the tile base is formed warp-parallel.  Called by the stand-alone kernel for the first chunk of a pass
+// and by the gather CTAs that ride along in the pass kernel of chunk k to fetch chunk k + 1 under its arithmetic.
+__device__ __forceinline__ void gather_need_warps(const Shards& psi, const TileGeom& g, const GatherGeom& gg, uint64_t tile_first,
+                                                  uint64_t n_tiles, double2* __restrict__ stage_out, uint32_t warp_id, uint32_t n_warps) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lmask = (1u << g.lbits) - 1u;
+    const double2* src = gg.own_half ? psi.p0 : psi.p1;  // the partner's shard
+    const BaseLane bl = base_lane_init(g);
+    for (uint64_t t = warp_id; t < n_tiles; t += n_warps) {
+        const uint64_t tnum = tile_first + t * g.tile_stride;
+        const uint64_t bit = (bl.act && ((tnum >> lane) & 1ull)) ? (1ull << bl.pos) : 0ull;
+        const uint64_t base = ((uint64_t)__reduce_or_sync(0xffffffffu, (uint32_t)(bit >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)bit);
+        double2* out = stage_out + t * (uint64_t)gg.n_need * 4u;
+        for (uint32_t q = lane; q < gg.n_need; q += 32u) {
+            const uint32_t kl = (uint32_t)__ldg(gg.need + q) * 4u;  // tile-local index inside the partner's half
+            const double2* p = src + (base | __ldg(g.scat + (kl >> g.lbits)) | (uint64_t)(kl & lmask));
+            const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
+            double2* o = out + (uint64_t)q * 4u;
+            o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3;
+        }
     }
+}
+__global__ void __launch_bounds__(256) k_gather_need(Shards psi, TileGeom g, GatherGeom gg, double2* __restrict__ stage_out) {
+    gather_need_warps(psi, g, gg, g.tile_first, g.n_tiles, stage_out, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),
+                      gridDim.x * (blockDim.x >> 5));
 }
 
 template <bool REAL>
@@ -844,8 +887,17 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
                                                      const DevSub* __restrict__ subs, int n_subs,
                                                      const DevCol* __restrict__ cols, int n_cols,
                                                      const DevColEntry* __restrict__ ents, int n_ents, double pass_scale,
-                                                     int* __restrict__ err) {
+                                                     int* __restrict__ err, GatherGeom gnext, uint64_t next_first, uint64_t next_tiles,
+                                                     double2* __restrict__ next_stage, uint32_t n_gctas) {
     extern __shared__ __align__(1024) double2 tile[];
+    // gather-form peer pass, chunk k: the first n_gctas CTAs fetch the partner amplitudes chunk k + 1 needs into the other
+    // staging buffer while the remaining CTAs run the pass on chunk k (NVLink reads under HBM-bound arithmetic)
+    if (blockIdx.x < n_gctas) {
+        gather_need_warps(psi, g, gnext, next_first, next_tiles, next_stage, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),
+                          n_gctas * (blockDim.x >> 5));
+        return;
+    }
+    const uint32_t cta = blockIdx.x - n_gctas, n_cta = gridDim.x - n_gctas;
     const uint32_t ts = 1u << g.tbits;
     const bool four = (ts >> 1) == 4u * blockDim.x;  // host guarantees: 4 pairs (one orbit) per thread, or at most 1 pair
     RotOp* optab = (RotOp*)(tile + ts);
@@ -874,7 +926,7 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
         f.pad[0] = f.pad[1] = 0;
         optab[r] = f;
     }
-    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+    for (uint64_t t = cta; t < g.n_tiles; t += n_cta) {
         const uint64_t base = tile_base(g, t);
         const uint64_t sbase = base | g.sign_base;
         __syncthreads();
@@ -990,33 +1042,6 @@ __global__ void __launch_bounds__(512, REAL ? 3 : 2) k_tile_rot(Shards psi, Tile
         }
     }
     if (bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores have landed
-}
-
-// ------------------------------------------------------------------------------------------
-// Warp-parallel tile base.  base = pdep(tile number, comp_mask): lane i owns the i-th set bit of comp_mask (found once
-// per kernel), a tile costs one shift/and per lane and two warp-wide OR reductions (REDUX) instead of a serial
-// bit loop in every thread.
-// ------------------------------------------------------------------------------------------
-struct BaseLane {
-    uint32_t pos;   // index-bit position of this lane's bit of comp_mask
-    uint32_t act;   // 0: comp_mask has fewer set bits than this lane's number
-};
-__device__ __forceinline__ BaseLane base_lane_init(const TileGeom& g) {
-    BaseLane bl;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint64_t m = g.comp_mask;
-    for (uint32_t i = 0; i < lane && m; ++i) m &= m - 1;  // drop the lane lowest set bits
-    bl.act = m ? 1u : 0u;
-    bl.pos = m ? (uint32_t)(__ffsll((long long)m) - 1) : 0u;
-    return bl;
-}
-__device__ __forceinline__ uint64_t tile_base_warp(const TileGeom& g, const BaseLane& bl, uint64_t t) {
-    const uint64_t tnum = g.tile_first + t * g.tile_stride;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t bit = (bl.act && ((tnum >> lane) & 1ull)) ? (1ull << bl.pos) : 0ull;
-    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)bit);
-    const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(bit >> 32));
-    return ((uint64_t)hi << 32) | lo;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2271,8 +2296,8 @@ struct vqe_ctx {
     cudaEvent_t ev_bar = nullptr;           // in-process group barrier
     bool psi_real = false;                  // buffer 0 is known to be purely real (imaginary parts exactly 0.0)
     PlanCache* plan_cache = nullptr;        // see rotations_impl
-    double2* gstage = nullptr;              // staging buffer of gather-form peer passes
-    size_t gstage_cap = 0;                  // in amplitudes
+    double2* gstage[2] = {nullptr, nullptr};  // staging buffers of gather-form peer passes (two: chunk k + 1 is fetched under chunk k)
+    size_t gstage_cap[2] = {0, 0};            // in amplitudes
     cudaStream_t stream = nullptr;
     double2* buf[4] = {nullptr, nullptr, nullptr, nullptr};  // psi, sigma, work + aux (local only: never a peer-pass operand)
     // staging
@@ -2524,7 +2549,8 @@ static void free_ctx(vqe_ctx* c) {
     if (c->d_peer_flags) cudaFree(c->d_peer_flags);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->plan_cache) free_plan_cache(c->plan_cache);
-    if (c->gstage) cudaFree(c->gstage);
+    for (int sb = 0; sb < 2; ++sb)
+        if (c->gstage[sb]) cudaFree(c->gstage[sb]);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->d_partial) cudaFree(c->d_partial);
@@ -3609,6 +3635,15 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
 }
 
 // upload + launch a planned op list on buffer 0 of every rank in the set
+// CTAs of a gather-form pass launch that fetch the NEXT chunk's partner amplitudes (the launch keeps its persistent grid:
+// they are carved out of it and grown back when the grid would otherwise be too small to hold them)
+static uint32_t gather_ctas(const vqe_ctx* c, bool wanted, int& grid) {
+    if (!wanted) return 0;
+    const int want = std::max(1, env_int("VQE_GATHER_CTAS", c->sm_count));
+    const int n = std::min(want, std::max(1, grid / 2));
+    if (grid - n < 1) grid = n + 1;
+    return (uint32_t)n;
+}
 static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
     int rc = VQE_OK;
     for (vqe_ctx* c : rs.r) {
@@ -3673,8 +3708,11 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
             for (vqe_ctx* c : rs.r) c->psi_real = real;
     }
     // one launch of the pass kernel on one rank (gg.n_need != 0: gather form over the tiles of the current chunk)
-    auto launch_pass = [&](vqe_ctx* c, size_t p, const TileGeom& g, const Shards& sh, const GatherGeom& gg) -> int {
+    auto launch_pass = [&](vqe_ctx* c, size_t p, const TileGeom& g, const Shards& sh, const GatherGeom& gg,
+                           const GatherGeom* gnext = nullptr, uint64_t next_first = 0, uint64_t next_tiles = 0,
+                           double2* next_stage = nullptr) -> int {
         const OpPass& ps = passes[p];
+        const GatherGeom gn = gnext ? *gnext : GatherGeom{nullptr, nullptr, 0u, 0u};
         size_t smem = tile_smem(ps.tp.tbits, 1, false) +
                       (ps.fast ? (ps.op_end - ps.op_begin) * sizeof(RotOp) + (ps.sup_end - ps.sup_begin) * sizeof(DevSuper) +
                                      (ps.sub_end - ps.sub_begin) * sizeof(DevSub) + (ps.col_end - ps.col_begin) * (sizeof(DevCol) + 4) +
@@ -3719,19 +3757,29 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                 k_tile_col<false><<<grid, thr, smem_c, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                    (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
         } else if (ps.fast && real_pass[p])
-            k_tile_rot<true><<<tile_grid(c, g.n_tiles, (smem <= 74 * 1024 && env_int("VQE_REAL_CTAS", 3) == 3) ? 3 : 0), threads, smem, c->stream>>>(
+        {
+            int grid_r = tile_grid(c, g.n_tiles, (smem <= 74 * 1024 && env_int("VQE_REAL_CTAS", 3) == 3) ? 3 : 0);
+            const uint32_t n_gctas = gather_ctas(c, gnext != nullptr, grid_r);
+            k_tile_rot<true><<<grid_r, threads, smem, c->stream>>>(
                 sh, g, gg, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
                 (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
                 (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
                 (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
-                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale, c->d_err);
+                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale, c->d_err,
+                gn, next_first, next_tiles, next_stage, n_gctas);
+        }
         else if (ps.fast)
-            k_tile_rot<false><<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
+        {
+            int grid_r = tile_grid(c, g.n_tiles);
+            const uint32_t n_gctas = gather_ctas(c, gnext != nullptr, grid_r);
+            k_tile_rot<false><<<grid_r, threads, smem, c->stream>>>(
                 sh, g, gg, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
                 (const DevSuper*)(c->d_stage + off_runs) + ps.sup_begin, (int)(ps.sup_end - ps.sup_begin),
                 (const DevSub*)(c->d_stage + off_subs) + ps.sub_begin, (int)(ps.sub_end - ps.sub_begin),
                 (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, (int)(ps.col_end - ps.col_begin),
-                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale, c->d_err);
+                (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)(ps.ent_end - ps.ent_begin), ps.pass_scale, c->d_err,
+                gn, next_first, next_tiles, next_stage, n_gctas);
+        }
         else
             k_tile_ops<<<tile_grid(c, g.n_tiles), threads, smem, c->stream>>>(
                 sh, g, (const DevOp*)(c->d_stage + off_ops) + ps.op_begin, (int)(ps.op_end - ps.op_begin),
@@ -3753,56 +3801,95 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
             // chunk, own half written back locally]; nothing is written remotely, so no barrier is needed afterwards
             const size_t n_need_max = std::max(ps.need_lo.size(), ps.need_hi.size());
             const uint64_t per_tile = (uint64_t)n_need_max * 4;                      // amplitudes per tile
+            // two staging buffers (chunk k is consumed while chunk k + 1 is fetched), together at most 1/8 of the shard
             const uint64_t cap_amp = std::max<uint64_t>(per_tile, std::min<uint64_t>(
-                (uint64_t)env_int("VQE_GATHER_STAGE_MB", 16384) * (1ull << 20) / sizeof(double2), (rs.r[0]->n_amp / 8) + per_tile));
+                (uint64_t)env_int("VQE_GATHER_STAGE_MB", 8192) * (1ull << 20) / sizeof(double2), (rs.r[0]->n_amp / 16) + per_tile));
             const uint64_t chunk_tiles = std::max<uint64_t>(1, std::min<uint64_t>(ps.tp.n_tiles, cap_amp / per_tile));
+            const bool overlap = env_int("VQE_GATHER_OVERLAP", 1) != 0 && chunk_tiles < ps.tp.n_tiles;
             for (vqe_ctx* c : rs.r) {
                 CK(cudaSetDevice(c->device));
-                if (c->gstage_cap < chunk_tiles * per_tile) {
-                    if (c->gstage) cudaFree(c->gstage);
-                    c->gstage = nullptr;
-                    c->gstage_cap = 0;
-                    cudaError_t e = cudaMalloc((void**)&c->gstage, chunk_tiles * per_tile * sizeof(double2));
+                for (int sb = 0; sb < (overlap ? 2 : 1); ++sb) {
+                    if (c->gstage_cap[sb] >= chunk_tiles * per_tile) continue;
+                    if (c->gstage[sb]) cudaFree(c->gstage[sb]);
+                    c->gstage[sb] = nullptr;
+                    c->gstage_cap[sb] = 0;
+                    cudaError_t e = cudaMalloc((void**)&c->gstage[sb], chunk_tiles * per_tile * sizeof(double2));
                     if (e != cudaSuccess)
                         return fail(VQE_ERR_NOMEM, "staging buffer of a gather-form peer pass (%.1f GB) failed: %s; set VQE_PEER_GATHER=0",
                                     chunk_tiles * per_tile * 16.0 / 1e9, cudaGetErrorString(e));
-                    c->gstage_cap = chunk_tiles * per_tile;
+                    c->gstage_cap[sb] = chunk_tiles * per_tile;
                 }
             }
-            for (uint64_t t0 = 0; t0 < ps.tp.n_tiles; t0 += chunk_tiles) {
+            // launch geometry of chunk ci on rank k (its staged amplitudes live in buffer ci & 1 when chunks overlap)
+            struct ChunkGeom {
+                TileGeom g;
+                Shards sh;
+                GatherGeom gg;
+                uint64_t bytes;
+            };
+            auto chunk_geom = [&](size_t k, uint64_t ci, ChunkGeom& cg) -> int {
+                vqe_ctx* c = rs.r[k];
+                const uint64_t t0 = ci * chunk_tiles;
                 const uint64_t nt = std::min<uint64_t>(chunk_tiles, ps.tp.n_tiles - t0);
-                std::vector<TileGeom> gs(rs.r.size());
-                std::vector<Shards> shs(rs.r.size());
-                std::vector<GatherGeom> ggs(rs.r.size());
+                int rc2 = make_geom(c, ps.tp, (const uint64_t*)(c->d_stage + scat_off[p]), buf, cg.g, cg.sh);
+                if (rc2) return rc2;
+                cg.g.n_tiles = nt;      // every rank walks ALL its tiles, chunk by chunk
+                cg.g.tile_first = t0;
+                cg.g.tile_stride = 1;
+                const int partner = c->rank ^ (int)ps.tp.gpat;
+                const bool is_hi = c->rank > partner;
+                const std::vector<uint16_t>& need = is_hi ? ps.need_hi : ps.need_lo;
+                cg.gg.stage = c->gstage[overlap ? (ci & 1) : 0];
+                cg.gg.need = (const uint16_t*)(c->d_stage + need_off[p]) + (is_hi ? ps.need_lo.size() : 0);
+                cg.gg.n_need = (uint32_t)need.size();
+                cg.gg.own_half = is_hi ? 1u : 0u;
+                cg.bytes = (uint64_t)need.size() * 4 * nt * sizeof(double2);
+                return VQE_OK;
+            };
+            auto gather_alone = [&](uint64_t ci) -> int {
                 for (size_t k = 0; k < rs.r.size(); ++k) {
                     vqe_ctx* c = rs.r[k];
                     CK(cudaSetDevice(c->device));
-                    rc = make_geom(c, ps.tp, (const uint64_t*)(c->d_stage + scat_off[p]), buf, gs[k], shs[k]);
-                    if (rc) return rc;
-                    gs[k].n_tiles = nt;      // every rank walks ALL its tiles, chunk by chunk
-                    gs[k].tile_first = t0;
-                    gs[k].tile_stride = 1;
-                    const int partner = c->rank ^ (int)ps.tp.gpat;
-                    const bool is_hi = c->rank > partner;
-                    const std::vector<uint16_t>& need = is_hi ? ps.need_hi : ps.need_lo;
-                    ggs[k].stage = c->gstage;
-                    ggs[k].need = (const uint16_t*)(c->d_stage + need_off[p]) + (is_hi ? ps.need_lo.size() : 0);
-                    ggs[k].n_need = (uint32_t)need.size();
-                    ggs[k].own_half = is_hi ? 1u : 0u;
-                    const uint64_t total_amp = (uint64_t)need.size() * 4 * nt;
-                    const int blocks = (int)std::min<uint64_t>((total_amp + 255) / 256, (uint64_t)c->sm_count * 16);
+                    ChunkGeom cg;
+                    int rc2 = chunk_geom(k, ci, cg);
+                    if (rc2) return rc2;
+                    const int blocks = (int)std::min<uint64_t>((cg.g.n_tiles + 7) / 8, (uint64_t)c->sm_count * 8);
                     ProfScope prof(c, 4);
-                    c->gather_bytes += total_amp * sizeof(double2);
-                    k_gather_need<<<std::max(1, blocks), 256, 0, c->stream>>>(shs[k], gs[k], ggs[k], c->gstage);
+                    c->gather_bytes += cg.bytes;
+                    k_gather_need<<<std::max(1, blocks), 256, 0, c->stream>>>(cg.sh, cg.g, cg.gg, const_cast<double2*>(cg.gg.stage));
                     c->launches++;
                     CK(cudaGetLastError());
                 }
-                rc = rank_barrier(rs);  // every rank has read what it needs before anyone overwrites its tiles
-                if (rc) return rc;
+                return VQE_OK;
+            };
+            const uint64_t n_chunks = (ps.tp.n_tiles + chunk_tiles - 1) / chunk_tiles;
+            for (uint64_t ci = 0; ci < n_chunks; ++ci) {
+                if (ci == 0 || !overlap) {
+                    rc = gather_alone(ci);
+                    if (rc) return rc;
+                    rc = rank_barrier(rs);  // every rank has read what it needs before anyone overwrites its tiles
+                    if (rc) return rc;
+                }
+                const bool prefetch = overlap && ci + 1 < n_chunks;
                 for (size_t k = 0; k < rs.r.size(); ++k) {
                     vqe_ctx* c = rs.r[k];
                     CK(cudaSetDevice(c->device));
-                    rc = launch_pass(c, p, gs[k], shs[k], ggs[k]);
+                    ChunkGeom cg, nx;
+                    rc = chunk_geom(k, ci, cg);
+                    if (rc) return rc;
+                    if (prefetch) {
+                        rc = chunk_geom(k, ci + 1, nx);
+                        if (rc) return rc;
+                        c->gather_bytes += nx.bytes;
+                        rc = launch_pass(c, p, cg.g, cg.sh, cg.gg, &nx.gg, nx.g.tile_first, nx.g.n_tiles, const_cast<double2*>(nx.gg.stage));
+                    } else {
+                        rc = launch_pass(c, p, cg.g, cg.sh, cg.gg);
+                    }
+                    if (rc) return rc;
+                }
+                if (prefetch) {
+                    // the partners' gather CTAs have read chunk ci + 1 of my shard before my next launch overwrites it
+                    rc = rank_barrier(rs);
                     if (rc) return rc;
                 }
             }
@@ -4485,36 +4572,110 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             lean_ok[g] = lean_eligible(xs[g], grp[g], nl, tb_local) ? 1 : 0;
             n_lean += lean_ok[g];
         }
-        while (n_lean) {
+        // (A) tile-bit sets of the passes, greedily for coverage (as the general passes below)
+        struct LeanPlan {
+            TilePlan tp;
+            bool swz;
+        };
+        std::vector<LeanPlan> lplans;
+        std::vector<char> covered(xs.size(), 0);
+        for (;;) {
             size_t seed = xs.size();
             for (size_t g = 0; g < xs.size(); ++g)
-                if (!done[g] && lean_ok[g]) { seed = g; break; }
+                if (!done[g] && lean_ok[g] && !covered[g]) { seed = g; break; }
             if (seed == xs.size()) break;
             uint64_t need = xs[seed] & lfull;
             const int lb_pass = fit_low_bits(need, lb, tbits_max, nl, false);
-            if (lb_pass < 0) { lean_ok[seed] = 0; --n_lean; continue; }
+            if (lb_pass < 0) { lean_ok[seed] = 0; continue; }
             std::vector<size_t> open;
             for (size_t g = 0; g < xs.size(); ++g)
-                if (!done[g] && lean_ok[g]) open.push_back(g);
+                if (!done[g] && lean_ok[g] && !covered[g]) open.push_back(g);
             need = cover_greedy(xs, open, need, (1ull << lb_pass) - 1ull, tb_local, nl, lfull);
-            PSPass p;
-            p.lean = true;
-            p.tp = make_plan(nl, need, tbits_max, lb_pass, 0);
-            p.swz = env_int("VQE_SWIZZLE", 1) != 0 && (host_only ? plan_tma(p.tp, true).ok : tma_available(p.tp, true));
-            size_t taken = 0;
+            LeanPlan lp;
+            lp.tp = make_plan(nl, need, tbits_max, lb_pass, 0);
+            lp.swz = env_int("VQE_SWIZZLE", 1) != 0 && (host_only ? plan_tma(lp.tp, true).ok : tma_available(lp.tp, true));
+            // a group that cannot be lowered even into an empty pass takes the general path
+            size_t n_cov = 0;
             for (size_t g : open) {
-                if ((xs[g] & lfull & ~p.tp.tile_mask) != 0) continue;
-                if (!lower_lean_group(p, xs[g], grp[g])) {
-                    if (p.flats2.empty() && g == seed) { lean_ok[g] = 0; --n_lean; }  // cannot be lowered at all: fat path
-                    continue;
-                }
-                done[g] = 1;
-                ++taken;
-                --n_lean;
+                if ((xs[g] & lfull & ~lp.tp.tile_mask) != 0) continue;
+                PSPass scratch;
+                scratch.lean = true;
+                scratch.tp = lp.tp;
+                scratch.swz = lp.swz;
+                if (!lower_lean_group(scratch, xs[g], grp[g])) { lean_ok[g] = 0; continue; }
+                covered[g] = 1;
+                ++n_cov;
             }
-            remaining -= taken;
-            if (taken) ps->passes.push_back(std::move(p));
+            if (n_cov) lplans.push_back(lp);
         }
+        // (B) every group goes to ONE of the passes whose tile bits cover it.  A pass costs max(HBM sweep, its entries), so
+        // the groups are spread for equal entry counts (most constrained groups first, each to its least loaded candidate)
+        // instead of piling up in the first pass that covers them: the heavy passes were 5-10 x the sweep time, the light
+        // ones idle at the HBM floor.  VQE_EXP_BALANCE=0 restores first-fit.
+        const bool balance = env_int("VQE_EXP_BALANCE", 1) != 0;
+        std::vector<std::vector<size_t>> members(lplans.size());
+        {
+            struct Cand {
+                size_t g;
+                std::vector<int> passes;
+                double cost;
+            };
+            std::vector<Cand> cands;
+            for (size_t g = 0; g < xs.size(); ++g) {
+                if (done[g] || !lean_ok[g] || !covered[g]) continue;
+                Cand c;
+                c.g = g;
+                for (size_t i = 0; i < lplans.size(); ++i)
+                    if ((xs[g] & lfull & ~lplans[i].tp.tile_mask) == 0) c.passes.push_back((int)i);
+                // entries = active occupation patterns x 256-pair chunks; estimated from the pattern count bound
+                PSPass scratch;
+                scratch.lean = true;
+                scratch.tp = lplans[c.passes[0]].tp;
+                scratch.swz = lplans[c.passes[0]].swz;
+                lower_lean_group(scratch, xs[g], grp[g]);
+                double cost = 0.0;
+                for (const DevFlat2& fl : scratch.flats2) cost += fl.tab == 0xffffu ? 1.0 : 1.5;  // additive entries read two tables
+                c.cost = cost;
+                cands.push_back(std::move(c));
+            }
+            std::vector<double> load(lplans.size(), 0.0);
+            if (balance)
+                std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) {
+                    if (a.passes.size() != b.passes.size()) return a.passes.size() < b.passes.size();
+                    return a.cost > b.cost;
+                });
+            for (const Cand& c : cands) {
+                int best = c.passes[0];
+                if (balance)
+                    for (int i : c.passes)
+                        if (load[i] < load[best]) best = i;
+                load[best] += c.cost;
+                members[best].push_back(c.g);
+            }
+        }
+        // (C) lower the groups of every pass (ascending group order: deterministic tables); a group that exceeds a pass's
+        // table capacities moves on to its next candidate, and to the general path when none takes it
+        std::vector<PSPass> lpass(lplans.size());
+        for (size_t i = 0; i < lplans.size(); ++i) {
+            lpass[i].lean = true;
+            lpass[i].tp = lplans[i].tp;
+            lpass[i].swz = lplans[i].swz;
+            std::sort(members[i].begin(), members[i].end());
+        }
+        std::vector<size_t> spill;
+        for (size_t i = 0; i < lplans.size(); ++i)
+            for (size_t g : members[i]) {
+                if (lower_lean_group(lpass[i], xs[g], grp[g])) done[g] = 1;
+                else spill.push_back(g);
+            }
+        for (size_t g : spill)
+            for (size_t i = 0; i < lplans.size() && !done[g]; ++i)
+                if ((xs[g] & lfull & ~lplans[i].tp.tile_mask) == 0 && lower_lean_group(lpass[i], xs[g], grp[g])) done[g] = 1;
+        for (size_t i = 0; i < lplans.size(); ++i)
+            if (!lpass[i].flats2.empty()) ps->passes.push_back(std::move(lpass[i]));
+        remaining = 0;
+        for (size_t g = 0; g < xs.size(); ++g) remaining += done[g] ? 0 : 1;
+        (void)n_lean;
     }
     while (remaining) {
         // Choose the tile bits of this pass greedily for COVERAGE (the Pauli sum is uploaded once and evaluated

@@ -32,7 +32,7 @@ def wl(gpu_required):
     from oracle import c_oracle
     from openvqe_b200.engine import Engine
     from openvqe_b200.lowering import PackedTerms
-    w = bench.load_workload()
+    w = bench.load_workload("h12")
     n = w["n"]
     rot, ham = bench.packed_from(w, "rot"), bench.packed_from(w, "ham")
     eng = Engine(n)
@@ -151,3 +151,57 @@ def test_quccsd_excitations_match_gate_by_gate_oracle(wl):
     e_ref = orc.expectation(psi, n, ham.x, ham.z, ham.ny, ham.cre, ham.cim)
     assert np.max(np.abs(got - psi)) < TOL_AMP
     assert abs(e_gpu.real - e_ref) < TOL_E, (e_gpu, e_ref)
+
+
+def test_c4_h2o_631g_active_space_matches_the_c_oracle(gpu_required):
+    """BASELINE config C4 on the molecule it names: H2O / 6-31G, O 1s frozen, (8e,12o) -> 24 qubits
+    (tests/golden/h2o_631g_24q.npz, oracle/make_golden_r3.py).  The full UCCSD program (11 008 rotations, 1 424 generators)
+    + <H> over all 8 921 terms against oracle/c, energy and state; then the gate-defined QUCCSD ansatz (reference
+    get_energy_qucc.py:11-56) through the drop-in API on its first excitations against the oracle's gate-by-gate run."""
+    import bench
+    from oracle import c_oracle
+    from oracle import statevector_oracle as orc_np
+    from openvqe_b200.engine import GATE_KINDS, get_engine
+    from openvqe_b200.lowering import PackedTerms
+    from openvqe_b200.ucc_family.get_energy_qucc import EnergyUCC
+    from tests.helpers import FermiOp
+    w = bench.load_workload("h2o")
+    n = w["n"]
+    rot, ham = bench.packed_from(w, "rot"), bench.packed_from(w, "ham")
+    assert (n, len(rot.x), len(ham.x), int(w["rot_owner"].max()) + 1) == (24, 11008, 8921, 1424)
+    c_oracle.load()
+    eng = get_engine(n)
+    hamp = PackedTerms(n, ham.x, ham.z, ham.ny, ham.cre, ham.cim)
+    ps = eng.paulisum(hamp)
+    theta = bench.thetas_for(w, 1, 0)[0]
+    angles = theta[w["rot_owner"]] * np.asarray(w["rot_c"], dtype=np.float64)
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[w["hf_init_sp"]] = 1.0
+    c_oracle.apply_rotations(psi, n, rot.x, rot.z, rot.ny, angles)
+    e_ref = c_oracle.expectation(psi, n, ham.x, ham.z, ham.ny, ham.cre, ham.cim)
+    eng.set_basis_state(w["hf_init_sp"])
+    e_hf = eng.expectation(ps).real
+    assert abs(e_hf - w["meta"]["hf_energy"]) < 1e-9          # <HF|H|HF> of the Pauli list = the SCF energy of the fixture tooling
+    eng.apply_rotations(rot.x, rot.z, rot.ny, angles)
+    e_gpu = eng.expectation(ps)
+    got = eng.get_state()
+    assert np.max(np.abs(got - psi)) < TOL_AMP
+    assert abs(e_gpu.real - e_ref) < TOL_E and abs(e_gpu.imag) < TOL_E, (e_gpu, e_ref)
+    assert e_ref < e_hf - 0.05                                  # MP2-size correlation energy recovered
+    assert np.count_nonzero(got[np.abs(psi) == 0.0]) == 0
+    # QUCCSD templates through the reference-shaped API: first 40 singles + 40 doubles of the excitation list
+    lens = w["exci_len"].astype(int)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    picks = list(range(0, 40)) + list(range(64, 104))
+    ops = [FermiOp(n, [int(q) for q in w["exci"][offs[k]:offs[k + 1]]]) for k in picks]
+    th = np.random.default_rng(8).uniform(-0.3, 0.3, size=len(ops)).tolist()
+
+    hobj, _ = bench.build_host_objects(w)   # duck-typed SpinHamiltonian (nbqbits / terms / constant_coeff), as the reference passes
+    e_api = EnergyUCC().action_quccsd(th, hobj, ops, w["hf_init_sp"], [])
+    gates = orc_np.quccsd_gates(n, w["hf_init_sp"], [list(op.terms[0].qbits) for op in ops], th)
+    psi2 = np.zeros(1 << n, dtype=np.complex128)
+    psi2[0] = 1.0
+    c_oracle.apply_gates(psi2, n, [GATE_KINDS[g[0]] for g in gates], [g[1][0] for g in gates],
+                         [g[1][1] if len(g[1]) > 1 else 0 for g in gates], [0.0 if g[2] is None else g[2] for g in gates])
+    e_ref2 = c_oracle.expectation(psi2, n, ham.x, ham.z, ham.ny, ham.cre, ham.cim)
+    assert abs(e_api - e_ref2) < TOL_E, (e_api, e_ref2)

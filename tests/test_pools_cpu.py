@@ -82,3 +82,35 @@ def test_normal_ordering_rules():
     assert pools.order_fermionic_term(1.0, "CcCc", [2, 1, 1, 3]) == [(1.0, "Cc", [2, 3]), (1.0, "CCcc", [1, 2, 1, 3])]
     # already ordered terms pass through; annihilators are sorted with the sign of the permutation
     assert pools.order_fermionic_term(0.5, "CCcc", [0, 1, 3, 2]) == [(-0.5, "CCcc", [0, 1, 2, 3])]
+
+
+def test_snap_ties_documented_deviation():
+    """The one place where the drop-in's selection can differ from the reference's float-equality semantics
+    (DESIGN.md section 4 item 1), pinned: what snap_ties does to exact zeros, to reduction noise, to true ties and -- the
+    deviation -- to two DISTINCT gradients closer than 1e-12 relative."""
+    from openvqe_b200._hotpath import snap_ties
+    from openvqe_b200.common_files.sorted_gradient import abs_sort_desc, corresponding_index, index_without_0, value_without_0
+
+    def selection(grads):   # the order in which the ADAPT loops pick operators (fermionic_adapt_vqe.py:165-180)
+        mags = [abs(v) for v in grads]
+        vals, idx = value_without_0(mags), index_without_0(mags)
+        return corresponding_index(vals, idx, abs_sort_desc(list(vals)))
+    # reduction noise below 1e-14 Ha becomes the exact zero the reference's scipy path produces
+    assert snap_ties([0.3, 3e-17, -0.1, 0.0]) == [0.3, 0.0, -0.1, 0.0]
+    # spin-complement partners (+g, -g) that differ in the last bit: magnitudes equalised to the lowest index, signs kept
+    g = 0.27328246013490346
+    out = snap_ties([g, 0.5, -g * (1 + 2e-16)])
+    assert out[0] == g and out[2] == -g and out[1] == 0.5
+    # ... so the reference's helpers resolve the tie to the lowest pool index, as with scipy's exact ties
+    assert selection(out) == [1, 0, 2]
+    # well-separated gradients (1e-9 relative) are left alone, order preserved
+    sep = [0.2, 0.2 * (1 + 1e-9), 0.1]
+    assert snap_ties(sep) == sep
+    # DEVIATION: two genuinely different gradients 5e-13 apart (relative) are merged; the reference would have picked index 1
+    # (the strictly larger one), the drop-in reports a tie and picks index 0.  Physical gradients of distinct operators this
+    # close do not occur in the fixtures: in the reference's own sweep over the 3 159-operator H6 pool the closest genuinely distinct
+    # magnitudes are 9.5e-5 apart (relative), while exact ties show up split in the last bit (2e-16) -- the case the snap is for.
+    near = [0.2, 0.2 * (1 + 5e-13), 0.1]
+    merged = snap_ties(near)
+    assert merged[0] == merged[1] == 0.2
+    assert selection(near)[0] == 1 and selection(merged)[0] == 0

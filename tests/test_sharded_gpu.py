@@ -224,6 +224,28 @@ def test_c5_synthetic_energy_vs_oracle(groups, n, g):
     assert abs(grp.norm2() - 1.0) < 1e-12
 
 
+@pytest.mark.parametrize("n,g,overlap", [(14, 2, "1"), (16, 3, "1"), (16, 3, "0"), (15, 1, "1")])
+def test_gather_form_chunks_prefetched_under_the_previous_chunk(gpu_required, monkeypatch, n, g, overlap):
+    """Gather-form peer passes cut into many chunks (staging buffer forced down to one tile): the partner amplitudes of
+    chunk k + 1 are fetched by the gather CTAs riding in the pass kernel of chunk k (VQE_GATHER_OVERLAP=1, two staging
+    buffers) or by a separate launch per chunk (=0); both must equal the oracle."""
+    from openvqe_b200.sharded import ShardGroup
+    from tools import c5_synthetic as c5
+    monkeypatch.setenv("VQE_GATHER_STAGE_MB", "0")
+    monkeypatch.setenv("VQE_GATHER_OVERLAP", overlap)
+    gen = c5.generators(n, k_gen=96)
+    ang = gen["theta"][gen["owner"]] * gen["coeff"]
+    hf = c5.hf_index(n)
+    grp = ShardGroup(n, g)
+    grp.set_basis_state(hf)
+    grp.apply_rotations(gen["x"], gen["z"], gen["ny"], ang)
+    ref = orc.basis_state(n, hf)
+    for x, z, ny, a in zip(gen["x"], gen["z"], gen["ny"], ang):
+        ref = orc.pauli_rotation(ref, int(x), int(z), int(ny), float(a))
+    assert np.max(np.abs(grp.get_state() - ref)) < TOL
+    assert sum(e.gather_bytes() for e in grp.ranks) > 0     # the program did take gather-form passes
+
+
 def test_c5_synthetic_sharded_equals_unsharded_at_22_qubits(gpu_required):
     """Size-independent property at a size the oracle cannot do: 8 virtual ranks vs one context, same energy."""
     from openvqe_b200.engine import Engine

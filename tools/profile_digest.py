@@ -5,6 +5,8 @@
                                                          plus the copy-engine / mbarrier lines of the hot kernels
   tools/profile_digest.py ncu   REPORT.ncu-rep OUT.json  key metrics of every launch in an `ncu --set full` report
   tools/profile_digest.py hot   REPORT.ncu-rep OUT.txt   hottest SASS lines by stall samples (source page)
+  tools/profile_digest.py traffic LAUNCHES.csv OUT.json  per-kernel averages of an ncu launch list (time, DRAM bytes, share);
+                                                         bench.py reads OUT.json for `roofline.traffic`
 """
 import csv
 import io
@@ -88,5 +90,31 @@ def hot(rep, out, top=45):
     open(out, "w").write("\n".join(lines) + "\n")
 
 
+def traffic(launches_csv, out):
+    import gzip
+    op = gzip.open if launches_csv.endswith(".gz") else open
+    with op(launches_csv, "rt") as f:
+        lines = [ln for ln in f if ln.startswith('"')]
+    rows = list(csv.DictReader(io.StringIO("".join(lines))))
+    per = {}
+    for r in rows:
+        d = per.setdefault(r["ID"], {"name": re.sub(r"^void ", "", r["Kernel Name"]).split("<")[0].split("(")[0]})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * ({"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r["Metric Unit"], 1.0)
+                                                                         if r["Metric Name"].startswith("gpu__time") else 1.0)
+    agg = {}
+    for d in per.values():
+        agg.setdefault(d["name"], []).append(d)
+    total = sum(d.get("gpu__time_duration.sum", 0.0) for d in per.values())
+    res = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over "
+                     "`python bench.py --steps 1 --warmup 1 --no-cpu --no-pool` (%s), averages per launch" % launches_csv}
+    for name, ds in agg.items():
+        t = [d.get("gpu__time_duration.sum", 0.0) for d in ds]
+        res[name] = {"launches": len(ds), "avg_us": sum(t) / len(t), "min_us": min(t), "max_us": max(t),
+                     "dram_read_bytes": sum(d.get("dram__bytes_read.sum", 0.0) for d in ds) / len(ds),
+                     "dram_write_bytes": sum(d.get("dram__bytes_write.sum", 0.0) for d in ds) / len(ds),
+                     "share": sum(t) / max(total, 1e-12)}
+    json.dump(res, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"sass": sass, "ncu": ncu, "hot": hot}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"sass": sass, "ncu": ncu, "hot": hot, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
