@@ -228,6 +228,9 @@ int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int tile_bits, int
  * tile.  Returns the number of mismatching elements (0 = consistent), -1 when the plan keeps per-segment copies. */
 int vqe_debug_tma_check(int n_local, uint64_t need_mask, int tile_bits, int low_bits, int max_tiles, int32_t* n_req,
                         int32_t* dims_used);
+/* the same for the real layout of the state buffer (one double per amplitude, tile elements of 8 bytes) */
+int vqe_debug_tma_check_rl(int n_local, uint64_t need_mask, int tile_bits, int low_bits, int max_tiles, int32_t* n_req,
+                           int32_t* dims_used);
 
 /* Raw device pointer / stream of a buffer. */
 int vqe_buffer_ptr(vqe_ctx* ctx, int buf, void** dev_ptr, uint64_t* n_amplitudes);

@@ -117,12 +117,16 @@ struct TileGeom {
                            // an element, byte-offset bits 4-6, is XORed with bits 7-9): whatever tile bits an operation
                            // fixes, a warp's 32 elements then spread over all eight chunk positions (no bank conflicts
                            // beyond the 16-byte stride itself).  0: natural layout.
+    uint32_t rl;           // 1: REAL LAYOUT -- the buffer holds the n_amp real parts as contiguous doubles (see vqe_ctx::real_layout);
+                           // tile elements are 8 bytes, the tensor map counts one double per amplitude
     TmaGeom tg;
 };
 // byte offset of a tile element in the (possibly swizzled) shared-memory tile; linear over XOR
 __host__ __device__ __forceinline__ uint32_t swz_off(uint32_t off, uint32_t swz) { return off ^ ((off >> 3) & swz); }
 // the same on element indices
 __host__ __device__ __forceinline__ uint32_t swz_idx(uint32_t l, uint32_t swz) { return l ^ ((l >> 3) & (swz >> 4)); }
+// ... and on indices of 8-byte elements (real layout): byte-offset bits 4-6 are element-index bits 1-3, bits 7-9 are bits 4-6
+__host__ __device__ __forceinline__ uint32_t swz_idx8(uint32_t l, uint32_t swz) { return l ^ ((l >> 3) & (swz >> 3)); }
 
 // Peer pass, "gather" form.  When the operations of a peer pass couple only a fraction of the partner's amplitudes
 // (collapsed runs: 1/8 of them for a JW double excitation), moving whole half-tiles over NVLink is wasteful.
@@ -190,6 +194,22 @@ __global__ void k_zero_set(double2* psi, uint64_t n_amp, uint64_t index) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; i < n_amp; i += stride) psi[i] = make_double2(i == index ? 1.0 : 0.0, 0.0);
+}
+
+__global__ void k_zero_set_real(double* psi, uint64_t n_amp, uint64_t index) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n_amp; i += stride) psi[i] = i == index ? 1.0 : 0.0;
+}
+// real layout -> interleaved complex, in place, one level: the reals [lo, hi) (hi <= 2 lo, or lo = 0 and hi = 1) become the
+// complex amplitudes [lo, hi), i.e. the doubles [2 lo, 2 hi), which do not overlap the reals still to be expanded
+__global__ void k_expand_level(double* buf, uint64_t lo, uint64_t hi) {
+    uint64_t i = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < hi; i += stride) {
+        const double v = buf[i];
+        reinterpret_cast<double2*>(buf)[i] = make_double2(v, 0.0);
+    }
 }
 
 // dst = alpha * x + beta * dst   (complex alpha, beta given as re/im)
@@ -653,28 +673,32 @@ __device__ __forceinline__ void tile_store_bulk(const double2* tile, const Shard
 __device__ __forceinline__ void tma_coords(const TmaGeom& tg, uint64_t idx, int (&c)[5]) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) c[i] = (int)((uint32_t)(idx >> tg.shift[i]) & tg.cmask[i]);
-    c[0] <<= 1;  // dimension 0 counts doubles (re, im)
 }
 __device__ __forceinline__ void tma_load_tile(double2* tile, const CUtensorMap* tm, const TileGeom& g, uint64_t base, uint64_t* bar) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to the slot come first
-    mbar_arrive_expect_tx(bar, 16u << g.tbits);
+    const uint32_t esz = g.rl ? 8u : 16u;
+    mbar_arrive_expect_tx(bar, esz << g.tbits);
     for (uint32_t r = 0; r < g.tg.n_req; ++r) {
         int c[5];
         tma_coords(g.tg, base | g.tg.req_bits[r], c);
+        if (!g.rl) c[0] <<= 1;  // dimension 0 counts doubles: (re, im) per amplitude, one per amplitude in the real layout
         asm volatile(
             "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
-                smem_u32(tile + (size_t)r * g.tg.req_amps)),
+                smem_u32(reinterpret_cast<char*>(tile) + (size_t)r * g.tg.req_amps * esz)),
             "l"(tm), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(smem_u32(bar))
             : "memory");
     }
 }
 // the caller has made the tile's generic writes visible to the async proxy (fence.proxy.async by the writers + barrier)
 __device__ __forceinline__ void tma_store_tile(const double2* tile, const CUtensorMap* tm, const TileGeom& g, uint64_t base) {
+    const uint32_t esz = g.rl ? 8u : 16u;
     for (uint32_t r = 0; r < g.tg.n_req; ++r) {
         int c[5];
         tma_coords(g.tg, base | g.tg.req_bits[r], c);
+        if (!g.rl) c[0] <<= 1;
         asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tm), "r"(c[0]),
-                     "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(smem_u32(tile + (size_t)r * g.tg.req_amps))
+                     "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]),
+                     "r"(smem_u32(reinterpret_cast<const char*>(tile) + (size_t)r * g.tg.req_amps * esz))
                      : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -1069,14 +1093,14 @@ struct ColItem {
     uint32_t items;      // items of the run (for the threads that own more than one)
 };
 __device__ __forceinline__ void col_lite_build(ColLite* lite, const DevCol* __restrict__ cols, const DevColEntry* __restrict__ ents,
-                                               int n_cols, uint32_t swz) {
+                                               int n_cols, uint32_t swz, bool rl = false) {
     for (int q = threadIdx.x; q < n_cols; q += blockDim.x) {
         const DevCol co = cols[q];
         const DevColEntry e0 = ents[co.ent_begin];
         ColLite L;
         L.c = e0.c;
         L.s = e0.s;
-        L.lxs = swz_idx(co.lx, swz);
+        L.lxs = rl ? swz_idx8(co.lx, swz) : swz_idx(co.lx, swz);
         L.lz = co.lz;
         L.pat = e0.pat;
         L.items = co.n_active << co.free_log;
@@ -1087,6 +1111,7 @@ __device__ __forceinline__ void col_lite_build(ColLite* lite, const DevCol* __re
         lite[q] = L;
     }
 }
+template <bool RL = false>
 __device__ __forceinline__ ColItem col_prep(const ColLite* lite, const DevColEntry* sent, const uint32_t* csign, int q, int n_cols,
                                             uint32_t it, uint32_t swz) {
     ColItem ci;
@@ -1114,7 +1139,7 @@ __device__ __forceinline__ ColItem col_prep(const ColLite* lite, const DevColEnt
         pat = en.pat;
     }
     l |= pat;
-    ci.ls = swz_idx(l, swz);
+    ci.ls = RL ? swz_idx8(l, swz) : swz_idx(l, swz);
     ci.lxs = L.lxs;
     ci.c = c;
     ci.sn = flipsign(sv, csign[q] + (uint32_t)__popc(l & L.lz));
@@ -1126,9 +1151,14 @@ template <bool REAL>
 struct ColPair {
     double2 a, b;
 };
-template <bool REAL>
+template <bool REAL, bool RL = false>
 __device__ __forceinline__ void col_load(const double2* tile, const ColItem& ci, ColPair<REAL>& pr) {
-    if (REAL) {
+    if (RL) {  // real layout: the tile holds doubles
+        const double* tr = reinterpret_cast<const double*>(tile);
+        pr.a.x = tr[ci.ls];
+        pr.b.x = tr[ci.ls ^ ci.lxs];
+        pr.a.y = pr.b.y = 0.0;
+    } else if (REAL) {
         pr.a.x = tile[ci.ls].x;
         pr.b.x = tile[ci.ls ^ ci.lxs].x;
         pr.a.y = pr.b.y = 0.0;
@@ -1137,10 +1167,14 @@ __device__ __forceinline__ void col_load(const double2* tile, const ColItem& ci,
         pr.b = tile[ci.ls ^ ci.lxs];
     }
 }
-template <bool REAL>
+template <bool REAL, bool RL = false>
 __device__ __forceinline__ void col_store(double2* tile, const ColItem& ci, const ColPair<REAL>& pr) {
     const double2 a = pr.a, b = pr.b;
-    if (REAL) {
+    if (RL) {
+        double* tr = reinterpret_cast<double*>(tile);
+        tr[ci.ls] = fma(ci.c, a.x, -ci.sn * b.x);
+        tr[ci.ls ^ ci.lxs] = fma(ci.c, b.x, ci.sn * a.x);
+    } else if (REAL) {
         tile[ci.ls].x = fma(ci.c, a.x, -ci.sn * b.x);
         tile[ci.ls ^ ci.lxs].x = fma(ci.c, b.x, ci.sn * a.x);
     } else {
@@ -1157,34 +1191,36 @@ __device__ __forceinline__ void col_store(double2* tile, const ColItem& ci, cons
     }
 }
 // all runs of a pass on the tile in shared memory; ends with a CTA barrier (every thread has passed `fence` before it)
-template <bool REAL>
+template <bool REAL, bool RL = false>
 __device__ __forceinline__ void col_runs(double2* tile, const ColLite* lite, const DevColEntry* sent, const uint32_t* csign, int n_cols,
                                          uint32_t swz, bool fence, ColItem cur) {
     const uint32_t bd = blockDim.x;
     for (int q = 0; q < n_cols; ++q) {
         const uint32_t items = cur.items;
         ColPair<REAL> pr;
-        if (cur.valid) col_load<REAL>(tile, cur, pr);
-        const ColItem nxt = col_prep(lite, sent, csign, q + 1, n_cols, threadIdx.x, swz);  // overlaps the loads above
-        if (cur.valid) col_store<REAL>(tile, cur, pr);
+        if (cur.valid) col_load<REAL, RL>(tile, cur, pr);
+        const ColItem nxt = col_prep<RL>(lite, sent, csign, q + 1, n_cols, threadIdx.x, swz);  // overlaps the loads above
+        if (cur.valid) col_store<REAL, RL>(tile, cur, pr);
         for (uint32_t it = threadIdx.x + bd; it < items; it += bd) {
-            const ColItem ci = col_prep(lite, sent, csign, q, n_cols, it, swz);
+            const ColItem ci = col_prep<RL>(lite, sent, csign, q, n_cols, it, swz);
             ColPair<REAL> p2;
-            col_load<REAL>(tile, ci, p2);
-            col_store<REAL>(tile, ci, p2);
+            col_load<REAL, RL>(tile, ci, p2);
+            col_store<REAL, RL>(tile, ci, p2);
         }
         cur = nxt;
         if (fence && q + 1 == n_cols) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes -> the async-proxy store
         __syncthreads();
     }
 }
-template <bool REAL>
-__global__ void __launch_bounds__(256, 3) k_tile_col(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
+// RL: the buffer is in the REAL LAYOUT (vqe_ctx::real_layout): tile elements are doubles (half the HBM traffic and half the
+// shared-memory wavefronts of the interleaved form), tensor-map staging only.
+template <bool REAL, bool RL>
+__global__ void __launch_bounds__(256, RL ? 4 : 3) k_tile_col(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
                                                      const DevCol* __restrict__ cols, int n_cols,
                                                      const DevColEntry* __restrict__ ents, int n_ents, int* __restrict__ err) {
     extern __shared__ __align__(1024) double2 tile[];
     const uint32_t ts = 1u << g.tbits;
-    ColLite* lite = (ColLite*)(tile + ts);
+    ColLite* lite = RL ? (ColLite*)(reinterpret_cast<double*>(tile) + ts) : (ColLite*)(tile + ts);
     DevColEntry* sent = (DevColEntry*)(lite + n_cols);
     uint64_t* szout = (uint64_t*)(sent + n_ents);
     uint32_t* scsign = (uint32_t*)(szout + n_cols);  // per tile: outside-tile Z parity of every run
@@ -1195,7 +1231,7 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(const __grid_constant__ CUt
     uint32_t mphase = 0;
     if (bulk && threadIdx.x == 0) mbar_init(&s_mbar, 1);
     const TileAddr ta = tile_addr_init(g, s_boff);
-    col_lite_build(lite, cols, ents, n_cols, g.swz);
+    col_lite_build(lite, cols, ents, n_cols, g.swz, RL);
     for (int q = threadIdx.x; q < n_cols; q += blockDim.x) szout[q] = cols[q].zout;
     for (int q = threadIdx.x; q < n_ents; q += blockDim.x) sent[q] = ents[q];
     const BaseLane bl = base_lane_init(g);
@@ -1210,7 +1246,7 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(const __grid_constant__ CUt
         else tile_load_async_fast(tile, psi, g, ta, s_boff, base);
         for (int r = threadIdx.x; r < n_cols; r += bd) scsign[r] = (uint32_t)__popcll(sbase & szout[r]) & 1u;
         __syncthreads();  // scsign visible
-        const ColItem first = col_prep(lite, sent, scsign, 0, n_cols, threadIdx.x, g.swz);
+        const ColItem first = col_prep<RL>(lite, sent, scsign, 0, n_cols, threadIdx.x, g.swz);
         if (bulk) {
             if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
             mphase ^= 1u;
@@ -1218,7 +1254,7 @@ __global__ void __launch_bounds__(256, 3) k_tile_col(const __grid_constant__ CUt
             cp_async_wait_all();
             __syncthreads();
         }
-        col_runs<REAL>(tile, lite, sent, scsign, n_cols, g.swz, tma, first);
+        col_runs<REAL, RL>(tile, lite, sent, scsign, n_cols, g.swz, tma, first);
         if (tma) {
             if (threadIdx.x == 0) {
                 tma_store_tile(tile, &tmap, g, base);
@@ -1886,7 +1922,10 @@ struct LeanUnit {           // decoded entry, per lane
     uint32_t o[8];
     double fr;
 };
-__host__ __device__ __forceinline__ void lean_decode(const uint4& q0, const uint4& q1, const uint4& q2, uint32_t lane, LeanUnit& u) {
+// lane_shift: log2 of the tile element size (4: interleaved complex, 3: real layout -- the entry must then be the real-layout
+// form produced by lean_entry_to_rl)
+__host__ __device__ __forceinline__ void lean_decode(const uint4& q0, const uint4& q1, const uint4& q2, uint32_t lane, LeanUnit& u,
+                                                     uint32_t lane_shift = 4) {
 #ifdef __CUDA_ARCH__
     u.fr = __hiloint2double((int)q0.y, (int)q0.x);
 #else
@@ -1895,7 +1934,7 @@ __host__ __device__ __forceinline__ void lean_decode(const uint4& q0, const uint
 #endif
     u.lx16 = q0.z & 0xffffu;
     const uint32_t lz16 = q0.z >> 16, pat16 = q0.w & 0xffffu;
-    uint32_t v = lane << 4;
+    uint32_t v = lane << lane_shift;
     v += v & (q1.x & 0xffffu);
     v += v & (q1.x >> 16);
     v += v & (q1.y & 0xffffu);
@@ -1917,6 +1956,23 @@ __host__ __device__ __forceinline__ void lean_decode(const uint4& q0, const uint
     u.o[6] = q2.w & 0xffffu; u.o[7] = q2.w >> 16;
 }
 
+// The real-layout form of an entry: every byte offset is halved (8-byte tile elements) and re-swizzled for the layout the
+// real-layout tile has in shared memory (swz_c / swz_r: the complex / real tile is 128-byte swizzled).
+static inline DevFlat2 lean_entry_to_rl(const DevFlat2& f, bool swz_c, bool swz_r) {
+    auto conv = [&](uint16_t off16) -> uint16_t {
+        const uint32_t nat = swz_c ? swz_off(off16, 0x70u) : off16;  // the swizzle is an involution
+        const uint32_t half = nat >> 1;
+        return (uint16_t)(swz_r ? swz_off(half, 0x70u) : half);
+    };
+    DevFlat2 r = f;
+    r.lx16 = conv(f.lx16);
+    r.lz16 = (uint16_t)(f.lz16 >> 1);    // natural-layout masks
+    r.pat16 = (uint16_t)(f.pat16 >> 1);
+    for (int k = 0; k < 4; ++k) r.hm16[k] = f.hm16[k] ? (uint16_t)((f.hm16[k] >> 1) | 0x8000u) : 0;
+    for (int j = 0; j < 8; ++j) r.o16[j] = conv(f.o16[j]);
+    return r;
+}
+
 // per-tile constants of the additive patterns (one thread per pattern, while the tile load is in flight)
 __device__ __forceinline__ void lean_betas(double* s_beta, const DevAddPat* __restrict__ addpat, int n_addpat,
                                            const DevAddOut* __restrict__ addout, uint64_t sbase) {
@@ -1935,7 +1991,7 @@ __device__ __forceinline__ void lean_betas(double* s_beta, const DevAddPat* __re
 // outside-tile Z mask of entry k+1 are fetched while entry k is evaluated.  Offsets are used in the tile's shared-memory
 // layout: with the 128-byte swizzle (swz = 0x70) the lane part is swizzled here, once per entry; the per-j offsets and the
 // X-mask were swizzled by the host (the map is linear over XOR).
-template <bool REAL>
+template <bool REAL, bool RL = false>
 __device__ __forceinline__ double lean_entries(const char* tb, const DevFlat2* __restrict__ flats, int e0, int e1, int stride,
                                                uint32_t lane, uint64_t sbase, const uint64_t* __restrict__ fzout,
                                                const double* __restrict__ addtab, const double* s_beta, uint32_t swz) {
@@ -1954,7 +2010,7 @@ __device__ __forceinline__ double lean_entries(const char* tb, const DevFlat2* _
             n2 = __ldg(np + 2);
         }
         LeanUnit u;
-        lean_decode(q0, q1, q2, lane, u);
+        lean_decode(q0, q1, q2, lane, u, RL ? 3u : 4u);
         const uint32_t sg = u.s0 + (uint32_t)__popcll(sbase & zo);
         const uint32_t vs = swz_off(u.v, swz);
         double part = 0.0;
@@ -1995,8 +2051,9 @@ __device__ __forceinline__ double lean_entries(const char* tb, const DevFlat2* _
     }
     return er;
 }
-template <bool REAL>
-__global__ void __launch_bounds__(256, 3) k_expect_lean(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
+// RL: real layout of the state buffer (8-byte tile elements; `flats` are then the real-layout entries, REAL is implied)
+template <bool REAL, int THREADS, bool RL = false>
+__global__ void __launch_bounds__(THREADS, 3) k_expect_lean(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
                                                         const DevFlat2* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
                                                         const DevAddPat* __restrict__ addpat, int n_addpat,
@@ -2007,7 +2064,7 @@ __global__ void __launch_bounds__(256, 3) k_expect_lean(const __grid_constant__ 
     __shared__ uint64_t s_boff[16];
     __shared__ __align__(8) uint64_t s_mbar;
     const uint32_t ts = 1u << g.tbits;
-    double* s_beta = (double*)(tile + ts);
+    double* s_beta = RL ? reinterpret_cast<double*>(tile) + ts : (double*)(tile + ts);
     const bool tma = g.tma != 0;
     const bool bulk = g.bulk != 0 || tma;
     uint32_t mphase = 0;
@@ -2036,7 +2093,7 @@ __global__ void __launch_bounds__(256, 3) k_expect_lean(const __grid_constant__ 
             cp_async_wait_all();
         }
         __syncthreads();
-        er += lean_entries<REAL>(tb, flats, f0 + (int)warp, f1, (int)nw, lane, sbase, fzout, addtab, s_beta, g.swz);
+        er += lean_entries<REAL, RL>(tb, flats, f0 + (int)warp, f1, (int)nw, lane, sbase, fzout, addtab, s_beta, g.swz);
     }
     double2 sres = block_sum2(er, 0.0, red);
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
@@ -2295,6 +2352,12 @@ struct vqe_ctx {
     int* d_err = nullptr;
     cudaEvent_t ev_bar = nullptr;           // in-process group barrier
     bool psi_real = false;                  // buffer 0 is known to be purely real (imaginary parts exactly 0.0)
+    // REAL LAYOUT of buffer 0: while the state is known to be purely real (|HF> followed by +-1-phase rotations: every UCC
+    // energy evaluation) only the real parts are kept, as n_amp contiguous doubles at the start of the buffer.  Every
+    // pass then moves half the bytes and the tiles hold 8-byte elements.  Entry points that are not layout-aware expand
+    // the buffer in place first (ensure_complex); real_layout implies psi_real.
+    bool real_layout = false;
+    bool real_layout_ok = false;            // VQE_REAL_LAYOUT (default on) and an unsharded context
     PlanCache* plan_cache = nullptr;        // see rotations_impl
     double2* gstage[2] = {nullptr, nullptr};  // staging buffers of gather-form peer passes (two: chunk k + 1 is fetched under chunk k)
     size_t gstage_cap[2] = {0, 0};            // in amplitudes
@@ -2417,6 +2480,22 @@ static int ensure_buf(vqe_ctx* c, int b) {
     return VQE_OK;
 }
 
+static int grid_1d(const vqe_ctx* c, uint64_t n_amp, int threads);
+// buffer b in interleaved complex form (only the state buffer is ever kept in the real layout)
+static int ensure_complex(vqe_ctx* c, int b) {
+    if (b != VQE_BUF_PSI || !c->real_layout) return VQE_OK;
+    double* buf = reinterpret_cast<double*>(c->buf[VQE_BUF_PSI]);
+    for (uint64_t hi = c->n_amp; hi >= 1; hi >>= 1) {
+        const uint64_t lo = hi >> 1;  // levels [N/2, N), [N/4, N/2), ..., [1, 2), [0, 1)
+        k_expand_level<<<grid_1d(c, hi - lo, 256), 256, 0, c->stream>>>(buf, lo, hi);
+        c->launches++;
+        if (hi == 1) break;
+    }
+    CK(cudaGetLastError());
+    c->real_layout = false;
+    return VQE_OK;
+}
+
 static size_t tile_smem(int tbits, int n_tiles_in_smem, bool term_cache) {
     size_t s = (size_t)n_tiles_in_smem * (16ull << tbits);
     if (term_cache)
@@ -2439,8 +2518,9 @@ static int set_kernel_attrs(int device) {
     SET_SMEM(k_tile_ops);
     SET_SMEM(k_tile_rot<false>);
     SET_SMEM(k_tile_rot<true>);
-    SET_SMEM(k_tile_col<false>);
-    SET_SMEM(k_tile_col<true>);
+    SET_SMEM((k_tile_col<false, false>));
+    SET_SMEM((k_tile_col<true, false>));
+    SET_SMEM((k_tile_col<true, true>));
     SET_SMEM(k_col_pipe<false>);
     SET_SMEM(k_col_pipe<true>);
     SET_SMEM(k_expect_pipe<false>);
@@ -2448,8 +2528,12 @@ static int set_kernel_attrs(int device) {
     SET_SMEM(k_tile_expect<false>);
     SET_SMEM(k_tile_expect<true>);
     SET_SMEM(k_tile_apply);
-    SET_SMEM(k_expect_lean<false>);
-    SET_SMEM(k_expect_lean<true>);
+    SET_SMEM((k_expect_lean<false, 256>));
+    SET_SMEM((k_expect_lean<true, 256>));
+    SET_SMEM((k_expect_lean<false, 384>));
+    SET_SMEM((k_expect_lean<true, 384>));
+    SET_SMEM((k_expect_lean<false, 512>));
+    SET_SMEM((k_expect_lean<true, 512>));
     SET_SMEM(k_apply_lean<false>);
     SET_SMEM(k_apply_lean<true>);
     SET_SMEM(k_tile_pool);
@@ -2486,7 +2570,11 @@ static int create_ctx(vqe_ctx** out, int n_qubits, int n_global, int rank, int d
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     c->tile_bits = env_int("VQE_TILE_BITS", 12);
-    c->low_bits = env_int("VQE_LOW_BITS", 5);
+    // low-bit floor of the tiles: tensor-map (TMA) tile loads make short contiguous runs cheap, so an unsharded context only
+    // insists on 16 amplitudes (256 bytes; 128 in the real layout) and leaves 8 tile bits to the planner; the peer passes of
+    // a sharded state copy segment by segment and keep 512-byte segments
+    c->low_bits = env_int("VQE_LOW_BITS", n_global ? 5 : 4);
+    c->real_layout_ok = env_int("VQE_REAL_LAYOUT", 1) != 0 && n_global == 0;
     c->threads = env_int("VQE_THREADS", 512);
     c->ctas_per_sm = env_int("VQE_CTAS_PER_SM", 2);
     if (c->tile_bits < 6 || c->tile_bits > 12) c->tile_bits = 12;
@@ -2753,6 +2841,7 @@ static int make_geom(const vqe_ctx* c, const TilePlan& tp, const uint64_t* d_sca
     g.bulk = (tp.lbits >= 3 && env_int("VQE_BULK", 1)) ? 1u : 0u;  // segments of at least 128 bytes
     g.tma = 0;
     g.swz = 0;
+    g.rl = 0;
     memset(&g.tg, 0, sizeof g.tg);
     if (!tp.vbit) {
         g.n_tiles = tp.n_tiles;
@@ -2809,19 +2898,22 @@ struct TmaShape {
     cuuint32_t box[5];
 };
 // Host-only: the tensor-map shape of a local tile plan (see TmaGeom).  ok = false: keep the per-segment bulk copies.
-static TmaShape plan_tma(const TilePlan& tp, bool swizzle) {
+// rl: real layout (8-byte elements, one double per amplitude) instead of interleaved complex (two doubles per amplitude)
+static TmaShape plan_tma(const TilePlan& tp, bool swizzle, bool rl = false) {
     TmaShape sh;
     memset(&sh.tg, 0, sizeof sh.tg);
     sh.swizzled = false;
+    const int r1 = rl ? 1 : 0;
     if (tp.vbit || tp.bits.empty() || tp.nl > 36) return sh;
-    if (swizzle && tp.lbits < 3) return sh;  // the 128-byte swizzle needs the three lowest index bits in the tile
+    if (swizzle && tp.lbits < 3 + r1) return sh;  // the 128-byte swizzle needs the three (real layout: four) lowest index bits in the tile
     // runs of adjacent tile bits; a run is cut where a box would exceed 256 elements (dimension 0 counts doubles)
     struct Run { int start, len; };
     std::vector<Run> runs;
     for (int b : tp.bits) {
         const bool adjacent = !runs.empty() && runs.back().start + runs.back().len == b;
         // the run at bit 0 is dimension 0 and counts doubles: at most 2^(7+1) of them; swizzled: exactly 8 amplitudes = 128 bytes
-        const int cap = (runs.size() == 1 && runs[0].start == 0) ? (swizzle ? 3 : 7) : 8;
+        // (real layout: one double per amplitude, so one index bit more in both cases)
+        const int cap = (runs.size() == 1 && runs[0].start == 0) ? (swizzle ? 3 + r1 : 7 + r1) : 8;
         if (adjacent && runs.back().len < cap) runs.back().len++;
         else runs.push_back({b, 1});
     }
@@ -2850,15 +2942,15 @@ static TmaShape plan_tma(const TilePlan& tp, bool swizzle) {
             }
             sh.tg.shift[i] = (uint32_t)lo;
             sh.tg.cmask[i] = (uint32_t)((1ull << span) - 1ull);
-            sh.gdim[i] = (i == 0) ? (2ull << span) : (1ull << span);
-            sh.box[i] = (i == 0) ? (2u << blog[i]) : (1u << blog[i]);
-            if (i > 0) sh.gstride[i - 1] = 16ull << lo;
+            sh.gdim[i] = (i == 0 && !rl) ? (2ull << span) : (1ull << span);
+            sh.box[i] = (i == 0 && !rl) ? (2u << blog[i]) : (1u << blog[i]);
+            if (i > 0) sh.gstride[i - 1] = (rl ? 8ull : 16ull) << lo;
         } else {
             sh.tg.shift[i] = 0;
             sh.tg.cmask[i] = 0;  // coordinate 0
             sh.gdim[i] = 1;
             sh.box[i] = 1;
-            sh.gstride[i - 1] = 16ull << tp.nl;
+            sh.gstride[i - 1] = (rl ? 8ull : 16ull) << tp.nl;
         }
     }
     sh.tg.n_req = 1u << extra.size();
@@ -2876,21 +2968,22 @@ static TmaShape plan_tma(const TilePlan& tp, bool swizzle) {
 // tensor-map form, the driver entry point is missing, or VQE_TMA=0.
 // would make_tmap(tp, ..., swizzle) succeed?  (plan-time decision of the lean Pauli-sum passes, whose entry tables are
 // pre-swizzled)
-static bool tma_available(const TilePlan& tp, bool swizzle) {
-    return env_int("VQE_TMA", 1) && tmap_encoder() && plan_tma(tp, swizzle).ok;
+static bool tma_available(const TilePlan& tp, bool swizzle, bool rl = false) {
+    return env_int("VQE_TMA", 1) && tmap_encoder() && plan_tma(tp, swizzle, rl).ok;
 }
 // swizzle: -1 = swizzled when the plan allows it, 0 = natural layout, 1 = swizzled or nothing
-static void make_tmap(const TilePlan& tp, double2* ptr, TileGeom& g, CUtensorMap* map, int swizzle = -1) {
+static void make_tmap(const TilePlan& tp, double2* ptr, TileGeom& g, CUtensorMap* map, int swizzle = -1, bool rl = false) {
     memset(map, 0, sizeof *map);
     g.tma = 0;
     g.swz = 0;
+    g.rl = rl ? 1u : 0u;
     memset(&g.tg, 0, sizeof g.tg);
     if (!env_int("VQE_TMA", 1) || !ptr) return;
     PFN_tmapEncodeTiled enc = tmap_encoder();
     if (!enc) return;
     if (!env_int("VQE_SWIZZLE", 1) && swizzle < 0) swizzle = 0;
-    TmaShape sh = plan_tma(tp, swizzle != 0);
-    if (!sh.ok && swizzle < 0) sh = plan_tma(tp, false);
+    TmaShape sh = plan_tma(tp, swizzle != 0, rl);
+    if (!sh.ok && swizzle < 0) sh = plan_tma(tp, false, rl);
     if (!sh.ok) return;
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)ptr, sh.gdim, sh.gstride, sh.box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -2906,15 +2999,27 @@ static void make_tmap(const TilePlan& tp, double2* ptr, TileGeom& g, CUtensorMap
 // (dimension 0 fastest, element = one double) for every request of up to `max_tiles` tiles and compares the global
 // element index of every tile element with the gather address the per-segment path uses.  Returns the number of
 // mismatching elements, or -1 when the plan has no tensor-map form.  *n_req / *rank_used describe the shape.
+static int tma_check_impl(int n_local, uint64_t need_mask, int tile_bits, int low_bits, int max_tiles, int32_t* n_req,
+                          int32_t* dims_used, bool rl);
 extern "C" int vqe_debug_tma_check(int n_local, uint64_t need_mask, int tile_bits, int low_bits, int max_tiles, int32_t* n_req,
                                    int32_t* dims_used) {
+    return tma_check_impl(n_local, need_mask, tile_bits, low_bits, max_tiles, n_req, dims_used, false);
+}
+// the same for the REAL LAYOUT of the state buffer (n_amp contiguous doubles, tile elements of 8 bytes)
+extern "C" int vqe_debug_tma_check_rl(int n_local, uint64_t need_mask, int tile_bits, int low_bits, int max_tiles, int32_t* n_req,
+                                      int32_t* dims_used) {
+    return tma_check_impl(n_local, need_mask, tile_bits, low_bits, max_tiles, n_req, dims_used, true);
+}
+static int tma_check_impl(int n_local, uint64_t need_mask, int tile_bits, int low_bits, int max_tiles, int32_t* n_req,
+                          int32_t* dims_used, bool rl) {
     if (n_local < 1 || n_local > 40) return fail(VQE_ERR_INVALID, "bad n_local");
     if (tile_bits < 1 || tile_bits > 12) tile_bits = 12;
     const bool want_swz = max_tiles < 0;  // negative max_tiles: check the 128-byte-swizzled shape
     max_tiles = max_tiles < 0 ? -max_tiles : max_tiles;
     const TilePlan tp = make_plan(n_local, need_mask, tile_bits, std::max(0, std::min(low_bits, tile_bits)), 0);
-    const TmaShape sh = plan_tma(tp, want_swz);
+    const TmaShape sh = plan_tma(tp, want_swz, rl);
     if (!sh.ok) return -1;
+    if (want_swz && sh.box[0] * 8 != 128) return 1 << 30;  // the swizzle atom is exactly 128 bytes wide
     if (n_req) *n_req = (int32_t)sh.tg.n_req;
     if (dims_used) {
         int d = 0;
@@ -2944,7 +3049,7 @@ extern "C" int vqe_debug_tma_check(int n_local, uint64_t need_mask, int tile_bit
             const uint64_t idx = base | sh.tg.req_bits[r];
             int64_t c[5];
             for (int i = 0; i < 5; ++i) c[i] = (int64_t)((uint32_t)(idx >> sh.tg.shift[i]) & sh.tg.cmask[i]);
-            c[0] <<= 1;
+            if (!rl) c[0] <<= 1;
             for (uint32_t e4 = 0; e4 < sh.box[4]; ++e4)
                 for (uint32_t e3 = 0; e3 < sh.box[3]; ++e3)
                     for (uint32_t e2 = 0; e2 < sh.box[2]; ++e2)
@@ -2956,12 +3061,13 @@ extern "C" int vqe_debug_tma_check(int n_local, uint64_t need_mask, int tile_bit
                                 if ((uint64_t)(c[0] + e0) >= sh.gdim[0] || (uint64_t)(c[1] + e1) >= sh.gdim[1] ||
                                     (uint64_t)(c[2] + e2) >= sh.gdim[2] || (uint64_t)(c[3] + e3) >= sh.gdim[3] ||
                                     (uint64_t)(c[4] + e4) >= sh.gdim[4]) { ++bad; continue; }
-                                const uint32_t kk = local >> 1;  // amplitude inside the tile
-                                const uint64_t want = (base | tp.scat[kk >> tp.lbits] | (uint64_t)(kk & lmask)) * 16ull + (local & 1u) * 8ull;
+                                const uint32_t kk = rl ? local : local >> 1;  // amplitude inside the tile
+                                const uint64_t amp = base | tp.scat[kk >> tp.lbits] | (uint64_t)(kk & lmask);
+                                const uint64_t want = rl ? amp * 8ull : amp * 16ull + (local & 1u) * 8ull;
                                 if (byte != want) ++bad;
                             }
         }
-        if (local != 2 * ts) bad += 1000000;
+        if (local != (rl ? ts : 2 * ts)) bad += 1000000;
     }
     return bad;
 }
@@ -3025,7 +3131,11 @@ extern "C" int vqe_set_basis_state(vqe_ctx* c, uint64_t index) {
     CK(cudaSetDevice(c->device));
     // sharded: only the rank that owns the index holds the 1 (an out-of-range local index leaves the shard zero)
     const uint64_t local = ((int)(index >> c->nl) == c->rank) ? (index & (c->n_amp - 1)) : ~0ull;
-    k_zero_set<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[0], c->n_amp, local);
+    if (c->real_layout_ok)
+        k_zero_set_real<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(reinterpret_cast<double*>(c->buf[0]), c->n_amp, local);
+    else
+        k_zero_set<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[0], c->n_amp, local);
+    c->real_layout = c->real_layout_ok;
     c->psi_real = true;
     c->launches++;
     CK(cudaGetLastError());
@@ -3038,7 +3148,7 @@ extern "C" int vqe_set_state(vqe_ctx* c, int b, const double* re_im) {
     int rc = ensure_buf(c, b);
     if (rc) return rc;
     c->h2d_bytes += c->n_amp * sizeof(double2);
-    if (b == VQE_BUF_PSI) c->psi_real = false;
+    if (b == VQE_BUF_PSI) c->psi_real = c->real_layout = false;  // overwritten as a whole, in complex form
     CK(cudaMemcpyAsync(c->buf[b], re_im, c->n_amp * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return VQE_OK;
@@ -3048,10 +3158,23 @@ extern "C" int vqe_get_state(vqe_ctx* c, int b, double* re_im) {
     CK(cudaSetDevice(c->device));
     int rc = ensure_buf(c, b);
     if (rc) return rc;
+    if (b == VQE_BUF_PSI && c->real_layout) {
+        // real layout: the n_amp real parts are copied into the upper half of the caller's array and interleaved there
+        double* tmp = re_im + c->n_amp;
+        c->d2h_bytes += c->n_amp * sizeof(double);
+        CK(cudaMemcpyAsync(tmp, c->buf[b], c->n_amp * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (uint64_t i = 0; i < c->n_amp; ++i) {  // ascending: slot 2i is below the unread reals n_amp + i.. for every i
+            const double v = tmp[i];
+            re_im[2 * i] = v;
+            re_im[2 * i + 1] = 0.0;
+        }
+        return vqe_shard_status(c);
+    }
     c->d2h_bytes += c->n_amp * sizeof(double2);
     CK(cudaMemcpyAsync(re_im, c->buf[b], c->n_amp * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    return VQE_OK;
+    return vqe_shard_status(c);
 }
 extern "C" int vqe_copy_buffer(vqe_ctx* c, int dst, int src) {
     if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
@@ -3061,7 +3184,9 @@ extern "C" int vqe_copy_buffer(vqe_ctx* c, int dst, int src) {
     rc = ensure_buf(c, src);
     if (rc) return rc;
     if (dst == src) return VQE_OK;
-    if (dst == VQE_BUF_PSI) c->psi_real = false;
+    rc = ensure_complex(c, src);
+    if (rc) return rc;
+    if (dst == VQE_BUF_PSI) c->psi_real = c->real_layout = false;
     CK(cudaMemcpyAsync(c->buf[dst], c->buf[src], c->n_amp * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
     return VQE_OK;
 }
@@ -3070,6 +3195,8 @@ extern "C" int vqe_buffer_ptr(vqe_ctx* c, int b, void** p, uint64_t* n_amp) {
     CK(cudaSetDevice(c->device));
     if (b < 0 || b > 3) return fail(VQE_ERR_INVALID, "bad buffer id %d", b);
     int rc = ensure_buf(c, b);
+    if (rc) return rc;
+    rc = ensure_complex(c, b);
     if (rc) return rc;
     *p = c->buf[b];
     if (b == VQE_BUF_PSI) c->psi_real = false;  // the caller may write through the pointer
@@ -3707,6 +3834,28 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
         if (buf == VQE_BUF_PSI)
             for (vqe_ctx* c : rs.r) c->psi_real = real;
     }
+    // Real layout of the state buffer (unsharded contexts, see vqe_ctx::real_layout): kept when EVERY pass is a purely real
+    // collapsed-run pass with a real-layout tensor-map form (every UCCSD / QUCCSD program); otherwise the buffer is expanded
+    // to interleaved complex first and the passes run as usual.
+    auto pass_all_col = [&](const OpPass& ps) {
+        return ps.fast && ps.sub_end == ps.sub_begin && ps.col_end > ps.col_begin && ps.pass_scale == 1.0 &&
+               (ps.sup_end - ps.sup_begin) == (ps.col_end - ps.col_begin) && env_int("VQE_COL_KERNEL", 1) != 0;
+    };
+    bool rl_plan = buf == VQE_BUF_PSI && rs.r.size() == 1 && rs.r[0]->real_layout && env_int("VQE_PIPE", 0) == 0;
+    if (rl_plan)
+        for (size_t p = 0; p < passes.size() && rl_plan; ++p) {
+            const OpPass& ps = passes[p];
+            const size_t smem_r = (8ull << ps.tp.tbits) + (size_t)(ps.col_end - ps.col_begin) * (sizeof(ColLite) + 8 + 4) +
+                                  (size_t)(ps.ent_end - ps.ent_begin) * sizeof(DevColEntry);
+            rl_plan = real_pass[p] && !ps.tp.vbit && pass_all_col(ps) && smem_r <= 200 * 1024 &&
+                      (tma_available(ps.tp, true, true) || tma_available(ps.tp, false, true));
+        }
+    if (!rl_plan && buf == VQE_BUF_PSI)
+        for (vqe_ctx* c : rs.r) {
+            CK(cudaSetDevice(c->device));
+            rc = ensure_complex(c, buf);
+            if (rc) return rc;
+        }
     // one launch of the pass kernel on one rank (gg.n_need != 0: gather form over the tiles of the current chunk)
     auto launch_pass = [&](vqe_ctx* c, size_t p, const TileGeom& g, const Shards& sh, const GatherGeom& gg,
                            const GatherGeom* gnext = nullptr, uint64_t next_first = 0, uint64_t next_tiles = 0,
@@ -3733,6 +3882,18 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                                   (size_t)n_ents * sizeof(DevColEntry);
             TileGeom gt = g;
             CUtensorMap tmap;
+            if (rl_plan) {
+                // real layout: 8-byte tile elements, tensor-map staging only, four CTAs per SM
+                make_tmap(ps.tp, sh.p0, gt, &tmap, -1, true);
+                if (!gt.tma) return fail(VQE_ERR_CUDA, "real-layout tensor map of a rotation pass could not be encoded");
+                const size_t smem_r = (8ull << ps.tp.tbits) + (size_t)n_cols * (sizeof(ColLite) + 8 + 4) + (size_t)n_ents * sizeof(DevColEntry);
+                const int grid_r = tile_grid(c, g.n_tiles, smem_r <= 54 * 1024 ? 4 : (smem_r <= 74 * 1024 ? 3 : 2));
+                k_tile_col<true, true><<<grid_r, thr, smem_r, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                                                                          (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
+                c->launches++;
+                CK(cudaGetLastError());
+                return VQE_OK;
+            }
             make_tmap(ps.tp, ps.tp.vbit ? nullptr : sh.p0, gt, &tmap);
             if ((gt.bulk || gt.tma) && smem_p <= 226 * 1024 && env_int("VQE_PIPE", 0) != 0) {
                 // tile ring: one persistent CTA per SM, loads two tiles ahead, stores draining behind
@@ -3751,10 +3912,10 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                     k_col_pipe<false><<<grid_p, thr_p, smem_p, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                            (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
             } else if (real_pass[p])
-                k_tile_col<true><<<grid, thr, smem_c, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                k_tile_col<true, false><<<grid, thr, smem_c, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                   (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
             else
-                k_tile_col<false><<<grid, thr, smem_c, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                k_tile_col<false, false><<<grid, thr, smem_c, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                    (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
         } else if (ps.fast && real_pass[p])
         {
@@ -4190,6 +4351,8 @@ extern "C" int vqe_scale_state(vqe_ctx* c, int b, double re, double im) {
     CK(cudaSetDevice(c->device));
     int rc = ensure_buf(c, b);
     if (rc) return rc;
+    rc = ensure_complex(c, b);
+    if (rc) return rc;
     if (b == VQE_BUF_PSI && im != 0.0) c->psi_real = false;
     k_axpby<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[b], c->buf[b], c->n_amp, re, im, 0.0, 0.0);
     c->launches++;
@@ -4205,6 +4368,9 @@ extern "C" int vqe_axpby(vqe_ctx* c, int dst, int x, double a_re, double a_im, d
     int rc = ensure_buf(c, dst);
     if (rc) return rc;
     rc = ensure_buf(c, x);
+    if (rc) return rc;
+    rc = ensure_complex(c, dst);
+    if (rc == VQE_OK) rc = ensure_complex(c, x);
     if (rc) return rc;
     if (dst == VQE_BUF_PSI) c->psi_real = false;
     k_axpby<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[dst], c->buf[x], c->n_amp, a_re, a_im, b_re, b_im);
@@ -4306,6 +4472,8 @@ struct PSPass {
     std::vector<DevAddOut> addout;
     size_t lean_terms = 0;              // Pauli strings folded into the entries (statistics)
     DevFlat2* d_flats2 = nullptr;
+    DevFlat2* d_flats2_rl = nullptr;    // the entries in real-layout form (expectation on a state kept as n_amp doubles)
+    bool rl_ok = false, rl_swz = false; // the pass has a real-layout tensor-map form | whose tile is swizzled
     uint32_t* d_goff = nullptr;
     double* d_addtab = nullptr;
     DevAddPat* d_addpat = nullptr;
@@ -5001,6 +5169,8 @@ static void free_paulisum_device(vqe_paulisum* ps) {
         p.d_flats = nullptr;
         p.d_fzout = nullptr;
         if (p.d_flats2) cudaFree(p.d_flats2);
+        if (p.d_flats2_rl) cudaFree(p.d_flats2_rl);
+        p.d_flats2_rl = nullptr;
         if (p.d_goff) cudaFree(p.d_goff);
         if (p.d_addtab) cudaFree(p.d_addtab);
         if (p.d_addpat) cudaFree(p.d_addpat);
@@ -5030,6 +5200,17 @@ static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
     for (PSPass& p : ps->passes) {
         if (p.lean) {
             int rc = upload_vec(&p.d_flats2, p.flats2);
+            // real-layout twin of the entries (unsharded contexts keep a purely real state as n_amp doubles)
+            p.rl_ok = false;
+            if (rc == VQE_OK && c->real_layout_ok && !p.tp.vbit && p.tp.tbits >= 9) {
+                p.rl_swz = env_int("VQE_SWIZZLE", 1) != 0 && tma_available(p.tp, true, true);
+                p.rl_ok = p.rl_swz || tma_available(p.tp, false, true);
+                if (p.rl_ok) {
+                    std::vector<DevFlat2> rl(p.flats2.size());
+                    for (size_t k = 0; k < rl.size(); ++k) rl[k] = lean_entry_to_rl(p.flats2[k], p.swz, p.rl_swz);
+                    rc = upload_vec(&p.d_flats2_rl, rl);
+                }
+            }
             if (rc == VQE_OK) rc = upload_vec(&p.d_goff, p.goff);
             if (rc == VQE_OK) rc = upload_vec(&p.d_addtab, p.addtab);
             if (rc == VQE_OK) rc = upload_vec(&p.d_addpat, p.addpat);
@@ -5224,6 +5405,34 @@ extern "C" int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int til
                 }
                 beta[k] = b;
             }
+            if (getenv("VQE_DEBUG_LEAN_RL") && atoi(getenv("VQE_DEBUG_LEAN_RL")) != 0) {
+                // the REAL-LAYOUT twin of the entries (lean_entry_to_rl) on a tile of doubles holding Re(psi), swizzled the way
+                // the real-layout tensor map delivers it: what k_expect_lean<true, T, true> evaluates (expectation only)
+                const bool swz_r = plan_tma(p.tp, true, true).ok;
+                if (!swz_r && !plan_tma(p.tp, false, true).ok) return fail(VQE_ERR_INVALID, "pass without a real-layout tensor-map form");
+                const uint32_t swr = swz_r ? 0x70u : 0u;
+                std::vector<double> tr(ts);
+                for (uint32_t k = 0; k < ts; ++k) tr[swz_idx8(k, swr)] = psi[base | p.tp.scat[k >> p.tp.lbits] | (uint64_t)(k & lmask)].x;
+                for (size_t e = 0; e < p.flats2.size(); ++e) {
+                    const DevFlat2 fr = lean_entry_to_rl(p.flats2[e], p.swz, swz_r);
+                    uint4 q[3];
+                    memcpy(q, &fr, sizeof(DevFlat2));
+                    const uint32_t par_out = (uint32_t)popc64(sbase & p.fzout[q[0].w >> 16]);
+                    for (uint32_t lane = 0; lane < 32; ++lane) {
+                        LeanUnit u;
+                        lean_decode(q[0], q[1], q[2], lane, u, 3);
+                        for (uint32_t j = 0; j < 8; ++j) {
+                            const uint32_t off = swz_off(u.v, swr) ^ u.o[j], offb = off ^ u.lx16;
+                            if ((off & 7u) || (offb & 7u) || (off >> 3) >= ts || (offb >> 3) >= ts) return fail(VQE_ERR_INVALID, "real-layout offset out of range");
+                            double gw = 0.5 * u.fr;
+                            if (u.tab != 0xffffu) gw *= beta[u.bidx] + p.addtab[u.tab + lane] + p.addtab[u.hi0 + j];
+                            if ((u.s0 + (u.jsign >> j) + par_out) & 1u) gw = -gw;
+                            total += 2.0 * gw * tr[off >> 3] * tr[offb >> 3];
+                        }
+                    }
+                }
+                continue;
+            }
             for (size_t e = 0; e < p.flats2.size(); ++e) {
                 uint4 q[3];
                 memcpy(q, &p.flats2[e], sizeof(DevFlat2));
@@ -5288,6 +5497,18 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
     const size_t n_pass = pss[0]->passes.size();
     bool real_state = b == VQE_BUF_PSI;  // the purely-real flag is only tracked for the state buffer
     for (vqe_ctx* c : rs.r) real_state = real_state && c->psi_real;
+    // Real layout of the state (unsharded): the lean passes read it as it is when every one of them has a real-layout form;
+    // the buffer is expanded to interleaved complex before the first general pass (or right away otherwise).
+    bool rl = b == VQE_BUF_PSI && nr == 1 && rs.r[0]->real_layout && real_state && env_int("VQE_PIPE", 0) == 0;
+    if (rl)
+        for (const PSPass& pp : pss[0]->passes)
+            if (pp.lean && !pp.rl_ok) rl = false;
+    if (!rl && b == VQE_BUF_PSI)
+        for (vqe_ctx* c : rs.r) {
+            CK(cudaSetDevice(c->device));
+            rc = ensure_complex(c, b);
+            if (rc) return rc;
+        }
     // per rank: grids and partial-sum layout (consecutive blocks of every pass this rank launches)
     std::vector<std::vector<dim3>> grids(nr, std::vector<dim3>(n_pass));
     std::vector<std::vector<TileGeom>> geoms(nr, std::vector<TileGeom>(n_pass));
@@ -5333,6 +5554,29 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             ProfScope prof(c, vbit ? 5 : 1);
             CUtensorMap tmap;
             memset(&tmap, 0, sizeof tmap);
+            if (rl && !pp.lean && c->real_layout) {  // first general pass: it reads the interleaved form
+                rc = ensure_complex(c, b);
+                if (rc) return rc;
+            }
+            const bool rl_pass = rl && pp.lean && c->real_layout;
+            if (rl_pass) {
+                make_tmap(pp.tp, shards[k][p].p0, geoms[k][p], &tmap, pp.rl_swz ? 1 : 0, true);
+                if (!geoms[k][p].tma) return fail(VQE_ERR_CUDA, "real-layout tensor map of an expectation pass could not be encoded");
+                const size_t smem_r = (8ull << pp.tp.tbits) + pp.addpat.size() * sizeof(double);
+                const int thr_l = env_int("VQE_EXP_LEAN_THREADS", 256);
+#define LAUNCH_EXPECT_RL(T)                                                                                                    \
+    k_expect_lean<true, T, true><<<grids[k][p], T, smem_r, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2_rl,       \
+                                                                       (int)pp.flats2.size(), pp.d_fzout, pp.d_addtab, pp.d_addpat, \
+                                                                       (int)pp.addpat.size(), pp.d_addout, c->d_partial + off[k], c->d_err)
+                if (thr_l == 512) LAUNCH_EXPECT_RL(512);
+                else if (thr_l == 384) LAUNCH_EXPECT_RL(384);
+                else LAUNCH_EXPECT_RL(256);
+#undef LAUNCH_EXPECT_RL
+                c->launches++;
+                CK(cudaGetLastError());
+                off[k] += (size_t)grids[k][p].x * grids[k][p].y;
+                continue;
+            }
             if (pp.lean) {
                 make_tmap(pp.tp, vbit ? nullptr : shards[k][p].p0, geoms[k][p], &tmap, pp.swz ? 1 : 0);
                 if (pp.swz && !geoms[k][p].tma)
@@ -5359,14 +5603,21 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                                                                                    pp.d_addout, c->d_partial + off[k], c->d_err);
             } else if (pp.lean) {
                 const size_t smem_l = tile_smem(pp.tp.tbits, 1, false) + pp.addpat.size() * sizeof(double);
-                if (real_state)
-                    k_expect_lean<true><<<grids[k][p], 256, smem_l, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
-                                                                                pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
-                                                                                pp.d_addout, c->d_partial + off[k], c->d_err);
-                else
-                    k_expect_lean<false><<<grids[k][p], 256, smem_l, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(),
-                                                                                 pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),
-                                                                                 pp.d_addout, c->d_partial + off[k], c->d_err);
+                const int thr_l = env_int("VQE_EXP_LEAN_THREADS", 256);
+#define LAUNCH_EXPECT_LEAN(R, T)                                                                                              \
+    k_expect_lean<R, T><<<grids[k][p], T, smem_l, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2, (int)pp.flats2.size(), \
+                                                              pp.d_fzout, pp.d_addtab, pp.d_addpat, (int)pp.addpat.size(),    \
+                                                              pp.d_addout, c->d_partial + off[k], c->d_err)
+                if (real_state) {
+                    if (thr_l == 512) LAUNCH_EXPECT_LEAN(true, 512);
+                    else if (thr_l == 384) LAUNCH_EXPECT_LEAN(true, 384);
+                    else LAUNCH_EXPECT_LEAN(true, 256);
+                } else {
+                    if (thr_l == 512) LAUNCH_EXPECT_LEAN(false, 512);
+                    else if (thr_l == 384) LAUNCH_EXPECT_LEAN(false, 384);
+                    else LAUNCH_EXPECT_LEAN(false, 256);
+                }
+#undef LAUNCH_EXPECT_LEAN
             } else if (pp.cplx)
                 k_tile_expect<true><<<grids[k][p], threads, smem, c->stream>>>(shards[k][p], geoms[k][p], pp.d_groups,
                                                                               (int)pp.groups.size(), pp.d_terms_expect,
@@ -5446,6 +5697,12 @@ static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* 
         int rc = ensure_buf(c, dst);
         if (rc) return rc;
         rc = ensure_buf(c, src);
+        if (rc) return rc;
+    }
+    for (vqe_ctx* c : rs.r) {
+        CK(cudaSetDevice(c->device));
+        int rc = ensure_complex(c, src);
+        if (rc == VQE_OK) rc = ensure_complex(c, dst);
         if (rc) return rc;
     }
     bool real_src = src == VQE_BUF_PSI;  // lean passes have real weights: a purely real source gives a purely real sigma
@@ -5571,6 +5828,9 @@ static int pool_impl(RankSet& rs, int bra, int ket, int n_ops, const int32_t* op
         rc = ensure_buf(c, bra);
         if (rc) return rc;
         rc = ensure_buf(c, ket);
+        if (rc) return rc;
+        rc = ensure_complex(c, bra);
+        if (rc == VQE_OK) rc = ensure_complex(c, ket);
         if (rc) return rc;
     }
     for (size_t k = 0; k < nr * 2 * (size_t)n_ops; ++k) out_per_rank[k] = 0.0;
@@ -5839,6 +6099,9 @@ extern "C" int vqe_inner(vqe_ctx* c, int a, int b, double* out) {
     if (rc) return rc;
     rc = ensure_buf(c, b);
     if (rc) return rc;
+    rc = ensure_complex(c, a);
+    if (rc == VQE_OK) rc = ensure_complex(c, b);
+    if (rc) return rc;
     return inner_bufs(c, c->buf[a], c->buf[b], out);
 }
 extern "C" int vqe_norm2(vqe_ctx* c, int b, double* out) {
@@ -5855,6 +6118,8 @@ extern "C" int vqe_overlap_host(vqe_ctx* c, int b, const double* vec, double* ou
     if (rc) return rc;
     int tmp = (b == VQE_BUF_WORK) ? VQE_BUF_SIGMA : VQE_BUF_WORK;
     rc = ensure_buf(c, tmp);
+    if (rc) return rc;
+    rc = ensure_complex(c, b);
     if (rc) return rc;
     CK(cudaMemcpyAsync(c->buf[tmp], vec, c->n_amp * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
     return inner_bufs(c, c->buf[tmp], c->buf[b], out);
@@ -5913,6 +6178,8 @@ extern "C" int vqe_apply_exp_paulisum(vqe_ctx* c, int n_terms, const uint64_t* x
         free_paulisum_device(&ps);
         return fail(VQE_ERR_INVALID, "exact exponential of non-commuting strings is not available on a sharded state");
     }
+    rc = ensure_complex(c, VQE_BUF_PSI);
+    if (rc) { free_paulisum_device(&ps); return rc; }
     c->psi_real = false;
     double2* term = c->buf[VQE_BUF_SIGMA];
     double2* next = c->buf[VQE_BUF_WORK];

@@ -360,3 +360,45 @@ def test_quccsd_get_energies_matches_the_reference_driver(gpu_required):
         assert len(th) == len(th_ref) == 26 and np.abs(np.array(th) - np.array(th_ref)).max() < 5e-3
     # the optimum found from the MP2 guess is the G4-class energy of the notebook (10^-3: different operator order)
     assert abs(it["minimum_energy_result1_guess"][0] - (-2.1770061634841933)) < 1e-3
+
+
+def test_c2_lih_sto3g_qubit_adapt(gpu_required):
+    """BASELINE config C2 on the molecule it names: LiH / STO-3G, r = 1.45 A, full space, 12 qubits
+    (tests/golden/lih_sto3g.json.gz: integrals from oracle/chem/gto.py, everything else produced by the unmodified reference
+    modules through the qat stand-in).  Whole-pool gradients of the 285-operator YXXX pool at |HF> and at a 3-operator
+    ADAPT state, the exact-exponential state itself, Trotterised energies, and the qubit_adapt_vqe loop."""
+    from openvqe_b200 import _hotpath
+    from openvqe_b200.adapt import qubit_adapt_vqe as qa
+    from openvqe_b200.common_files.pools import generate_yxxx_pool
+    from openvqe_b200.engine import get_engine
+    fx = load_golden("lih_sto3g.json.gz")
+    ham = ham_from_json(fx["hamiltonian"])
+    n_pool, pool = generate_yxxx_pool(12)
+    assert n_pool == fx["yxxx_pool_size"] == 285
+    hf = orc.basis_state(12, fx["hf_init_sp"])
+    assert abs(_hotpath.basis_energy(ham, fx["hf_init_sp"]) - fx["hf_energy"]) < TOL
+    eng = get_engine(12)
+    eng.set_state(hf)
+    g0 = 2.0 * np.abs(_hotpath.pool_overlaps(eng, ham, pool))
+    assert np.abs(g0 - np.array(fx["qubit_gradients_at_hf"])).max() < TOL
+    # the reference-shaped one-operator helper on a few operators (same numbers through calculate_gradient)
+    for k in (0, 7, 31, 284):
+        assert abs(qa.calculate_gradient(qa.term_to_matrix_sparse(pool[k]), hf, ham) - fx["qubit_gradients_at_hf"][k]) < TOL
+    a = fx["qubit_gradients_at_ansatz"]
+    st = qa.prepare_adapt_state(hf, [pool[i] for i in a["indices"]], a["parameters"]).reshape(-1)
+    assert np.abs(st - (np.array(a["state_re"]) + 1j * np.array(a["state_im"]))).max() < 1e-12
+    eng.set_state(st)
+    g1 = 2.0 * np.abs(_hotpath.pool_overlaps(eng, ham, pool))
+    assert np.abs(g1 - np.array(a["gradients"])).max() < TOL
+    for case in fx["ucc_action"]:
+        ops = [pool[i] for i in case["indices"]]
+        assert abs(qa.ucc_action(ham, ops, fx["hf_init_sp"], case["theta"]) - case["energy"]) < TOL
+    out = quiet(qa.qubit_adapt_vqe, ham, None, hf.reshape(-1, 1), 12, pool, fx["hf_init_sp"], fx["fci"], n_max_grads=1,
+                adapt_conver="norm", adapt_thresh=1e-7, adapt_maxiter=3, tolerance_sim=1e-9, method_sim="BFGS")
+    ref = fx["qubit_adapt_run"]["iterations_sim"]
+    assert np.abs(np.array(out[0]["energies"]) - np.array(ref["energies"])).max() < 1e-8
+    assert np.abs(np.array(out[0]["norms"]) - np.array(ref["norms"])).max() < 1e-6
+    assert abs(out[0]["Max_gradient"][0] - ref["Max_gradient"][0]) < TOL
+    for key in ("CNOTs", "Hadamard", "RX", "RY"):
+        assert out[0][key] == ref[key]
+    assert out[0]["energies"][-1] < fx["hf_energy"] - 1e-3 and out[0]["energies"][-1] > fx["fci"] - 1e-9

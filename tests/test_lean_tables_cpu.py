@@ -120,3 +120,46 @@ def test_groups_outside_the_lean_form_stay_on_the_general_path():
     sel[:4] = True
     e_ref, _ = _oracle(n, x, z, ny, c, psi, sel)
     assert abs(e - e_ref) < 1e-13
+
+
+@pytest.mark.parametrize("n,seed,low_bits", [(13, 11, 5), (15, 12, 4), (16, 13, 4), (14, 14, 3)])
+def test_real_layout_entries_reproduce_the_expectation(n, seed, low_bits, monkeypatch):
+    """The real-layout twin of the entries (state kept as n_amp doubles, 8-byte tile elements, its own 128-byte swizzle --
+    k_expect_lean<true, T, true>): lean_entry_to_rl + the kernels' decode routine on a tile of doubles = the oracle."""
+    x, z, ny, c = _relabelled_h6(n, seed)
+    rng = np.random.default_rng(200 + seed)
+    psi = rng.normal(size=1 << n)
+    psi = (psi / np.linalg.norm(psi)).astype(np.complex128)
+    monkeypatch.setenv("VQE_DEBUG_LEAN_RL", "1")
+    e, nlean, nfat, _ = _lean(n, x, z, ny, c, psi, low_bits=low_bits, want_sigma=False)
+    offdiag = x != 0
+    assert nlean == int(offdiag.sum())
+    e_ref, _ = _oracle(n, x, z, ny, c, psi, offdiag)
+    assert abs(e - e_ref) < 1e-12
+
+
+@pytest.mark.parametrize("rl", [False, True])
+def test_tensor_map_shapes_address_the_tiles(rl):
+    """Host emulation of the TMA box traversal (vqe_debug_tma_check / _rl): every element of every sampled tile lands where
+    the per-segment gather would put it -- interleaved complex and real layout, natural and 128-byte-swizzled shapes."""
+    from openvqe_b200 import _lib
+    lib = _lib.load()
+    fn = lib.vqe_debug_tma_check_rl if rl else lib.vqe_debug_tma_check
+    rng = np.random.default_rng(9)
+    checked = 0
+    for n_local in (12, 16, 20, 24, 30):
+        for low_bits in (3, 4, 5):
+            for _ in range(6):
+                k = int(rng.integers(0, 8))
+                hi = rng.choice(np.arange(low_bits, n_local), size=min(k, n_local - low_bits), replace=False) if n_local > low_bits else []
+                need = 0
+                for b in hi:
+                    need |= 1 << int(b)
+                for swz in (1, -1):
+                    nreq, dims = C.c_int32(), C.c_int32()
+                    bad = fn(n_local, need, 12, low_bits, swz * 5, C.byref(nreq), C.byref(dims))
+                    if bad == -1:
+                        continue  # the plan has no tensor-map form of this kind (the kernels then take another path)
+                    assert bad == 0, (rl, n_local, low_bits, hex(need), swz, bad)
+                    checked += 1
+    assert checked > 60
