@@ -56,6 +56,10 @@ int vqe_device_count(void);
 int vqe_create(vqe_ctx** out, int n_qubits, int device);
 void vqe_destroy(vqe_ctx* ctx);
 int vqe_n_qubits(const vqe_ctx* ctx);
+/* 1 while the state buffer is kept in the REAL LAYOUT (a purely real state -- |HF> followed by UCC / QUCCSD rotations -- stored
+ * as 2^n contiguous doubles; every pass then moves half the bytes), 0 = interleaved complex128.  Measurement only: the layout is
+ * internal, every entry point converts as needed. */
+int vqe_state_layout(const vqe_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
 uint64_t vqe_launch_count(const vqe_ctx* ctx);
 /* cumulative device time (ms) of the named kernel class since the last reset, measured with CUDA

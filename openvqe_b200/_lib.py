@@ -26,7 +26,7 @@ SYMBOLS = [
     "vqe_shard_barrier", "vqe_shard_status", "vqe_group_apply_pauli_rotations", "vqe_group_apply_gates",
     "vqe_group_expectation", "vqe_group_apply_paulisum", "vqe_group_pool_overlaps", "vqe_plan_rotations",
     "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf", "vqe_plan_paulisum", "vqe_debug_lean_host", "vqe_peer_bytes", "vqe_debug_tma_check",
-    "vqe_axpby", "vqe_debug_tma_check_rl",
+    "vqe_axpby", "vqe_debug_tma_check_rl", "vqe_state_layout",
 ]
 IPC_HANDLE_BYTES = 64
 SHARD_FLAGS = 3
@@ -58,6 +58,7 @@ def load():
         "vqe_create": (C.c_int, [P(vp), C.c_int, C.c_int]),
         "vqe_destroy": (None, [vp]),
         "vqe_n_qubits": (C.c_int, [vp]),
+        "vqe_state_layout": (C.c_int, [vp]),
         "vqe_launch_count": (u64, [vp]),
         "vqe_profile_enable": (C.c_int, [vp, C.c_int]),
         "vqe_profile_read": (C.c_int, [vp, C.c_int, P(dbl), P(u64), C.c_int]),

@@ -2053,7 +2053,7 @@ __device__ __forceinline__ double lean_entries(const char* tb, const DevFlat2* _
 }
 // RL: real layout of the state buffer (8-byte tile elements; `flats` are then the real-layout entries, REAL is implied)
 template <bool REAL, int THREADS, bool RL = false>
-__global__ void __launch_bounds__(THREADS, 3) k_expect_lean(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
+__global__ void __launch_bounds__(THREADS, RL ? 4 : 3) k_expect_lean(const __grid_constant__ CUtensorMap tmap, Shards psi, TileGeom g,
                                                         const DevFlat2* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
                                                         const DevAddPat* __restrict__ addpat, int n_addpat,
@@ -3073,6 +3073,7 @@ static int tma_check_impl(int n_local, uint64_t need_mask, int tile_bits, int lo
 }
 
 extern "C" int vqe_n_qubits(const vqe_ctx* c) { return c ? c->n : 0; }
+extern "C" int vqe_state_layout(const vqe_ctx* c) { return (c && c->real_layout) ? 1 : 0; }
 extern "C" uint64_t vqe_launch_count(const vqe_ctx* c) { return c ? c->launches : 0; }
 extern "C" int vqe_profile_enable(vqe_ctx* c, int on) {
     if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
@@ -5526,8 +5527,9 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             }
             const bool pipe = pp.lean && geoms[k][p].bulk && env_int("VQE_PIPE", 0) != 0 &&
                               3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double) <= 226 * 1024;
-            int gx = tile_grid(c, geoms[k][p].n_tiles, pipe ? 1 : (pp.lean ? 3 : 0));
-            int want = std::max(1, (c->sm_count * (pipe ? 1 : (pp.lean ? 3 : c->ctas_per_sm))) / gx);
+            const int lean_ctas = (rl && pp.lean) ? std::max(1, std::min(6, env_int("VQE_EXP_RL_CTAS", 4))) : 3;  // 32 KiB tiles, 64 registers
+            int gx = tile_grid(c, geoms[k][p].n_tiles, pipe ? 1 : (pp.lean ? lean_ctas : 0));
+            int want = std::max(1, (c->sm_count * (pipe ? 1 : (pp.lean ? lean_ctas : c->ctas_per_sm))) / gx);
             int gy = std::max(1, std::min<int>(pp.lean ? (int)((pp.flats2.size() + 7) / 8) : (int)pp.groups.size(), want));
             grids[k][p] = dim3(gx, gy, 1);
             total_blocks[k] += (size_t)gx * gy;

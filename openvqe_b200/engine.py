@@ -189,6 +189,11 @@ class Engine:
         return complex(out[0], out[1])
 
     # -- bookkeeping ---------------------------------------------------------
+    @property
+    def real_layout(self) -> bool:
+        """True while the state buffer is kept as 2^n doubles (purely real state; see include/vqe_b200.h)."""
+        return bool(self._lib.vqe_state_layout(self.handle))
+
     def synchronize(self):
         _lib.check(self._lib.vqe_synchronize(self.handle))
 

@@ -144,6 +144,37 @@ def slice_packed(p: PackedTerms, lo: int, hi: int) -> PackedTerms:
     return PackedTerms(p.n, p.x[a:b], p.z[a:b], p.ny[a:b], p.cre[a:b], p.cim[a:b], p.offsets[lo:hi + 1] - a)
 
 
+# ---- exact generator exponential on a sharded state -------------------------------------------------------
+def taylor_exp(engine, packed: PackedTerms, theta: float):
+    """psi <- exp(theta A) psi for an anti-Hermitian Pauli sum A on a SHARDED state (reference prepare_adapt_state,
+    adapt/fermionic_adapt_vqe.py:12-38, scipy expm_multiply).  Commuting strings are rotations; otherwise the scaled
+    Taylor series of vqe_apply_exp_paulisum is driven from the host, because its convergence test needs the norm of the
+    current term summed over all ranks:  psi <- (sum_m (theta A / s)^m / m!)^s psi  with  term <- (theta / (s m)) A term.
+    ``engine``: a ShardedEngine (every rank runs this in lockstep) or a ShardGroup; three state vectors per rank."""
+    import math
+    from ._hotpath import _strings_commute
+    keep = (packed.cre != 0) | (packed.cim != 0)
+    x, z, ny, cim = packed.x[keep], packed.z[keep], packed.ny[keep], packed.cim[keep]
+    if len(x) == 0 or theta == 0.0:
+        return
+    if np.any(packed.cre[keep] != 0.0):
+        raise _lib.VQEError("the generator is not anti-Hermitian (real coefficient parts)")
+    if _strings_commute(x, z):
+        engine.apply_rotations(x, z, ny, -float(theta) * cim)
+        return
+    from .engine import BUF_WORK
+    ps = engine.paulisum(PackedTerms(packed.n, x, z, ny, np.zeros_like(cim), cim))
+    scale = max(1, int(math.ceil(abs(theta) * float(np.abs(cim).sum()) / 0.5)))
+    for _ in range(scale):
+        engine.copy_buffer(BUF_SIGMA, BUF_PSI)
+        for m in range(1, 41):
+            engine.apply_paulisum(ps, dst=BUF_WORK, src=BUF_SIGMA)                 # next = A term
+            engine.axpby(BUF_SIGMA, BUF_WORK, float(theta) / (scale * m), 0.0)    # term = (theta / (s m)) next
+            engine.axpby(BUF_PSI, BUF_SIGMA, 1.0, 1.0)                            # psi += term
+            if engine.norm2(BUF_SIGMA) < 1e-34:
+                break
+
+
 # ---- one rank per process ------------------------------------------------------------------------------
 class ShardedEngine(Engine):
     """One rank of a sharded state (one process per GPU).  Every rank must issue the same sequence of calls."""
@@ -157,7 +188,10 @@ class ShardedEngine(Engine):
         rank = dist.get_rank(group)
         super().__init__(n_qubits, device, n_global=n_global_for(world), rank=rank)
         self.world = world
-        self._attached = [BUF_PSI] + ([BUF_SIGMA] if attach_scratch else [])
+        from .engine import BUF_WORK
+        # sigma (ADAPT sweeps) when two shards fit one GPU; the work vector too (Taylor exponential of a non-commuting
+        # generator: three vectors) when three do -- 2^31 amplitudes per rank, i.e. 34 qubits on 8 GPUs
+        self._attached = [BUF_PSI] + ([BUF_SIGMA] if attach_scratch else []) + ([BUF_WORK] if attach_scratch and self.n_local <= 31 else [])
         self._connect(self._attached)
 
     def _connect(self, bufs):
@@ -208,6 +242,17 @@ class ShardedEngine(Engine):
     def apply_paulisum(self, ps, dst=BUF_SIGMA, src=BUF_PSI):
         self._need_scratch("sigma = H psi")
         return super().apply_paulisum(ps, dst, src)
+
+    def apply_exp(self, packed: PackedTerms, theta: float):
+        """exp(theta A) on the sharded state (commuting strings: rotations; else the host-driven Taylor series)."""
+        from .engine import BUF_WORK
+        if BUF_WORK not in self._attached:
+            keep = (packed.cre != 0) | (packed.cim != 0)
+            from ._hotpath import _strings_commute
+            if not _strings_commute(packed.x[keep], packed.z[keep]):
+                raise _lib.VQEError("exact exponential of a non-commuting generator needs three state vectors per rank, "
+                                    "which do not fit for shards of 2^%d amplitudes" % self.n_local)
+        taylor_exp(self, packed, theta)
 
     def barrier(self):
         _lib.check(self._lib.vqe_shard_barrier(self.handle))
@@ -307,6 +352,17 @@ class ShardGroup:
     def synchronize(self):
         for e in self.ranks:
             e.synchronize()
+
+    def copy_buffer(self, dst, src):
+        for e in self.ranks:
+            e.copy_buffer(dst, src)
+
+    def axpby(self, dst, x, alpha=1.0, beta=1.0):
+        for e in self.ranks:
+            e.axpby(dst, x, alpha, beta)
+
+    def apply_exp(self, packed: PackedTerms, theta: float):
+        taylor_exp(self, packed, theta)
 
     # -- operations ----------------------------------------------------------------------------------------
     def apply_rotations(self, x, z, ny, angles):

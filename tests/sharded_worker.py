@@ -75,6 +75,16 @@ def main():
     assert isinstance(engine_mod.get_engine(n2), sh.ShardedEngine)
     e_orc = orc.ucc_action(th, ham2, gens, hf2)
     assert abs(e_api - e_orc) < 1e-10, (e_api, e_orc)
+    # exact exponential of a non-commuting generator on the sharded state (sigma and work vectors attached over IPC)
+    from openvqe_b200.lowering import pack_operator
+    from tests.helpers import random_antihermitian
+    eng2 = engine_mod.get_engine(n2)
+    psi2 = random_state(rng, n2)
+    eng2.set_state(psi2)
+    gen_nc = random_antihermitian(rng, n2, 5, max_weight=4)
+    eng2.apply_exp(pack_operator(gen_nc), 0.9)
+    ref2 = orc.fermionic_adapt_state(psi2, [gen_nc], [0.9])
+    assert np.max(np.abs(eng2.get_state() - ref2)) < 1e-11
     sh.disable()
     dist.barrier()
     if rank == 0:

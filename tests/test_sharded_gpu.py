@@ -246,6 +246,26 @@ def test_gather_form_chunks_prefetched_under_the_previous_chunk(gpu_required, mo
     assert sum(e.gather_bytes() for e in grp.ranks) > 0     # the program did take gather-form passes
 
 
+@pytest.mark.parametrize("n,g", [(8, 1), (11, 2), (13, 3)])
+def test_sharded_exact_exponential_of_noncommuting_generators(groups, n, g):
+    """Fermionic prepare_adapt_state (reference fermionic_adapt_vqe.py:12-38, expm_multiply of each whole generator) on a
+    sharded state: generators with strings on global qubits that do not commute (host-driven Taylor series, three
+    vectors per rank, peer passes between sigma and work) and commuting ones (rotations), against scipy."""
+    from openvqe_b200.lowering import pack_operator
+    rng = np.random.default_rng(1000 + n)
+    grp = groups(n, g)
+    psi = random_state(rng, n)
+    gens = [random_antihermitian(rng, n, 5, max_weight=4) for _ in range(3)]
+    gens.append(Ham(n, [T(0.7j, "XY", [0, n - 1]), T(-0.7j, "YX", [0, n - 1])]))   # commuting pair on a global qubit
+    thetas = [0.3, -0.8, 1.7, 0.4]
+    grp.set_state(psi)
+    for op, th in zip(gens, thetas):
+        grp.apply_exp(pack_operator(op), th)
+    ref = orc.fermionic_adapt_state(psi, gens, thetas)
+    assert np.max(np.abs(grp.get_state() - ref)) < 1e-11
+    assert abs(grp.norm2() - 1.0) < 1e-11
+
+
 def test_c5_synthetic_sharded_equals_unsharded_at_22_qubits(gpu_required):
     """Size-independent property at a size the oracle cannot do: 8 virtual ranks vs one context, same energy."""
     from openvqe_b200.engine import Engine
