@@ -792,6 +792,7 @@ def run_c5(args, rank, world, local_rank, dist=None, as_dict=False):
     eng.profile(False)
     prof = [(max_over_ranks(m), c) for m, c in prof]
     gather_bytes = eng.gather_bytes()
+    n_swaps, swap_bytes = eng.relabel_stats()
     # ---- e2e: the same evaluations through the reference-facing call EnergyUCC.ucc_action with host objects ------
     # (every rank makes the same call; the sharded engine is the process-wide engine of this register size)
     e2e = None
@@ -865,10 +866,20 @@ def run_c5(args, rank, world, local_rank, dist=None, as_dict=False):
         # closure names are read (inbound only, nothing is written remotely): bytes counted by the library per launch of
         # k_gather_need.  The figure below is inbound bytes per rank over the time of ALL peer-pass launches (gather
         # kernels and the local passes that follow them included), i.e. a lower bound of the link rate while busy.
+        # With qubit relabelling (default) a rotation never runs as a peer pass: a qubit the program flips is moved out of
+        # its global index bit by ONE exchange of half a shard (each rank reads a quarter of a shard from its partner and
+        # writes a quarter into it); the planner's peer-pass counts then describe the program WITHOUT relabelling.
+        relabelled = n_swaps > 0 or os.environ.get("VQE_RELABEL", "1") != "0"
+        planned = {"local": n_local_pass, "peer": n_peer_pass, "peer_in_gather_form": n_gather_pass}
+        if relabelled:
+            n_peer_pass = n_gather_pass = 0
+            n_local_pass = loc_n / evals
         n_exch = n_peer_pass - n_gather_pass
         gather_in = float(gather_bytes) if gather_bytes is not None else None
-        inbound = (gather_in if gather_in is not None else 0.0) + S_local * n_exch * evals
-        nvlink = {"peer_passes_per_eval": n_peer_pass, "gather_form_passes_per_eval": n_gather_pass,
+        inbound = (gather_in if gather_in is not None else 0.0) + S_local * n_exch * evals + float(swap_bytes)
+        nvlink = {"qubit_swaps_per_eval": n_swaps / evals, "swap_bytes_read_per_eval_per_rank": swap_bytes / evals,
+                  "rotation_passes_without_relabelling": planned,
+                  "peer_passes_per_eval": n_peer_pass, "gather_form_passes_per_eval": n_gather_pass,
                   "exchange_form_passes_per_eval": n_exch, "peer_launches_per_eval": peer_n / evals,
                   "peer_ms_per_eval": peer_ms / evals,
                   "gathered_bytes_per_eval_per_rank": gather_in / evals if gather_in is not None else None,
@@ -883,7 +894,8 @@ def run_c5(args, rank, world, local_rank, dist=None, as_dict=False):
                        % (n, " + %d FD gradient component(s)" % grad_components if grad_components else "",
                           n_rot, len(ham["x"]), ham["n_groups"], world, g),
            "qubits": n, "shard_bytes": S_local, "l2_policy": "shard (%.0f GB) larger than L2" % (S_local / 1e9),
-           "parallelism": "state sharded, peer passes over NVLink" if world > 1 else "1 GPU",
+           "parallelism": ("state sharded; qubit swaps (half a shard over NVLink each) keep the rotation passes local, "
+                           "expectation peer passes over NVLink") if world > 1 else "1 GPU",
            "rotation_passes": {"local": n_local_pass, "peer": n_peer_pass, "peer_in_gather_form": n_gather_pass},
            "expectation_passes": {"local": exl_n / evals, "peer": exp_n / evals}}
     body = {"value": evals / (ms / 1e3), "unit": "evals/s", "seconds_per_energy_evaluation": ms / 1e3 / evals,

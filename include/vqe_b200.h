@@ -187,6 +187,11 @@ int vqe_shard_info(const vqe_ctx* ctx, int* n_global, int* rank, int* n_local);
 int vqe_shard_export(vqe_ctx* ctx, int what, void* handle_out /* VQE_IPC_HANDLE_BYTES */);
 int vqe_shard_attach_ipc(vqe_ctx* ctx, int peer_rank, int what, const void* handle);
 int vqe_shard_attach_local(vqe_ctx* ctx, vqe_ctx* peer);
+/* Qubit relabelling of a sharded state (no counterpart in the reference): vqe_apply_pauli_rotations moves a qubit that its
+ * rotations flip out of a global (rank) index bit into a local one -- one exchange of half a shard over NVLink per move,
+ * chosen by Belady's rule over the program -- instead of a peer pass per rotation; the relabelling is internal (masks are
+ * always given in the caller's labelling).  Statistics: moves executed and bytes this rank read from partners in them. */
+int vqe_relabel_stats(vqe_ctx* ctx, uint64_t* swaps, uint64_t* swap_bytes, int reset);
 int vqe_shard_barrier(vqe_ctx* ctx); /* device-side barrier over all ranks, enqueued on the stream */
 int vqe_shard_status(vqe_ctx* ctx);  /* VQE_ERR_CUDA after a barrier timed out (a peer died) */
 

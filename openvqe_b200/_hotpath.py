@@ -111,10 +111,12 @@ def apply_gate_list(engine, gates):
     engine.apply_gates(kinds, q0, q1, ang)
 
 
-def prepare_quccsd_state(engine, n, hf_init_sp, cluster_ops, theta, use_tables=True):
+def prepare_quccsd_state(engine, n, hf_init_sp, cluster_ops, theta, use_tables=True, global_phase=True):
     """|psi> of the gate-defined QUCCSD ansatz (reference get_energy_qucc.py:38-51).  Every excitation template is
     applied as ONE tabulated plane rotation (the exact unitary of its gate list, see common_files/circuit.py); if
-    some excitation is not of that form, or touches a global qubit of a sharded state, the gate list is executed."""
+    some excitation is not of that form, or touches a global qubit of a sharded state, the gate list is executed.
+    ``global_phase=False`` leaves out the accumulated phase e^{i pi/4 * n_singles} of the single-excitation templates: an
+    expectation value does not see it, and without it the state stays purely real (real layout, real kernels)."""
     list_exci = [list(op.terms[0].qbits) for op in cluster_ops]
     if len(theta) < len(list_exci):
         raise IndexError("list index out of range")  # as the reference's list_theta[i] (circuit.py:95-106)
@@ -132,7 +134,7 @@ def prepare_quccsd_state(engine, n, hf_init_sp, cluster_ops, theta, use_tables=T
     x, offs, pat, cosv, sinv, phase = ops
     engine.set_basis_state(hf_index(n, hf_init_sp))
     engine.apply_plane_rotations(x, offs, pat, cosv, sinv)
-    if phase != 1.0:
+    if phase != 1.0 and global_phase:
         engine.scale_state(phase)
 
 
@@ -140,7 +142,7 @@ def quccsd_energy(theta, hamiltonian_sp, cluster_ops, hf_init_sp, device=None):
     """E(theta) of the gate-defined QUCCSD ansatz (reference get_energy_qucc.py:11-56)."""
     n = hamiltonian_sp.nbqbits
     engine = get_engine(n, device)
-    prepare_quccsd_state(engine, n, hf_init_sp, cluster_ops, theta)
+    prepare_quccsd_state(engine, n, hf_init_sp, cluster_ops, theta, global_phase=False)
     return float(engine.expectation(engine.paulisum(hamiltonian_sp)).real)
 
 

@@ -34,6 +34,8 @@
 
 #include <algorithm>
 #include <string>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "vqe_b200.h"
@@ -2358,6 +2360,13 @@ struct vqe_ctx {
     // the buffer in place first (ensure_complex); real_layout implies psi_real.
     bool real_layout = false;
     bool real_layout_ok = false;            // VQE_REAL_LAYOUT (default on) and an unsharded context
+    // QUBIT RELABELLING of a sharded state (buffer 0 only): logical index bit b of the caller's masks lives at physical index
+    // bit perm[b] of the shards.  Identity after vqe_set_basis_state / vqe_set_state; the rotation entry point swaps a global
+    // with a local bit (k_swap_global_local: half a shard over NVLink, once) instead of running every later rotation that
+    // flips that qubit as a peer pass.  Entry points that need the caller's labelling undo the swaps first.
+    uint8_t perm[64];
+    std::vector<std::pair<int, int>> swap_history;  // (global slot, local slot) of every swap since the last reset
+    uint64_t n_swaps = 0, swap_bytes = 0;   // statistics: swaps executed, bytes this rank read from its partners in swaps
     PlanCache* plan_cache = nullptr;        // see rotations_impl
     double2* gstage[2] = {nullptr, nullptr};  // staging buffers of gather-form peer passes (two: chunk k + 1 is fetched under chunk k)
     size_t gstage_cap[2] = {0, 0};            // in amplitudes
@@ -2569,6 +2578,7 @@ static int create_ctx(vqe_ctx** out, int n_qubits, int n_global, int rank, int d
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    for (int b = 0; b < 64; ++b) c->perm[b] = (uint8_t)b;
     c->tile_bits = env_int("VQE_TILE_BITS", 12);
     // low-bit floor of the tiles: tensor-map (TMA) tile loads make short contiguous runs cheap, so an unsharded context only
     // insists on 16 amplitudes (256 bytes; 128 in the real layout) and leaves 8 tile bits to the planner; the peer passes of
@@ -2666,6 +2676,26 @@ extern "C" void vqe_destroy(vqe_ctx* c) {
 //   * one process driving all ranks (tests on one GPU, or a single-process multi-GPU run): peers are attached
 //     by pointer and the vqe_group_* entry points order the ranks' streams with CUDA events.
 // ------------------------------------------------------------------------------------------
+// Exchange of a GLOBAL with a LOCAL index bit between the shards of ranks lo (global bit 0) and hi (global bit 1): lo's
+// amplitudes with local bit L = 1 trade places with hi's amplitudes with L = 0 (all other bits equal).  Pair k of the
+// n_amp / 2 pairs: i0 = k with a zero inserted at bit L.  The two ranks of a pair each take half of the pairs, so every GPU
+// reads and writes a quarter of a shard remotely: half a shard per NVLink direction.  L >= 2: four consecutive pairs per
+// thread are contiguous (64 bytes per access stream, eight independent 16-byte loads in flight).
+__global__ void __launch_bounds__(256) k_swap_global_local(double2* __restrict__ lo, double2* __restrict__ hi, uint32_t L,
+                                                           uint64_t first, uint64_t count) {
+    const uint64_t lowmask = (1ull << L) - 1ull, lbit = 1ull << L;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4ull;
+    for (uint64_t k = first + (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 4ull; k < first + count; k += stride) {
+        const uint64_t i0 = ((k & ~lowmask) << 1) | (k & lowmask);
+        double2* pa = lo + (i0 | lbit);
+        double2* pb = hi + i0;
+        const double2 a0 = pa[0], a1 = pa[1], a2 = pa[2], a3 = pa[3];
+        const double2 b0 = pb[0], b1 = pb[1], b2 = pb[2], b3 = pb[3];
+        pa[0] = b0; pa[1] = b1; pa[2] = b2; pa[3] = b3;
+        pb[0] = a0; pb[1] = a1; pb[2] = a2; pb[3] = a3;
+    }
+}
+
 __global__ void k_flag_barrier(uint64_t* const* __restrict__ peer_flags, volatile uint64_t* my_flags, int rank,
                                int world, unsigned long long epoch, int* err) {
     const int p = threadIdx.x;
@@ -2869,6 +2899,106 @@ static int make_geom(const vqe_ctx* c, const TilePlan& tp, const uint64_t* d_sca
     if (!sh.p0 || !sh.p1)
         return fail(VQE_ERR_INVALID, "rank %d: buffer %d of rank %d is not attached (vqe_shard_attach_*)", c->rank, buf, partner);
     return VQE_OK;
+}
+
+// ---- qubit relabelling of a sharded state (see vqe_ctx::perm) ------------------------------------------------------
+static inline bool perm_is_identity(const vqe_ctx* c) {
+    for (int b = 0; b < c->n; ++b)
+        if (c->perm[b] != b) return false;
+    return true;
+}
+static inline void perm_reset(vqe_ctx* c) {
+    for (int b = 0; b < 64; ++b) c->perm[b] = (uint8_t)b;
+    c->swap_history.clear();
+}
+static inline uint64_t perm_mask(const uint8_t* perm, uint64_t m) {
+    uint64_t o = 0;
+    while (m) {
+        const int b = __builtin_ctzll(m);
+        o |= 1ull << perm[b];
+        m &= m - 1;
+    }
+    return o;
+}
+// every rank of the state this context belongs to, when they live in this process (vqe_shard_attach_local); else the
+// context alone (one process per GPU: every process issues the same calls)
+static RankSet group_of(vqe_ctx* c) {
+    RankSet rs;
+    bool local_group = c->world > 1;
+    for (int r = 0; r < c->world && local_group; ++r)
+        if (r != c->rank && !c->peer_ctx[r]) local_group = false;
+    if (!local_group) {
+        rs.r.push_back(c);
+        return rs;
+    }
+    for (int r = 0; r < c->world; ++r) rs.r.push_back(r == c->rank ? c : c->peer_ctx[r]);
+    return rs;
+}
+// swap the contents of physical index bits gslot (a rank bit, >= nl) and lslot (a local bit) of buffer 0 on all ranks
+static int swap_global_local(RankSet& rs, int gslot, int lslot) {
+    vqe_ctx* c0 = rs.r[0];
+    if (gslot < c0->nl || gslot >= c0->n || lslot < 2 || lslot >= c0->nl) return fail(VQE_ERR_INVALID, "bad qubit swap %d <-> %d", gslot, lslot);
+    int rc = rank_barrier(rs);  // everything issued so far has finished on both shards
+    if (rc) return rc;
+    const int gbit = 1 << (gslot - c0->nl);
+    for (vqe_ctx* c : rs.r) {
+        CK(cudaSetDevice(c->device));
+        rc = ensure_buf(c, VQE_BUF_PSI);
+        if (rc) return rc;
+        const int partner = c->rank ^ gbit;
+        const int lo = std::min(c->rank, partner), hi = std::max(c->rank, partner);
+        double2* plo = shard_ptr(c, VQE_BUF_PSI, lo);
+        double2* phi = shard_ptr(c, VQE_BUF_PSI, hi);
+        if (!plo || !phi) return fail(VQE_ERR_INVALID, "rank %d: the state of rank %d is not attached (vqe_shard_attach_*)", c->rank, partner);
+        const uint64_t n_pairs = c->n_amp >> 1, half = n_pairs >> 1;
+        const uint64_t first = c->rank == lo ? 0 : half, count = c->rank == lo ? half : n_pairs - half;
+        const int blocks = (int)std::min<uint64_t>((count / 4 + 255) / 256, (uint64_t)c->sm_count * 8);
+        ProfScope prof(c, 4);
+        k_swap_global_local<<<std::max(1, blocks), 256, 0, c->stream>>>(plo, phi, (uint32_t)lslot, first, count);
+        c->launches++;
+        c->n_swaps++;
+        c->swap_bytes += count * sizeof(double2);
+        CK(cudaGetLastError());
+    }
+    rc = rank_barrier(rs);  // the exchange is complete before anyone touches its shard again
+    if (rc) return rc;
+    for (vqe_ctx* c : rs.r) {
+        int a = -1, b = -1;
+        for (int q = 0; q < c->n; ++q) {
+            if (c->perm[q] == gslot) a = q;
+            if (c->perm[q] == lslot) b = q;
+        }
+        c->perm[a] = (uint8_t)lslot;
+        c->perm[b] = (uint8_t)gslot;
+        c->swap_history.push_back({gslot, lslot});
+    }
+    return VQE_OK;
+}
+// Undo all swaps (in reverse order: a swap is its own inverse): afterwards buffer 0 is labelled as the caller labels it.
+static int restore_labelling(RankSet& rs) {
+    vqe_ctx* c = rs.r[0];
+    if (c->world == 1) return VQE_OK;
+    while (!c->swap_history.empty()) {
+        const std::pair<int, int> sw = c->swap_history.back();
+        int rc = swap_global_local(rs, sw.first, sw.second);  // pushes the swap again ...
+        if (rc) return rc;
+        for (vqe_ctx* r : rs.r) {                                // ... so two entries go
+            r->swap_history.pop_back();
+            r->swap_history.pop_back();
+        }
+    }
+    if (!perm_is_identity(c)) return fail(VQE_ERR_INVALID, "qubit relabelling could not be undone");
+    return VQE_OK;
+}
+static int need_caller_labelling(vqe_ctx* c) {
+    if (c->world == 1 || c->swap_history.empty()) return VQE_OK;
+    RankSet rs = group_of(c);
+    return restore_labelling(rs);
+}
+static int need_caller_labelling(RankSet& rs) {
+    if (rs.r.empty() || !rs.r[0] || rs.r[0]->world == 1 || rs.r[0]->swap_history.empty()) return VQE_OK;
+    if (rs.r.size() == 1) return need_caller_labelling(rs.r[0]);
+    return restore_labelling(rs);
 }
 
 // ---- tensor maps ------------------------------------------------------------------------------------------
@@ -3120,6 +3250,14 @@ extern "C" int vqe_peer_bytes(vqe_ctx* c, uint64_t* gathered, int reset) {
     return VQE_OK;
 }
 
+extern "C" int vqe_relabel_stats(vqe_ctx* c, uint64_t* swaps, uint64_t* swap_bytes, int reset) {
+    if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
+    if (swaps) *swaps = c->n_swaps;
+    if (swap_bytes) *swap_bytes = c->swap_bytes;
+    if (reset) c->n_swaps = c->swap_bytes = 0;
+    return VQE_OK;
+}
+
 static int grid_1d(const vqe_ctx* c, uint64_t n_amp, int threads) {
     uint64_t want = (n_amp + threads - 1) / threads;
     uint64_t cap = (uint64_t)c->sm_count * 8;
@@ -3138,6 +3276,7 @@ extern "C" int vqe_set_basis_state(vqe_ctx* c, uint64_t index) {
         k_zero_set<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[0], c->n_amp, local);
     c->real_layout = c->real_layout_ok;
     c->psi_real = true;
+    perm_reset(c);  // a fresh state is labelled as the caller labels it
     c->launches++;
     CK(cudaGetLastError());
     return VQE_OK;
@@ -3149,7 +3288,10 @@ extern "C" int vqe_set_state(vqe_ctx* c, int b, const double* re_im) {
     int rc = ensure_buf(c, b);
     if (rc) return rc;
     c->h2d_bytes += c->n_amp * sizeof(double2);
-    if (b == VQE_BUF_PSI) c->psi_real = c->real_layout = false;  // overwritten as a whole, in complex form
+    if (b == VQE_BUF_PSI) {
+        c->psi_real = c->real_layout = false;  // overwritten as a whole, in complex form, in the caller's labelling
+        perm_reset(c);
+    }
     CK(cudaMemcpyAsync(c->buf[b], re_im, c->n_amp * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return VQE_OK;
@@ -3159,6 +3301,10 @@ extern "C" int vqe_get_state(vqe_ctx* c, int b, double* re_im) {
     CK(cudaSetDevice(c->device));
     int rc = ensure_buf(c, b);
     if (rc) return rc;
+    if (b == VQE_BUF_PSI) {
+        rc = need_caller_labelling(c);
+        if (rc) return rc;
+    }
     if (b == VQE_BUF_PSI && c->real_layout) {
         // real layout: the n_amp real parts are copied into the upper half of the caller's array and interleaved there
         double* tmp = re_im + c->n_amp;
@@ -3185,9 +3331,16 @@ extern "C" int vqe_copy_buffer(vqe_ctx* c, int dst, int src) {
     rc = ensure_buf(c, src);
     if (rc) return rc;
     if (dst == src) return VQE_OK;
+    if (src == VQE_BUF_PSI) {
+        rc = need_caller_labelling(c);
+        if (rc) return rc;
+    }
     rc = ensure_complex(c, src);
     if (rc) return rc;
-    if (dst == VQE_BUF_PSI) c->psi_real = c->real_layout = false;
+    if (dst == VQE_BUF_PSI) {
+        c->psi_real = c->real_layout = false;
+        perm_reset(c);  // overwritten with a vector in the caller's labelling
+    }
     CK(cudaMemcpyAsync(c->buf[dst], c->buf[src], c->n_amp * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
     return VQE_OK;
 }
@@ -3198,6 +3351,7 @@ extern "C" int vqe_buffer_ptr(vqe_ctx* c, int b, void** p, uint64_t* n_amp) {
     int rc = ensure_buf(c, b);
     if (rc) return rc;
     rc = ensure_complex(c, b);
+    if (rc == VQE_OK && b == VQE_BUF_PSI) rc = need_caller_labelling(c);
     if (rc) return rc;
     *p = c->buf[b];
     if (b == VQE_BUF_PSI) c->psi_real = false;  // the caller may write through the pointer
@@ -3967,7 +4121,7 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
             const uint64_t cap_amp = std::max<uint64_t>(per_tile, std::min<uint64_t>(
                 (uint64_t)env_int("VQE_GATHER_STAGE_MB", 8192) * (1ull << 20) / sizeof(double2), (rs.r[0]->n_amp / 16) + per_tile));
             const uint64_t chunk_tiles = std::max<uint64_t>(1, std::min<uint64_t>(ps.tp.n_tiles, cap_amp / per_tile));
-            const bool overlap = env_int("VQE_GATHER_OVERLAP", 1) != 0 && chunk_tiles < ps.tp.n_tiles;
+            const bool overlap = env_int("VQE_GATHER_OVERLAP", 0) != 0 && chunk_tiles < ps.tp.n_tiles;  // measured slower on 2 x B200 (profiles/r2_summary.md): off
             for (vqe_ctx* c : rs.r) {
                 CK(cudaSetDevice(c->device));
                 for (int sb = 0; sb < (overlap ? 2 : 1); ++sb) {
@@ -4144,7 +4298,7 @@ static bool refresh_plan(OpPlan& plan, const std::vector<double>& ang, const std
     return true;
 }
 
-static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const uint64_t* zmask, const int32_t* ny,
+static int rotations_core(RankSet& rs, int n_rot, const uint64_t* xmask, const uint64_t* zmask, const int32_t* ny,
                           const double* angle, int buf = VQE_BUF_PSI) {
     int rc0 = check_rankset(rs);
     if (rc0) return rc0;
@@ -4219,6 +4373,82 @@ static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const u
         pc->valid = true;
     }
     return launch_plan(rs, pc->plan, buf);
+}
+// Rotations on a SHARDED state with qubit relabelling.  A rotation whose X-mask touches a global slot would run as a peer
+// pass -- and so would every later rotation that flips the same qubit.  Instead the logical bit is moved into a local
+// slot ONCE (swap_global_local: half a shard over NVLink, about the cost of one peer pass) and the local slot that gives
+// way is the one whose logical bit is flipped furthest in the future (Belady's rule over the rest of the program; slots
+// below VQE_RELABEL_FLOOR = 12 keep their bits so that swaps move contiguous runs of 64 KiB).  The masks of the following rotations
+// are translated through the permutation; the permutation stays in force after the call (vqe_expectation evaluates a
+// permuted twin of the Pauli sum; anything else that needs the caller's labelling undoes the swaps).  For the random C5
+// program on 8 GPUs: 19 swaps instead of 68 peer passes.
+static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const uint64_t* zmask, const int32_t* ny,
+                          const double* angle, int buf = VQE_BUF_PSI) {
+    int rc = check_rankset(rs);
+    if (rc) return rc;
+    vqe_ctx* c = rs.r[0];
+    if (c->world == 1 || buf != VQE_BUF_PSI) return rotations_core(rs, n_rot, xmask, zmask, ny, angle, buf);
+    if (n_rot < 0 || (n_rot > 0 && (!xmask || !zmask || !ny || !angle))) return fail(VQE_ERR_INVALID, "null array");
+    const int RELABEL_FLOOR = std::max(2, std::min(env_int("VQE_RELABEL_FLOOR", 12), c->nl - 4));
+    const bool relabel = env_int("VQE_RELABEL", 1) != 0 && c->nl >= 8;
+    if (!relabel) {
+        rc = need_caller_labelling(rs);
+        if (rc) return rc;
+        return rotations_core(rs, n_rot, xmask, zmask, ny, angle, buf);
+    }
+    const int n = c->n, nl = c->nl;
+    const uint64_t full = (1ull << n) - 1ull;
+    // for every logical bit: the rotations that flip it, ascending (zero-angle rotations are identities)
+    std::vector<std::vector<int>> uses(n);
+    for (int k = 0; k < n_rot; ++k) {
+        if ((xmask[k] | zmask[k]) & ~full) return fail(VQE_ERR_INVALID, "rotation %d: mask has bits >= n_qubits", k);
+        if (angle[k] == 0.0) continue;
+        for (uint64_t m = xmask[k]; m; m &= m - 1) uses[__builtin_ctzll(m)].push_back(k);
+    }
+    std::vector<size_t> cursor(n, 0);
+    auto next_use = [&](int bit, int k) {
+        size_t& p = cursor[bit];
+        while (p < uses[bit].size() && uses[bit][p] <= k) ++p;
+        return p < uses[bit].size() ? uses[bit][p] : INT32_MAX;
+    };
+    std::vector<uint64_t> tx, tz;
+    std::vector<int32_t> tny;
+    std::vector<double> tang;
+    auto flush = [&]() -> int {
+        if (tx.empty()) return VQE_OK;
+        int rcf = rotations_core(rs, (int)tx.size(), tx.data(), tz.data(), tny.data(), tang.data(), buf);
+        tx.clear(); tz.clear(); tny.clear(); tang.clear();
+        return rcf;
+    };
+    const uint64_t gmask = ((1ull << c->g) - 1ull) << nl;
+    for (int k = 0; k < n_rot; ++k) {
+        if (angle[k] == 0.0) continue;
+        uint64_t px = perm_mask(c->perm, xmask[k]);
+        while (px & gmask) {
+            // the logical bit in the lowest touched global slot moves to the local slot whose bit is needed last
+            const int gslot = __builtin_ctzll(px & gmask);
+            int inv[64];
+            for (int q = 0; q < n; ++q) inv[c->perm[q]] = q;
+            int best = -1, best_use = -1;
+            for (int slot = nl - 1; slot >= RELABEL_FLOOR; --slot) {
+                const int lb = inv[slot];
+                if ((xmask[k] >> lb) & 1ull) continue;
+                const int nu = next_use(lb, k);
+                if (nu > best_use) { best_use = nu; best = slot; }
+            }
+            if (best < 0) break;  // (cannot happen: a rotation flips at most tile_bits qubits) -> peer pass
+            rc = flush();
+            if (rc) return rc;
+            rc = swap_global_local(rs, gslot, best);
+            if (rc) return rc;
+            px = perm_mask(c->perm, xmask[k]);
+        }
+        tx.push_back(px);
+        tz.push_back(perm_mask(c->perm, zmask[k]));
+        tny.push_back(ny[k]);
+        tang.push_back(angle[k]);
+    }
+    return flush();
 }
 extern "C" int vqe_apply_pauli_rotations(vqe_ctx* c, int n_rot, const uint64_t* xmask, const uint64_t* zmask,
                                          const int32_t* ny, const double* angle) {
@@ -4321,6 +4551,10 @@ extern "C" int vqe_apply_plane_rotations(vqe_ctx* c, int n_ops, const uint64_t* 
                                          const uint64_t* pattern, const double* cosv, const double* sinv) {
     if (!c) return fail(VQE_ERR_INVALID, "ctx is null");
     if (n_ops < 0 || (n_ops > 0 && (!xmask || !tab_offsets))) return fail(VQE_ERR_INVALID, "null array");
+    {
+        int rcl = need_caller_labelling(c);
+        if (rcl) return rcl;
+    }
     const uint64_t full = (1ull << c->n) - 1ull;
     std::vector<HostOp> ops;
     ops.reserve(n_ops);
@@ -4372,6 +4606,7 @@ extern "C" int vqe_axpby(vqe_ctx* c, int dst, int x, double a_re, double a_im, d
     if (rc) return rc;
     rc = ensure_complex(c, dst);
     if (rc == VQE_OK) rc = ensure_complex(c, x);
+    if (rc == VQE_OK && (dst == VQE_BUF_PSI) != (x == VQE_BUF_PSI)) rc = need_caller_labelling(c);
     if (rc) return rc;
     if (dst == VQE_BUF_PSI) c->psi_real = false;
     k_axpby<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[dst], c->buf[x], c->n_amp, a_re, a_im, b_re, b_im);
@@ -4394,6 +4629,7 @@ extern "C" int vqe_group_apply_pauli_rotations(vqe_ctx* const* ranks, int n_rank
 static int gates_impl(RankSet& rs, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
                       const double* angle) {
     int rc0 = check_rankset(rs);
+    if (rc0 == VQE_OK) rc0 = need_caller_labelling(rs);
     if (rc0) return rc0;
     vqe_ctx* c = rs.r[0];
     if (n_gates < 0 || (n_gates > 0 && (!kind || !q0))) return fail(VQE_ERR_INVALID, "null array");
@@ -4467,7 +4703,8 @@ struct PSPass {
     bool lean = false;
     bool swz = false;                   // the entries' per-j offsets and X-masks are stored in the 128-byte-swizzled layout
     std::vector<DevFlat2> flats2;       // entries, group after group
-    std::vector<uint32_t> goff;         // n_lean_groups + 1 offsets into flats2 (sigma = O psi walks the groups)
+    std::vector<uint32_t> goff;         // n_lean_groups + 1 entry counts (statistics; the entries are re-ordered into batches)
+    std::vector<uint32_t> boff;         // n_batches + 1 offsets into flats2: sigma = O psi walks the batches (see batch_lean_entries)
     std::vector<double> addtab;         // T_lo[32] + T_hi[...] of every additive pattern
     std::vector<DevAddPat> addpat;
     std::vector<DevAddOut> addout;
@@ -4480,15 +4717,19 @@ struct PSPass {
     DevAddPat* d_addpat = nullptr;
     DevAddOut* d_addout = nullptr;
 };
-struct vqe_paulisum {
-    int n = 0, nl = 0, device = 0, n_groups = 0;
-    std::vector<PSPass> passes;
-};
-
 struct HTerm {
     uint64_t x, z;
     int ny;
     double cr, ci;
+};
+struct vqe_paulisum {
+    int n = 0, nl = 0, device = 0, n_groups = 0;
+    std::vector<PSPass> passes;
+    // the strings as given (caller's labelling) and the planner settings: a relabelled sharded state (vqe_ctx::perm) is
+    // evaluated with a twin of the sum whose masks are translated through the permutation, built on first use
+    std::vector<HTerm> terms;
+    int tile_bits = 12, low_bits = 5, threads = 512;
+    std::map<std::string, vqe_paulisum*> variants;
 };
 
 static void mul_i_pow(double& r, double& i, int k) {
@@ -4650,6 +4891,60 @@ static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& te
     p.addout.insert(p.addout.end(), outs.begin(), outs.end());
     p.lean_terms += terms.size();
     return true;
+}
+
+// sigma = O psi adds  G(l) psi[l ^ x]  into an accumulator tile; entries whose (a, b) element sets are disjoint can be worked
+// on between the same two barriers without any thread touching another's accumulator element.  The entries of a pass are
+// therefore re-ordered into conflict-free BATCHES (first fit, in entry order: deterministic), instead of one barrier
+// interval per X-mask group: a group has ~2 entries = 563 items for 512 threads (55 % of the slots busy), a batch holds
+// several, and there are fewer barriers.  The expectation kernel is indifferent to the entry order.
+static void batch_lean_entries(PSPass& p) {
+    const size_t ne = p.flats2.size();
+    p.boff.clear();
+    p.boff.push_back(0);
+    if (ne == 0) return;
+    const uint32_t ts = 1u << p.tp.tbits;
+    const size_t words = (ts + 63) / 64;
+    const uint32_t sw = p.swz ? 0x70u : 0u;
+    std::vector<std::vector<uint64_t>> touched(ne, std::vector<uint64_t>(words, 0));
+    for (size_t e = 0; e < ne; ++e) {
+        uint4 q[3];
+        memcpy(q, &p.flats2[e], sizeof(DevFlat2));
+        for (uint32_t lane = 0; lane < 32; ++lane) {
+            LeanUnit u;
+            lean_decode(q[0], q[1], q[2], lane, u);
+            for (uint32_t j = 0; j < 8; ++j) {
+                const uint32_t off = swz_off(u.v, sw) ^ u.o[j], offb = off ^ u.lx16;
+                touched[e][(off >> 4) >> 6] |= 1ull << ((off >> 4) & 63u);
+                touched[e][(offb >> 4) >> 6] |= 1ull << ((offb >> 4) & 63u);
+            }
+        }
+    }
+    const size_t max_batch = (size_t)std::max(1, env_int("VQE_APPLY_BATCH", 16));
+    std::vector<std::vector<size_t>> batches;
+    std::vector<std::vector<uint64_t>> used;
+    for (size_t e = 0; e < ne; ++e) {
+        size_t b = 0;
+        for (; b < batches.size(); ++b) {
+            if (batches[b].size() >= max_batch) continue;
+            bool clash = false;
+            for (size_t w = 0; w < words && !clash; ++w) clash = (used[b][w] & touched[e][w]) != 0;
+            if (!clash) break;
+        }
+        if (b == batches.size()) {
+            batches.emplace_back();
+            used.emplace_back(words, 0);
+        }
+        batches[b].push_back(e);
+        for (size_t w = 0; w < words; ++w) used[b][w] |= touched[e][w];
+    }
+    std::vector<DevFlat2> re;
+    re.reserve(ne);
+    for (const auto& bt : batches) {
+        for (size_t e : bt) re.push_back(p.flats2[e]);
+        p.boff.push_back((uint32_t)re.size());
+    }
+    p.flats2.swap(re);
 }
 
 // Tile bits of a pass, chosen greedily for COVERAGE: seed with `need`, repeatedly add the bit that completes the most
@@ -4841,7 +5136,10 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             for (size_t i = 0; i < lplans.size() && !done[g]; ++i)
                 if ((xs[g] & lfull & ~lplans[i].tp.tile_mask) == 0 && lower_lean_group(lpass[i], xs[g], grp[g])) done[g] = 1;
         for (size_t i = 0; i < lplans.size(); ++i)
-            if (!lpass[i].flats2.empty()) ps->passes.push_back(std::move(lpass[i]));
+            if (!lpass[i].flats2.empty()) {
+                batch_lean_entries(lpass[i]);
+                ps->passes.push_back(std::move(lpass[i]));
+            }
         remaining = 0;
         for (size_t g = 0; g < xs.size(); ++g) remaining += done[g] ? 0 : 1;
         (void)n_lean;
@@ -5212,7 +5510,7 @@ static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
                     rc = upload_vec(&p.d_flats2_rl, rl);
                 }
             }
-            if (rc == VQE_OK) rc = upload_vec(&p.d_goff, p.goff);
+            if (rc == VQE_OK) rc = upload_vec(&p.d_goff, p.boff);
             if (rc == VQE_OK) rc = upload_vec(&p.d_addtab, p.addtab);
             if (rc == VQE_OK) rc = upload_vec(&p.d_addpat, p.addpat);
             if (rc == VQE_OK) rc = upload_vec(&p.d_addout, p.addout);
@@ -5277,6 +5575,10 @@ extern "C" int vqe_paulisum_create(vqe_ctx* c, vqe_paulisum** out, int n_terms, 
     if (rc) return rc;
     vqe_paulisum* ps = new vqe_paulisum();
     ps->device = c->device;
+    if (c->world > 1) ps->terms = terms;  // kept for relabelled twins (sharded states only)
+    ps->tile_bits = c->tile_bits;
+    ps->low_bits = c->low_bits;
+    ps->threads = c->threads;
     rc = build_paulisum(ps, c->n, c->nl, c->tile_bits, c->low_bits, c->threads, std::move(terms));
     if (rc == VQE_OK) rc = upload_paulisum(c, ps);
     if (rc) {
@@ -5318,8 +5620,8 @@ extern "C" int vqe_plan_paulisum(int n_qubits, int n_global, int tile_bits, int 
         if (getenv("VQE_DEBUG_PLAN") && atoi(getenv("VQE_DEBUG_PLAN")) >= 3 && pp.lean) {
             size_t n_add = 0;
             for (const DevFlat2& fl : pp.flats2) n_add += fl.tab != 0xffffu;
-            fprintf(stderr, "[pspass] %zu LEAN groups %zu terms %zu entries %zu (additive %zu) addpat %zu addout %zu tab %zu lbits %d tbits %d\n", p,
-                    pp.goff.size() - 1, pp.lean_terms, pp.flats2.size(), n_add, pp.addpat.size(), pp.addout.size(), pp.addtab.size(),
+            fprintf(stderr, "[pspass] %zu LEAN groups %zu terms %zu entries %zu (additive %zu) batches %zu addpat %zu addout %zu tab %zu lbits %d tbits %d\n", p,
+                    pp.goff.size() - 1, pp.lean_terms, pp.flats2.size(), n_add, pp.boff.size() - 1, pp.addpat.size(), pp.addout.size(), pp.addtab.size(),
                     pp.tp.lbits, pp.tp.tbits);
         } else if (getenv("VQE_DEBUG_PLAN") && atoi(getenv("VQE_DEBUG_PLAN")) >= 3) {
             size_t n_flatg = 0, n_colg = 0, n_clsg = 0, cls_terms = 0, diag_terms = 0, col_items = 0, aflat_groups = 0, aterm = 0;
@@ -5468,8 +5770,53 @@ extern "C" int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int til
 extern "C" void vqe_paulisum_destroy(vqe_paulisum* ps) {
     if (!ps) return;
     cudaSetDevice(ps->device);
+    for (auto& kv : ps->variants) {
+        free_paulisum_device(kv.second);
+        delete kv.second;
+    }
     free_paulisum_device(ps);
     delete ps;
+}
+// the twin of `ps` for the current relabelling of context c (built, uploaded and cached on first use)
+static int paulisum_variant(vqe_ctx* c, const vqe_paulisum* ps, const vqe_paulisum** out) {
+    *out = ps;
+    if (c->world == 1 || perm_is_identity(c)) return VQE_OK;
+    if (ps->terms.empty() && !ps->passes.empty())
+        return fail(VQE_ERR_INVALID, "the Pauli sum was created on an unsharded context and cannot follow a relabelled state");
+    vqe_paulisum* root = const_cast<vqe_paulisum*>(ps);
+    const std::string key((const char*)c->perm, (size_t)c->n);
+    auto it = root->variants.find(key);
+    if (it != root->variants.end()) {
+        *out = it->second;
+        return VQE_OK;
+    }
+    std::vector<HTerm> terms = ps->terms;
+    for (HTerm& t : terms) {
+        t.x = perm_mask(c->perm, t.x);
+        t.z = perm_mask(c->perm, t.z);
+    }
+    vqe_paulisum* v = new vqe_paulisum();
+    v->device = ps->device;
+    v->tile_bits = ps->tile_bits;
+    v->low_bits = ps->low_bits;
+    v->threads = ps->threads;
+    CK(cudaSetDevice(c->device));
+    int rc = build_paulisum(v, ps->n, ps->nl, ps->tile_bits, ps->low_bits, ps->threads, std::move(terms));
+    if (rc == VQE_OK) rc = upload_paulisum(c, v);
+    if (rc) {
+        free_paulisum_device(v);
+        delete v;
+        return rc;
+    }
+    if (root->variants.size() >= 8) {  // an optimisation re-uses one relabelling; keep the cache small
+        auto old = root->variants.begin();
+        free_paulisum_device(old->second);
+        delete old->second;
+        root->variants.erase(old);
+    }
+    root->variants[key] = v;
+    *out = v;
+    return VQE_OK;
 }
 extern "C" int vqe_paulisum_groups(const vqe_paulisum* ps) { return ps ? ps->n_groups : 0; }
 extern "C" int vqe_paulisum_passes(const vqe_paulisum* ps) { return ps ? (int)ps->passes.size() : 0; }
@@ -5477,11 +5824,20 @@ extern "C" int vqe_paulisum_passes(const vqe_paulisum* ps) { return ps ? (int)ps
 // <buf|O|buf> on every rank of the set.  Peer passes (groups whose X-mask flips global bits) read the partner's
 // shard over NVLink; each super-tile is evaluated by exactly one rank of the pair.  out_per_rank[2r], [2r+1] =
 // partial sum of rank rs.r[r]; the caller adds the partials in rank order.
-static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss, double* out_per_rank) {
+static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss_in, double* out_per_rank) {
     int rc = check_rankset(rs);
     if (rc) return rc;
-    if (!pss || !out_per_rank) return fail(VQE_ERR_INVALID, "null argument");
+    if (!pss_in || !out_per_rank) return fail(VQE_ERR_INVALID, "null argument");
     const size_t nr = rs.r.size();
+    // a relabelled sharded state is evaluated with the relabelled twin of the sum (buffer 0 only)
+    std::vector<const vqe_paulisum*> eff(pss_in, pss_in + nr);
+    if (b == VQE_BUF_PSI)
+        for (size_t k = 0; k < nr; ++k) {
+            if (!pss_in[k]) return fail(VQE_ERR_INVALID, "null Pauli sum");
+            rc = paulisum_variant(rs.r[k], pss_in[k], &eff[k]);
+            if (rc) return rc;
+        }
+    const vqe_paulisum* const* pss = eff.data();
     for (size_t k = 0; k < nr; ++k) {
         vqe_ctx* c = rs.r[k];
         const vqe_paulisum* ps = pss[k];
@@ -5693,6 +6049,10 @@ extern "C" int vqe_group_expectation(vqe_ctx* const* ranks, int n_ranks, int b, 
 // partner's shard; every (super-)tile of dst is written by exactly one CTA per pass.
 static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* const* pss) {
     const size_t nr = rs.r.size();
+    if (dst == VQE_BUF_PSI || src == VQE_BUF_PSI) {
+        int rcl = need_caller_labelling(rs);
+        if (rcl) return rcl;
+    }
     for (size_t k = 0; k < nr; ++k) {
         vqe_ctx* c = rs.r[k];
         CK(cudaSetDevice(c->device));
@@ -5746,7 +6106,7 @@ static int apply_paulisum_rs(RankSet& rs, int dst, int src, const vqe_paulisum* 
                 make_tmap(pp.tp, vbit ? nullptr : ssrc.p0, g, &tmap, pp.swz ? 1 : 0);
                 if (pp.swz && !g.tma)
                     return fail(VQE_ERR_CUDA, "the Pauli sum was lowered for tensor-map (TMA) tile loads, which are not available now");
-                const int n_lg = (int)pp.goff.size() - 1;
+                const int n_lg = (int)pp.boff.size() - 1;  // conflict-free batches of entries
                 const int thr = (int)std::min<uint64_t>(512, std::max<uint64_t>(32, ts / 2));
                 if (real_src) {
                     const size_t smem_l = (16ull << pp.tp.tbits) + (8ull << pp.tp.tbits) + pp.addpat.size() * sizeof(double);
@@ -5825,6 +6185,10 @@ static int pool_impl(RankSet& rs, int bra, int ket, int n_ops, const int32_t* op
     if (n_ops < 0 || (n_ops > 0 && !op_offsets)) return fail(VQE_ERR_INVALID, "null offsets");
     const size_t nr = rs.r.size();
     vqe_ctx* c0 = rs.r[0];
+    if (bra == VQE_BUF_PSI || ket == VQE_BUF_PSI) {
+        rc = need_caller_labelling(rs);
+        if (rc) return rc;
+    }
     for (vqe_ctx* c : rs.r) {
         CK(cudaSetDevice(c->device));
         rc = ensure_buf(c, bra);
@@ -6103,6 +6467,7 @@ extern "C" int vqe_inner(vqe_ctx* c, int a, int b, double* out) {
     if (rc) return rc;
     rc = ensure_complex(c, a);
     if (rc == VQE_OK) rc = ensure_complex(c, b);
+    if (rc == VQE_OK && (a == VQE_BUF_PSI) != (b == VQE_BUF_PSI)) rc = need_caller_labelling(c);  // <psi|psi> does not care
     if (rc) return rc;
     return inner_bufs(c, c->buf[a], c->buf[b], out);
 }
@@ -6122,6 +6487,7 @@ extern "C" int vqe_overlap_host(vqe_ctx* c, int b, const double* vec, double* ou
     rc = ensure_buf(c, tmp);
     if (rc) return rc;
     rc = ensure_complex(c, b);
+    if (rc == VQE_OK && b == VQE_BUF_PSI) rc = need_caller_labelling(c);
     if (rc) return rc;
     CK(cudaMemcpyAsync(c->buf[tmp], vec, c->n_amp * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
     return inner_bufs(c, c->buf[tmp], c->buf[b], out);
@@ -6136,6 +6502,8 @@ extern "C" int vqe_apply_exp_paulisum(vqe_ctx* c, int n_terms, const uint64_t* x
     int rc = collect_terms(c, n_terms, x, z, ny, cre, cim, terms);
     if (rc) return rc;
     if (terms.empty() || theta == 0.0) return VQE_OK;
+    rc = need_caller_labelling(c);
+    if (rc) return rc;
     // anti-Hermitian  <=>  every coefficient purely imaginary
     bool antiherm = true, commute = true;
     for (const HTerm& t : terms)

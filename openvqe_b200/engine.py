@@ -228,6 +228,12 @@ class Engine:
         _lib.check(self._lib.vqe_peer_bytes(self.handle, C.byref(g), 1 if reset else 0))
         return g.value
 
+    def relabel_stats(self, reset=False):
+        """(qubit swaps executed, bytes this rank read from partner shards in them) -- sharded states, see include/vqe_b200.h."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.vqe_relabel_stats(self.handle, C.byref(a), C.byref(b), 1 if reset else 0))
+        return a.value, b.value
+
     def buffer_ptr(self, buf=BUF_PSI):
         p, n = C.c_void_p(), C.c_uint64()
         _lib.check(self._lib.vqe_buffer_ptr(self.handle, buf, C.byref(p), C.byref(n)))

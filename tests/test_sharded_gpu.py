@@ -31,6 +31,15 @@ def groups(gpu_required):
     return get
 
 
+@pytest.fixture(params=["relabel", "peer-passes"], autouse=True)
+def relabel_mode(request, monkeypatch):
+    """Every test runs twice: with qubit relabelling (rotations that flip a global qubit trigger a global<->local swap, all
+    passes stay local; VQE_RELABEL_FLOOR lowered so that small shards take part) and without (peer passes)."""
+    monkeypatch.setenv("VQE_RELABEL", "1" if request.param == "relabel" else "0")
+    monkeypatch.setenv("VQE_RELABEL_FLOOR", "4")
+    return request.param
+
+
 CASES = [(4, 1), (6, 2), (9, 1), (9, 3), (13, 1), (13, 2), (14, 3), (16, 2), (18, 1)]
 
 
@@ -233,6 +242,7 @@ def test_gather_form_chunks_prefetched_under_the_previous_chunk(gpu_required, mo
     from tools import c5_synthetic as c5
     monkeypatch.setenv("VQE_GATHER_STAGE_MB", "0")
     monkeypatch.setenv("VQE_GATHER_OVERLAP", overlap)
+    monkeypatch.setenv("VQE_RELABEL", "0")   # this test is about peer passes
     gen = c5.generators(n, k_gen=96)
     ang = gen["theta"][gen["owner"]] * gen["coeff"]
     hf = c5.hf_index(n)
@@ -264,6 +274,46 @@ def test_sharded_exact_exponential_of_noncommuting_generators(groups, n, g):
     ref = orc.fermionic_adapt_state(psi, gens, thetas)
     assert np.max(np.abs(grp.get_state() - ref)) < 1e-11
     assert abs(grp.norm2() - 1.0) < 1e-11
+
+
+def test_relabelling_swaps_instead_of_peer_passes(gpu_required, monkeypatch):
+    """The C5 program on 8 virtual ranks with relabelling: far fewer qubit swaps than rotations that flip a global qubit, no
+    gather-form traffic, the state (read back in the caller's labelling: swaps undone) and the energy (evaluated on the
+    relabelled state with the relabelled twin of H) equal the oracle; then the state is re-used in the caller's labelling."""
+    from openvqe_b200.lowering import PackedTerms
+    from openvqe_b200.sharded import ShardGroup
+    from tools import c5_synthetic as c5
+    monkeypatch.setenv("VQE_RELABEL", "1")
+    monkeypatch.setenv("VQE_RELABEL_FLOOR", "5")
+    n, g = 16, 3
+    gen, ham = c5.generators(n, k_gen=128), c5.hamiltonian(n)
+    ang = gen["theta"][gen["owner"]] * gen["coeff"]
+    hf = c5.hf_index(n)
+    grp = ShardGroup(n, g)
+    grp.set_basis_state(hf)
+    grp.apply_rotations(gen["x"], gen["z"], gen["ny"], ang)
+    swaps = grp.ranks[0].relabel_stats()[0]
+    touching = len({int(o) for o, x in zip(gen["owner"], gen["x"]) if int(x) >> (n - g)})
+    assert 0 < swaps < touching and sum(e.gather_bytes() for e in grp.ranks) == 0
+    ps = grp.paulisum(PackedTerms(n, ham["x"], ham["z"], ham["ny"], ham["cre"], np.zeros_like(ham["cre"])))
+    e = grp.expectation(ps)                     # on the relabelled state
+    ref = orc.basis_state(n, hf)
+    for x, z, ny, a in zip(gen["x"], gen["z"], gen["ny"], ang):
+        ref = orc.pauli_rotation(ref, int(x), int(z), int(ny), float(a))
+    e_ref = sum(c * np.vdot(ref, orc.apply_pauli(ref, int(x), int(z), int(ny))) for x, z, ny, c in
+                zip(ham["x"], ham["z"], ham["ny"], ham["cre"]))
+    assert abs(e.real - e_ref.real) < 1e-10 and abs(e.imag) < 1e-10
+    assert np.max(np.abs(grp.get_state() - ref)) < TOL      # undoes the swaps
+    assert grp.ranks[0].relabel_stats()[0] == 2 * swaps
+    e2 = grp.expectation(ps)                    # now in the caller's labelling
+    assert abs(e2 - e) < 1e-12
+    # a second program on top (relabels again), then sigma = H psi (needs the caller's labelling)
+    grp.apply_rotations(gen["x"][:200], gen["z"][:200], gen["ny"][:200], -ang[:200])
+    for x, z, ny, a in zip(gen["x"][:200], gen["z"][:200], gen["ny"][:200], -ang[:200]):
+        ref = orc.pauli_rotation(ref, int(x), int(z), int(ny), float(a))
+    grp.apply_paulisum(ps, dst=1, src=0)
+    sig_ref = sum(c * orc.apply_pauli(ref, int(x), int(z), int(ny)) for x, z, ny, c in zip(ham["x"], ham["z"], ham["ny"], ham["cre"]))
+    assert np.max(np.abs(grp.get_state(1) - sig_ref)) < 1e-11
 
 
 def test_c5_synthetic_sharded_equals_unsharded_at_22_qubits(gpu_required):
