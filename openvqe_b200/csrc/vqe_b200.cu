@@ -2584,7 +2584,8 @@ static int create_ctx(vqe_ctx** out, int n_qubits, int n_global, int rank, int d
     // insists on 16 amplitudes (256 bytes; 128 in the real layout) and leaves 8 tile bits to the planner; the peer passes of
     // a sharded state copy segment by segment and keep 512-byte segments
     c->low_bits = env_int("VQE_LOW_BITS", n_global ? 5 : 4);
-    c->real_layout_ok = env_int("VQE_REAL_LAYOUT", 1) != 0 && n_global == 0;
+    // (a sharded state keeps it through the rotation passes only, which qubit relabelling makes local; see launch_plan)
+    c->real_layout_ok = env_int("VQE_REAL_LAYOUT", 1) != 0 && (n_global == 0 || env_int("VQE_RELABEL", 1) != 0);
     c->threads = env_int("VQE_THREADS", 512);
     c->ctas_per_sm = env_int("VQE_CTAS_PER_SM", 2);
     if (c->tile_bits < 6 || c->tile_bits > 12) c->tile_bits = 12;
@@ -2679,20 +2680,36 @@ extern "C" void vqe_destroy(vqe_ctx* c) {
 // Exchange of a GLOBAL with a LOCAL index bit between the shards of ranks lo (global bit 0) and hi (global bit 1): lo's
 // amplitudes with local bit L = 1 trade places with hi's amplitudes with L = 0 (all other bits equal).  Pair k of the
 // n_amp / 2 pairs: i0 = k with a zero inserted at bit L.  The two ranks of a pair each take half of the pairs, so every GPU
-// reads and writes a quarter of a shard remotely: half a shard per NVLink direction.  L >= 2: four consecutive pairs per
-// thread are contiguous (64 bytes per access stream, eight independent 16-byte loads in flight).
-__global__ void __launch_bounds__(256) k_swap_global_local(double2* __restrict__ lo, double2* __restrict__ hi, uint32_t L,
-                                                           uint64_t first, uint64_t count) {
+// reads and writes a quarter of a shard remotely: half a shard per NVLink direction.  Consecutive lanes take consecutive
+// pairs (512 contiguous bytes per warp and access stream -- a lane stride of 64 bytes cut the NVLink rate to a third),
+// four pairs a block-width apart per thread: eight independent loads in flight.  T = double2, or double while the state
+// is kept in the real layout.
+template <typename T>
+__global__ void __launch_bounds__(256) k_swap_global_local(T* __restrict__ lo, T* __restrict__ hi, uint32_t L, uint64_t first,
+                                                           uint64_t count) {
     const uint64_t lowmask = (1ull << L) - 1ull, lbit = 1ull << L;
+    const uint64_t end = first + count;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4ull;
-    for (uint64_t k = first + (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 4ull; k < first + count; k += stride) {
-        const uint64_t i0 = ((k & ~lowmask) << 1) | (k & lowmask);
-        double2* pa = lo + (i0 | lbit);
-        double2* pb = hi + i0;
-        const double2 a0 = pa[0], a1 = pa[1], a2 = pa[2], a3 = pa[3];
-        const double2 b0 = pb[0], b1 = pb[1], b2 = pb[2], b3 = pb[3];
-        pa[0] = b0; pa[1] = b1; pa[2] = b2; pa[3] = b3;
-        pb[0] = a0; pb[1] = a1; pb[2] = a2; pb[3] = a3;
+    for (uint64_t k0 = first + (uint64_t)blockIdx.x * blockDim.x * 4ull + threadIdx.x; k0 < end; k0 += stride) {
+        T a[4], b[4];
+        uint64_t ia[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t k = k0 + (uint64_t)u * blockDim.x;
+            ia[u] = ((k & ~lowmask) << 1) | (k & lowmask);
+            if (k < end) {
+                a[u] = lo[ia[u] | lbit];
+                b[u] = hi[ia[u]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t k = k0 + (uint64_t)u * blockDim.x;
+            if (k < end) {
+                lo[ia[u] | lbit] = b[u];
+                hi[ia[u]] = a[u];
+            }
+        }
     }
 }
 
@@ -2937,7 +2954,9 @@ static RankSet group_of(vqe_ctx* c) {
 // swap the contents of physical index bits gslot (a rank bit, >= nl) and lslot (a local bit) of buffer 0 on all ranks
 static int swap_global_local(RankSet& rs, int gslot, int lslot) {
     vqe_ctx* c0 = rs.r[0];
-    if (gslot < c0->nl || gslot >= c0->n || lslot < 2 || lslot >= c0->nl) return fail(VQE_ERR_INVALID, "bad qubit swap %d <-> %d", gslot, lslot);
+    if (gslot < c0->nl || gslot >= c0->n || lslot < 0 || lslot >= c0->nl) return fail(VQE_ERR_INVALID, "bad qubit swap %d <-> %d", gslot, lslot);
+    for (vqe_ctx* c : rs.r)
+        if (c->real_layout != c0->real_layout) return fail(VQE_ERR_INVALID, "the ranks disagree on the layout of the state");
     int rc = rank_barrier(rs);  // everything issued so far has finished on both shards
     if (rc) return rc;
     const int gbit = 1 << (gslot - c0->nl);
@@ -2952,12 +2971,16 @@ static int swap_global_local(RankSet& rs, int gslot, int lslot) {
         if (!plo || !phi) return fail(VQE_ERR_INVALID, "rank %d: the state of rank %d is not attached (vqe_shard_attach_*)", c->rank, partner);
         const uint64_t n_pairs = c->n_amp >> 1, half = n_pairs >> 1;
         const uint64_t first = c->rank == lo ? 0 : half, count = c->rank == lo ? half : n_pairs - half;
-        const int blocks = (int)std::min<uint64_t>((count / 4 + 255) / 256, (uint64_t)c->sm_count * 8);
+        const int blocks = (int)std::min<uint64_t>((count + 1023) / 1024, (uint64_t)c->sm_count * 8);
         ProfScope prof(c, 4);
-        k_swap_global_local<<<std::max(1, blocks), 256, 0, c->stream>>>(plo, phi, (uint32_t)lslot, first, count);
+        if (c->real_layout)  // the state is kept as n_amp doubles: the same exchange on 8-byte elements
+            k_swap_global_local<double><<<std::max(1, blocks), 256, 0, c->stream>>>(reinterpret_cast<double*>(plo), reinterpret_cast<double*>(phi),
+                                                                                     (uint32_t)lslot, first, count);
+        else
+            k_swap_global_local<double2><<<std::max(1, blocks), 256, 0, c->stream>>>(plo, phi, (uint32_t)lslot, first, count);
         c->launches++;
         c->n_swaps++;
-        c->swap_bytes += count * sizeof(double2);
+        c->swap_bytes += count * (c->real_layout ? sizeof(double) : sizeof(double2));
         CK(cudaGetLastError());
     }
     rc = rank_barrier(rs);  // the exchange is complete before anyone touches its shard again
@@ -3996,7 +4019,8 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
         return ps.fast && ps.sub_end == ps.sub_begin && ps.col_end > ps.col_begin && ps.pass_scale == 1.0 &&
                (ps.sup_end - ps.sup_begin) == (ps.col_end - ps.col_begin) && env_int("VQE_COL_KERNEL", 1) != 0;
     };
-    bool rl_plan = buf == VQE_BUF_PSI && rs.r.size() == 1 && rs.r[0]->real_layout && env_int("VQE_PIPE", 0) == 0;
+    bool rl_plan = buf == VQE_BUF_PSI && env_int("VQE_PIPE", 0) == 0;
+    for (vqe_ctx* c : rs.r) rl_plan = rl_plan && c->real_layout;
     if (rl_plan)
         for (size_t p = 0; p < passes.size() && rl_plan; ++p) {
             const OpPass& ps = passes[p];
@@ -5856,10 +5880,13 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss_i
     for (vqe_ctx* c : rs.r) real_state = real_state && c->psi_real;
     // Real layout of the state (unsharded): the lean passes read it as it is when every one of them has a real-layout form;
     // the buffer is expanded to interleaved complex before the first general pass (or right away otherwise).
-    bool rl = b == VQE_BUF_PSI && nr == 1 && rs.r[0]->real_layout && real_state && env_int("VQE_PIPE", 0) == 0;
-    if (rl)
-        for (const PSPass& pp : pss[0]->passes)
+    // (lean passes are always local passes, also on a shard; peer and general passes come after them)
+    bool rl = b == VQE_BUF_PSI && real_state && env_int("VQE_PIPE", 0) == 0;
+    for (size_t k = 0; k < nr && rl; ++k) {
+        rl = rs.r[k]->real_layout;
+        for (const PSPass& pp : pss[k]->passes)
             if (pp.lean && !pp.rl_ok) rl = false;
+    }
     if (!rl && b == VQE_BUF_PSI)
         for (vqe_ctx* c : rs.r) {
             CK(cudaSetDevice(c->device));
@@ -5898,6 +5925,13 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss_i
     bool fenced = false;
     for (size_t p = 0; p < n_pass; ++p) {
         const bool vbit = pss[0]->passes[p].tp.vbit;
+        if (rl && !pss[0]->passes[p].lean)  // first general pass: every rank expands its shard BEFORE any partner reads it
+            for (vqe_ctx* c : rs.r)
+                if (c->real_layout) {
+                    CK(cudaSetDevice(c->device));
+                    rc = ensure_complex(c, b);
+                    if (rc) return rc;
+                }
         if (vbit && !fenced) {
             rc = rank_barrier(rs);
             if (rc) return rc;
