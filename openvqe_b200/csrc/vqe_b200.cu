@@ -4402,7 +4402,7 @@ static int rotations_core(RankSet& rs, int n_rot, const uint64_t* xmask, const u
 // pass -- and so would every later rotation that flips the same qubit.  Instead the logical bit is moved into a local
 // slot ONCE (swap_global_local: half a shard over NVLink, about the cost of one peer pass) and the local slot that gives
 // way is the one whose logical bit is flipped furthest in the future (Belady's rule over the rest of the program; slots
-// below VQE_RELABEL_FLOOR = 12 keep their bits so that swaps move contiguous runs of 64 KiB).  The masks of the following rotations
+// below VQE_RELABEL_FLOOR = 10 keep their bits so that swaps move contiguous runs of at least 8 KiB).  The masks of the following rotations
 // are translated through the permutation; the permutation stays in force after the call (vqe_expectation evaluates a
 // permuted twin of the Pauli sum; anything else that needs the caller's labelling undoes the swaps).  For the random C5
 // program on 8 GPUs: 19 swaps instead of 68 peer passes.
@@ -4413,7 +4413,7 @@ static int rotations_impl(RankSet& rs, int n_rot, const uint64_t* xmask, const u
     vqe_ctx* c = rs.r[0];
     if (c->world == 1 || buf != VQE_BUF_PSI) return rotations_core(rs, n_rot, xmask, zmask, ny, angle, buf);
     if (n_rot < 0 || (n_rot > 0 && (!xmask || !zmask || !ny || !angle))) return fail(VQE_ERR_INVALID, "null array");
-    const int RELABEL_FLOOR = std::max(2, std::min(env_int("VQE_RELABEL_FLOOR", 12), c->nl - 4));
+    const int RELABEL_FLOOR = std::max(2, std::min(env_int("VQE_RELABEL_FLOOR", 10), c->nl - 4));
     const bool relabel = env_int("VQE_RELABEL", 1) != 0 && c->nl >= 8;
     if (!relabel) {
         rc = need_caller_labelling(rs);
@@ -5801,23 +5801,34 @@ extern "C" void vqe_paulisum_destroy(vqe_paulisum* ps) {
     free_paulisum_device(ps);
     delete ps;
 }
-// the twin of `ps` for the current relabelling of context c (built, uploaded and cached on first use)
-static int paulisum_variant(vqe_ctx* c, const vqe_paulisum* ps, const vqe_paulisum** out) {
+// A twin of `ps` for the current relabelling of context c (built, uploaded and cached on first use).  tag '*': the whole
+// sum; 'A' / 'B': the two parts of a split evaluation (see expectation_impl), selected by `pick`.
+static int paulisum_variant(vqe_ctx* c, const vqe_paulisum* ps, char tag, const std::vector<char>* pick, const vqe_paulisum** out) {
     *out = ps;
-    if (c->world == 1 || perm_is_identity(c)) return VQE_OK;
+    if (c->world == 1 || (tag == '*' && perm_is_identity(c))) return VQE_OK;
     if (ps->terms.empty() && !ps->passes.empty())
         return fail(VQE_ERR_INVALID, "the Pauli sum was created on an unsharded context and cannot follow a relabelled state");
     vqe_paulisum* root = const_cast<vqe_paulisum*>(ps);
-    const std::string key((const char*)c->perm, (size_t)c->n);
+    std::string key((const char*)c->perm, (size_t)c->n);
+    key.push_back(tag);
+    if (pick) {  // the selection is part of the identity of the twin
+        uint64_t h = 1469598103934665603ull;
+        for (char v : *pick) h = (h ^ (uint64_t)(unsigned char)v) * 1099511628211ull;
+        key.append((const char*)&h, sizeof h);
+    }
     auto it = root->variants.find(key);
     if (it != root->variants.end()) {
         *out = it->second;
         return VQE_OK;
     }
-    std::vector<HTerm> terms = ps->terms;
-    for (HTerm& t : terms) {
+    std::vector<HTerm> terms;
+    terms.reserve(ps->terms.size());
+    for (size_t k = 0; k < ps->terms.size(); ++k) {
+        if (pick && !(*pick)[k]) continue;
+        HTerm t = ps->terms[k];
         t.x = perm_mask(c->perm, t.x);
         t.z = perm_mask(c->perm, t.z);
+        terms.push_back(t);
     }
     vqe_paulisum* v = new vqe_paulisum();
     v->device = ps->device;
@@ -5832,11 +5843,11 @@ static int paulisum_variant(vqe_ctx* c, const vqe_paulisum* ps, const vqe_paulis
         delete v;
         return rc;
     }
-    if (root->variants.size() >= 8) {  // an optimisation re-uses one relabelling; keep the cache small
-        auto old = root->variants.begin();
-        free_paulisum_device(old->second);
-        delete old->second;
-        root->variants.erase(old);
+    if (root->variants.size() >= 12) {  // an optimisation re-uses one relabelling; keep the cache small
+        auto oldest = root->variants.begin();
+        free_paulisum_device(oldest->second);
+        delete oldest->second;
+        root->variants.erase(oldest);
     }
     root->variants[key] = v;
     *out = v;
@@ -5848,20 +5859,11 @@ extern "C" int vqe_paulisum_passes(const vqe_paulisum* ps) { return ps ? (int)ps
 // <buf|O|buf> on every rank of the set.  Peer passes (groups whose X-mask flips global bits) read the partner's
 // shard over NVLink; each super-tile is evaluated by exactly one rank of the pair.  out_per_rank[2r], [2r+1] =
 // partial sum of rank rs.r[r]; the caller adds the partials in rank order.
-static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss_in, double* out_per_rank) {
+static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, double* out_per_rank) {
     int rc = check_rankset(rs);
     if (rc) return rc;
-    if (!pss_in || !out_per_rank) return fail(VQE_ERR_INVALID, "null argument");
+    if (!pss || !out_per_rank) return fail(VQE_ERR_INVALID, "null argument");
     const size_t nr = rs.r.size();
-    // a relabelled sharded state is evaluated with the relabelled twin of the sum (buffer 0 only)
-    std::vector<const vqe_paulisum*> eff(pss_in, pss_in + nr);
-    if (b == VQE_BUF_PSI)
-        for (size_t k = 0; k < nr; ++k) {
-            if (!pss_in[k]) return fail(VQE_ERR_INVALID, "null Pauli sum");
-            rc = paulisum_variant(rs.r[k], pss_in[k], &eff[k]);
-            if (rc) return rc;
-        }
-    const vqe_paulisum* const* pss = eff.data();
     for (size_t k = 0; k < nr; ++k) {
         vqe_ctx* c = rs.r[k];
         const vqe_paulisum* ps = pss[k];
@@ -6059,6 +6061,81 @@ static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss_i
     return VQE_OK;
 }
 
+// <buf|O|buf>.  On a (relabelled) sharded state the sum is evaluated through its relabelled twin; when strings would
+// still flip a global qubit the evaluation is SPLIT: part A -- the X-mask groups that are local as the state stands --
+// first, then up to n_global qubit swaps that move the qubits part B flips out of the global slots (into local slots whose
+// qubits part B never flips), then part B (all the rest, diagonal group included) on local passes.  A peer pass reads
+// half a shard over NVLink per global pattern (8 x 102 ms at 36 qubits on 8 GPUs); a swap costs half of that once.
+static int expectation_impl(RankSet& rs, int b, const vqe_paulisum* const* pss_in, double* out_per_rank) {
+    int rc = check_rankset(rs);
+    if (rc) return rc;
+    if (!pss_in || !out_per_rank) return fail(VQE_ERR_INVALID, "null argument");
+    const size_t nr = rs.r.size();
+    for (size_t k = 0; k < nr; ++k)
+        if (!pss_in[k]) return fail(VQE_ERR_INVALID, "null Pauli sum");
+    vqe_ctx* c0 = rs.r[0];
+    std::vector<const vqe_paulisum*> eff(pss_in, pss_in + nr);
+    if (b != VQE_BUF_PSI || c0->world == 1) return expectation_core(rs, b, eff.data(), out_per_rank);
+    const vqe_paulisum* ps0 = pss_in[0];
+    const uint64_t gmask = ((1ull << c0->g) - 1ull) << c0->nl;
+    const bool can_split = env_int("VQE_RELABEL", 1) != 0 && c0->nl >= 8 && !ps0->terms.empty();
+    std::vector<char> in_a(ps0->terms.size(), 0), in_b(ps0->terms.size(), 0);
+    bool any_a = false, any_peer = false;
+    if (can_split)
+        for (size_t k = 0; k < ps0->terms.size(); ++k) {
+            const uint64_t px = perm_mask(c0->perm, ps0->terms[k].x);
+            if (px & gmask) any_peer = true;
+            in_a[k] = (ps0->terms[k].x != 0 && !(px & gmask)) ? 1 : 0;
+            in_b[k] = in_a[k] ? 0 : 1;
+            any_a = any_a || in_a[k];
+        }
+    if (!can_split || !any_peer) {
+        for (size_t k = 0; k < nr; ++k) {
+            rc = paulisum_variant(rs.r[k], pss_in[k], '*', nullptr, &eff[k]);
+            if (rc) return rc;
+        }
+        return expectation_core(rs, b, eff.data(), out_per_rank);
+    }
+    for (size_t k = 0; k < nr; ++k)
+        if (pss_in[k]->terms.size() != ps0->terms.size()) return fail(VQE_ERR_INVALID, "Pauli sums of the ranks differ");
+    std::vector<double> part(2 * nr, 0.0);
+    for (size_t k = 0; k < 2 * nr; ++k) out_per_rank[k] = 0.0;
+    if (any_a) {
+        for (size_t k = 0; k < nr; ++k) {
+            rc = paulisum_variant(rs.r[k], pss_in[k], 'A', &in_a, &eff[k]);
+            if (rc) return rc;
+        }
+        rc = expectation_core(rs, b, eff.data(), part.data());
+        if (rc) return rc;
+        for (size_t k = 0; k < 2 * nr; ++k) out_per_rank[k] += part[k];
+    }
+    // qubits part B flips, per logical bit
+    const int n = c0->n, nl = c0->nl;
+    std::vector<int> busy(n, 0);
+    for (size_t k = 0; k < ps0->terms.size(); ++k)
+        if (in_b[k])
+            for (uint64_t m = ps0->terms[k].x; m; m &= m - 1) busy[__builtin_ctzll(m)]++;
+    const int floor_slot = std::max(2, std::min(env_int("VQE_RELABEL_FLOOR", 10), nl - 4));
+    for (int gs = nl; gs < n; ++gs) {
+        int inv[64];
+        for (int q = 0; q < n; ++q) inv[c0->perm[q]] = q;
+        if (busy[inv[gs]] == 0) continue;
+        int best = -1;
+        for (int slot = nl - 1; slot >= floor_slot; --slot)
+            if (best < 0 || busy[inv[slot]] < busy[inv[best]]) best = slot;
+        if (best < 0 || busy[inv[best]] >= busy[inv[gs]]) continue;
+        rc = swap_global_local(rs, gs, best);
+        if (rc) return rc;
+    }
+    for (size_t k = 0; k < nr; ++k) {
+        rc = paulisum_variant(rs.r[k], pss_in[k], 'B', &in_b, &eff[k]);
+        if (rc) return rc;
+    }
+    rc = expectation_core(rs, b, eff.data(), part.data());
+    if (rc) return rc;
+    for (size_t k = 0; k < 2 * nr; ++k) out_per_rank[k] += part[k];
+    return VQE_OK;
+}
 extern "C" int vqe_expectation(vqe_ctx* c, int b, const vqe_paulisum* ps, double* out) {
     if (!c || !ps || !out) return fail(VQE_ERR_INVALID, "null argument");
     RankSet rs;
