@@ -252,9 +252,9 @@ def run_reference(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)",
             "data": "synthetic", "config": config_for(w, world), "energy_first_step": energies[0],
             "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port",
-                             "sample": "every timed step is one FULL evaluation (14112 rotations + 14905 terms, one 2^24 sweep each); "
+                             "sample": "every timed step is one FULL evaluation (%d rotations + %d terms, one 2^%d sweep each); "
                                        "CPU port = oracle/c/vqe_oracle.c (OpenMP, %d threads set explicitly), the reference's own myQLM "
-                                       "simulator is not installable here" % cores,
+                                       "simulator is not installable here" % (len(rot.x), len(ham.x), n, cores),
                              "seconds_per_step": secs, "wall_s": time.perf_counter() - t_start},
             "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
