@@ -3443,6 +3443,7 @@ struct OpPlan {
     std::vector<ColPat> col_pats;
     std::vector<double> rot_cos;    // cosine of every dop (fast passes)
     bool cacheable = true;
+    int tile_bits = 12;             // 13: planned for the real layout of the state (tiles of 2^13 doubles = 64 KiB)
 };
 
 static bool fast_eligible(const HostOp& h) {
@@ -3504,6 +3505,8 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
             const uint64_t u = need | (ops[j].x & lfull);
             // shrink the low-bit floor when the shard is tiny (tests): the planner only needs "fits"
             if (!plan_fits(u, lowmask, tile_bits, nl, npat != 0)) break;
+            // 13-bit tiles exist only in the real layout, which is staged by tensor-map requests: the pass must keep one
+            if (tile_bits > 12 && j > i && !plan_tma(make_plan(nl, u, tile_bits, lb, npat), false, true).ok) break;
             need = u;
             pat = npat;
             ctrl_glob = nctrl;
@@ -3940,6 +3943,20 @@ static int run_ops(RankSet& rs, const std::vector<HostOp>& ops) {
 }
 
 // upload + launch a planned op list on buffer 0 of every rank in the set
+// Can every pass of the plan run on the REAL LAYOUT of the state (k_tile_col<true, true>)?  Purely real collapsed-run
+// passes, local, with a real-layout tensor-map form and tables that fit next to the tile.
+static bool plan_runs_in_real_layout(const OpPlan& plan) {
+    if (env_int("VQE_COL_KERNEL", 1) == 0 || env_int("VQE_PIPE", 0) != 0) return false;
+    for (const OpPass& ps : plan.passes) {
+        const bool all_col = ps.fast && !ps.has_imag && ps.sub_end == ps.sub_begin && ps.col_end > ps.col_begin && ps.pass_scale == 1.0 &&
+                             (ps.sup_end - ps.sup_begin) == (ps.col_end - ps.col_begin);
+        const size_t smem_r = (8ull << ps.tp.tbits) + (size_t)(ps.col_end - ps.col_begin) * (sizeof(ColLite) + 8 + 4) +
+                              (size_t)(ps.ent_end - ps.ent_begin) * sizeof(DevColEntry);
+        if (!all_col || ps.tp.vbit || smem_r > 110 * 1024) return false;
+        if (!(tma_available(ps.tp, true, true) || tma_available(ps.tp, false, true))) return false;
+    }
+    return true;
+}
 // CTAs of a gather-form pass launch that fetch the NEXT chunk's partner amplitudes (the launch keeps its persistent grid:
 // they are carved out of it and grown back when the grid would otherwise be too small to hold them)
 static uint32_t gather_ctas(const vqe_ctx* c, bool wanted, int& grid) {
@@ -4015,20 +4032,11 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
     // Real layout of the state buffer (unsharded contexts, see vqe_ctx::real_layout): kept when EVERY pass is a purely real
     // collapsed-run pass with a real-layout tensor-map form (every UCCSD / QUCCSD program); otherwise the buffer is expanded
     // to interleaved complex first and the passes run as usual.
-    auto pass_all_col = [&](const OpPass& ps) {
-        return ps.fast && ps.sub_end == ps.sub_begin && ps.col_end > ps.col_begin && ps.pass_scale == 1.0 &&
-               (ps.sup_end - ps.sup_begin) == (ps.col_end - ps.col_begin) && env_int("VQE_COL_KERNEL", 1) != 0;
-    };
-    bool rl_plan = buf == VQE_BUF_PSI && env_int("VQE_PIPE", 0) == 0;
+    bool rl_plan = buf == VQE_BUF_PSI;
     for (vqe_ctx* c : rs.r) rl_plan = rl_plan && c->real_layout;
-    if (rl_plan)
-        for (size_t p = 0; p < passes.size() && rl_plan; ++p) {
-            const OpPass& ps = passes[p];
-            const size_t smem_r = (8ull << ps.tp.tbits) + (size_t)(ps.col_end - ps.col_begin) * (sizeof(ColLite) + 8 + 4) +
-                                  (size_t)(ps.ent_end - ps.ent_begin) * sizeof(DevColEntry);
-            rl_plan = real_pass[p] && !ps.tp.vbit && pass_all_col(ps) && smem_r <= 200 * 1024 &&
-                      (tma_available(ps.tp, true, true) || tma_available(ps.tp, false, true));
-        }
+    for (size_t p = 0; p < passes.size() && rl_plan; ++p) rl_plan = real_pass[p] != 0;
+    rl_plan = rl_plan && plan_runs_in_real_layout(plan);
+    if (!rl_plan && plan.tile_bits > 12) return fail(VQE_ERR_INVALID, "a 13-bit tile plan needs the real layout of the state");
     if (!rl_plan && buf == VQE_BUF_PSI)
         for (vqe_ctx* c : rs.r) {
             CK(cudaSetDevice(c->device));
@@ -4351,6 +4359,23 @@ static int rotations_core(RankSet& rs, int n_rot, const uint64_t* xmask, const u
     }
     PlanCache* pc = c->plan_cache;
     const bool use_cache = env_int("VQE_PLAN_CACHE", 1) != 0;
+    // REAL LAYOUT: a tile of 2^13 doubles fills the same 64 KiB as 2^12 complex amplitudes, so a pass may use one more tile
+    // bit (fewer sweeps over the state).  Only if the whole plan then runs in the real layout; else the usual 12-bit plan.
+    bool rl_now = buf == VQE_BUF_PSI && all_fast && env_int("VQE_RL_TILE_BITS", 13) > 12 && c->nl >= 13;
+    for (vqe_ctx* r : rs.r) rl_now = rl_now && r->real_layout;
+    auto make_rot_plan = [&](const std::vector<HostOp>& hops, OpPlan& plan) -> int {
+        if (rl_now) {
+            plan = OpPlan();
+            int rcp = plan_ops(c->n, c->nl, 13, c->low_bits, 1024, hops, plan);
+            if (rcp == VQE_OK && plan_runs_in_real_layout(plan)) {
+                plan.tile_bits = 13;
+                return VQE_OK;
+            }
+        }
+        plan = OpPlan();
+        return plan_ops(c->n, c->nl, c->tile_bits, c->low_bits, c->threads, hops, plan);
+    };
+    if (pc && pc->valid && pc->plan.tile_bits > 12 && !rl_now) pc->valid = false;  // planned for a layout the state has left
     if (use_cache && all_fast && pc && pc->valid && (int)pc->cls.size() == n_rot &&
         memcmp(pc->cls.data(), cls.data(), n_rot) == 0 && memcmp(pc->x.data(), xmask, n_rot * sizeof(uint64_t)) == 0 &&
         memcmp(pc->z.data(), zmask, n_rot * sizeof(uint64_t)) == 0 && memcmp(pc->ny.data(), ny, n_rot * sizeof(int32_t)) == 0) {
@@ -4378,14 +4403,13 @@ static int rotations_core(RankSet& rs, int n_rot, const uint64_t* xmask, const u
     if (ops.empty()) return VQE_OK;
     if (!(use_cache && all_fast)) {
         OpPlan plan;
-        int rcp = plan_ops(c->n, c->nl, c->tile_bits, c->low_bits, c->threads, ops, plan);
+        int rcp = make_rot_plan(ops, plan);
         if (rcp) return rcp;
         return launch_plan(rs, plan, buf);
     }
     if (!pc) pc = c->plan_cache = new PlanCache();
     pc->valid = false;
-    pc->plan = OpPlan();
-    int rc = plan_ops(c->n, c->nl, c->tile_bits, c->low_bits, c->threads, ops, pc->plan);
+    int rc = make_rot_plan(ops, pc->plan);
     if (rc) return rc;
     bool fast_only = pc->plan.cacheable && pc->plan.rot_cos.size() == pc->plan.dops.size();
     for (const OpPass& p : pc->plan.passes) fast_only = fast_only && p.fast;
@@ -4497,7 +4521,7 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
                                   int32_t* pass_n_ops, uint64_t* pass_tile_mask) {
     if (n_qubits < 1 || n_qubits > 40 || n_global < 0 || n_global > 6 || n_global >= n_qubits)
         return fail(VQE_ERR_INVALID, "bad qubit counts");
-    if (tile_bits < 6 || tile_bits > 12) tile_bits = 12;
+    if (tile_bits < 6 || tile_bits > 13) tile_bits = 12;  // 13: the real-layout plan of a purely real state (tiles of doubles)
     if (low_bits < 0 || low_bits > tile_bits) low_bits = 5;
     if (!n_passes || n_rot < 0 || (n_rot > 0 && (!xmask || !zmask || !ny || !angle))) return fail(VQE_ERR_INVALID, "null array");
     std::vector<HostOp> ops;
@@ -4514,7 +4538,7 @@ extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int
         ops.push_back(h);
     }
     OpPlan plan;
-    int rc = plan_ops(n_qubits, n_qubits - n_global, tile_bits, low_bits, 512, ops, plan);
+    int rc = plan_ops(n_qubits, n_qubits - n_global, tile_bits, low_bits, tile_bits > 12 ? 1024 : 512, ops, plan);
     if (rc) return rc;
     *n_passes = (int32_t)plan.passes.size();
     for (size_t p = 0; p < plan.passes.size() && (int)p < cap; ++p) {
