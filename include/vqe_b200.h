@@ -216,6 +216,15 @@ int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int low_bits, 
                        const uint64_t* zmask, const int32_t* ny, const double* angle, int cap, int32_t* n_passes,
                        int32_t* pass_kind, uint64_t* pass_pattern, int32_t* pass_n_ops, uint64_t* pass_tile_mask);
 
+/* Host-only interpreter of the item-table rotation kernels (no CUDA call; test support): plans the program for the real
+ * layout of an unsharded n-qubit state as vqe_apply_pauli_rotations does, builds the per-item tables the kernels read
+ * (form 1: the 16-bit segments of k_col_stab, the default GPU path; form 0: the 32-bit words of k_col_tab) and applies
+ * them tile by tile, with the kernels' per-item arithmetic, to the HOST state psi_re (2^n doubles, in place).
+ * VQE_ERR_INVALID when the program has no real-layout collapsed-run plan. */
+int vqe_debug_coltab_host(int n_qubits, int tile_bits, int low_bits, int form, int n_rot, const uint64_t* xmask,
+                          const uint64_t* zmask, const int32_t* ny, const double* angle, double* psi_re,
+                          int32_t* n_passes, int32_t* n_words);
+
 /* Host-only view of the Pauli-sum planner (no CUDA call): X-mask grouping and packing of the groups into tile
  * passes (what vqe_paulisum_create builds).  *n_groups = distinct X-masks, *n_passes = state sweeps per evaluation;
  * per pass (at most `cap` written): number of groups, number of terms, tile-bit mask. */

@@ -33,6 +33,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <map>
 #include <string>
@@ -1269,6 +1270,298 @@ __global__ void __launch_bounds__(256, RL ? 4 : 3) k_tile_col(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------
+// k_col_tab: the real-layout collapsed-run pass with a host-built ITEM TABLE.  Which shared-memory element an item of a
+// run touches (index deposit, pattern, swizzle) and the Z parity of that element depend only on the masks of the program,
+// not on the tile or the angles, so the host tabulates them once per plan: one 32-bit word per item,
+//   bits 0-15  byte offset of the a-side element in the (swizzled) tile,  bit 16  parity(l & lz),  bits 17-  pattern number.
+// k_tile_col spends ~45 of its ~95 warp instructions per (warp, run) on that index work; here an item costs one coalesced
+// 4-byte load (through L1: every tile of the pass reads the same words), a sign flip, the pair load, 4 FP64 operations and
+// the pair store.  The words of run q+1 are fetched before the barrier that ends run q.
+// Programmatic dependent launch: the prologue (descriptor build) runs under the tail of the previous pass; the state is
+// first touched after griddepcontrol.wait.
+// ------------------------------------------------------------------------------------------
+struct ColTabRun {         // 32 bytes, shared memory, built once per CTA
+    double c, s;           // cos, sin of entry 0 (runs with a single active pattern never read the entry table)
+    uint32_t lxb;          // X-mask as a BYTE offset in the tile's shared-memory layout
+    uint32_t items;
+    uint32_t tab_off;      // first word of the run in the pass's item table
+    uint32_t ent0;         // first entry of the run | bit 31: several active patterns
+};
+static_assert(sizeof(ColTabRun) == 32, "ColTabRun layout");
+#define COLTAB_INVALID 0xffffffffu
+__device__ __forceinline__ void coltab_rotate(char* tb, uint32_t w, const ColTabRun& R, const double2* scs, uint32_t cs, double a, double b) {
+    double c = R.c, s = R.s;
+    if (R.ent0 >> 31) {
+        const double2 e = scs[(R.ent0 & 0x7fffffffu) + (w >> 17)];
+        c = e.x;
+        s = e.y;
+    }
+    const double sn = flipsign(s, (w >> 16) ^ cs);
+    const uint32_t off = w & 0xffffu;
+    *reinterpret_cast<double*>(tb + off) = fma(c, a, -sn * b);
+    *reinterpret_cast<double*>(tb + (off ^ R.lxb)) = fma(c, b, sn * a);
+}
+__global__ void __launch_bounds__(256, 4) k_col_tab(const __grid_constant__ CUtensorMap tmap, TileGeom g, const DevCol* __restrict__ cols,
+                                                    int n_cols, const DevColEntry* __restrict__ ents, int n_ents,
+                                                    const uint32_t* __restrict__ tab, int skeleton, int* __restrict__ err) {
+    extern __shared__ __align__(1024) double2 tile[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t ts = 1u << g.tbits;
+    char* tb = reinterpret_cast<char*>(tile);
+    ColTabRun* run = reinterpret_cast<ColTabRun*>(tb + ((size_t)ts << 3));
+    double2* scs = reinterpret_cast<double2*>(run + n_cols);
+    uint64_t* szout = reinterpret_cast<uint64_t*>(scs + n_ents);
+    uint32_t* scsign = reinterpret_cast<uint32_t*>(szout + n_cols);
+    __shared__ __align__(8) uint64_t s_mbar;
+    uint32_t mphase = 0;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) mbar_init(&s_mbar, 1);
+    for (int q = tid; q < n_cols; q += 256) {
+        const DevCol co = cols[q];
+        const DevColEntry e0 = ents[co.ent_begin];
+        ColTabRun R;
+        R.c = e0.c;
+        R.s = e0.s;
+        R.lxb = swz_idx8(co.lx, g.swz) << 3;
+        R.items = co.n_active << co.free_log;
+        R.tab_off = co.pad;
+        R.ent0 = co.ent_begin | (co.n_active > 1u ? 0x80000000u : 0u);
+        run[q] = R;
+        szout[q] = co.zout;
+    }
+    for (int q = tid; q < n_ents; q += 256) scs[q] = make_double2(ents[q].c, ents[q].s);
+    const BaseLane bl = base_lane_init(g);
+    __syncthreads();
+    // the item words of run 0 are the same for every tile
+    uint32_t f0 = COLTAB_INVALID, f1 = COLTAB_INVALID;
+    if (n_cols > 0) {
+        const uint32_t it0 = run[0].items, o0 = run[0].tab_off;
+        if (tid < it0) f0 = __ldg(tab + o0 + tid);
+        if (tid + 256u < it0) f1 = __ldg(tab + o0 + tid + 256u);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous pass has written the whole state
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = tile_base_warp(g, bl, t);
+        const uint64_t sbase = base | g.sign_base;
+        __syncthreads();  // the store of the previous tile has read shared memory (thread 0 waited for it)
+        if (tid == 0) tma_load_tile(tile, &tmap, g, base, &s_mbar);
+        for (int r = tid; r < n_cols; r += 256) scsign[r] = (uint32_t)__popcll(sbase & szout[r]) & 1u;
+        __syncthreads();  // scsign visible
+        if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
+        mphase ^= 1u;
+        uint32_t w0 = f0, w1 = f1;
+        const int nq = skeleton ? 0 : n_cols;
+        for (int q = 0; q < nq; ++q) {
+            const ColTabRun R = run[q];
+            const uint32_t cs = scsign[q];
+            double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
+            if (w0 != COLTAB_INVALID) {
+                a0 = *reinterpret_cast<const double*>(tb + (w0 & 0xffffu));
+                b0 = *reinterpret_cast<const double*>(tb + ((w0 & 0xffffu) ^ R.lxb));
+            }
+            if (w1 != COLTAB_INVALID) {
+                a1 = *reinterpret_cast<const double*>(tb + (w1 & 0xffffu));
+                b1 = *reinterpret_cast<const double*>(tb + ((w1 & 0xffffu) ^ R.lxb));
+            }
+            uint32_t n0 = COLTAB_INVALID, n1 = COLTAB_INVALID;
+            if (q + 1 < n_cols) {  // next run's words: in flight across the arithmetic and the barrier
+                const uint32_t itn = run[q + 1].items, on = run[q + 1].tab_off;
+                if (tid < itn) n0 = __ldg(tab + on + tid);
+                if (tid + 256u < itn) n1 = __ldg(tab + on + tid + 256u);
+            }
+            if (w0 != COLTAB_INVALID) coltab_rotate(tb, w0, R, scs, cs, a0, b0);
+            if (w1 != COLTAB_INVALID) coltab_rotate(tb, w1, R, scs, cs, a1, b1);
+            // items beyond two per thread (JW singles: 8 per thread in a 13-bit tile; tabulated plane rotations): four at a time
+            for (uint32_t it = tid + 512u; it < R.items; it += 1024u) {
+                uint32_t w[4];
+                double a[4], b[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = (it + 256u * k < R.items) ? __ldg(tab + R.tab_off + it + 256u * k) : COLTAB_INVALID;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (w[k] != COLTAB_INVALID) {
+                        a[k] = *reinterpret_cast<const double*>(tb + (w[k] & 0xffffu));
+                        b[k] = *reinterpret_cast<const double*>(tb + ((w[k] & 0xffffu) ^ R.lxb));
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (w[k] != COLTAB_INVALID) coltab_rotate(tb, w[k], R, scs, cs, a[k], b[k]);
+            }
+            w0 = n0;
+            w1 = n1;
+            if (q + 1 == n_cols) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes -> the async-proxy store
+            __syncthreads();
+        }
+        if (nq == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+        }
+        if (tid == 0) {
+            tma_store_tile(tile, &tmap, g, base);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores have landed
+}
+
+// ------------------------------------------------------------------------------------------
+// k_col_stab: k_col_tab with the pass's item table in SHARED memory, 16 bits per item: (element index in the swizzled tile)
+// << 3 | parity(l & lz), i.e. the byte offset with the sign in bit 0; 0xffff = no item.  Global-memory words cost an L2 round
+// trip per run while the L2 is saturated by the streaming tiles; a copy next to the tile costs one LDS.U16 per item.
+// The table is cut into SEGMENTS of 512 slots: every active pattern of a run is ceil(items / 512) segments (a JW double in
+// a 13-bit tile: exactly one, a JW single: four), each with its own 32-byte descriptor (cos, sin, X offset, flags); only the
+// last segment of a run ends with the CTA barrier -- the items of a run touch disjoint pairs.  A thread's slot of segment
+// e + 1 is fetched before the barrier of segment e, so the chain of a run is  pair load -> 4 FP64 operations -> pair store
+// -> barrier.  Shared memory is addressed through 32-bit shared-window addresses (ld.shared / st.shared).
+// Passes whose table does not fit next to the tile keep k_tile_col.
+// ------------------------------------------------------------------------------------------
+#define COLSEG 512u
+struct ColSub {            // 32 bytes, shared memory, one per segment
+    double c, s;
+    uint32_t lxb;          // X-mask as a BYTE offset in the tile's shared-memory layout
+    uint32_t meta;         // bit 0: outside-tile Z parity of the tile at hand | bit 16: last segment of its run (barrier) | bit 17: all 512 slots hold items
+    uint32_t zsel;         // which of the run's outside-tile Z masks (index into the per-segment array)
+    uint32_t pad;
+};
+static_assert(sizeof(ColSub) == 32, "ColSub layout");
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+// THREADS = 512: one slot per thread and segment; 256: two.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_col_stab(const __grid_constant__ CUtensorMap tmap, TileGeom g, const DevCol* __restrict__ cols,
+                                                     int n_cols, const DevColEntry* __restrict__ ents, int n_seg,
+                                                     const uint16_t* __restrict__ tab, int skeleton, int* __restrict__ err) {
+    constexpr int PF = (int)COLSEG / THREADS;   // slots per thread and segment
+    extern __shared__ __align__(1024) double2 tile[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t ts = 1u << g.tbits;
+    char* tb = reinterpret_cast<char*>(tile);
+    ColSub* sub = reinterpret_cast<ColSub*>(tb + ((size_t)ts << 3));
+    uint64_t* szout = reinterpret_cast<uint64_t*>(sub + n_seg);
+    uint16_t* stab = reinterpret_cast<uint16_t*>(szout + n_seg);   // n_seg * 40 bytes after the tile: 8-byte aligned; the copy below needs 16
+    stab = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(stab) + 15u) & ~(uintptr_t)15u);
+    __shared__ __align__(8) uint64_t s_mbar;
+    uint32_t mphase = 0;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) mbar_init(&s_mbar, 1);
+    for (int q = tid; q < n_cols; q += THREADS) {
+        const DevCol co = cols[q];
+        const uint32_t lxb = swz_idx8(co.lx, g.swz) << 3;
+        const uint32_t per_pat = max(1u, (1u << co.free_log) / COLSEG);
+        const bool full = (1u << co.free_log) >= COLSEG;
+        uint32_t sg = __ldg(reinterpret_cast<const uint32_t*>(tab) + q);   // first segment of the run in the pass (table header)
+        for (uint32_t pi = 0; pi < co.n_active; ++pi) {
+            const DevColEntry en = ents[co.ent_begin + pi];
+            for (uint32_t k = 0; k < per_pat; ++k, ++sg) {
+                ColSub S;
+                S.c = en.c;
+                S.s = en.s;
+                S.lxb = lxb;
+                S.meta = ((pi + 1u == co.n_active && k + 1u == per_pat) ? 0x10000u : 0u) | (full ? 0x20000u : 0u);
+                S.zsel = 0;
+                S.pad = 0;
+                sub[sg] = S;
+                szout[sg] = co.zout;
+            }
+        }
+    }
+    {   // the table: 16-byte copies (a segment is 1 KiB)
+        const uint4* src = reinterpret_cast<const uint4*>(tab + ((2 * n_cols + 7) & ~7));
+        uint4* dst = reinterpret_cast<uint4*>(stab);
+        const int n16 = n_seg * (int)(COLSEG / 8u);
+        for (int k = tid; k < n16; k += THREADS) dst[k] = __ldg(src + k);
+    }
+    const BaseLane bl = base_lane_init(g);
+    const uint32_t tile32 = smem_u32(tile), sub32 = smem_u32(sub), stab32 = smem_u32(stab) + 2u * tid;
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous pass has written the whole state
+    const int ns = skeleton ? 0 : n_seg;
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        const uint64_t base = tile_base_warp(g, bl, t);
+        const uint64_t sbase = base | g.sign_base;
+        __syncthreads();  // the store of the previous tile has read shared memory (thread 0 waited for it)
+        if (tid == 0) tma_load_tile(tile, &tmap, g, base, &s_mbar);
+        for (int r = tid; r < n_seg; r += THREADS) sub[r].meta = (sub[r].meta & ~1u) | ((uint32_t)__popcll(sbase & szout[r]) & 1u);
+        uint32_t w[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) w[k] = ns > 0 ? lds_u16(stab32 + 2u * THREADS * k) : 0xffffu;
+        __syncthreads();  // signs visible
+        if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
+        mphase ^= 1u;
+        for (int e = 0; e < ns; ++e) {
+            const uint4 d0 = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(sub) + 32 * e);
+            const uint2 d1 = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(sub) + 32 * e + 16);
+            const double c = __hiloint2double((int)d0.y, (int)d0.x);
+            const uint32_t lxb = d1.x, meta = d1.y;
+            double a[PF], b[PF];
+            uint32_t off[PF];
+            if (meta & 0x20000u) {  // every slot of the segment holds an item (uniform): no per-thread checks
+#pragma unroll
+                for (int k = 0; k < PF; ++k) {
+                    off[k] = w[k] & 0xfff8u;   // relative to the tile: the partner is an XOR of the RELATIVE offset
+                    a[k] = lds_f64(tile32 + off[k]);
+                    b[k] = lds_f64(tile32 + (off[k] ^ lxb));
+                }
+                uint32_t nw[PF];
+#pragma unroll
+                for (int k = 0; k < PF; ++k) nw[k] = e + 1 < ns ? lds_u16(stab32 + 2u * (COLSEG * (uint32_t)(e + 1) + THREADS * k)) : 0xffffu;
+#pragma unroll
+                for (int k = 0; k < PF; ++k) {
+                    const double sn = __hiloint2double((int)(d0.w ^ ((w[k] ^ meta) << 31)), (int)d0.z);
+                    sts_f64(tile32 + off[k], fma(c, a[k], -sn * b[k]));
+                    sts_f64(tile32 + (off[k] ^ lxb), fma(c, b[k], sn * a[k]));
+                }
+#pragma unroll
+                for (int k = 0; k < PF; ++k) w[k] = nw[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < PF; ++k) {
+                    off[k] = w[k] & 0xfff8u;
+                    a[k] = b[k] = 0.0;
+                    if (w[k] != 0xffffu) {
+                        a[k] = lds_f64(tile32 + off[k]);
+                        b[k] = lds_f64(tile32 + (off[k] ^ lxb));
+                    }
+                }
+                uint32_t nw[PF];
+#pragma unroll
+                for (int k = 0; k < PF; ++k) nw[k] = e + 1 < ns ? lds_u16(stab32 + 2u * (COLSEG * (uint32_t)(e + 1) + THREADS * k)) : 0xffffu;
+#pragma unroll
+                for (int k = 0; k < PF; ++k)
+                    if (w[k] != 0xffffu) {
+                        const double sn = __hiloint2double((int)(d0.w ^ ((w[k] ^ meta) << 31)), (int)d0.z);
+                        sts_f64(tile32 + off[k], fma(c, a[k], -sn * b[k]));
+                        sts_f64(tile32 + (off[k] ^ lxb), fma(c, b[k], sn * a[k]));
+                    }
+#pragma unroll
+                for (int k = 0; k < PF; ++k) w[k] = nw[k];
+            }
+            if (e + 1 == ns) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes -> the async-proxy store
+            if (meta & 0x10000u) __syncthreads();
+        }
+        if (ns == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+        }
+        if (tid == 0) {
+            tma_store_tile(tile, &tmap, g, base);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores have landed
+    (void)sub32;
+}
+
+// ------------------------------------------------------------------------------------------
 // Tile ring.  One persistent CTA per SM owns NSLOT shared-memory tile slots (3 x 64 KiB).  Warp 0 is the copy issuer:
 // bulk loads (cp.async.bulk + mbarrier complete_tx) run two tiles ahead of the arithmetic and the bulk store of tile k
 // drains while tile k+1 is being worked on, so HBM traffic and arithmetic overlap by construction instead of relying on
@@ -2017,19 +2310,25 @@ __device__ __forceinline__ double lean_entries(const char* tb, const DevFlat2* _
         const uint32_t vs = swz_off(u.v, swz);
         double part = 0.0;
         if (u.tab == 0xffffu) {
+            // The sign of pair j is LINEAR in the bits of j (o_j is the XOR of three basis offsets, plus the chunk part that
+            // all eight share): sum_j (-1)^sigma(j) w_j is a three-level butterfly with one +-1.0 factor per level -- seven
+            // DFMAs and no per-pair sign arithmetic.  The common sign (bit 0 of jsign) joins the entry's sign below.
+            double wj[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint32_t off = vs ^ u.o[j];
-                double w;
                 if (REAL) {
-                    w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
+                    wj[j] = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
                 } else {
                     const double2 a = *reinterpret_cast<const double2*>(tb + off);
                     const double2 b = *reinterpret_cast<const double2*>(tb + (off ^ u.lx16));
-                    w = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
+                    wj[j] = fma(b.x, a.x, b.y * a.y);  // Re(conj(b) a)
                 }
-                part += flipsign(w, u.jsign >> j);
             }
+            const double g0 = flipsign(1.0, u.jsign ^ (u.jsign >> 1)), g1 = flipsign(1.0, u.jsign ^ (u.jsign >> 2)),
+                         g2 = flipsign(1.0, u.jsign ^ (u.jsign >> 4));
+            const double t0 = fma(g0, wj[1], wj[0]), t1 = fma(g0, wj[3], wj[2]), t2 = fma(g0, wj[5], wj[4]), t3 = fma(g0, wj[7], wj[6]);
+            part = flipsign(fma(g2, fma(g1, t3, t2), fma(g1, t1, t0)), u.jsign);
         } else {
             const double gl = s_beta[u.bidx] + __ldg(addtab + u.tab + lane);
 #pragma unroll
@@ -2096,6 +2395,173 @@ __global__ void __launch_bounds__(THREADS, RL ? 4 : 3) k_expect_lean(const __gri
         }
         __syncthreads();
         er += lean_entries<REAL, RL>(tb, flats, f0 + (int)warp, f1, (int)nw, lane, sbase, fzout, addtab, s_beta, g.swz);
+    }
+    double2 sres = block_sum2(er, 0.0, red);
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
+}
+
+// One entry's pair sum on one real-layout tile (see lean_entries): eight pairs per lane, signs by the three-level butterfly.
+__device__ __forceinline__ double lean_part_rl(const char* tb, const LeanUnit& u, uint32_t vs, uint32_t lane, const double* __restrict__ addtab,
+                                               const double* s_beta) {
+    double part;
+    if (u.tab == 0xffffu) {
+        double wj[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t off = vs ^ u.o[j];
+            wj[j] = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
+        }
+        const double g0 = flipsign(1.0, u.jsign ^ (u.jsign >> 1)), g1 = flipsign(1.0, u.jsign ^ (u.jsign >> 2)),
+                     g2 = flipsign(1.0, u.jsign ^ (u.jsign >> 4));
+        const double t0 = fma(g0, wj[1], wj[0]), t1 = fma(g0, wj[3], wj[2]), t2 = fma(g0, wj[5], wj[4]), t3 = fma(g0, wj[7], wj[6]);
+        part = flipsign(fma(g2, fma(g1, t3, t2), fma(g1, t1, t0)), u.jsign);
+    } else {
+        part = 0.0;
+        const double gl = s_beta[u.bidx] + __ldg(addtab + u.tab + lane);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t off = vs ^ u.o[j];
+            const double w = *reinterpret_cast<const double*>(tb + off) * *reinterpret_cast<const double*>(tb + (off ^ u.lx16));
+            part = fma(flipsign(w, u.jsign >> j), gl + __ldg(addtab + u.hi0 + j), part);
+        }
+    }
+    return part;
+}
+// lean_entries for TWO real-layout tiles resident at once (tb1 == nullptr: one): an entry is fetched and decoded once
+// (about two thirds of the instructions of an entry are decode: descriptor unpack, index deposit, parity) and evaluated on
+// both tiles -- only the outside-tile sign and the per-tile constants differ.
+__device__ __forceinline__ double lean_entries_pair(const char* tb0, const char* tb1, const DevFlat2* __restrict__ flats, int e0, int e1,
+                                                    int stride, uint32_t lane, uint64_t sbase0, uint64_t sbase1,
+                                                    const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
+                                                    const double* s_beta0, const double* s_beta1, uint32_t swz) {
+    double er = 0.0;
+    if (e0 >= e1) return er;
+    const uint4* ep = reinterpret_cast<const uint4*>(flats + e0);
+    uint4 q0 = __ldg(ep), q1 = __ldg(ep + 1), q2 = __ldg(ep + 2);
+    uint64_t zo = __ldg(fzout + (q0.w >> 16));
+    for (int e = e0; e < e1; e += stride) {
+        uint4 n0 = q0, n1 = q1, n2 = q2;
+        uint64_t nzo = zo;
+        if (e + stride < e1) {
+            const uint4* np = reinterpret_cast<const uint4*>(flats + e + stride);
+            n0 = __ldg(np);
+            n1 = __ldg(np + 1);
+            n2 = __ldg(np + 2);
+        }
+        LeanUnit u;
+        lean_decode(q0, q1, q2, lane, u, 3u);
+        const uint32_t vs = swz_off(u.v, swz);
+        double part = flipsign(lean_part_rl(tb0, u, vs, lane, addtab, s_beta0), u.s0 + (uint32_t)__popcll(sbase0 & zo));
+        if (tb1) part += flipsign(lean_part_rl(tb1, u, vs, lane, addtab, s_beta1), u.s0 + (uint32_t)__popcll(sbase1 & zo));
+        er = fma(u.fr, part, er);
+        if (e + stride < e1) nzo = __ldg(fzout + (n0.w >> 16));
+        q0 = n0; q1 = n1; q2 = n2;
+        zo = nzo;
+    }
+    return er;
+}
+// Real-layout expectation pass, pair mode: both tile slots of the CTA are loaded and every entry is evaluated on both
+// (lean_entries_pair); other CTAs of the SM cover the load.  Same launch geometry and shared-memory layout as k_expect_rl2.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 3) k_expect_rlp(const __grid_constant__ CUtensorMap tmap, TileGeom g,
+                                                        const DevFlat2* __restrict__ flats, int n_flats,
+                                                        const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
+                                                        const DevAddPat* __restrict__ addpat, int n_addpat,
+                                                        const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
+                                                        int* __restrict__ err) {
+    extern __shared__ __align__(1024) double2 tile[];
+    __shared__ double red[64];
+    __shared__ __align__(8) uint64_t s_mbar;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t slot_bytes = 8u << g.tbits;
+    char* tb = reinterpret_cast<char*>(tile);
+    double* s_beta = reinterpret_cast<double*>(tb + 2u * slot_bytes);   // [2][n_addpat]
+    if (threadIdx.x == 0) mbar_init(&s_mbar, 2);
+    const BaseLane bl = base_lane_init(g);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int fper = (n_flats + gridDim.y - 1) / gridDim.y;   // blockIdx.y splits the entry list (states with few tiles)
+    const int f0 = min(n_flats, (int)blockIdx.y * fper), f1 = min(n_flats, f0 + fper);
+    uint32_t mphase = 0;
+    double er = 0.0;
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the state is complete
+    for (uint64_t t = blockIdx.x; t < g.n_tiles; t += 2ull * gridDim.x) {
+        const uint64_t t1 = t + gridDim.x;
+        const bool two = t1 < g.n_tiles;
+        const uint64_t base0 = tile_base_warp(g, bl, t);
+        const uint64_t base1 = tile_base_warp(g, bl, two ? t1 : t);
+        __syncthreads();  // the previous pair is fully consumed
+        if (threadIdx.x == 0) {
+            tma_load_tile(tile, &tmap, g, base0, &s_mbar);
+            if (two) tma_load_tile(reinterpret_cast<double2*>(tb + slot_bytes), &tmap, g, base1, &s_mbar);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_mbar)) : "memory");
+        }
+        lean_betas(s_beta, addpat, n_addpat, addout, base0 | g.sign_base);
+        if (two) lean_betas(s_beta + n_addpat, addpat, n_addpat, addout, base1 | g.sign_base);
+        if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
+        mphase ^= 1u;
+        __syncthreads();
+        er += lean_entries_pair(tb, two ? tb + slot_bytes : nullptr, flats, f0 + (int)warp, f1, (int)nw, lane, base0 | g.sign_base,
+                                base1 | g.sign_base, fzout, addtab, s_beta, s_beta + n_addpat, g.swz);
+    }
+    double2 sres = block_sum2(er, 0.0, red);
+    if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
+}
+
+// Real-layout expectation pass with TWO tile slots per CTA: the pass only reads the state, so the tensor-map load of the
+// CTA's next tile (and its per-tile constants) is issued before the entries of the current tile are evaluated -- no warp
+// ever waits for HBM after the first tile.  Three CTAs per SM (2 x 32 KiB each).  Programmatic dependent launch: the
+// prologue runs under the tail of the previous pass; the state is first read after griddepcontrol.wait.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 3) k_expect_rl2(const __grid_constant__ CUtensorMap tmap, TileGeom g,
+                                                        const DevFlat2* __restrict__ flats, int n_flats,
+                                                        const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
+                                                        const DevAddPat* __restrict__ addpat, int n_addpat,
+                                                        const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
+                                                        int* __restrict__ err) {
+    extern __shared__ __align__(1024) double2 tile[];
+    __shared__ double red[64];
+    __shared__ __align__(8) uint64_t s_mbar[2];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t slot_bytes = 8u << g.tbits;
+    char* tb = reinterpret_cast<char*>(tile);
+    double* s_beta = reinterpret_cast<double*>(tb + 2u * slot_bytes);   // [2][n_addpat]
+    if (threadIdx.x == 0) {
+        mbar_init(&s_mbar[0], 1);
+        mbar_init(&s_mbar[1], 1);
+    }
+    const BaseLane bl = base_lane_init(g);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int fper = (n_flats + gridDim.y - 1) / gridDim.y;   // blockIdx.y splits the entry list (states with few tiles)
+    const int f0 = min(n_flats, (int)blockIdx.y * fper), f1 = min(n_flats, f0 + fper);
+    uint32_t ph0 = 0, ph1 = 0;
+    double er = 0.0;
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the state is complete
+    uint64_t t = blockIdx.x;
+    uint64_t base = 0;
+    if (t < g.n_tiles) {
+        base = tile_base_warp(g, bl, t);
+        if (threadIdx.x == 0) tma_load_tile(tile, &tmap, g, base, &s_mbar[0]);
+        lean_betas(s_beta, addpat, n_addpat, addout, base | g.sign_base);
+    }
+    __syncthreads();
+    for (uint32_t k = 0; t < g.n_tiles; t += gridDim.x, ++k) {
+        const uint32_t sl = k & 1u;
+        const uint64_t sbase = base | g.sign_base;
+        const uint64_t tn = t + gridDim.x;
+        if (tn < g.n_tiles) {  // the other slot was consumed before the barrier that ended the previous iteration
+            base = tile_base_warp(g, bl, tn);
+            if (threadIdx.x == 0)
+                tma_load_tile(reinterpret_cast<double2*>(tb + (sl ^ 1u) * slot_bytes), &tmap, g, base, &s_mbar[sl ^ 1u]);
+            lean_betas(s_beta + (sl ^ 1u) * n_addpat, addpat, n_addpat, addout, base | g.sign_base);
+        }
+        const bool ok = mbar_wait(&s_mbar[sl], sl ? ph1 : ph0);
+        if (!ok && err) *err = 2;
+        if (sl) ph1 ^= 1u; else ph0 ^= 1u;
+        er += lean_entries<true, true>(tb + sl * slot_bytes, flats, f0 + (int)warp, f1, (int)nw, lane, sbase, fzout, addtab,
+                                       s_beta + sl * n_addpat, g.swz);
+        __syncthreads();  // slot sl is free again; the constants of the next tile are in place
     }
     double2 sres = block_sum2(er, 0.0, red);
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
@@ -2368,6 +2834,10 @@ struct vqe_ctx {
     std::vector<std::pair<int, int>> swap_history;  // (global slot, local slot) of every swap since the last reset
     uint64_t n_swaps = 0, swap_bytes = 0;   // statistics: swaps executed, bytes this rank read from its partners in swaps
     PlanCache* plan_cache = nullptr;        // see rotations_impl
+    char* d_coltab = nullptr;               // item table of the plan whose identity is coltab_gen (k_col_stab: 16-bit items; k_col_tab: 32-bit)
+    size_t coltab_cap = 0;                  // in bytes
+    uint64_t coltab_gen = 0;
+    int coltab_mode = 0;                    // 1: 32-bit words (k_col_tab), 2: 16-bit items (k_col_stab)
     double2* gstage[2] = {nullptr, nullptr};  // staging buffers of gather-form peer passes (two: chunk k + 1 is fetched under chunk k)
     size_t gstage_cap[2] = {0, 0};            // in amplitudes
     cudaStream_t stream = nullptr;
@@ -2530,6 +3000,13 @@ static int set_kernel_attrs(int device) {
     SET_SMEM((k_tile_col<false, false>));
     SET_SMEM((k_tile_col<true, false>));
     SET_SMEM((k_tile_col<true, true>));
+    SET_SMEM(k_col_tab);
+    SET_SMEM((k_col_stab<256, 3>));
+    SET_SMEM((k_col_stab<512, 2>));
+    SET_SMEM((k_col_stab<512, 3>));
+    SET_SMEM(k_expect_rl2<256>);
+    SET_SMEM(k_expect_rlp<256>);
+    SET_SMEM(k_expect_rl2<384>);
     SET_SMEM(k_col_pipe<false>);
     SET_SMEM(k_col_pipe<true>);
     SET_SMEM(k_expect_pipe<false>);
@@ -2648,6 +3125,7 @@ static void free_ctx(vqe_ctx* c) {
     if (c->d_peer_flags) cudaFree(c->d_peer_flags);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->plan_cache) free_plan_cache(c->plan_cache);
+    if (c->d_coltab) cudaFree(c->d_coltab);
     for (int sb = 0; sb < 2; ++sb)
         if (c->gstage[sb]) cudaFree(c->gstage[sb]);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -3124,6 +3602,13 @@ static TmaShape plan_tma(const TilePlan& tp, bool swizzle, bool rl = false) {
 static bool tma_available(const TilePlan& tp, bool swizzle, bool rl = false) {
     return env_int("VQE_TMA", 1) && tmap_encoder() && plan_tma(tp, swizzle, rl).ok;
 }
+// the shared-memory swizzle make_tmap(tp, ..., -1, true) will choose for a real-layout tile (0x70 or 0)
+static uint32_t rl_tile_swz(const TilePlan& tp) {
+    const bool want = env_int("VQE_SWIZZLE", 1) != 0;
+    TmaShape sh = plan_tma(tp, want, true);
+    if (!sh.ok && want) sh = plan_tma(tp, false, true);
+    return sh.ok && sh.swizzled ? 0x70u : 0u;
+}
 // swizzle: -1 = swizzled when the plan allows it, 0 = natural layout, 1 = swizzled or nothing
 static void make_tmap(const TilePlan& tp, double2* ptr, TileGeom& g, CUtensorMap* map, int swizzle = -1, bool rl = false) {
     memset(map, 0, sizeof *map);
@@ -3444,6 +3929,15 @@ struct OpPlan {
     std::vector<double> rot_cos;    // cosine of every dop (fast passes)
     bool cacheable = true;
     int tile_bits = 12;             // 13: planned for the real layout of the state (tiles of 2^13 doubles = 64 KiB)
+    // item table of the real-layout collapsed-run kernel (k_col_tab), built on first use (launch_plan) and kept on the
+    // device per context while the plan lives: angle-independent, so a cached plan uploads it once
+    mutable uint64_t gen = 0;                  // identity of the table (0: not built)
+    mutable std::vector<uint32_t> coltab;      // all passes
+    mutable std::vector<size_t> coltab_off;    // first word of every pass
+    mutable std::vector<uint32_t> coltab_swz;  // the tile swizzle every pass was tabulated for
+    mutable std::vector<uint16_t> coltab16;    // the same items in 16 bits (k_col_stab), every pass padded to a multiple of 8 items
+    mutable std::vector<size_t> coltab16_off;
+    mutable std::vector<uint32_t> coltab16_seg;  // segments per pass
 };
 
 static bool fast_eligible(const HostOp& h) {
@@ -3922,6 +4416,13 @@ static int plan_ops(int n, int nl, int tile_bits, int low_bits, int threads_cfg,
                             p.sup_end - p.sup_begin, p.need_lo.size(), p.need_hi.size(), half_groups, p.gather ? "gather" : "exchange");
             }
         }
+        if (p.fast) {   // first word of every collapsed run in the pass's item table (k_col_tab)
+            uint32_t running = 0;
+            for (size_t q = p.col_begin; q < dcols.size(); ++q) {
+                dcols[q].pad = running;
+                running += dcols[q].n_active << dcols[q].free_log;
+            }
+        }
         passes.push_back(std::move(p));
         i = j;
     }
@@ -3956,6 +4457,70 @@ static bool plan_runs_in_real_layout(const OpPlan& plan) {
         if (!(tma_available(ps.tp, true, true) || tma_available(ps.tp, false, true))) return false;
     }
     return true;
+}
+// Item table of k_col_tab for every pass of a real-layout collapsed-run plan (pure host code).  One word per item of a run:
+// bits 0-15 byte offset of the a-side element in the pass's (swizzled) shared-memory tile, bit 16 parity(l & lz),
+// bits 17- pattern number within the run.  The index arithmetic is the one k_tile_col does per thread and run (col_prep).
+static int build_coltab(const OpPlan& plan) {
+    static std::atomic<uint64_t> next_gen{1};
+    const std::vector<OpPass>& passes = plan.passes;
+    plan.coltab.clear();
+    plan.coltab_off.assign(passes.size(), 0);
+    plan.coltab_swz.assign(passes.size(), 0);
+    for (size_t p = 0; p < passes.size(); ++p) {
+        const OpPass& ps = passes[p];
+        const uint32_t swz = rl_tile_swz(ps.tp);
+        plan.coltab_off[p] = plan.coltab.size();
+        plan.coltab_swz[p] = swz;
+        for (size_t q = ps.col_begin; q < ps.col_end; ++q) {
+            const DevCol& co = plan.dcols[q];
+            const uint32_t items = co.n_active << co.free_log;
+            if (co.pad != plan.coltab.size() - plan.coltab_off[p] || ps.tp.tbits > 13)
+                return fail(VQE_ERR_INVALID, "item table of pass %zu is inconsistent with its run descriptors", p);
+            for (uint32_t it = 0; it < items; ++it) {
+                uint32_t l = it & ((1u << co.free_log) - 1u);
+                for (int d = 0; d < 6; ++d) l += l & co.dpos[d];
+                const uint32_t pi = it >> co.free_log;
+                l |= plan.dents[ps.ent_begin + co.ent_begin + pi].pat;
+                const uint32_t par = (uint32_t)__builtin_popcount(l & co.lz) & 1u;
+                plan.coltab.push_back((swz_idx8(l, swz) << 3) | (par << 16) | (pi << 17));
+            }
+        }
+    }
+    // 16-bit form (k_col_stab): per pass [first segment of every run: n_cols x uint32, padded to 16 bytes][segments of 512 slots]:
+    // slot = (element index << 3) | parity, 0xffff = empty; a pattern of a run is ceil(2^free_log / 512) segments
+    plan.coltab16.clear();
+    plan.coltab16_off.assign(passes.size(), 0);
+    plan.coltab16_seg.assign(passes.size(), 0);
+    for (size_t p = 0; p < passes.size(); ++p) {
+        const OpPass& ps = passes[p];
+        plan.coltab16_off[p] = plan.coltab16.size();
+        const size_t n_cols = ps.col_end - ps.col_begin;
+        const size_t head = (2 * n_cols + 7) & ~size_t(7);   // in uint16
+        plan.coltab16.resize(plan.coltab16.size() + head, 0);
+        uint32_t n_seg = 0;
+        for (size_t q = ps.col_begin; q < ps.col_end; ++q) {
+            const DevCol& co = plan.dcols[q];
+            uint32_t* first = reinterpret_cast<uint32_t*>(plan.coltab16.data() + plan.coltab16_off[p]) + (q - ps.col_begin);
+            *first = n_seg;
+            const uint32_t per_pat_items = 1u << co.free_log;
+            const uint32_t per_pat_seg = std::max<uint32_t>(1u, per_pat_items / COLSEG);
+            for (uint32_t pi = 0; pi < co.n_active; ++pi)
+                for (uint32_t k = 0; k < per_pat_seg; ++k, ++n_seg)
+                    for (uint32_t sl = 0; sl < COLSEG; ++sl) {
+                        const uint32_t it_in_pat = k * COLSEG + sl;
+                        if (it_in_pat >= per_pat_items) {
+                            plan.coltab16.push_back(0xffffu);
+                            continue;
+                        }
+                        const uint32_t w = plan.coltab[plan.coltab_off[p] + co.pad + (pi << co.free_log) + it_in_pat];
+                        plan.coltab16.push_back((uint16_t)((w & 0xfff8u) | ((w >> 16) & 1u)));
+                    }
+        }
+        plan.coltab16_seg[p] = n_seg;
+    }
+    plan.gen = next_gen++;
+    return VQE_OK;
 }
 // CTAs of a gather-form pass launch that fetch the NEXT chunk's partner amplitudes (the launch keeps its persistent grid:
 // they are carved out of it and grown back when the grid would otherwise be too small to hold them)
@@ -4043,6 +4608,35 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
             rc = ensure_complex(c, buf);
             if (rc) return rc;
         }
+    // item table of k_col_tab: built once per plan, uploaded once per context and plan
+    // VQE_COL_TAB: 0 = k_tile_col (index arithmetic per thread and run), 1 = k_col_tab (32-bit items in global memory),
+    // 2 = k_col_stab (16-bit items next to the tile in shared memory; passes whose table does not fit keep k_tile_col)
+    const int tab_mode = rl_plan ? std::max(0, std::min(2, env_int("VQE_COL_TAB", 2))) : 0;
+    const bool use_tab = tab_mode != 0;
+    if (use_tab) {
+        if (plan.gen == 0) {
+            rc = build_coltab(plan);
+            if (rc) return rc;
+        }
+        const void* tab_src = tab_mode == 2 ? (const void*)plan.coltab16.data() : (const void*)plan.coltab.data();
+        const size_t tab_bytes = tab_mode == 2 ? plan.coltab16.size() * sizeof(uint16_t) : plan.coltab.size() * sizeof(uint32_t);
+        for (vqe_ctx* c : rs.r) {
+            if (c->coltab_gen == plan.gen && c->coltab_mode == tab_mode) continue;
+            CK(cudaSetDevice(c->device));
+            if (c->coltab_cap < std::max<size_t>(16, tab_bytes)) {
+                if (c->d_coltab) cudaFree(c->d_coltab);
+                c->d_coltab = nullptr;
+                c->coltab_cap = 0;
+                if (cudaMalloc((void**)&c->d_coltab, std::max<size_t>(16, tab_bytes)) != cudaSuccess)
+                    return fail(VQE_ERR_NOMEM, "item table of the rotation plan (%.1f MB)", tab_bytes / 1e6);
+                c->coltab_cap = std::max<size_t>(16, tab_bytes);
+            }
+            if (tab_bytes) CK(cudaMemcpyAsync(c->d_coltab, tab_src, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+            c->h2d_bytes += tab_bytes;
+            c->coltab_gen = plan.gen;
+            c->coltab_mode = tab_mode;
+        }
+    }
     // one launch of the pass kernel on one rank (gg.n_need != 0: gather form over the tiles of the current chunk)
     auto launch_pass = [&](vqe_ctx* c, size_t p, const TileGeom& g, const Shards& sh, const GatherGeom& gg,
                            const GatherGeom* gnext = nullptr, uint64_t next_first = 0, uint64_t next_tiles = 0,
@@ -4075,6 +4669,53 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                 if (!gt.tma) return fail(VQE_ERR_CUDA, "real-layout tensor map of a rotation pass could not be encoded");
                 const size_t smem_r = (8ull << ps.tp.tbits) + (size_t)n_cols * (sizeof(ColLite) + 8 + 4) + (size_t)n_ents * sizeof(DevColEntry);
                 const int grid_r = tile_grid(c, g.n_tiles, smem_r <= 54 * 1024 ? 4 : (smem_r <= 74 * 1024 ? 3 : 2));
+                const size_t n_seg = tab_mode == 2 ? plan.coltab16_seg[p] : 0;
+                const size_t smem_s = (8ull << ps.tp.tbits) + n_seg * (sizeof(ColSub) + 8) + 16 + n_seg * COLSEG * sizeof(uint16_t);
+                if (tab_mode == 2 && smem_s <= 110 * 1024) {
+                    if (gt.swz != plan.coltab_swz[p]) return fail(VQE_ERR_CUDA, "tile swizzle of pass %zu differs from its item table", p);
+                    const int ctas_s = smem_s <= 74 * 1024 ? 3 : 2;
+                    const int grid_s = tile_grid(c, g.n_tiles, ctas_s);
+                    int thr_s = env_int(ctas_s == 3 ? "VQE_STAB_THREADS3" : "VQE_STAB_THREADS2", 512);
+                    if (thr_s != 512) thr_s = 256;
+                    cudaLaunchConfig_t cfg;
+                    memset(&cfg, 0, sizeof cfg);
+                    cfg.gridDim = dim3((unsigned)grid_s);
+                    cfg.blockDim = dim3((unsigned)thr_s);
+                    cfg.dynamicSmemBytes = smem_s;
+                    cfg.stream = c->stream;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = env_int("VQE_PDL", 1) != 0 ? 1 : 0;
+                    auto kern = thr_s == 512 ? (ctas_s == 3 ? k_col_stab<512, 3> : k_col_stab<512, 2>) : k_col_stab<256, 3>;
+                    CK(cudaLaunchKernelEx(&cfg, kern, tmap, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                                          (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)n_seg,
+                                          (const uint16_t*)c->d_coltab + plan.coltab16_off[p], env_int("VQE_DEBUG_SKELETON", 0), c->d_err));
+                    c->launches++;
+                    return VQE_OK;
+                }
+                if (tab_mode == 1) {
+                    if (gt.swz != plan.coltab_swz[p]) return fail(VQE_ERR_CUDA, "tile swizzle of pass %zu differs from its item table", p);
+                    const size_t smem_t = (8ull << ps.tp.tbits) + (size_t)n_cols * (sizeof(ColTabRun) + 8 + 4) + (size_t)n_ents * sizeof(double2);
+                    const int grid_t = tile_grid(c, g.n_tiles, smem_t <= 54 * 1024 ? 4 : (smem_t <= 74 * 1024 ? 3 : 2));
+                    cudaLaunchConfig_t cfg;
+                    memset(&cfg, 0, sizeof cfg);
+                    cfg.gridDim = dim3((unsigned)grid_t);
+                    cfg.blockDim = dim3(256);
+                    cfg.dynamicSmemBytes = smem_t;
+                    cfg.stream = c->stream;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = env_int("VQE_PDL", 1) != 0 ? 1 : 0;
+                    CK(cudaLaunchKernelEx(&cfg, k_col_tab, tmap, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
+                                          (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents,
+                                          (const uint32_t*)c->d_coltab + plan.coltab_off[p], env_int("VQE_DEBUG_SKELETON", 0), c->d_err));
+                    c->launches++;
+                    return VQE_OK;
+                }
                 k_tile_col<true, true><<<grid_r, thr, smem_r, c->stream>>>(tmap, sh, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                                                           (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, n_ents, c->d_err);
                 c->launches++;
@@ -4515,6 +5156,109 @@ extern "C" int vqe_apply_pauli_rotations_buf(vqe_ctx* c, int buf, int n_rot, con
 // a state of n_qubits with n_global rank bits.  Used by the CPU tests of the sharding logic and by bench.py to
 // report local / peer pass counts.  pass_kind: 0 = local pass, 1 = peer pass in exchange form, 2 = peer pass in
 // gather form (pattern in pass_pattern).
+// Host-only interpreter of the item-table rotation kernel (no CUDA call; CPU test support): plans the rotation program
+// for the real layout of an unsharded state exactly as vqe_apply_pauli_rotations does, builds the item table k_col_tab
+// reads (build_coltab) and walks it tile by tile on a HOST state of 2^n doubles, with the kernel's own per-item
+// arithmetic.  Returns VQE_ERR_INVALID when the program has no real-layout collapsed-run plan (then the GPU path does
+// not use the table either).
+extern "C" int vqe_debug_coltab_host(int n_qubits, int tile_bits, int low_bits, int form, int n_rot, const uint64_t* xmask,
+                                     const uint64_t* zmask, const int32_t* ny, const double* angle, double* psi_re,
+                                     int32_t* n_passes, int32_t* n_words) {
+    if (n_qubits < 1 || n_qubits > 30) return fail(VQE_ERR_INVALID, "bad qubit count");
+    if (tile_bits < 6 || tile_bits > 13) tile_bits = 13;
+    tile_bits = std::min(tile_bits, n_qubits);
+    if (low_bits < 0 || low_bits > tile_bits) low_bits = 4;
+    if (n_rot < 0 || !psi_re || (n_rot > 0 && (!xmask || !zmask || !ny || !angle))) return fail(VQE_ERR_INVALID, "null array");
+    std::vector<HostOp> ops;
+    for (int k = 0; k < n_rot; ++k) {
+        if (angle[k] == 0.0) continue;
+        HostOp h = HostOp();
+        h.kind = OP_ROT;
+        h.x = xmask[k];
+        h.z = zmask[k];
+        h.ny = ny[k];
+        h.c = cos(angle[k]);
+        h.s = sin(angle[k]);
+        h.ang = angle[k];
+        if (h.x == 0 || fabs(h.c) < 0.3) return fail(VQE_ERR_INVALID, "rotation %d takes the general path", k);
+        ops.push_back(h);
+    }
+    OpPlan plan;
+    int rc = plan_ops(n_qubits, n_qubits, tile_bits, low_bits, tile_bits > 12 ? 1024 : 512, ops, plan);
+    if (rc) return rc;
+    for (const OpPass& ps : plan.passes) {
+        const bool all_col = ps.fast && !ps.has_imag && ps.sub_end == ps.sub_begin && ps.col_end > ps.col_begin && ps.pass_scale == 1.0 &&
+                             (ps.sup_end - ps.sup_begin) == (ps.col_end - ps.col_begin);
+        if (!all_col || ps.tp.vbit) return fail(VQE_ERR_INVALID, "the program has a pass that is not a real collapsed-run pass");
+    }
+    rc = build_coltab(plan);
+    if (rc) return rc;
+    if (n_passes) *n_passes = (int32_t)plan.passes.size();
+    if (n_words) *n_words = (int32_t)plan.coltab.size();
+    for (size_t p = 0; p < plan.passes.size(); ++p) {
+        const OpPass& ps = plan.passes[p];
+        const uint32_t ts = 1u << ps.tp.tbits, swz = plan.coltab_swz[p];
+        const uint32_t lmask = (1u << ps.tp.lbits) - 1u;
+        const uint32_t* tab = plan.coltab.data() + plan.coltab_off[p];
+        std::vector<double> tile(ts);
+        std::vector<uint64_t> addr(ts);
+        for (uint64_t t = 0; t < ps.tp.n_tiles; ++t) {
+            uint64_t base = 0, v = t, m = ps.tp.comp_mask;
+            while (m) {  // pdep
+                const uint64_t low = m & (0 - m);
+                if (v & 1) base |= low;
+                v >>= 1;
+                m ^= low;
+            }
+            for (uint32_t k = 0; k < ts; ++k) {
+                addr[swz_idx8(k, swz)] = base | ps.tp.scat[k >> ps.tp.lbits] | (uint64_t)(k & lmask);
+                tile[swz_idx8(k, swz)] = psi_re[base | ps.tp.scat[k >> ps.tp.lbits] | (uint64_t)(k & lmask)];
+            }
+            // the 16-bit segment table k_col_stab reads: [first segment of every run][segments of 512 slots]
+            const uint16_t* t16 = plan.coltab16.data() + plan.coltab16_off[p];
+            const size_t n_cols = ps.col_end - ps.col_begin;
+            const uint16_t* seg0 = t16 + ((2 * n_cols + 7) & ~size_t(7));
+            for (size_t q = ps.col_begin; q < ps.col_end; ++q) {
+                const DevCol& co = plan.dcols[q];
+                const uint32_t lxb = swz_idx8(co.lx, swz) << 3, items = co.n_active << co.free_log;
+                const uint32_t cs = (uint32_t)__builtin_popcountll(base & co.zout) & 1u;
+                if (form == 0) {  // 32-bit words (k_col_tab)
+                    for (uint32_t it = 0; it < items; ++it) {
+                        const uint32_t w = tab[co.pad + it];
+                        const DevColEntry& en = plan.dents[ps.ent_begin + co.ent_begin + (co.n_active > 1u ? (w >> 17) : 0u)];
+                        const double sn = (((w >> 16) ^ cs) & 1u) ? -en.s : en.s;
+                        const uint32_t ia = (w & 0xffffu) >> 3, ib = ((w & 0xffffu) ^ lxb) >> 3;
+                        const double a = tile[ia], b = tile[ib];
+                        tile[ia] = fma(en.c, a, -sn * b);
+                        tile[ib] = fma(en.c, b, sn * a);
+                    }
+                    continue;
+                }
+                uint32_t sg = reinterpret_cast<const uint32_t*>(t16)[q - ps.col_begin];
+                const uint32_t per_pat = std::max<uint32_t>(1u, (1u << co.free_log) / COLSEG);
+                uint32_t seen = 0;
+                for (uint32_t pi = 0; pi < co.n_active; ++pi) {
+                    const DevColEntry& en = plan.dents[ps.ent_begin + co.ent_begin + pi];
+                    for (uint32_t k = 0; k < per_pat; ++k, ++sg)
+                        for (uint32_t sl = 0; sl < COLSEG; ++sl) {
+                            const uint32_t w = seg0[(size_t)sg * COLSEG + sl];
+                            if (w == 0xffffu) continue;
+                            ++seen;
+                            const double sn = ((w ^ cs) & 1u) ? -en.s : en.s;
+                            const uint32_t ia = (w & 0xfff8u) >> 3, ib = ((w & 0xfff8u) ^ lxb) >> 3;
+                            const double a = tile[ia], b = tile[ib];
+                            tile[ia] = fma(en.c, a, -sn * b);
+                            tile[ib] = fma(en.c, b, sn * a);
+                        }
+                }
+                if (seen != items) return fail(VQE_ERR_INVALID, "segment table of pass %zu holds %u items of run %zu, expected %u", p, seen, q - ps.col_begin, items);
+            }
+            for (uint32_t k = 0; k < ts; ++k) psi_re[addr[k]] = tile[k];
+        }
+    }
+    return VQE_OK;
+}
+
 extern "C" int vqe_plan_rotations(int n_qubits, int n_global, int tile_bits, int low_bits, int n_rot,
                                   const uint64_t* xmask, const uint64_t* zmask, const int32_t* ny, const double* angle,
                                   int cap, int32_t* n_passes, int32_t* pass_kind, uint64_t* pass_pattern,
@@ -5936,7 +6680,9 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             }
             const bool pipe = pp.lean && geoms[k][p].bulk && env_int("VQE_PIPE", 0) != 0 &&
                               3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double) <= 226 * 1024;
-            const int lean_ctas = (rl && pp.lean) ? std::max(1, std::min(6, env_int("VQE_EXP_RL_CTAS", 4))) : 3;  // 32 KiB tiles, 64 registers
+            // real layout: 32 KiB tiles; two slots per CTA and 3 CTAs per SM (k_expect_rl2), or one slot and 4 CTAs (64 registers)
+            const bool rl2 = env_int("VQE_EXP_RL2", 1) != 0 && 2 * (8ull << pp.tp.tbits) + pp.addpat.size() * 16 <= 74 * 1024;
+            const int lean_ctas = (rl && pp.lean) ? std::max(1, std::min(6, env_int("VQE_EXP_RL_CTAS", rl2 ? 3 : 4))) : 3;
             int gx = tile_grid(c, geoms[k][p].n_tiles, pipe ? 1 : (pp.lean ? lean_ctas : 0));
             int want = std::max(1, (c->sm_count * (pipe ? 1 : (pp.lean ? lean_ctas : c->ctas_per_sm))) / gx);
             int gy = std::max(1, std::min<int>(pp.lean ? (int)((pp.flats2.size() + 7) / 8) : (int)pp.groups.size(), want));
@@ -5982,6 +6728,35 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                 if (!geoms[k][p].tma) return fail(VQE_ERR_CUDA, "real-layout tensor map of an expectation pass could not be encoded");
                 const size_t smem_r = (8ull << pp.tp.tbits) + pp.addpat.size() * sizeof(double);
                 const int thr_l = env_int("VQE_EXP_LEAN_THREADS", 256);
+                const size_t smem_2 = 2 * (8ull << pp.tp.tbits) + 2 * pp.addpat.size() * sizeof(double);
+                if (env_int("VQE_EXP_RL2", 1) != 0 && smem_2 <= 74 * 1024 && (thr_l == 256 || thr_l == 384)) {
+                    cudaLaunchConfig_t cfg;
+                    memset(&cfg, 0, sizeof cfg);
+                    cfg.gridDim = grids[k][p];
+                    cfg.blockDim = dim3((unsigned)thr_l);
+                    cfg.dynamicSmemBytes = smem_2;
+                    cfg.stream = c->stream;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = env_int("VQE_PDL", 1) != 0 ? 1 : 0;
+                    if (thr_l == 384)
+                        CK(cudaLaunchKernelEx(&cfg, k_expect_rl2<384>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, (int)pp.flats2.size(),
+                                              (const uint64_t*)pp.d_fzout, (const double*)pp.d_addtab, (const DevAddPat*)pp.d_addpat,
+                                              (int)pp.addpat.size(), (const DevAddOut*)pp.d_addout, c->d_partial + off[k], c->d_err));
+                    else if (env_int("VQE_EXP_PAIR", 1) != 0)
+                        CK(cudaLaunchKernelEx(&cfg, k_expect_rlp<256>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, (int)pp.flats2.size(),
+                                              (const uint64_t*)pp.d_fzout, (const double*)pp.d_addtab, (const DevAddPat*)pp.d_addpat,
+                                              (int)pp.addpat.size(), (const DevAddOut*)pp.d_addout, c->d_partial + off[k], c->d_err));
+                    else
+                        CK(cudaLaunchKernelEx(&cfg, k_expect_rl2<256>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, (int)pp.flats2.size(),
+                                              (const uint64_t*)pp.d_fzout, (const double*)pp.d_addtab, (const DevAddPat*)pp.d_addpat,
+                                              (int)pp.addpat.size(), (const DevAddOut*)pp.d_addout, c->d_partial + off[k], c->d_err));
+                    c->launches++;
+                    off[k] += (size_t)grids[k][p].x * grids[k][p].y;
+                    continue;
+                }
 #define LAUNCH_EXPECT_RL(T)                                                                                                    \
     k_expect_lean<true, T, true><<<grids[k][p], T, smem_r, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2_rl,       \
                                                                        (int)pp.flats2.size(), pp.d_fzout, pp.d_addtab, pp.d_addpat, \
