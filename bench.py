@@ -640,12 +640,20 @@ def run_ours(args, rank, world, local_rank):
             ent["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, " + os.path.relpath(NCU_TRAFFIC, ROOT)
         return ent
 
-    prep = kernel_entry("k_tile_col", "rotation passes (every consecutive Pauli rotation whose X-mask fits the tile bits, collapsed runs)",
+    # kernel names of the default path: the real layout runs the item-table rotation kernel and the pair-mode expectation kernel
+    rot_kernel = "k_col_stab" if real_layout and os.environ.get("VQE_COL_TAB", "2") == "2" else "k_tile_col"
+    exp_kernel = "k_expect_rlp" if real_layout and os.environ.get("VQE_EXP_RL2", "1") != "0" else "k_expect_lean"
+    prep = kernel_entry(rot_kernel, "rotation passes (every consecutive Pauli rotation whose X-mask fits the tile bits, collapsed runs)",
                         prep_ms, prep_n, 2.0 * S_phys, n_rot * 2.0 * S * args.steps, "rotations_per_pass", n_rot * args.steps)
-    expk = kernel_entry("k_expect_lean", "expectation passes (every X-mask group whose X-mask fits the tile bits)",
+    expk = kernel_entry(exp_kernel, "expectation passes (every X-mask group whose X-mask fits the tile bits)",
                         exp_ms, exp_n, S_phys, n_groups * S * args.steps, "groups_per_pass", n_groups * args.steps)
     for ent in (prep, expk):
         ent["state_layout"] = "real (2^n doubles: the state of a UCC evaluation is purely real)" if real_layout else "interleaved complex128"
+    # what keeps the fraction below 1: a pass does r rotations / g groups of arithmetic on the tile while it sits in shared memory
+    prep["limited_by"] = ("HBM for passes with few runs (7-9 JW doubles: ~0.8 of the peak), shared-memory wavefronts for passes with 25-28 "
+                          "runs (2 loads + 2 stores of 8 bytes per rotated pair)")
+    expk["limited_by"] = ("shared-memory bandwidth and issue: 16 bytes of tile reads per visited pair, ~230 pair visits per amplitude and "
+                          "evaluation against 8 bytes of HBM traffic per amplitude and pass")
     dom, other = (prep, expk) if prep_ms >= exp_ms else (expk, prep)
     line = {"metric": "ucc_energy_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

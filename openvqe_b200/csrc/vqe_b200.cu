@@ -1407,7 +1407,10 @@ __global__ void __launch_bounds__(256, 4) k_col_tab(const __grid_constant__ CUte
 // ------------------------------------------------------------------------------------------
 // k_col_stab: k_col_tab with the pass's item table in SHARED memory, 16 bits per item: (element index in the swizzled tile)
 // << 3 | parity(l & lz), i.e. the byte offset with the sign in bit 0; 0xffff = no item.  Global-memory words cost an L2 round
-// trip per run while the L2 is saturated by the streaming tiles; a copy next to the tile costs one LDS.U16 per item.
+// trip per run while the L2 is saturated by the streaming tiles; a copy next to the tile costs two LDS.U16 per item.
+// FACTORED: the index deposit, the swizzle and the parity are all linear over XOR, so the word of slot s of a segment is
+// LANE[s & 31] ^ GROUP[s >> 5] (the pattern and the segment's own index bits folded into GROUP): 48 words = 96 bytes per
+// segment instead of 512 words, so every pass keeps three CTAs per SM.
 // The table is cut into SEGMENTS of 512 slots: every active pattern of a run is ceil(items / 512) segments (a JW double in
 // a 13-bit tile: exactly one, a JW single: four), each with its own 32-byte descriptor (cos, sin, X offset, flags); only the
 // last segment of a run ends with the CTA barrier -- the items of a run touch disjoint pairs.  A thread's slot of segment
@@ -1416,6 +1419,7 @@ __global__ void __launch_bounds__(256, 4) k_col_tab(const __grid_constant__ CUte
 // Passes whose table does not fit next to the tile keep k_tile_col.
 // ------------------------------------------------------------------------------------------
 #define COLSEG 512u
+#define COLFACT 48u      // 16-bit words of a segment's factored table: 32 lane parts + 16 group parts
 struct ColSub {            // 32 bytes, shared memory, one per segment
     double c, s;
     uint32_t lxb;          // X-mask as a BYTE offset in the tile's shared-memory layout
@@ -1435,6 +1439,11 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
+// slot word = lane part ^ group part (0xffff in either: the slot is empty)
+__device__ __forceinline__ uint32_t col_slot(uint32_t lane_addr, uint32_t grp_addr) {
+    const uint32_t wl = lds_u16(lane_addr), wg = lds_u16(grp_addr);
+    return (wl == 0xffffu || wg == 0xffffu) ? 0xffffu : (wl ^ wg);
+}
 // THREADS = 512: one slot per thread and segment; 256: two.
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_col_stab(const __grid_constant__ CUtensorMap tmap, TileGeom g, const DevCol* __restrict__ cols,
@@ -1448,7 +1457,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_col_stab(const __grid_constan
     ColSub* sub = reinterpret_cast<ColSub*>(tb + ((size_t)ts << 3));
     uint64_t* szout = reinterpret_cast<uint64_t*>(sub + n_seg);
     uint16_t* stab = reinterpret_cast<uint16_t*>(szout + n_seg);   // n_seg * 40 bytes after the tile: 8-byte aligned; the copy below needs 16
-    stab = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(stab) + 15u) & ~(uintptr_t)15u);
+    stab = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(stab) + 15u) & ~(uintptr_t)15u);   // [n_seg][COLFACT]
     __shared__ __align__(8) uint64_t s_mbar;
     uint32_t mphase = 0;
     const uint32_t tid = threadIdx.x;
@@ -1474,14 +1483,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_col_stab(const __grid_constan
             }
         }
     }
-    {   // the table: 16-byte copies (a segment is 1 KiB)
+    {   // the table: 16-byte copies (a segment is 96 bytes)
         const uint4* src = reinterpret_cast<const uint4*>(tab + ((2 * n_cols + 7) & ~7));
         uint4* dst = reinterpret_cast<uint4*>(stab);
-        const int n16 = n_seg * (int)(COLSEG / 8u);
+        const int n16 = n_seg * (int)(COLFACT / 8u);
         for (int k = tid; k < n16; k += THREADS) dst[k] = __ldg(src + k);
     }
     const BaseLane bl = base_lane_init(g);
-    const uint32_t tile32 = smem_u32(tile), sub32 = smem_u32(sub), stab32 = smem_u32(stab) + 2u * tid;
+    // a thread's slot k of a segment is  s = tid + THREADS * k:  lane part s & 31, group part s >> 5
+    const uint32_t tile32 = smem_u32(tile), sub32 = smem_u32(sub), lane32 = smem_u32(stab) + 2u * (tid & 31u),
+                   grp32 = smem_u32(stab) + 64u + 2u * (tid >> 5);
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous pass has written the whole state
     const int ns = skeleton ? 0 : n_seg;
@@ -1493,7 +1504,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_col_stab(const __grid_constan
         for (int r = tid; r < n_seg; r += THREADS) sub[r].meta = (sub[r].meta & ~1u) | ((uint32_t)__popcll(sbase & szout[r]) & 1u);
         uint32_t w[PF];
 #pragma unroll
-        for (int k = 0; k < PF; ++k) w[k] = ns > 0 ? lds_u16(stab32 + 2u * THREADS * k) : 0xffffu;
+        for (int k = 0; k < PF; ++k) w[k] = ns > 0 ? col_slot(lane32, grp32 + (THREADS / 16) * k) : 0xffffu;
         __syncthreads();  // signs visible
         if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
         mphase ^= 1u;
@@ -1513,7 +1524,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_col_stab(const __grid_constan
                 }
                 uint32_t nw[PF];
 #pragma unroll
-                for (int k = 0; k < PF; ++k) nw[k] = e + 1 < ns ? lds_u16(stab32 + 2u * (COLSEG * (uint32_t)(e + 1) + THREADS * k)) : 0xffffu;
+                for (int k = 0; k < PF; ++k)
+                    nw[k] = e + 1 < ns ? col_slot(lane32 + 2u * COLFACT * (uint32_t)(e + 1), grp32 + 2u * COLFACT * (uint32_t)(e + 1) + (THREADS / 16) * k) : 0xffffu;
 #pragma unroll
                 for (int k = 0; k < PF; ++k) {
                     const double sn = __hiloint2double((int)(d0.w ^ ((w[k] ^ meta) << 31)), (int)d0.z);
@@ -1534,7 +1546,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_col_stab(const __grid_constan
                 }
                 uint32_t nw[PF];
 #pragma unroll
-                for (int k = 0; k < PF; ++k) nw[k] = e + 1 < ns ? lds_u16(stab32 + 2u * (COLSEG * (uint32_t)(e + 1) + THREADS * k)) : 0xffffu;
+                for (int k = 0; k < PF; ++k)
+                    nw[k] = e + 1 < ns ? col_slot(lane32 + 2u * COLFACT * (uint32_t)(e + 1), grp32 + 2u * COLFACT * (uint32_t)(e + 1) + (THREADS / 16) * k) : 0xffffu;
 #pragma unroll
                 for (int k = 0; k < PF; ++k)
                     if (w[k] != 0xffffu) {
@@ -2398,6 +2411,73 @@ __global__ void __launch_bounds__(THREADS, RL ? 4 : 3) k_expect_lean(const __gri
     }
     double2 sres = block_sum2(er, 0.0, red);
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_expect_diag2_rl: <psi|D|psi> on the REAL LAYOUT for a diagonal operator that is at most quadratic in the Z letters,
+//   D(l) = c0 + sum_p a_p s_p + sum_{p<q} b_pq s_p s_q,   s_p = (-1)^(bit p of l)
+// -- the X-mask-0 group of a molecular Hamiltonian (number operators and Coulomb / exchange pairs: Z_p, Z_p Z_q).  The
+// general expectation kernel needs the interleaved complex form (one in-place expansion of the state per evaluation) and
+// a Walsh-Hadamard pass over hundreds of strings; here a chunk of 2^tb contiguous amplitudes (index bits t below tb, o above)
+// splits D into  K(o) + sum_{p<tb} s_p v_p(o) + T(t):  K and the tb coefficients v_p = a_p + sum_{q>=tb} b_pq s_q are
+// computed once per chunk, the linear part is tabulated as A[t & 31] + B[t >> 5], and T (2^tb doubles, the same for every
+// chunk) comes from the host.  Per amplitude: psi^2 times three table values; the state streams through once, coalesced.
+// Fixed grid, per-CTA partials, fixed-order block reduction: bit-reproducible like the other expectation kernels.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_expect_diag2_rl(const double* __restrict__ psi, uint64_t n_amp, int n, int tb, uint64_t sign_base,
+                                                         double c0, const double* __restrict__ a, const double* __restrict__ b,
+                                                         const double* __restrict__ t_tab, double2* __restrict__ partial) {
+    __shared__ double sv[16], sA[32], sB[256], sK, red[64];
+    const uint32_t tid = threadIdx.x, chunk = 1u << tb;
+    const uint64_t n_chunks = n_amp >> tb;
+    const int lb = tb < 5 ? tb : 5;
+    double acc = 0.0;
+    for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const uint64_t o = (ch << tb) | sign_base;   // the chunk's amplitudes are o | t, t < 2^tb
+        __syncthreads();                             // the tables of the previous chunk are consumed
+        if ((int)tid < tb) {
+            double v = a[tid];
+            for (int q = tb; q < n; ++q) {
+                const double bq = b[(size_t)tid * n + q];
+                v += ((o >> q) & 1ull) ? -bq : bq;
+            }
+            sv[tid] = v;
+        }
+        if (tid >= 32u && tid < 64u) {   // K(o): lane L sums the rows p = tb + L, tb + L + 32, ...; fixed-shape warp reduction
+            double k = 0.0;
+            for (int pp = tb + (int)(tid - 32u); pp < n; pp += 32) {
+                double inner = a[pp];
+                for (int q = pp + 1; q < n; ++q) {
+                    const double bq = b[(size_t)pp * n + q];
+                    inner += ((o >> q) & 1ull) ? -bq : bq;
+                }
+                k += ((o >> pp) & 1ull) ? -inner : inner;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) k += __shfl_xor_sync(0xffffffffu, k, d);
+            if (tid == 32u) sK = k + c0;
+        }
+        __syncthreads();
+        if (tid < 32u) {
+            double sgm = 0.0;
+            for (int pp = 0; pp < lb; ++pp) sgm += ((tid >> pp) & 1u) ? -sv[pp] : sv[pp];
+            sA[tid] = sgm;
+        }
+        for (uint32_t j = tid; j < (chunk >> lb) && j < 256u; j += 256u) {
+            double sgm = 0.0;
+            for (int pp = lb; pp < tb; ++pp) sgm += ((j >> (pp - lb)) & 1u) ? -sv[pp] : sv[pp];
+            sB[j] = sgm;
+        }
+        __syncthreads();
+        const double ka = sK + sA[tid & 31u];   // t & 31 == tid & 31 for every t this thread visits (stride 256)
+        const double* __restrict__ src = psi + (ch << tb);
+        for (uint32_t t = tid; t < chunk; t += 256u) {
+            const double x = src[t];
+            acc = fma(x * x, ka + sB[t >> lb] + __ldg(t_tab + t), acc);
+        }
+    }
+    const double2 sres = block_sum2(acc, 0.0, red);
+    if (tid == 0) partial[blockIdx.x] = sres;
 }
 
 // One entry's pair sum on one real-layout tile (see lean_entries): eight pairs per lane, signs by the three-level butterfly.
@@ -4487,8 +4567,9 @@ static int build_coltab(const OpPlan& plan) {
             }
         }
     }
-    // 16-bit form (k_col_stab): per pass [first segment of every run: n_cols x uint32, padded to 16 bytes][segments of 512 slots]:
-    // slot = (element index << 3) | parity, 0xffff = empty; a pattern of a run is ceil(2^free_log / 512) segments
+    // 16-bit form (k_col_stab): per pass [first segment of every run: n_cols x uint32, padded to 16 bytes][segments]: a segment
+    // is 512 slots, slot = (element index << 3) | parity or 0xffff = empty, stored FACTORED as 32 lane parts + 16 group parts
+    // (slot s = LANE[s & 31] ^ GROUP[s >> 5]); a pattern of a run is ceil(2^free_log / 512) segments
     plan.coltab16.clear();
     plan.coltab16_off.assign(passes.size(), 0);
     plan.coltab16_seg.assign(passes.size(), 0);
@@ -4506,16 +4587,25 @@ static int build_coltab(const OpPlan& plan) {
             const uint32_t per_pat_items = 1u << co.free_log;
             const uint32_t per_pat_seg = std::max<uint32_t>(1u, per_pat_items / COLSEG);
             for (uint32_t pi = 0; pi < co.n_active; ++pi)
-                for (uint32_t k = 0; k < per_pat_seg; ++k, ++n_seg)
-                    for (uint32_t sl = 0; sl < COLSEG; ++sl) {
+                for (uint32_t k = 0; k < per_pat_seg; ++k, ++n_seg) {
+                    // factored form of the segment's 512 slots: word(s) = LANE[s & 31] ^ GROUP[s >> 5]
+                    auto w16 = [&](uint32_t sl) -> uint32_t {   // the slot's word from the 32-bit table, 0xffff when empty
                         const uint32_t it_in_pat = k * COLSEG + sl;
-                        if (it_in_pat >= per_pat_items) {
-                            plan.coltab16.push_back(0xffffu);
-                            continue;
-                        }
+                        if (it_in_pat >= per_pat_items) return 0xffffu;
                         const uint32_t w = plan.coltab[plan.coltab_off[p] + co.pad + (pi << co.free_log) + it_in_pat];
-                        plan.coltab16.push_back((uint16_t)((w & 0xfff8u) | ((w >> 16) & 1u)));
+                        return (w & 0xfff8u) | ((w >> 16) & 1u);
+                    };
+                    uint16_t fact[COLFACT];
+                    const uint32_t w00 = w16(0);
+                    for (uint32_t ln = 0; ln < 32; ++ln) fact[ln] = w16(ln) == 0xffffu ? 0xffffu : (uint16_t)(w16(ln) ^ w00);
+                    for (uint32_t gj = 0; gj < 16; ++gj) fact[32 + gj] = (uint16_t)w16(32 * gj);
+                    for (uint32_t sl = 0; sl < COLSEG; ++sl) {   // the factorisation must reproduce every slot
+                        const uint32_t wl = fact[sl & 31u], wg = fact[32 + (sl >> 5)];
+                        const uint32_t got = (wl == 0xffffu || wg == 0xffffu) ? 0xffffu : (wl ^ wg);
+                        if (got != w16(sl)) return fail(VQE_ERR_INVALID, "item table of pass %zu does not factor (run %zu, slot %u)", p, q - ps.col_begin, sl);
                     }
+                    plan.coltab16.insert(plan.coltab16.end(), fact, fact + COLFACT);
+                }
         }
         plan.coltab16_seg[p] = n_seg;
     }
@@ -4670,7 +4760,7 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                 const size_t smem_r = (8ull << ps.tp.tbits) + (size_t)n_cols * (sizeof(ColLite) + 8 + 4) + (size_t)n_ents * sizeof(DevColEntry);
                 const int grid_r = tile_grid(c, g.n_tiles, smem_r <= 54 * 1024 ? 4 : (smem_r <= 74 * 1024 ? 3 : 2));
                 const size_t n_seg = tab_mode == 2 ? plan.coltab16_seg[p] : 0;
-                const size_t smem_s = (8ull << ps.tp.tbits) + n_seg * (sizeof(ColSub) + 8) + 16 + n_seg * COLSEG * sizeof(uint16_t);
+                const size_t smem_s = (8ull << ps.tp.tbits) + n_seg * (sizeof(ColSub) + 8) + 16 + n_seg * COLFACT * sizeof(uint16_t);
                 if (tab_mode == 2 && smem_s <= 110 * 1024) {
                     if (gt.swz != plan.coltab_swz[p]) return fail(VQE_ERR_CUDA, "tile swizzle of pass %zu differs from its item table", p);
                     const int ctas_s = smem_s <= 74 * 1024 ? 3 : 2;
@@ -5241,8 +5331,9 @@ extern "C" int vqe_debug_coltab_host(int n_qubits, int tile_bits, int low_bits, 
                     const DevColEntry& en = plan.dents[ps.ent_begin + co.ent_begin + pi];
                     for (uint32_t k = 0; k < per_pat; ++k, ++sg)
                         for (uint32_t sl = 0; sl < COLSEG; ++sl) {
-                            const uint32_t w = seg0[(size_t)sg * COLSEG + sl];
-                            if (w == 0xffffu) continue;
+                            const uint32_t wl = seg0[(size_t)sg * COLFACT + (sl & 31u)], wg = seg0[(size_t)sg * COLFACT + 32u + (sl >> 5)];
+                            if (wl == 0xffffu || wg == 0xffffu) continue;
+                            const uint32_t w = wl ^ wg;
                             ++seen;
                             const double sn = ((w ^ cs) & 1u) ? -en.s : en.s;
                             const uint32_t ia = (w & 0xfff8u) >> 3, ib = ((w & 0xfff8u) ^ lxb) >> 3;
@@ -5504,6 +5595,7 @@ struct PSPass {
     DevFlat2* d_flats2 = nullptr;
     DevFlat2* d_flats2_rl = nullptr;    // the entries in real-layout form (expectation on a state kept as n_amp doubles)
     bool rl_ok = false, rl_swz = false; // the pass has a real-layout tensor-map form | whose tile is swizzled
+    bool diag_only = false;             // general pass that holds nothing but X-mask-0 groups (see vqe_paulisum::diag2)
     uint32_t* d_goff = nullptr;
     double* d_addtab = nullptr;
     DevAddPat* d_addpat = nullptr;
@@ -5522,6 +5614,15 @@ struct vqe_paulisum {
     std::vector<HTerm> terms;
     int tile_bits = 12, low_bits = 5, threads = 512;
     std::map<std::string, vqe_paulisum*> variants;
+    // The diagonal part (X-mask 0) as a quadratic form in the Z letters, when it is one (real weights, strings of at most
+    // two Z letters) and sits alone in its general passes: evaluated on the real layout by k_expect_diag2_rl.
+    struct Diag2 {
+        bool on = false;
+        int tb = 0;                     // chunk bits: min(13, nl)
+        double c0 = 0.0;
+        std::vector<double> a, b, t;    // a[n], b[n * n] (p < q), t[2^tb]
+        double *d_a = nullptr, *d_b = nullptr, *d_t = nullptr;
+    } diag2;
 };
 
 static void mul_i_pow(double& r, double& i, int k) {
@@ -5778,6 +5879,39 @@ static uint64_t cover_greedy(const std::vector<uint64_t>& xs, const std::vector<
 
 static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int low_bits, int threads_cfg,
                           std::vector<HTerm> terms, bool host_only = false) {
+    {   // the diagonal part as a quadratic form (see vqe_paulisum::Diag2); the passes that hold it are marked at the end
+        vqe_paulisum::Diag2& d = ps->diag2;
+        d = vqe_paulisum::Diag2();
+        bool ok = env_int("VQE_DIAG2", 1) != 0 && n <= 62, any = false;
+        d.a.assign(n, 0.0);
+        d.b.assign((size_t)n * n, 0.0);
+        for (const HTerm& t : terms) {
+            if (t.x != 0 || !ok) continue;
+            any = true;
+            const int wz = popc64(t.z);
+            if (t.ci != 0.0 || wz > 2) { ok = false; break; }
+            if (wz == 0) d.c0 += t.cr;
+            else if (wz == 1) d.a[__builtin_ctzll(t.z)] += t.cr;
+            else {
+                const int p0 = __builtin_ctzll(t.z), q0 = 63 - __builtin_clzll(t.z);
+                d.b[(size_t)p0 * n + q0] += t.cr;
+            }
+        }
+        d.on = ok && any;
+        if (d.on) {
+            d.tb = std::min(13, nl);
+            d.t.assign((size_t)1 << d.tb, 0.0);
+            for (uint32_t tt = 0; tt < (1u << d.tb); ++tt) {
+                double acc = 0.0;
+                for (int p0 = 0; p0 < d.tb; ++p0)
+                    for (int q0 = p0 + 1; q0 < d.tb; ++q0) {
+                        const double bq = d.b[(size_t)p0 * n + q0];
+                        if (bq != 0.0) acc += (((tt >> p0) ^ (tt >> q0)) & 1u) ? -bq : bq;
+                    }
+                d.t[tt] = acc;
+            }
+        }
+    }
     // group by x (stable: keep first-appearance order of groups, term order inside)
     std::vector<uint64_t> xs;
     std::vector<std::vector<HTerm>> grp;
@@ -6228,6 +6362,17 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
         }
         ps->passes.push_back(std::move(p));
     }
+    if (ps->diag2.on) {   // the quadratic form replaces the X-mask-0 groups only if they sit alone in their passes
+        for (PSPass& p : ps->passes) {
+            if (p.lean) continue;
+            size_t n0 = 0;
+            for (const DevGroup& gr : p.groups) n0 += (gr.lx == 0 && !p.tp.vbit) ? 1 : 0;
+            p.diag_only = n0 == p.groups.size() && n0 > 0;
+            if (n0 != 0 && !p.diag_only) ps->diag2.on = false;
+        }
+        if (!ps->diag2.on)
+            for (PSPass& p : ps->passes) p.diag_only = false;
+    }
     if (getenv("VQE_DEBUG_PLAN")) {
         size_t ng = 0, nc = 0, ne = 0, nt = 0, nfl = 0;
         for (const PSPass& p : ps->passes) {
@@ -6244,6 +6389,10 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
 }
 
 static void free_paulisum_device(vqe_paulisum* ps) {
+    if (ps->diag2.d_a) cudaFree(ps->diag2.d_a);
+    if (ps->diag2.d_b) cudaFree(ps->diag2.d_b);
+    if (ps->diag2.d_t) cudaFree(ps->diag2.d_t);
+    ps->diag2.d_a = ps->diag2.d_b = ps->diag2.d_t = nullptr;
     for (PSPass& p : ps->passes) {
         if (p.d_groups) cudaFree(p.d_groups);
         if (p.d_terms_expect) cudaFree(p.d_terms_expect);
@@ -6288,6 +6437,12 @@ static int upload_vec(T** dptr, const std::vector<T>& v) {
     return VQE_OK;
 }
 static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
+    if (ps->diag2.on) {
+        int rc = upload_vec(&ps->diag2.d_a, ps->diag2.a);
+        if (rc == VQE_OK) rc = upload_vec(&ps->diag2.d_b, ps->diag2.b);
+        if (rc == VQE_OK) rc = upload_vec(&ps->diag2.d_t, ps->diag2.t);
+        if (rc) return rc;
+    }
     for (PSPass& p : ps->passes) {
         if (p.lean) {
             int rc = upload_vec(&p.d_flats2, p.flats2);
@@ -6678,6 +6833,15 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                 grids[k][p] = dim3(0, 0, 1);
                 continue;
             }
+            if (rl && pp.diag_only && pss[k]->diag2.on) {
+                // the diagonal part on the real layout (k_expect_diag2_rl): one launch for all X-mask-0 passes, no expansion
+                bool first = true;
+                for (size_t p2 = 0; p2 < p; ++p2) first = first && !pss[k]->passes[p2].diag_only;
+                const uint64_t n_chunks = c->n_amp >> pss[k]->diag2.tb;
+                grids[k][p] = first ? dim3((unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_chunks, (uint64_t)c->sm_count * 8)), 1, 1) : dim3(0, 0, 1);
+                total_blocks[k] += first ? grids[k][p].x : 0;
+                continue;
+            }
             const bool pipe = pp.lean && geoms[k][p].bulk && env_int("VQE_PIPE", 0) != 0 &&
                               3 * tile_smem(pp.tp.tbits, 1, false) + 2 * pp.addpat.size() * sizeof(double) <= 226 * 1024;
             // real layout: 32 KiB tiles; two slots per CTA and 3 CTAs per SM (k_expect_rl2), or one slot and 4 CTAs (64 registers)
@@ -6697,7 +6861,8 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
     bool fenced = false;
     for (size_t p = 0; p < n_pass; ++p) {
         const bool vbit = pss[0]->passes[p].tp.vbit;
-        if (rl && !pss[0]->passes[p].lean)  // first general pass: every rank expands its shard BEFORE any partner reads it
+        const bool diag_rl = rl && pss[0]->passes[p].diag_only && pss[0]->diag2.on;   // evaluated on the real layout
+        if (rl && !pss[0]->passes[p].lean && !diag_rl)  // first general pass: every rank expands its shard BEFORE any partner reads it
             for (vqe_ctx* c : rs.r)
                 if (c->real_layout) {
                     CK(cudaSetDevice(c->device));
@@ -6718,6 +6883,15 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             ProfScope prof(c, vbit ? 5 : 1);
             CUtensorMap tmap;
             memset(&tmap, 0, sizeof tmap);
+            if (diag_rl && pss[k]->diag2.on && c->real_layout) {
+                const vqe_paulisum::Diag2& dg = pss[k]->diag2;
+                k_expect_diag2_rl<<<grids[k][p].x, 256, 0, c->stream>>>(reinterpret_cast<const double*>(shards[k][p].p0), c->n_amp, c->n, dg.tb,
+                                                                       geoms[k][p].sign_base, dg.c0, dg.d_a, dg.d_b, dg.d_t, c->d_partial + off[k]);
+                c->launches++;
+                CK(cudaGetLastError());
+                off[k] += (size_t)grids[k][p].x;
+                continue;
+            }
             if (rl && !pp.lean && c->real_layout) {  // first general pass: it reads the interleaved form
                 rc = ensure_complex(c, b);
                 if (rc) return rc;

@@ -197,6 +197,50 @@ def test_expectation_matches_oracle(engines, n, nterms):
     assert abs(got.imag) < 1e-11
 
 
+@pytest.mark.parametrize("n", [5, 12, 14, 17])
+def test_diagonal_quadratic_form_on_the_real_layout(engines, n):
+    """The X-mask-0 part of a molecular Hamiltonian (Z_p, Z_p Z_q) is evaluated as a quadratic form directly on the real
+    layout of a UCC state (k_expect_diag2_rl): no expansion to interleaved complex, the state stays in the real layout.
+    A diagonal part with a three-Z string is not a quadratic form and takes the general pass (expansion)."""
+    from openvqe_b200.lowering import pack_operator
+    from tests.helpers import jw_excitation
+    rng = np.random.default_rng(5100 + n)
+    eng = engines(n)
+    # a purely real state: |HF> followed by JW excitations (odd-ny rotations)
+    xs, zs, nys, angs = [], [], [], []
+    for g in range(6):
+        if n >= 4 and g % 3:
+            p, q, r, s = sorted(rng.choice(n, size=4, replace=False).tolist())
+            pk = pack_operator(jw_excitation(n, [r, s], [p, q]))
+        else:
+            p, q = sorted(rng.choice(n, size=2, replace=False).tolist())
+            pk = pack_operator(jw_excitation(n, [q], [p]))
+        th = float(rng.uniform(-0.7, 0.7))
+        for k in range(len(pk)):
+            xs.append(int(pk.x[k])); zs.append(int(pk.z[k])); nys.append(int(pk.ny[k])); angs.append(th * float(pk.cre[k]))
+    hf = ((1 << (n // 2)) - 1) << (n - n // 2)
+    ref = orc.basis_state(n, hf)
+    for x, z, ny, a in zip(xs, zs, nys, angs):
+        ref = orc.pauli_rotation(ref, x, z, ny, a)
+    terms = [T(float(rng.normal()), "Z", [q]) for q in range(n)]
+    terms += [T(float(rng.normal()), "ZZ", [p, q]) for p in range(n) for q in range(p + 1, n) if rng.random() < 0.7]
+    terms += [T(float(rng.normal()), "XX", sorted(rng.choice(n, size=2, replace=False).tolist())) for _ in range(3)]
+    ham = Ham(n, terms, 0.41)
+    for extra, stays_real in (([], True), ([T(0.3, "ZZZ", [0, 1, 2])], False)):
+        if extra and n < 3:
+            continue
+        h2 = Ham(n, terms + extra, 0.41)
+        ps = eng.paulisum(h2)
+        eng.set_basis_state(hf)
+        eng.apply_rotations(xs, zs, nys, angs)
+        was_real = eng.real_layout
+        got = eng.expectation(ps)
+        assert abs(got.real - orc.expectation(ref, h2)) < 1e-11 and abs(got.imag) < 1e-11
+        if was_real and n >= 13:
+            assert eng.real_layout == stays_real
+        assert np.max(np.abs(eng.get_state() - ref)) < TOL
+
+
 def test_expectation_complex_coefficients(engines):
     n = 7
     rng = np.random.default_rng(5)
