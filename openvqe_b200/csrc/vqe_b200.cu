@@ -2540,10 +2540,43 @@ __device__ __forceinline__ double lean_entries_pair(const char* tb0, const char*
     }
     return er;
 }
+// lean_entries_pair with TWO entries in flight per warp: the decode chain of one entry overlaps the pair loads of the other
+// (the kernel is latency-bound at 24 warps per SM).  Needs ~128 registers: 2 CTAs per SM.
+__device__ __forceinline__ double lean_entries_pair2(const char* tb0, const char* tb1, const DevFlat2* __restrict__ flats, int e0, int e1,
+                                                     int stride, uint32_t lane, uint64_t sbase0, uint64_t sbase1,
+                                                     const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
+                                                     const double* s_beta0, const double* s_beta1, uint32_t swz) {
+    double er = 0.0;
+    for (int e = e0; e < e1; e += 2 * stride) {
+        const bool two = e + stride < e1;
+        const uint4* pa = reinterpret_cast<const uint4*>(flats + e);
+        const uint4* pb = reinterpret_cast<const uint4*>(flats + (two ? e + stride : e));
+        const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+        const uint4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+        const uint64_t zoa = __ldg(fzout + (a0.w >> 16)), zob = __ldg(fzout + (b0.w >> 16));
+        LeanUnit ua, ub;
+        lean_decode(a0, a1, a2, lane, ua, 3u);
+        lean_decode(b0, b1, b2, lane, ub, 3u);
+        const uint32_t vsa = swz_off(ua.v, swz), vsb = swz_off(ub.v, swz);
+        double pa0 = lean_part_rl(tb0, ua, vsa, lane, addtab, s_beta0);
+        double pb0 = lean_part_rl(tb0, ub, vsb, lane, addtab, s_beta0);
+        pa0 = flipsign(pa0, ua.s0 + (uint32_t)__popcll(sbase0 & zoa));
+        pb0 = flipsign(pb0, ub.s0 + (uint32_t)__popcll(sbase0 & zob));
+        if (tb1) {
+            const double pa1 = lean_part_rl(tb1, ua, vsa, lane, addtab, s_beta1);
+            const double pb1 = lean_part_rl(tb1, ub, vsb, lane, addtab, s_beta1);
+            pa0 += flipsign(pa1, ua.s0 + (uint32_t)__popcll(sbase1 & zoa));
+            pb0 += flipsign(pb1, ub.s0 + (uint32_t)__popcll(sbase1 & zob));
+        }
+        er = fma(ua.fr, pa0, er);
+        if (two) er = fma(ub.fr, pb0, er);
+    }
+    return er;
+}
 // Real-layout expectation pass, pair mode: both tile slots of the CTA are loaded and every entry is evaluated on both
 // (lean_entries_pair); other CTAs of the SM cover the load.  Same launch geometry and shared-memory layout as k_expect_rl2.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 3) k_expect_rlp(const __grid_constant__ CUtensorMap tmap, TileGeom g,
+template <int THREADS, bool DUAL = false>
+__global__ void __launch_bounds__(THREADS, DUAL ? 2 : 3) k_expect_rlp(const __grid_constant__ CUtensorMap tmap, TileGeom g,
                                                         const DevFlat2* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
                                                         const DevAddPat* __restrict__ addpat, int n_addpat,
@@ -2581,8 +2614,12 @@ __global__ void __launch_bounds__(THREADS, 3) k_expect_rlp(const __grid_constant
         if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
         mphase ^= 1u;
         __syncthreads();
-        er += lean_entries_pair(tb, two ? tb + slot_bytes : nullptr, flats, f0 + (int)warp, f1, (int)nw, lane, base0 | g.sign_base,
-                                base1 | g.sign_base, fzout, addtab, s_beta, s_beta + n_addpat, g.swz);
+        if (DUAL)
+            er += lean_entries_pair2(tb, two ? tb + slot_bytes : nullptr, flats, f0 + (int)warp, f1, (int)nw, lane, base0 | g.sign_base,
+                                     base1 | g.sign_base, fzout, addtab, s_beta, s_beta + n_addpat, g.swz);
+        else
+            er += lean_entries_pair(tb, two ? tb + slot_bytes : nullptr, flats, f0 + (int)warp, f1, (int)nw, lane, base0 | g.sign_base,
+                                    base1 | g.sign_base, fzout, addtab, s_beta, s_beta + n_addpat, g.swz);
     }
     double2 sres = block_sum2(er, 0.0, red);
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
@@ -2914,6 +2951,7 @@ struct vqe_ctx {
     std::vector<std::pair<int, int>> swap_history;  // (global slot, local slot) of every swap since the last reset
     uint64_t n_swaps = 0, swap_bytes = 0;   // statistics: swaps executed, bytes this rank read from its partners in swaps
     PlanCache* plan_cache = nullptr;        // see rotations_impl
+    size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside and largest access-policy window (0: not used)
     char* d_coltab = nullptr;               // item table of the plan whose identity is coltab_gen (k_col_stab: 16-bit items; k_col_tab: 32-bit)
     size_t coltab_cap = 0;                  // in bytes
     uint64_t coltab_gen = 0;
@@ -3086,6 +3124,7 @@ static int set_kernel_attrs(int device) {
     SET_SMEM((k_col_stab<512, 3>));
     SET_SMEM(k_expect_rl2<256>);
     SET_SMEM(k_expect_rlp<256>);
+    SET_SMEM((k_expect_rlp<256, true>));
     SET_SMEM(k_expect_rl2<384>);
     SET_SMEM(k_col_pipe<false>);
     SET_SMEM(k_col_pipe<true>);
@@ -3135,6 +3174,20 @@ static int create_ctx(vqe_ctx** out, int n_qubits, int n_global, int rank, int d
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    // L2 residency of a state that is not much larger than the L2 (24 qubits in the real layout: 134 MB against 126 MB): the
+    // pass kernels are launched with an access-policy window over the state that marks a fraction of its lines PERSISTING,
+    // sized to the persisting set-aside, and the rest streaming -- consecutive passes then find that fraction in L2 (reads
+    // and write-backs) instead of every pass streaming the whole state through HBM.  MEASURED SLOWER on B200 (rotation passes
+    // 67 -> 114 us whatever the hit ratio: the set-aside shrinks the L2 left to the streaming tiles): off, VQE_L2_PERSIST=1 enables it.
+    if (env_int("VQE_L2_PERSIST", 0) != 0 && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        const size_t want = (size_t)((double)prop.persistingL2CacheMaxSize * env_int("VQE_L2_PERSIST_PCT", 100) / 100.0);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            c->l2_persist_bytes = want;
+            c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        } else {
+            cudaGetLastError();
+        }
+    }
     for (int b = 0; b < 64; ++b) c->perm[b] = (uint8_t)b;
     c->tile_bits = env_int("VQE_TILE_BITS", 12);
     // low-bit floor of the tiles: tensor-map (TMA) tile loads make short contiguous runs cheap, so an unsharded context only
@@ -3205,6 +3258,7 @@ static void free_ctx(vqe_ctx* c) {
     if (c->d_peer_flags) cudaFree(c->d_peer_flags);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->plan_cache) free_plan_cache(c->plan_cache);
+    if (c->l2_persist_bytes) cudaCtxResetPersistingL2Cache();   // the persisting lines of this state go back to normal
     if (c->d_coltab) cudaFree(c->d_coltab);
     for (int sb = 0; sb < 2; ++sb)
         if (c->gstage[sb]) cudaFree(c->gstage[sb]);
@@ -3967,8 +4021,16 @@ struct HostOp {
     std::vector<double> pcos, psin;
 };
 
+// Persistent grid of a pass kernel.  The CTAs stride over the tiles, so with `cap` resident CTAs a pass takes
+// ceil(n_tiles / cap) rounds; the grid is then shrunk to ceil(n_tiles / rounds) so that every CTA works in every round
+// (2048 tiles on 444 slots: 410 CTAs x 5 tiles instead of a last round with 39 % of the slots idle) with VQE_GRID_BALANCE=1.
+// Measured: no gain for the HBM-bound rotation passes, 4 % slower expectation passes (they want every slot): off by default.
 static int tile_grid(const vqe_ctx* c, uint64_t n_tiles, int ctas_per_sm = 0) {
     uint64_t cap = (uint64_t)c->sm_count * (ctas_per_sm ? ctas_per_sm : c->ctas_per_sm);
+    if (n_tiles > cap && env_int("VQE_GRID_BALANCE", 0) != 0) {
+        const uint64_t rounds = (n_tiles + cap - 1) / cap;
+        cap = (n_tiles + rounds - 1) / rounds;
+    }
     return (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, cap));
 }
 
@@ -4538,6 +4600,21 @@ static bool plan_runs_in_real_layout(const OpPlan& plan) {
     }
     return true;
 }
+// Launch attribute: access-policy window over `bytes` of the state at `base` (see vqe_create).  Returns 1 when the attribute
+// was filled.  Only for states up to a few times the set-aside: beyond that the resident fraction is not worth the
+// L2 capacity taken from everything else.
+static int l2_window_attr(const vqe_ctx* c, cudaLaunchAttribute* at, const void* base, size_t bytes) {
+    if (!c->l2_persist_bytes || !base || bytes == 0 || bytes > 4 * c->l2_persist_bytes) return 0;
+    const size_t win = std::min(bytes, c->l2_window_max);
+    memset(at, 0, sizeof *at);
+    at->id = cudaLaunchAttributeAccessPolicyWindow;
+    at->val.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    at->val.accessPolicyWindow.num_bytes = win;
+    at->val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_bytes * env_int("VQE_L2_HIT_PCT", 100) / 100.0 / (double)win);
+    at->val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at->val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    return 1;
+}
 // Item table of k_col_tab for every pass of a real-layout collapsed-run plan (pure host code).  One word per item of a run:
 // bits 0-15 byte offset of the a-side element in the pass's (swizzled) shared-memory tile, bit 16 parity(l & lz),
 // bits 17- pattern number within the run.  The index arithmetic is the one k_tile_col does per thread and run (col_prep).
@@ -4773,11 +4850,16 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                     cfg.blockDim = dim3((unsigned)thr_s);
                     cfg.dynamicSmemBytes = smem_s;
                     cfg.stream = c->stream;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                    at[0].val.programmaticStreamSerializationAllowed = 1;
+                    cudaLaunchAttribute at[2];
+                    unsigned n_at = 0;
+                    if (env_int("VQE_PDL", 1) != 0) {
+                        at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                        at[n_at].val.programmaticStreamSerializationAllowed = 1;
+                        ++n_at;
+                    }
+                    n_at += (unsigned)l2_window_attr(c, &at[n_at], sh.p0, (size_t)c->n_amp * sizeof(double));
                     cfg.attrs = at;
-                    cfg.numAttrs = env_int("VQE_PDL", 1) != 0 ? 1 : 0;
+                    cfg.numAttrs = n_at;
                     auto kern = thr_s == 512 ? (ctas_s == 3 ? k_col_stab<512, 3> : k_col_stab<512, 2>) : k_col_stab<256, 3>;
                     CK(cudaLaunchKernelEx(&cfg, kern, tmap, gt, (const DevCol*)(c->d_stage + off_cols) + ps.col_begin, n_cols,
                                           (const DevColEntry*)(c->d_stage + off_ents) + ps.ent_begin, (int)n_seg,
@@ -6910,13 +6992,22 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                     cfg.blockDim = dim3((unsigned)thr_l);
                     cfg.dynamicSmemBytes = smem_2;
                     cfg.stream = c->stream;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                    at[0].val.programmaticStreamSerializationAllowed = 1;
+                    cudaLaunchAttribute at[2];
+                    unsigned n_at = 0;
+                    if (env_int("VQE_PDL", 1) != 0) {
+                        at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                        at[n_at].val.programmaticStreamSerializationAllowed = 1;
+                        ++n_at;
+                    }
+                    n_at += (unsigned)l2_window_attr(c, &at[n_at], shards[k][p].p0, (size_t)c->n_amp * sizeof(double));
                     cfg.attrs = at;
-                    cfg.numAttrs = env_int("VQE_PDL", 1) != 0 ? 1 : 0;
+                    cfg.numAttrs = n_at;
                     if (thr_l == 384)
                         CK(cudaLaunchKernelEx(&cfg, k_expect_rl2<384>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, (int)pp.flats2.size(),
+                                              (const uint64_t*)pp.d_fzout, (const double*)pp.d_addtab, (const DevAddPat*)pp.d_addpat,
+                                              (int)pp.addpat.size(), (const DevAddOut*)pp.d_addout, c->d_partial + off[k], c->d_err));
+                    else if (env_int("VQE_EXP_PAIR", 1) == 2)   // two entries in flight per warp, 2 CTAs per SM (A/B)
+                        CK(cudaLaunchKernelEx(&cfg, k_expect_rlp<256, true>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, (int)pp.flats2.size(),
                                               (const uint64_t*)pp.d_fzout, (const double*)pp.d_addtab, (const DevAddPat*)pp.d_addpat,
                                               (int)pp.addpat.size(), (const DevAddOut*)pp.d_addout, c->d_partial + off[k], c->d_err));
                     else if (env_int("VQE_EXP_PAIR", 1) != 0)
