@@ -122,6 +122,8 @@ struct TileGeom {
                            // beyond the 16-byte stride itself).  0: natural layout.
     uint32_t rl;           // 1: REAL LAYOUT -- the buffer holds the n_amp real parts as contiguous doubles (see vqe_ctx::real_layout);
                            // tile elements are 8 bytes, the tensor map counts one double per amplitude
+    uint32_t rev;          // 1: the tiles are walked downwards (tile_first - k * tile_stride): consecutive passes over a state
+                           // of about the size of the L2 alternate, so a pass starts with what the previous one touched last
     TmaGeom tg;
 };
 // byte offset of a tile element in the (possibly swizzled) shared-memory tile; linear over XOR
@@ -305,7 +307,7 @@ __device__ __forceinline__ double2* amp_addr(const TileGeom& g, const Shards& sh
     return sh.p0 + (base | __ldg(g.scat + (k >> g.lbits)) | (uint64_t)(k & lmask));
 }
 __device__ __forceinline__ uint64_t tile_base(const TileGeom& g, uint64_t t) {
-    return pdep64(g.tile_first + t * g.tile_stride, g.comp_mask);
+    return pdep64(g.rev ? g.tile_first - t * g.tile_stride : g.tile_first + t * g.tile_stride, g.comp_mask);
 }
 
 __device__ __forceinline__ void tile_load(double2* tile, const Shards& src, const TileGeom& g, uint64_t base) {
@@ -866,7 +868,7 @@ __device__ __forceinline__ BaseLane base_lane_init(const TileGeom& g) {
     return bl;
 }
 __device__ __forceinline__ uint64_t tile_base_warp(const TileGeom& g, const BaseLane& bl, uint64_t t) {
-    const uint64_t tnum = g.tile_first + t * g.tile_stride;
+    const uint64_t tnum = g.rev ? g.tile_first - t * g.tile_stride : g.tile_first + t * g.tile_stride;
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t bit = (bl.act && ((tnum >> lane) & 1ull)) ? (1ull << bl.pos) : 0ull;
     const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)bit);
@@ -2426,13 +2428,14 @@ __global__ void __launch_bounds__(THREADS, RL ? 4 : 3) k_expect_lean(const __gri
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_expect_diag2_rl(const double* __restrict__ psi, uint64_t n_amp, int n, int tb, uint64_t sign_base,
                                                          double c0, const double* __restrict__ a, const double* __restrict__ b,
-                                                         const double* __restrict__ t_tab, double2* __restrict__ partial) {
+                                                         const double* __restrict__ t_tab, int rev, double2* __restrict__ partial) {
     __shared__ double sv[16], sA[32], sB[256], sK, red[64];
     const uint32_t tid = threadIdx.x, chunk = 1u << tb;
     const uint64_t n_chunks = n_amp >> tb;
     const int lb = tb < 5 ? tb : 5;
     double acc = 0.0;
-    for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    for (uint64_t k = blockIdx.x; k < n_chunks; k += gridDim.x) {
+        const uint64_t ch = rev ? n_chunks - 1 - k : k;   // alternating walk (see launch_plan): start where the previous pass ended
         const uint64_t o = (ch << tb) | sign_base;   // the chunk's amplitudes are o | t, t < 2^tb
         __syncthreads();                             // the tables of the previous chunk are consumed
         if ((int)tid < tb) {
@@ -2951,6 +2954,7 @@ struct vqe_ctx {
     std::vector<std::pair<int, int>> swap_history;  // (global slot, local slot) of every swap since the last reset
     uint64_t n_swaps = 0, swap_bytes = 0;   // statistics: swaps executed, bytes this rank read from its partners in swaps
     PlanCache* plan_cache = nullptr;        // see rotations_impl
+    bool walk_desc = false;                 // the last pass over buffer 0 walked its tiles downwards (see launch_plan: alternating walk)
     size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside and largest access-policy window (0: not used)
     char* d_coltab = nullptr;               // item table of the plan whose identity is coltab_gen (k_col_stab: 16-bit items; k_col_tab: 32-bit)
     size_t coltab_cap = 0;                  // in bytes
@@ -3501,6 +3505,7 @@ static int make_geom(const vqe_ctx* c, const TilePlan& tp, const uint64_t* d_sca
     g.tma = 0;
     g.swz = 0;
     g.rl = 0;
+    g.rev = 0;
     memset(&g.tg, 0, sizeof g.tg);
     if (!tp.vbit) {
         g.n_tiles = tp.n_tiles;
@@ -3916,6 +3921,7 @@ extern "C" int vqe_set_basis_state(vqe_ctx* c, uint64_t index) {
         k_zero_set_real<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(reinterpret_cast<double*>(c->buf[0]), c->n_amp, local);
     else
         k_zero_set<<<grid_1d(c, c->n_amp, 256), 256, 0, c->stream>>>(c->buf[0], c->n_amp, local);
+    c->walk_desc = false;   // written by ascending address
     c->real_layout = c->real_layout_ok;
     c->psi_real = true;
     perm_reset(c);  // a fresh state is labelled as the caller labels it
@@ -4634,9 +4640,39 @@ static int build_coltab(const OpPlan& plan) {
             const uint32_t items = co.n_active << co.free_log;
             if (co.pad != plan.coltab.size() - plan.coltab_off[p] || ps.tp.tbits > 13)
                 return fail(VQE_ERR_INVALID, "item table of pass %zu is inconsistent with its run descriptors", p);
+            // Which free tile position each bit of the item number drives.  Any bijection is a valid enumeration of the run's
+            // pairs; the one chosen makes the 16 lanes of a half-warp (item bits 0-3) hit 16 different 8-byte bank pairs: a
+            // 64-bit shared-memory access is served per half-warp, and the bank pair of an element is bits 0-3 of its swizzled
+            // index, so bits 0-3 go to free positions whose images under the swizzle are linearly independent in those four
+            // bits (the plain ascending order conflicts 2-way whenever the X-mask holds tile position 2 or 3 -- 29 % of the
+            // wavefronts of a 25-run pass were replays).  Only a fixed position 0 leaves a conflict no order can avoid.
+            std::vector<uint32_t> order;
+            {
+                uint32_t fixed = 0;
+                for (uint32_t d = 0; d < co.nd && d < 6; ++d) fixed |= 1u << __builtin_popcount(~co.dpos[d]);
+                std::vector<uint32_t> freep;
+                for (uint32_t b2 = 0; b2 < (uint32_t)ps.tp.tbits; ++b2)
+                    if (!((fixed >> b2) & 1u)) freep.push_back(b2);
+                if (freep.size() != co.free_log) return fail(VQE_ERR_INVALID, "run descriptor of pass %zu: %zu free positions, free_log %u", p, freep.size(), co.free_log);
+                std::vector<char> used(freep.size(), 0);
+                uint32_t basis[4] = {0, 0, 0, 0};   // GF(2) basis of the chosen bank images, reduced by leading bit
+                if (env_int("VQE_COL_LANE_ORDER", 1) != 0)
+                    for (size_t k = 0; k < freep.size() && order.size() < 4; ++k) {
+                        uint32_t v = swz_idx8(1u << freep[k], swz) & 0xfu;
+                        for (int b3 = 3; b3 >= 0; --b3)
+                            if (((v >> b3) & 1u) && basis[b3]) v ^= basis[b3];
+                        if (!v) continue;
+                        basis[31 - __builtin_clz(v)] = v;
+                        used[k] = 1;
+                        order.push_back(freep[k]);
+                    }
+                for (size_t k = 0; k < freep.size(); ++k)
+                    if (!used[k]) order.push_back(freep[k]);
+            }
             for (uint32_t it = 0; it < items; ++it) {
-                uint32_t l = it & ((1u << co.free_log) - 1u);
-                for (int d = 0; d < 6; ++d) l += l & co.dpos[d];
+                uint32_t l = 0;
+                for (uint32_t k = 0; k < co.free_log; ++k)
+                    if ((it >> k) & 1u) l |= 1u << order[k];
                 const uint32_t pi = it >> co.free_log;
                 l |= plan.dents[ps.ent_begin + co.ent_begin + pi].pat;
                 const uint32_t par = (uint32_t)__builtin_popcount(l & co.lz) & 1u;
@@ -4842,6 +4878,18 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
                     if (gt.swz != plan.coltab_swz[p]) return fail(VQE_ERR_CUDA, "tile swizzle of pass %zu differs from its item table", p);
                     const int ctas_s = smem_s <= 74 * 1024 ? 3 : 2;
                     const int grid_s = tile_grid(c, g.n_tiles, ctas_s);
+                    // Consecutive passes walk the tiles in alternating directions: a pass reads and rewrites every line of the
+                    // state once (the footprint never grows), so what the previous pass touched last is what the L2 still
+                    // holds when the state is about its size (24 qubits in the real layout: 134 MB against 126 MB), and the
+                    // next pass starts there.  H2O: rotation passes 65 -> 58 us on average.  (Ordering the tiles by the
+                    // recency of their lines under the previous pass's own bit significance measured 2 us slower.)
+                    if (buf == VQE_BUF_PSI && gt.tile_stride == 1 && gt.tile_first == 0 && env_int("VQE_ALT_ORDER", 1) != 0) {
+                        c->walk_desc = !c->walk_desc;
+                        if (c->walk_desc) {
+                            gt.rev = 1;
+                            gt.tile_first = gt.n_tiles - 1;
+                        }
+                    }
                     int thr_s = env_int(ctas_s == 3 ? "VQE_STAB_THREADS3" : "VQE_STAB_THREADS2", 512);
                     if (thr_s != 512) thr_s = 256;
                     cudaLaunchConfig_t cfg;
@@ -6941,6 +6989,11 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
     }
     std::vector<size_t> off(nr, 0);
     bool fenced = false;
+    // the passes alternate their walk starting from the direction the state was last written in; the record is put back
+    // afterwards (the passes only read), so a repeated evaluation of the same state takes the same directions -- and sums
+    // its partials in the same order
+    std::vector<char> walk0(nr, 0);
+    for (size_t k = 0; k < nr; ++k) walk0[k] = rs.r[k]->walk_desc ? 1 : 0;
     for (size_t p = 0; p < n_pass; ++p) {
         const bool vbit = pss[0]->passes[p].tp.vbit;
         const bool diag_rl = rl && pss[0]->passes[p].diag_only && pss[0]->diag2.on;   // evaluated on the real layout
@@ -6967,8 +7020,10 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             memset(&tmap, 0, sizeof tmap);
             if (diag_rl && pss[k]->diag2.on && c->real_layout) {
                 const vqe_paulisum::Diag2& dg = pss[k]->diag2;
+                if (env_int("VQE_ALT_ORDER", 1) != 0) c->walk_desc = !c->walk_desc;
                 k_expect_diag2_rl<<<grids[k][p].x, 256, 0, c->stream>>>(reinterpret_cast<const double*>(shards[k][p].p0), c->n_amp, c->n, dg.tb,
-                                                                       geoms[k][p].sign_base, dg.c0, dg.d_a, dg.d_b, dg.d_t, c->d_partial + off[k]);
+                                                                       geoms[k][p].sign_base, dg.c0, dg.d_a, dg.d_b, dg.d_t, c->walk_desc ? 1 : 0,
+                                                                       c->d_partial + off[k]);
                 c->launches++;
                 CK(cudaGetLastError());
                 off[k] += (size_t)grids[k][p].x;
@@ -6985,6 +7040,13 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                 const size_t smem_r = (8ull << pp.tp.tbits) + pp.addpat.size() * sizeof(double);
                 const int thr_l = env_int("VQE_EXP_LEAN_THREADS", 256);
                 const size_t smem_2 = 2 * (8ull << pp.tp.tbits) + 2 * pp.addpat.size() * sizeof(double);
+                if (b == VQE_BUF_PSI && geoms[k][p].tile_stride == 1 && geoms[k][p].tile_first == 0 && env_int("VQE_ALT_ORDER", 1) != 0) {
+                    c->walk_desc = !c->walk_desc;   // alternating walk, as for the rotation passes
+                    if (c->walk_desc) {
+                        geoms[k][p].rev = 1;
+                        geoms[k][p].tile_first = geoms[k][p].n_tiles - 1;
+                    }
+                }
                 if (env_int("VQE_EXP_RL2", 1) != 0 && smem_2 <= 74 * 1024 && (thr_l == 256 || thr_l == 384)) {
                     cudaLaunchConfig_t cfg;
                     memset(&cfg, 0, sizeof cfg);
@@ -7099,6 +7161,7 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
             fenced = true;
         }
     }
+    for (size_t k = 0; k < nr; ++k) rs.r[k]->walk_desc = walk0[k] != 0;
     for (size_t k = 0; k < nr; ++k) {
         vqe_ctx* c = rs.r[k];
         out_per_rank[2 * k] = out_per_rank[2 * k + 1] = 0.0;
