@@ -4086,6 +4086,7 @@ struct OpPlan {
     mutable std::vector<uint16_t> coltab16;    // the same items in 16 bits (k_col_stab), every pass padded to a multiple of 8 items
     mutable std::vector<size_t> coltab16_off;
     mutable std::vector<uint32_t> coltab16_seg;  // segments per pass
+    mutable bool coltab_has32 = false;           // the 32-bit words were built too (k_col_tab, host interpreter form 0)
 };
 
 static bool fast_eligible(const HostOp& h) {
@@ -4624,22 +4625,34 @@ static int l2_window_attr(const vqe_ctx* c, cudaLaunchAttribute* at, const void*
 // Item table of k_col_tab for every pass of a real-layout collapsed-run plan (pure host code).  One word per item of a run:
 // bits 0-15 byte offset of the a-side element in the pass's (swizzled) shared-memory tile, bit 16 parity(l & lz),
 // bits 17- pattern number within the run.  The index arithmetic is the one k_tile_col does per thread and run (col_prep).
-static int build_coltab(const OpPlan& plan) {
+static int build_coltab(const OpPlan& plan, bool want32) {
     static std::atomic<uint64_t> next_gen{1};
     const std::vector<OpPass>& passes = plan.passes;
     plan.coltab.clear();
     plan.coltab_off.assign(passes.size(), 0);
     plan.coltab_swz.assign(passes.size(), 0);
+    plan.coltab16.clear();
+    plan.coltab16_off.assign(passes.size(), 0);
+    plan.coltab16_seg.assign(passes.size(), 0);
+    plan.coltab_has32 = want32;
     for (size_t p = 0; p < passes.size(); ++p) {
         const OpPass& ps = passes[p];
         const uint32_t swz = rl_tile_swz(ps.tp);
         plan.coltab_off[p] = plan.coltab.size();
         plan.coltab_swz[p] = swz;
+        // 16-bit form (k_col_stab): per pass [first segment of every run: n_cols x uint32, padded to 16 bytes][segments]: a segment
+        // is 512 slots, slot = (element index << 3) | parity or 0xffff = empty, stored FACTORED as 32 lane parts + 16 group parts
+        // (slot s = LANE[s & 31] ^ GROUP[s >> 5]); a pattern of a run is ceil(2^free_log / 512) segments
+        plan.coltab16_off[p] = plan.coltab16.size();
+        const size_t n_cols = ps.col_end - ps.col_begin;
+        if (ps.tp.tbits > 13) return fail(VQE_ERR_INVALID, "item table: %d-bit tile", ps.tp.tbits);
+        plan.coltab16.resize(plan.coltab16.size() + ((2 * n_cols + 7) & ~size_t(7)), 0);
+        uint32_t n_seg = 0, items_seen = 0;
         for (size_t q = ps.col_begin; q < ps.col_end; ++q) {
             const DevCol& co = plan.dcols[q];
             const uint32_t items = co.n_active << co.free_log;
-            if (co.pad != plan.coltab.size() - plan.coltab_off[p] || ps.tp.tbits > 13)
-                return fail(VQE_ERR_INVALID, "item table of pass %zu is inconsistent with its run descriptors", p);
+            if (co.pad != items_seen) return fail(VQE_ERR_INVALID, "item table of pass %zu is inconsistent with its run descriptors", p);
+            items_seen += items;
             // Which free tile position each bit of the item number drives.  Any bijection is a valid enumeration of the run's
             // pairs; the one chosen makes the 16 lanes of a half-warp (item bits 0-3) hit 16 different 8-byte bank pairs: a
             // 64-bit shared-memory access is served per half-warp, and the bank pair of an element is bits 0-3 of its swizzled
@@ -4669,56 +4682,40 @@ static int build_coltab(const OpPlan& plan) {
                 for (size_t k = 0; k < freep.size(); ++k)
                     if (!used[k]) order.push_back(freep[k]);
             }
-            for (uint32_t it = 0; it < items; ++it) {
-                uint32_t l = 0;
+            // index deposit, swizzle and parity are linear over XOR: the word of an item is the XOR of one word per set bit of
+            // its number and the word of its pattern
+            auto word_of = [&](uint32_t l) -> uint32_t {   // (byte offset in the swizzled tile) | parity in bit 0
+                return (swz_idx8(l, swz) << 3) | ((uint32_t)__builtin_popcount(l & co.lz) & 1u);
+            };
+            uint32_t wbit[16];
+            for (uint32_t k = 0; k < co.free_log; ++k) wbit[k] = word_of(1u << order[k]);
+            auto word_free = [&](uint32_t it_in_pat) -> uint32_t {
+                uint32_t w = 0;
                 for (uint32_t k = 0; k < co.free_log; ++k)
-                    if ((it >> k) & 1u) l |= 1u << order[k];
-                const uint32_t pi = it >> co.free_log;
-                l |= plan.dents[ps.ent_begin + co.ent_begin + pi].pat;
-                const uint32_t par = (uint32_t)__builtin_popcount(l & co.lz) & 1u;
-                plan.coltab.push_back((swz_idx8(l, swz) << 3) | (par << 16) | (pi << 17));
-            }
-        }
-    }
-    // 16-bit form (k_col_stab): per pass [first segment of every run: n_cols x uint32, padded to 16 bytes][segments]: a segment
-    // is 512 slots, slot = (element index << 3) | parity or 0xffff = empty, stored FACTORED as 32 lane parts + 16 group parts
-    // (slot s = LANE[s & 31] ^ GROUP[s >> 5]); a pattern of a run is ceil(2^free_log / 512) segments
-    plan.coltab16.clear();
-    plan.coltab16_off.assign(passes.size(), 0);
-    plan.coltab16_seg.assign(passes.size(), 0);
-    for (size_t p = 0; p < passes.size(); ++p) {
-        const OpPass& ps = passes[p];
-        plan.coltab16_off[p] = plan.coltab16.size();
-        const size_t n_cols = ps.col_end - ps.col_begin;
-        const size_t head = (2 * n_cols + 7) & ~size_t(7);   // in uint16
-        plan.coltab16.resize(plan.coltab16.size() + head, 0);
-        uint32_t n_seg = 0;
-        for (size_t q = ps.col_begin; q < ps.col_end; ++q) {
-            const DevCol& co = plan.dcols[q];
-            uint32_t* first = reinterpret_cast<uint32_t*>(plan.coltab16.data() + plan.coltab16_off[p]) + (q - ps.col_begin);
-            *first = n_seg;
+                    if ((it_in_pat >> k) & 1u) w ^= wbit[k];
+                return w;
+            };
+            if (want32)
+                for (uint32_t it = 0; it < items; ++it) {
+                    const uint32_t pi = it >> co.free_log;
+                    const uint32_t w = word_free(it & ((1u << co.free_log) - 1u)) ^ word_of(plan.dents[ps.ent_begin + co.ent_begin + pi].pat);
+                    plan.coltab.push_back((w & 0xfff8u) | ((w & 1u) << 16) | (pi << 17));
+                }
+            reinterpret_cast<uint32_t*>(plan.coltab16.data() + plan.coltab16_off[p])[q - ps.col_begin] = n_seg;
             const uint32_t per_pat_items = 1u << co.free_log;
             const uint32_t per_pat_seg = std::max<uint32_t>(1u, per_pat_items / COLSEG);
-            for (uint32_t pi = 0; pi < co.n_active; ++pi)
+            uint16_t lane[32];
+            for (uint32_t ln = 0; ln < 32; ++ln) lane[ln] = ln < per_pat_items ? (uint16_t)word_free(ln) : (uint16_t)0xffffu;
+            for (uint32_t pi = 0; pi < co.n_active; ++pi) {
+                const uint32_t wpat = word_of(plan.dents[ps.ent_begin + co.ent_begin + pi].pat);
                 for (uint32_t k = 0; k < per_pat_seg; ++k, ++n_seg) {
-                    // factored form of the segment's 512 slots: word(s) = LANE[s & 31] ^ GROUP[s >> 5]
-                    auto w16 = [&](uint32_t sl) -> uint32_t {   // the slot's word from the 32-bit table, 0xffff when empty
-                        const uint32_t it_in_pat = k * COLSEG + sl;
-                        if (it_in_pat >= per_pat_items) return 0xffffu;
-                        const uint32_t w = plan.coltab[plan.coltab_off[p] + co.pad + (pi << co.free_log) + it_in_pat];
-                        return (w & 0xfff8u) | ((w >> 16) & 1u);
-                    };
-                    uint16_t fact[COLFACT];
-                    const uint32_t w00 = w16(0);
-                    for (uint32_t ln = 0; ln < 32; ++ln) fact[ln] = w16(ln) == 0xffffu ? 0xffffu : (uint16_t)(w16(ln) ^ w00);
-                    for (uint32_t gj = 0; gj < 16; ++gj) fact[32 + gj] = (uint16_t)w16(32 * gj);
-                    for (uint32_t sl = 0; sl < COLSEG; ++sl) {   // the factorisation must reproduce every slot
-                        const uint32_t wl = fact[sl & 31u], wg = fact[32 + (sl >> 5)];
-                        const uint32_t got = (wl == 0xffffu || wg == 0xffffu) ? 0xffffu : (wl ^ wg);
-                        if (got != w16(sl)) return fail(VQE_ERR_INVALID, "item table of pass %zu does not factor (run %zu, slot %u)", p, q - ps.col_begin, sl);
+                    plan.coltab16.insert(plan.coltab16.end(), lane, lane + 32);
+                    for (uint32_t gj = 0; gj < 16; ++gj) {
+                        const uint32_t it_in_pat = k * COLSEG + 32u * gj;
+                        plan.coltab16.push_back(it_in_pat < per_pat_items ? (uint16_t)(word_free(it_in_pat) ^ wpat) : (uint16_t)0xffffu);
                     }
-                    plan.coltab16.insert(plan.coltab16.end(), fact, fact + COLFACT);
                 }
+            }
         }
         plan.coltab16_seg[p] = n_seg;
     }
@@ -4817,8 +4814,8 @@ static int launch_plan(RankSet& rs, const OpPlan& plan, int buf) {
     const int tab_mode = rl_plan ? std::max(0, std::min(2, env_int("VQE_COL_TAB", 2))) : 0;
     const bool use_tab = tab_mode != 0;
     if (use_tab) {
-        if (plan.gen == 0) {
-            rc = build_coltab(plan);
+        if (plan.gen == 0 || (tab_mode == 1 && !plan.coltab_has32)) {
+            rc = build_coltab(plan, tab_mode == 1);
             if (rc) return rc;
         }
         const void* tab_src = tab_mode == 2 ? (const void*)plan.coltab16.data() : (const void*)plan.coltab.data();
@@ -5411,7 +5408,7 @@ extern "C" int vqe_debug_coltab_host(int n_qubits, int tile_bits, int low_bits, 
                              (ps.sup_end - ps.sup_begin) == (ps.col_end - ps.col_begin);
         if (!all_col || ps.tp.vbit) return fail(VQE_ERR_INVALID, "the program has a pass that is not a real collapsed-run pass");
     }
-    rc = build_coltab(plan);
+    rc = build_coltab(plan, true);
     if (rc) return rc;
     if (n_passes) *n_passes = (int32_t)plan.passes.size();
     if (n_words) *n_words = (int32_t)plan.coltab.size();

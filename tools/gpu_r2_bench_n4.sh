@@ -1,4 +1,5 @@
 #!/bin/bash
+# the driver's own command at N = 4 (replicas + the sharded C5 leg)
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29724 bench.py --gpus 4 --steps 5 --warmup 3 > gpurun_out/r2c19_bench_n4.json 2> gpurun_out/r2c19_bench_n4.err
-tail -c 400 gpurun_out/r2c19_bench_n4.json; tail -3 gpurun_out/r2c19_bench_n4.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29724 bench.py --gpus 4 --steps 5 --warmup 3 > gpurun_out/r2g_bench_n4.json 2> gpurun_out/r2g_bench_n4.err
+tail -c 300 gpurun_out/r2g_bench_n4.json; tail -3 gpurun_out/r2g_bench_n4.err

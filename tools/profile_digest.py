@@ -68,25 +68,41 @@ def ncu(rep, out):
     json.dump({"report": rep, "launches": res}, open(out, "w"), indent=1)
 
 
-def hot(rep, out, top=45):
+def hot(rep, out, top=40):
+    """Hottest SASS lines by stall samples, with the dominant stall reason, for every distinct launch of the report
+    (the source page repeats its header per launch; ncu lists a launch twice when two sections carry the source view)."""
     rows = ncu_rows(rep, "source")
-    hdr = rows[1]
-    ix = {h: i for i, h in enumerate(hdr)}
-    body = [r for r in rows[2:] if len(r) == len(hdr)]
-    ti = sum(int(r[ix["Instructions Executed"]]) for r in body)
-    ts = sum(int(r[ix["# Samples"]]) for r in body)
-    lines = ["# %s" % rows[0][1][:120], "# warp instructions %d, stall samples %d, SASS lines %d" % (ti, ts, len(body)), ""]
-    ops = {}
-    for r in body:
-        toks = r[ix["Source"]].split()
-        op = (toks[1] if toks and toks[0].startswith("@") else (toks[0] if toks else "?")).split(".")[0]
-        ops[op] = ops.get(op, 0) + int(r[ix["Instructions Executed"]])
-    lines.append("opcode mix (%% of executed warp instructions): %s" %
-                 [(k, round(100.0 * v / max(ti, 1), 1)) for k, v in sorted(ops.items(), key=lambda kv: -kv[1])[:16]])
-    lines += ["", "samples   share  executed   instruction"]
-    for r in sorted(body, key=lambda r: -int(r[ix["# Samples"]]))[:top]:
-        lines.append("%7s %6.1f%% %9s   %s" % (r[ix["# Samples"]], 100.0 * int(r[ix["# Samples"]]) / max(ts, 1),
-                                             r[ix["Instructions Executed"]], r[ix["Source"]].strip()[:100]))
+    heads = [i for i, r in enumerate(rows) if "Instructions Executed" in r]
+    lines, seen = [], set()
+    for li, h in enumerate(heads):
+        end = heads[li + 1] - 1 if li + 1 < len(heads) else len(rows)
+        hdr = rows[h]
+        ix = {c: i for i, c in enumerate(hdr)}
+        body = [r for r in rows[h + 1:end] if len(r) == len(hdr)]
+        ti = sum(int(r[ix["Instructions Executed"]]) for r in body)
+        ts = sum(int(r[ix["# Samples"]]) for r in body)
+        key = (ti, ts, len(body))
+        if key in seen or not body:
+            continue
+        seen.add(key)
+        stalls = [c for c in hdr if c.startswith("stall_") and "Not Issued" not in c]
+        agg = {s_: sum(int(r[ix[s_]] or 0) for r in body) for s_ in stalls}
+        title = rows[h - 1][1][:120] if h > 0 and len(rows[h - 1]) > 1 else ""
+        lines += ["# launch %d %s" % (len(seen) - 1, title), "# warp instructions %d, stall samples %d, SASS lines %d" % (ti, ts, len(body)),
+                  "# stall samples by reason: %s" % [(k[6:], v) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]]]
+        ops = {}
+        for r in body:
+            toks = r[ix["Source"]].split()
+            op = (toks[1] if toks and toks[0].startswith("@") else (toks[0] if toks else "?")).split(".")[0]
+            ops[op] = ops.get(op, 0) + int(r[ix["Instructions Executed"]])
+        lines.append("# opcode mix (%% of executed warp instructions): %s" %
+                     [(k, round(100.0 * v / max(ti, 1), 1)) for k, v in sorted(ops.items(), key=lambda kv: -kv[1])[:16]])
+        lines += ["", "samples   share  executed  main stall        instruction"]
+        for r in sorted(body, key=lambda r: -int(r[ix["# Samples"]]))[:top]:
+            st = max(stalls, key=lambda s_: int(r[ix[s_]] or 0))
+            lines.append("%7s %6.1f%% %9s  %-16s  %s" % (r[ix["# Samples"]], 100.0 * int(r[ix["# Samples"]]) / max(ts, 1),
+                                                         r[ix["Instructions Executed"]], st[6:], r[ix["Source"]].strip()[:100]))
+        lines.append("")
     open(out, "w").write("\n".join(lines) + "\n")
 
 
