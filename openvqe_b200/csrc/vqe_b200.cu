@@ -34,6 +34,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <string>
 #include <map>
 #include <string>
@@ -2266,6 +2267,27 @@ __host__ __device__ __forceinline__ void lean_decode(const uint4& q0, const uint
     u.o[6] = q2.w & 0xffffu; u.o[7] = q2.w >> 16;
 }
 
+// the fields of an entry that do not depend on the lane (the lane part then comes from a lane table, see PSPass::rlp)
+__host__ __device__ __forceinline__ void lean_decode_uniform(const uint4& q0, const uint4& q1, const uint4& q2, LeanUnit& u) {
+#ifdef __CUDA_ARCH__
+    u.fr = __hiloint2double((int)q0.y, (int)q0.x);
+#else
+    uint64_t bits = ((uint64_t)q0.y << 32) | q0.x;
+    memcpy(&u.fr, &bits, 8);
+#endif
+    u.lx16 = q0.z & 0xffffu;
+    u.v = 0;
+    u.s0 = 0;
+    u.jsign = q1.z & 0xffffu;
+    u.tab = q1.z >> 16;
+    u.hi0 = q1.w & 0xffffu;
+    u.bidx = q1.w >> 16;
+    u.o[0] = q2.x & 0xffffu; u.o[1] = q2.x >> 16;
+    u.o[2] = q2.y & 0xffffu; u.o[3] = q2.y >> 16;
+    u.o[4] = q2.z & 0xffffu; u.o[5] = q2.z >> 16;
+    u.o[6] = q2.w & 0xffffu; u.o[7] = q2.w >> 16;
+}
+
 // The real-layout form of an entry: every byte offset is halved (8-byte tile elements) and re-swizzled for the layout the
 // real-layout tile has in shared memory (swz_c / swz_r: the complex / real tile is 128-byte swizzled).
 static inline DevFlat2 lean_entry_to_rl(const DevFlat2& f, bool swz_c, bool swz_r) {
@@ -2513,78 +2535,60 @@ __device__ __forceinline__ double lean_part_rl(const char* tb, const LeanUnit& u
 // lean_entries for TWO real-layout tiles resident at once (tb1 == nullptr: one): an entry is fetched and decoded once
 // (about two thirds of the instructions of an entry are decode: descriptor unpack, index deposit, parity) and evaluated on
 // both tiles -- only the outside-tile sign and the per-tile constants differ.
+// lanetab != nullptr: the entries are those of the real-layout twin (PSPass::rlp) -- the per-lane part of an entry (byte offset
+// of the lane's a-side element for j = 0, pattern and swizzle included, with the Z parity in bit 0) is read from the twin's
+// lane table, 32 words per entry, instead of being deposited from the lane number.
 __device__ __forceinline__ double lean_entries_pair(const char* tb0, const char* tb1, const DevFlat2* __restrict__ flats, int e0, int e1,
                                                     int stride, uint32_t lane, uint64_t sbase0, uint64_t sbase1,
                                                     const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
-                                                    const double* s_beta0, const double* s_beta1, uint32_t swz) {
+                                                    const double* s_beta0, const double* s_beta1, uint32_t swz,
+                                                    const uint16_t* __restrict__ lanetab = nullptr) {
     double er = 0.0;
     if (e0 >= e1) return er;
     const uint4* ep = reinterpret_cast<const uint4*>(flats + e0);
     uint4 q0 = __ldg(ep), q1 = __ldg(ep + 1), q2 = __ldg(ep + 2);
     uint64_t zo = __ldg(fzout + (q0.w >> 16));
+    uint32_t lw = lanetab ? (uint32_t)__ldg(lanetab + (size_t)e0 * 32u + lane) : 0u;
     for (int e = e0; e < e1; e += stride) {
         uint4 n0 = q0, n1 = q1, n2 = q2;
         uint64_t nzo = zo;
+        uint32_t nlw = lw;
         if (e + stride < e1) {
             const uint4* np = reinterpret_cast<const uint4*>(flats + e + stride);
             n0 = __ldg(np);
             n1 = __ldg(np + 1);
             n2 = __ldg(np + 2);
+            if (lanetab) nlw = (uint32_t)__ldg(lanetab + (size_t)(e + stride) * 32u + lane);
         }
         LeanUnit u;
-        lean_decode(q0, q1, q2, lane, u, 3u);
-        const uint32_t vs = swz_off(u.v, swz);
+        uint32_t vs;
+        if (lanetab) {
+            lean_decode_uniform(q0, q1, q2, u);
+            vs = lw & 0xfff8u;
+            u.s0 = lw & 1u;
+        } else {
+            lean_decode(q0, q1, q2, lane, u, 3u);
+            vs = swz_off(u.v, swz);
+        }
         double part = flipsign(lean_part_rl(tb0, u, vs, lane, addtab, s_beta0), u.s0 + (uint32_t)__popcll(sbase0 & zo));
         if (tb1) part += flipsign(lean_part_rl(tb1, u, vs, lane, addtab, s_beta1), u.s0 + (uint32_t)__popcll(sbase1 & zo));
         er = fma(u.fr, part, er);
         if (e + stride < e1) nzo = __ldg(fzout + (n0.w >> 16));
         q0 = n0; q1 = n1; q2 = n2;
         zo = nzo;
-    }
-    return er;
-}
-// lean_entries_pair with TWO entries in flight per warp: the decode chain of one entry overlaps the pair loads of the other
-// (the kernel is latency-bound at 24 warps per SM).  Needs ~128 registers: 2 CTAs per SM.
-__device__ __forceinline__ double lean_entries_pair2(const char* tb0, const char* tb1, const DevFlat2* __restrict__ flats, int e0, int e1,
-                                                     int stride, uint32_t lane, uint64_t sbase0, uint64_t sbase1,
-                                                     const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
-                                                     const double* s_beta0, const double* s_beta1, uint32_t swz) {
-    double er = 0.0;
-    for (int e = e0; e < e1; e += 2 * stride) {
-        const bool two = e + stride < e1;
-        const uint4* pa = reinterpret_cast<const uint4*>(flats + e);
-        const uint4* pb = reinterpret_cast<const uint4*>(flats + (two ? e + stride : e));
-        const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
-        const uint4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
-        const uint64_t zoa = __ldg(fzout + (a0.w >> 16)), zob = __ldg(fzout + (b0.w >> 16));
-        LeanUnit ua, ub;
-        lean_decode(a0, a1, a2, lane, ua, 3u);
-        lean_decode(b0, b1, b2, lane, ub, 3u);
-        const uint32_t vsa = swz_off(ua.v, swz), vsb = swz_off(ub.v, swz);
-        double pa0 = lean_part_rl(tb0, ua, vsa, lane, addtab, s_beta0);
-        double pb0 = lean_part_rl(tb0, ub, vsb, lane, addtab, s_beta0);
-        pa0 = flipsign(pa0, ua.s0 + (uint32_t)__popcll(sbase0 & zoa));
-        pb0 = flipsign(pb0, ub.s0 + (uint32_t)__popcll(sbase0 & zob));
-        if (tb1) {
-            const double pa1 = lean_part_rl(tb1, ua, vsa, lane, addtab, s_beta1);
-            const double pb1 = lean_part_rl(tb1, ub, vsb, lane, addtab, s_beta1);
-            pa0 += flipsign(pa1, ua.s0 + (uint32_t)__popcll(sbase1 & zoa));
-            pb0 += flipsign(pb1, ub.s0 + (uint32_t)__popcll(sbase1 & zob));
-        }
-        er = fma(ua.fr, pa0, er);
-        if (two) er = fma(ub.fr, pb0, er);
+        lw = nlw;
     }
     return er;
 }
 // Real-layout expectation pass, pair mode: both tile slots of the CTA are loaded and every entry is evaluated on both
 // (lean_entries_pair); other CTAs of the SM cover the load.  Same launch geometry and shared-memory layout as k_expect_rl2.
-template <int THREADS, bool DUAL = false>
-__global__ void __launch_bounds__(THREADS, DUAL ? 2 : 3) k_expect_rlp(const __grid_constant__ CUtensorMap tmap, TileGeom g,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 3) k_expect_rlp(const __grid_constant__ CUtensorMap tmap, TileGeom g,
                                                         const DevFlat2* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
                                                         const DevAddPat* __restrict__ addpat, int n_addpat,
-                                                        const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
-                                                        int* __restrict__ err) {
+                                                        const DevAddOut* __restrict__ addout, const uint16_t* __restrict__ lanetab,
+                                                        double2* __restrict__ partial, int* __restrict__ err) {
     extern __shared__ __align__(1024) double2 tile[];
     __shared__ double red[64];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -2617,12 +2621,8 @@ __global__ void __launch_bounds__(THREADS, DUAL ? 2 : 3) k_expect_rlp(const __gr
         if (!mbar_wait(&s_mbar, mphase) && err) *err = 2;
         mphase ^= 1u;
         __syncthreads();
-        if (DUAL)
-            er += lean_entries_pair2(tb, two ? tb + slot_bytes : nullptr, flats, f0 + (int)warp, f1, (int)nw, lane, base0 | g.sign_base,
-                                     base1 | g.sign_base, fzout, addtab, s_beta, s_beta + n_addpat, g.swz);
-        else
-            er += lean_entries_pair(tb, two ? tb + slot_bytes : nullptr, flats, f0 + (int)warp, f1, (int)nw, lane, base0 | g.sign_base,
-                                    base1 | g.sign_base, fzout, addtab, s_beta, s_beta + n_addpat, g.swz);
+        er += lean_entries_pair(tb, two ? tb + slot_bytes : nullptr, flats, f0 + (int)warp, f1, (int)nw, lane, base0 | g.sign_base,
+                                    base1 | g.sign_base, fzout, addtab, s_beta, s_beta + n_addpat, g.swz, lanetab);
     }
     double2 sres = block_sum2(er, 0.0, red);
     if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sres;
@@ -2637,8 +2637,8 @@ __global__ void __launch_bounds__(THREADS, 3) k_expect_rl2(const __grid_constant
                                                         const DevFlat2* __restrict__ flats, int n_flats,
                                                         const uint64_t* __restrict__ fzout, const double* __restrict__ addtab,
                                                         const DevAddPat* __restrict__ addpat, int n_addpat,
-                                                        const DevAddOut* __restrict__ addout, double2* __restrict__ partial,
-                                                        int* __restrict__ err) {
+                                                        const DevAddOut* __restrict__ addout, const uint16_t* __restrict__ lanetab,
+                                                        double2* __restrict__ partial, int* __restrict__ err) {
     extern __shared__ __align__(1024) double2 tile[];
     __shared__ double red[64];
     __shared__ __align__(8) uint64_t s_mbar[2];
@@ -2679,8 +2679,8 @@ __global__ void __launch_bounds__(THREADS, 3) k_expect_rl2(const __grid_constant
         const bool ok = mbar_wait(&s_mbar[sl], sl ? ph1 : ph0);
         if (!ok && err) *err = 2;
         if (sl) ph1 ^= 1u; else ph0 ^= 1u;
-        er += lean_entries<true, true>(tb + sl * slot_bytes, flats, f0 + (int)warp, f1, (int)nw, lane, sbase, fzout, addtab,
-                                       s_beta + sl * n_addpat, g.swz);
+        er += lean_entries_pair(tb + sl * slot_bytes, nullptr, flats, f0 + (int)warp, f1, (int)nw, lane, sbase, sbase, fzout, addtab,
+                                s_beta + sl * n_addpat, s_beta + sl * n_addpat, g.swz, lanetab);
         __syncthreads();  // slot sl is free again; the constants of the next tile are in place
     }
     double2 sres = block_sum2(er, 0.0, red);
@@ -3128,7 +3128,6 @@ static int set_kernel_attrs(int device) {
     SET_SMEM((k_col_stab<512, 3>));
     SET_SMEM(k_expect_rl2<256>);
     SET_SMEM(k_expect_rlp<256>);
-    SET_SMEM((k_expect_rlp<256, true>));
     SET_SMEM(k_expect_rl2<384>);
     SET_SMEM(k_col_pipe<false>);
     SET_SMEM(k_col_pipe<true>);
@@ -5723,6 +5722,18 @@ struct PSPass {
     DevFlat2* d_flats2_rl = nullptr;    // the entries in real-layout form (expectation on a state kept as n_amp doubles)
     bool rl_ok = false, rl_swz = false; // the pass has a real-layout tensor-map form | whose tile is swizzled
     bool diag_only = false;             // general pass that holds nothing but X-mask-0 groups (see vqe_paulisum::diag2)
+    // REAL-LAYOUT TWIN with a LANE TABLE (expectation on a state kept as n_amp doubles; k_expect_rlp / k_expect_rl2): the same
+    // groups lowered a second time, directly into real-layout offsets, with the free tile positions assigned so that the 16
+    // lanes of a half-warp hit 16 different 8-byte bank pairs (see lower_lean_group, rl_order), and the per-lane part of an
+    // entry (index deposit, pattern, swizzle, parity) tabulated: 32 words of (byte offset | parity) per entry.
+    std::shared_ptr<PSPass> rlp;        // flats2 / addtab / addpat / addout / fzout of the twin; rlp->swz = the real-layout swizzle
+    std::vector<uint16_t> lane_rl;      // (in the twin) 32 lane words per entry
+    bool rl_lane = false;               // the twin is uploaded and in use (d_flats2_rl then holds ITS entries)
+    uint16_t* d_lane_rl = nullptr;
+    double* d_addtab_rl = nullptr;
+    DevAddPat* d_addpat_rl = nullptr;
+    DevAddOut* d_addout_rl = nullptr;
+    uint64_t* d_fzout_rl = nullptr;
     uint32_t* d_goff = nullptr;
     double* d_addtab = nullptr;
     DevAddPat* d_addpat = nullptr;
@@ -5779,7 +5790,12 @@ static bool lean_eligible(uint64_t x, const std::vector<HTerm>& terms, int nl, i
 
 // Lower one eligible group into entries of pass p (appended; nothing is appended when the pass capacities would be
 // exceeded -> false).  See the comment block above DevFlat2 for the algebra.
-static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& terms) {
+// rl_order: lower into the REAL-LAYOUT twin (PSPass::rlp): offsets in bytes of 8-byte elements, swizzled with p.swz as the
+// real-layout swizzle, 32 lane words per entry in p.lane_rl, and the free tile positions re-ordered -- entry bits 0-3 (the 16
+// lanes of a half-warp, which a 64-bit shared-memory access is served for) go to free positions whose images under the
+// swizzle are linearly independent in the four bank-pair bits, the rest ascending.  The plain ascending order conflicts
+// 2-way whenever the X-mask holds tile position 0, 2 or 3: 36 % of the wavefronts of an H2O expectation pass were replays.
+static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& terms, bool rl_order = false) {
     const TilePlan& tp = p.tp;
     const uint32_t lx = plan_lx(x, tp);
     const int nx = __builtin_popcount(lx);
@@ -5787,6 +5803,22 @@ static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& te
     const uint32_t hb = 31 - __builtin_clz(lx);
     std::vector<uint32_t> xpos, fpos;
     for (int b = 0; b < tb; ++b) ((lx >> b) & 1u ? xpos : fpos).push_back((uint32_t)b);
+    if (rl_order) {
+        const uint32_t swr = p.swz ? 0x70u : 0u;
+        std::vector<uint32_t> first, rest;
+        uint32_t basis[4] = {0, 0, 0, 0};
+        for (uint32_t b : fpos) {
+            uint32_t v = first.size() < 4 ? (swz_idx8(1u << b, swr) & 0xfu) : 0u;
+            for (int b3 = 3; b3 >= 0 && v; --b3)
+                if (((v >> b3) & 1u) && basis[b3]) v ^= basis[b3];
+            if (v) {
+                basis[31 - __builtin_clz(v)] = v;
+                first.push_back(b);
+            } else rest.push_back(b);
+        }
+        fpos = first;
+        fpos.insert(fpos.end(), rest.begin(), rest.end());
+    }
     const uint32_t lz0 = plan_lz(terms[0].z, tp);
     const uint64_t zout0 = plan_zout(terms[0].z, tp);
     struct LT {
@@ -5818,6 +5850,7 @@ static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& te
         return o;
     };
     std::vector<DevFlat2> ents;
+    std::vector<uint16_t> lanes;
     std::vector<double> tabs;
     std::vector<DevAddPat> pats;
     std::vector<DevAddOut> outs;
@@ -5879,18 +5912,25 @@ static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& te
             DevFlat2 fl;
             memset(&fl, 0, sizeof fl);
             const uint32_t sw = p.swz ? 0x70u : 0u;
+            const uint32_t esh = rl_order ? 3u : 4u;   // log2 of the tile element size
             fl.fr = additive ? 2.0 : 2.0 * beta0;
-            fl.lx16 = (uint16_t)swz_off(lx << 4, sw);
-            fl.lz16 = (uint16_t)(lz0 << 4);
-            fl.pat16 = (uint16_t)(pat << 4);
+            fl.lx16 = (uint16_t)swz_off(lx << esh, sw);
+            fl.lz16 = (uint16_t)(lz0 << esh);
+            fl.pat16 = (uint16_t)(pat << esh);
             fl.zsel = (uint16_t)zsel;
-            for (int k = 0; k < 4; ++k) fl.hm16[k] = k < nx ? (uint16_t)(~((1u << (xpos[k] + 4)) - 1u) & 0xffffu) : 0;
+            // (the twin's lane part comes from its lane table: no deposit masks)
+            for (int k = 0; k < 4; ++k) fl.hm16[k] = (k < nx && !rl_order) ? (uint16_t)(~((1u << (xpos[k] + 4)) - 1u) & 0xffffu) : 0;
             uint32_t js = 0;
             for (uint32_t j = 0; j < 8; ++j) {
                 const uint32_t oj = pdep_free((ch << 8) | (j << 5));
-                fl.o16[j] = (uint16_t)swz_off(oj << 4, sw);
+                fl.o16[j] = (uint16_t)swz_off(oj << esh, sw);
                 if (__builtin_popcount(oj & lz0) & 1) js |= 1u << j;
             }
+            if (rl_order)
+                for (uint32_t ln = 0; ln < 32; ++ln) {
+                    const uint32_t l = pdep_free(ln) | pat;
+                    lanes.push_back((uint16_t)(swz_off(l << 3, sw) | ((uint32_t)__builtin_popcount(l & lz0) & 1u)));
+                }
             fl.jsign = (uint16_t)js;
             fl.tab = (uint16_t)tab;
             fl.hi0 = additive ? (uint16_t)(tab + 32 + (ch << 3)) : 0;
@@ -5905,6 +5945,7 @@ static bool lower_lean_group(PSPass& p, uint64_t x, const std::vector<HTerm>& te
     if (zsel == p.fzout.size()) p.fzout.push_back(zout0);
     if (p.goff.empty()) p.goff.push_back(0);
     p.flats2.insert(p.flats2.end(), ents.begin(), ents.end());
+    p.lane_rl.insert(p.lane_rl.end(), lanes.begin(), lanes.end());
     p.goff.push_back((uint32_t)p.flats2.size());
     p.addtab.insert(p.addtab.end(), tabs.begin(), tabs.end());
     p.addpat.insert(p.addpat.end(), pats.begin(), pats.end());
@@ -6178,16 +6219,34 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
             lpass[i].tp = lplans[i].tp;
             lpass[i].swz = lplans[i].swz;
             std::sort(members[i].begin(), members[i].end());
+            // the real-layout twin with its lane table (see PSPass::rlp), when the pass has a real-layout tensor-map form
+            if (env_int("VQE_EXP_LANE_TAB", 1) != 0 && env_int("VQE_EXP_RL2", 1) != 0 && !lplans[i].tp.vbit && lplans[i].tp.tbits >= 9) {
+                const bool sw_ok = env_int("VQE_SWIZZLE", 1) != 0 &&
+                                   (host_only ? plan_tma(lplans[i].tp, true, true).ok : tma_available(lplans[i].tp, true, true));
+                const bool nat_ok = host_only ? plan_tma(lplans[i].tp, false, true).ok : tma_available(lplans[i].tp, false, true);
+                if (sw_ok || nat_ok) {
+                    lpass[i].rlp = std::make_shared<PSPass>();
+                    lpass[i].rlp->lean = true;
+                    lpass[i].rlp->tp = lplans[i].tp;
+                    lpass[i].rlp->swz = sw_ok;
+                }
+            }
         }
+        // lowers a group into a pass and, in the same order, into its real-layout twin (the twin is dropped if it ever refuses)
+        auto lower_both = [&](PSPass& ps2, size_t g) -> bool {
+            if (!lower_lean_group(ps2, xs[g], grp[g])) return false;
+            if (ps2.rlp && !lower_lean_group(*ps2.rlp, xs[g], grp[g], true)) ps2.rlp.reset();
+            return true;
+        };
         std::vector<size_t> spill;
         for (size_t i = 0; i < lplans.size(); ++i)
             for (size_t g : members[i]) {
-                if (lower_lean_group(lpass[i], xs[g], grp[g])) done[g] = 1;
+                if (lower_both(lpass[i], g)) done[g] = 1;
                 else spill.push_back(g);
             }
         for (size_t g : spill)
             for (size_t i = 0; i < lplans.size() && !done[g]; ++i)
-                if ((xs[g] & lfull & ~lplans[i].tp.tile_mask) == 0 && lower_lean_group(lpass[i], xs[g], grp[g])) done[g] = 1;
+                if ((xs[g] & lfull & ~lplans[i].tp.tile_mask) == 0 && lower_both(lpass[i], g)) done[g] = 1;
         for (size_t i = 0; i < lplans.size(); ++i)
             if (!lpass[i].flats2.empty()) {
                 batch_lean_entries(lpass[i]);
@@ -6538,6 +6597,16 @@ static void free_paulisum_device(vqe_paulisum* ps) {
         if (p.d_flats2) cudaFree(p.d_flats2);
         if (p.d_flats2_rl) cudaFree(p.d_flats2_rl);
         p.d_flats2_rl = nullptr;
+        if (p.d_lane_rl) cudaFree(p.d_lane_rl);
+        if (p.d_addtab_rl) cudaFree(p.d_addtab_rl);
+        if (p.d_addpat_rl) cudaFree(p.d_addpat_rl);
+        if (p.d_addout_rl) cudaFree(p.d_addout_rl);
+        if (p.d_fzout_rl) cudaFree(p.d_fzout_rl);
+        p.d_lane_rl = nullptr;
+        p.d_addtab_rl = nullptr;
+        p.d_addpat_rl = nullptr;
+        p.d_addout_rl = nullptr;
+        p.d_fzout_rl = nullptr;
         if (p.d_goff) cudaFree(p.d_goff);
         if (p.d_addtab) cudaFree(p.d_addtab);
         if (p.d_addpat) cudaFree(p.d_addpat);
@@ -6575,10 +6644,21 @@ static int upload_paulisum(vqe_ctx* c, vqe_paulisum* ps) {
             int rc = upload_vec(&p.d_flats2, p.flats2);
             // real-layout twin of the entries (unsharded contexts keep a purely real state as n_amp doubles)
             p.rl_ok = false;
+            p.rl_lane = false;
             if (rc == VQE_OK && c->real_layout_ok && !p.tp.vbit && p.tp.tbits >= 9) {
                 p.rl_swz = env_int("VQE_SWIZZLE", 1) != 0 && tma_available(p.tp, true, true);
                 p.rl_ok = p.rl_swz || tma_available(p.tp, false, true);
-                if (p.rl_ok) {
+                if (p.rl_ok && p.rlp && p.rlp->swz == p.rl_swz && p.rlp->flats2.size() == p.flats2.size() &&
+                    p.rlp->lane_rl.size() == 32 * p.flats2.size()) {
+                    // the twin lowered for the real layout (lane table, conflict-free lane order)
+                    rc = upload_vec(&p.d_flats2_rl, p.rlp->flats2);
+                    if (rc == VQE_OK) rc = upload_vec(&p.d_lane_rl, p.rlp->lane_rl);
+                    if (rc == VQE_OK) rc = upload_vec(&p.d_addtab_rl, p.rlp->addtab);
+                    if (rc == VQE_OK) rc = upload_vec(&p.d_addpat_rl, p.rlp->addpat);
+                    if (rc == VQE_OK) rc = upload_vec(&p.d_addout_rl, p.rlp->addout);
+                    if (rc == VQE_OK) rc = upload_vec(&p.d_fzout_rl, p.rlp->fzout);
+                    p.rl_lane = rc == VQE_OK;
+                } else if (p.rl_ok) {
                     std::vector<DevFlat2> rl(p.flats2.size());
                     for (size_t k = 0; k < rl.size(); ++k) rl[k] = lean_entry_to_rl(p.flats2[k], p.swz, p.rl_swz);
                     rc = upload_vec(&p.d_flats2_rl, rl);
@@ -6790,6 +6870,40 @@ extern "C" int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int til
                 const uint32_t swr = swz_r ? 0x70u : 0u;
                 std::vector<double> tr(ts);
                 for (uint32_t k = 0; k < ts; ++k) tr[swz_idx8(k, swr)] = psi[base | p.tp.scat[k >> p.tp.lbits] | (uint64_t)(k & lmask)].x;
+                if (atoi(getenv("VQE_DEBUG_LEAN_RL")) == 2) {
+                    // the twin lowered for the real layout with its lane table (PSPass::rlp): what k_expect_rlp / k_expect_rl2 read
+                    if (!p.rlp || p.rlp->swz != swz_r || p.rlp->lane_rl.size() != 32 * p.rlp->flats2.size() || p.rlp->flats2.size() != p.flats2.size())
+                        return fail(VQE_ERR_INVALID, "pass without a real-layout twin");
+                    const PSPass& r = *p.rlp;
+                    std::vector<double> rbeta(r.addpat.size());
+                    for (size_t k = 0; k < r.addpat.size(); ++k) {
+                        double b = r.addpat[k].beta0;
+                        for (uint32_t q = 0; q < r.addpat[k].out_count; ++q) {
+                            const DevAddOut& ao = r.addout[r.addpat[k].out_begin + q];
+                            b += (popc64(sbase & ao.zrel) & 1) ? -ao.c : ao.c;
+                        }
+                        rbeta[k] = b;
+                    }
+                    for (size_t e = 0; e < r.flats2.size(); ++e) {
+                        uint4 q[3];
+                        memcpy(q, &r.flats2[e], sizeof(DevFlat2));
+                        const uint32_t par_out = (uint32_t)popc64(sbase & r.fzout[q[0].w >> 16]);
+                        LeanUnit u;
+                        lean_decode_uniform(q[0], q[1], q[2], u);
+                        for (uint32_t lane = 0; lane < 32; ++lane) {
+                            const uint32_t lw = r.lane_rl[e * 32 + lane];
+                            for (uint32_t j = 0; j < 8; ++j) {
+                                const uint32_t off = (lw & 0xfff8u) ^ u.o[j], offb = off ^ u.lx16;
+                                if ((off & 7u) || (offb & 7u) || (off >> 3) >= ts || (offb >> 3) >= ts) return fail(VQE_ERR_INVALID, "real-layout offset out of range");
+                                double gw = 0.5 * u.fr;
+                                if (u.tab != 0xffffu) gw *= rbeta[u.bidx] + r.addtab[u.tab + lane] + r.addtab[u.hi0 + j];
+                                if (((lw & 1u) + (u.jsign >> j) + par_out) & 1u) gw = -gw;
+                                total += 2.0 * gw * tr[off >> 3] * tr[offb >> 3];
+                            }
+                        }
+                    }
+                    continue;
+                }
                 for (size_t e = 0; e < p.flats2.size(); ++e) {
                     const DevFlat2 fr = lean_entry_to_rl(p.flats2[e], p.swz, swz_r);
                     uint4 q[3];
@@ -7036,7 +7150,17 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                 if (!geoms[k][p].tma) return fail(VQE_ERR_CUDA, "real-layout tensor map of an expectation pass could not be encoded");
                 const size_t smem_r = (8ull << pp.tp.tbits) + pp.addpat.size() * sizeof(double);
                 const int thr_l = env_int("VQE_EXP_LEAN_THREADS", 256);
-                const size_t smem_2 = 2 * (8ull << pp.tp.tbits) + 2 * pp.addpat.size() * sizeof(double);
+                // entries of the pass: the real-layout twin with its lane table (PSPass::rlp) when it was uploaded, else the
+                // converted entries of the interleaved form (in-kernel index deposit)
+                const bool lane = pp.rl_lane;
+                const int n_fl = lane ? (int)pp.rlp->flats2.size() : (int)pp.flats2.size();
+                const int n_ap = lane ? (int)pp.rlp->addpat.size() : (int)pp.addpat.size();
+                const uint64_t* fz = lane ? pp.d_fzout_rl : pp.d_fzout;
+                const double* atab = lane ? pp.d_addtab_rl : pp.d_addtab;
+                const DevAddPat* apat = lane ? pp.d_addpat_rl : pp.d_addpat;
+                const DevAddOut* aout = lane ? pp.d_addout_rl : pp.d_addout;
+                const uint16_t* ltab = lane ? pp.d_lane_rl : nullptr;
+                const size_t smem_2 = 2 * (8ull << pp.tp.tbits) + 2 * (size_t)n_ap * sizeof(double);
                 if (b == VQE_BUF_PSI && geoms[k][p].tile_stride == 1 && geoms[k][p].tile_first == 0 && env_int("VQE_ALT_ORDER", 1) != 0) {
                     c->walk_desc = !c->walk_desc;   // alternating walk, as for the rotation passes
                     if (c->walk_desc) {
@@ -7062,25 +7186,20 @@ static int expectation_core(RankSet& rs, int b, const vqe_paulisum* const* pss, 
                     cfg.attrs = at;
                     cfg.numAttrs = n_at;
                     if (thr_l == 384)
-                        CK(cudaLaunchKernelEx(&cfg, k_expect_rl2<384>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, (int)pp.flats2.size(),
-                                              (const uint64_t*)pp.d_fzout, (const double*)pp.d_addtab, (const DevAddPat*)pp.d_addpat,
-                                              (int)pp.addpat.size(), (const DevAddOut*)pp.d_addout, c->d_partial + off[k], c->d_err));
-                    else if (env_int("VQE_EXP_PAIR", 1) == 2)   // two entries in flight per warp, 2 CTAs per SM (A/B)
-                        CK(cudaLaunchKernelEx(&cfg, k_expect_rlp<256, true>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, (int)pp.flats2.size(),
-                                              (const uint64_t*)pp.d_fzout, (const double*)pp.d_addtab, (const DevAddPat*)pp.d_addpat,
-                                              (int)pp.addpat.size(), (const DevAddOut*)pp.d_addout, c->d_partial + off[k], c->d_err));
+                        CK(cudaLaunchKernelEx(&cfg, k_expect_rl2<384>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, n_fl, fz, atab, apat, n_ap,
+                                              aout, ltab, c->d_partial + off[k], c->d_err));
                     else if (env_int("VQE_EXP_PAIR", 1) != 0)
-                        CK(cudaLaunchKernelEx(&cfg, k_expect_rlp<256>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, (int)pp.flats2.size(),
-                                              (const uint64_t*)pp.d_fzout, (const double*)pp.d_addtab, (const DevAddPat*)pp.d_addpat,
-                                              (int)pp.addpat.size(), (const DevAddOut*)pp.d_addout, c->d_partial + off[k], c->d_err));
+                        CK(cudaLaunchKernelEx(&cfg, k_expect_rlp<256>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, n_fl, fz, atab, apat, n_ap,
+                                              aout, ltab, c->d_partial + off[k], c->d_err));
                     else
-                        CK(cudaLaunchKernelEx(&cfg, k_expect_rl2<256>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, (int)pp.flats2.size(),
-                                              (const uint64_t*)pp.d_fzout, (const double*)pp.d_addtab, (const DevAddPat*)pp.d_addpat,
-                                              (int)pp.addpat.size(), (const DevAddOut*)pp.d_addout, c->d_partial + off[k], c->d_err));
+                        CK(cudaLaunchKernelEx(&cfg, k_expect_rl2<256>, tmap, geoms[k][p], (const DevFlat2*)pp.d_flats2_rl, n_fl, fz, atab, apat, n_ap,
+                                              aout, ltab, c->d_partial + off[k], c->d_err));
                     c->launches++;
                     off[k] += (size_t)grids[k][p].x * grids[k][p].y;
                     continue;
                 }
+                if (lane) return fail(VQE_ERR_INVALID, "the Pauli sum was lowered with a lane table (VQE_EXP_LANE_TAB), which only the two-slot "
+                                                       "real-layout kernels read: VQE_EXP_RL2 / VQE_EXP_LEAN_THREADS changed after vqe_paulisum_create?");
 #define LAUNCH_EXPECT_RL(T)                                                                                                    \
     k_expect_lean<true, T, true><<<grids[k][p], T, smem_r, c->stream>>>(tmap, shards[k][p], geoms[k][p], pp.d_flats2_rl,       \
                                                                        (int)pp.flats2.size(), pp.d_fzout, pp.d_addtab, pp.d_addpat, \

@@ -122,15 +122,17 @@ def test_groups_outside_the_lean_form_stay_on_the_general_path():
     assert abs(e - e_ref) < 1e-13
 
 
+@pytest.mark.parametrize("form", ["1", "2"])
 @pytest.mark.parametrize("n,seed,low_bits", [(13, 11, 5), (15, 12, 4), (16, 13, 4), (14, 14, 3)])
-def test_real_layout_entries_reproduce_the_expectation(n, seed, low_bits, monkeypatch):
-    """The real-layout twin of the entries (state kept as n_amp doubles, 8-byte tile elements, its own 128-byte swizzle --
-    k_expect_lean<true, T, true>): lean_entry_to_rl + the kernels' decode routine on a tile of doubles = the oracle."""
+def test_real_layout_entries_reproduce_the_expectation(n, seed, low_bits, form, monkeypatch):
+    """The real-layout forms of the entries (state kept as n_amp doubles, 8-byte tile elements, its own 128-byte swizzle) on a
+    tile of doubles = the oracle.  Form 1: lean_entry_to_rl + the kernels' decode routine (k_expect_lean<true, T, true>);
+    form 2: the twin lowered for the real layout with its lane table and conflict-free lane order (k_expect_rlp, the default)."""
     x, z, ny, c = _relabelled_h6(n, seed)
     rng = np.random.default_rng(200 + seed)
     psi = rng.normal(size=1 << n)
     psi = (psi / np.linalg.norm(psi)).astype(np.complex128)
-    monkeypatch.setenv("VQE_DEBUG_LEAN_RL", "1")
+    monkeypatch.setenv("VQE_DEBUG_LEAN_RL", form)
     e, nlean, nfat, _ = _lean(n, x, z, ny, c, psi, low_bits=low_bits, want_sigma=False)
     offdiag = x != 0
     assert nlean == int(offdiag.sum())
