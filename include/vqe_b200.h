@@ -241,6 +241,14 @@ int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int tile_bits, int
                         const double* psi_re_im, double* out_re, int32_t* n_lean_terms, int32_t* n_fat_terms,
                         double* sigma_re_im);
 
+/* Host-only interpreter of the diagonal-part kernel k_expect_diag2_rl (no CUDA call; test support): the X-mask-0 strings of
+ * the sum as a quadratic form in the Z letters, built as vqe_paulisum_create builds it, evaluated on the HOST state psi_re
+ * (2^(n_qubits - n_global) doubles of rank `rank`) with the kernel's chunk decomposition.  *is_form = 0 when the diagonal
+ * part is not a quadratic form (the GPU path then takes the general pass). */
+int vqe_debug_diag2_host(int n_qubits, int n_global, int rank, int n_terms, const uint64_t* xmask, const uint64_t* zmask,
+                         const int32_t* ny, const double* cre, const double* cim, const double* psi_re, double* out_re,
+                         int32_t* is_form);
+
 /* Host-only check (no CUDA call; test support) of the tensor-map (TMA) form of the tile plan that covers the local
  * index bits `need_mask`: emulates the box traversal of every request and compares with the gather addresses of the
  * tile.  Returns the number of mismatching elements (0 = consistent), -1 when the plan keeps per-segment copies. */

@@ -6955,6 +6955,57 @@ extern "C" int vqe_debug_lean_host(int n_qubits, int n_global, int rank, int til
     if (n_fat_terms) *n_fat_terms = (int32_t)fat_terms;
     return VQE_OK;
 }
+// Host-only interpreter of k_expect_diag2_rl (no CUDA call; CPU test support): builds the quadratic form of the diagonal part
+// (X-mask 0) of the Pauli sum exactly as vqe_paulisum_create does and evaluates  sum_l psi_l^2 D(l)  on a HOST state of
+// 2^n_local doubles of rank `rank`, chunk by chunk, with the kernel's decomposition  D = K(o) + A[t & 31] + B[t >> 5] + T(t).
+// *is_form = 0 (and *out_re untouched) when the diagonal part is not a quadratic form (a string with more than two Z
+// letters, a complex weight): the GPU path then takes the general pass.
+extern "C" int vqe_debug_diag2_host(int n_qubits, int n_global, int rank, int n_terms, const uint64_t* x, const uint64_t* z,
+                                    const int32_t* ny, const double* cre, const double* cim, const double* psi_re, double* out_re,
+                                    int32_t* is_form) {
+    if (n_qubits < 1 || n_qubits > 30 || n_global < 0 || n_global >= n_qubits) return fail(VQE_ERR_INVALID, "bad qubit counts");
+    if (!psi_re || !out_re || !is_form) return fail(VQE_ERR_INVALID, "null argument");
+    vqe_ctx fake;
+    fake.n = n_qubits;
+    std::vector<HTerm> terms;
+    int rc = collect_terms(&fake, n_terms, x, z, ny, cre, cim, terms);
+    if (rc) return rc;
+    vqe_paulisum ps;
+    const int n = n_qubits, nl = n_qubits - n_global;
+    rc = build_paulisum(&ps, n, nl, 12, n_global ? 5 : 4, 512, std::move(terms), true);
+    if (rc) return rc;
+    const vqe_paulisum::Diag2& d = ps.diag2;
+    *is_form = d.on ? 1 : 0;
+    if (!d.on) return VQE_OK;
+    const int tb = d.tb, lb = tb < 5 ? tb : 5;
+    const uint64_t n_amp = 1ull << nl, n_chunks = n_amp >> tb, sign_base = (uint64_t)rank << nl;
+    auto sgn = [](uint64_t o, int q, double v) { return ((o >> q) & 1ull) ? -v : v; };
+    double total = 0.0;
+    for (uint64_t ch = 0; ch < n_chunks; ++ch) {
+        const uint64_t o = (ch << tb) | sign_base;
+        std::vector<double> v(tb), A(32, 0.0), B((size_t)1 << (tb - lb), 0.0);
+        for (int p0 = 0; p0 < tb; ++p0) {
+            v[p0] = d.a[p0];
+            for (int q0 = tb; q0 < n; ++q0) v[p0] += sgn(o, q0, d.b[(size_t)p0 * n + q0]);
+        }
+        double K = d.c0;
+        for (int p0 = tb; p0 < n; ++p0) {
+            double inner = d.a[p0];
+            for (int q0 = p0 + 1; q0 < n; ++q0) inner += sgn(o, q0, d.b[(size_t)p0 * n + q0]);
+            K += sgn(o, p0, inner);
+        }
+        for (uint32_t i = 0; i < 32; ++i)
+            for (int p0 = 0; p0 < lb; ++p0) A[i] += ((i >> p0) & 1u) ? -v[p0] : v[p0];
+        for (uint32_t j = 0; j < B.size(); ++j)
+            for (int p0 = lb; p0 < tb; ++p0) B[j] += ((j >> (p0 - lb)) & 1u) ? -v[p0] : v[p0];
+        for (uint32_t t = 0; t < (1u << tb); ++t) {
+            const double xv = psi_re[(ch << tb) | t];
+            total += xv * xv * (K + A[t & 31u] + B[t >> lb] + d.t[t]);
+        }
+    }
+    *out_re = total;
+    return VQE_OK;
+}
 extern "C" void vqe_paulisum_destroy(vqe_paulisum* ps) {
     if (!ps) return;
     cudaSetDevice(ps->device);

@@ -165,3 +165,34 @@ def test_tensor_map_shapes_address_the_tiles(rl):
                     assert bad == 0, (rl, n_local, low_bits, hex(need), swz, bad)
                     checked += 1
     assert checked > 60
+
+
+@pytest.mark.parametrize("n,n_global,rank", [(12, 0, 0), (14, 0, 0), (16, 0, 0), (15, 2, 3), (13, 1, 0)])
+def test_diagonal_part_as_a_quadratic_form(n, n_global, rank):
+    """k_expect_diag2_rl evaluates the X-mask-0 strings of a molecular Hamiltonian (Z_p, Z_p Z_q) as a quadratic form in the Z
+    letters, chunk by chunk (K(o) + A[t & 31] + B[t >> 5] + T(t)); the host interpreter builds the form with the library's own
+    routine and walks the same decomposition -- also on a shard, where the rank bits enter as outside-chunk signs."""
+    from openvqe_b200 import _lib
+    lib = _lib.load()
+    x, z, ny, c = _relabelled_h6(n, 40 + n)
+    nl = n - n_global
+    rng = np.random.default_rng(700 + n)
+    psi_full = np.zeros(1 << n)
+    lo, hi = rank << nl, (rank + 1) << nl
+    psi_full[lo:hi] = rng.normal(size=1 << nl)
+    shard = np.ascontiguousarray(psi_full[lo:hi])
+    out, form = C.c_double(), C.c_int32()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    cim = np.zeros_like(c)
+    _lib.check(lib.vqe_debug_diag2_host(n, n_global, rank, len(x), p(x), p(z), p(ny.astype(np.int32)), p(c), p(cim), p(shard),
+                                        C.byref(out), C.byref(form)))
+    assert form.value == 1
+    diag = x == 0
+    e_ref, _ = _oracle(n, x, z, ny, c, psi_full.astype(np.complex128), diag)
+    assert abs(out.value - e_ref) < 1e-11 * max(1.0, abs(e_ref))
+    # a three-Z string is not a quadratic form: the GPU path keeps the general pass
+    x2, z2 = np.append(x, np.uint64(0)), np.append(z, np.uint64(0b111))
+    ny2, c2 = np.append(ny, 0).astype(np.int32), np.append(c, 0.25)
+    _lib.check(lib.vqe_debug_diag2_host(n, n_global, rank, len(x2), p(x2), p(z2), p(ny2), p(c2), p(np.zeros_like(c2)), p(shard),
+                                        C.byref(out), C.byref(form)))
+    assert form.value == 0
