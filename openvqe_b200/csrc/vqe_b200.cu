@@ -6102,7 +6102,6 @@ static int build_paulisum(vqe_paulisum* ps, int n, int nl, int tbits_max, int lo
     ps->nl = nl;
     ps->n_groups = (int)xs.size();
     const int lb = std::min(low_bits, std::min(tbits_max, nl));
-    const uint64_t lowmask = (1ull << lb) - 1ull;
     const uint64_t lfull = (1ull << nl) - 1ull;
     // split oversize groups so that each fits in the term cache
     {
