@@ -225,6 +225,14 @@ int vqe_debug_coltab_host(int n_qubits, int tile_bits, int low_bits, int form, i
                           const uint64_t* zmask, const int32_t* ny, const double* angle, double* psi_re,
                           int32_t* n_passes, int32_t* n_words);
 
+/* Host-only census of the shared-memory bank pairs the item tables of k_col_stab address (no CUDA call; test support): a
+ * 64-bit access is served per half-warp, conflict-free when its 16 elements sit in 16 different 8-byte bank pairs.
+ * *accesses = half-warp accesses over all segments of the plan, *conflicting = those with two lanes in one bank pair,
+ * *unavoidable = those of runs whose free tile positions cannot reach all 16 bank pairs whatever the item order. */
+int vqe_debug_coltab_banks(int n_qubits, int tile_bits, int low_bits, int n_rot, const uint64_t* xmask,
+                           const uint64_t* zmask, const int32_t* ny, const double* angle, int64_t* accesses,
+                           int64_t* conflicting, int64_t* unavoidable);
+
 /* Host-only view of the Pauli-sum planner (no CUDA call): X-mask grouping and packing of the groups into tile
  * passes (what vqe_paulisum_create builds).  *n_groups = distinct X-masks, *n_passes = state sweeps per evaluation;
  * per pass (at most `cap` written): number of groups, number of terms, tile-bit mask. */

@@ -26,7 +26,7 @@ SYMBOLS = [
     "vqe_shard_barrier", "vqe_shard_status", "vqe_group_apply_pauli_rotations", "vqe_group_apply_gates",
     "vqe_group_expectation", "vqe_group_apply_paulisum", "vqe_group_pool_overlaps", "vqe_plan_rotations",
     "vqe_apply_plane_rotations", "vqe_scale_state", "vqe_apply_pauli_rotations_buf", "vqe_plan_paulisum", "vqe_debug_lean_host", "vqe_peer_bytes", "vqe_debug_tma_check",
-    "vqe_axpby", "vqe_debug_tma_check_rl", "vqe_state_layout", "vqe_relabel_stats", "vqe_debug_coltab_host", "vqe_debug_diag2_host",
+    "vqe_axpby", "vqe_debug_tma_check_rl", "vqe_state_layout", "vqe_relabel_stats", "vqe_debug_coltab_host", "vqe_debug_diag2_host", "vqe_debug_coltab_banks",
 ]
 IPC_HANDLE_BYTES = 64
 SHARD_FLAGS = 3
@@ -109,6 +109,7 @@ def load():
         "vqe_peer_bytes": (C.c_int, [vp, P(u64), C.c_int]),
         "vqe_relabel_stats": (C.c_int, [vp, P(u64), P(u64), C.c_int]),
         "vqe_debug_coltab_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, P(i32), P(i32)]),
+        "vqe_debug_coltab_banks": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
         "vqe_debug_diag2_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, P(dbl), P(i32)]),
         "vqe_debug_lean_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                           P(dbl), P(i32), P(i32), vp]),

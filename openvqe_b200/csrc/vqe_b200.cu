@@ -4657,7 +4657,8 @@ static int build_coltab(const OpPlan& plan, bool want32) {
             // 64-bit shared-memory access is served per half-warp, and the bank pair of an element is bits 0-3 of its swizzled
             // index, so bits 0-3 go to free positions whose images under the swizzle are linearly independent in those four
             // bits (the plain ascending order conflicts 2-way whenever the X-mask holds tile position 2 or 3 -- 29 % of the
-            // wavefronts of a 25-run pass were replays).  Only a fixed position 0 leaves a conflict no order can avoid.
+            // wavefronts of a 25-run pass were replays).  What no order can avoid: a fixed position 0, or both positions that feed
+            // one bank bit fixed (vqe_debug_coltab_banks counts both kinds; tests/test_coltab_cpu.py).
             std::vector<uint32_t> order;
             {
                 uint32_t fixed = 0;
@@ -5471,6 +5472,90 @@ extern "C" int vqe_debug_coltab_host(int n_qubits, int tile_bits, int low_bits, 
                 if (seen != items) return fail(VQE_ERR_INVALID, "segment table of pass %zu holds %u items of run %zu, expected %u", p, seen, q - ps.col_begin, items);
             }
             for (uint32_t k = 0; k < ts; ++k) psi_re[addr[k]] = tile[k];
+        }
+    }
+    return VQE_OK;
+}
+
+// Host-only census of the shared-memory banks the item tables of k_col_stab address (no CUDA call; CPU test support).  A 64-bit
+// shared-memory access is served per half-warp: 16 lanes x 8 bytes = one 128-byte wavefront when the 16 elements sit in 16
+// different 8-byte bank pairs (bits 3-6 of the byte offset).  For every segment of every run of the plan the a-side offsets of
+// the 32 half-warps are checked.  *accesses = half-warp accesses, *conflicting = those with two lanes in one bank pair,
+// *unavoidable = those of runs whose free tile positions cannot reach all 16 bank pairs whatever the item order (tile position 0
+// fixed, or both positions that feed one bank bit).
+extern "C" int vqe_debug_coltab_banks(int n_qubits, int tile_bits, int low_bits, int n_rot, const uint64_t* xmask,
+                                      const uint64_t* zmask, const int32_t* ny, const double* angle, int64_t* accesses,
+                                      int64_t* conflicting, int64_t* unavoidable) {
+    if (n_qubits < 1 || n_qubits > 30) return fail(VQE_ERR_INVALID, "bad qubit count");
+    if (tile_bits < 6 || tile_bits > 13) tile_bits = 13;
+    tile_bits = std::min(tile_bits, n_qubits);
+    if (low_bits < 0 || low_bits > tile_bits) low_bits = 4;
+    if (n_rot < 0 || !accesses || !conflicting || !unavoidable || (n_rot > 0 && (!xmask || !zmask || !ny || !angle)))
+        return fail(VQE_ERR_INVALID, "null array");
+    std::vector<HostOp> ops;
+    for (int k = 0; k < n_rot; ++k) {
+        if (angle[k] == 0.0) continue;
+        HostOp h = HostOp();
+        h.kind = OP_ROT;
+        h.x = xmask[k];
+        h.z = zmask[k];
+        h.ny = ny[k];
+        h.c = cos(angle[k]);
+        h.s = sin(angle[k]);
+        h.ang = angle[k];
+        ops.push_back(h);
+    }
+    OpPlan plan;
+    int rc = plan_ops(n_qubits, n_qubits, tile_bits, low_bits, tile_bits > 12 ? 1024 : 512, ops, plan);
+    if (rc) return rc;
+    rc = build_coltab(plan, false);
+    if (rc) return rc;
+    *accesses = *conflicting = *unavoidable = 0;
+    for (size_t p = 0; p < plan.passes.size(); ++p) {
+        const OpPass& ps = plan.passes[p];
+        const size_t n_cols = ps.col_end - ps.col_begin;
+        const uint16_t* t16 = plan.coltab16.data() + plan.coltab16_off[p];
+        const uint16_t* seg0 = t16 + ((2 * n_cols + 7) & ~size_t(7));
+        for (size_t q = ps.col_begin; q < ps.col_end; ++q) {
+            const DevCol& co = plan.dcols[q];
+            // unavoidable: the images of the run's FREE tile positions under the swizzle do not span the four bank-pair bits
+            // (position 0 fixed, or both positions that feed one bank bit -- p and p + 3 for p = 1, 2, 3 -- fixed)
+            bool fixes0 = false;
+            {
+                uint32_t fixed = 0, basis[4] = {0, 0, 0, 0};
+                int rank = 0;
+                for (uint32_t d = 0; d < co.nd && d < 6; ++d) fixed |= 1u << __builtin_popcount(~co.dpos[d]);
+                for (uint32_t b2 = 0; b2 < (uint32_t)ps.tp.tbits; ++b2) {
+                    if ((fixed >> b2) & 1u) continue;
+                    uint32_t v = swz_idx8(1u << b2, plan.coltab_swz[p]) & 0xfu;
+                    for (int b3 = 3; b3 >= 0 && v; --b3)
+                        if (((v >> b3) & 1u) && basis[b3]) v ^= basis[b3];
+                    if (v) {
+                        basis[31 - __builtin_clz(v)] = v;
+                        ++rank;
+                    }
+                }
+                fixes0 = rank < 4;
+            }
+            uint32_t sg = reinterpret_cast<const uint32_t*>(t16)[q - ps.col_begin];
+            const uint32_t per_pat = std::max<uint32_t>(1u, (1u << co.free_log) / COLSEG);
+            for (uint32_t k = 0; k < co.n_active * per_pat; ++k, ++sg)
+                for (uint32_t hw = 0; hw < COLSEG / 16u; ++hw) {
+                    uint32_t seen = 0, lanes = 0;
+                    for (uint32_t ln = 0; ln < 16; ++ln) {
+                        const uint32_t sl = hw * 16u + ln;
+                        const uint32_t wl = seg0[(size_t)sg * COLFACT + (sl & 31u)], wg = seg0[(size_t)sg * COLFACT + 32u + (sl >> 5)];
+                        if (wl == 0xffffu || wg == 0xffffu) continue;
+                        seen |= 1u << ((((wl ^ wg) & 0xfff8u) >> 3) & 15u);
+                        ++lanes;
+                    }
+                    if (!lanes) continue;
+                    ++*accesses;
+                    if ((uint32_t)__builtin_popcount(seen) < lanes) {
+                        ++*conflicting;
+                        if (fixes0) ++*unavoidable;
+                    }
+                }
         }
     }
     return VQE_OK;

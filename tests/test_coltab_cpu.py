@@ -99,3 +99,31 @@ def test_item_table_refuses_programs_outside_the_real_collapsed_form():
     x2, z2, ny2 = term_masks("YYXX", [1, 4, 6, 9], n)
     with pytest.raises(_lib.VQEError):
         _coltab(n, [x, x2], [z, z2], [ny, ny2], [0.3, 0.2], np.ones(1 << n) / 2.0 ** 7)
+
+
+def _banks(n, xs, zs, nys, angs, tile_bits=13, low_bits=4):
+    from openvqe_b200 import _lib
+    lib = _lib.load()
+    x = np.ascontiguousarray(xs, dtype=np.uint64)
+    z = np.ascontiguousarray(zs, dtype=np.uint64)
+    ny = np.ascontiguousarray(nys, dtype=np.int32)
+    a = np.ascontiguousarray(angs, dtype=np.float64)
+    acc, con, una = C.c_int64(), C.c_int64(), C.c_int64()
+    p = lambda v: v.ctypes.data_as(C.c_void_p)
+    _lib.check(lib.vqe_debug_coltab_banks(n, tile_bits, low_bits, len(x), p(x), p(z), p(ny), p(a), C.byref(acc), C.byref(con),
+                                          C.byref(una)))
+    return acc.value, con.value, una.value
+
+
+def test_item_order_leaves_only_the_unavoidable_bank_conflicts(monkeypatch):
+    """A 64-bit shared-memory access is served per half-warp.  With the item order the tables are built with, the 16 elements of
+    a half-warp sit in 16 different 8-byte bank pairs for every run whose free tile positions can reach all bank pairs at all
+    (not when the X-mask fixes tile position 0, or both positions that feed one bank bit under the 128-byte swizzle); the plain
+    ascending enumeration also conflicts when the X-mask holds position 2 or 3."""
+    n = 16
+    xs, zs, nys, angs = _jw_program(n, 60, 9001)
+    acc, con, una = _banks(n, xs, zs, nys, angs)
+    assert acc > 1000 and con == una
+    monkeypatch.setenv("VQE_COL_LANE_ORDER", "0")
+    acc0, con0, una0 = _banks(n, xs, zs, nys, angs)
+    assert acc0 == acc and una0 == una and con0 > con
